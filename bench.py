@@ -1,0 +1,459 @@
+#!/usr/bin/env python
+"""bench.py — Mreads/s demultiplexed by the matcher core, on BASELINE.json's headline config.
+
+One "step" = one pass of the hot path (barcode bytes in -> result word per read + per-sample counts) over one batch
+of synthetic reads of the named config, per GPU.  Prints ONE JSON line on rank 0 (see the contract in the task).
+
+  value      whole-job Mreads/s with the packed batch already resident in HBM (CUDA events, max over ranks,
+             includes the final NCCL all-reduce of the per-sample count table when N > 1)
+  e2e        same metric through the reference-facing C-ABI call fqtk_b200_matcher_assign_batch with HOST (pinned)
+             buffers: ASCII barcode rows in, result words out, H2D/D2H inside the timed region
+  roofline   dominant kernel vs the measured HBM copy peak, on ALGORITHMIC bytes B(L) = 4*ceil(L/8) + 4 per read
+  cpu_baseline   the oracle (C restatement of the reference's matcher, memo cache on) timed on this box's host cores
+
+`--impl reference` times the reference's CPU implementation of the path (the oracle port; the reference is Rust and
+cannot be built in this image) on the same workload: each step is a bounded sample of the same read stream.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Mreads/sec demuxed (dual 8+8bp, 384 samples) at 1/2/4/8 B200 vs ref CPU"
+UNIT = "Mreads/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--config", type=int, default=3, help="BASELINE.json configs index + 1 (3 = the headline)")
+    ap.add_argument("--reads", type=int, default=0, help="override reads per GPU per step (default: the config's N)")
+    ap.add_argument("--e2e-reads", type=int, default=128 << 20, help="reads per GPU per e2e step (pinned host memory)")
+    ap.add_argument("--mode", choices=["auto", "table", "brute"], default="auto")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-brute", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target CPU seconds for the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def host_reads(panel, seed, first, n, threads=16):
+    """Host replay of the synthetic stream, sliced over a few threads (ctypes releases the GIL)."""
+    from fqtk_b200 import synth
+
+    L = panel.shape[1]
+    out = np.empty((n, L), dtype=np.uint8)
+    threads = max(1, min(threads, os.cpu_count() or 1, n // 100_000 + 1))
+    bounds = [n * t // threads for t in range(threads + 1)]
+
+    def work(t):
+        lo, hi = bounds[t], bounds[t + 1]
+        if hi > lo:
+            out[lo:hi] = synth.reads_host(panel, seed, first + lo, hi - lo)
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, range(threads)))
+    return out
+
+
+def time_oracle(cfg, panel, reads, threads):
+    """Mreads/s of the oracle on `reads` (1 thread = the reference's model; >1 = OpenMP upper bound)."""
+    import oracle
+
+    bcs = [bytes(r) for r in panel]
+    if threads == 1:
+        m = oracle.OracleMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, use_cache=True)
+        m.assign_batch(reads[: min(len(reads), 200_000)], want_results=False)  # touch code + warm the memo cache
+        t0 = time.perf_counter()
+        _, counts = m.assign_batch(reads, want_results=False)
+        dt = time.perf_counter() - t0
+        return len(reads) / dt / 1e6, 1, counts
+    t0 = time.perf_counter()
+    _, counts, used = oracle.assign_batch_mt(panel, cfg.max_mismatches, cfg.min_mismatch_delta, reads,
+                                             threads=threads, want_results=False)
+    dt = time.perf_counter() - t0
+    return len(reads) / dt / 1e6, used, counts
+
+
+def cpu_baseline(cfg, panel, seconds, all_cores=True):
+    import oracle
+
+    calib = host_reads(panel, cfg.seed_reads, 0, 1_000_000)
+    rate, _, _ = time_oracle(cfg, panel, calib, 1)
+    n = int(min(max(rate * 1e6 * seconds, 2_000_000), 96_000_000, cfg.n_reads))
+    reads = host_reads(panel, cfg.seed_reads, 0, n)
+    v1, _, counts1 = time_oracle(cfg, panel, reads, 1)
+    out = {
+        "value": round(v1, 3), "unit": UNIT, "cores": 1, "kind": "port",
+        "sample": f"first {n} reads of the same synthetic stream, held in host memory; oracle/fqtk_oracle.c literal "
+                  f"restatement, memo cache on, 1 thread = the reference's threading model for the matcher "
+                  f"(demux.rs:945-977 is serial)",
+    }
+    if all_cores:
+        cores = oracle.max_threads()
+        vN, used, countsN = time_oracle(cfg, panel, reads, cores)
+        assert np.array_equal(counts1, countsN)
+        out["all_cores_upper_bound"] = {
+            "value": round(vN, 3), "cores": used,
+            "note": "reads sharded over all host threads with a private matcher + cache each (OpenMP); the reference "
+                    "does NOT do this — upper bound only"}
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = f"/tmp/fqtk_b200_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(cfg_id, mode):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(f"cfg{cfg_id}_{mode}")
+        except Exception:
+            return None
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference arm: the reference's own CPU algorithm for the path (oracle port), bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from fqtk_b200 import synth
+
+    cfg = synth.CONFIGS[args.config]
+    panel = synth.panel(cfg)
+    total_steps = args.steps + args.warmup
+    calib = host_reads(panel, cfg.seed_reads, 0, 1_000_000)
+    rate, _, _ = time_oracle(cfg, panel, calib, 1)
+    per_step_s = min(10.0, max(0.5, 120.0 / max(1, total_steps)))
+    n = int(min(max(rate * 1e6 * per_step_s, 1_000_000), 96_000_000, cfg.n_reads))
+    reads = host_reads(panel, cfg.seed_reads, 0, n)
+    import oracle
+
+    bcs = [bytes(r) for r in panel]
+    m = oracle.OracleMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, use_cache=True)
+    for _ in range(args.warmup):
+        m.assign_batch(reads, want_results=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m.assign_batch(reads, want_results=True)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt / 1e6
+    cores_all = oracle.max_threads()
+    vN, used, _ = time_oracle(cfg, panel, reads, cores_all)
+    sample = (f"each step = the first {n} reads of the config's synthetic stream (of {cfg.n_reads}), in host memory; "
+              f"literal C restatement of BarcodeMatcher::assign with memo cache on, 1 thread (the reference's matcher "
+              f"is serial, demux.rs:945-977)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": config_dict(cfg, n, "reference-cpu"),
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "all_cores_upper_bound": {"value": round(vN, 3), "cores": used,
+                                                   "note": "OpenMP-sharded, one matcher + cache per thread; NOT what "
+                                                           "the reference does"}},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(cfg, n_reads, mode):
+    return {
+        "workload": cfg.name, "read_structures": cfg.read_structures, "n_samples": cfg.n_samples,
+        "barcode_len": cfg.barcode_len, "max_mismatches": cfg.max_mismatches,
+        "min_mismatch_delta": cfg.min_mismatch_delta, "reads_per_gpu_per_step": n_reads, "kernel_mode": mode,
+        "input": "4-bit packed barcode words (BitEnc layout), HBM-resident", "l2": "inputs larger than L2 (no flush)",
+    }
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from fqtk_b200 import BarcodeMatcher, _lib, synth
+    from fqtk_b200.barcode_matching import kernel_launches
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: fqtk_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = synth.CONFIGS[args.config]
+    n = args.reads or cfg.n_reads
+    W = cfg.words_per_read
+    panel = synth.panel(cfg)
+    bcs = [bytes(r) for r in panel]
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # each rank synthesises its own shard [rank*n, (rank+1)*n) of the stream straight into HBM (weak scaling)
+    d_packed = torch.empty((n, W), dtype=torch.int32, device=dev)
+    d_res = torch.empty(n, dtype=torch.int32, device=dev)
+    synth.reads_device(panel, cfg.seed_reads, rank * n, n, 0, d_packed.data_ptr(), stream)
+    matcher = BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, use_cache=(args.mode != "brute"),
+                             device=local)
+    if args.mode == "table" and matcher.mode != "table":
+        raise SystemExit("memo table could not be built for this config")
+    mode = matcher.mode
+    info = matcher.info()
+    counts_t = torch.zeros(cfg.n_samples + 1, dtype=torch.int64, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def one_pass():
+        matcher.assign_packed_device(d_packed.data_ptr(), n, d_res.data_ptr(), stream)
+
+    for _ in range(max(args.warmup, 0)):
+        one_pass()
+    barrier()
+    matcher.reset_counts()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.15)
+    launches0 = kernel_launches()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 2)]
+    barrier()
+    evs[0].record()
+    for k in range(args.steps):
+        one_pass()
+        evs[k + 1].record()
+    if world > 1:
+        # the single collective of the path: the final per-sample count table (S+1 u64) summed over NVLink
+        # (int64 view of the matcher's own device counters; cudaMemcpyAsync-free: same stream ordering)
+        counts_t.copy_(_tensor_from_ptr(torch, matcher.counts_device_ptr(), cfg.n_samples + 1, dev))
+        dist.all_reduce(counts_t, op=dist.ReduceOp.SUM)
+    evs[args.steps + 1].record()
+    barrier()
+    launches = kernel_launches() - launches0
+    if sampler:
+        time.sleep(0.15)
+        clocks = sampler.stop()
+    total_ms = evs[0].elapsed_time(evs[args.steps + 1])
+    kernel_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    if world == 1:
+        counts_t.copy_(_tensor_from_ptr(torch, matcher.counts_device_ptr(), cfg.n_samples + 1, dev))
+    counts = counts_t.cpu().numpy()
+    assert int(counts.sum()) == n * args.steps * world, "per-sample counts must add up to every read processed"
+    value = n * args.steps * world / (total_ms * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (this rank's launches; algorithmic bytes only) ----
+    peak, peak_src = measured_peak()
+    k_ms = statistics.mean(kernel_ms)
+    bytes_per_launch = n * cfg.algorithmic_bytes_per_read
+    achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+        "traffic": ncu_traffic(args.config, mode), "kernel": "k_probe" if mode == "table" else "k_brute",
+        "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_read": cfg.algorithmic_bytes_per_read,
+        "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
+        "pair_compares_per_s": round(n * cfg.n_samples / (k_ms * 1e-3), 1) if mode == "brute" else None,
+    }
+
+    # ---- brute-force kernel family on the same batch, for the record ----
+    brute = None
+    if mode == "table" and not args.no_brute:
+        matcher.set_mode("brute")
+        nb = min(n, 64 << 20)
+        matcher.assign_packed_device(d_packed.data_ptr(), nb, d_res.data_ptr(), stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reps = 3
+        for _ in range(reps):
+            matcher.assign_packed_device(d_packed.data_ptr(), nb, d_res.data_ptr(), stream)
+        e1.record()
+        torch.cuda.synchronize()
+        bms = e0.elapsed_time(e1) / reps
+        brute = {"kernel": "k_brute", "reads": nb, "ms": round(bms, 4), "value": round(nb / (bms * 1e-3) / 1e6, 2),
+                 "unit": UNIT + " per GPU", "pair_compares_per_s": round(nb * cfg.n_samples / (bms * 1e-3), 1),
+                 "roofline_frac": round(nb * cfg.algorithmic_bytes_per_read / (bms * 1e-3) / 1e9 / peak, 5)}
+        matcher.set_mode("table")
+        matcher.reset_counts()
+
+    # ---- e2e: the reference-facing C-ABI call on HOST buffers (pinned), H2D + kernel + D2H every step ----
+    e2e = None
+    if not args.no_e2e:
+        import ctypes as C
+        import psutil
+
+        L = cfg.barcode_len
+        ne = min(args.e2e_reads, n)
+        avail = psutil.virtual_memory().available
+        while ne * (L + 4) * max(1, min(world, 8)) > 0.25 * avail and ne > (1 << 20):
+            ne //= 2
+        d_ascii = torch.empty((ne, L), dtype=torch.uint8, device=dev)
+        synth.reads_device(panel, cfg.seed_reads, rank * n, ne, d_ascii.data_ptr(), 0, stream)
+        h_in, h_out = C.c_void_p(), C.c_void_p()
+        _lib.check(_lib.lib().fqtk_b200_host_alloc(C.byref(h_in), ne * L))
+        _lib.check(_lib.lib().fqtk_b200_host_alloc(C.byref(h_out), ne * 4))
+        h_in_np = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_uint8)), shape=(ne, L))
+        h_out_np = np.ctypeslib.as_array(C.cast(h_out, C.POINTER(C.c_uint32)), shape=(ne,))
+        h_in_np[:] = d_ascii.cpu().numpy()
+        del d_ascii
+        matcher.reset_counts()
+        for _ in range(2):
+            matcher.assign_batch_ptr(h_in.value, ne, L, h_out.value)
+        matcher.reset_counts()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            matcher.assign_batch_ptr(h_in.value, ne, L, h_out.value)  # synchronous: returns with results on the host
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        # the host results must be the device path's results for the same reads
+        matcher.reset_counts()
+        matcher.assign_packed_device(d_packed.data_ptr(), min(ne, 1 << 20), d_res.data_ptr(), stream)
+        torch.cuda.synchronize()
+        chk = min(ne, 1 << 20)
+        assert np.array_equal(d_res[:chk].cpu().numpy().view(np.uint32), h_out_np[:chk]), "e2e results differ"
+        e2e = {"value": round(ne * args.steps * world / dt / 1e6, 2), "unit": UNIT,
+               "h2d_bytes_per_step": ne * L * world, "d2h_bytes_per_step": ne * 4 * world,
+               "reads_per_gpu_per_step": ne, "ms_per_step": round(dt / args.steps * 1e3, 3),
+               "api": "fqtk_b200_matcher_assign_batch (ASCII rows in pinned host memory -> result words in pinned "
+                      "host memory; chunked H2D / kernel / D2H overlap inside the call)"}
+        _lib.lib().fqtk_b200_host_free(h_in)
+        _lib.lib().fqtk_b200_host_free(h_out)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(cfg, panel, args.cpu_seconds)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": config_dict(cfg, n, mode),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
+            "memo_table": {"entries": int(info.table_entries), "slots": int(info.table_slots),
+                           "bytes": int(info.table_bytes), "candidates": int(info.table_candidates)},
+            "brute_force": brute,
+            "matched_fraction": round(1.0 - float(counts[-1]) / float(counts.sum()), 5),
+        }
+        print(json.dumps(line), flush=True)
+    matcher.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _tensor_from_ptr(torch, ptr, n, dev):
+    """int64 torch view of a raw device pointer owned by the matcher (its u64 count table)."""
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(h, device=dev)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

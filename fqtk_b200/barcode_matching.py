@@ -1,0 +1,194 @@
+"""Host-side mirror of the reference's matcher interface (src/lib/barcode_matching.rs:15-186) over the C ABI.
+
+Same names, argument meaning and error behaviour as the reference so the parity tests read like its own tests:
+
+    BarcodeMatcher(samples, max_mismatches, min_mismatch_delta, use_cache)   # ::new, :55-86
+    matcher.assign(read_bases) -> Optional[BarcodeMatch]                     # ::assign, :165-186
+    BarcodeMatch(best_match, best_mismatches, next_best_mismatches)          # :16-25
+
+plus the batched forms the GPU needs (`assign_batch` on host arrays, `assign_packed_device` /
+`assign_ascii_device` on raw device pointers) and the caller's per-sample counts (demux.rs:970-974).
+Every call goes to the CUDA library; there is no Python or CPU matching path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .samples import barcodes_of
+
+
+class MatcherPanic(Exception):
+    """Stands in for a Rust panic on the reference path; `.args[0]` is the reference's panic text."""
+
+
+@dataclass(frozen=True)
+class BarcodeMatch:
+    """barcode_matching.rs:16-25"""
+    best_match: int
+    best_mismatches: int
+    next_best_mismatches: int
+
+
+def unpack(word: int) -> Optional[BarcodeMatch]:
+    word = int(word)
+    if word == _lib.NONE:
+        return None
+    return BarcodeMatch(word >> 16, (word >> 8) & 0xFF, word & 0xFF)
+
+
+def _raise(rc: int) -> None:
+    msg = _lib.last_error()
+    if rc in (_lib.ERR_EMPTY_PANEL, _lib.ERR_EMPTY_BARCODE, _lib.ERR_LENGTH):
+        raise MatcherPanic(msg)
+    raise _lib.Fqtk_b200Error(rc, msg)
+
+
+class BarcodeMatcher:
+    """BarcodeMatcher (barcode_matching.rs:29-186).  `samples`: Sample objects, str or bytes barcodes, in sheet order."""
+
+    def __init__(self, samples: Sequence, max_mismatches: int, min_mismatch_delta: int, use_cache: bool = True,
+                 device: int = 0):
+        if not (0 <= max_mismatches <= 255 and 0 <= min_mismatch_delta <= 255):
+            raise OverflowError("max_mismatches / min_mismatch_delta must fit in u8 (demux.rs:923-924)")
+        bcs = barcodes_of(samples)
+        if len(bcs) == 0:
+            raise MatcherPanic("Must provide at least one sample")
+        if any(len(b) == 0 for b in bcs):
+            raise MatcherPanic("Sample barcode cannot be empty string")
+        L = len(bcs[0])
+        if any(len(b) != L for b in bcs):
+            # the reference only notices at match time (count_mismatches panics, :95-106); a dense panel cannot hold it
+            raise MatcherPanic("All barcodes must have the same length")
+        self.n_samples = len(bcs)
+        self.barcode_len = L
+        self.max_mismatches = max_mismatches
+        self.min_mismatch_delta = min_mismatch_delta
+        self.use_cache = bool(use_cache)
+        panel = np.frombuffer(b"".join(bcs), dtype=np.uint8)
+        self._h = C.c_void_p()
+        rc = _lib.lib().fqtk_b200_matcher_create(panel.ctypes.data, self.n_samples, L, max_mismatches,
+                                                 min_mismatch_delta, int(self.use_cache), device, C.byref(self._h))
+        if rc != _lib.OK:
+            self._h = None
+            _raise(rc)
+
+    # -- lifecycle ----------------------------------------------------------------------------------
+    def close(self) -> None:
+        h = getattr(self, "_h", None)
+        if h:
+            _lib.lib().fqtk_b200_matcher_destroy(h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- introspection ------------------------------------------------------------------------------
+    def info(self) -> _lib.MatcherInfo:
+        info = _lib.MatcherInfo()
+        _lib.check(_lib.lib().fqtk_b200_matcher_get_info(self._h, C.byref(info)))
+        return info
+
+    @property
+    def mode(self) -> str:
+        return {_lib.MODE_BRUTE: "brute", _lib.MODE_TABLE: "table"}[self.info().mode]
+
+    def set_mode(self, mode: str) -> None:
+        _lib.check(_lib.lib().fqtk_b200_matcher_set_mode(self._h, {"brute": _lib.MODE_BRUTE, "table": _lib.MODE_TABLE}[mode]))
+
+    @property
+    def words_per_read(self) -> int:
+        return (self.barcode_len + 7) // 8
+
+    # -- the reference's call ------------------------------------------------------------------------
+    def assign_word(self, read_bases: bytes) -> int:
+        out = C.c_uint32()
+        rb = bytes(read_bases)
+        rc = _lib.lib().fqtk_b200_matcher_assign(self._h, rb, len(rb), C.byref(out))
+        if rc != _lib.OK:
+            _raise(rc)
+        return int(out.value)
+
+    def assign(self, read_bases: bytes) -> Optional[BarcodeMatch]:
+        """BarcodeMatcher::assign, barcode_matching.rs:165-186."""
+        return unpack(self.assign_word(read_bases))
+
+    # -- batched forms ----------------------------------------------------------------------------------
+    def assign_batch(self, reads: np.ndarray, lengths: Optional[np.ndarray] = None,
+                     out: Optional[np.ndarray] = None) -> np.ndarray:
+        """reads: (N, stride) uint8 host array, row i = one read's concatenated sample-barcode bases
+        (demux.rs:121-123).  Returns uint32[N] result words."""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        assert reads.ndim == 2
+        n, stride = reads.shape
+        if out is None:
+            out = np.empty(n, dtype=np.uint32)
+        assert out.dtype == np.uint32 and out.shape == (n,) and out.flags.c_contiguous
+        lp = None
+        if lengths is not None:
+            lengths = np.ascontiguousarray(lengths, dtype=np.uint32)
+            assert lengths.shape == (n,)
+            lp = lengths.ctypes.data
+        rc = _lib.lib().fqtk_b200_matcher_assign_batch(self._h, reads.ctypes.data, n, stride, lp, out.ctypes.data)
+        if rc != _lib.OK:
+            _raise(rc)
+        return out
+
+    def assign_batch_ptr(self, rows_ptr: int, n: int, stride: int, results_ptr: int, lengths_ptr: int = 0) -> None:
+        """Same call on raw host pointers (e.g. pinned buffers from fqtk_b200_host_alloc / torch pin_memory)."""
+        rc = _lib.lib().fqtk_b200_matcher_assign_batch(self._h, rows_ptr, n, stride, lengths_ptr or None, results_ptr)
+        if rc != _lib.OK:
+            _raise(rc)
+
+    def assign_packed_device(self, d_packed: int, n: int, d_results: int, stream: int = 0) -> None:
+        """HBM-resident batch: raw device pointers (packed BitEnc words in, result words out), async on `stream`."""
+        rc = _lib.lib().fqtk_b200_matcher_assign_packed_device(self._h, d_packed, n, d_results, stream or None)
+        if rc != _lib.OK:
+            _raise(rc)
+
+    def assign_ascii_device(self, d_ascii: int, n: int, stride: int, d_results: int, d_lengths: int = 0,
+                            stream: int = 0) -> None:
+        rc = _lib.lib().fqtk_b200_matcher_assign_ascii_device(self._h, d_ascii, n, stride, d_lengths or None,
+                                                              d_results, stream or None)
+        if rc != _lib.OK:
+            _raise(rc)
+
+    # -- the caller's counters (demux.rs:970-974) ------------------------------------------------------
+    def counts(self) -> np.ndarray:
+        """uint64[S + 1]; last element = unmatched."""
+        out = np.zeros(self.n_samples + 1, dtype=np.uint64)
+        _lib.check(_lib.lib().fqtk_b200_matcher_counts(self._h, out.ctypes.data))
+        return out
+
+    def counts_device_ptr(self) -> int:
+        p = C.c_void_p()
+        _lib.check(_lib.lib().fqtk_b200_matcher_counts_device(self._h, C.byref(p)))
+        return int(p.value)
+
+    def reset_counts(self) -> None:
+        _lib.check(_lib.lib().fqtk_b200_matcher_reset_counts(self._h))
+
+
+def encode(bases: bytes) -> list[int]:
+    """encode(), src/lib/mod.rs:49-61 -> u32 blocks of the width-4 BitEnc layout."""
+    rb = bytes(bases)
+    out = (C.c_uint32 * max(1, (len(rb) + 7) // 8))()
+    _lib.check(_lib.lib().fqtk_b200_encode_host(rb, len(rb), out))
+    return [int(out[i]) for i in range((len(rb) + 7) // 8)]
+
+
+def kernel_launches() -> int:
+    return int(_lib.lib().fqtk_b200_kernel_launches())

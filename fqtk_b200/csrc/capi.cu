@@ -1,0 +1,605 @@
+// capi.cu — the extern "C" boundary (include/fqtk_b200.h) over the sm_100a kernels.
+//
+// Host-side responsibilities that mirror the reference (fulcrumgenomics/fqtk @ 45dbb99):
+//   * BarcodeMatcher::new        src/lib/barcode_matching.rs:55-86   -> fqtk_b200_matcher_create (panel upper-casing,
+//                                                                       max_ns_in_barcodes, encoding, memo table)
+//   * BarcodeMatcher::assign     src/lib/barcode_matching.rs:165-186 -> length rules + no-call pre-filter for rows
+//                                                                       whose length differs from L
+//   * demux.rs:968-975           -> counts[S+1]
+// No CPU matching path exists here: distances, decisions and the memo-table contents all come from the kernels.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/fqtk_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fq {
+cudaError_t synth_reads_device(const uint8_t* d_panel, uint32_t S, uint32_t L, uint64_t seed, uint64_t first,
+                               uint64_t n, uint8_t* d_ascii, uint32_t* d_packed, int sm_count, cudaStream_t stream);
+void synth_reads_host(const uint8_t* panel, uint32_t S, uint32_t L, uint64_t seed, uint64_t first, uint64_t n,
+                      uint8_t* out);
+int synth_panel_host(uint64_t seed, uint32_t S, uint32_t L, uint32_t min_distance, uint32_t n_degenerate,
+                     uint8_t* out);
+}  // namespace fq
+
+namespace {
+
+thread_local std::string g_err;
+uint64_t g_table_budget = 32ull << 20;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(FQTK_B200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                         \
+    do {                                                 \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+constexpr int N_PIPE = 3;                       // chunks in flight for the host-buffer call
+constexpr uint64_t CHUNK_BYTES = 32ull << 20;   // ASCII bytes per chunk
+
+}  // namespace
+
+struct fqtk_b200_matcher {
+    int device = 0;
+    fq::LaunchGeometry geo{};
+    uint32_t S = 0, L = 0, W = 0, P = 0;
+    uint8_t max_mm = 0, min_delta = 0;
+    uint32_t max_ns = 0;
+    std::vector<uint8_t> panel;  // upper-cased ASCII, S x L
+    uint4* d_planes = nullptr;
+    uint32_t* d_not_exp = nullptr;
+    uint32_t* d_table = nullptr;
+    unsigned long long* d_counts = nullptr;
+    fq::MatchParams params{};
+    int mode = FQTK_B200_MODE_BRUTE;
+    uint64_t table_entries = 0, table_slots = 0, table_bytes = 0, table_candidates = 0;
+    // host-buffer pipeline
+    cudaStream_t streams[N_PIPE] = {};
+    uint8_t* d_in[N_PIPE] = {};
+    uint32_t* d_out[N_PIPE] = {};
+    uint32_t* d_len[N_PIPE] = {};
+    size_t in_cap = 0, out_cap = 0;  // bytes / reads per pipeline slot
+    uint32_t* d_scratch = nullptr;   // packed scratch for the L > 32 ASCII route
+    size_t scratch_words = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------
+// memo-table construction: enumerate every A/C/G/T/N string within max_mm mismatches of some barcode, let the
+// brute-force KERNEL compute each one's result, keep the Some(..) ones in an open-addressing table.
+// ------------------------------------------------------------------------------------------------------
+const uint32_t ALPHABET[5] = {1u, 2u, 4u, 8u, 15u};
+
+// number of neighbourhood strings (with duplicates across barcodes), saturating at limit + 1
+uint64_t neighbourhood_size(const std::vector<uint8_t>& masks, uint32_t S, uint32_t L, uint32_t mm, uint64_t limit) {
+    const uint32_t K = std::min(mm, L);
+    long double total = 0;
+    std::vector<long double> ways(K + 1), nxt(K + 1);
+    for (uint32_t j = 0; j < S; j++) {
+        std::fill(ways.begin(), ways.end(), 0.0L);
+        ways[0] = 1;
+        for (uint32_t i = 0; i < L; i++) {
+            const uint32_t e = masks[(size_t)j * L + i];
+            uint32_t n_match = 0;
+            for (uint32_t o : ALPHABET) n_match += (o & ~e & 0xFu) == 0u;
+            const uint32_t n_mis = 5u - n_match;
+            for (uint32_t k = 0; k <= K; k++) nxt[k] = ways[k] * n_match + (k ? ways[k - 1] * n_mis : 0.0L);
+            ways.swap(nxt);
+        }
+        for (uint32_t k = 0; k <= K; k++) total += ways[k];
+        if (total > (long double)limit) return limit + 1;
+    }
+    return (uint64_t)total;
+}
+
+struct Enumerator {
+    const uint8_t* e;  // L masks of one barcode
+    uint32_t L, W, K;
+    std::vector<uint32_t>* out;
+    uint32_t cur[fq::MAX_FAST_WORDS];
+    void rec(uint32_t i, uint32_t used) {
+        if (i == L) {
+            out->insert(out->end(), cur, cur + W);
+            return;
+        }
+        const uint32_t word = i >> 3, sh = 4u * (i & 7u);
+        for (uint32_t o : ALPHABET) {
+            const bool mis = (o & ~(uint32_t)e[i] & 0xFu) != 0u;
+            if (mis && used == K) continue;
+            cur[word] = (cur[word] & ~(0xFu << sh)) | (o << sh);
+            rec(i + 1, used + (mis ? 1u : 0u));
+        }
+        cur[word] &= ~(0xFu << sh);
+    }
+};
+
+template <int W>
+void host_insert(std::vector<uint32_t>& table, uint32_t slot_mask, const uint32_t* key, uint32_t val,
+                 uint64_t& inserted) {
+    const int EW = fq::table_entry_words(W), VI = fq::table_value_index(W);
+    uint32_t kw[W];
+    for (int k = 0; k < W; k++) kw[k] = key[k];
+    uint32_t slot = fq::hash_key<W>(kw) & slot_mask;
+    for (;;) {
+        uint32_t* ent = table.data() + (size_t)slot * EW;
+        if (ent[VI] == fq::NONE) {
+            for (int k = 0; k < W; k++) ent[k] = kw[k];
+            ent[VI] = val;
+            inserted++;
+            return;
+        }
+        bool same = true;
+        for (int k = 0; k < W; k++) same = same && ent[k] == kw[k];
+        if (same) return;  // the same string reached from two barcodes: identical value by construction
+        slot = (slot + 1u) & slot_mask;
+    }
+}
+
+int build_table(fqtk_b200_matcher* m) {
+    const uint32_t S = m->S, L = m->L, W = m->W;
+    std::vector<uint8_t> masks((size_t)S * L);
+    for (size_t t = 0; t < masks.size(); t++) masks[t] = (uint8_t)fq::encode_byte(m->panel[t]);
+    const uint64_t cand = neighbourhood_size(masks, S, L, m->max_mm, g_table_budget);
+    if (cand > g_table_budget || cand >= (1ull << 31)) return 1;  // over budget: stay in brute mode
+
+    std::vector<uint32_t> keys;
+    keys.reserve((size_t)cand * W);
+    Enumerator en{nullptr, L, W, std::min<uint32_t>(m->max_mm, L), &keys, {0, 0, 0, 0}};
+    for (uint32_t j = 0; j < S; j++) {
+        en.e = masks.data() + (size_t)j * L;
+        std::memset(en.cur, 0, sizeof en.cur);
+        en.rec(0, 0);
+    }
+    const uint64_t n = keys.size() / W;
+    m->table_candidates = n;
+
+    // evaluate every candidate with the brute-force kernel
+    uint32_t *d_keys = nullptr, *d_res = nullptr;
+    CU(cudaMalloc(&d_keys, std::max<size_t>(16, keys.size() * 4)));
+    CU(cudaMalloc(&d_res, std::max<size_t>(16, n * 4)));
+    CU(cudaMemcpy(d_keys, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice));
+    fq::ReadSource src{d_keys, nullptr, nullptr, 0, n};
+    CU(fq::launch_brute(m->params, src, d_res, m->geo, m->streams[0]));
+    std::vector<uint32_t> res(n);
+    CU(cudaMemcpyAsync(res.data(), d_res, n * 4, cudaMemcpyDeviceToHost, m->streams[0]));
+    CU(cudaStreamSynchronize(m->streams[0]));
+    cudaFree(d_keys);
+    cudaFree(d_res);
+    CU(cudaMemsetAsync(m->d_counts, 0, (size_t)(S + 1) * 8, m->streams[0]));  // the build pass is not a batch
+
+    uint64_t n_some = 0;
+    for (uint64_t t = 0; t < n; t++) n_some += res[t] != fq::NONE;
+    uint64_t slots = 1024;
+    while (slots < 2 * n_some) slots <<= 1;  // load factor <= 0.5
+    const int EW = fq::table_entry_words((int)W);
+    std::vector<uint32_t> table((size_t)slots * EW, 0xFFFFFFFFu);
+    uint64_t inserted = 0;
+    const uint32_t mask = (uint32_t)(slots - 1);
+    for (uint64_t t = 0; t < n; t++) {
+        if (res[t] == fq::NONE) continue;
+        const uint32_t* key = keys.data() + t * W;
+        switch (W) {
+            case 1: host_insert<1>(table, mask, key, res[t], inserted); break;
+            case 2: host_insert<2>(table, mask, key, res[t], inserted); break;
+            case 3: host_insert<3>(table, mask, key, res[t], inserted); break;
+            default: host_insert<4>(table, mask, key, res[t], inserted); break;
+        }
+    }
+    CU(cudaMalloc(&m->d_table, table.size() * 4));
+    CU(cudaMemcpy(m->d_table, table.data(), table.size() * 4, cudaMemcpyHostToDevice));
+    m->table_entries = inserted;
+    m->table_slots = slots;
+    m->table_bytes = table.size() * 4;
+    m->params.table = m->d_table;
+    m->params.slot_mask = mask;
+    return 0;
+}
+
+int ensure_pipeline(fqtk_b200_matcher* m, size_t in_bytes, size_t out_reads, bool want_len) {
+    if (in_bytes > m->in_cap) {
+        for (int s = 0; s < N_PIPE; s++) {
+            if (m->d_in[s]) cudaFree(m->d_in[s]);
+            m->d_in[s] = nullptr;
+            CU(cudaMalloc(&m->d_in[s], in_bytes));
+        }
+        m->in_cap = in_bytes;
+    }
+    if (out_reads > m->out_cap) {
+        for (int s = 0; s < N_PIPE; s++) {
+            if (m->d_out[s]) cudaFree(m->d_out[s]);
+            if (m->d_len[s]) cudaFree(m->d_len[s]);
+            m->d_out[s] = m->d_len[s] = nullptr;
+            CU(cudaMalloc(&m->d_out[s], out_reads * 4));
+        }
+        m->out_cap = out_reads;
+    }
+    if (want_len) {
+        for (int s = 0; s < N_PIPE; s++)
+            if (!m->d_len[s]) CU(cudaMalloc(&m->d_len[s], m->out_cap * 4));
+    }
+    return FQTK_B200_OK;
+}
+
+int run_device(fqtk_b200_matcher* m, const fq::ReadSource& src, uint32_t* d_results, cudaStream_t st) {
+    if (src.n >= (1ull << 32)) return fail(FQTK_B200_ERR_ARG, "n_reads must be < 2^32 per device call");
+    fq::ReadSource s = src;
+    if (m->W > (uint32_t)fq::MAX_FAST_WORDS && s.ascii) {  // L > 32: pack first, then the long-barcode kernel
+        const size_t need = (size_t)s.n * m->W;
+        if (need > m->scratch_words) {
+            if (m->d_scratch) cudaFree(m->d_scratch);
+            m->d_scratch = nullptr;
+            CU(cudaMalloc(&m->d_scratch, need * 4));
+            m->scratch_words = need;
+        }
+        if (s.lengths) return fail(FQTK_B200_ERR_UNSUPPORTED, "per-row lengths with barcodes longer than 32 bases");
+        CU(fq::launch_pack(s.ascii, s.n, m->L, s.stride, m->d_scratch, m->geo, st));
+        s.ascii = nullptr;
+        s.packed = m->d_scratch;
+    }
+    if (m->mode == FQTK_B200_MODE_TABLE)
+        CU(fq::launch_probe(m->params, s, d_results, m->geo, st));
+    else
+        CU(fq::launch_brute(m->params, s, d_results, m->geo, st));
+    return FQTK_B200_OK;
+}
+
+}  // namespace
+
+// ======================================================================================================
+extern "C" {
+
+const char* fqtk_b200_last_error(void) { return g_err.c_str(); }
+
+int fqtk_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+void fqtk_b200_set_table_budget(uint64_t max_candidates) { g_table_budget = max_candidates; }
+
+uint64_t fqtk_b200_kernel_launches(void) { return fq::kernel_launches(); }
+
+int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t S, uint32_t L, uint8_t max_mm, uint8_t min_delta,
+                             int use_cache, int device, fqtk_b200_matcher** out) {
+    if (!out) return fail(FQTK_B200_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (S == 0) return fail(FQTK_B200_ERR_EMPTY_PANEL, "Must provide at least one sample");
+    if (L == 0) return fail(FQTK_B200_ERR_EMPTY_BARCODE, "Sample barcode cannot be empty string");
+    if (!panel_ascii) return fail(FQTK_B200_ERR_ARG, "panel_ascii is NULL");
+    if (S > FQTK_B200_MAX_SAMPLES) return fail(FQTK_B200_ERR_UNSUPPORTED, "more than 65535 samples");
+    if (L > FQTK_B200_MAX_BARCODE_LEN) return fail(FQTK_B200_ERR_UNSUPPORTED, "barcodes longer than 254 bases");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(FQTK_B200_ERR_CUDA, "no CUDA device: fqtk_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(FQTK_B200_ERR_ARG, "bad device ordinal");
+    CU(cudaSetDevice(device));
+
+    fqtk_b200_matcher* m = new (std::nothrow) fqtk_b200_matcher();
+    if (!m) return fail(FQTK_B200_ERR_ARG, "out of host memory");
+    m->device = device;
+    m->S = S;
+    m->L = L;
+    m->W = fq::words_for_len(L);
+    m->P = fq::planes_for_len(L);
+    m->max_mm = max_mm;
+    m->min_delta = min_delta;
+    cudaDeviceProp prop{};
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete m;
+        return cuda_fail(e, "cudaGetDeviceProperties");
+    }
+    m->geo.sm_count = prop.multiProcessorCount;
+    m->geo.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+
+    // barcode_matching.rs:67-76: upper-case, count no-calls, encode
+    m->panel.resize((size_t)S * L);
+    for (uint32_t j = 0; j < S; j++) {
+        uint32_t ns = 0;
+        for (uint32_t i = 0; i < L; i++) {
+            uint8_t b = panel_ascii[(size_t)j * L + i];
+            if (b >= 'a' && b <= 'z') b = (uint8_t)(b - 32);
+            m->panel[(size_t)j * L + i] = b;
+            ns += fq::byte_is_nocall(b);
+        }
+        m->max_ns = std::max(m->max_ns, ns);
+    }
+    const uint32_t W = m->W, P = m->P;
+    std::vector<uint4> planes((size_t)S * P, make_uint4(0, 0, 0, 0));
+    std::vector<uint32_t> not_exp((size_t)S * W, 0u);
+    for (uint32_t j = 0; j < S; j++) {
+        for (uint32_t i = 0; i < L; i++) {
+            const uint32_t emask = fq::encode_byte(m->panel[(size_t)j * L + i]);
+            const uint32_t forbid = ~emask & 0xFu;
+            not_exp[(size_t)j * W + (i >> 3)] |= forbid << (4u * (i & 7u));
+            uint4& q = planes[(size_t)j * P + (i >> 5)];
+            const uint32_t bit = 1u << (i & 31u);
+            if (forbid & 1u) q.x |= bit;
+            if (forbid & 2u) q.y |= bit;
+            if (forbid & 4u) q.z |= bit;
+            if (forbid & 8u) q.w |= bit;
+        }
+    }
+    int rc = FQTK_B200_OK;
+    auto bail = [&](int code) {
+        fqtk_b200_matcher_destroy(m);
+        return code;
+    };
+#define CUB(call)                                      \
+    do {                                               \
+        cudaError_t e__ = (call);                      \
+        if (e__ != cudaSuccess) return bail(cuda_fail(e__, #call)); \
+    } while (0)
+    CUB(cudaMalloc(&m->d_planes, planes.size() * sizeof(uint4)));
+    CUB(cudaMemcpy(m->d_planes, planes.data(), planes.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    CUB(cudaMalloc(&m->d_not_exp, not_exp.size() * 4));
+    CUB(cudaMemcpy(m->d_not_exp, not_exp.data(), not_exp.size() * 4, cudaMemcpyHostToDevice));
+    CUB(cudaMalloc(&m->d_counts, (size_t)(S + 1) * 8));
+    CUB(cudaMemset(m->d_counts, 0, (size_t)(S + 1) * 8));
+    for (int s = 0; s < N_PIPE; s++) CUB(cudaStreamCreateWithFlags(&m->streams[s], cudaStreamNonBlocking));
+#undef CUB
+    m->params.planes = m->d_planes;
+    m->params.not_exp = m->d_not_exp;
+    m->params.table = nullptr;
+    m->params.counts = m->d_counts;
+    m->params.S = S;
+    m->params.L = L;
+    m->params.W = W;
+    m->params.P = P;
+    m->params.max_mm = max_mm;
+    m->params.min_delta = min_delta;
+    m->params.last_pad = fq::last_word_pad_for_len(L);
+    m->params.slot_mask = 0;
+    m->mode = FQTK_B200_MODE_BRUTE;
+    if (use_cache && W <= (uint32_t)fq::MAX_FAST_WORDS) {
+        rc = build_table(m);
+        if (rc < 0) return bail(rc);
+        if (rc == 0) m->mode = FQTK_B200_MODE_TABLE;
+    }
+    cudaError_t es = cudaDeviceSynchronize();
+    if (es != cudaSuccess) return bail(cuda_fail(es, "create sync"));
+    *out = m;
+    return FQTK_B200_OK;
+}
+
+void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    for (int s = 0; s < N_PIPE; s++) {
+        if (m->d_in[s]) cudaFree(m->d_in[s]);
+        if (m->d_out[s]) cudaFree(m->d_out[s]);
+        if (m->d_len[s]) cudaFree(m->d_len[s]);
+        if (m->streams[s]) cudaStreamDestroy(m->streams[s]);
+    }
+    if (m->d_scratch) cudaFree(m->d_scratch);
+    if (m->d_planes) cudaFree(m->d_planes);
+    if (m->d_not_exp) cudaFree(m->d_not_exp);
+    if (m->d_table) cudaFree(m->d_table);
+    if (m->d_counts) cudaFree(m->d_counts);
+    delete m;
+}
+
+int fqtk_b200_matcher_get_info(const fqtk_b200_matcher* m, fqtk_b200_matcher_info* info) {
+    if (!m || !info) return fail(FQTK_B200_ERR_ARG, "NULL argument");
+    info->n_samples = m->S;
+    info->barcode_len = m->L;
+    info->words_per_read = m->W;
+    info->max_ns_in_barcodes = m->max_ns;
+    info->mode = (uint32_t)m->mode;
+    info->device = (uint32_t)m->device;
+    info->table_entries = m->table_entries;
+    info->table_slots = m->table_slots;
+    info->table_bytes = m->table_bytes;
+    info->table_candidates = m->table_candidates;
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_matcher_set_mode(fqtk_b200_matcher* m, int mode) {
+    if (!m) return fail(FQTK_B200_ERR_ARG, "NULL matcher");
+    if (mode == FQTK_B200_MODE_BRUTE) {
+        m->mode = mode;
+        return FQTK_B200_OK;
+    }
+    if (mode == FQTK_B200_MODE_TABLE) {
+        if (!m->d_table) return fail(FQTK_B200_ERR_ARG, "this matcher has no memo table");
+        m->mode = mode;
+        return FQTK_B200_OK;
+    }
+    return fail(FQTK_B200_ERR_ARG, "unknown mode");
+}
+
+int fqtk_b200_matcher_assign_packed_device(fqtk_b200_matcher* m, const uint32_t* d_packed, uint64_t n,
+                                           uint32_t* d_results, void* stream) {
+    if (!m || (n && (!d_packed || !d_results))) return fail(FQTK_B200_ERR_ARG, "NULL argument");
+    if ((reinterpret_cast<uintptr_t>(d_packed) & 15u) || (reinterpret_cast<uintptr_t>(d_results) & 3u))
+        return fail(FQTK_B200_ERR_ARG, "d_packed must be 16-byte aligned, d_results 4-byte aligned");
+    CU(cudaSetDevice(m->device));
+    fq::ReadSource src{d_packed, nullptr, nullptr, 0, n};
+    return run_device(m, src, d_results, (cudaStream_t)stream);
+}
+
+int fqtk_b200_matcher_assign_ascii_device(fqtk_b200_matcher* m, const uint8_t* d_ascii, uint64_t n, uint64_t stride,
+                                          const uint32_t* d_lengths, uint32_t* d_results, void* stream) {
+    if (!m || (n && (!d_ascii || !d_results))) return fail(FQTK_B200_ERR_ARG, "NULL argument");
+    if (stride < m->L && !d_lengths) return fail(FQTK_B200_ERR_ARG, "row_stride smaller than the barcode length");
+    CU(cudaSetDevice(m->device));
+    fq::ReadSource src{nullptr, d_ascii, d_lengths, stride, n};
+    return run_device(m, src, d_results, (cudaStream_t)stream);
+}
+
+int fqtk_b200_pack_device(const uint8_t* d_ascii, uint64_t n, uint32_t L, uint64_t stride, uint32_t* d_packed,
+                          void* stream) {
+    if (n && (!d_ascii || !d_packed)) return fail(FQTK_B200_ERR_ARG, "NULL argument");
+    if (L == 0 || L > FQTK_B200_MAX_BARCODE_LEN || stride < L) return fail(FQTK_B200_ERR_ARG, "bad length / stride");
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, dev));
+    fq::LaunchGeometry g{prop.multiProcessorCount, (int)prop.sharedMemPerBlockOptin};
+    CU(fq::launch_pack(d_ascii, n, L, stride, d_packed, g, (cudaStream_t)stream));
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_encode_host(const uint8_t* bases, size_t len, uint32_t* out_blocks) {
+    if ((len && !bases) || !out_blocks) return fail(FQTK_B200_ERR_ARG, "NULL argument");
+    const size_t W = (len + 7) / 8;
+    for (size_t w = 0; w < W; w++) out_blocks[w] = 0;
+    for (size_t i = 0; i < len; i++) out_blocks[i >> 3] |= fq::encode_byte(bases[i]) << (4u * (i & 7u));
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_matcher_assign_batch(fqtk_b200_matcher* m, const uint8_t* rows, uint64_t n, uint64_t stride,
+                                   const uint32_t* lengths, uint32_t* results) {
+    if (!m || (n && (!rows || !results))) return fail(FQTK_B200_ERR_ARG, "NULL argument");
+    if (n == 0) return FQTK_B200_OK;
+    const uint32_t L = m->L;
+    if (!lengths && stride < L) return fail(FQTK_B200_ERR_ARG, "row_stride smaller than the barcode length");
+    if (lengths) {
+        // barcode_matching.rs:165-172 for rows that would reach count_mismatches with the wrong length (:95-106)
+        for (uint64_t i = 0; i < n; i++) {
+            const uint32_t len = lengths[i];
+            if (len > stride) return fail(FQTK_B200_ERR_ARG, "lengths[i] exceeds row_stride");
+            if (len <= L) continue;
+            const uint8_t* r = rows + i * stride;
+            size_t nocalls = 0;
+            for (uint32_t k = 0; k < len; k++) nocalls += fq::byte_is_nocall(r[k]);
+            if (nocalls > (size_t)m->max_mm + m->max_ns) continue;  // pre-filter makes it None before the panic
+            char buf[160];
+            std::snprintf(buf, sizeof buf, "Read barcode (row %llu) length (%u) differs from expected barcode (",
+                          (unsigned long long)i, len);
+            std::string msg(buf);
+            msg.append(reinterpret_cast<const char*>(m->panel.data()), L);
+            std::snprintf(buf, sizeof buf, ") length (%u) for sample 0", L);
+            msg += buf;
+            return fail(FQTK_B200_ERR_LENGTH, msg);
+        }
+    }
+    CU(cudaSetDevice(m->device));
+    uint64_t chunk = CHUNK_BYTES / std::max<uint64_t>(stride, 1);
+    chunk = std::max<uint64_t>(chunk, 1024);
+    chunk = std::min<uint64_t>(chunk, n);
+    chunk &= ~3ull;
+    if (chunk == 0) chunk = n;
+    int rc = ensure_pipeline(m, (size_t)(chunk * stride + 16), (size_t)chunk, lengths != nullptr);
+    if (rc != FQTK_B200_OK) return rc;
+    uint64_t done = 0;
+    int slot = 0;
+    while (done < n) {
+        const uint64_t c = std::min(chunk, n - done);
+        cudaStream_t st = m->streams[slot];
+        // the caller's last row need not be padded out to `stride`: copy only up to its last valid byte
+        const size_t copy_bytes = (size_t)((c - 1) * stride) + (lengths ? (size_t)lengths[done + c - 1] : (size_t)L);
+        if (copy_bytes) CU(cudaMemcpyAsync(m->d_in[slot], rows + done * stride, copy_bytes, cudaMemcpyHostToDevice, st));
+        if (lengths) CU(cudaMemcpyAsync(m->d_len[slot], lengths + done, c * 4, cudaMemcpyHostToDevice, st));
+        fq::ReadSource src{nullptr, m->d_in[slot], lengths ? m->d_len[slot] : nullptr, stride, c};
+        rc = run_device(m, src, m->d_out[slot], st);
+        if (rc != FQTK_B200_OK) return rc;
+        CU(cudaMemcpyAsync(results + done, m->d_out[slot], c * 4, cudaMemcpyDeviceToHost, st));
+        done += c;
+        slot = (slot + 1) % N_PIPE;
+    }
+    for (int s = 0; s < N_PIPE; s++) CU(cudaStreamSynchronize(m->streams[s]));
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_matcher_assign(fqtk_b200_matcher* m, const uint8_t* read_bases, size_t len, uint32_t* result) {
+    if (!m || !result || (len && !read_bases)) return fail(FQTK_B200_ERR_ARG, "NULL argument");
+    if (len > 0xFFFFFFFFull) return fail(FQTK_B200_ERR_ARG, "read too long");
+    const uint32_t len32 = (uint32_t)len;
+    if (len == 0) {  // nothing to ship to the device: :167-169 makes it None (L >= 1); count it as the caller does
+        *result = FQTK_B200_NONE;
+        CU(cudaSetDevice(m->device));
+        CU(cudaDeviceSynchronize());
+        unsigned long long c = 0;
+        CU(cudaMemcpy(&c, m->d_counts + m->S, 8, cudaMemcpyDeviceToHost));
+        c += 1;
+        CU(cudaMemcpy(m->d_counts + m->S, &c, 8, cudaMemcpyHostToDevice));
+        return FQTK_B200_OK;
+    }
+    return fqtk_b200_matcher_assign_batch(m, read_bases, 1, len, &len32, result);
+}
+
+int fqtk_b200_matcher_counts(fqtk_b200_matcher* m, uint64_t* out) {
+    if (!m || !out) return fail(FQTK_B200_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(m->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, m->d_counts, (size_t)(m->S + 1) * 8, cudaMemcpyDeviceToHost));
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_matcher_counts_device(fqtk_b200_matcher* m, uint64_t** d_counts) {
+    if (!m || !d_counts) return fail(FQTK_B200_ERR_ARG, "NULL argument");
+    *d_counts = reinterpret_cast<uint64_t*>(m->d_counts);
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_matcher_reset_counts(fqtk_b200_matcher* m) {
+    if (!m) return fail(FQTK_B200_ERR_ARG, "NULL matcher");
+    CU(cudaSetDevice(m->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemset(m->d_counts, 0, (size_t)(m->S + 1) * 8));
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(FQTK_B200_ERR_ARG, "NULL argument");
+    CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_host_free(void* ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_synth_panel(uint64_t seed, uint32_t S, uint32_t L, uint32_t min_distance, uint32_t n_degenerate,
+                          uint8_t* out) {
+    if (!out || S == 0 || L == 0 || L > FQTK_B200_MAX_BARCODE_LEN) return fail(FQTK_B200_ERR_ARG, "bad argument");
+    if (fq::synth_panel_host(seed, S, L, min_distance, n_degenerate, out) != 0)
+        return fail(FQTK_B200_ERR_ARG, "no panel with that many samples at that distance");
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_synth_reads_host(const uint8_t* panel, uint32_t S, uint32_t L, uint64_t seed, uint64_t first,
+                               uint64_t n, uint8_t* out) {
+    if (!panel || (n && !out) || S == 0 || L == 0 || L > FQTK_B200_MAX_BARCODE_LEN)
+        return fail(FQTK_B200_ERR_ARG, "bad argument");
+    fq::synth_reads_host(panel, S, L, seed, first, n, out);
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_synth_reads_device(const uint8_t* panel, uint32_t S, uint32_t L, uint64_t seed, uint64_t first,
+                                 uint64_t n, uint8_t* d_ascii, uint32_t* d_packed, void* stream) {
+    if (!panel || S == 0 || L == 0 || L > FQTK_B200_MAX_BARCODE_LEN) return fail(FQTK_B200_ERR_ARG, "bad argument");
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, dev));
+    uint8_t* d_panel = nullptr;
+    CU(cudaMalloc(&d_panel, (size_t)S * L));
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(d_panel, panel, (size_t)S * L, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = fq::synth_reads_device(d_panel, S, L, seed, first, n, d_ascii, d_packed,
+                                                     prop.multiProcessorCount, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_panel);
+    if (e != cudaSuccess) return cuda_fail(e, "synth_reads_device");
+    return FQTK_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+// common.cuh — encoding, bit-plane and hashing primitives shared by host and device code.
+//
+// Everything here restates *semantics* of the reference (fulcrumgenomics/fqtk @ 45dbb99), not its code:
+//   encode_byte      : IUPAC_MASKS + byte_is_nocall + to_ascii_uppercase   src/lib/mod.rs:26-61,85-87
+//   packed layout    : width-4 BitEnc, symbol i at bits 4*(i%8) of u32 i/8  src/lib/bitenc.rs:311-322
+//   mismatch rule    : obs & !exp != 0 per symbol                           src/lib/bitenc.rs:441-452
+//   decision rule    : best/next-best, max_mismatches, min_mismatch_delta   src/lib/barcode_matching.rs:119-160
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define FQ_HD __host__ __device__ __forceinline__
+#define FQ_D __device__ __forceinline__
+
+namespace fq {
+
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr uint32_t EMPTY_KEY = 0xFFFFFFFFu;  // running-min sentinel: no barcode seen yet
+constexpr int MAX_FAST_WORDS = 4;            // L <= 32 keeps a read in <= 4 packed words / one 32-bit plane set
+
+// ASCII byte -> 4-bit base set {A=1,C=2,G=4,T=8}.  No-calls 'N','n','.' -> 15; letters are upper-cased first;
+// 'U' = T; IUPAC degenerate codes are unions; every other byte -> 0 (which can never mismatch).
+FQ_HD uint32_t encode_byte(uint32_t b) {
+    if (b == '.') return 15u;
+    if (b >= 'a' && b <= 'z') b -= 32u;
+    switch (b) {
+        case 'A': return 1u;
+        case 'C': return 2u;
+        case 'G': return 4u;
+        case 'T': return 8u;
+        case 'U': return 8u;
+        case 'M': return 3u;   // A|C
+        case 'R': return 5u;   // A|G
+        case 'W': return 9u;   // A|T
+        case 'S': return 6u;   // C|G
+        case 'Y': return 10u;  // C|T
+        case 'K': return 12u;  // G|T
+        case 'V': return 7u;   // A|C|G
+        case 'H': return 11u;  // A|C|T
+        case 'D': return 13u;  // A|G|T
+        case 'B': return 14u;  // C|G|T
+        case 'N': return 15u;
+        default: return 0u;
+    }
+}
+
+FQ_HD bool byte_is_nocall(uint32_t b) { return b == 'N' || b == 'n' || b == '.'; }
+
+FQ_HD uint32_t words_for_len(uint32_t L) { return (L + 7u) / 8u; }
+FQ_HD uint32_t planes_for_len(uint32_t L) { return (L + 31u) / 32u; }
+
+// Bit k of each of the 8 nibbles of x, gathered into the low 8 bits (nibble i -> bit i).
+FQ_HD uint32_t gather_nibble_bit(uint32_t x, int k) {
+    uint32_t y = (x >> k) & 0x11111111u;
+    y = (y | (y >> 3)) & 0x03030303u;
+    y = (y | (y >> 6)) & 0x000F000Fu;
+    y = (y | (y >> 12)) & 0x000000FFu;
+    return y;
+}
+
+// Four "has base X" bit-planes (X = A,C,G,T) of up to 32 symbols held in up to four packed words.
+template <int W>
+FQ_HD void planes_from_words(const uint32_t (&w)[W], uint32_t (&pl)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int i = 0; i < W; i++) v |= gather_nibble_bit(w[i], k) << (8 * i);
+        pl[k] = v;
+    }
+}
+
+// True when every symbol of the read is one of A,C,G,T,N (masks 1,2,4,8,15) — the alphabet the memo table
+// enumerates.  `pad_or` has 0x1 in every nibble beyond the barcode length so padding never trips the test.
+FQ_HD bool word_in_table_alphabet(uint32_t x) {
+    const uint32_t sum = (x & 0x11111111u) + ((x >> 1) & 0x11111111u) + ((x >> 2) & 0x11111111u) +
+                         ((x >> 3) & 0x11111111u);                       // per-nibble popcount, 0..4
+    // a nibble is fine iff its popcount is 1 (bit0 set, bit1 clear) or 4 (bit2 set); 0, 2 and 3 are not
+    const uint32_t ok = ~(sum >> 1) & (sum | (sum >> 2)) & 0x11111111u;
+    return ok == 0x11111111u;
+}
+
+template <int W>
+FQ_HD bool read_in_table_alphabet(const uint32_t (&w)[W], uint32_t last_word_pad) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < W; i++) ok = ok && word_in_table_alphabet(i == W - 1 ? (w[i] | last_word_pad) : w[i]);
+    return ok;
+}
+
+FQ_HD uint32_t last_word_pad_for_len(uint32_t L) {
+    const uint32_t used = L % 8u;
+    return used == 0u ? 0u : (0x11111111u << (4u * used));
+}
+
+// 32-bit mix of a W-word key; identical on host (table build) and device (probe).
+template <int W>
+FQ_HD uint32_t hash_key(const uint32_t (&w)[W]) {
+    uint32_t h = 0x9E3779B9u;
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        h = (h ^ w[i]) * 0x85EBCA6Bu;
+        h ^= h >> 15;
+    }
+    h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+
+// Running best / second-best on keys (distance << 16 | sample index): keys are unique per sample, so plain
+// min / second-min on the key gives min distance, FIRST index among ties (strict '<' at
+// barcode_matching.rs:132) and the second-smallest distance with multiplicity (:140).
+FQ_HD void track2(uint32_t& k1, uint32_t& k2, uint32_t key) {
+    const uint32_t hi = k1 > key ? k1 : key;
+    k1 = k1 < key ? k1 : key;
+    k2 = k2 < hi ? k2 : hi;
+}
+
+FQ_HD void merge2(uint32_t& k1, uint32_t& k2, uint32_t o1, uint32_t o2) {
+    const uint32_t hi = k1 > o1 ? k1 : o1;
+    const uint32_t lo2 = k2 < o2 ? k2 : o2;
+    k1 = k1 < o1 ? k1 : o1;
+    k2 = hi < lo2 ? hi : lo2;
+}
+
+// barcode_matching.rs:149-159.  k2 == EMPTY_KEY means a single-sample panel: next_best stays 255 (:122).
+FQ_HD uint32_t decide(uint32_t k1, uint32_t k2, uint32_t max_mismatches, uint32_t min_delta) {
+    const uint32_t best = k1 >> 16, idx = k1 & 0xFFFFu;
+    const uint32_t next = (k2 == EMPTY_KEY) ? 255u : (k2 >> 16);
+    if (best > max_mismatches || (next - best) < min_delta) return NONE;
+    return (idx << 16) | (best << 8) | next;
+}
+
+}  // namespace fq

@@ -1,0 +1,50 @@
+// kernels.h — host-side launch interface of the sm_100a kernels (internal; the public ABI is include/fqtk_b200.h).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fq {
+
+// Device-resident description of a matcher's panel and decision parameters.
+struct MatchParams {
+    const uint4* planes;       // [S * P] "forbidden base" bit-planes per barcode: .x/.y/.z/.w bit i set iff position
+                               //  32*p + i of the barcode does NOT admit A/C/G/T
+    const uint32_t* not_exp;   // [S * W] ~expected nibble words (only read by the L > 32 kernel)
+    const uint32_t* table;     // memo table entries (nullptr in brute mode)
+    unsigned long long* counts;  // [S + 1] per-sample counts, last = unmatched
+    uint32_t S, L, W, P;
+    uint32_t max_mm, min_delta;
+    uint32_t last_pad;         // 0x1 in every padding nibble of the last packed word
+    uint32_t slot_mask;        // table slots - 1
+};
+
+// Where a batch of reads lives on the device.
+struct ReadSource {
+    const uint32_t* packed;    // n * W words, or nullptr
+    const uint8_t* ascii;      // n rows of `stride` bytes, or nullptr
+    const uint32_t* lengths;   // optional per-row lengths for the ASCII form
+    uint64_t stride;
+    uint64_t n;                // < 2^32
+};
+
+struct LaunchGeometry {
+    int sm_count;
+    int max_smem_optin;
+};
+
+// Table entry geometry by key width (words): {key words..., value, padding}.
+inline __host__ __device__ int table_entry_words(int W) { return W == 1 ? 2 : (W <= 3 ? 4 : 8); }
+inline __host__ __device__ int table_value_index(int W) { return W == 4 ? 4 : W; }
+
+cudaError_t launch_brute(const MatchParams& p, const ReadSource& src, uint32_t* d_results, const LaunchGeometry& g,
+                         cudaStream_t stream);
+cudaError_t launch_probe(const MatchParams& p, const ReadSource& src, uint32_t* d_results, const LaunchGeometry& g,
+                         cudaStream_t stream);
+cudaError_t launch_pack(const uint8_t* d_ascii, uint64_t n, uint32_t L, uint64_t stride, uint32_t* d_packed,
+                        const LaunchGeometry& g, cudaStream_t stream);
+cudaError_t prepare_kernels(const LaunchGeometry& g);  // opt-in shared memory attributes, once per device
+
+uint64_t kernel_launches();
+void count_launch();
+
+}  // namespace fq

@@ -1,0 +1,500 @@
+// match_kernels.cu — the sm_100a kernels of the demux barcode matcher.
+//
+// What they compute is the closed form of BarcodeMatcher::assign (src/lib/barcode_matching.rs:119-186 of the
+// reference; derivation in SURVEY.md Appendix A.2): exact IUPAC-aware distance d_j = #{i : obs_i & !exp_ji != 0}
+// (src/lib/bitenc.rs:441-452) to every barcode j, best = min d_j with the FIRST index on ties, next = second
+// smallest with multiplicity, None iff best > max_mismatches or next - best < min_mismatch_delta; then the
+// caller's count rule (src/bin/commands/demux.rs:970-974).
+//
+// Two kernel families, bit-identical results:
+//   k_brute  — thread per read, whole panel as "forbidden base" bit-planes in shared memory (broadcast LDS.128),
+//              4 logic ops + 1 popcount per (read, barcode) pair, running (distance<<16 | index) min / second-min.
+//   k_probe  — memo-table kernel: the read's packed words are the key of a pre-computed open-addressing table
+//              holding the result of every A/C/G/T/N string within max_mismatches of some barcode (the device
+//              analogue of the reference's AHashMap cache, barcode_matching.rs:173-182, pre-filled).  A miss on
+//              an in-alphabet read is None; a miss on any other read (IUPAC / junk / lowercase-only symbols) is
+//              resolved by the whole warp brute-forcing that one read with shuffle min / second-min reduction.
+// Per-sample counts: CTA-private shared-memory histogram (atomics), flushed once per CTA with 64-bit REDs.
+#include <atomic>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fq {
+
+static std::atomic<uint64_t> g_launches{0};
+uint64_t kernel_launches() { return g_launches.load(); }
+void count_launch() { g_launches.fetch_add(1); }
+
+constexpr uint32_t HIST_SMEM_BINS = 8192;  // S + 1 <= this: CTA-private histogram lives in shared memory
+constexpr int BRUTE_THREADS = 512;
+constexpr int PROBE_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------------------
+// read loaders
+// ------------------------------------------------------------------------------------------------------
+template <int W>
+FQ_D void load_packed(const uint32_t* __restrict__ packed, uint64_t i, uint32_t (&w)[W]) {
+    if constexpr (W == 2) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(packed) + i);
+        w[0] = v.x;
+        w[1] = v.y;
+    } else if constexpr (W == 4) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(packed) + i);
+        w[0] = v.x;
+        w[1] = v.y;
+        w[2] = v.z;
+        w[3] = v.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < W; k++) w[k] = __ldg(packed + i * W + k);
+    }
+}
+
+// encode() of one ASCII row (mod.rs:49-61) through the shared-memory LUT.  Returns false when the row's
+// length differs from L (short rows are None, barcode_matching.rs:167-169; long rows were vetted by the host).
+template <int W>
+FQ_D bool load_ascii(const ReadSource& src, uint64_t i, uint32_t L, const uint8_t* __restrict__ lut,
+                     uint32_t (&w)[W]) {
+#pragma unroll
+    for (int k = 0; k < W; k++) w[k] = 0u;
+    if (src.lengths != nullptr && __ldg(src.lengths + i) != L) return false;
+    const uint8_t* row = src.ascii + i * src.stride;
+    const bool aligned4 = ((reinterpret_cast<uintptr_t>(row) & 3u) == 0u);
+#pragma unroll
+    for (int wi = 0; wi < W; wi++) {
+        uint32_t acc = 0u;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const uint32_t k0 = wi * 8u + half * 4u;
+            if (k0 + 4u <= L && aligned4) {
+                const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(row + k0));
+                acc |= (uint32_t)lut[v & 0xFFu] << (16 * half);
+                acc |= (uint32_t)lut[(v >> 8) & 0xFFu] << (16 * half + 4);
+                acc |= (uint32_t)lut[(v >> 16) & 0xFFu] << (16 * half + 8);
+                acc |= (uint32_t)lut[v >> 24] << (16 * half + 12);
+            } else {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const uint32_t k = k0 + b;
+                    if (k < L) acc |= (uint32_t)lut[__ldg(row + k)] << (16 * half + 4 * b);
+                }
+            }
+        }
+        w[wi] = acc;
+    }
+    return true;
+}
+
+FQ_D void init_lut(uint8_t* lut) {
+    for (uint32_t t = threadIdx.x; t < 256u; t += blockDim.x) lut[t] = (uint8_t)encode_byte(t);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// counting
+// ------------------------------------------------------------------------------------------------------
+struct Counter {
+    uint32_t* s_hist;           // nullptr -> straight to global
+    unsigned long long* g_counts;
+    uint32_t S;
+    uint32_t none_local;
+
+    FQ_D void init(uint32_t* smem_hist, const MatchParams& p) {
+        S = p.S;
+        g_counts = p.counts;
+        none_local = 0u;
+        s_hist = (p.S + 1u <= HIST_SMEM_BINS) ? smem_hist : nullptr;
+        if (s_hist)
+            for (uint32_t b = threadIdx.x; b <= S; b += blockDim.x) s_hist[b] = 0u;
+    }
+    FQ_D void add(uint32_t result) {
+        if (result == NONE) {
+            none_local++;  // unmatched is the hot bin: keep it in a register, reduce per warp at the end
+        } else if (s_hist) {
+            atomicAdd(&s_hist[result >> 16], 1u);
+        } else {
+            atomicAdd(&g_counts[result >> 16], 1ull);
+        }
+    }
+    // all threads of the CTA must call this
+    FQ_D void flush() {
+        uint32_t v = none_local;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
+        if ((threadIdx.x & 31u) == 0u && v) {
+            if (s_hist)
+                atomicAdd(&s_hist[S], v);
+            else
+                atomicAdd(&g_counts[S], (unsigned long long)v);
+        }
+        if (s_hist) {
+            __syncthreads();
+            for (uint32_t b = threadIdx.x; b <= S; b += blockDim.x) {
+                const uint32_t c = s_hist[b];
+                if (c) atomicAdd(&g_counts[b], (unsigned long long)c);
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// k_brute: thread per read, panel planes in shared memory (or global when they do not fit)
+// ------------------------------------------------------------------------------------------------------
+template <int W, bool ASCII, bool PANEL_SMEM>
+__global__ void __launch_bounds__(BRUTE_THREADS) k_brute(const MatchParams p, const ReadSource src,
+                                                         uint32_t* __restrict__ results) {
+    extern __shared__ uint4 s_dyn[];
+    __shared__ uint8_t s_lut[256];
+    uint4* s_planes = s_dyn;
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_dyn + (PANEL_SMEM ? p.S : 0u));
+
+    if constexpr (PANEL_SMEM) {
+        for (uint32_t j = threadIdx.x; j < p.S; j += blockDim.x) s_planes[j] = __ldg(p.planes + j);
+    }
+    if constexpr (ASCII) init_lut(s_lut);
+    Counter cnt;
+    cnt.init(s_hist, p);
+    __syncthreads();
+
+    const uint4* __restrict__ planes = PANEL_SMEM ? s_planes : p.planes;
+    const uint64_t total = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < src.n; i += total) {
+        uint32_t w[W];
+        bool row_ok = true;
+        if constexpr (ASCII)
+            row_ok = load_ascii<W>(src, i, p.L, s_lut, w);
+        else
+            load_packed<W>(src.packed, i, w);
+        uint32_t pl[4];
+        planes_from_words<W>(w, pl);
+        uint32_t k1 = EMPTY_KEY, k2 = EMPTY_KEY;
+#pragma unroll 8
+        for (uint32_t j = 0; j < p.S; j++) {
+            uint4 nb;
+            if constexpr (PANEL_SMEM)
+                nb = planes[j];
+            else
+                nb = __ldg(planes + j);
+            const uint32_t m = (pl[0] & nb.x) | (pl[1] & nb.y) | (pl[2] & nb.z) | (pl[3] & nb.w);
+            track2(k1, k2, ((uint32_t)__popc(m) << 16) | j);
+        }
+        const uint32_t res = row_ok ? decide(k1, k2, p.max_mm, p.min_delta) : NONE;
+        results[i] = res;
+        cnt.add(res);
+    }
+    cnt.flush();
+}
+
+// L > 32: nibble-word form straight from the packed layout (rare; barcodes this long are unusual).
+__global__ void __launch_bounds__(256) k_brute_long(const MatchParams p, const ReadSource src,
+                                                    uint32_t* __restrict__ results) {
+    extern __shared__ uint4 s_dyn[];
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_dyn);
+    Counter cnt;
+    cnt.init(s_hist, p);
+    __syncthreads();
+    const uint64_t total = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < src.n; i += total) {
+        uint32_t r[32];
+        for (uint32_t k = 0; k < p.W; k++) r[k] = __ldg(src.packed + i * p.W + k);
+        uint32_t k1 = EMPTY_KEY, k2 = EMPTY_KEY;
+        for (uint32_t j = 0; j < p.S; j++) {
+            uint32_t d = 0;
+            for (uint32_t k = 0; k < p.W; k++) {
+                uint32_t x = r[k] & __ldg(p.not_exp + (size_t)j * p.W + k);
+                x |= x >> 1;
+                x |= x >> 2;
+                d += __popc(x & 0x11111111u);
+            }
+            track2(k1, k2, (d << 16) | j);
+        }
+        const uint32_t res = decide(k1, k2, p.max_mm, p.min_delta);
+        results[i] = res;
+        cnt.add(res);
+    }
+    cnt.flush();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_probe: memo-table lookup, warp-cooperative brute force for out-of-alphabet reads
+// ------------------------------------------------------------------------------------------------------
+template <int W>
+FQ_D uint32_t warp_brute_one(const MatchParams& p, const uint32_t (&w)[W], uint32_t lane) {
+    uint32_t pl[4];
+    planes_from_words<W>(w, pl);
+    uint32_t k1 = EMPTY_KEY, k2 = EMPTY_KEY;
+    for (uint32_t j = lane; j < p.S; j += 32u) {
+        const uint4 nb = __ldg(p.planes + j);
+        const uint32_t m = (pl[0] & nb.x) | (pl[1] & nb.y) | (pl[2] & nb.z) | (pl[3] & nb.w);
+        track2(k1, k2, ((uint32_t)__popc(m) << 16) | j);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const uint32_t o1 = __shfl_xor_sync(0xFFFFFFFFu, k1, off);
+        const uint32_t o2 = __shfl_xor_sync(0xFFFFFFFFu, k2, off);
+        merge2(k1, k2, o1, o2);
+    }
+    return decide(k1, k2, p.max_mm, p.min_delta);
+}
+
+// One table lookup.  Returns true on a hit (res = stored Some(..) word); false when an empty slot ends the probe.
+template <int W>
+FQ_D bool table_lookup(const MatchParams& p, const uint32_t (&w)[W], uint32_t& res) {
+    uint32_t slot = hash_key<W>(w) & p.slot_mask;
+    for (;;) {
+        if constexpr (W == 1) {
+            const uint2 e = __ldg(reinterpret_cast<const uint2*>(p.table) + slot);
+            if (e.x == w[0] && e.y != NONE) { res = e.y; return true; }
+            if (e.y == NONE) return false;
+        } else if constexpr (W == 2) {
+            const uint4 e = __ldg(reinterpret_cast<const uint4*>(p.table) + slot);
+            if (e.x == w[0] && e.y == w[1] && e.z != NONE) { res = e.z; return true; }
+            if (e.z == NONE) return false;
+        } else if constexpr (W == 3) {
+            const uint4 e = __ldg(reinterpret_cast<const uint4*>(p.table) + slot);
+            if (e.x == w[0] && e.y == w[1] && e.z == w[2] && e.w != NONE) { res = e.w; return true; }
+            if (e.w == NONE) return false;
+        } else {
+            const uint4 e = __ldg(reinterpret_cast<const uint4*>(p.table) + 2u * (size_t)slot);
+            const uint32_t v = __ldg(p.table + 8u * (size_t)slot + 4u);
+            if (e.x == w[0] && e.y == w[1] && e.z == w[2] && e.w == w[3] && v != NONE) { res = v; return true; }
+            if (v == NONE) return false;
+        }
+        slot = (slot + 1u) & p.slot_mask;
+    }
+}
+
+template <int W, int R, bool ASCII>
+__global__ void __launch_bounds__(PROBE_THREADS) k_probe(const MatchParams p, const ReadSource src,
+                                                         uint32_t* __restrict__ results) {
+    extern __shared__ uint4 s_dyn[];
+    __shared__ uint8_t s_lut[256];
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_dyn);
+    if constexpr (ASCII) init_lut(s_lut);
+    Counter cnt;
+    cnt.init(s_hist, p);
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t n_groups = (src.n + R - 1) / R;
+    const uint64_t total = (uint64_t)gridDim.x * blockDim.x;
+    // warp-uniform trip count so the whole warp is present for the cooperative slow path
+    for (uint64_t gbase = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); gbase < n_groups; gbase += total) {
+        const uint64_t g = gbase + lane;
+        uint32_t w[R][W];
+        uint32_t res[R];
+        bool valid[R], row_ok[R];
+        const bool full = (g + 1) * R <= src.n;
+
+        if constexpr (!ASCII && R == 4) {
+            if (full) {  // 4 reads = W x 16 B, one LDG.128 each, fully coalesced across the warp
+                uint32_t flat[4 * W];
+#pragma unroll
+                for (int v = 0; v < W; v++) {
+                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(src.packed) + g * W + v);
+                    flat[4 * v + 0] = q.x;
+                    flat[4 * v + 1] = q.y;
+                    flat[4 * v + 2] = q.z;
+                    flat[4 * v + 3] = q.w;
+                }
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+#pragma unroll
+                    for (int k = 0; k < W; k++) w[r][k] = flat[r * W + k];
+                    valid[r] = true;
+                    row_ok[r] = true;
+                }
+            }
+        }
+        if (ASCII || R != 4 || !full) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const uint64_t i = g * R + r;
+                valid[r] = i < src.n;
+                row_ok[r] = true;
+#pragma unroll
+                for (int k = 0; k < W; k++) w[r][k] = 0u;
+                if (valid[r]) {
+                    if constexpr (ASCII)
+                        row_ok[r] = load_ascii<W>(src, i, p.L, s_lut, w[r]);
+                    else
+                        load_packed<W>(src.packed, i, w[r]);
+                }
+            }
+        }
+
+        bool slow[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            res[r] = NONE;
+            slow[r] = false;
+            if (valid[r] && row_ok[r]) {
+                if (!table_lookup<W>(p, w[r], res[r])) {
+                    res[r] = NONE;
+                    slow[r] = !read_in_table_alphabet<W>(w[r], p.last_pad);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            uint32_t pending = __ballot_sync(0xFFFFFFFFu, slow[r]);
+            while (pending) {
+                const int src_lane = __ffs(pending) - 1;
+                pending &= pending - 1u;
+                uint32_t bw[W];
+#pragma unroll
+                for (int k = 0; k < W; k++) bw[k] = __shfl_sync(0xFFFFFFFFu, w[r][k], src_lane);
+                const uint32_t out = warp_brute_one<W>(p, bw, lane);
+                if ((int)lane == src_lane) res[r] = out;
+            }
+        }
+
+        if (R == 4 && full) {
+            reinterpret_cast<uint4*>(results)[g] = make_uint4(res[0], res[1], res[2], res[3]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if (valid[r]) results[g * R + r] = res[r];
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            if (valid[r]) cnt.add(res[r]);
+    }
+    cnt.flush();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_pack: encode() for a batch (mod.rs:49-61), any L
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack(const uint8_t* __restrict__ ascii, uint64_t n, uint32_t L,
+                                              uint64_t stride, uint32_t* __restrict__ packed) {
+    __shared__ uint8_t s_lut[256];
+    init_lut(s_lut);
+    __syncthreads();
+    const uint32_t W = words_for_len(L);
+    const uint64_t total = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += total) {
+        const uint8_t* row = ascii + i * stride;
+        for (uint32_t wi = 0; wi < W; wi++) {
+            uint32_t acc = 0u;
+            for (uint32_t b = 0; b < 8u; b++) {
+                const uint32_t k = wi * 8u + b;
+                if (k < L) acc |= (uint32_t)s_lut[__ldg(row + k)] << (4u * b);
+            }
+            packed[i * W + wi] = acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------------
+static uint32_t hist_bytes(const MatchParams& p) {
+    return (p.S + 1u <= HIST_SMEM_BINS) ? (p.S + 1u) * 4u : 0u;
+}
+
+template <typename K>
+static int grid_for(K kernel, int threads, size_t smem, const LaunchGeometry& g, uint64_t work_items) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+    uint64_t want = (work_items + threads - 1) / threads;
+    uint64_t cap = (uint64_t)g.sm_count * occ;  // persistent: one wave of resident CTAs, grid-stride inside
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+template <int W, bool ASCII>
+static cudaError_t launch_brute_w(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
+                                  const LaunchGeometry& g, cudaStream_t stream) {
+    const size_t panel_bytes = (size_t)p.S * sizeof(uint4);
+    const size_t hb = hist_bytes(p);
+    const bool panel_smem = panel_bytes + hb + 1024 <= (size_t)g.max_smem_optin;
+    if (panel_smem) {
+        auto k = k_brute<W, ASCII, true>;
+        const size_t smem = panel_bytes + hb;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int grid = grid_for(k, BRUTE_THREADS, smem, g, src.n);
+        k<<<grid, BRUTE_THREADS, smem, stream>>>(p, src, d_results);
+    } else {
+        auto k = k_brute<W, ASCII, false>;
+        const int grid = grid_for(k, BRUTE_THREADS, hb, g, src.n);
+        k<<<grid, BRUTE_THREADS, hb, stream>>>(p, src, d_results);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_brute(const MatchParams& p, const ReadSource& src, uint32_t* d_results, const LaunchGeometry& g,
+                         cudaStream_t stream) {
+    if (src.n == 0) return cudaSuccess;
+    const bool ascii = src.ascii != nullptr;
+    if (p.W > (uint32_t)MAX_FAST_WORDS) {
+        if (ascii) return cudaErrorInvalidValue;  // caller packs first
+        const size_t hb = hist_bytes(p);
+        const int grid = grid_for(k_brute_long, 256, hb, g, src.n);
+        k_brute_long<<<grid, 256, hb, stream>>>(p, src, d_results);
+        count_launch();
+        return cudaGetLastError();
+    }
+    switch (p.W) {
+        case 1: return ascii ? launch_brute_w<1, true>(p, src, d_results, g, stream) : launch_brute_w<1, false>(p, src, d_results, g, stream);
+        case 2: return ascii ? launch_brute_w<2, true>(p, src, d_results, g, stream) : launch_brute_w<2, false>(p, src, d_results, g, stream);
+        case 3: return ascii ? launch_brute_w<3, true>(p, src, d_results, g, stream) : launch_brute_w<3, false>(p, src, d_results, g, stream);
+        default: return ascii ? launch_brute_w<4, true>(p, src, d_results, g, stream) : launch_brute_w<4, false>(p, src, d_results, g, stream);
+    }
+}
+
+template <int W, int R, bool ASCII>
+static cudaError_t launch_probe_w(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
+                                  const LaunchGeometry& g, cudaStream_t stream) {
+    auto k = k_probe<W, R, ASCII>;
+    const size_t hb = hist_bytes(p);
+    const uint64_t n_groups = (src.n + R - 1) / R;
+    const int grid = grid_for(k, PROBE_THREADS, hb, g, n_groups);
+    k<<<grid, PROBE_THREADS, hb, stream>>>(p, src, d_results);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_probe(const MatchParams& p, const ReadSource& src, uint32_t* d_results, const LaunchGeometry& g,
+                         cudaStream_t stream) {
+    if (src.n == 0) return cudaSuccess;
+    if (p.table == nullptr || p.W > (uint32_t)MAX_FAST_WORDS) return cudaErrorInvalidValue;
+    const bool ascii = src.ascii != nullptr;
+    if (ascii) {
+        switch (p.W) {
+            case 1: return launch_probe_w<1, 1, true>(p, src, d_results, g, stream);
+            case 2: return launch_probe_w<2, 1, true>(p, src, d_results, g, stream);
+            case 3: return launch_probe_w<3, 1, true>(p, src, d_results, g, stream);
+            default: return launch_probe_w<4, 1, true>(p, src, d_results, g, stream);
+        }
+    }
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(src.packed) | reinterpret_cast<uintptr_t>(d_results)) & 15u) == 0u;
+    if (vec_ok) {
+        switch (p.W) {
+            case 1: return launch_probe_w<1, 4, false>(p, src, d_results, g, stream);
+            case 2: return launch_probe_w<2, 4, false>(p, src, d_results, g, stream);
+            case 3: return launch_probe_w<3, 4, false>(p, src, d_results, g, stream);
+            default: return launch_probe_w<4, 4, false>(p, src, d_results, g, stream);
+        }
+    }
+    switch (p.W) {
+        case 1: return launch_probe_w<1, 1, false>(p, src, d_results, g, stream);
+        case 2: return launch_probe_w<2, 1, false>(p, src, d_results, g, stream);
+        case 3: return launch_probe_w<3, 1, false>(p, src, d_results, g, stream);
+        default: return launch_probe_w<4, 1, false>(p, src, d_results, g, stream);
+    }
+}
+
+cudaError_t launch_pack(const uint8_t* d_ascii, uint64_t n, uint32_t L, uint64_t stride, uint32_t* d_packed,
+                        const LaunchGeometry& g, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const int grid = grid_for(k_pack, 256, 0, g, n);
+    k_pack<<<grid, 256, 0, stream>>>(d_ascii, n, L, stride, d_packed);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t prepare_kernels(const LaunchGeometry&) { return cudaSuccess; }
+
+}  // namespace fq

@@ -1,0 +1,158 @@
+/*
+ * fqtk_b200.h — C ABI of the B200-native (sm_100a) replacement for fqtk's `demux` barcode-matcher hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, never unwinds.  It replaces
+ * the public Rust API of `fqtk_lib::barcode_matching` (reference paths relative to the fqtk repo root):
+ *
+ *   BarcodeMatcher::new(samples, max_mismatches, min_mismatch_delta, use_cache)   src/lib/barcode_matching.rs:55-86
+ *   BarcodeMatcher::assign(&mut self, read_bases) -> Option<BarcodeMatch>          src/lib/barcode_matching.rs:165-186
+ *   struct BarcodeMatch { best_match, best_mismatches, next_best_mismatches }      src/lib/barcode_matching.rs:16-25
+ *   the caller's count rule (templates += 1 per Some / per None)                  src/bin/commands/demux.rs:968-975
+ *   encode() / IUPAC_MASKS / byte_is_nocall                                        src/lib/mod.rs:26-61,85-87
+ *
+ * The only change asked of the caller (demux.rs:945-977) is to collect K read-sets, make ONE batch call,
+ * and route the results in index order.  INTEGRATION.md shows the Rust `extern "C"` block and safe wrapper.
+ *
+ * Threading: a handle is NOT thread-safe (same contract as `&mut self`); one handle per device.
+ * Errors: every function returns FQTK_B200_OK or a negative code; fqtk_b200_last_error() (thread-local)
+ * holds the text, which for the reference's panics is the reference's own panic message.
+ * There is no CPU fallback: every entry point that matches reads needs a CUDA device.
+ */
+#ifndef FQTK_B200_H
+#define FQTK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define FQTK_B200_API
+#else
+#define FQTK_B200_API __attribute__((visibility("default")))
+#endif
+
+/* ---- result word: one u32 per read (replaces Option<BarcodeMatch>, barcode_matching.rs:16-25) ----
+ *   FQTK_B200_NONE                                   Option::None
+ *   (best_match << 16) | (best_mismatches << 8) | next_best_mismatches      Some(..)
+ * best_match < S <= 65535; next_best_mismatches keeps the reference's 255 sentinel for a 1-sample panel. */
+#define FQTK_B200_NONE 0xFFFFFFFFu
+#define FQTK_B200_BEST_MATCH(w) ((uint32_t)(w) >> 16)
+#define FQTK_B200_BEST_MISMATCHES(w) (((uint32_t)(w) >> 8) & 0xFFu)
+#define FQTK_B200_NEXT_BEST_MISMATCHES(w) ((uint32_t)(w) & 0xFFu)
+
+#define FQTK_B200_MAX_SAMPLES 65535u
+#define FQTK_B200_MAX_BARCODE_LEN 254u /* u8 distances with a 255 sentinel, as in the reference */
+
+/* ---- status codes ---- */
+#define FQTK_B200_OK 0
+#define FQTK_B200_ERR_EMPTY_PANEL (-1)   /* panic "Must provide at least one sample"       barcode_matching.rs:61    */
+#define FQTK_B200_ERR_EMPTY_BARCODE (-2) /* panic "Sample barcode cannot be empty string"  barcode_matching.rs:62-65 */
+#define FQTK_B200_ERR_LENGTH (-3)        /* panic "Read barcode (..) length (..) differs.." barcode_matching.rs:95-106 */
+#define FQTK_B200_ERR_ARG (-4)
+#define FQTK_B200_ERR_CUDA (-5)
+#define FQTK_B200_ERR_UNSUPPORTED (-6)   /* S > 65535 or L > 254 */
+
+typedef struct fqtk_b200_matcher fqtk_b200_matcher;
+
+/* which kernel family a matcher runs */
+#define FQTK_B200_MODE_BRUTE 1 /* every read x every barcode, bit-plane popcount, thread per read */
+#define FQTK_B200_MODE_TABLE 2 /* pre-computed memo table of the <= max_mismatches neighbourhood, warp-cooperative
+                                  brute force for reads outside the table's alphabet */
+
+typedef struct {
+    uint32_t n_samples;          /* S */
+    uint32_t barcode_len;        /* L */
+    uint32_t words_per_read;     /* W = ceil(L/8): u32 blocks of the 4-bit BitEnc layout (bitenc.rs:311-322) */
+    uint32_t max_ns_in_barcodes; /* barcode_matching.rs:73-74 */
+    uint32_t mode;               /* FQTK_B200_MODE_* */
+    uint32_t device;
+    uint64_t table_entries;      /* memo-table entries (0 in brute mode) */
+    uint64_t table_slots;
+    uint64_t table_bytes;
+    uint64_t table_candidates;   /* neighbourhood strings enumerated before filtering to Some(..) */
+} fqtk_b200_matcher_info;
+
+/* ---- lifecycle -------------------------------------------------------------------------------------
+ * BarcodeMatcher::new (barcode_matching.rs:55-86).  `panel_ascii` = S rows of L bytes, row-major, in sample-sheet
+ * order (first-index tie-break depends on it).  Bytes are upper-cased (:71) and encoded exactly as the reference's
+ * encode() does; the panel is copied, the caller may free it on return.
+ * `use_cache`: the reference's memo-cache switch (demux.rs:925 passes true).  Non-zero builds the device memo table
+ * when the panel's <= max_mismatches neighbourhood fits `fqtk_b200_set_table_budget` (default 64 Mi candidates),
+ * zero (or an over-budget panel, or L > 32) selects the brute-force kernels.  Results are identical either way. */
+FQTK_B200_API int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t n_samples, uint32_t barcode_len,
+                                           uint8_t max_mismatches, uint8_t min_mismatch_delta, int use_cache,
+                                           int device, fqtk_b200_matcher** out);
+FQTK_B200_API void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m);
+FQTK_B200_API int fqtk_b200_matcher_get_info(const fqtk_b200_matcher* m, fqtk_b200_matcher_info* info);
+FQTK_B200_API void fqtk_b200_set_table_budget(uint64_t max_candidates);
+
+/* ---- reference-facing calls: HOST buffers ----------------------------------------------------------
+ * BarcodeMatcher::assign (barcode_matching.rs:165-186) for one read, any length: len < L -> NONE (:167-169);
+ * len > L -> FQTK_B200_ERR_LENGTH (:95-106) unless the no-call pre-filter (:170-172) already made it NONE.
+ * Adds 1 to counts[best_match] or counts[S] like the caller does (demux.rs:970-974). */
+FQTK_B200_API int fqtk_b200_matcher_assign(fqtk_b200_matcher* m, const uint8_t* read_bases, size_t len,
+                                           uint32_t* result);
+
+/* The batched form of the same call: `n_reads` rows, row i at barcodes_ascii + i*row_stride.
+ * `lengths` NULL  -> every row holds exactly L bases (row_stride >= L).
+ * `lengths` given -> row i holds lengths[i] <= row_stride bases with the single-read length rules above;
+ *                    the whole call fails with FQTK_B200_ERR_LENGTH (nothing counted) if any row would panic.
+ * Synchronous.  Internally chunked and double-buffered (H2D, kernel, D2H overlap); pass memory from
+ * fqtk_b200_host_alloc (pinned) for full PCIe rate.  results[i] is written for every row; counts accumulate. */
+FQTK_B200_API int fqtk_b200_matcher_assign_batch(fqtk_b200_matcher* m, const uint8_t* barcodes_ascii,
+                                                 uint64_t n_reads, uint64_t row_stride, const uint32_t* lengths,
+                                                 uint32_t* results);
+
+/* ---- HBM-resident calls: DEVICE buffers, asynchronous on `stream` (a cudaStream_t, NULL = default) ----
+ * `d_packed`: n_reads * W u32 words, read i at words [i*W, (i+1)*W), symbol k of a read in bits 4*(k%8) of its
+ * word k/8 — the reference's own BitEnc layout (mod.rs:49-61, bitenc.rs:311-322).  `d_results`: n_reads u32.
+ * n_reads < 2^32 per call.  Counts accumulate on the device; read them with fqtk_b200_matcher_counts. */
+FQTK_B200_API int fqtk_b200_matcher_assign_packed_device(fqtk_b200_matcher* m, const uint32_t* d_packed,
+                                                         uint64_t n_reads, uint32_t* d_results, void* stream);
+/* Same with ASCII rows on the device (encode fused into the kernel); d_lengths may be NULL. */
+FQTK_B200_API int fqtk_b200_matcher_assign_ascii_device(fqtk_b200_matcher* m, const uint8_t* d_ascii,
+                                                        uint64_t n_reads, uint64_t row_stride,
+                                                        const uint32_t* d_lengths, uint32_t* d_results, void* stream);
+/* encode() on the device: ASCII rows -> packed words (mod.rs:49-61). */
+FQTK_B200_API int fqtk_b200_pack_device(const uint8_t* d_ascii, uint64_t n_reads, uint32_t barcode_len,
+                                        uint64_t row_stride, uint32_t* d_packed, void* stream);
+/* encode() on the host for one sequence: out = ceil(len/8) u32 blocks.  Pure encoding, no matching. */
+FQTK_B200_API int fqtk_b200_encode_host(const uint8_t* bases, size_t len, uint32_t* out_blocks);
+
+/* ---- per-sample counts (DemuxMetric.templates, demux.rs:458,971,974): S+1 u64, last = unmatched ---- */
+FQTK_B200_API int fqtk_b200_matcher_counts(fqtk_b200_matcher* m, uint64_t* out_counts); /* syncs the device */
+FQTK_B200_API int fqtk_b200_matcher_counts_device(fqtk_b200_matcher* m, uint64_t** d_counts); /* for ncclAllReduce */
+FQTK_B200_API int fqtk_b200_matcher_reset_counts(fqtk_b200_matcher* m);
+
+/* ---- control / introspection ---- */
+FQTK_B200_API int fqtk_b200_matcher_set_mode(fqtk_b200_matcher* m, int mode); /* TABLE needs a built table */
+FQTK_B200_API uint64_t fqtk_b200_kernel_launches(void); /* kernels launched by this library in this process */
+FQTK_B200_API const char* fqtk_b200_last_error(void);
+FQTK_B200_API int fqtk_b200_device_count(void);
+
+/* ---- pinned host memory for the host-buffer calls ---- */
+FQTK_B200_API int fqtk_b200_host_alloc(void** ptr, size_t bytes);
+FQTK_B200_API int fqtk_b200_host_free(void* ptr);
+
+/* ---- deterministic synthetic workload; counter-based, identical on host and device ----
+ * Panel: S barcodes of length L over ACGT with pairwise Hamming distance >= min_distance (greedy, rejection);
+ * `n_degenerate` positions per barcode are then rewritten to IUPAC degenerate codes (cfg 5).
+ * Reads: read i depends only on (seed, i): 90 % true (uniform sample, degenerate positions resolved, per-base
+ * 0.5 % substitution, 0.2 % no-call), 8 % near-miss (plus 2-3 forced substitutions), 2 % uniform random L-mers. */
+FQTK_B200_API int fqtk_b200_synth_panel(uint64_t seed, uint32_t n_samples, uint32_t barcode_len,
+                                        uint32_t min_distance, uint32_t n_degenerate, uint8_t* out_panel_ascii);
+FQTK_B200_API int fqtk_b200_synth_reads_host(const uint8_t* panel_ascii, uint32_t n_samples, uint32_t barcode_len,
+                                             uint64_t seed, uint64_t first_read, uint64_t n_reads,
+                                             uint8_t* out_ascii /* n_reads * L */);
+FQTK_B200_API int fqtk_b200_synth_reads_device(const uint8_t* panel_ascii, uint32_t n_samples, uint32_t barcode_len,
+                                               uint64_t seed, uint64_t first_read, uint64_t n_reads,
+                                               uint8_t* d_ascii /* or NULL */, uint32_t* d_packed /* or NULL */,
+                                               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FQTK_B200_H */

@@ -1,0 +1,335 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+Bit-exact (integer / index work): result word per read and counts[S+1].  Needs a B200 (run via gpurun)."""
+import numpy as np
+import pytest
+
+import oracle
+from fqtk_b200 import BarcodeMatch, BarcodeMatcher, MatcherPanic, _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+MODES = [True, False]  # use_cache: True -> memo-table kernels, False -> brute-force kernels (rstest cases in the reference)
+
+
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available()
+    return torch
+
+
+def to_match(t):
+    return None if t is None else BarcodeMatch(*t)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the reference's own known-answer tests, through the mirrored interface
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("use_cache", MODES)
+def test_reference_assign_kats(kats, use_cache):
+    for case in kats["assign"]:
+        with BarcodeMatcher(case["barcodes"], case["max_mismatches"], case["min_mismatch_delta"], use_cache) as m:
+            assert m.assign(case["read"].encode()) == to_match(case["expect"]), case
+
+
+@pytest.mark.parametrize("use_cache", MODES)
+def test_reference_count_mismatches_kats_via_single_sample_panel(kats, use_cache):
+    # count_mismatches (barcode_matching.rs:89-110) is observable as best_mismatches against a 1-sample panel
+    for case in kats["count_mismatches"]:
+        if case["expected"] == "":
+            continue  # an empty barcode cannot be constructed (barcode_matching.rs:62-65)
+        with BarcodeMatcher([case["expected"]], 255, 0, use_cache) as m:
+            got = m.assign(case["observed"].encode())
+            assert got == BarcodeMatch(0, case["mismatches"], 255), case
+
+
+@pytest.mark.parametrize("use_cache", MODES)
+def test_reference_demux_caller_vectors(kats, use_cache):
+    for case in kats["demux_caller"]:
+        with BarcodeMatcher(case["barcodes"], case["max_mismatches"], case["min_mismatch_delta"], use_cache) as m:
+            reads = np.frombuffer("".join(case["reads"]).encode(), dtype=np.uint8).reshape(len(case["reads"]), -1)
+            res = m.assign_batch(reads)
+            got = [None if r == _lib.NONE else int(r) >> 16 for r in res]
+            assert got == case["expect_sample"], case["source"]
+            assert m.counts().tolist() == case["expect_counts"], case["source"]
+
+
+def test_matcher_instantiation(kats):
+    ok = kats["matcher_new"]["ok"]
+    BarcodeMatcher(ok["barcodes"], ok["max_mismatches"], ok["min_mismatch_delta"]).close()
+    with pytest.raises(MatcherPanic, match="Must provide at least one sample"):
+        BarcodeMatcher([], 2, 1)
+
+
+@pytest.mark.parametrize("use_cache", MODES)
+def test_length_rules(use_cache):
+    with BarcodeMatcher(["ACGTAC", "TTTTTT"], 1, 1, use_cache) as m:
+        assert m.assign(b"ACGTA") is None            # barcode_matching.rs:167-169
+        assert m.assign(b"") is None
+        with pytest.raises(MatcherPanic, match="differs from expected barcode"):
+            m.assign(b"ACGTACG")                      # :95-106
+        assert m.assign(b"NNNNNNN") is None           # no-call pre-filter (:170-172) fires before the panic
+        assert m.assign(b"ACGTAC") == BarcodeMatch(0, 0, 5)
+        assert m.counts().tolist() == [1, 0, 3]       # the failed call counted nothing
+        # batched with per-row lengths
+        rows = np.zeros((4, 8), dtype=np.uint8)
+        lens = np.array([6, 5, 6, 7], dtype=np.uint32)
+        for i, s in enumerate([b"ACGTAC", b"TTTTT", b"TTTTTA", b"NNNNNNN"]):
+            rows[i, :len(s)] = np.frombuffer(s, dtype=np.uint8)
+        m.reset_counts()
+        res = m.assign_batch(rows, lengths=lens)
+        assert [None if r == _lib.NONE else int(r) >> 16 for r in res] == [0, None, 1, None]
+        assert m.counts().tolist() == [1, 1, 2]
+        lens[3] = 8
+        rows[3] = np.frombuffer(b"ACGTACGT", dtype=np.uint8)
+        with pytest.raises(MatcherPanic):
+            m.assign_batch(rows, lengths=lens)
+        assert m.counts().tolist() == [1, 1, 2], "a failing batch counts nothing"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# randomized parity against the oracle: both kernel families, host ASCII path and device packed / ASCII paths
+# ---------------------------------------------------------------------------------------------------------
+ALPHABETS = {
+    "acgt": b"ACGT",
+    "acgtn": b"ACGTN",
+    "iupac": b"ACGTUMRWSYKVHDBNn.",
+    "dirty": b"ACGTNn.acgtRYKMXx-*0 ",
+}
+
+
+def random_panel(rng, S, L, alphabet):
+    seen, bcs = set(), []
+    guard = 0
+    while len(bcs) < S and guard < 100 * S:
+        guard += 1
+        if bcs and rng.random() < 0.4:
+            b = bytearray(bcs[int(rng.integers(0, len(bcs)))])
+            b[int(rng.integers(0, L))] = alphabet[int(rng.integers(0, len(alphabet)))]
+            b = bytes(b)
+        else:
+            b = bytes(alphabet[i] for i in rng.integers(0, len(alphabet), L))
+        if b not in seen:
+            seen.add(b)
+            bcs.append(b)
+    return bcs
+
+
+def random_reads(rng, bcs, L, n, alphabet):
+    panel = np.frombuffer(b"".join(bcs), dtype=np.uint8).reshape(len(bcs), L)
+    reads = panel[rng.integers(0, len(bcs), n)].copy()
+    nsub = rng.integers(0, 4, n)
+    for k in range(3):
+        rows = np.nonzero(nsub > k)[0]
+        reads[rows, rng.integers(0, L, rows.size)] = np.frombuffer(alphabet, dtype=np.uint8)[
+            rng.integers(0, len(alphabet), rows.size)]
+    rnd = rng.random(n) < 0.2
+    reads[rnd] = np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), (int(rnd.sum()), L))]
+    return reads
+
+
+def check_against_oracle(bcs, mm, delta, reads, use_cache, expect_mode=None):
+    torch = torch_cuda()
+    om = oracle.OracleMatcher(bcs, mm, delta, use_cache=True)
+    want, want_counts = om.assign_batch(reads, mode=0)
+    n, L = reads.shape
+    with BarcodeMatcher(bcs, mm, delta, use_cache) as m:
+        if expect_mode:
+            assert m.mode == expect_mode
+        # 1) reference-facing host-buffer call
+        got = m.assign_batch(reads)
+        bad = np.nonzero(got != want)[0]
+        assert bad.size == 0, (m.mode, bytes(reads[bad[0]]), hex(int(got[bad[0]])), hex(int(want[bad[0]])))
+        assert np.array_equal(m.counts(), want_counts)
+        # 2) HBM-resident packed call
+        m.reset_counts()
+        packed = synth.pack_host(reads)
+        d_packed = torch.from_numpy(packed.view(np.int32)).cuda()
+        d_res = torch.empty(n, dtype=torch.int32, device="cuda")
+        m.assign_packed_device(d_packed.data_ptr(), n, d_res.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got2 = d_res.cpu().numpy().view(np.uint32)
+        assert np.array_equal(got2, want)
+        assert np.array_equal(m.counts(), want_counts)
+        # 3) device ASCII call with a padded row stride
+        m.reset_counts()
+        stride = L + 3
+        padded = np.full((n, stride), ord("#"), dtype=np.uint8)
+        padded[:, :L] = reads
+        d_ascii = torch.from_numpy(padded).cuda()
+        d_res.zero_()
+        m.assign_ascii_device(d_ascii.data_ptr(), n, stride, d_res.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_res.cpu().numpy().view(np.uint32), want)
+        assert np.array_equal(m.counts(), want_counts)
+
+
+@pytest.mark.parametrize("use_cache", MODES)
+@pytest.mark.parametrize("seed", range(4))
+def test_fuzz_small_panels(seed, use_cache):
+    rng = np.random.default_rng(100 + seed)
+    for _ in range(12):
+        L = int(rng.choice([1, 2, 4, 7, 8, 9, 15, 16, 17, 20, 24, 31, 32]))
+        S = int(rng.choice([1, 2, 3, 8, 33, 100]))
+        pa = ALPHABETS[["acgt", "acgtn", "iupac"][int(rng.integers(0, 3))]]
+        ra = ALPHABETS[["acgt", "acgtn", "dirty"][int(rng.integers(0, 3))]]
+        bcs = random_panel(rng, S, L, pa)
+        mm = int(rng.choice([0, 1, 2, 3]))
+        delta = int(rng.choice([0, 1, 2, 3, 100]))
+        reads = random_reads(rng, bcs, L, 3000 + int(rng.integers(0, 7)), ra)
+        check_against_oracle(bcs, mm, delta, reads, use_cache)
+
+
+@pytest.mark.parametrize("use_cache", MODES)
+def test_fuzz_extreme_parameters(use_cache):
+    rng = np.random.default_rng(77)
+    for mm, delta in [(100, 0), (100, 3), (255, 255), (0, 0), (0, 255), (8, 1)]:
+        bcs = random_panel(rng, 20, 8, ALPHABETS["acgtn"])
+        reads = random_reads(rng, bcs, 8, 2000, ALPHABETS["dirty"])
+        check_against_oracle(bcs, mm, delta, reads, use_cache)
+
+
+def test_long_barcodes_take_the_generic_kernel():
+    rng = np.random.default_rng(5)
+    for L in (33, 40, 64, 100, 254):
+        bcs = random_panel(rng, 17, L, ALPHABETS["iupac"])
+        reads = random_reads(rng, bcs, L, 1500, ALPHABETS["dirty"])
+        check_against_oracle(bcs, 2, 1, reads, use_cache=True, expect_mode="brute")
+
+
+def test_many_samples_use_global_histogram_and_big_panel():
+    rng = np.random.default_rng(6)
+    S, L = 9000, 12  # S + 1 > 8192 shared-memory bins
+    panel = synth.make_panel(99, S, L, 3)
+    bcs = [bytes(r) for r in panel]
+    reads = random_reads(rng, bcs, L, 20000, ALPHABETS["acgtn"])
+    check_against_oracle(bcs, 1, 2, reads, use_cache=True, expect_mode="table")
+    check_against_oracle(bcs, 1, 2, reads, use_cache=False, expect_mode="brute")
+    # panel planes larger than shared memory: S * 16 B > 227 KB
+    S2 = 15000
+    panel2 = synth.make_panel(98, S2, 14, 3)
+    bcs2 = [bytes(r) for r in panel2]
+    reads2 = random_reads(rng, bcs2, 14, 8000, ALPHABETS["acgtn"])
+    check_against_oracle(bcs2, 1, 2, reads2, use_cache=False, expect_mode="brute")
+
+
+def test_table_budget_falls_back_to_brute():
+    L = _lib.lib()
+    try:
+        L.fqtk_b200_set_table_budget(10)
+        with BarcodeMatcher(["ACGTACGT", "TTTTACGT"], 1, 1, use_cache=True) as m:
+            assert m.mode == "brute"
+            assert m.assign(b"ACGTACGT") == BarcodeMatch(0, 0, 4)
+    finally:
+        L.fqtk_b200_set_table_budget(32 << 20)
+    with BarcodeMatcher(["NNNNNNNNNNNNNNNNNNNN", "ACGTACGTACGTACGTACGT"], 1, 0, use_cache=True) as m:
+        assert m.mode == "brute"  # a catch-all barcode's neighbourhood (5^20) is over any budget
+        assert m.assign(b"ACGTACGTACGTACGTACGT") == BarcodeMatch(0, 0, 0)  # tie: first index wins, delta 0 allows it
+
+
+def test_out_of_alphabet_reads_take_the_warp_cooperative_path():
+    """Reads with IUPAC / junk symbols are never in the memo table; every lane pattern of the slow path is hit."""
+    rng = np.random.default_rng(8)
+    cfg = synth.CONFIGS[3]
+    panel = synth.panel(cfg)
+    bcs = [bytes(r) for r in panel]
+    reads = synth.reads_host(panel, cfg.seed_reads, 0, 40000)
+    for frac in (0.01, 0.3, 1.0):
+        r = reads.copy()
+        rows = np.nonzero(rng.random(r.shape[0]) < frac)[0]
+        r[rows, rng.integers(0, 16, rows.size)] = np.frombuffer(b"RYKMSWBDHVXacgtn.-", dtype=np.uint8)[
+            rng.integers(0, 18, rows.size)]
+        check_against_oracle(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, r, use_cache=True, expect_mode="table")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE.json configs on their synthetic streams (reduced N against the oracle; full N by properties)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg_id,n", [(1, 10_000), (2, 300_000), (3, 300_000), (4, 200_000), (5, 120_000)])
+@pytest.mark.parametrize("use_cache", MODES)
+def test_configs_reduced_n(cfg_id, n, use_cache):
+    cfg = synth.CONFIGS[cfg_id]
+    panel = synth.panel(cfg)
+    reads = synth.reads_host(panel, cfg.seed_reads, 0, n)
+    check_against_oracle([bytes(r) for r in panel], cfg.max_mismatches, cfg.min_mismatch_delta, reads, use_cache,
+                         expect_mode="table" if use_cache else "brute")
+
+
+def test_synth_device_equals_host():
+    torch = torch_cuda()
+    for cfg_id in (2, 3, 5):
+        cfg = synth.CONFIGS[cfg_id]
+        panel = synth.panel(cfg)
+        n, first = 50_001, 123_456_789
+        host = synth.reads_host(panel, cfg.seed_reads, first, n)
+        d_ascii = torch.empty((n, cfg.barcode_len), dtype=torch.uint8, device="cuda")
+        d_packed = torch.empty((n, cfg.words_per_read), dtype=torch.int32, device="cuda")
+        synth.reads_device(panel, cfg.seed_reads, first, n, d_ascii.data_ptr(), d_packed.data_ptr(),
+                           torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_ascii.cpu().numpy(), host)
+        assert np.array_equal(d_packed.cpu().numpy().view(np.uint32), synth.pack_host(host))
+        # pack kernel = encode()
+        d_packed2 = torch.zeros_like(d_packed)
+        _lib.check(_lib.lib().fqtk_b200_pack_device(d_ascii.data_ptr(), n, cfg.barcode_len, cfg.barcode_len,
+                                                    d_packed2.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert torch.equal(d_packed, d_packed2)
+
+
+@pytest.mark.parametrize("cfg_id", [2, 3, 4, 5])
+def test_configs_full_size_properties(cfg_id):
+    """At BASELINE.json's full N: (i) table kernels == brute kernels read-for-read (checksum of the XOR and an
+    exact equality), (ii) counts sum to N and equal the histogram of the result words, (iii) strided sub-ranges
+    replayed on the host agree with the oracle, (iv) idempotence: a second pass doubles every count."""
+    torch = torch_cuda()
+    cfg = synth.CONFIGS[cfg_id]
+    panel = synth.panel(cfg)
+    bcs = [bytes(r) for r in panel]
+    free, _ = torch.cuda.mem_get_info()
+    n = cfg.n_reads
+    W = cfg.words_per_read
+    need = n * (4 * W + 8) + (2 << 30)
+    assert need < free, "full-size config must fit one B200"
+    stream = torch.cuda.current_stream().cuda_stream
+    d_packed = torch.empty((n, W), dtype=torch.int32, device="cuda")
+    synth.reads_device(panel, cfg.seed_reads, 0, n, 0, d_packed.data_ptr(), stream)
+    res_t = torch.empty(n, dtype=torch.int32, device="cuda")
+    res_b = torch.empty(n, dtype=torch.int32, device="cuda")
+    with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, True) as mt, \
+            BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, False) as mb:
+        assert mt.mode == "table" and mb.mode == "brute"
+        mt.assign_packed_device(d_packed.data_ptr(), n, res_t.data_ptr(), stream)
+        mb.assign_packed_device(d_packed.data_ptr(), n, res_b.data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert torch.equal(res_t, res_b)
+        ct, cb = mt.counts(), mb.counts()
+        assert np.array_equal(ct, cb)
+        assert int(ct.sum()) == n
+        # histogram of result words == counts
+        idx = torch.where(res_t == -1, torch.full_like(res_t, cfg.n_samples), (res_t >> 16) & 0xFFFF)
+        hist = torch.bincount(idx.to(torch.int64), minlength=cfg.n_samples + 1).cpu().numpy().astype(np.uint64)
+        assert np.array_equal(hist, ct)
+        del idx
+        # strided sub-ranges against the oracle
+        om = oracle.OracleMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, use_cache=True)
+        span = 20_000
+        for first in (0, n // 3 + 17, n - span):
+            host_reads = synth.reads_host(panel, cfg.seed_reads, first, span)
+            want, _ = om.assign_batch(host_reads)
+            got = res_t[first:first + span].cpu().numpy().view(np.uint32)
+            assert np.array_equal(got, want), (cfg_id, first)
+        # idempotence of the counters
+        mt.assign_packed_device(d_packed.data_ptr(), n, res_t.data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(mt.counts(), 2 * ct)
+        assert torch.equal(res_t, res_b)
+
+
+def test_kernel_launch_counter_moves():
+    from fqtk_b200.barcode_matching import kernel_launches
+
+    before = kernel_launches()
+    with BarcodeMatcher(["ACGT", "TTTT"], 1, 1) as m:
+        m.assign(b"ACGT")
+    assert kernel_launches() > before

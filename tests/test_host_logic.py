@@ -1,0 +1,159 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every symbol the header
+declares, the host encoder agrees with the oracle, the synthetic generator is deterministic and replayable, the
+sample-sheet mirror validates like the reference, and matching refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from fqtk_b200 import _lib, synth
+from fqtk_b200.barcode_matching import BarcodeMatcher, encode
+from fqtk_b200.samples import Sample, SampleGroup, SampleSheetError
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "fqtk_b200.h")).read()
+    declared = set(re.findall(r"FQTK_B200_API\s+[\w\s\*]+?\b(fqtk_b200_\w+)\s*\(", header))
+    assert len(declared) >= 20
+    assert declared == set(_lib.SYMBOLS)
+    L = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_product_does_not_link_or_import_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "fqtk_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "fqtk_oracle" not in text and "liboracle" not in text, f
+    header = open(os.path.join(ROOT, "include", "fqtk_b200.h")).read()
+    assert "oracle" not in header.lower()
+
+
+def test_encode_host_matches_oracle():
+    rng = np.random.default_rng(3)
+    alphabet = np.frombuffer(b"ACGTUMRWSYKVHDBNacgtumrwsykvhdbn.-*X019 \x00\xff", dtype=np.uint8)
+    for _ in range(500):
+        n = int(rng.integers(0, 70))
+        s = bytes(rng.choice(alphabet, n))
+        want, _ = oracle.encode(s)
+        assert encode(s) == want
+
+
+def test_pack_host_matches_encode():
+    rng = np.random.default_rng(4)
+    for L in (1, 7, 8, 9, 16, 20, 33):
+        reads = rng.choice(np.frombuffer(b"ACGTNacgtn.RYKM-", dtype=np.uint8), size=(50, L))
+        packed = synth.pack_host(reads)
+        for r, p in zip(reads, packed):
+            assert encode(bytes(r)) == [int(x) for x in p]
+
+
+@pytest.mark.parametrize("cfg_id", [1, 2, 3, 4])
+def test_synth_panel_properties(cfg_id):
+    cfg = synth.CONFIGS[cfg_id]
+    p = synth.panel(cfg)
+    assert p.shape == (cfg.n_samples, cfg.barcode_len)
+    assert set(np.unique(p).tolist()) <= set(b"ACGT")
+    assert np.array_equal(p, synth.panel(cfg)), "deterministic"
+    # pairwise Hamming distance >= 3 (sampled for the big panel)
+    rows = p if cfg.n_samples <= 400 else p[:400]
+    d = (rows[:, None, :] != rows[None, :, :]).sum(-1)
+    d[np.arange(len(rows)), np.arange(len(rows))] = 99
+    assert d.min() >= cfg.min_distance
+
+
+def test_synth_panel_cfg5_is_a_valid_degenerate_sheet():
+    cfg = synth.CONFIGS[5]
+    p = synth.panel(cfg)
+    strings = [bytes(r).decode() for r in p]
+    group = SampleGroup.from_samples([Sample(f"s{i}", b, i) for i, b in enumerate(strings)])  # samples.rs validations
+    assert len(group.samples) == cfg.n_samples
+    degenerate = np.isin(p, np.frombuffer(b"RYSWKMBDHVN", dtype=np.uint8)).sum(1)
+    assert (degenerate == cfg.n_degenerate).all()
+
+
+def test_synth_reads_are_counter_based():
+    cfg = synth.CONFIGS[3]
+    p = synth.panel(cfg)
+    whole = synth.reads_host(p, cfg.seed_reads, 0, 5000)
+    part = synth.reads_host(p, cfg.seed_reads, 1234, 777)
+    assert np.array_equal(whole[1234:1234 + 777], part)
+    assert set(np.unique(whole).tolist()) <= set(b"ACGTN")
+    other = synth.reads_host(p, cfg.seed_reads + 1, 0, 5000)
+    assert not np.array_equal(whole, other)
+
+
+def test_synth_mix_matches_spec():
+    """~90 % true / 8 % near-miss / 2 % random: judged through the oracle's view of the reads."""
+    cfg = synth.CONFIGS[3]
+    p = synth.panel(cfg)
+    reads = synth.reads_host(p, cfg.seed_reads, 0, 40000)
+    m = oracle.OracleMatcher([bytes(r) for r in p], cfg.max_mismatches, cfg.min_mismatch_delta)
+    res, counts = m.assign_batch(reads)
+    matched = float((res != oracle.NONE).mean())
+    assert 0.85 < matched < 0.93
+    exact = float(((res & 0xFF00) == 0)[res != oracle.NONE].mean())
+    assert exact > 0.85
+    assert int(counts.sum()) == reads.shape[0]
+    per_sample = counts[:-1].astype(float)
+    assert per_sample.min() > 0.4 * per_sample.mean()
+
+
+def test_sample_sheet_validations(tmp_path):
+    assert Sample.new(0, "s_1_example_name", "GATTANN").barcode == "GATTANN"  # samples.rs:205-211
+    with pytest.raises(SampleSheetError, match="Sample name cannot be empty"):
+        Sample.new(0, "", "ACGT")
+    with pytest.raises(SampleSheetError, match="Sample barcode cannot be empty"):
+        Sample.new(0, "s", "")
+    with pytest.raises(SampleSheetError, match="All sample barcode bases"):
+        Sample.new(0, "s", "ACGTX")
+    with pytest.raises(SampleSheetError, match="All sample barcode bases"):
+        Sample.new(0, "s", "acgt")  # lowercase is invalid in the sheet (mod.rs:121-124)
+    with pytest.raises(SampleSheetError, match="Must provide one or more sample"):
+        SampleGroup.from_samples([])
+    with pytest.raises(SampleSheetError, match="Each sample name must be unique"):
+        SampleGroup.from_samples([Sample("a", "ACGT"), Sample("a", "TTTT")])
+    with pytest.raises(SampleSheetError, match="Each sample barcode must be unique"):
+        SampleGroup.from_samples([Sample("a", "ACGT"), Sample("b", "ACGT")])
+    with pytest.raises(SampleSheetError, match="All barcodes must have the same length"):
+        SampleGroup.from_samples([Sample("a", "ACGT"), Sample("b", "ACGTA")])
+    f = tmp_path / "sheet.tsv"
+    f.write_text("sample_id\tbarcode\nsample1\tGATTACA\nsample2\tCATGCTA\n\n\n")  # samples.rs:160-199
+    g = SampleGroup.from_file(str(f))
+    assert [s.sample_id for s in g.samples] == ["sample1", "sample2"]
+    assert g.barcodes() == ["GATTACA", "CATGCTA"]
+    assert [s.ordinal for s in g.samples] == [0, 1]
+    f.write_text("sample_id,barcode\nsample1,GATTACA\n")  # samples.rs:213-233
+    with pytest.raises(SampleSheetError, match="DelimFileHeaderError"):
+        SampleGroup.from_file(str(f))
+    f.write_text("sample1\tGATTACA\nsample2\tCATGCTA\n")  # no header, samples.rs:238-255
+    with pytest.raises(SampleSheetError, match="DelimFileHeaderError"):
+        SampleGroup.from_file(str(f))
+
+
+def test_matcher_argument_errors_without_touching_a_gpu():
+    from fqtk_b200.barcode_matching import MatcherPanic
+
+    with pytest.raises(MatcherPanic, match="Must provide at least one sample"):
+        BarcodeMatcher([], 2, 1)
+    with pytest.raises(MatcherPanic, match="Sample barcode cannot be empty string"):
+        BarcodeMatcher([""], 2, 1)
+    with pytest.raises(OverflowError):
+        BarcodeMatcher(["ACGT"], 256, 1)  # demux.rs:923-924: u8::try_from
+
+
+def test_no_cpu_fallback_when_no_gpu_is_visible():
+    if _lib.lib().fqtk_b200_device_count() > 0:
+        pytest.skip("a GPU is visible here")
+    with pytest.raises(_lib.Fqtk_b200Error) as ei:
+        BarcodeMatcher(["ACGT", "TTTT"], 1, 1)
+    assert ei.value.code == _lib.ERR_CUDA
+    assert "no CPU fallback" in ei.value.message
