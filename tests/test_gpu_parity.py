@@ -219,7 +219,7 @@ def test_table_budget_falls_back_to_brute():
         L.fqtk_b200_set_table_budget(10)
         with BarcodeMatcher(["ACGTACGT", "TTTTACGT"], 1, 1, use_cache=True) as m:
             assert m.mode == "brute"
-            assert m.assign(b"ACGTACGT") == BarcodeMatch(0, 0, 4)
+            assert m.assign(b"ACGTACGT") == BarcodeMatch(0, 0, 3)
     finally:
         L.fqtk_b200_set_table_budget(32 << 20)
     with BarcodeMatcher(["NNNNNNNNNNNNNNNNNNNN", "ACGTACGTACGTACGTACGT"], 1, 0, use_cache=True) as m:
