@@ -36,7 +36,7 @@ class MatcherInfo(C.Structure):
         ("n_samples", C.c_uint32), ("barcode_len", C.c_uint32), ("words_per_read", C.c_uint32),
         ("max_ns_in_barcodes", C.c_uint32), ("mode", C.c_uint32), ("device", C.c_uint32),
         ("table_entries", C.c_uint64), ("table_slots", C.c_uint64), ("table_bytes", C.c_uint64),
-        ("table_candidates", C.c_uint64),
+        ("table_candidates", C.c_uint64), ("tier_entries", C.c_uint64), ("tier_slots", C.c_uint64),
     ]
 
 

@@ -32,6 +32,7 @@ namespace {
 
 thread_local std::string g_err;
 uint64_t g_table_budget = 32ull << 20;
+size_t g_tier_budget_bytes = 96u << 10;  // shared memory the hot tier may take per CTA
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -61,6 +62,9 @@ struct fqtk_b200_matcher {
     uint4* d_planes = nullptr;
     uint32_t* d_not_exp = nullptr;
     uint32_t* d_table = nullptr;
+    uint32_t* d_tier_keys = nullptr;
+    uint32_t* d_tier_vals = nullptr;
+    uint64_t tier_entries = 0;
     unsigned long long* d_counts = nullptr;
     fq::MatchParams params{};
     int mode = FQTK_B200_MODE_BRUTE;
@@ -126,26 +130,82 @@ struct Enumerator {
     }
 };
 
+// Insert into the bucketised memo table (kernels.h: 32-byte buckets, linear probing over buckets).
 template <int W>
-void host_insert(std::vector<uint32_t>& table, uint32_t slot_mask, const uint32_t* key, uint32_t val,
+void host_insert(std::vector<uint32_t>& table, uint32_t n_buckets, const uint32_t* key, uint32_t val,
                  uint64_t& inserted) {
-    const int EW = fq::table_entry_words(W), VI = fq::table_value_index(W);
     uint32_t kw[W];
     for (int k = 0; k < W; k++) kw[k] = key[k];
-    uint32_t slot = fq::hash_key<W>(kw) & slot_mask;
+    uint32_t b = fq::bucket_of_hash(fq::hash_key<W>(kw), n_buckets);
+    constexpr int EPB = W <= 3 ? 2 : 1, EW = 8 / EPB, VI = W <= 3 ? 3 : 4;
     for (;;) {
-        uint32_t* ent = table.data() + (size_t)slot * EW;
-        if (ent[VI] == fq::NONE) {
-            for (int k = 0; k < W; k++) ent[k] = kw[k];
-            ent[VI] = val;
-            inserted++;
-            return;
+        for (int e = 0; e < EPB; e++) {
+            uint32_t* ent = table.data() + (size_t)b * 8 + (size_t)e * EW;
+            if (ent[VI] == fq::NONE) {
+                for (int k = 0; k < EW; k++) ent[k] = 0u;
+                for (int k = 0; k < W; k++) ent[k] = kw[k];
+                ent[VI] = val;
+                inserted++;
+                return;
+            }
+            bool same = true;
+            for (int k = 0; k < W; k++) same = same && ent[k] == kw[k];
+            if (same) return;  // the same string reached from two barcodes: identical value by construction
         }
-        bool same = true;
-        for (int k = 0; k < W; k++) same = same && ent[k] == kw[k];
-        if (same) return;  // the same string reached from two barcodes: identical value by construction
-        slot = (slot + 1u) & slot_mask;
+        b = (b + 1u == n_buckets) ? 0u : b + 1u;
     }
+}
+
+// Hot tier: 2-choice cuckoo over the entries whose best distance is 0.  It is only a cache of the memo table, so a
+// key that cannot be placed (or does not fit the shared-memory budget) is simply left out.
+template <int W>
+void build_tier(const std::vector<uint32_t>& keys, const std::vector<uint32_t>& res, uint64_t n, size_t budget_bytes,
+                std::vector<uint32_t>& tkeys, std::vector<uint32_t>& tvals, uint32_t& slots_out, uint64_t& placed) {
+    constexpr int KP = W <= 2 ? W : 4;
+    uint64_t n_hot = 0;
+    for (uint64_t t = 0; t < n; t++) n_hot += (res[t] != fq::NONE && ((res[t] >> 8) & 0xFFu) == 0u);
+    uint32_t slots = 16;
+    while ((uint64_t)slots * 2 < n_hot * 5 && slots < 65536u) slots <<= 1;           // load <= 0.4
+    while (slots > 16 && (size_t)slots * (KP + 1) * 4 > budget_bytes) slots >>= 1;   // shared-memory budget
+    placed = 0;
+    slots_out = 0;
+    if (n_hot == 0 || (size_t)slots * (KP + 1) * 4 > budget_bytes) return;
+    const uint32_t mask = slots - 1;
+    tkeys.assign((size_t)slots * KP, 0xFFFFFFFFu);
+    tvals.assign(slots, fq::NONE);
+    const uint64_t cap = (uint64_t)slots * 45 / 100;
+    for (uint64_t t = 0; t < n && placed < cap; t++) {
+        if (res[t] == fq::NONE || ((res[t] >> 8) & 0xFFu) != 0u) continue;
+        uint32_t ck[KP], cv = res[t];
+        for (int k = 0; k < KP; k++) ck[k] = k < W ? keys[t * W + k] : 0u;
+        bool done = false;
+        for (int kick = 0; kick < 256 && !done; kick++) {
+            uint32_t kw[W];
+            for (int k = 0; k < W; k++) kw[k] = ck[k];
+            const uint32_t h = fq::hash_key<W>(kw);
+            const uint32_t s[2] = {fq::tier_slot1(h, mask), fq::tier_slot2(h, mask)};
+            for (int c = 0; c < 2 && !done; c++) {  // already there (duplicate candidate)?
+                bool same = tvals[s[c]] != fq::NONE;
+                for (int k = 0; k < KP; k++) same = same && tkeys[(size_t)s[c] * KP + k] == ck[k];
+                if (same) done = true;
+            }
+            if (done) break;
+            for (int c = 0; c < 2 && !done; c++) {
+                if (tvals[s[c]] == fq::NONE) {
+                    for (int k = 0; k < KP; k++) tkeys[(size_t)s[c] * KP + k] = ck[k];
+                    tvals[s[c]] = cv;
+                    placed++;
+                    done = true;
+                }
+            }
+            if (done) break;
+            const uint32_t victim = s[(kick ^ (h >> 7)) & 1u];  // evict one of the two residents and carry it on
+            for (int k = 0; k < KP; k++) std::swap(ck[k], tkeys[(size_t)victim * KP + k]);
+            std::swap(cv, tvals[victim]);
+        }
+        // not placed after 256 kicks: whichever key is in hand stays out of the tier (it is still in the memo table)
+    }
+    slots_out = slots;
 }
 
 int build_table(fqtk_b200_matcher* m) {
@@ -182,29 +242,52 @@ int build_table(fqtk_b200_matcher* m) {
 
     uint64_t n_some = 0;
     for (uint64_t t = 0; t < n; t++) n_some += res[t] != fq::NONE;
-    uint64_t slots = 1024;
-    while (slots < 2 * n_some) slots <<= 1;  // load factor <= 0.5
-    const int EW = fq::table_entry_words((int)W);
-    std::vector<uint32_t> table((size_t)slots * EW, 0xFFFFFFFFu);
+    const int EPB = fq::table_entries_per_bucket((int)W);
+    uint64_t buckets64 = (n_some * 100 + 45 * EPB - 1) / (45 * EPB);  // load factor <= 0.45
+    if (buckets64 < 64) buckets64 = 64;
+    if (buckets64 >= (1ull << 31)) return 1;
+    const uint32_t n_buckets = (uint32_t)buckets64;
+    std::vector<uint32_t> table((size_t)n_buckets * 8, 0xFFFFFFFFu);
     uint64_t inserted = 0;
-    const uint32_t mask = (uint32_t)(slots - 1);
     for (uint64_t t = 0; t < n; t++) {
         if (res[t] == fq::NONE) continue;
         const uint32_t* key = keys.data() + t * W;
         switch (W) {
-            case 1: host_insert<1>(table, mask, key, res[t], inserted); break;
-            case 2: host_insert<2>(table, mask, key, res[t], inserted); break;
-            case 3: host_insert<3>(table, mask, key, res[t], inserted); break;
-            default: host_insert<4>(table, mask, key, res[t], inserted); break;
+            case 1: host_insert<1>(table, n_buckets, key, res[t], inserted); break;
+            case 2: host_insert<2>(table, n_buckets, key, res[t], inserted); break;
+            case 3: host_insert<3>(table, n_buckets, key, res[t], inserted); break;
+            default: host_insert<4>(table, n_buckets, key, res[t], inserted); break;
         }
     }
     CU(cudaMalloc(&m->d_table, table.size() * 4));
     CU(cudaMemcpy(m->d_table, table.data(), table.size() * 4, cudaMemcpyHostToDevice));
     m->table_entries = inserted;
-    m->table_slots = slots;
+    m->table_slots = (uint64_t)n_buckets * EPB;
     m->table_bytes = table.size() * 4;
     m->params.table = m->d_table;
-    m->params.slot_mask = mask;
+    m->params.n_buckets = n_buckets;
+
+    // hot tier for shared memory
+    std::vector<uint32_t> tkeys, tvals;
+    uint32_t tslots = 0;
+    uint64_t placed = 0;
+    const size_t budget = g_tier_budget_bytes;
+    switch (W) {
+        case 1: build_tier<1>(keys, res, n, budget, tkeys, tvals, tslots, placed); break;
+        case 2: build_tier<2>(keys, res, n, budget, tkeys, tvals, tslots, placed); break;
+        case 3: build_tier<3>(keys, res, n, budget, tkeys, tvals, tslots, placed); break;
+        default: build_tier<4>(keys, res, n, budget, tkeys, tvals, tslots, placed); break;
+    }
+    if (tslots) {
+        CU(cudaMalloc(&m->d_tier_keys, tkeys.size() * 4));
+        CU(cudaMemcpy(m->d_tier_keys, tkeys.data(), tkeys.size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&m->d_tier_vals, tvals.size() * 4));
+        CU(cudaMemcpy(m->d_tier_vals, tvals.data(), tvals.size() * 4, cudaMemcpyHostToDevice));
+        m->params.tier_keys = m->d_tier_keys;
+        m->params.tier_vals = m->d_tier_vals;
+        m->params.tier_slots = tslots;
+        m->tier_entries = placed;
+    }
     return 0;
 }
 
@@ -363,7 +446,10 @@ int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t S, uint32_t L,
     m->params.max_mm = max_mm;
     m->params.min_delta = min_delta;
     m->params.last_pad = fq::last_word_pad_for_len(L);
-    m->params.slot_mask = 0;
+    m->params.n_buckets = 0;
+    m->params.tier_keys = nullptr;
+    m->params.tier_vals = nullptr;
+    m->params.tier_slots = 0;
     m->mode = FQTK_B200_MODE_BRUTE;
     if (use_cache && W <= (uint32_t)fq::MAX_FAST_WORDS) {
         rc = build_table(m);
@@ -390,6 +476,8 @@ void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m) {
     if (m->d_planes) cudaFree(m->d_planes);
     if (m->d_not_exp) cudaFree(m->d_not_exp);
     if (m->d_table) cudaFree(m->d_table);
+    if (m->d_tier_keys) cudaFree(m->d_tier_keys);
+    if (m->d_tier_vals) cudaFree(m->d_tier_vals);
     if (m->d_counts) cudaFree(m->d_counts);
     delete m;
 }
@@ -406,6 +494,8 @@ int fqtk_b200_matcher_get_info(const fqtk_b200_matcher* m, fqtk_b200_matcher_inf
     info->table_slots = m->table_slots;
     info->table_bytes = m->table_bytes;
     info->table_candidates = m->table_candidates;
+    info->tier_entries = m->tier_entries;
+    info->tier_slots = m->params.tier_slots;
     return FQTK_B200_OK;
 }
 

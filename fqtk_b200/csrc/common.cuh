@@ -107,6 +107,14 @@ FQ_HD uint32_t hash_key(const uint32_t (&w)[W]) {
     return h;
 }
 
+// Where a key lives: memo-table bucket (global memory) and the two candidate slots of the shared-memory hot tier,
+// all derived from the one 32-bit hash.
+FQ_HD uint32_t bucket_of_hash(uint32_t h, uint32_t n_buckets) {                    // fast range: [0, n_buckets)
+    return (uint32_t)(((uint64_t)(h * 0x9E3779B1u) * (uint64_t)n_buckets) >> 32);
+}
+FQ_HD uint32_t tier_slot1(uint32_t h, uint32_t mask) { return h & mask; }
+FQ_HD uint32_t tier_slot2(uint32_t h, uint32_t mask) { return (h >> 16) & mask; }  // tier_slots <= 65536
+
 // Running best / second-best on keys (distance << 16 | sample index): keys are unique per sample, so plain
 // min / second-min on the key gives min distance, FIRST index among ties (strict '<' at
 // barcode_matching.rs:132) and the second-smallest distance with multiplicity (:140).

@@ -29,6 +29,7 @@ void count_launch() { g_launches.fetch_add(1); }
 constexpr uint32_t HIST_SMEM_BINS = 8192;  // S + 1 <= this: CTA-private histogram lives in shared memory
 constexpr int BRUTE_THREADS = 512;
 constexpr int PROBE_THREADS = 256;
+constexpr int PROBE2_THREADS = 512;
 
 // ------------------------------------------------------------------------------------------------------
 // read loaders
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(256) k_brute_long(const MatchParams p, const R
 }
 
 // ------------------------------------------------------------------------------------------------------
-// k_probe: memo-table lookup, warp-cooperative brute force for out-of-alphabet reads
+// memo-table kernels
 // ------------------------------------------------------------------------------------------------------
 template <int W>
 FQ_D uint32_t warp_brute_one(const MatchParams& p, const uint32_t (&w)[W], uint32_t lane) {
@@ -237,34 +238,37 @@ FQ_D uint32_t warp_brute_one(const MatchParams& p, const uint32_t (&w)[W], uint3
     return decide(k1, k2, p.max_mm, p.min_delta);
 }
 
-// One table lookup.  Returns true on a hit (res = stored Some(..) word); false when an empty slot ends the probe.
+// One 32-byte bucket = one sector, fetched with a single 256-bit load (LDG.E.ENL2.256 on sm_100a).
+FQ_D void load_bucket(const uint32_t* __restrict__ table, uint32_t bucket, uint32_t (&e)[8]) {
+    const uint32_t* q = table + (size_t)bucket * TABLE_BUCKET_WORDS;
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(e[0]), "=r"(e[1]), "=r"(e[2]), "=r"(e[3]), "=r"(e[4]), "=r"(e[5]), "=r"(e[6]), "=r"(e[7])
+                 : "l"(q));
+}
+
+// One memo-table lookup (bucketised linear probing; an empty entry in a bucket ends the probe).
+// Returns true on a hit (res = stored Some(..) word).
 template <int W>
-FQ_D bool table_lookup(const MatchParams& p, const uint32_t (&w)[W], uint32_t& res) {
-    uint32_t slot = hash_key<W>(w) & p.slot_mask;
+FQ_D bool table_lookup(const MatchParams& p, const uint32_t (&w)[W], uint32_t h, uint32_t& res) {
+    uint32_t b = bucket_of_hash(h, p.n_buckets);
     for (;;) {
-        if constexpr (W == 1) {
-            const uint2 e = __ldg(reinterpret_cast<const uint2*>(p.table) + slot);
-            if (e.x == w[0] && e.y != NONE) { res = e.y; return true; }
-            if (e.y == NONE) return false;
-        } else if constexpr (W == 2) {
-            const uint4 e = __ldg(reinterpret_cast<const uint4*>(p.table) + slot);
-            if (e.x == w[0] && e.y == w[1] && e.z != NONE) { res = e.z; return true; }
-            if (e.z == NONE) return false;
-        } else if constexpr (W == 3) {
-            const uint4 e = __ldg(reinterpret_cast<const uint4*>(p.table) + slot);
-            if (e.x == w[0] && e.y == w[1] && e.z == w[2] && e.w != NONE) { res = e.w; return true; }
-            if (e.w == NONE) return false;
+        uint32_t e[8];
+        load_bucket(p.table, b, e);
+        if constexpr (W <= 3) {
+            const uint32_t k0 = w[0], k1 = W > 1 ? w[W > 1 ? 1 : 0] : 0u, k2 = W > 2 ? w[W > 2 ? 2 : 0] : 0u;
+            if (e[0] == k0 && e[1] == k1 && e[2] == k2 && e[3] != NONE) { res = e[3]; return true; }
+            if (e[4] == k0 && e[5] == k1 && e[6] == k2 && e[7] != NONE) { res = e[7]; return true; }
+            if (e[3] == NONE || e[7] == NONE) return false;
         } else {
-            const uint4 e = __ldg(reinterpret_cast<const uint4*>(p.table) + 2u * (size_t)slot);
-            const uint32_t v = __ldg(p.table + 8u * (size_t)slot + 4u);
-            if (e.x == w[0] && e.y == w[1] && e.z == w[2] && e.w == w[3] && v != NONE) { res = v; return true; }
-            if (v == NONE) return false;
+            if (e[0] == w[0] && e[1] == w[1] && e[2] == w[2] && e[3] == w[3] && e[4] != NONE) { res = e[4]; return true; }
+            if (e[4] == NONE) return false;
         }
-        slot = (slot + 1u) & p.slot_mask;
+        b = (b + 1u == p.n_buckets) ? 0u : b + 1u;
     }
 }
 
-template <int W, int R, bool ASCII>
+// k_probe: one read per thread; the ASCII (host-batch / e2e) route and the fallback for unaligned device buffers.
+template <int W, bool ASCII>
 __global__ void __launch_bounds__(PROBE_THREADS) k_probe(const MatchParams p, const ReadSource src,
                                                          uint32_t* __restrict__ results) {
     extern __shared__ uint4 s_dyn[];
@@ -276,80 +280,199 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe(const MatchParams p, co
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t n_groups = (src.n + R - 1) / R;
     const uint64_t total = (uint64_t)gridDim.x * blockDim.x;
     // warp-uniform trip count so the whole warp is present for the cooperative slow path
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < src.n; base += total) {
+        const uint64_t i = base + lane;
+        const bool valid = i < src.n;
+        uint32_t w[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) w[k] = 0u;
+        bool row_ok = true;
+        if (valid) {
+            if constexpr (ASCII)
+                row_ok = load_ascii<W>(src, i, p.L, s_lut, w);
+            else
+                load_packed<W>(src.packed, i, w);
+        }
+        uint32_t res = NONE;
+        bool slow = false;
+        if (valid && row_ok) {
+            if (!table_lookup<W>(p, w, hash_key<W>(w), res)) {
+                res = NONE;
+                slow = !read_in_table_alphabet<W>(w, p.last_pad);
+            }
+        }
+        uint32_t pending = __ballot_sync(0xFFFFFFFFu, slow);
+        while (pending) {
+            const int src_lane = __ffs(pending) - 1;
+            pending &= pending - 1u;
+            uint32_t bw[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) bw[k] = __shfl_sync(0xFFFFFFFFu, w[k], src_lane);
+            const uint32_t out = warp_brute_one<W>(p, bw, lane);
+            if ((int)lane == src_lane) res = out;
+        }
+        if (valid) {
+            results[i] = res;
+            cnt.add(res);
+        }
+    }
+    cnt.flush();
+}
+
+// k_probe2: the HBM-resident packed route.  Four reads per thread (W x LDG.128, one STG.128), three tiers:
+//   1. hot tier in SHARED memory: the table entries whose best distance is 0 (the barcodes themselves and their
+//      expansions), 2-choice cuckoo -> two independent LDS per read, no loop.  ~80 % of real reads end here.
+//   2. the remaining reads of the warp (all four slots) are compacted into a per-warp shared-memory queue so that
+//      the global memo-table probe, the alphabet test and the result write-back run once per ~32 such reads
+//      instead of once per slot with mostly idle lanes.
+//   3. reads outside the table's alphabet: warp-cooperative brute force (same as k_probe).
+constexpr int PROBE2_R = 4;
+constexpr int PROBE2_QUEUE = 32 * PROBE2_R;
+
+template <int W>
+__global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, const ReadSource src,
+                                                           uint32_t* __restrict__ results) {
+    constexpr int R = PROBE2_R;
+    constexpr int KP = W <= 2 ? W : 4;
+    extern __shared__ uint4 s_dyn[];
+    // layout: tier keys | tier vals | per-warp queues (keys, results) | histogram
+    uint32_t* s_tkeys = reinterpret_cast<uint32_t*>(s_dyn);
+    uint32_t* s_tvals = s_tkeys + (size_t)p.tier_slots * KP;
+    uint32_t* s_queue = s_tvals + p.tier_slots;
+    const uint32_t n_warps = blockDim.x >> 5;
+    uint32_t* s_hist = s_queue + (size_t)n_warps * PROBE2_QUEUE * (W + 1);
+
+    for (uint32_t t = threadIdx.x; t < p.tier_slots * KP; t += blockDim.x) s_tkeys[t] = __ldg(p.tier_keys + t);
+    for (uint32_t t = threadIdx.x; t < p.tier_slots; t += blockDim.x) s_tvals[t] = __ldg(p.tier_vals + t);
+    Counter cnt;
+    cnt.init(s_hist, p);
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    uint32_t* q_keys = s_queue + (size_t)(threadIdx.x >> 5) * PROBE2_QUEUE * (W + 1);
+    uint32_t* q_res = q_keys + PROBE2_QUEUE * W;
+    const uint32_t tmask = p.tier_slots - 1u;
+    const bool has_tier = p.tier_slots != 0u;
+
+    const uint64_t n_groups = (src.n + R - 1) / R;
+    const uint64_t total = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t gbase = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); gbase < n_groups; gbase += total) {
         const uint64_t g = gbase + lane;
         uint32_t w[R][W];
         uint32_t res[R];
-        bool valid[R], row_ok[R];
+        bool valid[R];
         const bool full = (g + 1) * R <= src.n;
-
-        if constexpr (!ASCII && R == 4) {
-            if (full) {  // 4 reads = W x 16 B, one LDG.128 each, fully coalesced across the warp
-                uint32_t flat[4 * W];
+        if (full) {  // 4 reads = W x 16 B, one LDG.128 each, fully coalesced across the warp
+            uint32_t flat[R * W];
 #pragma unroll
-                for (int v = 0; v < W; v++) {
-                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(src.packed) + g * W + v);
-                    flat[4 * v + 0] = q.x;
-                    flat[4 * v + 1] = q.y;
-                    flat[4 * v + 2] = q.z;
-                    flat[4 * v + 3] = q.w;
-                }
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-#pragma unroll
-                    for (int k = 0; k < W; k++) w[r][k] = flat[r * W + k];
-                    valid[r] = true;
-                    row_ok[r] = true;
-                }
+            for (int v = 0; v < W; v++) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(src.packed) + g * W + v);
+                flat[4 * v + 0] = q.x;
+                flat[4 * v + 1] = q.y;
+                flat[4 * v + 2] = q.z;
+                flat[4 * v + 3] = q.w;
             }
-        }
-        if (ASCII || R != 4 || !full) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+#pragma unroll
+                for (int k = 0; k < W; k++) w[r][k] = flat[r * W + k];
+                valid[r] = true;
+            }
+        } else {
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const uint64_t i = g * R + r;
                 valid[r] = i < src.n;
-                row_ok[r] = true;
 #pragma unroll
-                for (int k = 0; k < W; k++) w[r][k] = 0u;
-                if (valid[r]) {
-                    if constexpr (ASCII)
-                        row_ok[r] = load_ascii<W>(src, i, p.L, s_lut, w[r]);
-                    else
-                        load_packed<W>(src.packed, i, w[r]);
+                for (int k = 0; k < W; k++) w[r][k] = valid[r] ? __ldg(src.packed + i * W + k) : 0u;
+            }
+        }
+
+        // ---- tier 1: shared-memory cuckoo probe ----
+        bool pend[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            res[r] = NONE;
+            pend[r] = valid[r];
+            if (has_tier && valid[r]) {
+                const uint32_t hsh = hash_key<W>(w[r]);
+                const uint32_t s1 = tier_slot1(hsh, tmask), s2 = tier_slot2(hsh, tmask);
+                bool m1, m2;
+                if constexpr (KP == 1) {
+                    m1 = s_tkeys[s1] == w[r][0];
+                    m2 = s_tkeys[s2] == w[r][0];
+                } else if constexpr (KP == 2) {
+                    const uint2 a = reinterpret_cast<const uint2*>(s_tkeys)[s1];
+                    const uint2 b = reinterpret_cast<const uint2*>(s_tkeys)[s2];
+                    m1 = a.x == w[r][0] && a.y == w[r][1];
+                    m2 = b.x == w[r][0] && b.y == w[r][1];
+                } else {
+                    const uint4 a = reinterpret_cast<const uint4*>(s_tkeys)[s1];
+                    const uint4 b = reinterpret_cast<const uint4*>(s_tkeys)[s2];
+                    const uint32_t k3 = W > 3 ? w[r][W > 3 ? 3 : 0] : 0u;
+                    m1 = a.x == w[r][0] && a.y == w[r][1] && a.z == w[r][2] && a.w == k3;
+                    m2 = b.x == w[r][0] && b.y == w[r][1] && b.z == w[r][2] && b.w == k3;
+                }
+                if (m1 || m2) {
+                    const uint32_t v = s_tvals[m1 ? s1 : s2];
+                    if (v != NONE) {  // an empty slot's all-ones key can equal an all-N read
+                        res[r] = v;
+                        pend[r] = false;
+                    }
                 }
             }
         }
 
-        bool slow[R];
+        // ---- tier 2: compact the warp's remaining reads into its queue ----
+        uint32_t qcount = 0;  // warp-uniform
+        uint32_t qi[R];
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            res[r] = NONE;
-            slow[r] = false;
-            if (valid[r] && row_ok[r]) {
-                if (!table_lookup<W>(p, w[r], res[r])) {
-                    res[r] = NONE;
-                    slow[r] = !read_in_table_alphabet<W>(w[r], p.last_pad);
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pend[r]);
+            qi[r] = qcount + __popc(bal & lane_lt);
+            if (pend[r]) {
+#pragma unroll
+                for (int k = 0; k < W; k++) q_keys[qi[r] * W + k] = w[r][k];
+            }
+            qcount += __popc(bal);
+        }
+        __syncwarp();
+        for (uint32_t qb = 0; qb < qcount; qb += 32u) {
+            const uint32_t q = qb + lane;
+            const bool active = q < qcount;
+            uint32_t kw[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) kw[k] = active ? q_keys[q * W + k] : 0u;
+            uint32_t out = NONE;
+            bool slow = false;
+            if (active) {
+                if (!table_lookup<W>(p, kw, hash_key<W>(kw), out)) {
+                    out = NONE;
+                    slow = !read_in_table_alphabet<W>(kw, p.last_pad);
                 }
             }
-        }
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            uint32_t pending = __ballot_sync(0xFFFFFFFFu, slow[r]);
+            uint32_t pending = __ballot_sync(0xFFFFFFFFu, slow);
             while (pending) {
                 const int src_lane = __ffs(pending) - 1;
                 pending &= pending - 1u;
                 uint32_t bw[W];
 #pragma unroll
-                for (int k = 0; k < W; k++) bw[k] = __shfl_sync(0xFFFFFFFFu, w[r][k], src_lane);
-                const uint32_t out = warp_brute_one<W>(p, bw, lane);
-                if ((int)lane == src_lane) res[r] = out;
+                for (int k = 0; k < W; k++) bw[k] = __shfl_sync(0xFFFFFFFFu, kw[k], src_lane);
+                const uint32_t o = warp_brute_one<W>(p, bw, lane);
+                if ((int)lane == src_lane) out = o;
             }
+            if (active) q_res[q] = out;
         }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            if (pend[r]) res[r] = q_res[qi[r]];
+        __syncwarp();  // the queue is reused by the next iteration
 
-        if (R == 4 && full) {
+        if (full) {
             reinterpret_cast<uint4*>(results)[g] = make_uint4(res[0], res[1], res[2], res[3]);
         } else {
 #pragma unroll
@@ -444,14 +567,31 @@ cudaError_t launch_brute(const MatchParams& p, const ReadSource& src, uint32_t* 
     }
 }
 
-template <int W, int R, bool ASCII>
+template <int W, bool ASCII>
 static cudaError_t launch_probe_w(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
                                   const LaunchGeometry& g, cudaStream_t stream) {
-    auto k = k_probe<W, R, ASCII>;
+    auto k = k_probe<W, ASCII>;
     const size_t hb = hist_bytes(p);
-    const uint64_t n_groups = (src.n + R - 1) / R;
-    const int grid = grid_for(k, PROBE_THREADS, hb, g, n_groups);
+    const int grid = grid_for(k, PROBE_THREADS, hb, g, src.n);
     k<<<grid, PROBE_THREADS, hb, stream>>>(p, src, d_results);
+    count_launch();
+    return cudaGetLastError();
+}
+
+size_t probe2_smem_bytes(const MatchParams& p, int threads) {
+    const size_t KP = (size_t)tier_key_words((int)p.W);
+    return (size_t)p.tier_slots * (KP + 1) * 4 + (size_t)(threads / 32) * PROBE2_QUEUE * (p.W + 1) * 4 + hist_bytes(p);
+}
+
+template <int W>
+static cudaError_t launch_probe2_w(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
+                                   const LaunchGeometry& g, cudaStream_t stream) {
+    auto k = k_probe2<W>;
+    const size_t smem = probe2_smem_bytes(p, PROBE2_THREADS);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const uint64_t n_groups = (src.n + PROBE2_R - 1) / PROBE2_R;
+    const int grid = grid_for(k, PROBE2_THREADS, smem, g, n_groups);
+    k<<<grid, PROBE2_THREADS, smem, stream>>>(p, src, d_results);
     count_launch();
     return cudaGetLastError();
 }
@@ -463,26 +603,27 @@ cudaError_t launch_probe(const MatchParams& p, const ReadSource& src, uint32_t* 
     const bool ascii = src.ascii != nullptr;
     if (ascii) {
         switch (p.W) {
-            case 1: return launch_probe_w<1, 1, true>(p, src, d_results, g, stream);
-            case 2: return launch_probe_w<2, 1, true>(p, src, d_results, g, stream);
-            case 3: return launch_probe_w<3, 1, true>(p, src, d_results, g, stream);
-            default: return launch_probe_w<4, 1, true>(p, src, d_results, g, stream);
+            case 1: return launch_probe_w<1, true>(p, src, d_results, g, stream);
+            case 2: return launch_probe_w<2, true>(p, src, d_results, g, stream);
+            case 3: return launch_probe_w<3, true>(p, src, d_results, g, stream);
+            default: return launch_probe_w<4, true>(p, src, d_results, g, stream);
         }
     }
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(src.packed) | reinterpret_cast<uintptr_t>(d_results)) & 15u) == 0u;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(src.packed) | reinterpret_cast<uintptr_t>(d_results)) & 15u) == 0u &&
+                        probe2_smem_bytes(p, PROBE2_THREADS) + 1024 <= (size_t)g.max_smem_optin;
     if (vec_ok) {
         switch (p.W) {
-            case 1: return launch_probe_w<1, 4, false>(p, src, d_results, g, stream);
-            case 2: return launch_probe_w<2, 4, false>(p, src, d_results, g, stream);
-            case 3: return launch_probe_w<3, 4, false>(p, src, d_results, g, stream);
-            default: return launch_probe_w<4, 4, false>(p, src, d_results, g, stream);
+            case 1: return launch_probe2_w<1>(p, src, d_results, g, stream);
+            case 2: return launch_probe2_w<2>(p, src, d_results, g, stream);
+            case 3: return launch_probe2_w<3>(p, src, d_results, g, stream);
+            default: return launch_probe2_w<4>(p, src, d_results, g, stream);
         }
     }
     switch (p.W) {
-        case 1: return launch_probe_w<1, 1, false>(p, src, d_results, g, stream);
-        case 2: return launch_probe_w<2, 1, false>(p, src, d_results, g, stream);
-        case 3: return launch_probe_w<3, 1, false>(p, src, d_results, g, stream);
-        default: return launch_probe_w<4, 1, false>(p, src, d_results, g, stream);
+        case 1: return launch_probe_w<1, false>(p, src, d_results, g, stream);
+        case 2: return launch_probe_w<2, false>(p, src, d_results, g, stream);
+        case 3: return launch_probe_w<3, false>(p, src, d_results, g, stream);
+        default: return launch_probe_w<4, false>(p, src, d_results, g, stream);
     }
 }
 

@@ -73,6 +73,8 @@ typedef struct {
     uint64_t table_slots;
     uint64_t table_bytes;
     uint64_t table_candidates;   /* neighbourhood strings enumerated before filtering to Some(..) */
+    uint64_t tier_entries;       /* memo-table entries (best distance 0) also cached in the shared-memory hot tier */
+    uint64_t tier_slots;
 } fqtk_b200_matcher_info;
 
 /* ---- lifecycle -------------------------------------------------------------------------------------
@@ -80,7 +82,7 @@ typedef struct {
  * order (first-index tie-break depends on it).  Bytes are upper-cased (:71) and encoded exactly as the reference's
  * encode() does; the panel is copied, the caller may free it on return.
  * `use_cache`: the reference's memo-cache switch (demux.rs:925 passes true).  Non-zero builds the device memo table
- * when the panel's <= max_mismatches neighbourhood fits `fqtk_b200_set_table_budget` (default 64 Mi candidates),
+ * when the panel's <= max_mismatches neighbourhood fits `fqtk_b200_set_table_budget` (default 32 Mi candidates),
  * zero (or an over-budget panel, or L > 32) selects the brute-force kernels.  Results are identical either way. */
 FQTK_B200_API int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t n_samples, uint32_t barcode_len,
                                            uint8_t max_mismatches, uint8_t min_mismatch_delta, int use_cache,
