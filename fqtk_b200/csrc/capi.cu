@@ -62,8 +62,7 @@ struct fqtk_b200_matcher {
     uint4* d_planes = nullptr;
     uint32_t* d_not_exp = nullptr;
     uint32_t* d_table = nullptr;
-    uint32_t* d_tier_keys = nullptr;
-    uint32_t* d_tier_vals = nullptr;
+    uint32_t* d_tier = nullptr;
     uint64_t tier_entries = 0;
     unsigned long long* d_counts = nullptr;
     fq::MatchParams params{};
@@ -156,52 +155,52 @@ void host_insert(std::vector<uint32_t>& table, uint32_t n_buckets, const uint32_
     }
 }
 
-// Hot tier: 2-choice cuckoo over the entries whose best distance is 0.  It is only a cache of the memo table, so a
-// key that cannot be placed (or does not fit the shared-memory budget) is simply left out.
+// Hot tier: 2-choice cuckoo over the entries whose best distance is 0 (layout: kernels.h).  It is only a cache of
+// the memo table, so a key that cannot be placed (or does not fit the shared-memory budget) is simply left out.
 template <int W>
 void build_tier(const std::vector<uint32_t>& keys, const std::vector<uint32_t>& res, uint64_t n, size_t budget_bytes,
-                std::vector<uint32_t>& tkeys, std::vector<uint32_t>& tvals, uint32_t& slots_out, uint64_t& placed) {
-    constexpr int KP = W <= 2 ? W : 4;
+                std::vector<uint32_t>& tier, uint32_t& slots_out, uint64_t& placed) {
+    const int TE = fq::tier_entry_words(W), TV = fq::tier_value_index(W);
     uint64_t n_hot = 0;
     for (uint64_t t = 0; t < n; t++) n_hot += (res[t] != fq::NONE && ((res[t] >> 8) & 0xFFu) == 0u);
     uint32_t slots = 16;
-    while ((uint64_t)slots * 2 < n_hot * 5 && slots < 65536u) slots <<= 1;           // load <= 0.4
-    while (slots > 16 && (size_t)slots * (KP + 1) * 4 > budget_bytes) slots >>= 1;   // shared-memory budget
+    while ((uint64_t)slots * 2 < n_hot * 5 && slots < (1u << 20)) slots <<= 1;   // load <= 0.4
+    while (slots > 16 && (size_t)slots * TE * 4 > budget_bytes) slots >>= 1;     // shared-memory budget
     placed = 0;
     slots_out = 0;
-    if (n_hot == 0 || (size_t)slots * (KP + 1) * 4 > budget_bytes) return;
-    const uint32_t mask = slots - 1;
-    tkeys.assign((size_t)slots * KP, 0xFFFFFFFFu);
-    tvals.assign(slots, fq::NONE);
+    if (n_hot == 0 || (size_t)slots * TE * 4 > budget_bytes) return;
+    uint32_t shift = 32;
+    while ((1u << (32 - shift)) < slots) shift--;
+    tier.assign((size_t)slots * TE, 0xFFFFFFFFu);
     const uint64_t cap = (uint64_t)slots * 45 / 100;
     for (uint64_t t = 0; t < n && placed < cap; t++) {
         if (res[t] == fq::NONE || ((res[t] >> 8) & 0xFFu) != 0u) continue;
-        uint32_t ck[KP], cv = res[t];
-        for (int k = 0; k < KP; k++) ck[k] = k < W ? keys[t * W + k] : 0u;
+        uint32_t ck[W], cv = res[t];
+        for (int k = 0; k < W; k++) ck[k] = keys[t * W + k];
         bool done = false;
         for (int kick = 0; kick < 256 && !done; kick++) {
-            uint32_t kw[W];
-            for (int k = 0; k < W; k++) kw[k] = ck[k];
-            const uint32_t h = fq::hash_key<W>(kw);
-            const uint32_t s[2] = {fq::tier_slot1(h, mask), fq::tier_slot2(h, mask)};
+            const uint32_t s[2] = {fq::tier_hash1<W>(ck) >> shift, fq::tier_hash2<W>(ck) >> shift};
             for (int c = 0; c < 2 && !done; c++) {  // already there (duplicate candidate)?
-                bool same = tvals[s[c]] != fq::NONE;
-                for (int k = 0; k < KP; k++) same = same && tkeys[(size_t)s[c] * KP + k] == ck[k];
+                const uint32_t* ent = tier.data() + (size_t)s[c] * TE;
+                bool same = ent[TV] != fq::NONE;
+                for (int k = 0; k < W; k++) same = same && ent[k] == ck[k];
                 if (same) done = true;
             }
             if (done) break;
             for (int c = 0; c < 2 && !done; c++) {
-                if (tvals[s[c]] == fq::NONE) {
-                    for (int k = 0; k < KP; k++) tkeys[(size_t)s[c] * KP + k] = ck[k];
-                    tvals[s[c]] = cv;
+                uint32_t* ent = tier.data() + (size_t)s[c] * TE;
+                if (ent[TV] == fq::NONE) {
+                    for (int k = 0; k < TE; k++) ent[k] = 0u;
+                    for (int k = 0; k < W; k++) ent[k] = ck[k];
+                    ent[TV] = cv;
                     placed++;
                     done = true;
                 }
             }
             if (done) break;
-            const uint32_t victim = s[(kick ^ (h >> 7)) & 1u];  // evict one of the two residents and carry it on
-            for (int k = 0; k < KP; k++) std::swap(ck[k], tkeys[(size_t)victim * KP + k]);
-            std::swap(cv, tvals[victim]);
+            uint32_t* victim = tier.data() + (size_t)s[(kick ^ (ck[0] >> 9)) & 1u] * TE;  // evict a resident, carry it on
+            for (int k = 0; k < W; k++) std::swap(ck[k], victim[k]);
+            std::swap(cv, victim[TV]);
         }
         // not placed after 256 kicks: whichever key is in hand stays out of the tier (it is still in the memo table)
     }
@@ -243,7 +242,9 @@ int build_table(fqtk_b200_matcher* m) {
     uint64_t n_some = 0;
     for (uint64_t t = 0; t < n; t++) n_some += res[t] != fq::NONE;
     const int EPB = fq::table_entries_per_bucket((int)W);
-    uint64_t buckets64 = (n_some * 100 + 45 * EPB - 1) / (45 * EPB);  // load factor <= 0.45
+    // load factor: 0.2 while the table stays small (a probe almost never leaves its first bucket), 0.45 beyond 32 MB
+    const uint64_t pct = (n_some * 32 * 100 / (20 * EPB) <= (32ull << 20)) ? 20 : 45;
+    uint64_t buckets64 = (n_some * 100 + pct * EPB - 1) / (pct * EPB);
     if (buckets64 < 64) buckets64 = 64;
     if (buckets64 >= (1ull << 31)) return 1;
     const uint32_t n_buckets = (uint32_t)buckets64;
@@ -268,24 +269,24 @@ int build_table(fqtk_b200_matcher* m) {
     m->params.n_buckets = n_buckets;
 
     // hot tier for shared memory
-    std::vector<uint32_t> tkeys, tvals;
+    std::vector<uint32_t> tier;
     uint32_t tslots = 0;
     uint64_t placed = 0;
     const size_t budget = g_tier_budget_bytes;
     switch (W) {
-        case 1: build_tier<1>(keys, res, n, budget, tkeys, tvals, tslots, placed); break;
-        case 2: build_tier<2>(keys, res, n, budget, tkeys, tvals, tslots, placed); break;
-        case 3: build_tier<3>(keys, res, n, budget, tkeys, tvals, tslots, placed); break;
-        default: build_tier<4>(keys, res, n, budget, tkeys, tvals, tslots, placed); break;
+        case 1: build_tier<1>(keys, res, n, budget, tier, tslots, placed); break;
+        case 2: build_tier<2>(keys, res, n, budget, tier, tslots, placed); break;
+        case 3: build_tier<3>(keys, res, n, budget, tier, tslots, placed); break;
+        default: build_tier<4>(keys, res, n, budget, tier, tslots, placed); break;
     }
     if (tslots) {
-        CU(cudaMalloc(&m->d_tier_keys, tkeys.size() * 4));
-        CU(cudaMemcpy(m->d_tier_keys, tkeys.data(), tkeys.size() * 4, cudaMemcpyHostToDevice));
-        CU(cudaMalloc(&m->d_tier_vals, tvals.size() * 4));
-        CU(cudaMemcpy(m->d_tier_vals, tvals.data(), tvals.size() * 4, cudaMemcpyHostToDevice));
-        m->params.tier_keys = m->d_tier_keys;
-        m->params.tier_vals = m->d_tier_vals;
+        CU(cudaMalloc(&m->d_tier, tier.size() * 4));
+        CU(cudaMemcpy(m->d_tier, tier.data(), tier.size() * 4, cudaMemcpyHostToDevice));
+        m->params.tier_entries = m->d_tier;
         m->params.tier_slots = tslots;
+        uint32_t shift = 32;
+        while ((1u << (32 - shift)) < tslots) shift--;
+        m->params.tier_shift = shift;
         m->tier_entries = placed;
     }
     return 0;
@@ -447,9 +448,9 @@ int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t S, uint32_t L,
     m->params.min_delta = min_delta;
     m->params.last_pad = fq::last_word_pad_for_len(L);
     m->params.n_buckets = 0;
-    m->params.tier_keys = nullptr;
-    m->params.tier_vals = nullptr;
+    m->params.tier_entries = nullptr;
     m->params.tier_slots = 0;
+    m->params.tier_shift = 32;
     m->mode = FQTK_B200_MODE_BRUTE;
     if (use_cache && W <= (uint32_t)fq::MAX_FAST_WORDS) {
         rc = build_table(m);
@@ -476,8 +477,7 @@ void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m) {
     if (m->d_planes) cudaFree(m->d_planes);
     if (m->d_not_exp) cudaFree(m->d_not_exp);
     if (m->d_table) cudaFree(m->d_table);
-    if (m->d_tier_keys) cudaFree(m->d_tier_keys);
-    if (m->d_tier_vals) cudaFree(m->d_tier_vals);
+    if (m->d_tier) cudaFree(m->d_tier);
     if (m->d_counts) cudaFree(m->d_counts);
     delete m;
 }

@@ -72,20 +72,22 @@ FQ_HD void planes_from_words(const uint32_t (&w)[W], uint32_t (&pl)[4]) {
 
 // True when every symbol of the read is one of A,C,G,T,N (masks 1,2,4,8,15) — the alphabet the memo table
 // enumerates.  `pad_or` has 0x1 in every nibble beyond the barcode length so padding never trips the test.
-FQ_HD bool word_in_table_alphabet(uint32_t x) {
-    const uint32_t sum = (x & 0x11111111u) + ((x >> 1) & 0x11111111u) + ((x >> 2) & 0x11111111u) +
-                         ((x >> 3) & 0x11111111u);                       // per-nibble popcount, 0..4
-    // a nibble is fine iff its popcount is 1 (bit0 set, bit1 clear) or 4 (bit2 set); 0, 2 and 3 are not
-    const uint32_t ok = ~(sum >> 1) & (sum | (sum >> 2)) & 0x11111111u;
-    return ok == 0x11111111u;
+// Per nibble: bit 0 of the result is set iff the nibble's popcount is 1 or 4 (other result bits are garbage).
+// With a,b,c,d = the nibble's four bits: parity3 = a^b^c, maj3 = majority(a,b,c);
+//   exactly one of four = (parity3 & ~maj3 & ~d) | (~parity3 & ~maj3 & d);  all four = parity3 & maj3 & d.
+FQ_HD uint32_t nibble_ok_bits(uint32_t x) {
+    const uint32_t b = x >> 1, c = x >> 2, d = x >> 3;
+    const uint32_t par = x ^ b ^ c;
+    const uint32_t maj = (x & b) | (x & c) | (b & c);
+    return (par & ~maj & ~d) | (~par & ~maj & d) | (par & maj & d);
 }
 
 template <int W>
 FQ_HD bool read_in_table_alphabet(const uint32_t (&w)[W], uint32_t last_word_pad) {
-    bool ok = true;
+    uint32_t ok = 0x11111111u;
 #pragma unroll
-    for (int i = 0; i < W; i++) ok = ok && word_in_table_alphabet(i == W - 1 ? (w[i] | last_word_pad) : w[i]);
-    return ok;
+    for (int i = 0; i < W; i++) ok &= nibble_ok_bits(i == W - 1 ? (w[i] | last_word_pad) : w[i]);
+    return ok == 0x11111111u;
 }
 
 FQ_HD uint32_t last_word_pad_for_len(uint32_t L) {
@@ -107,13 +109,25 @@ FQ_HD uint32_t hash_key(const uint32_t (&w)[W]) {
     return h;
 }
 
-// Where a key lives: memo-table bucket (global memory) and the two candidate slots of the shared-memory hot tier,
-// all derived from the one 32-bit hash.
+// Memo-table bucket (global memory) of a key, from its 32-bit hash.
 FQ_HD uint32_t bucket_of_hash(uint32_t h, uint32_t n_buckets) {                    // fast range: [0, n_buckets)
     return (uint32_t)(((uint64_t)(h * 0x9E3779B1u) * (uint64_t)n_buckets) >> 32);
 }
-FQ_HD uint32_t tier_slot1(uint32_t h, uint32_t mask) { return h & mask; }
-FQ_HD uint32_t tier_slot2(uint32_t h, uint32_t mask) { return (h >> 16) & mask; }  // tier_slots <= 65536
+// Hot-tier slots: two cheap multiply-add hashes, top bits (IMAD runs on the FMA pipe, off the ALU pipe the
+// compares live on).  slot = hash >> tier_shift.
+template <int W>
+FQ_HD uint32_t tier_hash(const uint32_t (&w)[W], uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+    uint32_t h = w[0] * c0;
+    if constexpr (W > 1) h += w[W > 1 ? 1 : 0] * c1;
+    if constexpr (W > 2) h += w[W > 2 ? 2 : 0] * c2;
+    if constexpr (W > 3) h += w[W > 3 ? 3 : 0] * c3;
+    return h;
+}
+template <int W>
+FQ_HD uint32_t tier_hash1(const uint32_t (&w)[W]) { return tier_hash<W>(w, 0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu); }
+template <int W>
+FQ_HD uint32_t tier_hash2(const uint32_t (&w)[W]) { return tier_hash<W>(w, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u); }
+
 
 // Running best / second-best on keys (distance << 16 | sample index): keys are unique per sample, so plain
 // min / second-min on the key gives min distance, FIRST index among ties (strict '<' at

@@ -11,14 +11,15 @@ struct MatchParams {
                                //  32*p + i of the barcode does NOT admit A/C/G/T
     const uint32_t* not_exp;   // [S * W] ~expected nibble words (only read by the L > 32 kernel)
     const uint32_t* table;     // memo table: 32-byte buckets in global memory (nullptr in brute mode)
-    const uint32_t* tier_keys; // hot tier (entries whose best distance is 0), staged into shared memory by k_probe2:
-    const uint32_t* tier_vals; //   2-choice cuckoo, tier_slots x KP key words + tier_slots result words
+    const uint32_t* tier_entries;  // hot tier (table entries whose best distance is 0), staged into shared memory by
+                                   //   k_probe2: 2-choice cuckoo, tier_slots entries of tier_entry_words(W) words
     unsigned long long* counts;  // [S + 1] per-sample counts, last = unmatched
     uint32_t S, L, W, P;
     uint32_t max_mm, min_delta;
     uint32_t last_pad;         // 0x1 in every padding nibble of the last packed word
     uint32_t n_buckets;        // memo-table buckets
-    uint32_t tier_slots;       // power of two <= 65536, 0 = no hot tier
+    uint32_t tier_slots;       // power of two, 0 = no hot tier
+    uint32_t tier_shift;       // 32 - log2(tier_slots); 32 = no hot tier
 };
 
 // Where a batch of reads lives on the device.
@@ -37,10 +38,12 @@ struct LaunchGeometry {
 
 // Memo-table geometry.  A bucket is 32 bytes = one DRAM/L2 sector, fetched with one 256-bit load.
 //   W <= 3: two entries {k0, k1, k2, value} (missing key words are 0);  W == 4: one entry {k0..k3, value, 0, 0, 0}.
-// Hot-tier keys are padded to KP = 1, 2 or 4 words so a probe is one LDS.32 / LDS.64 / LDS.128.
+// Hot-tier entries: W = 1: {k0, value}; W = 2: {k0, k1, value, 0}; W = 3: {k0, k1, k2, value};
+//   W = 4: {k0, k1, k2, k3, value, 0, 0, 0}.  Empty slots are all-ones (value NONE).
 constexpr int TABLE_BUCKET_WORDS = 8;
 inline __host__ __device__ int table_entries_per_bucket(int W) { return W <= 3 ? 2 : 1; }
-inline __host__ __device__ int tier_key_words(int W) { return W <= 2 ? W : 4; }
+inline __host__ __device__ int tier_entry_words(int W) { return W == 1 ? 2 : (W <= 3 ? 4 : 8); }
+inline __host__ __device__ int tier_value_index(int W) { return W == 1 ? 1 : (W == 2 ? 2 : (W == 3 ? 3 : 4)); }
 
 cudaError_t launch_brute(const MatchParams& p, const ReadSource& src, uint32_t* d_results, const LaunchGeometry& g,
                          cudaStream_t stream);

@@ -246,25 +246,30 @@ FQ_D void load_bucket(const uint32_t* __restrict__ table, uint32_t bucket, uint3
                  : "l"(q));
 }
 
-// One memo-table lookup (bucketised linear probing; an empty entry in a bucket ends the probe).
-// Returns true on a hit (res = stored Some(..) word).
+// One memo-table lookup: bucketised linear probing, single-exit loop; an empty entry in a bucket ends the probe.
+// Returns true on a hit (res = stored Some(..) word); res is NONE otherwise.
 template <int W>
 FQ_D bool table_lookup(const MatchParams& p, const uint32_t (&w)[W], uint32_t h, uint32_t& res) {
     uint32_t b = bucket_of_hash(h, p.n_buckets);
     for (;;) {
         uint32_t e[8];
         load_bucket(p.table, b, e);
+        bool end;
         if constexpr (W <= 3) {
-            const uint32_t k0 = w[0], k1 = W > 1 ? w[W > 1 ? 1 : 0] : 0u, k2 = W > 2 ? w[W > 2 ? 2 : 0] : 0u;
-            if (e[0] == k0 && e[1] == k1 && e[2] == k2 && e[3] != NONE) { res = e[3]; return true; }
-            if (e[4] == k0 && e[5] == k1 && e[6] == k2 && e[7] != NONE) { res = e[7]; return true; }
-            if (e[3] == NONE || e[7] == NONE) return false;
+            const uint32_t k1 = W > 1 ? w[W > 1 ? 1 : 0] : 0u, k2 = W > 2 ? w[W > 2 ? 2 : 0] : 0u;
+            const bool m0 = e[0] == w[0] && e[1] == k1 && e[2] == k2;
+            const bool m1 = e[4] == w[0] && e[5] == k1 && e[6] == k2;
+            res = m0 ? e[3] : (m1 ? e[7] : NONE);  // an empty entry's all-ones key may equal an all-N read: value NONE
+            end = res != NONE || e[3] == NONE || e[7] == NONE;
         } else {
-            if (e[0] == w[0] && e[1] == w[1] && e[2] == w[2] && e[3] == w[3] && e[4] != NONE) { res = e[4]; return true; }
-            if (e[4] == NONE) return false;
+            const bool m0 = e[0] == w[0] && e[1] == w[1] && e[2] == w[2] && e[3] == w[3];
+            res = m0 ? e[4] : NONE;
+            end = res != NONE || e[4] == NONE;
         }
+        if (end) break;
         b = (b + 1u == p.n_buckets) ? 0u : b + 1u;
     }
+    return res != NONE;
 }
 
 // k_probe: one read per thread; the ASCII (host-batch / e2e) route and the fallback for unaligned device buffers.
@@ -298,10 +303,8 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe(const MatchParams p, co
         uint32_t res = NONE;
         bool slow = false;
         if (valid && row_ok) {
-            if (!table_lookup<W>(p, w, hash_key<W>(w), res)) {
-                res = NONE;
-                slow = !read_in_table_alphabet<W>(w, p.last_pad);
-            }
+            const bool hit = table_lookup<W>(p, w, hash_key<W>(w), res);
+            slow = !hit && !read_in_table_alphabet<W>(w, p.last_pad);
         }
         uint32_t pending = __ballot_sync(0xFFFFFFFFu, slow);
         while (pending) {
@@ -321,13 +324,15 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe(const MatchParams p, co
     cnt.flush();
 }
 
-// k_probe2: the HBM-resident packed route.  Four reads per thread (W x LDG.128, one STG.128), three tiers:
+// k_probe2: the HBM-resident packed route.  A warp owns tiles of 128 consecutive reads, four per lane
+// (W x LDG.128 in, one STG.128 out), and resolves them through three tiers:
 //   1. hot tier in SHARED memory: the table entries whose best distance is 0 (the barcodes themselves and their
 //      expansions), 2-choice cuckoo -> two independent LDS per read, no loop.  ~80 % of real reads end here.
-//   2. the remaining reads of the warp (all four slots) are compacted into a per-warp shared-memory queue so that
-//      the global memo-table probe, the alphabet test and the result write-back run once per ~32 such reads
-//      instead of once per slot with mostly idle lanes.
+//   2. the tile's remaining reads (all four slots) are compacted into a per-warp shared-memory queue so that the
+//      global memo-table probe, the alphabet test and the result write-back run once per ~32 such reads instead of
+//      once per slot with mostly idle lanes.
 //   3. reads outside the table's alphabet: warp-cooperative brute force (same as k_probe).
+// The < 128-read tail of a batch is finished by one warp with the one-read-per-lane code of k_probe.
 constexpr int PROBE2_R = 4;
 constexpr int PROBE2_QUEUE = 32 * PROBE2_R;
 
@@ -335,17 +340,16 @@ template <int W>
 __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, const ReadSource src,
                                                            uint32_t* __restrict__ results) {
     constexpr int R = PROBE2_R;
-    constexpr int KP = W <= 2 ? W : 4;
+    constexpr int TE = W == 1 ? 2 : (W <= 3 ? 4 : 8);  // tier entry words: {key.., value} (W = 4: {k0..k3, value, pad})
+    constexpr int TV = W == 1 ? 1 : (W == 2 ? 2 : (W == 3 ? 3 : 4));  // index of the value word
     extern __shared__ uint4 s_dyn[];
-    // layout: tier keys | tier vals | per-warp queues (keys, results) | histogram
-    uint32_t* s_tkeys = reinterpret_cast<uint32_t*>(s_dyn);
-    uint32_t* s_tvals = s_tkeys + (size_t)p.tier_slots * KP;
-    uint32_t* s_queue = s_tvals + p.tier_slots;
+    // layout: tier entries | per-warp queues (keys, results) | histogram
+    uint32_t* s_tier = reinterpret_cast<uint32_t*>(s_dyn);
+    uint32_t* s_queue = s_tier + (size_t)p.tier_slots * TE;
     const uint32_t n_warps = blockDim.x >> 5;
     uint32_t* s_hist = s_queue + (size_t)n_warps * PROBE2_QUEUE * (W + 1);
 
-    for (uint32_t t = threadIdx.x; t < p.tier_slots * KP; t += blockDim.x) s_tkeys[t] = __ldg(p.tier_keys + t);
-    for (uint32_t t = threadIdx.x; t < p.tier_slots; t += blockDim.x) s_tvals[t] = __ldg(p.tier_vals + t);
+    for (uint32_t t = threadIdx.x; t < p.tier_slots * TE; t += blockDim.x) s_tier[t] = __ldg(p.tier_entries + t);
     Counter cnt;
     cnt.init(s_hist, p);
     __syncthreads();
@@ -354,86 +358,66 @@ __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, 
     const uint32_t lane_lt = (1u << lane) - 1u;
     uint32_t* q_keys = s_queue + (size_t)(threadIdx.x >> 5) * PROBE2_QUEUE * (W + 1);
     uint32_t* q_res = q_keys + PROBE2_QUEUE * W;
-    const uint32_t tmask = p.tier_slots - 1u;
-    const bool has_tier = p.tier_slots != 0u;
+    const uint32_t tshift = p.tier_shift;  // 32 - log2(tier_slots)
 
-    const uint64_t n_groups = (src.n + R - 1) / R;
-    const uint64_t total = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t gbase = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); gbase < n_groups; gbase += total) {
-        const uint64_t g = gbase + lane;
+    const uint32_t n_tiles = (uint32_t)(src.n / (uint64_t)PROBE2_QUEUE);
+    const uint32_t warp_stride = gridDim.x * n_warps;
+    for (uint32_t tile = blockIdx.x * n_warps + (threadIdx.x >> 5); tile < n_tiles; tile += warp_stride) {
+        const uint32_t g = tile * 32u + lane;  // this lane's group of 4 consecutive reads
         uint32_t w[R][W];
         uint32_t res[R];
-        bool valid[R];
-        const bool full = (g + 1) * R <= src.n;
-        if (full) {  // 4 reads = W x 16 B, one LDG.128 each, fully coalesced across the warp
+        {
             uint32_t flat[R * W];
+            const uint4* in = reinterpret_cast<const uint4*>(src.packed) + (size_t)g * W;
 #pragma unroll
             for (int v = 0; v < W; v++) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(src.packed) + g * W + v);
+                const uint4 q = __ldg(in + v);
                 flat[4 * v + 0] = q.x;
                 flat[4 * v + 1] = q.y;
                 flat[4 * v + 2] = q.z;
                 flat[4 * v + 3] = q.w;
             }
 #pragma unroll
-            for (int r = 0; r < R; r++) {
+            for (int r = 0; r < R; r++)
 #pragma unroll
                 for (int k = 0; k < W; k++) w[r][k] = flat[r * W + k];
-                valid[r] = true;
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                const uint64_t i = g * R + r;
-                valid[r] = i < src.n;
-#pragma unroll
-                for (int k = 0; k < W; k++) w[r][k] = valid[r] ? __ldg(src.packed + i * W + k) : 0u;
-            }
         }
 
-        // ---- tier 1: shared-memory cuckoo probe ----
-        bool pend[R];
+        // ---- tier 1: shared-memory cuckoo probe (a NONE value = empty slot = not found here) ----
 #pragma unroll
         for (int r = 0; r < R; r++) {
             res[r] = NONE;
-            pend[r] = valid[r];
-            if (has_tier && valid[r]) {
-                const uint32_t hsh = hash_key<W>(w[r]);
-                const uint32_t s1 = tier_slot1(hsh, tmask), s2 = tier_slot2(hsh, tmask);
-                bool m1, m2;
-                if constexpr (KP == 1) {
-                    m1 = s_tkeys[s1] == w[r][0];
-                    m2 = s_tkeys[s2] == w[r][0];
-                } else if constexpr (KP == 2) {
-                    const uint2 a = reinterpret_cast<const uint2*>(s_tkeys)[s1];
-                    const uint2 b = reinterpret_cast<const uint2*>(s_tkeys)[s2];
-                    m1 = a.x == w[r][0] && a.y == w[r][1];
-                    m2 = b.x == w[r][0] && b.y == w[r][1];
+            if (tshift < 32u) {
+                const uint32_t s1 = tier_hash1<W>(w[r]) >> tshift, s2 = tier_hash2<W>(w[r]) >> tshift;
+                if constexpr (W == 1) {
+                    const uint2 a = reinterpret_cast<const uint2*>(s_tier)[s1];
+                    const uint2 b = reinterpret_cast<const uint2*>(s_tier)[s2];
+                    res[r] = (a.x == w[r][0]) ? a.y : ((b.x == w[r][0]) ? b.y : NONE);
+                } else if constexpr (W <= 3) {
+                    const uint4 a = reinterpret_cast<const uint4*>(s_tier)[s1];
+                    const uint4 b = reinterpret_cast<const uint4*>(s_tier)[s2];
+                    const bool m1 = a.x == w[r][0] && a.y == w[r][1] && (W == 2 || a.z == w[r][W > 2 ? 2 : 0]);
+                    const bool m2 = b.x == w[r][0] && b.y == w[r][1] && (W == 2 || b.z == w[r][W > 2 ? 2 : 0]);
+                    res[r] = m1 ? (W == 2 ? a.z : a.w) : (m2 ? (W == 2 ? b.z : b.w) : NONE);
                 } else {
-                    const uint4 a = reinterpret_cast<const uint4*>(s_tkeys)[s1];
-                    const uint4 b = reinterpret_cast<const uint4*>(s_tkeys)[s2];
-                    const uint32_t k3 = W > 3 ? w[r][W > 3 ? 3 : 0] : 0u;
-                    m1 = a.x == w[r][0] && a.y == w[r][1] && a.z == w[r][2] && a.w == k3;
-                    m2 = b.x == w[r][0] && b.y == w[r][1] && b.z == w[r][2] && b.w == k3;
-                }
-                if (m1 || m2) {
-                    const uint32_t v = s_tvals[m1 ? s1 : s2];
-                    if (v != NONE) {  // an empty slot's all-ones key can equal an all-N read
-                        res[r] = v;
-                        pend[r] = false;
-                    }
+                    const uint4 a = reinterpret_cast<const uint4*>(s_tier)[2u * s1];
+                    const uint4 b = reinterpret_cast<const uint4*>(s_tier)[2u * s2];
+                    const bool m1 = a.x == w[r][0] && a.y == w[r][1] && a.z == w[r][2] && a.w == w[r][W > 3 ? 3 : 0];
+                    const bool m2 = b.x == w[r][0] && b.y == w[r][1] && b.z == w[r][2] && b.w == w[r][W > 3 ? 3 : 0];
+                    if (m1 || m2) res[r] = s_tier[(m1 ? s1 : s2) * TE + TV];
                 }
             }
         }
 
-        // ---- tier 2: compact the warp's remaining reads into its queue ----
+        // ---- tier 2: compact the tile's unresolved reads into the warp's queue ----
         uint32_t qcount = 0;  // warp-uniform
         uint32_t qi[R];
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pend[r]);
+            const bool pend = res[r] == NONE;
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pend);
             qi[r] = qcount + __popc(bal & lane_lt);
-            if (pend[r]) {
+            if (pend) {
 #pragma unroll
                 for (int k = 0; k < W; k++) q_keys[qi[r] * W + k] = w[r][k];
             }
@@ -449,10 +433,8 @@ __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, 
             uint32_t out = NONE;
             bool slow = false;
             if (active) {
-                if (!table_lookup<W>(p, kw, hash_key<W>(kw), out)) {
-                    out = NONE;
-                    slow = !read_in_table_alphabet<W>(kw, p.last_pad);
-                }
+                const bool hit = table_lookup<W>(p, kw, hash_key<W>(kw), out);
+                slow = !hit && !read_in_table_alphabet<W>(kw, p.last_pad);
             }
             uint32_t pending = __ballot_sync(0xFFFFFFFFu, slow);
             while (pending) {
@@ -467,21 +449,46 @@ __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, 
             if (active) q_res[q] = out;
         }
         __syncwarp();
+        // every read that went through the queue had res == NONE; a queue result of NONE leaves it NONE
 #pragma unroll
         for (int r = 0; r < R; r++)
-            if (pend[r]) res[r] = q_res[qi[r]];
-        __syncwarp();  // the queue is reused by the next iteration
+            if (res[r] == NONE) res[r] = q_res[qi[r]];
+        __syncwarp();  // the queue is reused by the next tile
 
-        if (full) {
-            reinterpret_cast<uint4*>(results)[g] = make_uint4(res[0], res[1], res[2], res[3]);
-        } else {
+        reinterpret_cast<uint4*>(results)[g] = make_uint4(res[0], res[1], res[2], res[3]);
 #pragma unroll
-            for (int r = 0; r < R; r++)
-                if (valid[r]) results[g * R + r] = res[r];
+        for (int r = 0; r < R; r++) cnt.add(res[r]);
+    }
+
+    // ---- tail: fewer than 128 reads, one per lane, first warp of the grid ----
+    if (blockIdx.x == 0 && threadIdx.x < 32u) {
+        for (uint64_t base = (uint64_t)n_tiles * PROBE2_QUEUE; base < src.n; base += 32u) {
+            const uint64_t i = base + lane;
+            const bool valid = i < src.n;
+            uint32_t kw[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) kw[k] = valid ? __ldg(src.packed + i * W + k) : 0u;
+            uint32_t out = NONE;
+            bool slow = false;
+            if (valid) {
+                const bool hit = table_lookup<W>(p, kw, hash_key<W>(kw), out);
+                slow = !hit && !read_in_table_alphabet<W>(kw, p.last_pad);
+            }
+            uint32_t pending = __ballot_sync(0xFFFFFFFFu, slow);
+            while (pending) {
+                const int src_lane = __ffs(pending) - 1;
+                pending &= pending - 1u;
+                uint32_t bw[W];
+#pragma unroll
+                for (int k = 0; k < W; k++) bw[k] = __shfl_sync(0xFFFFFFFFu, kw[k], src_lane);
+                const uint32_t o = warp_brute_one<W>(p, bw, lane);
+                if ((int)lane == src_lane) out = o;
+            }
+            if (valid) {
+                results[i] = out;
+                cnt.add(out);
+            }
         }
-#pragma unroll
-        for (int r = 0; r < R; r++)
-            if (valid[r]) cnt.add(res[r]);
     }
     cnt.flush();
 }
@@ -579,8 +586,8 @@ static cudaError_t launch_probe_w(const MatchParams& p, const ReadSource& src, u
 }
 
 size_t probe2_smem_bytes(const MatchParams& p, int threads) {
-    const size_t KP = (size_t)tier_key_words((int)p.W);
-    return (size_t)p.tier_slots * (KP + 1) * 4 + (size_t)(threads / 32) * PROBE2_QUEUE * (p.W + 1) * 4 + hist_bytes(p);
+    return (size_t)p.tier_slots * tier_entry_words((int)p.W) * 4 +
+           (size_t)(threads / 32) * PROBE2_QUEUE * (p.W + 1) * 4 + hist_bytes(p);
 }
 
 template <int W>
@@ -610,6 +617,7 @@ cudaError_t launch_probe(const MatchParams& p, const ReadSource& src, uint32_t* 
         }
     }
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(src.packed) | reinterpret_cast<uintptr_t>(d_results)) & 15u) == 0u &&
+                        p.S + 1u <= HIST_SMEM_BINS &&
                         probe2_smem_bytes(p, PROBE2_THREADS) + 1024 <= (size_t)g.max_smem_optin;
     if (vec_ok) {
         switch (p.W) {
