@@ -32,7 +32,7 @@ namespace {
 
 thread_local std::string g_err;
 uint64_t g_table_budget = 32ull << 20;
-size_t g_tier_budget_bytes = 96u << 10;  // shared memory the hot tier may take per CTA
+size_t g_tier_budget_bytes = 132u << 10;  // shared memory the hot tier may take per CTA
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -63,6 +63,7 @@ struct fqtk_b200_matcher {
     uint32_t* d_not_exp = nullptr;
     uint32_t* d_table = nullptr;
     uint32_t* d_tier = nullptr;
+    uint32_t* d_bloom = nullptr;
     uint64_t tier_entries = 0;
     unsigned long long* d_counts = nullptr;
     fq::MatchParams params{};
@@ -160,18 +161,18 @@ void host_insert(std::vector<uint32_t>& table, uint32_t n_buckets, const uint32_
 template <int W>
 void build_tier(const std::vector<uint32_t>& keys, const std::vector<uint32_t>& res, uint64_t n, size_t budget_bytes,
                 std::vector<uint32_t>& tier, uint32_t& slots_out, uint64_t& placed) {
-    const int TE = fq::tier_entry_words(W), TV = fq::tier_value_index(W);
+    const int TE = fq::tier_entry_words(W);
     uint64_t n_hot = 0;
     for (uint64_t t = 0; t < n; t++) n_hot += (res[t] != fq::NONE && ((res[t] >> 8) & 0xFFu) == 0u);
     uint32_t slots = 16;
-    while ((uint64_t)slots * 2 < n_hot * 5 && slots < (1u << 20)) slots <<= 1;   // load <= 0.4
-    while (slots > 16 && (size_t)slots * TE * 4 > budget_bytes) slots >>= 1;     // shared-memory budget
+    while ((uint64_t)slots * 2 < n_hot * 5 && slots < (1u << 20)) slots <<= 1;            // load <= 0.4
+    while (slots > 16 && (size_t)slots * (TE + (W == 4)) * 4 > budget_bytes) slots >>= 1;  // shared-memory budget
     placed = 0;
     slots_out = 0;
-    if (n_hot == 0 || (size_t)slots * TE * 4 > budget_bytes) return;
+    if (n_hot == 0 || (size_t)slots * (TE + (W == 4)) * 4 > budget_bytes) return;
     uint32_t shift = 32;
     while ((1u << (32 - shift)) < slots) shift--;
-    tier.assign((size_t)slots * TE, 0xFFFFFFFFu);
+    std::vector<uint32_t> tk((size_t)slots * W, 0xFFFFFFFFu), tv(slots, fq::NONE);
     const uint64_t cap = (uint64_t)slots * 45 / 100;
     for (uint64_t t = 0; t < n && placed < cap; t++) {
         if (res[t] == fq::NONE || ((res[t] >> 8) & 0xFFu) != 0u) continue;
@@ -181,28 +182,43 @@ void build_tier(const std::vector<uint32_t>& keys, const std::vector<uint32_t>& 
         for (int kick = 0; kick < 256 && !done; kick++) {
             const uint32_t s[2] = {fq::tier_hash1<W>(ck) >> shift, fq::tier_hash2<W>(ck) >> shift};
             for (int c = 0; c < 2 && !done; c++) {  // already there (duplicate candidate)?
-                const uint32_t* ent = tier.data() + (size_t)s[c] * TE;
-                bool same = ent[TV] != fq::NONE;
-                for (int k = 0; k < W; k++) same = same && ent[k] == ck[k];
+                bool same = tv[s[c]] != fq::NONE;
+                for (int k = 0; k < W; k++) same = same && tk[(size_t)s[c] * W + k] == ck[k];
                 if (same) done = true;
             }
             if (done) break;
             for (int c = 0; c < 2 && !done; c++) {
-                uint32_t* ent = tier.data() + (size_t)s[c] * TE;
-                if (ent[TV] == fq::NONE) {
-                    for (int k = 0; k < TE; k++) ent[k] = 0u;
-                    for (int k = 0; k < W; k++) ent[k] = ck[k];
-                    ent[TV] = cv;
+                if (tv[s[c]] == fq::NONE) {
+                    for (int k = 0; k < W; k++) tk[(size_t)s[c] * W + k] = ck[k];
+                    tv[s[c]] = cv;
                     placed++;
                     done = true;
                 }
             }
             if (done) break;
-            uint32_t* victim = tier.data() + (size_t)s[(kick ^ (ck[0] >> 9)) & 1u] * TE;  // evict a resident, carry it on
-            for (int k = 0; k < W; k++) std::swap(ck[k], victim[k]);
-            std::swap(cv, victim[TV]);
+            const uint32_t victim = s[(kick ^ (ck[0] >> 9)) & 1u];  // evict a resident and carry it on
+            for (int k = 0; k < W; k++) std::swap(ck[k], tk[(size_t)victim * W + k]);
+            std::swap(cv, tv[victim]);
         }
         // not placed after 256 kicks: whichever key is in hand stays out of the tier (it is still in the memo table)
+    }
+    // serialise into the device layout
+    if (W == 4) {
+        tier.assign((size_t)slots * 5, 0xFFFFFFFFu);
+        for (uint32_t e = 0; e < slots; e++) {
+            for (int k = 0; k < 4; k++) tier[(size_t)e * 4 + k] = tk[(size_t)e * W + (k < W ? k : 0)];
+            tier[(size_t)slots * 4 + e] = tv[e];
+        }
+    } else {
+        const int TV = fq::tier_value_index(W);
+        tier.assign((size_t)slots * TE, 0u);
+        for (uint32_t e = 0; e < slots; e++) {
+            uint32_t* ent = tier.data() + (size_t)e * TE;
+            for (int k = 0; k < W; k++) ent[k] = tk[(size_t)e * W + k];
+            ent[TV] = tv[e];
+            if (tv[e] == fq::NONE)
+                for (int k = 0; k < TE; k++) ent[k] = 0xFFFFFFFFu;
+        }
     }
     slots_out = slots;
 }
@@ -268,17 +284,20 @@ int build_table(fqtk_b200_matcher* m) {
     m->params.table = m->d_table;
     m->params.n_buckets = n_buckets;
 
-    // hot tier for shared memory
+    // hot tier + Bloom filter for shared memory (k_probe2)
+    const size_t smem_max = (size_t)m->geo.max_smem_optin - 2048;
+    const size_t fixed = fq::probe2_fixed_smem_bytes(W, S, fq::probe2_threads());
     std::vector<uint32_t> tier;
     uint32_t tslots = 0;
     uint64_t placed = 0;
-    const size_t budget = g_tier_budget_bytes;
+    const size_t budget = std::min(g_tier_budget_bytes, smem_max > fixed ? smem_max - fixed : 0);
     switch (W) {
         case 1: build_tier<1>(keys, res, n, budget, tier, tslots, placed); break;
         case 2: build_tier<2>(keys, res, n, budget, tier, tslots, placed); break;
         case 3: build_tier<3>(keys, res, n, budget, tier, tslots, placed); break;
         default: build_tier<4>(keys, res, n, budget, tier, tslots, placed); break;
     }
+    size_t tier_bytes = 0;
     if (tslots) {
         CU(cudaMalloc(&m->d_tier, tier.size() * 4));
         CU(cudaMemcpy(m->d_tier, tier.data(), tier.size() * 4, cudaMemcpyHostToDevice));
@@ -288,6 +307,39 @@ int build_table(fqtk_b200_matcher* m) {
         while ((1u << (32 - shift)) < tslots) shift--;
         m->params.tier_shift = shift;
         m->tier_entries = placed;
+        // replicas: as many as tile the banks once, while the tier stays within its budget
+        const size_t entry_bytes = (size_t)fq::tier_entry_words((int)W) * 4;
+        uint32_t rep = (uint32_t)fq::tier_max_rep((int)W);
+        while (rep > 1 && (size_t)tslots * rep * entry_bytes + (W == 4 ? (size_t)tslots * 4 : 0) > budget) rep >>= 1;
+        m->params.tier_rep = rep;
+        tier_bytes = (size_t)tslots * rep * entry_bytes + (W == 4 ? (size_t)tslots * 4 : 0);
+    }
+    // Bloom filter over every table key: >= 8 bits per key, at most 32 KB, only if it still fits
+    {
+        uint32_t words = 64;
+        while ((uint64_t)words * 32 < inserted * 12 && words < 8192u) words <<= 1;
+        if ((uint64_t)words * 32 >= inserted * 8 && fixed + tier_bytes + (size_t)words * 4 <= smem_max) {
+            std::vector<uint32_t> bloom(words, 0u);
+            uint32_t bshift = 32;
+            while ((1u << (32 - bshift)) < words) bshift--;
+            for (uint64_t t = 0; t < n; t++) {
+                if (res[t] == fq::NONE) continue;
+                uint32_t h;
+                const uint32_t* key = keys.data() + t * W;
+                switch (W) {
+                    case 1: { uint32_t kw[1] = {key[0]}; h = fq::hash_key<1>(kw); break; }
+                    case 2: { uint32_t kw[2] = {key[0], key[1]}; h = fq::hash_key<2>(kw); break; }
+                    case 3: { uint32_t kw[3] = {key[0], key[1], key[2]}; h = fq::hash_key<3>(kw); break; }
+                    default: { uint32_t kw[4] = {key[0], key[1], key[2], key[3]}; h = fq::hash_key<4>(kw); break; }
+                }
+                bloom[h >> bshift] |= fq::bloom_mask(h);
+            }
+            CU(cudaMalloc(&m->d_bloom, bloom.size() * 4));
+            CU(cudaMemcpy(m->d_bloom, bloom.data(), bloom.size() * 4, cudaMemcpyHostToDevice));
+            m->params.bloom = m->d_bloom;
+            m->params.bloom_words = words;
+            m->params.bloom_shift = bshift;
+        }
     }
     return 0;
 }
@@ -451,6 +503,10 @@ int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t S, uint32_t L,
     m->params.tier_entries = nullptr;
     m->params.tier_slots = 0;
     m->params.tier_shift = 32;
+    m->params.tier_rep = 1;
+    m->params.bloom = nullptr;
+    m->params.bloom_words = 0;
+    m->params.bloom_shift = 32;
     m->mode = FQTK_B200_MODE_BRUTE;
     if (use_cache && W <= (uint32_t)fq::MAX_FAST_WORDS) {
         rc = build_table(m);
@@ -478,6 +534,7 @@ void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m) {
     if (m->d_not_exp) cudaFree(m->d_not_exp);
     if (m->d_table) cudaFree(m->d_table);
     if (m->d_tier) cudaFree(m->d_tier);
+    if (m->d_bloom) cudaFree(m->d_bloom);
     if (m->d_counts) cudaFree(m->d_counts);
     delete m;
 }

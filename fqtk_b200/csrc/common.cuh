@@ -129,6 +129,9 @@ template <int W>
 FQ_HD uint32_t tier_hash2(const uint32_t (&w)[W]) { return tier_hash<W>(w, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u); }
 
 
+// Blocked Bloom filter: one 32-bit word per key (top hash bits), three bit positions from the low hash bits.
+FQ_HD uint32_t bloom_mask(uint32_t h) { return (1u << (h & 31u)) | (1u << ((h >> 5) & 31u)) | (1u << ((h >> 10) & 31u)); }
+
 // Running best / second-best on keys (distance << 16 | sample index): keys are unique per sample, so plain
 // min / second-min on the key gives min distance, FIRST index among ties (strict '<' at
 // barcode_matching.rs:132) and the second-smallest distance with multiplicity (:140).

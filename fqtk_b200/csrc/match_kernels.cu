@@ -29,7 +29,7 @@ void count_launch() { g_launches.fetch_add(1); }
 constexpr uint32_t HIST_SMEM_BINS = 8192;  // S + 1 <= this: CTA-private histogram lives in shared memory
 constexpr int BRUTE_THREADS = 512;
 constexpr int PROBE_THREADS = 256;
-constexpr int PROBE2_THREADS = 512;
+constexpr int PROBE2_THREADS = 1024;
 
 // ------------------------------------------------------------------------------------------------------
 // read loaders
@@ -340,16 +340,27 @@ template <int W>
 __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, const ReadSource src,
                                                            uint32_t* __restrict__ results) {
     constexpr int R = PROBE2_R;
-    constexpr int TE = W == 1 ? 2 : (W <= 3 ? 4 : 8);  // tier entry words: {key.., value} (W = 4: {k0..k3, value, pad})
-    constexpr int TV = W == 1 ? 1 : (W == 2 ? 2 : (W == 3 ? 3 : 4));  // index of the value word
+    constexpr int TE = W == 1 ? 2 : 4;  // tier entry words (kernels.h)
     extern __shared__ uint4 s_dyn[];
-    // layout: tier entries | per-warp queues (keys, results) | histogram
+    // layout: tier replicas | (W = 4: tier values) | Bloom words | per-warp queues (keys, results) | histogram
     uint32_t* s_tier = reinterpret_cast<uint32_t*>(s_dyn);
-    uint32_t* s_queue = s_tier + (size_t)p.tier_slots * TE;
+    const uint32_t rep = p.tier_rep;
+    uint32_t* s_tvals = s_tier + (size_t)p.tier_slots * rep * TE;
+    uint32_t* s_bloom = s_tvals + (W == 4 ? p.tier_slots : 0u);
+    uint32_t* s_queue = s_bloom + p.bloom_words;
     const uint32_t n_warps = blockDim.x >> 5;
     uint32_t* s_hist = s_queue + (size_t)n_warps * PROBE2_QUEUE * (W + 1);
 
-    for (uint32_t t = threadIdx.x; t < p.tier_slots * TE; t += blockDim.x) s_tier[t] = __ldg(p.tier_entries + t);
+    // entry e, replica r lives at word (e * rep + r) * TE: with rep = 8 (16 with 8-byte entries) replica r owns one
+    // fixed group of banks, so the 32 lanes of a probe hit every bank group exactly 4 (2) times — no conflicts
+    for (uint32_t t = threadIdx.x; t < p.tier_slots * rep * TE; t += blockDim.x) {
+        const uint32_t e = t / (rep * TE), k = t % TE;
+        s_tier[t] = __ldg(p.tier_entries + e * TE + k);
+    }
+    if constexpr (W == 4)
+        for (uint32_t t = threadIdx.x; t < p.tier_slots; t += blockDim.x)
+            s_tvals[t] = __ldg(p.tier_entries + (size_t)p.tier_slots * TE + t);
+    for (uint32_t t = threadIdx.x; t < p.bloom_words; t += blockDim.x) s_bloom[t] = __ldg(p.bloom + t);
     Counter cnt;
     cnt.init(s_hist, p);
     __syncthreads();
@@ -359,6 +370,8 @@ __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, 
     uint32_t* q_keys = s_queue + (size_t)(threadIdx.x >> 5) * PROBE2_QUEUE * (W + 1);
     uint32_t* q_res = q_keys + PROBE2_QUEUE * W;
     const uint32_t tshift = p.tier_shift;  // 32 - log2(tier_slots)
+    const uint32_t* my_tier = s_tier + (lane & (rep - 1u)) * TE;  // this lane's replica
+    const uint32_t tstride = rep * TE;                             // words between consecutive slots of one replica
 
     const uint32_t n_tiles = (uint32_t)(src.n / (uint64_t)PROBE2_QUEUE);
     const uint32_t warp_stride = gridDim.x * n_warps;
@@ -390,21 +403,25 @@ __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, 
             if (tshift < 32u) {
                 const uint32_t s1 = tier_hash1<W>(w[r]) >> tshift, s2 = tier_hash2<W>(w[r]) >> tshift;
                 if constexpr (W == 1) {
-                    const uint2 a = reinterpret_cast<const uint2*>(s_tier)[s1];
-                    const uint2 b = reinterpret_cast<const uint2*>(s_tier)[s2];
+                    const uint2 a = *reinterpret_cast<const uint2*>(my_tier + s1 * tstride);
+                    const uint2 b = *reinterpret_cast<const uint2*>(my_tier + s2 * tstride);
                     res[r] = (a.x == w[r][0]) ? a.y : ((b.x == w[r][0]) ? b.y : NONE);
-                } else if constexpr (W <= 3) {
-                    const uint4 a = reinterpret_cast<const uint4*>(s_tier)[s1];
-                    const uint4 b = reinterpret_cast<const uint4*>(s_tier)[s2];
-                    const bool m1 = a.x == w[r][0] && a.y == w[r][1] && (W == 2 || a.z == w[r][W > 2 ? 2 : 0]);
-                    const bool m2 = b.x == w[r][0] && b.y == w[r][1] && (W == 2 || b.z == w[r][W > 2 ? 2 : 0]);
-                    res[r] = m1 ? (W == 2 ? a.z : a.w) : (m2 ? (W == 2 ? b.z : b.w) : NONE);
                 } else {
-                    const uint4 a = reinterpret_cast<const uint4*>(s_tier)[2u * s1];
-                    const uint4 b = reinterpret_cast<const uint4*>(s_tier)[2u * s2];
-                    const bool m1 = a.x == w[r][0] && a.y == w[r][1] && a.z == w[r][2] && a.w == w[r][W > 3 ? 3 : 0];
-                    const bool m2 = b.x == w[r][0] && b.y == w[r][1] && b.z == w[r][2] && b.w == w[r][W > 3 ? 3 : 0];
-                    if (m1 || m2) res[r] = s_tier[(m1 ? s1 : s2) * TE + TV];
+                    const uint4 a = *reinterpret_cast<const uint4*>(my_tier + s1 * tstride);
+                    const uint4 b = *reinterpret_cast<const uint4*>(my_tier + s2 * tstride);
+                    if constexpr (W == 2) {
+                        const bool m1 = a.x == w[r][0] && a.y == w[r][1];
+                        const bool m2 = b.x == w[r][0] && b.y == w[r][1];
+                        res[r] = m1 ? a.z : (m2 ? b.z : NONE);
+                    } else if constexpr (W == 3) {
+                        const bool m1 = a.x == w[r][0] && a.y == w[r][1] && a.z == w[r][W > 2 ? 2 : 0];
+                        const bool m2 = b.x == w[r][0] && b.y == w[r][1] && b.z == w[r][W > 2 ? 2 : 0];
+                        res[r] = m1 ? a.w : (m2 ? b.w : NONE);
+                    } else {
+                        const bool m1 = a.x == w[r][0] && a.y == w[r][1] && a.z == w[r][W > 2 ? 2 : 0] && a.w == w[r][W > 3 ? 3 : 0];
+                        const bool m2 = b.x == w[r][0] && b.y == w[r][1] && b.z == w[r][W > 2 ? 2 : 0] && b.w == w[r][W > 3 ? 3 : 0];
+                        if (m1 || m2) res[r] = s_tvals[m1 ? s1 : s2];
+                    }
                 }
             }
         }
@@ -433,7 +450,13 @@ __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, 
             uint32_t out = NONE;
             bool slow = false;
             if (active) {
-                const bool hit = table_lookup<W>(p, kw, hash_key<W>(kw), out);
+                const uint32_t h = hash_key<W>(kw);
+                bool maybe = true;  // the Bloom filter (when present) rules out most reads that are in no table entry
+                if (p.bloom_words) {
+                    const uint32_t bm = bloom_mask(h);
+                    maybe = (s_bloom[h >> p.bloom_shift] & bm) == bm;
+                }
+                const bool hit = maybe && table_lookup<W>(p, kw, h, out);
                 slow = !hit && !read_in_table_alphabet<W>(kw, p.last_pad);
             }
             uint32_t pending = __ballot_sync(0xFFFFFFFFu, slow);
@@ -585,10 +608,16 @@ static cudaError_t launch_probe_w(const MatchParams& p, const ReadSource& src, u
     return cudaGetLastError();
 }
 
-size_t probe2_smem_bytes(const MatchParams& p, int threads) {
-    return (size_t)p.tier_slots * tier_entry_words((int)p.W) * 4 +
-           (size_t)(threads / 32) * PROBE2_QUEUE * (p.W + 1) * 4 + hist_bytes(p);
+size_t probe2_fixed_smem_bytes(uint32_t W, uint32_t S, int threads) {  // queues + histogram
+    return (size_t)(threads / 32) * PROBE2_QUEUE * (W + 1) * 4 + (S + 1u <= HIST_SMEM_BINS ? (S + 1u) * 4u : 0u);
 }
+
+size_t probe2_smem_bytes(const MatchParams& p, int threads) {
+    return (size_t)p.tier_slots * p.tier_rep * tier_entry_words((int)p.W) * 4 + (p.W == 4 ? (size_t)p.tier_slots * 4 : 0) +
+           (size_t)p.bloom_words * 4 + probe2_fixed_smem_bytes(p.W, p.S, threads);
+}
+
+int probe2_threads() { return PROBE2_THREADS; }
 
 template <int W>
 static cudaError_t launch_probe2_w(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
