@@ -95,17 +95,17 @@ FQ_HD uint32_t last_word_pad_for_len(uint32_t L) {
     return used == 0u ? 0u : (0x11111111u << (4u * used));
 }
 
-// 32-bit mix of a W-word key; identical on host (table build) and device (probe).
+// 32-bit mix of a W-word key; identical on host (table build) and device (probe): multiply-add over the words
+// (FMA pipe), then one xorshift-multiply round so that every output bit depends on every input nibble.
 template <int W>
 FQ_HD uint32_t hash_key(const uint32_t (&w)[W]) {
-    uint32_t h = 0x9E3779B9u;
-#pragma unroll
-    for (int i = 0; i < W; i++) {
-        h = (h ^ w[i]) * 0x85EBCA6Bu;
-        h ^= h >> 15;
-    }
-    h *= 0xC2B2AE35u;
-    h ^= h >> 16;
+    uint32_t h = w[0] * 0x9E3779B9u;
+    if constexpr (W > 1) h += w[W > 1 ? 1 : 0] * 0x85EBCA6Bu;
+    if constexpr (W > 2) h += w[W > 2 ? 2 : 0] * 0xC2B2AE35u;
+    if constexpr (W > 3) h += w[W > 3 ? 3 : 0] * 0x27D4EB2Fu;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 13;
     return h;
 }
 

@@ -336,6 +336,74 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe(const MatchParams p, co
 constexpr int PROBE2_R = 4;
 constexpr int PROBE2_QUEUE = 32 * PROBE2_R;
 
+// shared-memory access by 32-bit window address (keeps address arithmetic to one IMAD / IADD per access)
+FQ_D uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+FQ_D uint4 lds128_ro(uint32_t a) {  // read-only data (tier): may be scheduled freely
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+FQ_D uint2 lds64_ro(uint32_t a) {
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+FQ_D uint32_t lds32_ro(uint32_t a) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+FQ_D uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+FQ_D void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+template <int W>
+FQ_D void sts_key(uint32_t a, const uint32_t (&w)[W]) {
+    if constexpr (W == 1) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(w[0]) : "memory");
+    } else if constexpr (W == 2) {
+        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(w[0]), "r"(w[1]) : "memory");
+    } else if constexpr (W == 3) {
+        asm volatile("st.shared.u32 [%0], %1;\n\tst.shared.u32 [%0+4], %2;\n\tst.shared.u32 [%0+8], %3;" ::"r"(a), "r"(w[0]),
+                     "r"(w[W > 1 ? 1 : 0]), "r"(w[W > 2 ? 2 : 0])
+                     : "memory");
+    } else {
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(w[0]), "r"(w[W > 1 ? 1 : 0]),
+                     "r"(w[W > 2 ? 2 : 0]), "r"(w[W > 3 ? 3 : 0])
+                     : "memory");
+    }
+}
+template <int W>
+FQ_D void lds_key(uint32_t a, uint32_t (&w)[W]) {
+    if constexpr (W == 1) {
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[0]) : "r"(a) : "memory");
+    } else if constexpr (W == 2) {
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(a) : "memory");
+    } else if constexpr (W == 3) {
+        asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];"
+                     : "=r"(w[0]), "=r"(w[W > 1 ? 1 : 0]), "=r"(w[W > 2 ? 2 : 0])
+                     : "r"(a)
+                     : "memory");
+    } else {
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(w[0]), "=r"(w[W > 1 ? 1 : 0]), "=r"(w[W > 2 ? 2 : 0]), "=r"(w[W > 3 ? 3 : 0])
+                     : "r"(a)
+                     : "memory");
+    }
+}
+// histogram: hist[result >> 16] += 1 unless the result is NONE (predicated, no branch)
+FQ_D void red_hist(uint32_t hist_addr, uint32_t result) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 a;\n\t"
+        "setp.ne.u32 p, %1, 0xffffffff;\n\t"
+        "shr.u32 a, %1, 14;\n\tand.b32 a, a, 0x3fffc;\n\tadd.u32 a, a, %0;\n\t"
+        "@p red.shared.add.u32 [a], 1;\n\t}"
+        ::"r"(hist_addr), "r"(result)
+        : "memory");
+}
+
 template <int W>
 __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, const ReadSource src,
                                                            uint32_t* __restrict__ results) {
@@ -367,48 +435,68 @@ __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, 
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lane_lt = (1u << lane) - 1u;
-    uint32_t* q_keys = s_queue + (size_t)(threadIdx.x >> 5) * PROBE2_QUEUE * (W + 1);
-    uint32_t* q_res = q_keys + PROBE2_QUEUE * W;
+    const uint32_t warp_in_cta = threadIdx.x >> 5;
+    // 32-bit shared-window addresses, computed once
+    uint32_t a_tier = smem_addr(s_tier) + (lane & (rep - 1u)) * (TE * 4u);  // this lane's replica
+    const uint32_t tier_step = rep * TE * 4u;                                // bytes between slots of one replica
+    uint32_t a_qk = smem_addr(s_queue) + warp_in_cta * (PROBE2_QUEUE * (W + 1) * 4u);
+    uint32_t a_qr = a_qk + PROBE2_QUEUE * W * 4u;
+    uint32_t a_hist = smem_addr(s_hist);
+    const uint32_t a_tvals = smem_addr(s_tvals), a_bloom = smem_addr(s_bloom);
+    asm volatile("" : "+r"(a_tier), "+r"(a_qk), "+r"(a_qr), "+r"(a_hist));  // keep them in registers
     const uint32_t tshift = p.tier_shift;  // 32 - log2(tier_slots)
-    const uint32_t* my_tier = s_tier + (lane & (rep - 1u)) * TE;  // this lane's replica
-    const uint32_t tstride = rep * TE;                             // words between consecutive slots of one replica
+    const bool has_tier = tshift < 32u;
+    uint32_t none_count = 0;
 
     const uint32_t n_tiles = (uint32_t)(src.n / (uint64_t)PROBE2_QUEUE);
     const uint32_t warp_stride = gridDim.x * n_warps;
-    for (uint32_t tile = blockIdx.x * n_warps + (threadIdx.x >> 5); tile < n_tiles; tile += warp_stride) {
+    uint32_t tile = blockIdx.x * n_warps + warp_in_cta;
+
+    // software pipeline: the next tile's keys are in flight while this one is resolved
+    uint32_t nxt[R * W];
+    if (tile < n_tiles) {
+        const uint4* in = reinterpret_cast<const uint4*>(src.packed) + (size_t)(tile * 32u + lane) * W;
+#pragma unroll
+        for (int v = 0; v < W; v++) {
+            const uint4 q = __ldg(in + v);
+            nxt[4 * v + 0] = q.x;
+            nxt[4 * v + 1] = q.y;
+            nxt[4 * v + 2] = q.z;
+            nxt[4 * v + 3] = q.w;
+        }
+    }
+    for (; tile < n_tiles; tile += warp_stride) {
         const uint32_t g = tile * 32u + lane;  // this lane's group of 4 consecutive reads
         uint32_t w[R][W];
         uint32_t res[R];
-        {
-            uint32_t flat[R * W];
-            const uint4* in = reinterpret_cast<const uint4*>(src.packed) + (size_t)g * W;
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int k = 0; k < W; k++) w[r][k] = nxt[r * W + k];
+        if (tile + warp_stride < n_tiles) {
+            const uint4* in = reinterpret_cast<const uint4*>(src.packed) + (size_t)((tile + warp_stride) * 32u + lane) * W;
 #pragma unroll
             for (int v = 0; v < W; v++) {
                 const uint4 q = __ldg(in + v);
-                flat[4 * v + 0] = q.x;
-                flat[4 * v + 1] = q.y;
-                flat[4 * v + 2] = q.z;
-                flat[4 * v + 3] = q.w;
+                nxt[4 * v + 0] = q.x;
+                nxt[4 * v + 1] = q.y;
+                nxt[4 * v + 2] = q.z;
+                nxt[4 * v + 3] = q.w;
             }
-#pragma unroll
-            for (int r = 0; r < R; r++)
-#pragma unroll
-                for (int k = 0; k < W; k++) w[r][k] = flat[r * W + k];
         }
 
         // ---- tier 1: shared-memory cuckoo probe (a NONE value = empty slot = not found here) ----
 #pragma unroll
         for (int r = 0; r < R; r++) {
             res[r] = NONE;
-            if (tshift < 32u) {
+            if (has_tier) {
                 const uint32_t s1 = tier_hash1<W>(w[r]) >> tshift, s2 = tier_hash2<W>(w[r]) >> tshift;
+                const uint32_t a1 = a_tier + s1 * tier_step, a2 = a_tier + s2 * tier_step;
                 if constexpr (W == 1) {
-                    const uint2 a = *reinterpret_cast<const uint2*>(my_tier + s1 * tstride);
-                    const uint2 b = *reinterpret_cast<const uint2*>(my_tier + s2 * tstride);
+                    const uint2 a = lds64_ro(a1), b = lds64_ro(a2);
                     res[r] = (a.x == w[r][0]) ? a.y : ((b.x == w[r][0]) ? b.y : NONE);
                 } else {
-                    const uint4 a = *reinterpret_cast<const uint4*>(my_tier + s1 * tstride);
-                    const uint4 b = *reinterpret_cast<const uint4*>(my_tier + s2 * tstride);
+                    const uint4 a = lds128_ro(a1), b = lds128_ro(a2);
                     if constexpr (W == 2) {
                         const bool m1 = a.x == w[r][0] && a.y == w[r][1];
                         const bool m2 = b.x == w[r][0] && b.y == w[r][1];
@@ -420,7 +508,7 @@ __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, 
                     } else {
                         const bool m1 = a.x == w[r][0] && a.y == w[r][1] && a.z == w[r][W > 2 ? 2 : 0] && a.w == w[r][W > 3 ? 3 : 0];
                         const bool m2 = b.x == w[r][0] && b.y == w[r][1] && b.z == w[r][W > 2 ? 2 : 0] && b.w == w[r][W > 3 ? 3 : 0];
-                        if (m1 || m2) res[r] = s_tvals[m1 ? s1 : s2];
+                        if (m1 || m2) res[r] = lds32_ro(a_tvals + (m1 ? s1 : s2) * 4u);
                     }
                 }
             }
@@ -434,10 +522,7 @@ __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, 
             const bool pend = res[r] == NONE;
             const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pend);
             qi[r] = qcount + __popc(bal & lane_lt);
-            if (pend) {
-#pragma unroll
-                for (int k = 0; k < W; k++) q_keys[qi[r] * W + k] = w[r][k];
-            }
+            if (pend) sts_key<W>(a_qk + qi[r] * (W * 4u), w[r]);
             qcount += __popc(bal);
         }
         __syncwarp();
@@ -446,18 +531,19 @@ __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, 
             const bool active = q < qcount;
             uint32_t kw[W];
 #pragma unroll
-            for (int k = 0; k < W; k++) kw[k] = active ? q_keys[q * W + k] : 0u;
+            for (int k = 0; k < W; k++) kw[k] = 0u;
             uint32_t out = NONE;
             bool slow = false;
             if (active) {
+                lds_key<W>(a_qk + q * (W * 4u), kw);
                 const uint32_t h = hash_key<W>(kw);
                 bool maybe = true;  // the Bloom filter (when present) rules out most reads that are in no table entry
                 if (p.bloom_words) {
                     const uint32_t bm = bloom_mask(h);
-                    maybe = (s_bloom[h >> p.bloom_shift] & bm) == bm;
+                    maybe = (lds32_ro(a_bloom + (h >> p.bloom_shift) * 4u) & bm) == bm;
                 }
-                const bool hit = maybe && table_lookup<W>(p, kw, h, out);
-                slow = !hit && !read_in_table_alphabet<W>(kw, p.last_pad);
+                if (maybe) table_lookup<W>(p, kw, h, out);
+                slow = out == NONE && !read_in_table_alphabet<W>(kw, p.last_pad);
             }
             uint32_t pending = __ballot_sync(0xFFFFFFFFu, slow);
             while (pending) {
@@ -469,19 +555,23 @@ __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, 
                 const uint32_t o = warp_brute_one<W>(p, bw, lane);
                 if ((int)lane == src_lane) out = o;
             }
-            if (active) q_res[q] = out;
+            if (active) sts32(a_qr + q * 4u, out);
         }
         __syncwarp();
         // every read that went through the queue had res == NONE; a queue result of NONE leaves it NONE
 #pragma unroll
         for (int r = 0; r < R; r++)
-            if (res[r] == NONE) res[r] = q_res[qi[r]];
+            if (res[r] == NONE) res[r] = lds32(a_qr + qi[r] * 4u);
         __syncwarp();  // the queue is reused by the next tile
 
         reinterpret_cast<uint4*>(results)[g] = make_uint4(res[0], res[1], res[2], res[3]);
 #pragma unroll
-        for (int r = 0; r < R; r++) cnt.add(res[r]);
+        for (int r = 0; r < R; r++) {
+            red_hist(a_hist, res[r]);
+            none_count += (res[r] == NONE);
+        }
     }
+    cnt.none_local = none_count;
 
     // ---- tail: fewer than 128 reads, one per lane, first warp of the grid ----
     if (blockIdx.x == 0 && threadIdx.x < 32u) {
