@@ -130,29 +130,27 @@ struct Enumerator {
     }
 };
 
-// Insert into the bucketised memo table (kernels.h: 32-byte buckets, linear probing over buckets).
+// Insert into the memo table (kernels.h: one slot per probe, linear probing).
 template <int W>
-void host_insert(std::vector<uint32_t>& table, uint32_t n_buckets, const uint32_t* key, uint32_t val,
+void host_insert(std::vector<uint32_t>& table, uint32_t n_slots, const uint32_t* key, uint32_t val,
                  uint64_t& inserted) {
     uint32_t kw[W];
     for (int k = 0; k < W; k++) kw[k] = key[k];
-    uint32_t b = fq::bucket_of_hash(fq::hash_key<W>(kw), n_buckets);
-    constexpr int EPB = W <= 3 ? 2 : 1, EW = 8 / EPB, VI = W <= 3 ? 3 : 4;
+    uint32_t b = fq::bucket_of_hash(fq::hash_key<W>(kw), n_slots);
+    const int SW = fq::table_slot_words(W), VI = fq::table_value_index(W);
     for (;;) {
-        for (int e = 0; e < EPB; e++) {
-            uint32_t* ent = table.data() + (size_t)b * 8 + (size_t)e * EW;
-            if (ent[VI] == fq::NONE) {
-                for (int k = 0; k < EW; k++) ent[k] = 0u;
-                for (int k = 0; k < W; k++) ent[k] = kw[k];
-                ent[VI] = val;
-                inserted++;
-                return;
-            }
-            bool same = true;
-            for (int k = 0; k < W; k++) same = same && ent[k] == kw[k];
-            if (same) return;  // the same string reached from two barcodes: identical value by construction
+        uint32_t* ent = table.data() + (size_t)b * SW;
+        if (ent[VI] == fq::NONE) {
+            for (int k = 0; k < SW; k++) ent[k] = 0u;
+            for (int k = 0; k < W; k++) ent[k] = kw[k];
+            ent[VI] = val;
+            inserted++;
+            return;
         }
-        b = (b + 1u == n_buckets) ? 0u : b + 1u;
+        bool same = true;
+        for (int k = 0; k < W; k++) same = same && ent[k] == kw[k];
+        if (same) return;  // the same string reached from two barcodes: identical value by construction
+        b = (b + 1u == n_slots) ? 0u : b + 1u;
     }
 }
 
@@ -257,14 +255,14 @@ int build_table(fqtk_b200_matcher* m) {
 
     uint64_t n_some = 0;
     for (uint64_t t = 0; t < n; t++) n_some += res[t] != fq::NONE;
-    const int EPB = fq::table_entries_per_bucket((int)W);
-    // load factor: 0.2 while the table stays small (a probe almost never leaves its first bucket), 0.45 beyond 32 MB
-    const uint64_t pct = (n_some * 32 * 100 / (20 * EPB) <= (32ull << 20)) ? 20 : 45;
-    uint64_t buckets64 = (n_some * 100 + pct * EPB - 1) / (pct * EPB);
-    if (buckets64 < 64) buckets64 = 64;
-    if (buckets64 >= (1ull << 31)) return 1;
-    const uint32_t n_buckets = (uint32_t)buckets64;
-    std::vector<uint32_t> table((size_t)n_buckets * 8, 0xFFFFFFFFu);
+    // load factor: 0.2 while the table stays small (a probe almost never goes past its first slot), 0.4 beyond 64 MB
+    const int SW = fq::table_slot_words((int)W);
+    const uint64_t pct = (n_some * SW * 4 * 100 / 20 <= (64ull << 20)) ? 20 : 40;
+    uint64_t slots64 = (n_some * 100 + pct - 1) / pct;
+    if (slots64 < 64) slots64 = 64;
+    if (slots64 >= (1ull << 31)) return 1;
+    const uint32_t n_buckets = (uint32_t)slots64;
+    std::vector<uint32_t> table((size_t)n_buckets * SW, 0xFFFFFFFFu);
     uint64_t inserted = 0;
     for (uint64_t t = 0; t < n; t++) {
         if (res[t] == fq::NONE) continue;
@@ -279,7 +277,7 @@ int build_table(fqtk_b200_matcher* m) {
     CU(cudaMalloc(&m->d_table, table.size() * 4));
     CU(cudaMemcpy(m->d_table, table.data(), table.size() * 4, cudaMemcpyHostToDevice));
     m->table_entries = inserted;
-    m->table_slots = (uint64_t)n_buckets * EPB;
+    m->table_slots = n_buckets;
     m->table_bytes = table.size() * 4;
     m->params.table = m->d_table;
     m->params.n_buckets = n_buckets;
@@ -504,6 +502,7 @@ int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t S, uint32_t L,
     m->params.tier_slots = 0;
     m->params.tier_shift = 32;
     m->params.tier_rep = 1;
+    m->params.hist_rep = fq::probe2_hist_rep(S);
     m->params.bloom = nullptr;
     m->params.bloom_words = 0;
     m->params.bloom_shift = 32;

@@ -10,7 +10,7 @@ struct MatchParams {
     const uint4* planes;       // [S * P] "forbidden base" bit-planes per barcode: .x/.y/.z/.w bit i set iff position
                                //  32*p + i of the barcode does NOT admit A/C/G/T
     const uint32_t* not_exp;   // [S * W] ~expected nibble words (only read by the L > 32 kernel)
-    const uint32_t* table;     // memo table: 32-byte buckets in global memory (nullptr in brute mode)
+    const uint32_t* table;     // memo table slots in global memory (nullptr in brute mode)
     const uint32_t* tier_entries;  // hot tier (table entries whose best distance is 0), staged into shared memory by
                                    //   k_probe2: 2-choice cuckoo, tier_slots entries of tier_entry_words(W) words
                                    //   (W = 4: tier_slots x 4 key words, then tier_slots value words)
@@ -19,11 +19,12 @@ struct MatchParams {
     uint32_t S, L, W, P;
     uint32_t max_mm, min_delta;
     uint32_t last_pad;         // 0x1 in every padding nibble of the last packed word
-    uint32_t n_buckets;        // memo-table buckets
+    uint32_t n_buckets;        // memo-table slots
     uint32_t tier_slots;       // power of two, 0 = no hot tier
     uint32_t tier_shift;       // 32 - log2(tier_slots); 32 = no hot tier
     uint32_t tier_rep;         // shared-memory replicas of the hot tier (power of two): lane l reads replica l % rep, so
                                //   lanes of a warp spread over distinct banks whatever slots they probe
+    uint32_t hist_rep;         // shared-memory replicas of the k_probe2 histogram (power of two <= 32)
     uint32_t bloom_words;      // power of two, 0 = no filter
     uint32_t bloom_shift;      // 32 - log2(bloom_words)
 };
@@ -42,12 +43,14 @@ struct LaunchGeometry {
     int max_smem_optin;
 };
 
-// Memo-table geometry.  A bucket is 32 bytes = one DRAM/L2 sector, fetched with one 256-bit load.
-//   W <= 3: two entries {k0, k1, k2, value} (missing key words are 0);  W == 4: one entry {k0..k3, value, 0, 0, 0}.
+// Memo-table geometry: open addressing, linear probing, one slot per probe.
+//   W <= 3: 16-byte slots {k0, k1, k2, value} (missing key words are 0), one LDG.128 per probe;
+//   W == 4: 32-byte slots {k0..k3, value, 0, 0, 0}, one 256-bit load per probe.
+// Empty slots are all-ones (value NONE).  `n_buckets` is the slot count.
+inline __host__ __device__ int table_slot_words(int W) { return W <= 3 ? 4 : 8; }
+inline __host__ __device__ int table_value_index(int W) { return W <= 3 ? 3 : 4; }
 // Hot-tier entries: W = 1: {k0, value}; W = 2: {k0, k1, value, 0}; W = 3: {k0, k1, k2, value};
 //   W = 4: {k0, k1, k2, k3} with the values in a separate array.  Empty slots are all-ones (value NONE).
-constexpr int TABLE_BUCKET_WORDS = 8;
-inline __host__ __device__ int table_entries_per_bucket(int W) { return W <= 3 ? 2 : 1; }
 inline __host__ __device__ int tier_entry_words(int W) { return W == 1 ? 2 : 4; }
 inline __host__ __device__ int tier_value_index(int W) { return W == 1 ? 1 : (W == 2 ? 2 : 3); }  // W = 4: separate array
 inline __host__ __device__ int tier_max_rep(int W) { return W == 1 ? 16 : 8; }  // replicas that tile all 32 banks once
@@ -62,6 +65,7 @@ cudaError_t prepare_kernels(const LaunchGeometry& g);  // opt-in shared memory a
 
 size_t probe2_fixed_smem_bytes(uint32_t W, uint32_t S, int threads);  // k_probe2 shared memory besides tier + Bloom
 int probe2_threads();
+uint32_t probe2_hist_rep(uint32_t S);
 
 uint64_t kernel_launches();
 void count_launch();

@@ -238,35 +238,34 @@ FQ_D uint32_t warp_brute_one(const MatchParams& p, const uint32_t (&w)[W], uint3
     return decide(k1, k2, p.max_mm, p.min_delta);
 }
 
-// One 32-byte bucket = one sector, fetched with a single 256-bit load (LDG.E.ENL2.256 on sm_100a).
-FQ_D void load_bucket(const uint32_t* __restrict__ table, uint32_t bucket, uint32_t (&e)[8]) {
-    const uint32_t* q = table + (size_t)bucket * TABLE_BUCKET_WORDS;
+// Memo-table slots (kernels.h): W <= 3 -> 16 bytes {k0, k1, k2, value}, one LDG.128 per probe;
+// W = 4 -> 32 bytes {k0..k3, value, pad}, one 256-bit load (LDG.E.ENL2.256 on sm_100a) per probe.
+FQ_D void load_slot32(const uint32_t* __restrict__ table, uint32_t slot, uint32_t (&e)[8]) {
+    const uint32_t* q = table + (size_t)slot * 8;
     asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(e[0]), "=r"(e[1]), "=r"(e[2]), "=r"(e[3]), "=r"(e[4]), "=r"(e[5]), "=r"(e[6]), "=r"(e[7])
                  : "l"(q));
 }
 
-// One memo-table lookup: bucketised linear probing, single-exit loop; an empty entry in a bucket ends the probe.
+// One memo-table lookup: linear probing, single-exit loop; an empty slot (value NONE) ends the probe.
 // Returns true on a hit (res = stored Some(..) word); res is NONE otherwise.
 template <int W>
 FQ_D bool table_lookup(const MatchParams& p, const uint32_t (&w)[W], uint32_t h, uint32_t& res) {
     uint32_t b = bucket_of_hash(h, p.n_buckets);
     for (;;) {
-        uint32_t e[8];
-        load_bucket(p.table, b, e);
-        bool end;
+        uint32_t v;  // the probed slot's value
         if constexpr (W <= 3) {
+            const uint4 e = __ldg(reinterpret_cast<const uint4*>(p.table) + b);
             const uint32_t k1 = W > 1 ? w[W > 1 ? 1 : 0] : 0u, k2 = W > 2 ? w[W > 2 ? 2 : 0] : 0u;
-            const bool m0 = e[0] == w[0] && e[1] == k1 && e[2] == k2;
-            const bool m1 = e[4] == w[0] && e[5] == k1 && e[6] == k2;
-            res = m0 ? e[3] : (m1 ? e[7] : NONE);  // an empty entry's all-ones key may equal an all-N read: value NONE
-            end = res != NONE || e[3] == NONE || e[7] == NONE;
-        } else {
-            const bool m0 = e[0] == w[0] && e[1] == w[1] && e[2] == w[2] && e[3] == w[3];
-            res = m0 ? e[4] : NONE;
-            end = res != NONE || e[4] == NONE;
+            v = e.w;
+            res = (e.x == w[0] && e.y == k1 && e.z == k2) ? v : NONE;  // an empty slot's all-ones key may equal an
+        } else {                                                        // all-N read: its value is NONE anyway
+            uint32_t e[8];
+            load_slot32(p.table, b, e);
+            v = e[4];
+            res = (e[0] == w[0] && e[1] == w[1] && e[2] == w[2] && e[3] == w[3]) ? v : NONE;
         }
-        if (end) break;
+        if (res != NONE || v == NONE) break;
         b = (b + 1u == p.n_buckets) ? 0u : b + 1u;
     }
     return res != NONE;
@@ -334,7 +333,9 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe(const MatchParams p, co
 //   3. reads outside the table's alphabet: warp-cooperative brute force (same as k_probe).
 // The < 128-read tail of a batch is finished by one warp with the one-read-per-lane code of k_probe.
 constexpr int PROBE2_R = 4;
-constexpr int PROBE2_QUEUE = 32 * PROBE2_R;
+constexpr int PROBE2_TILE = 32 * PROBE2_R;   // reads per warp tile
+constexpr int PROBE2_QUEUE = PROBE2_TILE;    // queue entries per warp: every read of a tile may be unresolved
+constexpr uint32_t PROBE2_HIST_BYTES = 25u << 10;  // shared memory the replicated histogram may take
 
 // shared-memory access by 32-bit window address (keeps address arithmetic to one IMAD / IADD per access)
 FQ_D uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -393,31 +394,32 @@ FQ_D void lds_key(uint32_t a, uint32_t (&w)[W]) {
                      : "memory");
     }
 }
-// histogram: hist[result >> 16] += 1 unless the result is NONE (predicated, no branch)
-FQ_D void red_hist(uint32_t hist_addr, uint32_t result) {
+// histogram: hist[(result >> 16) * hrep + lane % hrep] += 1 unless the result is NONE (predicated, no branch).
+// `hist_lane_addr` already includes the lane's replica offset; `hshift` = log2(hrep * 4 bytes).
+FQ_D void red_hist(uint32_t hist_lane_addr, uint32_t hshift, uint32_t result) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .u32 a;\n\t"
-        "setp.ne.u32 p, %1, 0xffffffff;\n\t"
-        "shr.u32 a, %1, 14;\n\tand.b32 a, a, 0x3fffc;\n\tadd.u32 a, a, %0;\n\t"
+        "setp.ne.u32 p, %2, 0xffffffff;\n\t"
+        "shr.u32 a, %2, 16;\n\tshl.b32 a, a, %1;\n\tadd.u32 a, a, %0;\n\t"
         "@p red.shared.add.u32 [a], 1;\n\t}"
-        ::"r"(hist_addr), "r"(result)
+        ::"r"(hist_lane_addr), "r"(hshift), "r"(result)
         : "memory");
 }
 
 template <int W>
-__global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, const ReadSource src,
+__global__ void __launch_bounds__(PROBE2_THREADS, 1) k_probe2(const MatchParams p, const ReadSource src,
                                                            uint32_t* __restrict__ results) {
     constexpr int R = PROBE2_R;
     constexpr int TE = W == 1 ? 2 : 4;  // tier entry words (kernels.h)
     extern __shared__ uint4 s_dyn[];
-    // layout: tier replicas | (W = 4: tier values) | Bloom words | per-warp queues (keys, results) | histogram
+    // layout: tier replicas | (W = 4: tier values) | Bloom words | per-warp queues | histogram replicas
     uint32_t* s_tier = reinterpret_cast<uint32_t*>(s_dyn);
     const uint32_t rep = p.tier_rep;
     uint32_t* s_tvals = s_tier + (size_t)p.tier_slots * rep * TE;
     uint32_t* s_bloom = s_tvals + (W == 4 ? p.tier_slots : 0u);
     uint32_t* s_queue = s_bloom + p.bloom_words;
     const uint32_t n_warps = blockDim.x >> 5;
-    uint32_t* s_hist = s_queue + (size_t)n_warps * PROBE2_QUEUE * (W + 1);
+    uint32_t* s_hist = s_queue + (size_t)n_warps * PROBE2_QUEUE * W;
 
     // entry e, replica r lives at word (e * rep + r) * TE: with rep = 8 (16 with 8-byte entries) replica r owns one
     // fixed group of banks, so the 32 lanes of a probe hit every bank group exactly 4 (2) times — no conflicts
@@ -429,8 +431,10 @@ __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, 
         for (uint32_t t = threadIdx.x; t < p.tier_slots; t += blockDim.x)
             s_tvals[t] = __ldg(p.tier_entries + (size_t)p.tier_slots * TE + t);
     for (uint32_t t = threadIdx.x; t < p.bloom_words; t += blockDim.x) s_bloom[t] = __ldg(p.bloom + t);
-    Counter cnt;
-    cnt.init(s_hist, p);
+    // histogram replicas: bin b of replica r at word b * hrep + r, lane l adds into replica l % hrep, so the lanes of
+    // one RED spread over distinct banks; the replicas are summed when the CTA flushes
+    const uint32_t hrep = p.hist_rep;
+    for (uint32_t t = threadIdx.x; t < (p.S + 1u) * hrep; t += blockDim.x) s_hist[t] = 0u;
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31u;
@@ -439,16 +443,16 @@ __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, 
     // 32-bit shared-window addresses, computed once
     uint32_t a_tier = smem_addr(s_tier) + (lane & (rep - 1u)) * (TE * 4u);  // this lane's replica
     const uint32_t tier_step = rep * TE * 4u;                                // bytes between slots of one replica
-    uint32_t a_qk = smem_addr(s_queue) + warp_in_cta * (PROBE2_QUEUE * (W + 1) * 4u);
-    uint32_t a_qr = a_qk + PROBE2_QUEUE * W * 4u;
-    uint32_t a_hist = smem_addr(s_hist);
+    uint32_t a_qk = smem_addr(s_queue) + warp_in_cta * (PROBE2_QUEUE * W * 4u);  // entry q: key in, result out (word 0)
+    uint32_t a_hist = smem_addr(s_hist) + (lane & (hrep - 1u)) * 4u;
+    const uint32_t hshift = 2u + (uint32_t)__popc(hrep - 1u);
     const uint32_t a_tvals = smem_addr(s_tvals), a_bloom = smem_addr(s_bloom);
-    asm volatile("" : "+r"(a_tier), "+r"(a_qk), "+r"(a_qr), "+r"(a_hist));  // keep them in registers
+    asm volatile("" : "+r"(a_tier), "+r"(a_qk), "+r"(a_hist));  // keep them in registers
     const uint32_t tshift = p.tier_shift;  // 32 - log2(tier_slots)
     const bool has_tier = tshift < 32u;
     uint32_t none_count = 0;
 
-    const uint32_t n_tiles = (uint32_t)(src.n / (uint64_t)PROBE2_QUEUE);
+    const uint32_t n_tiles = (uint32_t)(src.n / (uint64_t)PROBE2_TILE);
     const uint32_t warp_stride = gridDim.x * n_warps;
     uint32_t tile = blockIdx.x * n_warps + warp_in_cta;
 
@@ -555,27 +559,26 @@ __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, 
                 const uint32_t o = warp_brute_one<W>(p, bw, lane);
                 if ((int)lane == src_lane) out = o;
             }
-            if (active) sts32(a_qr + q * 4u, out);
+            if (active) sts32(a_qk + q * (W * 4u), out);  // the entry's key has been consumed: reuse it for the result
         }
         __syncwarp();
         // every read that went through the queue had res == NONE; a queue result of NONE leaves it NONE
 #pragma unroll
         for (int r = 0; r < R; r++)
-            if (res[r] == NONE) res[r] = lds32(a_qr + qi[r] * 4u);
+            if (res[r] == NONE) res[r] = lds32(a_qk + qi[r] * (W * 4u));
         __syncwarp();  // the queue is reused by the next tile
 
         reinterpret_cast<uint4*>(results)[g] = make_uint4(res[0], res[1], res[2], res[3]);
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            red_hist(a_hist, res[r]);
+            red_hist(a_hist, hshift, res[r]);
             none_count += (res[r] == NONE);
         }
     }
-    cnt.none_local = none_count;
 
     // ---- tail: fewer than 128 reads, one per lane, first warp of the grid ----
     if (blockIdx.x == 0 && threadIdx.x < 32u) {
-        for (uint64_t base = (uint64_t)n_tiles * PROBE2_QUEUE; base < src.n; base += 32u) {
+        for (uint64_t base = (uint64_t)n_tiles * PROBE2_TILE; base < src.n; base += 32u) {
             const uint64_t i = base + lane;
             const bool valid = i < src.n;
             uint32_t kw[W];
@@ -599,11 +602,21 @@ __global__ void __launch_bounds__(PROBE2_THREADS) k_probe2(const MatchParams p, 
             }
             if (valid) {
                 results[i] = out;
-                cnt.add(out);
+                red_hist(a_hist, hshift, out);
+                none_count += (out == NONE);
             }
         }
     }
-    cnt.flush();
+    // flush: unmatched from registers (one RED per warp), then the replicated bins
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) none_count += __shfl_xor_sync(0xFFFFFFFFu, none_count, off);
+    if (lane == 0u && none_count) atomicAdd(&s_hist[p.S * hrep], none_count);
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b <= p.S; b += blockDim.x) {
+        uint32_t c = 0;
+        for (uint32_t r = 0; r < hrep; r++) c += s_hist[b * hrep + r];
+        if (c) atomicAdd(&p.counts[b], (unsigned long long)c);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -698,8 +711,14 @@ static cudaError_t launch_probe_w(const MatchParams& p, const ReadSource& src, u
     return cudaGetLastError();
 }
 
-size_t probe2_fixed_smem_bytes(uint32_t W, uint32_t S, int threads) {  // queues + histogram
-    return (size_t)(threads / 32) * PROBE2_QUEUE * (W + 1) * 4 + (S + 1u <= HIST_SMEM_BINS ? (S + 1u) * 4u : 0u);
+uint32_t probe2_hist_rep(uint32_t S) {  // histogram replicas (power of two <= 32) within PROBE2_HIST_BYTES
+    uint32_t rep = 32;
+    while (rep > 1 && (size_t)(S + 1u) * rep * 4u > PROBE2_HIST_BYTES) rep >>= 1;
+    return rep;
+}
+
+size_t probe2_fixed_smem_bytes(uint32_t W, uint32_t S, int threads) {  // queues + replicated histogram
+    return (size_t)(threads / 32) * PROBE2_QUEUE * W * 4 + (size_t)(S + 1u) * probe2_hist_rep(S) * 4u;
 }
 
 size_t probe2_smem_bytes(const MatchParams& p, int threads) {
