@@ -254,6 +254,7 @@ def run_b200(args):
 
     from fqtk_b200 import BarcodeMatcher, _lib, synth
     from fqtk_b200.barcode_matching import kernel_launches
+    from fqtk_b200.distributed import all_reduce_counts, tensor_from_device_ptr, weak_shard_first_read
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -275,7 +276,7 @@ def run_b200(args):
     # each rank synthesises its own shard [rank*n, (rank+1)*n) of the stream straight into HBM (weak scaling)
     d_packed = torch.empty((n, W), dtype=torch.int32, device=dev)
     d_res = torch.empty(n, dtype=torch.int32, device=dev)
-    synth.reads_device(panel, cfg.seed_reads, rank * n, n, 0, d_packed.data_ptr(), stream)
+    synth.reads_device(panel, cfg.seed_reads, weak_shard_first_read(n, rank), n, 0, d_packed.data_ptr(), stream)
     matcher = BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, use_cache=(args.mode != "brute"),
                              device=local)
     if args.mode == "table" and matcher.mode != "table":
@@ -312,8 +313,8 @@ def run_b200(args):
     if world > 1:
         # the single collective of the path: the final per-sample count table (S+1 u64) summed over NVLink
         # (int64 view of the matcher's own device counters; cudaMemcpyAsync-free: same stream ordering)
-        counts_t.copy_(_tensor_from_ptr(torch, matcher.counts_device_ptr(), cfg.n_samples + 1, dev))
-        dist.all_reduce(counts_t, op=dist.ReduceOp.SUM)
+        counts_t.copy_(tensor_from_device_ptr(matcher.counts_device_ptr(), cfg.n_samples + 1, dev))
+        all_reduce_counts(counts_t)
     evs[args.steps + 1].record()
     barrier()
     launches = kernel_launches() - launches0
@@ -327,7 +328,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     if world == 1:
-        counts_t.copy_(_tensor_from_ptr(torch, matcher.counts_device_ptr(), cfg.n_samples + 1, dev))
+        counts_t.copy_(tensor_from_device_ptr(matcher.counts_device_ptr(), cfg.n_samples + 1, dev))
     counts = counts_t.cpu().numpy()
     assert int(counts.sum()) == n * args.steps * world, "per-sample counts must add up to every read processed"
     value = n * args.steps * world / (total_ms * 1e-3) / 1e6
@@ -339,7 +340,7 @@ def run_b200(args):
     achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-        "traffic": ncu_traffic(args.config, mode), "kernel": "k_probe" if mode == "table" else "k_brute",
+        "traffic": ncu_traffic(args.config, mode), "kernel": "k_probe2" if mode == "table" else "k_brute",
         "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_read": cfg.algorithmic_bytes_per_read,
         "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
         "pair_compares_per_s": round(n * cfg.n_samples / (k_ms * 1e-3), 1) if mode == "brute" else None,
@@ -378,7 +379,7 @@ def run_b200(args):
         while ne * (L + 4) * max(1, min(world, 8)) > 0.25 * avail and ne > (1 << 20):
             ne //= 2
         d_ascii = torch.empty((ne, L), dtype=torch.uint8, device=dev)
-        synth.reads_device(panel, cfg.seed_reads, rank * n, ne, d_ascii.data_ptr(), 0, stream)
+        synth.reads_device(panel, cfg.seed_reads, weak_shard_first_read(n, rank), ne, d_ascii.data_ptr(), 0, stream)
         h_in, h_out = C.c_void_p(), C.c_void_p()
         _lib.check(_lib.lib().fqtk_b200_host_alloc(C.byref(h_in), ne * L))
         _lib.check(_lib.lib().fqtk_b200_host_alloc(C.byref(h_out), ne * 4))
@@ -435,16 +436,6 @@ def run_b200(args):
     matcher.close()
     if world > 1:
         dist.destroy_process_group()
-
-
-def _tensor_from_ptr(torch, ptr, n, dev):
-    """int64 torch view of a raw device pointer owned by the matcher (its u64 count table)."""
-    class _Holder:
-        pass
-
-    h = _Holder()
-    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
-    return torch.as_tensor(h, device=dev)
 
 
 def main():

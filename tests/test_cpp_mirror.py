@@ -1,0 +1,30 @@
+"""Builds and runs the C++ host-mirror test (tests/cpp/test_barcode_matching.cpp): the reference's own assign()
+test cases, written against include/fqtk_b200.hpp, linked straight to the C-ABI library."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIBDIR = os.path.join(ROOT, "fqtk_b200")
+
+
+def _build(tmp_path):
+    exe = str(tmp_path / "test_barcode_matching")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", "test_barcode_matching.cpp"), "-o", exe,
+           "-L", LIBDIR, "-lfqtk_b200", f"-Wl,-rpath,{LIBDIR}"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return exe
+
+
+def test_cpp_mirror_compiles_against_the_c_abi(tmp_path):
+    assert os.path.exists(_build(tmp_path))
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_reference_cases(tmp_path):
+    exe = _build(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all reference assign cases pass" in r.stdout
