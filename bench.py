@@ -106,7 +106,7 @@ def cpu_baseline(cfg, panel, seconds, all_cores=True):
                   f"(demux.rs:945-977 is serial)",
     }
     if all_cores:
-        cores = oracle.max_threads()
+        cores = os.cpu_count() or oracle.max_threads()  # explicit: torchrun exports OMP_NUM_THREADS=1
         vN, used, countsN = time_oracle(cfg, panel, reads, cores)
         assert np.array_equal(counts1, countsN)
         out["all_cores_upper_bound"] = {
@@ -219,7 +219,7 @@ def run_reference(args):
         m.assign_batch(reads, want_results=True)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt / 1e6
-    cores_all = oracle.max_threads()
+    cores_all = os.cpu_count() or oracle.max_threads()  # explicit: torchrun exports OMP_NUM_THREADS=1
     vN, used, _ = time_oracle(cfg, panel, reads, cores_all)
     sample = (f"each step = the first {n} reads of the config's synthetic stream (of {cfg.n_reads}), in host memory; "
               f"literal C restatement of BarcodeMatcher::assign with memo cache on, 1 thread (the reference's matcher "

@@ -60,6 +60,7 @@ struct fqtk_b200_matcher {
     uint32_t max_ns = 0;
     std::vector<uint8_t> panel;  // upper-cased ASCII, S x L
     uint4* d_planes = nullptr;
+    uint4* d_planes2 = nullptr;
     uint32_t* d_not_exp = nullptr;
     uint32_t* d_table = nullptr;
     uint32_t* d_tier = nullptr;
@@ -453,7 +454,7 @@ int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t S, uint32_t L,
         m->max_ns = std::max(m->max_ns, ns);
     }
     const uint32_t W = m->W, P = m->P;
-    std::vector<uint4> planes((size_t)S * P, make_uint4(0, 0, 0, 0));
+    std::vector<uint4> planes((size_t)(S + 1) * P, make_uint4(0, 0, 0, 0));  // one spare entry: pairs of barcodes
     std::vector<uint32_t> not_exp((size_t)S * W, 0u);
     for (uint32_t j = 0; j < S; j++) {
         for (uint32_t i = 0; i < L; i++) {
@@ -468,6 +469,19 @@ int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t S, uint32_t L,
             if (forbid & 8u) q.w |= bit;
         }
     }
+    std::vector<uint4> planes2;
+    if (L <= 16) {  // two barcodes per plane word for k_brute<.., PK = 2>
+        planes2.assign((S + 1) / 2, make_uint4(0, 0, 0, 0));
+        for (uint32_t j = 0; j < S; j++) {
+            const uint4 q = planes[j];
+            uint4& d = planes2[j / 2];
+            const uint32_t sh = (j & 1u) ? 16u : 0u;
+            d.x |= q.x << sh;
+            d.y |= q.y << sh;
+            d.z |= q.z << sh;
+            d.w |= q.w << sh;
+        }
+    }
     int rc = FQTK_B200_OK;
     auto bail = [&](int code) {
         fqtk_b200_matcher_destroy(m);
@@ -480,6 +494,10 @@ int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t S, uint32_t L,
     } while (0)
     CUB(cudaMalloc(&m->d_planes, planes.size() * sizeof(uint4)));
     CUB(cudaMemcpy(m->d_planes, planes.data(), planes.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    if (!planes2.empty()) {
+        CUB(cudaMalloc(&m->d_planes2, planes2.size() * sizeof(uint4)));
+        CUB(cudaMemcpy(m->d_planes2, planes2.data(), planes2.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    }
     CUB(cudaMalloc(&m->d_not_exp, not_exp.size() * 4));
     CUB(cudaMemcpy(m->d_not_exp, not_exp.data(), not_exp.size() * 4, cudaMemcpyHostToDevice));
     CUB(cudaMalloc(&m->d_counts, (size_t)(S + 1) * 8));
@@ -487,6 +505,7 @@ int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t S, uint32_t L,
     for (int s = 0; s < N_PIPE; s++) CUB(cudaStreamCreateWithFlags(&m->streams[s], cudaStreamNonBlocking));
 #undef CUB
     m->params.planes = m->d_planes;
+    m->params.planes2 = m->d_planes2;
     m->params.not_exp = m->d_not_exp;
     m->params.table = nullptr;
     m->params.counts = m->d_counts;
@@ -530,6 +549,7 @@ void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m) {
     }
     if (m->d_scratch) cudaFree(m->d_scratch);
     if (m->d_planes) cudaFree(m->d_planes);
+    if (m->d_planes2) cudaFree(m->d_planes2);
     if (m->d_not_exp) cudaFree(m->d_not_exp);
     if (m->d_table) cudaFree(m->d_table);
     if (m->d_tier) cudaFree(m->d_tier);

@@ -9,6 +9,8 @@ namespace fq {
 struct MatchParams {
     const uint4* planes;       // [S * P] "forbidden base" bit-planes per barcode: .x/.y/.z/.w bit i set iff position
                                //  32*p + i of the barcode does NOT admit A/C/G/T
+    const uint4* planes2;      // L <= 16 only: [ceil(S/2)] the planes of barcodes 2q (low 16 bits) and 2q+1 (high 16 bits)
+                               //  packed into one word each; planes[] itself is padded to an even number of entries
     const uint32_t* not_exp;   // [S * W] ~expected nibble words (only read by the L > 32 kernel)
     const uint32_t* table;     // memo table slots in global memory (nullptr in brute mode)
     const uint32_t* tier_entries;  // hot tier (table entries whose best distance is 0), staged into shared memory by

@@ -140,24 +140,57 @@ struct Counter {
 
 // ------------------------------------------------------------------------------------------------------
 // k_brute: thread per read, panel planes in shared memory (or global when they do not fit)
+//
+// Barcodes are taken two at a time so the running best / second-best lives in u16x2 SIMD registers
+// (VIMNMX.U16x2: 3 instructions per TWO barcodes).  PK = 2 (L <= 16) additionally packs the two barcodes' forbidden
+// planes into the two 16-bit halves of one plane word, so the 4 logic ops are shared as well.
+// The SIMD lanes track distances only; the sample index comes from a coarse tag: after every chunk of
+// BRUTE_CHUNK_PAIRS pairs a strict improvement of the best distance records the chunk, and that one chunk is
+// re-scanned at the end for the FIRST index with the best distance (strict '<' at barcode_matching.rs:132).
 // ------------------------------------------------------------------------------------------------------
-template <int W, bool ASCII, bool PANEL_SMEM>
+constexpr uint32_t BRUTE_CHUNK_PAIRS = 8;  // 16 barcodes per chunk
+
+FQ_D uint32_t vmin2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
+FQ_D uint32_t vmax2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
+
+// distances of the pair's two barcodes, packed {d_odd : d_even} as u16x2
+template <int PK, bool PANEL_SMEM>
+FQ_D uint32_t pair_distances(const uint4* __restrict__ planes, uint32_t pair, const uint32_t (&pl)[4]) {
+    if constexpr (PK == 2) {
+        const uint4 nb = PANEL_SMEM ? planes[pair] : __ldg(planes + pair);
+        const uint32_t m = (pl[0] & nb.x) | (pl[1] & nb.y) | (pl[2] & nb.z) | (pl[3] & nb.w);
+        return (uint32_t)__popc(m >> 16) * 65536u + (uint32_t)__popc(m & 0xFFFFu);
+    } else {
+        const uint4 n0 = PANEL_SMEM ? planes[2u * pair] : __ldg(planes + 2u * pair);
+        const uint4 n1 = PANEL_SMEM ? planes[2u * pair + 1u] : __ldg(planes + 2u * pair + 1u);
+        const uint32_t m0 = (pl[0] & n0.x) | (pl[1] & n0.y) | (pl[2] & n0.z) | (pl[3] & n0.w);
+        const uint32_t m1 = (pl[0] & n1.x) | (pl[1] & n1.y) | (pl[2] & n1.z) | (pl[3] & n1.w);
+        return (uint32_t)__popc(m1) * 65536u + (uint32_t)__popc(m0);
+    }
+}
+
+template <int W, bool ASCII, bool PANEL_SMEM, int PK>
 __global__ void __launch_bounds__(BRUTE_THREADS) k_brute(const MatchParams p, const ReadSource src,
                                                          uint32_t* __restrict__ results) {
     extern __shared__ uint4 s_dyn[];
     __shared__ uint8_t s_lut[256];
     uint4* s_planes = s_dyn;
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_dyn + (PANEL_SMEM ? p.S : 0u));
+    const uint32_t n_pairs = (p.S + 1u) / 2u;
+    const uint32_t n_plane_words = (PK == 2) ? n_pairs : 2u * n_pairs;  // uint4 entries of the pair-ordered panel
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_dyn + (PANEL_SMEM ? n_plane_words : 0u));
+    const uint4* __restrict__ g_pairs = (PK == 2) ? p.planes2 : p.planes;  // planes[] is padded to an even count
 
     if constexpr (PANEL_SMEM) {
-        for (uint32_t j = threadIdx.x; j < p.S; j += blockDim.x) s_planes[j] = __ldg(p.planes + j);
+        for (uint32_t j = threadIdx.x; j < n_plane_words; j += blockDim.x) s_planes[j] = __ldg(g_pairs + j);
     }
     if constexpr (ASCII) init_lut(s_lut);
     Counter cnt;
     cnt.init(s_hist, p);
     __syncthreads();
 
-    const uint4* __restrict__ planes = PANEL_SMEM ? s_planes : p.planes;
+    const uint4* __restrict__ planes = PANEL_SMEM ? s_planes : g_pairs;
+    const uint32_t odd_tail = (p.S & 1u) ? 0xFFFF0000u : 0u;  // the last pair's second barcode does not exist
+    const uint32_t n_full_chunks = (n_pairs - (odd_tail ? 1u : 0u)) / BRUTE_CHUNK_PAIRS;
     const uint64_t total = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < src.n; i += total) {
         uint32_t w[W];
@@ -168,18 +201,75 @@ __global__ void __launch_bounds__(BRUTE_THREADS) k_brute(const MatchParams p, co
             load_packed<W>(src.packed, i, w);
         uint32_t pl[4];
         planes_from_words<W>(w, pl);
-        uint32_t k1 = EMPTY_KEY, k2 = EMPTY_KEY;
-#pragma unroll 8
-        for (uint32_t j = 0; j < p.S; j++) {
-            uint4 nb;
-            if constexpr (PANEL_SMEM)
-                nb = planes[j];
-            else
-                nb = __ldg(planes + j);
-            const uint32_t m = (pl[0] & nb.x) | (pl[1] & nb.y) | (pl[2] & nb.z) | (pl[3] & nb.w);
-            track2(k1, k2, ((uint32_t)__popc(m) << 16) | j);
+        if constexpr (PK == 2) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) pl[k] |= pl[k] << 16;  // the read's planes, once per packed barcode
         }
-        const uint32_t res = row_ok ? decide(k1, k2, p.max_mm, p.min_delta) : NONE;
+        uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;  // u16x2 running best / second best (even | odd barcodes)
+        uint32_t best = 0xFFFFu, best_chunk = 0u;
+        uint32_t pair = 0;
+        for (uint32_t c = 0; c < n_full_chunks; c++) {
+#pragma unroll
+            for (uint32_t u = 0; u < BRUTE_CHUNK_PAIRS; u++, pair++) {
+                const uint32_t d2 = pair_distances<PK, PANEL_SMEM>(planes, pair, pl);
+                const uint32_t hi = vmax2(k1, d2);
+                k1 = vmin2(k1, d2);
+                k2 = vmin2(k2, hi);
+            }
+            const uint32_t m = min(k1 & 0xFFFFu, k1 >> 16);
+            if (m < best) {
+                best = m;
+                best_chunk = c;
+            }
+        }
+        for (uint32_t c = n_full_chunks; pair < n_pairs; c++) {  // last, partial chunk (and the odd tail barcode)
+            const uint32_t stop = min(pair + BRUTE_CHUNK_PAIRS, n_pairs);
+            for (; pair < stop; pair++) {
+                uint32_t d2 = pair_distances<PK, PANEL_SMEM>(planes, pair, pl);
+                if (pair == n_pairs - 1u) d2 |= odd_tail;
+                const uint32_t hi = vmax2(k1, d2);
+                k1 = vmin2(k1, d2);
+                k2 = vmin2(k2, hi);
+            }
+            const uint32_t m = min(k1 & 0xFFFFu, k1 >> 16);
+            if (m < best) {
+                best = m;
+                best_chunk = c;
+            }
+        }
+        // second smallest with multiplicity across the two SIMD lanes (barcode_matching.rs:140)
+        const uint32_t a1 = k1 & 0xFFFFu, b1 = k1 >> 16, a2 = k2 & 0xFFFFu, b2 = k2 >> 16;
+        uint32_t next = min(max(a1, b1), min(a2, b2));
+        next = (next == 0xFFFFu) ? 255u : next;  // single-sample panel keeps the 255 sentinel (:122)
+        uint32_t res = NONE;
+        if (row_ok && best <= p.max_mm && (next - best) >= p.min_delta) {
+            // first index with the best distance inside the recorded chunk
+            uint32_t idx = 0xFFFFu;
+            if constexpr (PK == 2) {
+#pragma unroll 1
+                for (uint32_t q = 0; q < BRUTE_CHUNK_PAIRS; q++) {
+                    const uint32_t pr = best_chunk * BRUTE_CHUNK_PAIRS + q;
+                    if (pr < n_pairs) {
+                        uint32_t d2 = pair_distances<PK, PANEL_SMEM>(planes, pr, pl);
+                        if (pr == n_pairs - 1u) d2 |= odd_tail;
+                        if ((d2 >> 16) == best) idx = min(idx, 2u * pr + 1u);
+                        if ((d2 & 0xFFFFu) == best) idx = min(idx, 2u * pr);
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (uint32_t q = 0; q < BRUTE_CHUNK_PAIRS; q++) {
+                    const uint32_t pr = best_chunk * BRUTE_CHUNK_PAIRS + q;
+                    if (pr < n_pairs) {
+                        uint32_t d2 = pair_distances<PK, PANEL_SMEM>(planes, pr, pl);
+                        if (pr == n_pairs - 1u) d2 |= odd_tail;
+                        if ((d2 >> 16) == best) idx = min(idx, 2u * pr + 1u);
+                        if ((d2 & 0xFFFFu) == best) idx = min(idx, 2u * pr);
+                    }
+                }
+            }
+            res = (idx << 16) | (best << 8) | next;
+        }
         results[i] = res;
         cnt.add(res);
     }
@@ -659,25 +749,36 @@ static int grid_for(K kernel, int threads, size_t smem, const LaunchGeometry& g,
     return (int)(want < cap ? want : cap);
 }
 
-template <int W, bool ASCII>
-static cudaError_t launch_brute_w(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
-                                  const LaunchGeometry& g, cudaStream_t stream) {
-    const size_t panel_bytes = (size_t)p.S * sizeof(uint4);
+template <int W, bool ASCII, int PK>
+static cudaError_t launch_brute_wp(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
+                                   const LaunchGeometry& g, cudaStream_t stream) {
+    const uint32_t n_pairs = (p.S + 1u) / 2u;
+    const size_t panel_bytes = (size_t)(PK == 2 ? n_pairs : 2u * n_pairs) * sizeof(uint4);
     const size_t hb = hist_bytes(p);
     const bool panel_smem = panel_bytes + hb + 1024 <= (size_t)g.max_smem_optin;
     if (panel_smem) {
-        auto k = k_brute<W, ASCII, true>;
+        auto k = k_brute<W, ASCII, true, PK>;
         const size_t smem = panel_bytes + hb;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int grid = grid_for(k, BRUTE_THREADS, smem, g, src.n);
         k<<<grid, BRUTE_THREADS, smem, stream>>>(p, src, d_results);
     } else {
-        auto k = k_brute<W, ASCII, false>;
+        auto k = k_brute<W, ASCII, false, PK>;
         const int grid = grid_for(k, BRUTE_THREADS, hb, g, src.n);
         k<<<grid, BRUTE_THREADS, hb, stream>>>(p, src, d_results);
     }
     count_launch();
     return cudaGetLastError();
+}
+
+template <int W, bool ASCII>
+static cudaError_t launch_brute_w(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
+                                  const LaunchGeometry& g, cudaStream_t stream) {
+    if constexpr (W <= 2) {
+        return launch_brute_wp<W, ASCII, 2>(p, src, d_results, g, stream);  // L <= 16: two barcodes per plane word
+    } else {
+        return launch_brute_wp<W, ASCII, 1>(p, src, d_results, g, stream);
+    }
 }
 
 cudaError_t launch_brute(const MatchParams& p, const ReadSource& src, uint32_t* d_results, const LaunchGeometry& g,
