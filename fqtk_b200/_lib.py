@@ -23,6 +23,7 @@ MODE_TABLE = 2
 SYMBOLS = [
     "fqtk_b200_matcher_create", "fqtk_b200_matcher_destroy", "fqtk_b200_matcher_get_info",
     "fqtk_b200_set_table_budget", "fqtk_b200_matcher_assign", "fqtk_b200_matcher_assign_batch",
+    "fqtk_b200_matcher_assign_segments", "fqtk_b200_matcher_assign_segments_device",
     "fqtk_b200_matcher_assign_packed_device", "fqtk_b200_matcher_assign_ascii_device", "fqtk_b200_pack_device",
     "fqtk_b200_encode_host", "fqtk_b200_matcher_counts", "fqtk_b200_matcher_counts_device",
     "fqtk_b200_matcher_reset_counts", "fqtk_b200_matcher_set_mode", "fqtk_b200_kernel_launches",
@@ -38,6 +39,11 @@ class MatcherInfo(C.Structure):
         ("table_entries", C.c_uint64), ("table_slots", C.c_uint64), ("table_bytes", C.c_uint64),
         ("table_candidates", C.c_uint64), ("tier_entries", C.c_uint64), ("tier_slots", C.c_uint64),
     ]
+
+
+class Segment(C.Structure):
+    """fqtk_b200_segment"""
+    _fields_ = [("base", C.c_void_p), ("row_stride", C.c_uint64), ("offset", C.c_uint32), ("length", C.c_uint32)]
 
 
 class Fqtk_b200Error(RuntimeError):
@@ -67,6 +73,8 @@ def lib() -> C.CDLL:
         "fqtk_b200_set_table_budget": (None, [C.c_uint64]),
         "fqtk_b200_matcher_assign": (C.c_int, [vp, C.c_char_p, C.c_size_t, u32p]),
         "fqtk_b200_matcher_assign_batch": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp]),
+        "fqtk_b200_matcher_assign_segments": (C.c_int, [vp, C.POINTER(Segment), C.c_uint32, C.c_uint64, vp]),
+        "fqtk_b200_matcher_assign_segments_device": (C.c_int, [vp, C.POINTER(Segment), C.c_uint32, C.c_uint64, vp, vp]),
         "fqtk_b200_matcher_assign_packed_device": (C.c_int, [vp, vp, C.c_uint64, vp, vp]),
         "fqtk_b200_matcher_assign_ascii_device": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp, vp]),
         "fqtk_b200_pack_device": (C.c_int, [vp, C.c_uint64, C.c_uint32, C.c_uint64, vp, vp]),

@@ -153,6 +153,33 @@ class BarcodeMatcher:
         if rc != _lib.OK:
             _raise(rc)
 
+    def assign_segments(self, segments, n: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Barcodes that arrive in pieces (demux.rs:121-123): `segments` = [(rows, offset, length), ...] where `rows` is
+        a C-contiguous (n, stride) uint8 host array; the pieces are gathered + encoded on the device, in order."""
+        segs = (_lib.Segment * len(segments))()
+        keep = []
+        for k, (rows, offset, length) in enumerate(segments):
+            rows = np.ascontiguousarray(rows, dtype=np.uint8)
+            assert rows.ndim == 2 and rows.shape[0] >= n
+            keep.append(rows)
+            segs[k] = _lib.Segment(rows.ctypes.data, rows.shape[1], offset, length)
+        if out is None:
+            out = np.empty(n, dtype=np.uint32)
+        rc = _lib.lib().fqtk_b200_matcher_assign_segments(self._h, segs, len(segments), n, out.ctypes.data)
+        if rc != _lib.OK:
+            _raise(rc)
+        return out
+
+    def assign_segments_device(self, segments, n: int, d_results: int, stream: int = 0) -> None:
+        """Device form: `segments` = [(device_ptr, row_stride, offset, length), ...]."""
+        segs = (_lib.Segment * len(segments))()
+        for k, (ptr, stride, offset, length) in enumerate(segments):
+            segs[k] = _lib.Segment(ptr, stride, offset, length)
+        rc = _lib.lib().fqtk_b200_matcher_assign_segments_device(self._h, segs, len(segments), n, d_results,
+                                                                 stream or None)
+        if rc != _lib.OK:
+            _raise(rc)
+
     def assign_packed_device(self, d_packed: int, n: int, d_results: int, stream: int = 0) -> None:
         """HBM-resident batch: raw device pointers (packed BitEnc words in, result words out), async on `stream`."""
         rc = _lib.lib().fqtk_b200_matcher_assign_packed_device(self._h, d_packed, n, d_results, stream or None)

@@ -76,8 +76,10 @@ struct fqtk_b200_matcher {
     uint32_t* d_out[N_PIPE] = {};
     uint32_t* d_len[N_PIPE] = {};
     size_t in_cap = 0, out_cap = 0;  // bytes / reads per pipeline slot
-    uint32_t* d_scratch = nullptr;   // packed scratch for the L > 32 ASCII route
+    uint32_t* d_scratch = nullptr;   // packed scratch for the L > 32 ASCII route and the device segment gather
     size_t scratch_words = 0;
+    uint32_t* d_seg_packed[N_PIPE] = {};  // packed scratch per pipeline slot for the host segment gather
+    size_t seg_packed_words[N_PIPE] = {};
 };
 
 namespace {
@@ -375,6 +377,8 @@ int run_device(fqtk_b200_matcher* m, const fq::ReadSource& src, uint32_t* d_resu
         const size_t need = (size_t)s.n * m->W;
         if (need > m->scratch_words) {
             if (m->d_scratch) cudaFree(m->d_scratch);
+    for (int s = 0; s < N_PIPE; s++)
+        if (m->d_seg_packed[s]) cudaFree(m->d_seg_packed[s]);
             m->d_scratch = nullptr;
             CU(cudaMalloc(&m->d_scratch, need * 4));
             m->scratch_words = need;
@@ -548,6 +552,8 @@ void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m) {
         if (m->streams[s]) cudaStreamDestroy(m->streams[s]);
     }
     if (m->d_scratch) cudaFree(m->d_scratch);
+    for (int s = 0; s < N_PIPE; s++)
+        if (m->d_seg_packed[s]) cudaFree(m->d_seg_packed[s]);
     if (m->d_planes) cudaFree(m->d_planes);
     if (m->d_planes2) cudaFree(m->d_planes2);
     if (m->d_not_exp) cudaFree(m->d_not_exp);
@@ -673,6 +679,119 @@ int fqtk_b200_matcher_assign_batch(fqtk_b200_matcher* m, const uint8_t* rows, ui
         if (copy_bytes) CU(cudaMemcpyAsync(m->d_in[slot], rows + done * stride, copy_bytes, cudaMemcpyHostToDevice, st));
         if (lengths) CU(cudaMemcpyAsync(m->d_len[slot], lengths + done, c * 4, cudaMemcpyHostToDevice, st));
         fq::ReadSource src{nullptr, m->d_in[slot], lengths ? m->d_len[slot] : nullptr, stride, c};
+        rc = run_device(m, src, m->d_out[slot], st);
+        if (rc != FQTK_B200_OK) return rc;
+        CU(cudaMemcpyAsync(results + done, m->d_out[slot], c * 4, cudaMemcpyDeviceToHost, st));
+        done += c;
+        slot = (slot + 1) % N_PIPE;
+    }
+    for (int s = 0; s < N_PIPE; s++) CU(cudaStreamSynchronize(m->streams[s]));
+    return FQTK_B200_OK;
+}
+
+static int check_segments(const fqtk_b200_matcher* m, const fqtk_b200_segment* segs, uint32_t n_segs,
+                          fq::SegmentSource& out) {
+    if (!m || !segs || n_segs == 0 || n_segs > FQTK_B200_MAX_SEGMENTS)
+        return fail(FQTK_B200_ERR_ARG, "need 1..8 segments");
+    uint64_t total = 0;
+    out.n_segments = n_segs;
+    for (uint32_t s = 0; s < n_segs; s++) {
+        if (!segs[s].base || segs[s].length == 0 || (uint64_t)segs[s].offset + segs[s].length > segs[s].row_stride)
+            return fail(FQTK_B200_ERR_ARG, "bad segment (NULL base, zero length, or offset + length > row_stride)");
+        out.base[s] = segs[s].base;
+        out.stride[s] = segs[s].row_stride;
+        out.offset[s] = segs[s].offset;
+        out.length[s] = segs[s].length;
+        total += segs[s].length;
+    }
+    if (total != m->L) {  // shorter would make every read None (:167-169), longer is the reference's panic (:95-106)
+        char buf[160];
+        std::snprintf(buf, sizeof buf, "Read barcode length (%llu) differs from expected barcode length (%u)",
+                      (unsigned long long)total, m->L);
+        return fail(FQTK_B200_ERR_LENGTH, buf);
+    }
+    return FQTK_B200_OK;
+}
+
+static int ensure_scratch(fqtk_b200_matcher* m, uint32_t** slot, size_t* cap, size_t words) {
+    if (words > *cap) {
+        if (*slot) cudaFree(*slot);
+        *slot = nullptr;
+        CU(cudaMalloc(slot, words * 4));
+        *cap = words;
+    }
+    (void)m;
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_matcher_assign_segments_device(fqtk_b200_matcher* m, const fqtk_b200_segment* segs, uint32_t n_segs,
+                                             uint64_t n, uint32_t* d_results, void* stream) {
+    fq::SegmentSource ss{};
+    int rc = check_segments(m, segs, n_segs, ss);
+    if (rc != FQTK_B200_OK) return rc;
+    if (n && !d_results) return fail(FQTK_B200_ERR_ARG, "NULL results");
+    if (n >= (1ull << 32)) return fail(FQTK_B200_ERR_ARG, "n_reads must be < 2^32 per device call");
+    CU(cudaSetDevice(m->device));
+    rc = ensure_scratch(m, &m->d_scratch, &m->scratch_words, (size_t)n * m->W + 4);
+    if (rc != FQTK_B200_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(fq::launch_pack_segments(ss, n, m->L, m->d_scratch, m->geo, st));
+    fq::ReadSource src{m->d_scratch, nullptr, nullptr, 0, n};
+    return run_device(m, src, d_results, st);
+}
+
+int fqtk_b200_matcher_assign_segments(fqtk_b200_matcher* m, const fqtk_b200_segment* segs, uint32_t n_segs, uint64_t n,
+                                      uint32_t* results) {
+    fq::SegmentSource ss{};
+    int rc = check_segments(m, segs, n_segs, ss);
+    if (rc != FQTK_B200_OK) return rc;
+    if (n == 0) return FQTK_B200_OK;
+    if (!results) return fail(FQTK_B200_ERR_ARG, "NULL results");
+    CU(cudaSetDevice(m->device));
+    // sources may overlap or alias (two segments of the same FASTQ row): ship each distinct (base, stride) once
+    uint32_t n_src = 0, src_of[FQTK_B200_MAX_SEGMENTS];
+    const uint8_t* sbase[FQTK_B200_MAX_SEGMENTS];
+    uint64_t sstride[FQTK_B200_MAX_SEGMENTS], sspan[FQTK_B200_MAX_SEGMENTS];  // span = bytes of a row actually needed
+    for (uint32_t s = 0; s < n_segs; s++) {
+        uint32_t k = 0;
+        while (k < n_src && !(sbase[k] == ss.base[s] && sstride[k] == ss.stride[s])) k++;
+        if (k == n_src) {
+            sbase[k] = ss.base[s];
+            sstride[k] = ss.stride[s];
+            sspan[k] = 0;
+            n_src++;
+        }
+        src_of[s] = k;
+        sspan[k] = std::max<uint64_t>(sspan[k], (uint64_t)ss.offset[s] + ss.length[s]);
+    }
+    uint64_t bytes_per_read = 0;
+    for (uint32_t k = 0; k < n_src; k++) bytes_per_read += sstride[k];
+    uint64_t chunk = std::max<uint64_t>(CHUNK_BYTES / std::max<uint64_t>(bytes_per_read, 1), 1024);
+    chunk = std::min<uint64_t>(chunk, n) & ~3ull;
+    if (chunk == 0) chunk = n;
+    rc = ensure_pipeline(m, (size_t)(chunk * bytes_per_read + 64 * n_src), (size_t)chunk, false);
+    if (rc != FQTK_B200_OK) return rc;
+    for (int s = 0; s < N_PIPE; s++) {
+        rc = ensure_scratch(m, &m->d_seg_packed[s], &m->seg_packed_words[s], (size_t)chunk * m->W + 4);
+        if (rc != FQTK_B200_OK) return rc;
+    }
+    uint64_t done = 0;
+    int slot = 0;
+    while (done < n) {
+        const uint64_t c = std::min(chunk, n - done);
+        cudaStream_t st = m->streams[slot];
+        fq::SegmentSource dev = ss;
+        uint8_t* cursor = m->d_in[slot];
+        uint8_t* dbase[FQTK_B200_MAX_SEGMENTS];
+        for (uint32_t k = 0; k < n_src; k++) {
+            const size_t bytes = (size_t)((c - 1) * sstride[k] + sspan[k]);  // the last row need not be padded out
+            CU(cudaMemcpyAsync(cursor, sbase[k] + done * sstride[k], bytes, cudaMemcpyHostToDevice, st));
+            dbase[k] = cursor;
+            cursor += (c * sstride[k] + 63) & ~(size_t)63;
+        }
+        for (uint32_t s = 0; s < n_segs; s++) dev.base[s] = dbase[src_of[s]];
+        CU(fq::launch_pack_segments(dev, c, m->L, m->d_seg_packed[slot], m->geo, st));
+        fq::ReadSource src{m->d_seg_packed[slot], nullptr, nullptr, 0, c};
         rc = run_device(m, src, m->d_out[slot], st);
         if (rc != FQTK_B200_OK) return rc;
         CU(cudaMemcpyAsync(results + done, m->d_out[slot], c * 4, cudaMemcpyDeviceToHost, st));

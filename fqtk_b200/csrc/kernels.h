@@ -40,6 +40,15 @@ struct ReadSource {
     uint64_t n;                // < 2^32
 };
 
+// Fixed-length barcode segments scattered over several row sources (demux.rs:121-123 concatenation order).
+struct SegmentSource {
+    const uint8_t* base[8];
+    uint64_t stride[8];
+    uint32_t offset[8];
+    uint32_t length[8];
+    uint32_t n_segments;
+};
+
 struct LaunchGeometry {
     int sm_count;
     int max_smem_optin;
@@ -63,6 +72,8 @@ cudaError_t launch_probe(const MatchParams& p, const ReadSource& src, uint32_t* 
                          cudaStream_t stream);
 cudaError_t launch_pack(const uint8_t* d_ascii, uint64_t n, uint32_t L, uint64_t stride, uint32_t* d_packed,
                         const LaunchGeometry& g, cudaStream_t stream);
+cudaError_t launch_pack_segments(const SegmentSource& seg, uint64_t n, uint32_t L, uint32_t* d_packed,
+                                 const LaunchGeometry& g, cudaStream_t stream);
 cudaError_t prepare_kernels(const LaunchGeometry& g);  // opt-in shared memory attributes, once per device
 
 size_t probe2_fixed_smem_bytes(uint32_t W, uint32_t S, int threads);  // k_probe2 shared memory besides tier + Bloom

@@ -732,6 +732,31 @@ __global__ void __launch_bounds__(256) k_pack(const uint8_t* __restrict__ ascii,
     }
 }
 
+// k_pack_segments: sample_barcode_sequence() (demux.rs:121-123) + encode() (mod.rs:49-61) in one pass: the B segments
+// of a read are gathered from their sources in order and packed straight into the BitEnc word layout.
+__global__ void __launch_bounds__(256) k_pack_segments(const SegmentSource seg, uint64_t n, uint32_t L,
+                                                       uint32_t* __restrict__ packed) {
+    __shared__ uint8_t s_lut[256];
+    init_lut(s_lut);
+    __syncthreads();
+    const uint32_t W = words_for_len(L);
+    const uint64_t total = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += total) {
+        uint32_t acc = 0u, pos = 0u;  // pos = symbols emitted so far
+        for (uint32_t s = 0; s < seg.n_segments; s++) {
+            const uint8_t* src = seg.base[s] + i * seg.stride[s] + seg.offset[s];
+            for (uint32_t k = 0; k < seg.length[s]; k++, pos++) {
+                acc |= (uint32_t)s_lut[__ldg(src + k)] << (4u * (pos & 7u));
+                if ((pos & 7u) == 7u) {
+                    packed[i * W + (pos >> 3)] = acc;
+                    acc = 0u;
+                }
+            }
+        }
+        if (pos & 7u) packed[i * W + (pos >> 3)] = acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------
@@ -879,6 +904,15 @@ cudaError_t launch_pack(const uint8_t* d_ascii, uint64_t n, uint32_t L, uint64_t
     if (n == 0) return cudaSuccess;
     const int grid = grid_for(k_pack, 256, 0, g, n);
     k_pack<<<grid, 256, 0, stream>>>(d_ascii, n, L, stride, d_packed);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_segments(const SegmentSource& seg, uint64_t n, uint32_t L, uint32_t* d_packed,
+                                 const LaunchGeometry& g, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const int grid = grid_for(k_pack_segments, 256, 0, g, n);
+    k_pack_segments<<<grid, 256, 0, stream>>>(seg, n, L, d_packed);
     count_launch();
     return cudaGetLastError();
 }

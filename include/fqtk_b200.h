@@ -108,10 +108,31 @@ FQTK_B200_API int fqtk_b200_matcher_assign_batch(fqtk_b200_matcher* m, const uin
                                                  uint64_t n_reads, uint64_t row_stride, const uint32_t* lengths,
                                                  uint32_t* results);
 
+/* The same call for barcodes that arrive in pieces (SURVEY 8f "next" #1: B-segment extraction fused on the GPU).
+ * ReadSet::sample_barcode_sequence (demux.rs:121-123) concatenates the sample-barcode segments of ALL inputs, in input
+ * order then in-read order; here each fixed-length B segment is described once and gathered + encoded on the device:
+ * read i's barcode = seg[0].base[i*row_stride + offset .. +length) ++ seg[1]... (e.g. I1 rows ++ I2 rows for a
+ * dual index, or the first 16 bytes of R1 for an inline barcode).  The segment lengths must add up to L exactly.
+ * Up to FQTK_B200_MAX_SEGMENTS segments.  Host buffers, synchronous, chunked like assign_batch. */
+#define FQTK_B200_MAX_SEGMENTS 8
+typedef struct {
+    const uint8_t* base; /* row 0 of the source holding this segment */
+    uint64_t row_stride; /* bytes between consecutive reads in that source */
+    uint32_t offset;     /* first byte of the segment inside a row */
+    uint32_t length;     /* bases in the segment (> 0) */
+} fqtk_b200_segment;
+FQTK_B200_API int fqtk_b200_matcher_assign_segments(fqtk_b200_matcher* m, const fqtk_b200_segment* segments,
+                                                    uint32_t n_segments, uint64_t n_reads, uint32_t* results);
+/* Device-buffer form (segment bases are device pointers), asynchronous on `stream`. */
+FQTK_B200_API int fqtk_b200_matcher_assign_segments_device(fqtk_b200_matcher* m, const fqtk_b200_segment* segments,
+                                                           uint32_t n_segments, uint64_t n_reads,
+                                                           uint32_t* d_results, void* stream);
+
 /* ---- HBM-resident calls: DEVICE buffers, asynchronous on `stream` (a cudaStream_t, NULL = default) ----
  * `d_packed`: n_reads * W u32 words, read i at words [i*W, (i+1)*W), symbol k of a read in bits 4*(k%8) of its
  * word k/8 — the reference's own BitEnc layout (mod.rs:49-61, bitenc.rs:311-322).  `d_results`: n_reads u32.
- * n_reads < 2^32 per call.  Counts accumulate on the device; read them with fqtk_b200_matcher_counts. */
+ * n_reads < 2^32 per call.  Counts accumulate on the device; read them with fqtk_b200_matcher_counts.
+ * Device calls on one handle share its scratch buffers: issue them on ONE stream (or serialise them yourself). */
 FQTK_B200_API int fqtk_b200_matcher_assign_packed_device(fqtk_b200_matcher* m, const uint32_t* d_packed,
                                                          uint64_t n_reads, uint32_t* d_results, void* stream);
 /* Same with ASCII rows on the device (encode fused into the kernel); d_lengths may be NULL. */

@@ -333,3 +333,62 @@ def test_kernel_launch_counter_moves():
     with BarcodeMatcher(["ACGT", "TTTT"], 1, 1) as m:
         m.assign(b"ACGT")
     assert kernel_launches() > before
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SURVEY 8f "next" #1: B-segment gather + encode on the device (ReadSet::sample_barcode_sequence, demux.rs:121-123)
+# ---------------------------------------------------------------------------------------------------------
+def test_segments_reference_weird_read_structures(kats):
+    """demux.rs:1739-1800: 4B4M8S / 4B100T / 100S3B / 6B1S1M1T -> AAAA+AAAA+GAT+TACAGA -> Sample0000."""
+    case = [c for c in kats["demux_caller"] if "segments" in c][0]
+    rows = [b"AAAACCCCGGGGTTTT", b"A" * 104, b"T" * 100 + b"GAT", b"TACAGAAAT"]
+    arrays = [np.frombuffer(r, dtype=np.uint8).reshape(1, -1) for r in rows]
+    segs = [(arrays[0], 0, 4), (arrays[1], 0, 4), (arrays[2], 100, 3), (arrays[3], 0, 6)]
+    for use_cache in MODES:
+        with BarcodeMatcher(case["barcodes"], case["max_mismatches"], case["min_mismatch_delta"], use_cache) as m:
+            res = m.assign_segments(segs, 1)
+            assert int(res[0]) >> 16 == 0 and res[0] != _lib.NONE
+            assert m.counts().tolist() == case["expect_counts"]
+            with pytest.raises(MatcherPanic, match="differs from expected barcode length"):
+                m.assign_segments(segs[:3], 1)  # 11 bases for a 17-base panel
+
+
+@pytest.mark.parametrize("use_cache", MODES)
+def test_segments_equal_concatenated_rows(use_cache):
+    torch = torch_cuda()
+    rng = np.random.default_rng(21)
+    cfg = synth.CONFIGS[3]
+    panel = synth.panel(cfg)
+    bcs = [bytes(r) for r in panel]
+    n = 150_003
+    reads = synth.reads_host(panel, cfg.seed_reads, 777, n)
+    reads[::53, 5] = ord("n")
+    reads[::211, 11] = ord("Y")
+    # dual index: I1 = first 8 bases in its own 11-byte rows (offset 2), I2 = last 8 bases inside 151-byte R2 rows;
+    # plus a three-piece split that takes two pieces from the same source
+    i1 = np.full((n, 11), ord("#"), dtype=np.uint8)
+    i1[:, 2:10] = reads[:, :8]
+    r2 = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=(n, 151))
+    r2[:, 100:108] = reads[:, 8:]
+    three = np.full((n, 40), ord("-"), dtype=np.uint8)
+    three[:, 30:35] = reads[:, :5]
+    three[:, 1:4] = reads[:, 5:8]
+    with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, use_cache) as m:
+        want = m.assign_batch(reads)
+        want_counts = m.counts()
+        for segs in ([(i1, 2, 8), (r2, 100, 8)], [(three, 30, 5), (three, 1, 3), (r2, 100, 8)]):
+            m.reset_counts()
+            got = m.assign_segments(segs, n)
+            assert np.array_equal(got, want)
+            assert np.array_equal(m.counts(), want_counts)
+        # device form
+        m.reset_counts()
+        d_i1, d_r2 = torch.from_numpy(i1).cuda(), torch.from_numpy(r2).cuda()
+        d_res = torch.empty(n, dtype=torch.int32, device="cuda")
+        m.assign_segments_device([(d_i1.data_ptr(), 11, 2, 8), (d_r2.data_ptr(), 151, 100, 8)], n, d_res.data_ptr(),
+                                 torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_res.cpu().numpy().view(np.uint32), want)
+        assert np.array_equal(m.counts(), want_counts)
+    om = oracle.OracleMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta)
+    assert np.array_equal(om.assign_batch(reads)[0], want)
