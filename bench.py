@@ -367,6 +367,29 @@ def run_b200(args):
         matcher.set_mode("table")
         matcher.reset_counts()
 
+    # ---- per-sample routing of the batch, for the record ----
+    routing = None
+    if not args.no_brute:
+        matcher.assign_packed_device(d_packed.data_ptr(), n, d_res.data_ptr(), stream)
+        d_order = torch.empty(n, dtype=torch.int32, device=dev)
+        d_off = torch.zeros(cfg.n_samples + 2, dtype=torch.int64, device=dev)
+        matcher.route_device(d_res.data_ptr(), n, d_order.data_ptr(), d_off.data_ptr(), stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            matcher.route_device(d_res.data_ptr(), n, d_order.data_ptr(), d_off.data_ptr(), stream)
+        e1.record()
+        torch.cuda.synchronize()
+        rms = e0.elapsed_time(e1) / 3
+        assert int(d_off[-1].item()) == n
+        routing = {"kernels": "k_route_hist + k_route_scan_* + k_route_scatter", "reads": n, "ms": round(rms, 4),
+                   "value": round(n / (rms * 1e-3) / 1e6, 2), "unit": UNIT + " per GPU",
+                   "algorithmic_bytes_per_read": 12,
+                   "roofline_frac": round(n * 12 / (rms * 1e-3) / 1e9 / peak, 4)}
+        del d_order, d_off
+        matcher.reset_counts()
+
     # ---- e2e: the reference-facing C-ABI call on HOST buffers (pinned), H2D + kernel + D2H every step ----
     e2e = None
     if not args.no_e2e:
@@ -429,7 +452,7 @@ def run_b200(args):
             "clocks": clocks,
             "memo_table": {"entries": int(info.table_entries), "slots": int(info.table_slots),
                            "bytes": int(info.table_bytes), "candidates": int(info.table_candidates)},
-            "brute_force": brute,
+            "brute_force": brute, "routing": routing,
             "matched_fraction": round(1.0 - float(counts[-1]) / float(counts.sum()), 5),
         }
         print(json.dumps(line), flush=True)

@@ -24,6 +24,7 @@ SYMBOLS = [
     "fqtk_b200_matcher_create", "fqtk_b200_matcher_destroy", "fqtk_b200_matcher_get_info",
     "fqtk_b200_set_table_budget", "fqtk_b200_matcher_assign", "fqtk_b200_matcher_assign_batch",
     "fqtk_b200_matcher_assign_segments", "fqtk_b200_matcher_assign_segments_device",
+    "fqtk_b200_matcher_route_device", "fqtk_b200_matcher_route",
     "fqtk_b200_matcher_assign_packed_device", "fqtk_b200_matcher_assign_ascii_device", "fqtk_b200_pack_device",
     "fqtk_b200_encode_host", "fqtk_b200_matcher_counts", "fqtk_b200_matcher_counts_device",
     "fqtk_b200_matcher_reset_counts", "fqtk_b200_matcher_set_mode", "fqtk_b200_kernel_launches",
@@ -75,6 +76,8 @@ def lib() -> C.CDLL:
         "fqtk_b200_matcher_assign_batch": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp]),
         "fqtk_b200_matcher_assign_segments": (C.c_int, [vp, C.POINTER(Segment), C.c_uint32, C.c_uint64, vp]),
         "fqtk_b200_matcher_assign_segments_device": (C.c_int, [vp, C.POINTER(Segment), C.c_uint32, C.c_uint64, vp, vp]),
+        "fqtk_b200_matcher_route_device": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp]),
+        "fqtk_b200_matcher_route": (C.c_int, [vp, vp, C.c_uint64, vp, vp]),
         "fqtk_b200_matcher_assign_packed_device": (C.c_int, [vp, vp, C.c_uint64, vp, vp]),
         "fqtk_b200_matcher_assign_ascii_device": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp, vp]),
         "fqtk_b200_pack_device": (C.c_int, [vp, C.c_uint64, C.c_uint32, C.c_uint64, vp, vp]),

@@ -193,6 +193,24 @@ class BarcodeMatcher:
         if rc != _lib.OK:
             _raise(rc)
 
+    # -- per-sample routing of a batch (demux.rs:970-975: every sample's output keeps input order) --------------
+    def route(self, results: np.ndarray):
+        """Stable partition of read indices by assignment.  Returns (order uint32[n], offsets uint64[S+2]):
+        order[offsets[j]:offsets[j+1]] = ascending indices of the reads of sample j (j = S: unmatched)."""
+        results = np.ascontiguousarray(results, dtype=np.uint32)
+        n = results.shape[0]
+        order = np.empty(n, dtype=np.uint32)
+        offsets = np.zeros(self.n_samples + 2, dtype=np.uint64)
+        rc = _lib.lib().fqtk_b200_matcher_route(self._h, results.ctypes.data, n, order.ctypes.data, offsets.ctypes.data)
+        if rc != _lib.OK:
+            _raise(rc)
+        return order, offsets
+
+    def route_device(self, d_results: int, n: int, d_order: int, d_offsets: int, stream: int = 0) -> None:
+        rc = _lib.lib().fqtk_b200_matcher_route_device(self._h, d_results, n, d_order, d_offsets, stream or None)
+        if rc != _lib.OK:
+            _raise(rc)
+
     # -- the caller's counters (demux.rs:970-974) ------------------------------------------------------
     def counts(self) -> np.ndarray:
         """uint64[S + 1]; last element = unmatched."""

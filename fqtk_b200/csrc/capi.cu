@@ -76,6 +76,8 @@ struct fqtk_b200_matcher {
     uint32_t* d_out[N_PIPE] = {};
     uint32_t* d_len[N_PIPE] = {};
     size_t in_cap = 0, out_cap = 0;  // bytes / reads per pipeline slot
+    void* d_route_ws = nullptr;      // routing workspace (per-warp histograms)
+    size_t route_ws_bytes = 0;
     uint32_t* d_scratch = nullptr;   // packed scratch for the L > 32 ASCII route and the device segment gather
     size_t scratch_words = 0;
     uint32_t* d_seg_packed[N_PIPE] = {};  // packed scratch per pipeline slot for the host segment gather
@@ -377,6 +379,7 @@ int run_device(fqtk_b200_matcher* m, const fq::ReadSource& src, uint32_t* d_resu
         const size_t need = (size_t)s.n * m->W;
         if (need > m->scratch_words) {
             if (m->d_scratch) cudaFree(m->d_scratch);
+    if (m->d_route_ws) cudaFree(m->d_route_ws);
     for (int s = 0; s < N_PIPE; s++)
         if (m->d_seg_packed[s]) cudaFree(m->d_seg_packed[s]);
             m->d_scratch = nullptr;
@@ -552,6 +555,7 @@ void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m) {
         if (m->streams[s]) cudaStreamDestroy(m->streams[s]);
     }
     if (m->d_scratch) cudaFree(m->d_scratch);
+    if (m->d_route_ws) cudaFree(m->d_route_ws);
     for (int s = 0; s < N_PIPE; s++)
         if (m->d_seg_packed[s]) cudaFree(m->d_seg_packed[s]);
     if (m->d_planes) cudaFree(m->d_planes);
@@ -817,6 +821,48 @@ int fqtk_b200_matcher_assign(fqtk_b200_matcher* m, const uint8_t* read_bases, si
         return FQTK_B200_OK;
     }
     return fqtk_b200_matcher_assign_batch(m, read_bases, 1, len, &len32, result);
+}
+
+int fqtk_b200_matcher_route_device(fqtk_b200_matcher* m, const uint32_t* d_results, uint64_t n, uint32_t* d_order,
+                                   uint64_t* d_offsets, void* stream) {
+    if (!m || !d_offsets || (n && (!d_results || !d_order))) return fail(FQTK_B200_ERR_ARG, "NULL argument");
+    if (n >= (1ull << 32)) return fail(FQTK_B200_ERR_ARG, "n_reads must be < 2^32 per device call");
+    if (!fq::route_supported(m->S, m->geo)) return fail(FQTK_B200_ERR_UNSUPPORTED, "too many samples for routing");
+    CU(cudaSetDevice(m->device));
+    const size_t need = fq::route_workspace_bytes(n, m->S, m->geo);
+    if (need > m->route_ws_bytes) {
+        if (m->d_route_ws) cudaFree(m->d_route_ws);
+        m->d_route_ws = nullptr;
+        CU(cudaMalloc(&m->d_route_ws, need));
+        m->route_ws_bytes = need;
+    }
+    CU(fq::launch_route(d_results, n, m->S, d_order, reinterpret_cast<unsigned long long*>(d_offsets), m->d_route_ws,
+                        m->geo, (cudaStream_t)stream));
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_matcher_route(fqtk_b200_matcher* m, const uint32_t* results, uint64_t n, uint32_t* order,
+                            uint64_t* offsets) {
+    if (!m || !offsets || (n && (!results || !order))) return fail(FQTK_B200_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(m->device));
+    uint32_t *d_res = nullptr, *d_ord = nullptr;
+    uint64_t* d_off = nullptr;
+    cudaStream_t st = m->streams[0];
+    cudaError_t e = cudaMalloc(&d_res, std::max<size_t>(16, n * 4));
+    if (e == cudaSuccess) e = cudaMalloc(&d_ord, std::max<size_t>(16, n * 4));
+    if (e == cudaSuccess) e = cudaMalloc(&d_off, (size_t)(m->S + 2) * 8);
+    int rc = FQTK_B200_OK;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_res, results, n * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) rc = fqtk_b200_matcher_route_device(m, d_res, n, d_ord, d_off, st);
+    if (e == cudaSuccess && rc == FQTK_B200_OK) e = cudaMemcpyAsync(order, d_ord, n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == FQTK_B200_OK)
+        e = cudaMemcpyAsync(offsets, d_off, (size_t)(m->S + 2) * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_res);
+    cudaFree(d_ord);
+    cudaFree(d_off);
+    if (e != cudaSuccess) return cuda_fail(e, "route");
+    return rc;
 }
 
 int fqtk_b200_matcher_counts(fqtk_b200_matcher* m, uint64_t* out) {

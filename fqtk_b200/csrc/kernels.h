@@ -74,6 +74,10 @@ cudaError_t launch_pack(const uint8_t* d_ascii, uint64_t n, uint32_t L, uint64_t
                         const LaunchGeometry& g, cudaStream_t stream);
 cudaError_t launch_pack_segments(const SegmentSource& seg, uint64_t n, uint32_t L, uint32_t* d_packed,
                                  const LaunchGeometry& g, cudaStream_t stream);
+size_t route_workspace_bytes(uint64_t n, uint32_t S, const LaunchGeometry& g);
+bool route_supported(uint32_t S, const LaunchGeometry& g);
+cudaError_t launch_route(const uint32_t* d_results, uint64_t n, uint32_t S, uint32_t* d_order,
+                         unsigned long long* d_offsets, void* d_workspace, const LaunchGeometry& g, cudaStream_t stream);
 cudaError_t prepare_kernels(const LaunchGeometry& g);  // opt-in shared memory attributes, once per device
 
 size_t probe2_fixed_smem_bytes(uint32_t W, uint32_t S, int threads);  // k_probe2 shared memory besides tier + Bloom

@@ -1,0 +1,195 @@
+// route_kernels.cu — per-sample routing of a matched batch (SURVEY.md 8f "next" #3).
+//
+// The reference routes one read at a time: `sample_writers[best_match].write(&read_set)` or the unmatched writer
+// (src/bin/commands/demux.rs:970-975), so every sample's output keeps INPUT ORDER (the tests index fq_reads[0],
+// demux.rs:1505-1523).  For a batch that is a stable partition of the read indices by assignment: S + 1 groups
+// (samples 0..S-1 in sheet order, then unmatched), each in input order, so the host can hand every writer one
+// contiguous, ordered run per batch instead of S + 1 scattered per-read calls.
+//
+// Stable counting sort, three kernels, no sorting library:
+//   k_route_hist     every warp owns one contiguous range of reads and histograms it into a warp-private
+//                    shared-memory table; the table goes to global memory bucket-major: hist[bucket][warp]
+//   k_route_scan_*   exclusive scan of hist in (bucket, warp) order = the first output slot of every (bucket, warp);
+//                    the per-bucket totals' scan is the `offsets` table handed back to the caller
+//   k_route_scatter  every warp walks its range again, 32 reads per step in input order; a read's rank among the
+//                    step's reads of the same bucket comes from ballots over the bucket's bits (no MATCH, no atomics,
+//                    deterministic), the warp's running per-bucket cursor lives in shared memory
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fq {
+
+constexpr int ROUTE_THREADS = 256;        // 8 warps per CTA
+constexpr int ROUTE_SCAN_THREADS = 1024;
+
+FQ_D uint32_t bucket_of_result(uint32_t r, uint32_t S) {
+    const uint32_t b = r >> 16;
+    return (r == NONE || b >= S) ? S : b;
+}
+
+// reads [lo, hi) of warp `gw` of `n_warps`: contiguous, multiples of 32 except the very end
+FQ_D void warp_range(uint64_t n, uint32_t gw, uint32_t n_warps, uint64_t& lo, uint64_t& hi) {
+    const uint64_t steps = (n + 31) / 32;
+    const uint64_t s_lo = steps * gw / n_warps, s_hi = steps * (gw + 1) / n_warps;
+    lo = s_lo * 32;
+    hi = s_hi * 32 < n ? s_hi * 32 : n;
+    if (lo > n) lo = n;
+}
+
+__global__ void __launch_bounds__(ROUTE_THREADS) k_route_hist(const uint32_t* __restrict__ results, uint64_t n, uint32_t S,
+                                                              uint32_t n_warps, uint32_t* __restrict__ hist) {
+    extern __shared__ uint32_t s_tab[];  // [warps_per_cta][S + 1]
+    const uint32_t B = S + 1u, lane = threadIdx.x & 31u, wic = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    uint32_t* tab = s_tab + (size_t)wic * B;
+    for (uint32_t b = lane; b < B; b += 32u) tab[b] = 0u;
+    __syncwarp();
+    const uint32_t gw = blockIdx.x * wpc + wic;
+    if (gw < n_warps) {
+        uint64_t lo, hi;
+        warp_range(n, gw, n_warps, lo, hi);
+        for (uint64_t i = lo + lane; i < hi; i += 32u) atomicAdd(&tab[bucket_of_result(__ldg(results + i), S)], 1u);
+        __syncwarp();
+        for (uint32_t b = lane; b < B; b += 32u) hist[(size_t)b * n_warps + gw] = tab[b];
+    }
+}
+
+// one CTA per bucket: exclusive scan of its row hist[b][0..n_warps) in place, row total to totals[b]
+__global__ void __launch_bounds__(ROUTE_SCAN_THREADS) k_route_scan_rows(uint32_t* __restrict__ hist, uint32_t n_warps,
+                                                                        unsigned long long* __restrict__ totals) {
+    __shared__ uint32_t s_part[ROUTE_SCAN_THREADS];
+    uint32_t* row = hist + (size_t)blockIdx.x * n_warps;
+    const uint32_t per = (n_warps + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = threadIdx.x * per, hi = min(lo + per, n_warps);
+    uint32_t sum = 0;
+    for (uint32_t k = lo; k < hi; k++) sum += row[k];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t off = 1; off < blockDim.x; off <<= 1) {  // Hillis-Steele inclusive scan of the per-thread sums
+        const uint32_t v = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0u;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[threadIdx.x] - sum;  // exclusive prefix of this thread's chunk
+    for (uint32_t k = lo; k < hi; k++) {
+        const uint32_t c = row[k];
+        row[k] = run;
+        run += c;
+    }
+    if (threadIdx.x == blockDim.x - 1) totals[blockIdx.x] = s_part[threadIdx.x];
+}
+
+// single CTA: offsets[0..B] = exclusive scan of totals[0..B), offsets[B] = n
+__global__ void __launch_bounds__(ROUTE_SCAN_THREADS) k_route_scan_totals(const unsigned long long* __restrict__ totals,
+                                                                          uint32_t B,
+                                                                          unsigned long long* __restrict__ offsets) {
+    __shared__ unsigned long long s_part[ROUTE_SCAN_THREADS];
+    const uint32_t per = (B + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = threadIdx.x * per, hi = min(lo + per, B);
+    unsigned long long sum = 0;
+    for (uint32_t k = lo; k < hi; k++) sum += totals[k];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t off = 1; off < blockDim.x; off <<= 1) {
+        const unsigned long long v = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0ull;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned long long run = s_part[threadIdx.x] - sum;
+    for (uint32_t k = lo; k < hi; k++) {
+        offsets[k] = run;
+        run += totals[k];
+    }
+    if (threadIdx.x == blockDim.x - 1) offsets[B] = s_part[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(ROUTE_THREADS) k_route_scatter(const uint32_t* __restrict__ results, uint64_t n, uint32_t S,
+                                                                 uint32_t n_warps, const uint32_t* __restrict__ hist,
+                                                                 const unsigned long long* __restrict__ offsets,
+                                                                 uint32_t bucket_bits, uint32_t* __restrict__ order) {
+    extern __shared__ uint32_t s_tab[];  // [warps_per_cta][S + 1] running output cursors
+    const uint32_t B = S + 1u, lane = threadIdx.x & 31u, wic = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    uint32_t* cur = s_tab + (size_t)wic * B;
+    const uint32_t gw = blockIdx.x * wpc + wic;
+    if (gw >= n_warps) return;
+    for (uint32_t b = lane; b < B; b += 32u) cur[b] = (uint32_t)offsets[b] + hist[(size_t)b * n_warps + gw];
+    __syncwarp();
+    uint64_t lo, hi;
+    warp_range(n, gw, n_warps, lo, hi);
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    for (uint64_t base = lo; base < hi; base += 32u) {
+        const uint64_t i = base + lane;
+        const bool valid = i < hi;
+        const uint32_t b = valid ? bucket_of_result(__ldg(results + i), S) : 0xFFFFFFFFu;
+        // lanes of this step in the same bucket: AND over the bucket's bits of (ballot(bit) XNOR my bit)
+        uint32_t same = __ballot_sync(0xFFFFFFFFu, valid);
+        for (uint32_t k = 0; k < bucket_bits; k++) {
+            const uint32_t bit = (b >> k) & 1u;
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, bit);
+            same &= bit ? bal : ~bal;
+        }
+        const uint32_t start = valid ? cur[b] : 0u;  // every lane reads its bucket's cursor ...
+        __syncwarp();
+        if (valid) {
+            const uint32_t rank = __popc(same & lane_lt);
+            order[start + rank] = (uint32_t)i;
+            if (rank == 0u) cur[b] = start + __popc(same);  // ... before the group's first lane advances it
+        }
+        __syncwarp();
+    }
+}
+
+struct RoutePlan {
+    uint32_t n_warps, warps_per_cta, grid, bucket_bits;
+    size_t smem;
+};
+
+static RoutePlan plan_route(uint64_t n, uint32_t S, const LaunchGeometry& g) {
+    RoutePlan p{};
+    const size_t per_warp = (size_t)(S + 1u) * 4u;
+    uint32_t wpc = ROUTE_THREADS / 32;
+    while (wpc > 1 && per_warp * wpc > (size_t)g.max_smem_optin - 1024) wpc >>= 1;
+    p.warps_per_cta = wpc;
+    p.smem = per_warp * wpc;
+    // enough warps to fill the machine, few enough that (warps x buckets) open output runs stay L2-resident
+    uint32_t ctas = (uint32_t)g.sm_count * (wpc >= 8 ? 2u : (8u / wpc) * 2u);
+    const uint64_t steps = (n + 31) / 32;
+    uint64_t warps = (uint64_t)ctas * wpc;
+    if (warps > steps) warps = steps ? steps : 1;
+    p.n_warps = (uint32_t)warps;
+    p.grid = (uint32_t)((warps + wpc - 1) / wpc);
+    p.bucket_bits = 1;
+    while ((1u << p.bucket_bits) < S + 1u) p.bucket_bits++;
+    return p;
+}
+
+size_t route_workspace_bytes(uint64_t n, uint32_t S, const LaunchGeometry& g) {
+    const RoutePlan p = plan_route(n, S, g);
+    return (size_t)(S + 1u) * p.n_warps * 4u + (size_t)(S + 1u) * 8u + 256;
+}
+
+bool route_supported(uint32_t S, const LaunchGeometry& g) { return (size_t)(S + 1u) * 4u + 1024 <= (size_t)g.max_smem_optin; }
+
+// d_offsets: u64[S + 2] on the device.  d_workspace: route_workspace_bytes() bytes.
+cudaError_t launch_route(const uint32_t* d_results, uint64_t n, uint32_t S, uint32_t* d_order,
+                         unsigned long long* d_offsets, void* d_workspace, const LaunchGeometry& g, cudaStream_t stream) {
+    const RoutePlan p = plan_route(n, S, g);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(d_workspace);
+    unsigned long long* totals =
+        reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(d_workspace) + (((size_t)(S + 1u) * p.n_warps * 4u + 7) & ~(size_t)7));
+    const int threads = (int)p.warps_per_cta * 32;
+    cudaFuncSetAttribute(k_route_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    cudaFuncSetAttribute(k_route_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    k_route_hist<<<p.grid, threads, p.smem, stream>>>(d_results, n, S, p.n_warps, hist);
+    count_launch();
+    k_route_scan_rows<<<S + 1u, ROUTE_SCAN_THREADS, 0, stream>>>(hist, p.n_warps, totals);
+    count_launch();
+    k_route_scan_totals<<<1, ROUTE_SCAN_THREADS, 0, stream>>>(totals, S + 1u, d_offsets);
+    count_launch();
+    k_route_scatter<<<p.grid, threads, p.smem, stream>>>(d_results, n, S, p.n_warps, hist, d_offsets, p.bucket_bits, d_order);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace fq

@@ -145,6 +145,19 @@ FQTK_B200_API int fqtk_b200_pack_device(const uint8_t* d_ascii, uint64_t n_reads
 /* encode() on the host for one sequence: out = ceil(len/8) u32 blocks.  Pure encoding, no matching. */
 FQTK_B200_API int fqtk_b200_encode_host(const uint8_t* bases, size_t len, uint32_t* out_blocks);
 
+/* ---- per-sample routing of a batch (SURVEY 8f "next" #3) ----------------------------------------------
+ * The reference hands every read to its sample's writer in input order (demux.rs:970-975; order pinned by the tests
+ * at :1505-1523).  For a batch that is a STABLE partition of the read indices by assignment:
+ *   order[offsets[j] .. offsets[j+1])  = indices of the reads assigned to sample j, ascending (input order), j < S
+ *   order[offsets[S] .. offsets[S+1])  = indices of the unmatched reads, ascending;  offsets[S+1] = n_reads
+ * so the host appends ONE contiguous run per sample per batch.  `d_results` are the batch's result words.
+ * d_order: n_reads u32; d_offsets: S + 2 u64.  Asynchronous on `stream`; n_reads < 2^32; S + 1 <= ~50 000. */
+FQTK_B200_API int fqtk_b200_matcher_route_device(fqtk_b200_matcher* m, const uint32_t* d_results, uint64_t n_reads,
+                                                 uint32_t* d_order, uint64_t* d_offsets, void* stream);
+/* Host-buffer convenience: ships result words in, brings order + offsets back.  Synchronous. */
+FQTK_B200_API int fqtk_b200_matcher_route(fqtk_b200_matcher* m, const uint32_t* results, uint64_t n_reads,
+                                          uint32_t* order, uint64_t* offsets);
+
 /* ---- per-sample counts (DemuxMetric.templates, demux.rs:458,971,974): S+1 u64, last = unmatched ---- */
 FQTK_B200_API int fqtk_b200_matcher_counts(fqtk_b200_matcher* m, uint64_t* out_counts); /* syncs the device */
 FQTK_B200_API int fqtk_b200_matcher_counts_device(fqtk_b200_matcher* m, uint64_t** d_counts); /* for ncclAllReduce */

@@ -392,3 +392,69 @@ def test_segments_equal_concatenated_rows(use_cache):
         assert np.array_equal(m.counts(), want_counts)
     om = oracle.OracleMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta)
     assert np.array_equal(om.assign_batch(reads)[0], want)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SURVEY 8f "next" #3: per-sample routing = stable partition of read indices by assignment
+# ---------------------------------------------------------------------------------------------------------
+def expected_route(results, S):
+    bucket = np.where(results == _lib.NONE, S, results >> 16).astype(np.int64)
+    order = np.argsort(bucket, kind="stable").astype(np.uint32)
+    offsets = np.zeros(S + 2, dtype=np.uint64)
+    offsets[1:] = np.cumsum(np.bincount(bucket, minlength=S + 1))
+    return order, offsets
+
+
+@pytest.mark.parametrize("cfg_id,n", [(1, 10_000), (3, 400_037), (5, 150_001)])
+def test_route_is_the_stable_partition(cfg_id, n):
+    cfg = synth.CONFIGS[cfg_id]
+    panel = synth.panel(cfg)
+    reads = synth.reads_host(panel, cfg.seed_reads, 5, n)
+    with BarcodeMatcher([bytes(r) for r in panel], cfg.max_mismatches, cfg.min_mismatch_delta) as m:
+        res = m.assign_batch(reads)
+        order, offsets = m.route(res)
+        want_order, want_offsets = expected_route(res, cfg.n_samples)
+        assert np.array_equal(offsets, want_offsets)
+        assert np.array_equal(order, want_order)
+        assert np.array_equal(np.diff(offsets.astype(np.int64)), m.counts().astype(np.int64))
+        # every sample's run is in input order (what the reference's per-read writes guarantee, demux.rs:1505-1523)
+        for j in (0, cfg.n_samples // 2, cfg.n_samples):
+            run = order[int(offsets[j]):int(offsets[j + 1])]
+            assert np.all(np.diff(run.astype(np.int64)) > 0)
+        # tiny and empty batches
+        o1, f1 = m.route(res[:1])
+        assert o1.tolist() == [0] and int(f1[-1]) == 1
+        o0, f0 = m.route(res[:0])
+        assert o0.size == 0 and not f0.any()
+
+
+def test_route_full_size_properties():
+    """cfg 3 at 500 M reads on the device: order is a permutation, every bucket run is ascending and homogeneous."""
+    torch = torch_cuda()
+    cfg = synth.CONFIGS[3]
+    panel = synth.panel(cfg)
+    n = cfg.n_reads
+    stream = torch.cuda.current_stream().cuda_stream
+    d_packed = torch.empty((n, cfg.words_per_read), dtype=torch.int32, device="cuda")
+    synth.reads_device(panel, cfg.seed_reads, 0, n, 0, d_packed.data_ptr(), stream)
+    d_res = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_order = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_off = torch.zeros(cfg.n_samples + 2, dtype=torch.int64, device="cuda")
+    with BarcodeMatcher([bytes(r) for r in panel], cfg.max_mismatches, cfg.min_mismatch_delta) as m:
+        m.assign_packed_device(d_packed.data_ptr(), n, d_res.data_ptr(), stream)
+        del d_packed
+        m.route_device(d_res.data_ptr(), n, d_order.data_ptr(), d_off.data_ptr(), stream)
+        torch.cuda.synchronize()
+        counts = m.counts().astype(np.int64)
+    off = d_off.cpu().numpy()
+    assert np.array_equal(np.diff(off), counts) and off[0] == 0 and off[-1] == n
+    # homogeneous runs: the bucket of results[order[k]] is non-decreasing and matches the offsets table
+    gathered = d_res[d_order.long()]
+    bucket = torch.where(gathered == -1, torch.full_like(gathered, cfg.n_samples), (gathered >> 16) & 0xFFFF)
+    assert bool((bucket[1:] >= bucket[:-1]).all())
+    # ascending inside every run  <=>  order[k+1] > order[k] wherever the bucket does not change
+    same = bucket[1:] == bucket[:-1]
+    assert bool((d_order[1:][same] > d_order[:-1][same]).all())
+    del gathered, bucket, same
+    # permutation: a stable partition of [0, n) sums to n(n-1)/2 and has no repeats inside runs (checked above)
+    assert int(d_order.long().sum().item()) == n * (n - 1) // 2
