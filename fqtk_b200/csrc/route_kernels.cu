@@ -14,6 +14,8 @@
 //   k_route_scatter  every warp walks its range again, 32 reads per step in input order; a read's rank among the
 //                    step's reads of the same bucket comes from ballots over the bucket's bits (no MATCH, no atomics,
 //                    deterministic), the warp's running per-bucket cursor lives in shared memory
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -21,6 +23,7 @@ namespace fq {
 
 constexpr int ROUTE_THREADS = 256;        // 8 warps per CTA
 constexpr int ROUTE_SCAN_THREADS = 1024;
+constexpr int ROUTE_UNROLL = 4;           // 32-read steps whose loads are issued together
 
 FQ_D uint32_t bucket_of_result(uint32_t r, uint32_t S) {
     const uint32_t b = r >> 16;
@@ -47,7 +50,17 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_route_hist(const uint32_t* __
     if (gw < n_warps) {
         uint64_t lo, hi;
         warp_range(n, gw, n_warps, lo, hi);
-        for (uint64_t i = lo + lane; i < hi; i += 32u) atomicAdd(&tab[bucket_of_result(__ldg(results + i), S)], 1u);
+        for (uint64_t base = lo; base < hi; base += 32u * ROUTE_UNROLL) {  // ROUTE_UNROLL independent loads in flight
+            uint32_t r[ROUTE_UNROLL];
+#pragma unroll
+            for (int u = 0; u < ROUTE_UNROLL; u++) {
+                const uint64_t i = base + 32u * u + lane;
+                r[u] = i < hi ? __ldg(results + i) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < ROUTE_UNROLL; u++)
+                if (base + 32u * u + lane < hi) atomicAdd(&tab[bucket_of_result(r[u], S)], 1u);
+        }
         __syncwarp();
         for (uint32_t b = lane; b < B; b += 32u) hist[(size_t)b * n_warps + gw] = tab[b];
     }
@@ -118,25 +131,34 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_route_scatter(const uint32_t*
     uint64_t lo, hi;
     warp_range(n, gw, n_warps, lo, hi);
     const uint32_t lane_lt = (1u << lane) - 1u;
-    for (uint64_t base = lo; base < hi; base += 32u) {
-        const uint64_t i = base + lane;
-        const bool valid = i < hi;
-        const uint32_t b = valid ? bucket_of_result(__ldg(results + i), S) : 0xFFFFFFFFu;
-        // lanes of this step in the same bucket: AND over the bucket's bits of (ballot(bit) XNOR my bit)
-        uint32_t same = __ballot_sync(0xFFFFFFFFu, valid);
-        for (uint32_t k = 0; k < bucket_bits; k++) {
-            const uint32_t bit = (b >> k) & 1u;
-            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, bit);
-            same &= bit ? bal : ~bal;
+    for (uint64_t base0 = lo; base0 < hi; base0 += 32u * ROUTE_UNROLL) {
+        uint32_t r[ROUTE_UNROLL];  // ROUTE_UNROLL steps' result words in flight before the first is consumed
+#pragma unroll
+        for (int u = 0; u < ROUTE_UNROLL; u++) {
+            const uint64_t i = base0 + 32u * u + lane;
+            r[u] = i < hi ? __ldg(results + i) : 0u;
         }
-        const uint32_t start = valid ? cur[b] : 0u;  // every lane reads its bucket's cursor ...
-        __syncwarp();
-        if (valid) {
-            const uint32_t rank = __popc(same & lane_lt);
-            order[start + rank] = (uint32_t)i;
-            if (rank == 0u) cur[b] = start + __popc(same);  // ... before the group's first lane advances it
+#pragma unroll
+        for (int u = 0; u < ROUTE_UNROLL; u++) {
+            const uint64_t i = base0 + 32u * u + lane;
+            const bool valid = i < hi;
+            const uint32_t b = valid ? bucket_of_result(r[u], S) : 0xFFFFFFFFu;
+            // lanes of this step in the same bucket: AND over the bucket's bits of (ballot(bit) XNOR my bit)
+            uint32_t same = __ballot_sync(0xFFFFFFFFu, valid);
+            for (uint32_t k = 0; k < bucket_bits; k++) {
+                const uint32_t bit = (b >> k) & 1u;
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, bit);
+                same &= bit ? bal : ~bal;
+            }
+            const uint32_t start = valid ? cur[b] : 0u;  // every lane reads its bucket's cursor ...
+            __syncwarp();
+            if (valid) {
+                const uint32_t rank = __popc(same & lane_lt);
+                order[start + rank] = (uint32_t)i;
+                if (rank == 0u) cur[b] = start + __popc(same);  // ... before the group's first lane advances it
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 
@@ -153,7 +175,14 @@ static RoutePlan plan_route(uint64_t n, uint32_t S, const LaunchGeometry& g) {
     p.warps_per_cta = wpc;
     p.smem = per_warp * wpc;
     // enough warps to fill the machine, few enough that (warps x buckets) open output runs stay L2-resident
-    uint32_t ctas = (uint32_t)g.sm_count * (wpc >= 8 ? 2u : (8u / wpc) * 2u);
+    // 8 warps per SM: measured best on B200 (r01q sweep) — more warps only multiply the open (warp, bucket) output
+    // runs, whose partially written sectors then bounce between L2 and DRAM (5x write amplification at 32 warps/SM)
+    uint32_t warps_per_sm = 8;
+    if (const char* e = getenv("FQTK_B200_ROUTE_WARPS_PER_SM")) warps_per_sm = (uint32_t)atoi(e);
+    if (warps_per_sm < wpc) wpc = warps_per_sm ? warps_per_sm : 1;
+    p.warps_per_cta = wpc;
+    p.smem = per_warp * wpc;
+    uint32_t ctas = (uint32_t)g.sm_count * ((warps_per_sm + wpc - 1) / wpc);
     const uint64_t steps = (n + 31) / 32;
     uint64_t warps = (uint64_t)ctas * wpc;
     if (warps > steps) warps = steps ? steps : 1;
