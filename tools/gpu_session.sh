@@ -20,7 +20,7 @@ for s in $STEPS; do
     ncu)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" \
         python bench.py --steps 2 --warmup 1 --no-cpu-baseline --e2e-reads 8388608 > "$OUT/ncu_launches_bench.log" 2>&1; echo "ncu launches rc=$?"
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_probe -s 1 -c 2 -o "$OUT/prof_probe" -f \
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_probe2 -s 1 -c 1 -o "$OUT/prof_probe2" -f \
         python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-brute > "$OUT/ncu_probe.log" 2>&1; echo "ncu probe rc=$?"
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_brute -s 1 -c 1 -o "$OUT/prof_brute" -f \
         python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --mode brute --reads 67108864 > "$OUT/ncu_brute.log" 2>&1; echo "ncu brute rc=$?"
