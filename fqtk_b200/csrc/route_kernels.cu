@@ -14,6 +14,7 @@
 //   k_route_scatter  every warp walks its range again, 32 reads per step in input order; a read's rank among the
 //                    step's reads of the same bucket comes from ballots over the bucket's bits (no MATCH, no atomics,
 //                    deterministic), the warp's running per-bucket cursor lives in shared memory
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -162,13 +163,184 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_route_scatter(const uint32_t*
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Tile version (S + 1 <= RT_MAX_BUCKETS): a CTA owns a contiguous range and walks it in tiles of RT_TILE reads.
+// Each tile is counting-sorted inside shared memory (stable: warp w owns reads [512 w, 512 (w+1)) of the tile, ranks
+// inside a 32-read step come from ballots), then every bucket's run of the tile leaves as one contiguous burst at the
+// CTA's running cursor for that bucket — DRAM sees full sectors instead of scattered 4-byte stores.
+// ------------------------------------------------------------------------------------------------------
+constexpr int RT_THREADS = 512;
+constexpr int RT_WARPS = RT_THREADS / 32;
+constexpr int RT_TILE = 8192;
+constexpr int RT_STEPS = RT_TILE / RT_THREADS;  // 32-read steps per warp and tile
+constexpr uint32_t RT_MAX_BUCKETS = 2048;
+
+FQ_D void cta_range(uint64_t n, uint32_t c, uint32_t n_ctas, uint64_t& lo, uint64_t& hi) {
+    const uint64_t tiles = (n + RT_TILE - 1) / RT_TILE;
+    lo = tiles * c / n_ctas * RT_TILE;
+    hi = tiles * (c + 1) / n_ctas * RT_TILE;
+    if (lo > n) lo = n;
+    if (hi > n) hi = n;
+}
+
+__global__ void __launch_bounds__(RT_THREADS) k_route_hist_cta(const uint32_t* __restrict__ results, uint64_t n, uint32_t S,
+                                                               uint32_t n_ctas, uint32_t* __restrict__ hist) {
+    extern __shared__ uint32_t s_tab[];  // [S + 1]
+    const uint32_t B = S + 1u;
+    for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) s_tab[b] = 0u;
+    __syncthreads();
+    uint64_t lo, hi;
+    cta_range(n, blockIdx.x, n_ctas, lo, hi);
+    for (uint64_t base = lo; base < hi; base += (uint64_t)RT_THREADS * ROUTE_UNROLL) {
+        uint32_t r[ROUTE_UNROLL];
+#pragma unroll
+        for (int u = 0; u < ROUTE_UNROLL; u++) {
+            const uint64_t i = base + (uint64_t)RT_THREADS * u + threadIdx.x;
+            r[u] = i < hi ? __ldg(results + i) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < ROUTE_UNROLL; u++)
+            if (base + (uint64_t)RT_THREADS * u + threadIdx.x < hi) atomicAdd(&s_tab[bucket_of_result(r[u], S)], 1u);
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) hist[(size_t)b * n_ctas + blockIdx.x] = s_tab[b];
+}
+
+__global__ void __launch_bounds__(RT_THREADS) k_route_scatter_tile(const uint32_t* __restrict__ results, uint64_t n, uint32_t S,
+                                                                   uint32_t n_ctas, const uint32_t* __restrict__ hist,
+                                                                   const unsigned long long* __restrict__ offsets,
+                                                                   uint32_t bucket_bits, uint32_t* __restrict__ order) {
+    extern __shared__ uint32_t s_mem[];
+    const uint32_t B = S + 1u;
+    uint32_t* cursor = s_mem;                       // [B]  next output slot of every bucket for this CTA
+    uint32_t* ttotal = cursor + B;                  // [B]  reads of the tile per bucket
+    uint32_t* tbase = ttotal + B;                   // [B]  first sorted-tile position of every bucket
+    uint32_t* whist = tbase + B;                    // [RT_WARPS][B] per-warp counts, then per-warp running cursors
+    uint32_t* part = whist + (size_t)RT_WARPS * B;  // [RT_THREADS] scan partials
+    uint16_t* tbucket = reinterpret_cast<uint16_t*>(part + RT_THREADS);  // [RT_TILE] bucket of every read of the tile
+    uint16_t* sorted = tbucket + RT_TILE;                                // [RT_TILE] tile-local read index by position
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5, lane_lt = (1u << lane) - 1u;
+    uint32_t* my_hist = whist + (size_t)w * B;
+
+    for (uint32_t b = threadIdx.x; b < B; b += RT_THREADS)
+        cursor[b] = (uint32_t)offsets[b] + hist[(size_t)b * n_ctas + blockIdx.x];
+    uint64_t lo, hi;
+    cta_range(n, blockIdx.x, n_ctas, lo, hi);
+    for (uint64_t tile_lo = lo; tile_lo < hi; tile_lo += RT_TILE) {
+        const uint32_t tile_n = (uint32_t)min((uint64_t)RT_TILE, hi - tile_lo);
+        for (uint32_t t = threadIdx.x; t < RT_WARPS * B; t += RT_THREADS) whist[t] = 0u;
+        __syncthreads();
+        // A: buckets of the tile + per-warp counts
+        {
+            uint32_t r[RT_STEPS];
+#pragma unroll
+            for (int st = 0; st < RT_STEPS; st++) {
+                const uint32_t idx = w * (RT_STEPS * 32u) + st * 32u + lane;
+                r[st] = idx < tile_n ? __ldg(results + tile_lo + idx) : 0u;
+            }
+#pragma unroll
+            for (int st = 0; st < RT_STEPS; st++) {
+                const uint32_t idx = w * (RT_STEPS * 32u) + st * 32u + lane;
+                if (idx < tile_n) {
+                    const uint32_t b = bucket_of_result(r[st], S);
+                    tbucket[idx] = (uint16_t)b;
+                    atomicAdd(&my_hist[b], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        // B: per bucket, exclusive prefix over the warps (in place) and the tile total
+        for (uint32_t b = threadIdx.x; b < B; b += RT_THREADS) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int ww = 0; ww < RT_WARPS; ww++) {
+                const uint32_t c = whist[(size_t)ww * B + b];
+                whist[(size_t)ww * B + b] = acc;
+                acc += c;
+            }
+            ttotal[b] = acc;
+        }
+        __syncthreads();
+        // C: exclusive scan of the tile totals over the buckets -> first sorted position of every bucket
+        {
+            const uint32_t per = (B + RT_THREADS - 1) / RT_THREADS;
+            const uint32_t b_lo = threadIdx.x * per, b_hi = min(b_lo + per, B);
+            uint32_t sum = 0;
+            for (uint32_t b = b_lo; b < b_hi; b++) sum += ttotal[b];
+            part[threadIdx.x] = sum;
+            __syncthreads();
+            for (uint32_t off = 1; off < RT_THREADS; off <<= 1) {
+                const uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
+                __syncthreads();
+                part[threadIdx.x] += v;
+                __syncthreads();
+            }
+            uint32_t run = part[threadIdx.x] - sum;
+            for (uint32_t b = b_lo; b < b_hi; b++) {
+                tbase[b] = run;
+                run += ttotal[b];
+            }
+        }
+        __syncthreads();
+        // D: stable rank of every read inside the tile -> sorted[]
+        for (int st = 0; st < RT_STEPS; st++) {
+            const uint32_t idx = w * (RT_STEPS * 32u) + st * 32u + lane;
+            const bool valid = idx < tile_n;
+            const uint32_t b = valid ? tbucket[idx] : 0xFFFFu;
+            uint32_t same = __ballot_sync(0xFFFFFFFFu, valid);
+            for (uint32_t k = 0; k < bucket_bits; k++) {
+                const uint32_t bit = (b >> k) & 1u;
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, bit);
+                same &= bit ? bal : ~bal;
+            }
+            const uint32_t start = valid ? my_hist[b] : 0u;
+            __syncwarp();
+            if (valid) {
+                const uint32_t rank = __popc(same & lane_lt);
+                sorted[tbase[b] + start + rank] = (uint16_t)idx;
+                if (rank == 0u) my_hist[b] = start + __popc(same);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        // E: every bucket's run leaves as one contiguous burst at the CTA's cursor
+        for (uint32_t pos = threadIdx.x; pos < tile_n; pos += RT_THREADS) {
+            const uint32_t idx = sorted[pos];
+            const uint32_t b = tbucket[idx];
+            order[cursor[b] + (pos - tbase[b])] = (uint32_t)(tile_lo + idx);
+        }
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < B; b += RT_THREADS) cursor[b] += ttotal[b];
+        // (the loop-top zeroing + barrier orders this against the next tile)
+    }
+}
+
+static size_t route_tile_smem(uint32_t S) {
+    const size_t B = S + 1u;
+    return (3 * B + (size_t)RT_WARPS * B + RT_THREADS) * 4 + (size_t)RT_TILE * 2 * 2;
+}
+
 struct RoutePlan {
-    uint32_t n_warps, warps_per_cta, grid, bucket_bits;
+    uint32_t n_warps, warps_per_cta, grid, bucket_bits;  // n_warps = histogram columns (warps, or CTAs in tile mode)
     size_t smem;
+    bool tile;
 };
 
 static RoutePlan plan_route(uint64_t n, uint32_t S, const LaunchGeometry& g) {
     RoutePlan p{};
+    p.bucket_bits = 1;
+    while ((1u << p.bucket_bits) < S + 1u) p.bucket_bits++;
+    if (S + 1u <= RT_MAX_BUCKETS && route_tile_smem(S) + 1024 <= (size_t)g.max_smem_optin && !getenv("FQTK_B200_ROUTE_V1")) {
+        p.tile = true;
+        p.smem = route_tile_smem(S);
+        const uint64_t tiles = (n + RT_TILE - 1) / RT_TILE;
+        const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(3, ((size_t)g.max_smem_optin) / (p.smem + 1024)));
+        uint64_t ctas = (uint64_t)g.sm_count * per_sm;
+        if (ctas > tiles) ctas = tiles ? tiles : 1;
+        p.n_warps = p.grid = (uint32_t)ctas;
+        p.warps_per_cta = RT_WARPS;
+        return p;
+    }
     const size_t per_warp = (size_t)(S + 1u) * 4u;
     uint32_t wpc = ROUTE_THREADS / 32;
     while (wpc > 1 && per_warp * wpc > (size_t)g.max_smem_optin - 1024) wpc >>= 1;
@@ -207,6 +379,20 @@ cudaError_t launch_route(const uint32_t* d_results, uint64_t n, uint32_t S, uint
     uint32_t* hist = reinterpret_cast<uint32_t*>(d_workspace);
     unsigned long long* totals =
         reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(d_workspace) + (((size_t)(S + 1u) * p.n_warps * 4u + 7) & ~(size_t)7));
+    if (p.tile) {
+        const size_t hsmem = (size_t)(S + 1u) * 4u;
+        cudaFuncSetAttribute(k_route_scatter_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+        k_route_hist_cta<<<p.grid, RT_THREADS, hsmem, stream>>>(d_results, n, S, p.n_warps, hist);
+        count_launch();
+        k_route_scan_rows<<<S + 1u, ROUTE_SCAN_THREADS, 0, stream>>>(hist, p.n_warps, totals);
+        count_launch();
+        k_route_scan_totals<<<1, ROUTE_SCAN_THREADS, 0, stream>>>(totals, S + 1u, d_offsets);
+        count_launch();
+        k_route_scatter_tile<<<p.grid, RT_THREADS, p.smem, stream>>>(d_results, n, S, p.n_warps, hist, d_offsets,
+                                                                      p.bucket_bits, d_order);
+        count_launch();
+        return cudaGetLastError();
+    }
     const int threads = (int)p.warps_per_cta * 32;
     cudaFuncSetAttribute(k_route_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     cudaFuncSetAttribute(k_route_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
