@@ -48,7 +48,15 @@ int cuda_fail(cudaError_t e, const char* what) {
     } while (0)
 
 constexpr int N_PIPE = 3;                       // chunks in flight for the host-buffer call
-constexpr uint64_t CHUNK_BYTES = 32ull << 20;   // ASCII bytes per chunk
+uint64_t chunk_bytes() {                        // ASCII bytes per chunk (FQTK_B200_CHUNK_MB overrides, for tuning)
+    static const uint64_t v = [] {
+        const char* e = getenv("FQTK_B200_CHUNK_MB");
+        const long mb = e ? atol(e) : 0;
+        return (uint64_t)(mb > 0 ? mb : 32) << 20;
+    }();
+    return v;
+}
+#define CHUNK_BYTES chunk_bytes()
 
 }  // namespace
 
