@@ -236,7 +236,7 @@ def run_reference(args):
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_dict(cfg, n_reads, mode):
@@ -465,14 +465,33 @@ def run_b200(args):
             "brute_force": brute, "routing": routing,
             "matched_fraction": round(1.0 - float(counts[-1]) / float(counts.sum()), 5),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     matcher.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line: park the real fd 1 and point fd 1 at stderr, so that nothing a library
+    prints from C (NCCL's version banner, for one) can land in front of it."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

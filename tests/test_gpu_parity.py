@@ -458,3 +458,59 @@ def test_route_full_size_properties():
     del gathered, bucket, same
     # permutation: a stable partition of [0, n) sums to n(n-1)/2 and has no repeats inside runs (checked above)
     assert int(d_order.long().sum().item()) == n * (n - 1) // 2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# edges of the device entry points: tile boundaries, tiny batches, unaligned buffers, empty calls
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("use_cache", MODES)
+def test_batch_sizes_around_the_tile_boundaries(use_cache):
+    torch = torch_cuda()
+    cfg = synth.CONFIGS[3]
+    panel = synth.panel(cfg)
+    bcs = [bytes(r) for r in panel]
+    reads = synth.reads_host(panel, cfg.seed_reads, 99, 1200)
+    reads[::7, 2] = ord("K")  # out-of-alphabet reads in every tile, including the tail warp
+    packed = synth.pack_host(reads)
+    om = oracle.OracleMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta)
+    want_all, _ = om.assign_batch(reads)
+    stream = torch.cuda.current_stream().cuda_stream
+    with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, use_cache) as m:
+        d_all = torch.from_numpy(packed.view(np.int32)).cuda()
+        for n in (0, 1, 2, 31, 32, 33, 127, 128, 129, 255, 256, 257, 1023, 1199):
+            m.reset_counts()
+            d_res = torch.full((max(n, 1),), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
+            m.assign_packed_device(d_all.data_ptr(), n, d_res.data_ptr(), stream)
+            torch.cuda.synchronize()
+            got = d_res.cpu().numpy().view(np.uint32)[:n]
+            assert np.array_equal(got, want_all[:n]), n
+            c = m.counts()
+            assert int(c.sum()) == n
+        # result buffer only 4-byte aligned: the one-read-per-thread kernel takes over, same answers
+        n = 1000
+        d_res = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
+        m.reset_counts()
+        m.assign_packed_device(d_all.data_ptr(), n, d_res.data_ptr() + 4, stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_res.cpu().numpy().view(np.uint32)[1:], want_all[:n])
+        # packed input must be 16-byte aligned: refused, nothing counted
+        with pytest.raises(_lib.Fqtk_b200Error):
+            m.assign_packed_device(d_all.data_ptr() + 8, 10, d_res.data_ptr(), stream)
+        assert int(m.counts().sum()) == n
+        # empty host batch is a no-op
+        out = m.assign_batch(np.zeros((0, cfg.barcode_len), dtype=np.uint8))
+        assert out.shape == (0,)
+
+
+def test_single_sample_and_single_base_panels():
+    for bcs, mm, delta, reads in [
+        (["A"], 0, 0, [b"A", b"C", b"N", b"a", b"-"]),
+        (["N"], 0, 0, [b"A", b"N", b"."]),
+        (["ACGTACGT"], 1, 2, [b"ACGTACGT", b"ACGTACGA", b"TTTTTTTT", b"NNNNNNNN"]),
+        (["AC", "AG", "AT", "AA"], 0, 1, [b"AC", b"AG", b"AN", b"NN", b"TT"]),
+    ]:
+        om = oracle.OracleMatcher(bcs, mm, delta)
+        for use_cache in MODES:
+            with BarcodeMatcher(bcs, mm, delta, use_cache) as m:
+                for r in reads:
+                    assert m.assign(r) == om.assign_closed(r), (bcs, r, use_cache)
