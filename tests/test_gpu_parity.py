@@ -513,4 +513,6 @@ def test_single_sample_and_single_base_panels():
         for use_cache in MODES:
             with BarcodeMatcher(bcs, mm, delta, use_cache) as m:
                 for r in reads:
-                    assert m.assign(r) == om.assign_closed(r), (bcs, r, use_cache)
+                    got, want = m.assign(r), om.assign_closed(r)
+                    as_tuple = lambda x: None if x is None else (x.best_match, x.best_mismatches, x.next_best_mismatches)
+                    assert as_tuple(got) == as_tuple(want), (bcs, r, use_cache)
