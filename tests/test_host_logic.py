@@ -157,3 +157,26 @@ def test_no_cpu_fallback_when_no_gpu_is_visible():
         BarcodeMatcher(["ACGT", "TTTT"], 1, 1)
     assert ei.value.code == _lib.ERR_CUDA
     assert "no CPU fallback" in ei.value.message
+
+
+def test_demux_metrics_follow_the_reference_update_rule(tmp_path):
+    """DemuxMetric::update (demux.rs:481-496): mean and best exclude the unmatched pseudo-sample; unmatched row last,
+    barcode '.' (demux.rs:918).  The reference's own check (demux.rs:2058-2064): templates sum = 2, Sample0000 = 2."""
+    from fqtk_b200.metrics import demux_metrics, write_tsv
+
+    rows = demux_metrics(["Sample0000"], ["GATTGGG"], [2, 0])
+    assert sum(r.templates for r in rows) == 2 and rows[0].templates == 2
+    assert rows[-1].sample_id == "unmatched" and rows[-1].barcode == "."
+    rows = demux_metrics(["a", "b", "c"], ["AAAA", "CCCC", "GGGG"], [30, 10, 20, 40])
+    total, mean, best = 100.0, 20.0, 30.0
+    for r, t in zip(rows, [30, 10, 20, 40]):
+        assert r.templates == t
+        assert r.frac_templates == t / total and r.ratio_to_mean == t / mean and r.ratio_to_best == t / best
+    f = tmp_path / "demux-metrics.txt"
+    write_tsv(str(f), rows)
+    lines = f.read_text().splitlines()
+    assert lines[0] == "sample_id\tbarcode\ttemplates\tfrac_templates\tratio_to_mean\tratio_to_best"
+    assert lines[-1].split("\t")[:3] == ["unmatched", ".", "40"]
+    # an empty run divides by zero the way f64 does in the reference (NaN), it does not raise
+    rows = demux_metrics(["a"], ["AAAA"], [0, 0])
+    assert rows[0].frac_templates != rows[0].frac_templates
