@@ -10,6 +10,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    # The product refuses to run without its CUDA library (no CPU fallback).  In a checkout where it has not been
+    # built yet, build it once here (nvcc cross-compiles without a GPU) — same as __graft_entry__.build().
+    from fqtk_b200 import build as _build
+
+    if _build.is_stale():
+        _build.build()
 
 
 @pytest.fixture(scope="session")
