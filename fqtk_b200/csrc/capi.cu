@@ -177,10 +177,11 @@ void build_tier(const std::vector<uint32_t>& keys, const std::vector<uint32_t>& 
     for (uint64_t t = 0; t < n; t++) n_hot += (res[t] != fq::NONE && ((res[t] >> 8) & 0xFFu) == 0u);
     uint32_t slots = 16;
     while ((uint64_t)slots * 2 < n_hot * 5 && slots < (1u << 20)) slots <<= 1;            // load <= 0.4
-    while (slots > 16 && (size_t)slots * (TE + (W == 4)) * 4 > budget_bytes) slots >>= 1;  // shared-memory budget
+    const int SEPV = fq::tier_separate_values(W) ? 1 : 0;
+    while (slots > 16 && (size_t)slots * (TE + SEPV) * 4 > budget_bytes) slots >>= 1;  // shared-memory budget
     placed = 0;
     slots_out = 0;
-    if (n_hot == 0 || (size_t)slots * (TE + (W == 4)) * 4 > budget_bytes) return;
+    if (n_hot == 0 || (size_t)slots * (TE + SEPV) * 4 > budget_bytes) return;
     uint32_t shift = 32;
     while ((1u << (32 - shift)) < slots) shift--;
     std::vector<uint32_t> tk((size_t)slots * W, 0xFFFFFFFFu), tv(slots, fq::NONE);
@@ -214,11 +215,11 @@ void build_tier(const std::vector<uint32_t>& keys, const std::vector<uint32_t>& 
         // not placed after 256 kicks: whichever key is in hand stays out of the tier (it is still in the memo table)
     }
     // serialise into the device layout
-    if (W == 4) {
-        tier.assign((size_t)slots * 5, 0xFFFFFFFFu);
+    if (SEPV) {  // key entries, then the value array
+        tier.assign((size_t)slots * (TE + 1), 0xFFFFFFFFu);
         for (uint32_t e = 0; e < slots; e++) {
-            for (int k = 0; k < 4; k++) tier[(size_t)e * 4 + k] = tk[(size_t)e * W + (k < W ? k : 0)];
-            tier[(size_t)slots * 4 + e] = tv[e];
+            for (int k = 0; k < TE; k++) tier[(size_t)e * TE + k] = tk[(size_t)e * W + (k < W ? k : 0)];
+            tier[(size_t)slots * TE + e] = tv[e];
         }
     } else {
         const int TV = fq::tier_value_index(W);
@@ -321,9 +322,10 @@ int build_table(fqtk_b200_matcher* m) {
         // replicas: as many as tile the banks once, while the tier stays within its budget
         const size_t entry_bytes = (size_t)fq::tier_entry_words((int)W) * 4;
         uint32_t rep = (uint32_t)fq::tier_max_rep((int)W);
-        while (rep > 1 && (size_t)tslots * rep * entry_bytes + (W == 4 ? (size_t)tslots * 4 : 0) > budget) rep >>= 1;
+        const size_t vals_bytes = fq::tier_separate_values((int)W) ? (size_t)tslots * 4 : 0;
+        while (rep > 1 && (size_t)tslots * rep * entry_bytes + vals_bytes > budget) rep >>= 1;
         m->params.tier_rep = rep;
-        tier_bytes = (size_t)tslots * rep * entry_bytes + (W == 4 ? (size_t)tslots * 4 : 0);
+        tier_bytes = (size_t)tslots * rep * entry_bytes + vals_bytes;
     }
     // Bloom filter over every table key: >= 8 bits per key, at most 32 KB, only if it still fits
     {

@@ -15,7 +15,7 @@ struct MatchParams {
     const uint32_t* table;     // memo table slots in global memory (nullptr in brute mode)
     const uint32_t* tier_entries;  // hot tier (table entries whose best distance is 0), staged into shared memory by
                                    //   k_probe2: 2-choice cuckoo, tier_slots entries of tier_entry_words(W) words
-                                   //   (W = 4: tier_slots x 4 key words, then tier_slots value words)
+                                   //   (W = 2, 4: tier_slots key entries, then tier_slots value words)
     const uint32_t* bloom;         // blocked Bloom filter over every memo-table key (one 32-bit word, 3 bits per key)
     unsigned long long* counts;  // [S + 1] per-sample counts, last = unmatched
     uint32_t S, L, W, P;
@@ -60,11 +60,15 @@ struct LaunchGeometry {
 // Empty slots are all-ones (value NONE).  `n_buckets` is the slot count.
 inline __host__ __device__ int table_slot_words(int W) { return W <= 3 ? 4 : 8; }
 inline __host__ __device__ int table_value_index(int W) { return W <= 3 ? 3 : 4; }
-// Hot-tier entries: W = 1: {k0, value}; W = 2: {k0, k1, value, 0}; W = 3: {k0, k1, k2, value};
-//   W = 4: {k0, k1, k2, k3} with the values in a separate array.  Empty slots are all-ones (value NONE).
-inline __host__ __device__ int tier_entry_words(int W) { return W == 1 ? 2 : 4; }
-inline __host__ __device__ int tier_value_index(int W) { return W == 1 ? 1 : (W == 2 ? 2 : 3); }  // W = 4: separate array
-inline __host__ __device__ int tier_max_rep(int W) { return W == 1 ? 16 : 8; }  // replicas that tile all 32 banks once
+// Hot-tier entries: W = 1: {k0, value} (LDS.64); W = 2: {k0, k1} (LDS.64) with the values in a separate array;
+//   W = 3: {k0, k1, k2, value} (LDS.128); W = 4: {k0, k1, k2, k3} (LDS.128) with the values in a separate array.
+//   Measured on B200 (tools/microbench_lds.cu): a conflict-free LDS.64 costs 2.4 clk per warp, an LDS.128 8.0 clk, a
+//   random LDS.32 2.5 clk — so 8-byte probes plus one value fetch (7.1 clk) beat two 16-byte probes (16 clk).
+//   Empty slots are all-ones (value NONE).
+inline __host__ __device__ int tier_entry_words(int W) { return W <= 2 ? 2 : 4; }
+inline __host__ __device__ bool tier_separate_values(int W) { return W == 2 || W == 4; }
+inline __host__ __device__ int tier_value_index(int W) { return W == 1 ? 1 : 3; }  // fused layouts only (W = 1, 3)
+inline __host__ __device__ int tier_max_rep(int W) { return W <= 2 ? 16 : 8; }  // replicas that tile all 32 banks once
 
 cudaError_t launch_brute(const MatchParams& p, const ReadSource& src, uint32_t* d_results, const LaunchGeometry& g,
                          cudaStream_t stream);

@@ -500,13 +500,14 @@ template <int W>
 __global__ void __launch_bounds__(PROBE2_THREADS, 1) k_probe2(const MatchParams p, const ReadSource src,
                                                            uint32_t* __restrict__ results) {
     constexpr int R = PROBE2_R;
-    constexpr int TE = W == 1 ? 2 : 4;  // tier entry words (kernels.h)
+    constexpr int TE = W <= 2 ? 2 : 4;              // tier entry words (kernels.h)
+    constexpr bool SEPV = (W == 2 || W == 4);       // values in their own (unreplicated) array
     extern __shared__ uint4 s_dyn[];
     // layout: tier replicas | (W = 4: tier values) | Bloom words | per-warp queues | histogram replicas
     uint32_t* s_tier = reinterpret_cast<uint32_t*>(s_dyn);
     const uint32_t rep = p.tier_rep;
     uint32_t* s_tvals = s_tier + (size_t)p.tier_slots * rep * TE;
-    uint32_t* s_bloom = s_tvals + (W == 4 ? p.tier_slots : 0u);
+    uint32_t* s_bloom = s_tvals + (SEPV ? p.tier_slots : 0u);
     uint32_t* s_queue = s_bloom + p.bloom_words;
     const uint32_t n_warps = blockDim.x >> 5;
     uint32_t* s_hist = s_queue + (size_t)n_warps * PROBE2_QUEUE * W;
@@ -517,7 +518,7 @@ __global__ void __launch_bounds__(PROBE2_THREADS, 1) k_probe2(const MatchParams 
         const uint32_t e = t / (rep * TE), k = t % TE;
         s_tier[t] = __ldg(p.tier_entries + e * TE + k);
     }
-    if constexpr (W == 4)
+    if constexpr (SEPV)
         for (uint32_t t = threadIdx.x; t < p.tier_slots; t += blockDim.x)
             s_tvals[t] = __ldg(p.tier_entries + (size_t)p.tier_slots * TE + t);
     for (uint32_t t = threadIdx.x; t < p.bloom_words; t += blockDim.x) s_bloom[t] = __ldg(p.bloom + t);
@@ -589,13 +590,14 @@ __global__ void __launch_bounds__(PROBE2_THREADS, 1) k_probe2(const MatchParams 
                 if constexpr (W == 1) {
                     const uint2 a = lds64_ro(a1), b = lds64_ro(a2);
                     res[r] = (a.x == w[r][0]) ? a.y : ((b.x == w[r][0]) ? b.y : NONE);
+                } else if constexpr (W == 2) {
+                    const uint2 a = lds64_ro(a1), b = lds64_ro(a2);
+                    const bool m1 = a.x == w[r][0] && a.y == w[r][W > 1 ? 1 : 0];
+                    const bool m2 = b.x == w[r][0] && b.y == w[r][W > 1 ? 1 : 0];
+                    if (m1 || m2) res[r] = lds32_ro(a_tvals + (m1 ? s1 : s2) * 4u);
                 } else {
                     const uint4 a = lds128_ro(a1), b = lds128_ro(a2);
-                    if constexpr (W == 2) {
-                        const bool m1 = a.x == w[r][0] && a.y == w[r][1];
-                        const bool m2 = b.x == w[r][0] && b.y == w[r][1];
-                        res[r] = m1 ? a.z : (m2 ? b.z : NONE);
-                    } else if constexpr (W == 3) {
+                    if constexpr (W == 3) {
                         const bool m1 = a.x == w[r][0] && a.y == w[r][1] && a.z == w[r][W > 2 ? 2 : 0];
                         const bool m2 = b.x == w[r][0] && b.y == w[r][1] && b.z == w[r][W > 2 ? 2 : 0];
                         res[r] = m1 ? a.w : (m2 ? b.w : NONE);
@@ -848,7 +850,8 @@ size_t probe2_fixed_smem_bytes(uint32_t W, uint32_t S, int threads) {  // queues
 }
 
 size_t probe2_smem_bytes(const MatchParams& p, int threads) {
-    return (size_t)p.tier_slots * p.tier_rep * tier_entry_words((int)p.W) * 4 + (p.W == 4 ? (size_t)p.tier_slots * 4 : 0) +
+    return (size_t)p.tier_slots * p.tier_rep * tier_entry_words((int)p.W) * 4 +
+           (tier_separate_values((int)p.W) ? (size_t)p.tier_slots * 4 : 0) +
            (size_t)p.bloom_words * 4 + probe2_fixed_smem_bytes(p.W, p.S, threads);
 }
 
