@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=0, help="override reads per GPU per step (default: the config's N)")
     ap.add_argument("--e2e-reads", type=int, default=128 << 20, help="reads per GPU per e2e step (pinned host memory)")
     ap.add_argument("--mode", choices=["auto", "table", "brute"], default="auto")
+    ap.add_argument("--cuckoo", type=int, default=-1, choices=[-1, 0, 2, 3],
+                    help="shared-memory cuckoo table arity for k_probe3 (-1 auto, 0 = off -> k_probe2); A/B timing")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-brute", action="store_true")
@@ -181,12 +183,12 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(cfg_id, mode):
+def ncu_traffic(cfg_id, kernel):
     """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(f"cfg{cfg_id}_{mode}")
+            return json.load(open(p)).get(f"cfg{cfg_id}_{kernel.split('<')[0]}")
         except Exception:
             return None
     return None
@@ -287,12 +289,15 @@ def run_b200(args):
     d_packed = torch.empty((n, W), dtype=torch.int32, device=dev)
     d_res = torch.empty(n, dtype=torch.int32, device=dev)
     synth.reads_device(panel, cfg.seed_reads, weak_shard_first_read(n, rank), n, 0, d_packed.data_ptr(), stream)
+    _lib.lib().fqtk_b200_set_cuckoo_arity(args.cuckoo)
     matcher = BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, use_cache=(args.mode != "brute"),
                              device=local)
     if args.mode == "table" and matcher.mode != "table":
         raise SystemExit("memo table could not be built for this config")
     mode = matcher.mode
     info = matcher.info()
+    kernel = "k_brute" if mode != "table" else (
+        f"k_probe3<W={W},NP={int(info.cuckoo_probes)}>" if int(info.cuckoo_probes) and W <= 2 else "k_probe2")
     counts_t = torch.zeros(cfg.n_samples + 1, dtype=torch.int64, device=dev)
 
     def barrier():
@@ -350,7 +355,7 @@ def run_b200(args):
     achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-        "traffic": ncu_traffic(args.config, mode), "kernel": "k_probe2" if mode == "table" else "k_brute",
+        "traffic": ncu_traffic(args.config, kernel), "kernel": kernel,
         "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_read": cfg.algorithmic_bytes_per_read,
         "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
         "pair_compares_per_s": round(n * cfg.n_samples / (k_ms * 1e-3), 1) if mode == "brute" else None,
@@ -461,7 +466,9 @@ def run_b200(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks,
             "memo_table": {"entries": int(info.table_entries), "slots": int(info.table_slots),
-                           "bytes": int(info.table_bytes), "candidates": int(info.table_candidates)},
+                           "bytes": int(info.table_bytes), "candidates": int(info.table_candidates),
+                           "cuckoo_entries": int(info.cuckoo_entries), "cuckoo_probes": int(info.cuckoo_probes),
+                           "cuckoo_slots": int(info.cuckoo_slots)},
             "brute_force": brute, "routing": routing,
             "matched_fraction": round(1.0 - float(counts[-1]) / float(counts.sum()), 5),
         }

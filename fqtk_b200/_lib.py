@@ -22,7 +22,7 @@ MODE_TABLE = 2
 # every symbol include/fqtk_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "fqtk_b200_matcher_create", "fqtk_b200_matcher_destroy", "fqtk_b200_matcher_get_info",
-    "fqtk_b200_set_table_budget", "fqtk_b200_matcher_assign", "fqtk_b200_matcher_assign_batch",
+    "fqtk_b200_set_table_budget", "fqtk_b200_set_cuckoo_arity", "fqtk_b200_matcher_assign", "fqtk_b200_matcher_assign_batch",
     "fqtk_b200_matcher_assign_segments", "fqtk_b200_matcher_assign_segments_device",
     "fqtk_b200_matcher_route_device", "fqtk_b200_matcher_route",
     "fqtk_b200_matcher_assign_packed_device", "fqtk_b200_matcher_assign_ascii_device", "fqtk_b200_pack_device",
@@ -39,6 +39,7 @@ class MatcherInfo(C.Structure):
         ("max_ns_in_barcodes", C.c_uint32), ("mode", C.c_uint32), ("device", C.c_uint32),
         ("table_entries", C.c_uint64), ("table_slots", C.c_uint64), ("table_bytes", C.c_uint64),
         ("table_candidates", C.c_uint64), ("tier_entries", C.c_uint64), ("tier_slots", C.c_uint64),
+        ("cuckoo_entries", C.c_uint64), ("cuckoo_probes", C.c_uint32), ("cuckoo_slots", C.c_uint32),
     ]
 
 
@@ -72,6 +73,7 @@ def lib() -> C.CDLL:
         "fqtk_b200_matcher_destroy": (None, [vp]),
         "fqtk_b200_matcher_get_info": (C.c_int, [vp, C.POINTER(MatcherInfo)]),
         "fqtk_b200_set_table_budget": (None, [C.c_uint64]),
+        "fqtk_b200_set_cuckoo_arity": (None, [C.c_int]),
         "fqtk_b200_matcher_assign": (C.c_int, [vp, C.c_char_p, C.c_size_t, u32p]),
         "fqtk_b200_matcher_assign_batch": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp]),
         "fqtk_b200_matcher_assign_segments": (C.c_int, [vp, C.POINTER(Segment), C.c_uint32, C.c_uint64, vp]),

@@ -73,6 +73,8 @@ struct fqtk_b200_matcher {
     uint32_t* d_table = nullptr;
     uint32_t* d_tier = nullptr;
     uint32_t* d_bloom = nullptr;
+    uint32_t* d_cuckoo = nullptr;
+    uint64_t cuckoo_entries = 0;
     uint64_t tier_entries = 0;
     unsigned long long* d_counts = nullptr;
     fq::MatchParams params{};
@@ -235,6 +237,152 @@ void build_tier(const std::vector<uint32_t>& keys, const std::vector<uint32_t>& 
     slots_out = slots;
 }
 
+// k_probe3's shared-memory table (kernels.h): every Some(..) memo entry whose key is pure A/C/G/T, keyed by the
+// compressed 32-bit key, as an NP-ary cuckoo table of 4-byte quotient entries.  Returns 0 when built, 1 when the
+// panel does not qualify (the matcher then stays on k_probe2), < 0 on a CUDA error.
+int g_cuckoo_arity = -2;  // -2: not set (FQTK_B200_CK_NP decides, default auto)
+int ck_force_np() {  // -1 auto, 0 no cuckoo table (k_probe2 runs instead), 2 | 3 force the arity
+    if (g_cuckoo_arity != -2) return g_cuckoo_arity;
+    const char* e = getenv("FQTK_B200_CK_NP");
+    return e ? atoi(e) : -1;
+}
+
+template <int W>
+int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, const std::vector<uint32_t>& res,
+                   uint64_t n) {
+    const uint32_t S = m->S, pad = m->params.last_pad;
+    if (S + 1u > 8192u) return 1;
+    // pure-A/C/G/T entries, de-duplicated (the same string is enumerated once per barcode it is close to)
+    std::vector<std::pair<uint32_t, uint32_t>> ent;  // (compressed key, result word)
+    for (uint64_t t = 0; t < n; t++) {
+        if (res[t] == fq::NONE) continue;
+        uint32_t kw[W];
+        for (int k = 0; k < W; k++) kw[k] = keys[t * W + k];
+        bool valid;
+        const uint32_t k = fq::acgt_key<W>(kw, pad, valid);
+        if (valid) ent.emplace_back(k, res[t]);
+    }
+    std::sort(ent.begin(), ent.end());
+    ent.erase(std::unique(ent.begin(), ent.end()), ent.end());
+    for (size_t t = 1; t < ent.size(); t++)
+        if (ent[t].first == ent[t - 1].first) return 1;  // cannot happen: one string, one result
+    if (ent.empty()) return 1;
+    // value code = idx << (bb + nb) | best << nb | (next - next_min)
+    uint32_t max_idx = 0, max_best = 0, min_next = 255, max_next = 0;
+    for (auto& e : ent) {
+        max_idx = std::max(max_idx, e.second >> 16);
+        max_best = std::max(max_best, (e.second >> 8) & 0xFFu);
+        min_next = std::min(min_next, e.second & 0xFFu);
+        max_next = std::max(max_next, e.second & 0xFFu);
+    }
+    auto bits_for = [](uint32_t v) { uint32_t b = 0; while (b < 32 && (v >> b)) b++; return b; };
+    const uint32_t ib = bits_for(max_idx), bb = bits_for(max_best), nb = bits_for(max_next - min_next);
+    uint32_t cb = std::max(1u, ib + bb + nb);
+    auto code_of = [&](uint32_t r) {
+        return ((r >> 16) << (bb + nb)) | (((r >> 8) & 0xFFu) << nb) | ((r & 0xFFu) - min_next);
+    };
+    for (auto& e : ent)
+        if (code_of(e.second) == (1u << cb) - 1u) { cb++; break; }  // the all-ones code means "empty slot"
+    if (cb > 16) return 1;
+
+    // geometry: the smallest 2-ary layout at load <= 0.40, else the smallest 3-ary one at load <= 0.80, that leaves
+    // room for >= 4 histogram replicas
+    const size_t smem_max = (size_t)m->geo.max_smem_optin - 1024;
+    const size_t hist_min = (size_t)(S + 1u) * 4u * 4u;
+    struct Geo { uint32_t np, sb[3]; };
+    std::vector<Geo> options;
+    const int force = ck_force_np();
+    if (force == 0) return 1;
+    for (uint32_t s = std::max(cb, 4u); s <= 16; s++) {
+        if (force != 3) {
+            options.push_back({2, {s, s, 0}});
+            options.push_back({2, {s + 1, s, 0}});
+        }
+        if (force != 2) options.push_back({3, {s, s, s}});
+    }
+    auto slots_of = [](const Geo& g) { uint64_t t = 0; for (uint32_t i = 0; i < g.np; i++) t += 1ull << g.sb[i]; return t; };
+    std::stable_sort(options.begin(), options.end(), [&](const Geo& a, const Geo& b) {
+        if (force < 0 && a.np != b.np) return a.np < b.np;  // prefer two probes per read whenever they fit
+        return slots_of(a) < slots_of(b);
+    });
+    for (const Geo& g : options) {
+        const uint64_t slots = slots_of(g);
+        const double max_load = g.np == 2 ? 0.40 : 0.80;
+        if ((double)ent.size() > max_load * (double)slots) continue;
+        if (slots * 4 + hist_min > smem_max) continue;
+        uint32_t off[3] = {0, 0, 0};
+        for (uint32_t i = 1; i < g.np; i++) off[i] = off[i - 1] + (1u << g.sb[i - 1]);
+        std::vector<uint32_t> slot_key(slots, 0u), slot_code(slots, 0xFFFFFFFFu);  // code 0xFFFFFFFF = empty
+        uint64_t rng = 0x9E3779B97F4A7C15ull;
+        bool ok = true;
+        for (auto& e : ent) {
+            uint32_t ck = e.first, cc = code_of(e.second);
+            uint32_t avoid = 0xFFFFFFFFu;
+            bool placed = false;
+            for (int kick = 0; kick < 2000 && !placed; kick++) {
+                uint32_t pos[3];
+                for (uint32_t i = 0; i < g.np; i++) pos[i] = off[i] + ((ck * fq::ck_mul((int)i)) >> (32u - g.sb[i]));
+                for (uint32_t i = 0; i < g.np && !placed; i++)
+                    if (slot_code[pos[i]] == 0xFFFFFFFFu) {
+                        slot_key[pos[i]] = ck;
+                        slot_code[pos[i]] = cc;
+                        placed = true;
+                    }
+                if (placed) break;
+                rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                uint32_t v = (uint32_t)(rng >> 33) % g.np;
+                if (pos[v] == avoid) v = (v + 1u) % g.np;  // do not bounce straight back
+                std::swap(ck, slot_key[pos[v]]);
+                std::swap(cc, slot_code[pos[v]]);
+                avoid = pos[v];
+            }
+            if (!placed) { ok = false; break; }
+        }
+        if (!ok) continue;
+        // serialise + verify with the kernel's own arithmetic
+        std::vector<uint32_t> words(slots, 0xFFFFFFFFu);
+        for (uint32_t i = 0; i < g.np; i++)
+            for (uint32_t q = 0; q < (1u << g.sb[i]); q++) {
+                const uint32_t at = off[i] + q;
+                if (slot_code[at] == 0xFFFFFFFFu) continue;
+                words[at] = ((slot_key[at] * fq::ck_mul((int)i)) << g.sb[i]) | slot_code[at];
+            }
+        const uint32_t limit = (1u << cb) - 1u;
+        for (auto& e : ent) {
+            uint32_t u = 0xFFFFFFFFu;
+            for (uint32_t i = 0; i < g.np; i++) {
+                const uint32_t sl = (e.first * fq::ck_mul((int)i)) >> (32u - g.sb[i]);
+                u = std::min(u, words[off[i] + sl] ^ (e.first * (fq::ck_mul((int)i) << g.sb[i])));
+            }
+            if (!(u < limit) || u != code_of(e.second)) return fail(FQTK_B200_ERR_CUDA, "cuckoo table self-check failed");
+        }
+        CU(cudaMalloc(&m->d_cuckoo, words.size() * 4));
+        CU(cudaMemcpy(m->d_cuckoo, words.data(), words.size() * 4, cudaMemcpyHostToDevice));
+        fq::MatchParams& p = m->params;
+        p.ck_entries = m->d_cuckoo;
+        p.ck_np = g.np;
+        p.ck_words = (uint32_t)slots;
+        for (uint32_t i = 0; i < 3; i++) {
+            const uint32_t j = i < g.np ? i : 0;
+            p.ck_off[i] = off[j];
+            p.ck_shift[i] = 32u - g.sb[j];
+            p.ck_mulb[i] = fq::ck_mul((int)j) << g.sb[j];
+        }
+        p.ck_limit = limit;
+        p.ck_lb = bb + nb;
+        p.ck_bsh = 8u - nb;
+        p.ck_bmask8 = ((1u << bb) - 1u) << 8;
+        p.ck_nmask = (1u << nb) - 1u;
+        p.ck_next_min = min_next;
+        uint32_t rep = 32;
+        while (rep > 1 && fq::probe3_smem_bytes((uint32_t)slots, S, rep) > smem_max) rep >>= 1;
+        p.ck_hist_rep = rep;
+        m->cuckoo_entries = ent.size();
+        return 0;
+    }
+    return 1;
+}
+
 int build_table(fqtk_b200_matcher* m) {
     const uint32_t S = m->S, L = m->L, W = m->W;
     std::vector<uint8_t> masks((size_t)S * L);
@@ -354,6 +502,11 @@ int build_table(fqtk_b200_matcher* m) {
             m->params.bloom_shift = bshift;
         }
     }
+    // k_probe3's shared-memory cuckoo table of the pure-A/C/G/T entries (L <= 16)
+    if (W <= 2) {
+        const int rc = (W == 1) ? build_cuckoo_w<1>(m, keys, res, n) : build_cuckoo_w<2>(m, keys, res, n);
+        if (rc < 0) return rc;
+    }
     return 0;
 }
 
@@ -389,9 +542,6 @@ int run_device(fqtk_b200_matcher* m, const fq::ReadSource& src, uint32_t* d_resu
         const size_t need = (size_t)s.n * m->W;
         if (need > m->scratch_words) {
             if (m->d_scratch) cudaFree(m->d_scratch);
-    if (m->d_route_ws) cudaFree(m->d_route_ws);
-    for (int s = 0; s < N_PIPE; s++)
-        if (m->d_seg_packed[s]) cudaFree(m->d_seg_packed[s]);
             m->d_scratch = nullptr;
             CU(cudaMalloc(&m->d_scratch, need * 4));
             m->scratch_words = need;
@@ -422,6 +572,8 @@ int fqtk_b200_device_count(void) {
 }
 
 void fqtk_b200_set_table_budget(uint64_t max_candidates) { g_table_budget = max_candidates; }
+
+void fqtk_b200_set_cuckoo_arity(int arity) { g_cuckoo_arity = (arity == 0 || arity == 2 || arity == 3) ? arity : -1; }
 
 uint64_t fqtk_b200_kernel_launches(void) { return fq::kernel_launches(); }
 
@@ -542,6 +694,10 @@ int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t S, uint32_t L,
     m->params.bloom = nullptr;
     m->params.bloom_words = 0;
     m->params.bloom_shift = 32;
+    m->params.ck_entries = nullptr;
+    m->params.ck_np = 0;
+    m->params.ck_words = 0;
+    m->params.ck_hist_rep = 1;
     m->mode = FQTK_B200_MODE_BRUTE;
     if (use_cache && W <= (uint32_t)fq::MAX_FAST_WORDS) {
         rc = build_table(m);
@@ -574,6 +730,7 @@ void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m) {
     if (m->d_table) cudaFree(m->d_table);
     if (m->d_tier) cudaFree(m->d_tier);
     if (m->d_bloom) cudaFree(m->d_bloom);
+    if (m->d_cuckoo) cudaFree(m->d_cuckoo);
     if (m->d_counts) cudaFree(m->d_counts);
     delete m;
 }
@@ -592,6 +749,9 @@ int fqtk_b200_matcher_get_info(const fqtk_b200_matcher* m, fqtk_b200_matcher_inf
     info->table_candidates = m->table_candidates;
     info->tier_entries = m->tier_entries;
     info->tier_slots = m->params.tier_slots;
+    info->cuckoo_entries = m->cuckoo_entries;
+    info->cuckoo_probes = m->params.ck_np;
+    info->cuckoo_slots = m->params.ck_words;
     return FQTK_B200_OK;
 }
 

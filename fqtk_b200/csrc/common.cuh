@@ -95,6 +95,35 @@ FQ_HD uint32_t last_word_pad_for_len(uint32_t L) {
     return used == 0u ? 0u : (0x11111111u << (4u * used));
 }
 
+// ---- compressed A/C/G/T keys (k_probe3) -------------------------------------------------------------------
+// A read of L <= 16 symbols that are all one of A,C,G,T (one-hot nibbles 1,2,4,8) is mapped injectively onto 32
+// bits, two per symbol, with no table: word 0 keeps (n0^n1, n1^n2) in bits {0,1} of every nibble, word 1 keeps
+// (n1^n2, n2^n3) in bits {2,3} — a Gray code of the bit position.  `valid` is false for every other read (any
+// nibble that is not exactly one bit: no-calls, IUPAC codes, junk), which must not use the key.
+//   one-hot test per word: d = x - 0x11111111; every nibble is one-hot  <=>  d & (x | 0x88888888) == 0
+//   (no zero nibble -> no borrows -> (n-1) & n == 0 per nibble; the lowest zero nibble always leaves its bit 3 set).
+// `pad` (last_word_pad_for_len) puts an 'A' in the unused nibbles of the last word so they pass the test.
+template <int W>
+FQ_HD uint32_t acgt_key(const uint32_t (&w)[W], uint32_t pad, bool& valid) {
+    static_assert(W == 1 || W == 2, "compressed keys cover L <= 16");
+    const uint32_t x0 = (W == 1) ? (w[0] | pad) : w[0];
+    uint32_t bad = (x0 - 0x11111111u) & (x0 | 0x88888888u);
+    uint32_t k = (x0 ^ (x0 >> 1)) & 0x33333333u;
+    if constexpr (W == 2) {
+        const uint32_t x1 = w[W > 1 ? 1 : 0] | pad;
+        bad |= (x1 - 0x11111111u) & (x1 | 0x88888888u);
+        k |= (x1 ^ (x1 << 1)) & 0xCCCCCCCCu;
+    }
+    valid = bad == 0u;
+    return k;
+}
+
+// Fixed odd multipliers of the (up to three) cuckoo sub-tables: slot_i = (k * CK_MUL[i]) >> (32 - sb_i), and the low
+// 32 - sb_i bits of the same product are the remainder stored in the entry (multiplication by an odd constant is a
+// bijection of 32-bit keys, so slot + remainder identify the key exactly).
+constexpr uint32_t CK_MUL0 = 0x9E3779B1u, CK_MUL1 = 0x85EBCA77u, CK_MUL2 = 0xC2B2AE3Du;
+FQ_HD uint32_t ck_mul(int i) { return i == 0 ? CK_MUL0 : (i == 1 ? CK_MUL1 : CK_MUL2); }
+
 // 32-bit mix of a W-word key; identical on host (table build) and device (probe): multiply-add over the words
 // (FMA pipe), then one xorshift-multiply round so that every output bit depends on every input nibble.
 template <int W>

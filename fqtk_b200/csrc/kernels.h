@@ -29,7 +29,25 @@ struct MatchParams {
     uint32_t hist_rep;         // shared-memory replicas of the k_probe2 histogram (power of two <= 32)
     uint32_t bloom_words;      // power of two, 0 = no filter
     uint32_t bloom_shift;      // 32 - log2(bloom_words)
+    // k_probe3 (L <= 16): every memo-table entry whose key is pure A/C/G/T, as a 2- or 3-ary cuckoo table of 4-byte
+    // quotient entries staged into shared memory (layout: CuckooLayout below)
+    const uint32_t* ck_entries;  // ck_words words: sub-table 0 | sub-table 1 | (sub-table 2); nullptr = none
+    uint32_t ck_np;              // sub-tables (= probes per read): 0 = no cuckoo table, 2 or 3
+    uint32_t ck_words;           // total entries
+    uint32_t ck_off[3];          // first entry of sub-table i
+    uint32_t ck_shift[3];        // 32 - sb_i  (sub-table i has 2^sb_i slots)
+    uint32_t ck_mulb[3];         // ck_mul(i) << sb_i : k * ck_mulb[i] = the key's remainder, aligned with the entry's
+    uint32_t ck_limit;           // 2^cb - 1: a probe found its key iff (entry ^ remainder) < ck_limit
+    uint32_t ck_lb;              // value code = idx << lb | best << nb | (next - ck_next_min), lb = bb + nb
+    uint32_t ck_bsh, ck_bmask8;  // (code << ck_bsh) & ck_bmask8 = best << 8   (ck_bsh = 8 - nb)
+    uint32_t ck_nmask;           // code & ck_nmask = next - ck_next_min
+    uint32_t ck_next_min;
+    uint32_t ck_hist_rep;        // histogram replicas of k_probe3 (power of two <= 32)
 };
+
+// Cuckoo entry (4 bytes) of sub-table i: (remainder << sb_i) | code, where remainder = low (32 - sb_i) bits of
+// k * ck_mul(i), code < 2^cb - 1 <= 2^sb_i - 1.  Empty = 0xFFFFFFFF (its code field is all ones, which no real entry
+// uses, so an empty slot can never be taken for a key).
 
 // Where a batch of reads lives on the device.
 struct ReadSource {
@@ -84,6 +102,7 @@ cudaError_t launch_route(const uint32_t* d_results, uint64_t n, uint32_t S, uint
                          unsigned long long* d_offsets, void* d_workspace, const LaunchGeometry& g, cudaStream_t stream);
 cudaError_t prepare_kernels(const LaunchGeometry& g);  // opt-in shared memory attributes, once per device
 
+size_t probe3_smem_bytes(uint32_t ck_words, uint32_t S, uint32_t hist_rep);
 size_t probe2_fixed_smem_bytes(uint32_t W, uint32_t S, int threads);  // k_probe2 shared memory besides tier + Bloom
 int probe2_threads();
 uint32_t probe2_hist_rep(uint32_t S);

@@ -15,7 +15,9 @@
 //              an in-alphabet read is None; a miss on any other read (IUPAC / junk / lowercase-only symbols) is
 //              resolved by the whole warp brute-forcing that one read with shuffle min / second-min reduction.
 // Per-sample counts: CTA-private shared-memory histogram (atomics), flushed once per CTA with 64-bit REDs.
+#include <algorithm>
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -712,6 +714,190 @@ __global__ void __launch_bounds__(PROBE2_THREADS, 1) k_probe2(const MatchParams 
 }
 
 // ------------------------------------------------------------------------------------------------------
+// k_probe3: the HBM-resident packed route when every pure-A/C/G/T memo-table entry fits in shared memory (L <= 16,
+// e.g. cfg 2 / cfg 3).  No global-memory probe, no queue, no Bloom filter on the common path:
+//   * the read's one-hot nibbles are compressed to a 32-bit key (2 bits per base, common.cuh acgt_key) and tested
+//     for validity (every nibble exactly one bit) in ~10 integer ops;
+//   * the key is looked up in an NP-ary cuckoo table of 4-byte QUOTIENT entries in shared memory: sub-table i is
+//     indexed by the top sb_i bits of k * ck_mul(i) and the entry holds the low 32 - sb_i bits of that product next
+//     to a sb_i-bit value code, so one LDS.32 + one XOR both verify the key exactly and deliver the value;
+//     the NP candidates are merged with a min (at most one can match; an empty slot decodes to the largest code);
+//   * a valid read that is not in the table is farther than max_mismatches from every barcode -> None;
+//   * reads with any other symbol (no-calls, IUPAC, junk; ~3 % of real reads) take the slow path: the global memo
+//     table (which also holds the N-containing neighbours) and, outside its alphabet, the warp-cooperative scan.
+// A warp owns tiles of 128 consecutive reads, four per lane (W x LDG.128 in, one STG.128 out), double-buffered.
+// Per-sample counts: lane-replicated shared-memory histogram; the unmatched bin is (reads done) - (sum of bins).
+// ------------------------------------------------------------------------------------------------------
+constexpr int PROBE3_THREADS = 1024;
+constexpr int PROBE3_R = 4;
+constexpr int PROBE3_TILE = 32 * PROBE3_R;
+
+// One read: key, validity, NP probes, branch-free decode.  `bin` = sample index for the histogram (S when the read
+// is unmatched or must still go through the slow path).  Value code layout (kernels.h): idx | best | next - next_min.
+template <int W, int NP, bool PAD>
+FQ_D uint32_t ck_lookup(const MatchParams& p, const uint32_t (&base)[3], const uint32_t (&w)[W], bool& valid,
+                        uint32_t& bin) {
+    const uint32_t k = acgt_key<W>(w, PAD ? p.last_pad : 0u, valid);
+    uint32_t u = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        const uint32_t slot = (k * ck_mul(i)) >> p.ck_shift[i];
+        const uint32_t e = lds32_ro(base[i] + slot * 4u);
+        u = min(u, e ^ (k * p.ck_mulb[i]));  // < ck_limit iff this slot holds the key; then u is its value code
+    }
+    const bool found = valid && u < p.ck_limit;
+    const uint32_t idx = u >> p.ck_lb;
+    const uint32_t low = ((u << p.ck_bsh) & p.ck_bmask8) | (u & p.ck_nmask);  // best << 8 | (next - next_min)
+    bin = found ? idx : p.S;
+    return found ? idx * 65536u + low + p.ck_next_min : NONE;
+}
+
+// Resolves R reads per lane; every lane of the warp must call it (the slow path is warp-cooperative).
+template <int W, int NP, bool PAD, int R>
+FQ_D void probe3_resolve(const MatchParams& p, const uint32_t (&base)[3], const uint32_t (&w)[R][W],
+                         uint32_t (&res)[R], uint32_t (&bin)[R], uint32_t live, uint32_t lane) {
+    uint32_t bad = 0u;  // bit r: read r is not pure A/C/G/T
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        bool valid;
+        res[r] = ck_lookup<W, NP, PAD>(p, base, w[r], valid, bin[r]);
+        bad |= valid ? 0u : (1u << r);
+    }
+    bad &= live;
+    while (__any_sync(0xFFFFFFFFu, bad != 0u)) {
+        const uint32_t r = (uint32_t)__ffs(bad) - 1u;  // this lane's first unresolved read (if any)
+        uint32_t kw[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            kw[k] = w[0][k];
+#pragma unroll
+            for (int q = 1; q < R; q++) kw[k] = (r == (uint32_t)q) ? w[q][k] : kw[k];
+        }
+        uint32_t out = NONE;
+        bool slow = false;
+        if (bad) {
+            const bool hit = table_lookup<W>(p, kw, hash_key<W>(kw), out);
+            slow = !hit && !read_in_table_alphabet<W>(kw, p.last_pad);
+        }
+        uint32_t pending = __ballot_sync(0xFFFFFFFFu, slow);
+        while (pending) {
+            const int src_lane = __ffs(pending) - 1;
+            pending &= pending - 1u;
+            uint32_t bw[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) bw[k] = __shfl_sync(0xFFFFFFFFu, kw[k], src_lane);
+            const uint32_t o = warp_brute_one<W>(p, bw, lane);
+            if ((int)lane == src_lane) out = o;
+        }
+        if (bad) {
+            const uint32_t ob = (out == NONE) ? p.S : (out >> 16);
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                res[q] = (r == (uint32_t)q) ? out : res[q];
+                bin[q] = (r == (uint32_t)q) ? ob : bin[q];
+            }
+            bad &= bad - 1u;
+        }
+    }
+}
+
+// hist[bin * hrep + lane % hrep] += 1 (unconditional: unmatched reads have bin S)
+FQ_D void hist_inc(uint32_t hist_lane_addr, uint32_t hstride, uint32_t bin) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_lane_addr + bin * hstride) : "memory");
+}
+
+template <int W>
+FQ_D void probe3_load(const uint32_t* __restrict__ packed, uint32_t tile, uint32_t lane, uint32_t (&w)[PROBE3_R][W]) {
+    static_assert(W == 1 || W == 2, "k_probe3 covers L <= 16");
+    const uint4* in = reinterpret_cast<const uint4*>(packed) + (size_t)(tile * 32u + lane) * W;
+    if constexpr (W == 1) {
+        const uint4 q = __ldg(in);
+        w[0][0] = q.x; w[1][0] = q.y; w[2][0] = q.z; w[3][0] = q.w;
+    } else {
+        const uint4 q0 = __ldg(in), q1 = __ldg(in + 1);
+        w[0][0] = q0.x; w[0][W - 1] = q0.y; w[1][0] = q0.z; w[1][W - 1] = q0.w;
+        w[2][0] = q1.x; w[2][W - 1] = q1.y; w[3][0] = q1.z; w[3][W - 1] = q1.w;
+    }
+}
+
+template <int W, int NP, bool PAD>
+FQ_D void probe3_tile(const MatchParams& p, const uint32_t (&base)[3], const uint32_t (&w)[PROBE3_R][W],
+                      uint32_t* __restrict__ results, uint32_t tile, uint32_t lane, uint32_t a_hist, uint32_t hstride) {
+    uint32_t res[PROBE3_R], bin[PROBE3_R];
+    probe3_resolve<W, NP, PAD, PROBE3_R>(p, base, w, res, bin, 0xFu, lane);
+    reinterpret_cast<uint4*>(results)[tile * 32u + lane] = make_uint4(res[0], res[1], res[2], res[3]);
+#pragma unroll
+    for (int r = 0; r < PROBE3_R; r++) hist_inc(a_hist, hstride, bin[r]);
+}
+
+template <int W, int NP, bool PAD>
+__global__ void __launch_bounds__(PROBE3_THREADS, 1) k_probe3(const MatchParams p, const ReadSource src,
+                                                           uint32_t* __restrict__ results) {
+    extern __shared__ uint4 s_dyn[];
+    uint32_t* s_ck = reinterpret_cast<uint32_t*>(s_dyn);
+    uint32_t* s_hist = s_ck + p.ck_words;
+    const uint32_t hrep = p.ck_hist_rep;
+    {
+        const uint4* g4 = reinterpret_cast<const uint4*>(p.ck_entries);  // ck_words is a multiple of 4
+        uint4* s4 = reinterpret_cast<uint4*>(s_ck);
+        for (uint32_t t = threadIdx.x; t < p.ck_words / 4u; t += blockDim.x) s4[t] = __ldg(g4 + t);
+    }
+    for (uint32_t t = threadIdx.x; t < (p.S + 1u) * hrep; t += blockDim.x) s_hist[t] = 0u;
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_warps = blockDim.x >> 5, warp_in_cta = threadIdx.x >> 5;
+    uint32_t base[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) base[i] = smem_addr(s_ck) + p.ck_off[i < NP ? i : 0] * 4u;
+    uint32_t a_hist = smem_addr(s_hist) + (lane & (hrep - 1u)) * 4u;
+    const uint32_t hstride = hrep * 4u;
+    asm volatile("" : "+r"(base[0]), "+r"(base[1]), "+r"(base[2]), "+r"(a_hist));  // keep them in registers
+
+    const uint32_t n_tiles = (uint32_t)(src.n / (uint64_t)PROBE3_TILE);
+    const uint32_t stride = gridDim.x * n_warps;
+    uint32_t tile = blockIdx.x * n_warps + warp_in_cta;
+
+    // two register buffers, alternating: the next tile's keys are in flight while this one is resolved
+    uint32_t wa[PROBE3_R][W], wb[PROBE3_R][W];
+    if (tile < n_tiles) probe3_load<W>(src.packed, tile, lane, wa);
+    while (tile < n_tiles) {
+        uint32_t nt = tile + stride;
+        if (nt < n_tiles) probe3_load<W>(src.packed, nt, lane, wb);
+        probe3_tile<W, NP, PAD>(p, base, wa, results, tile, lane, a_hist, hstride);
+        tile = nt;
+        if (tile >= n_tiles) break;
+        nt = tile + stride;
+        if (nt < n_tiles) probe3_load<W>(src.packed, nt, lane, wa);
+        probe3_tile<W, NP, PAD>(p, base, wb, results, tile, lane, a_hist, hstride);
+        tile = nt;
+    }
+
+    // ---- tail: fewer than 128 reads, one per lane, first warp of the grid ----
+    if (blockIdx.x == 0 && threadIdx.x < 32u) {
+        for (uint64_t b0 = (uint64_t)n_tiles * PROBE3_TILE; b0 < src.n; b0 += 32u) {
+            const uint64_t i = b0 + lane;
+            const bool live = i < src.n;
+            uint32_t w1[1][W], r1[1], bin1[1];
+#pragma unroll
+            for (int k = 0; k < W; k++) w1[0][k] = live ? __ldg(src.packed + i * W + k) : 0u;
+            probe3_resolve<W, NP, PAD, 1>(p, base, w1, r1, bin1, live ? 1u : 0u, lane);
+            if (live) {
+                results[i] = r1[0];
+                hist_inc(a_hist, hstride, bin1[0]);
+            }
+        }
+    }
+    // ---- flush the replicated bins (bin S = unmatched) ----
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b <= p.S; b += blockDim.x) {
+        uint32_t c = 0;
+        for (uint32_t r = 0; r < hrep; r++) c += s_hist[b * hrep + r];
+        if (c) atomicAdd(&p.counts[b], (unsigned long long)c);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // k_pack: encode() for a batch (mod.rs:49-61), any L
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_pack(const uint8_t* __restrict__ ascii, uint64_t n, uint32_t L,
@@ -870,11 +1056,43 @@ static cudaError_t launch_probe2_w(const MatchParams& p, const ReadSource& src, 
     return cudaGetLastError();
 }
 
+size_t probe3_smem_bytes(uint32_t ck_words, uint32_t S, uint32_t hist_rep) {
+    return (size_t)ck_words * 4 + (size_t)(S + 1u) * hist_rep * 4;
+}
+
+template <int W, int NP, bool PAD>
+static cudaError_t launch_probe3_wnp(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
+                                     const LaunchGeometry& g, cudaStream_t stream) {
+    auto k = k_probe3<W, NP, PAD>;
+    const size_t smem = probe3_smem_bytes(p.ck_words, p.S, p.ck_hist_rep);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const uint64_t n_warp_tiles = (src.n + PROBE3_TILE - 1) / PROBE3_TILE;
+    const uint64_t want = (n_warp_tiles + PROBE3_THREADS / 32 - 1) / (PROBE3_THREADS / 32);
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)g.sm_count));
+    k<<<grid, PROBE3_THREADS, smem, stream>>>(p, src, d_results);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int W, int NP>
+static cudaError_t launch_probe3_wn(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
+                                    const LaunchGeometry& g, cudaStream_t stream) {
+    return p.last_pad ? launch_probe3_wnp<W, NP, true>(p, src, d_results, g, stream)
+                      : launch_probe3_wnp<W, NP, false>(p, src, d_results, g, stream);
+}
+
 cudaError_t launch_probe(const MatchParams& p, const ReadSource& src, uint32_t* d_results, const LaunchGeometry& g,
                          cudaStream_t stream) {
     if (src.n == 0) return cudaSuccess;
     if (p.table == nullptr || p.W > (uint32_t)MAX_FAST_WORDS) return cudaErrorInvalidValue;
     const bool ascii = src.ascii != nullptr;
+    if (!ascii && p.ck_np && p.W <= 2u &&
+        ((reinterpret_cast<uintptr_t>(src.packed) | reinterpret_cast<uintptr_t>(d_results)) & 15u) == 0u) {
+        if (p.W == 1) return p.ck_np == 2 ? launch_probe3_wn<1, 2>(p, src, d_results, g, stream)
+                                          : launch_probe3_wn<1, 3>(p, src, d_results, g, stream);
+        return p.ck_np == 2 ? launch_probe3_wn<2, 2>(p, src, d_results, g, stream)
+                            : launch_probe3_wn<2, 3>(p, src, d_results, g, stream);
+    }
     if (ascii) {
         switch (p.W) {
             case 1: return launch_probe_w<1, true>(p, src, d_results, g, stream);

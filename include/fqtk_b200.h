@@ -75,6 +75,9 @@ typedef struct {
     uint64_t table_candidates;   /* neighbourhood strings enumerated before filtering to Some(..) */
     uint64_t tier_entries;       /* memo-table entries (best distance 0) also cached in the shared-memory hot tier */
     uint64_t tier_slots;
+    uint64_t cuckoo_entries;     /* pure-A/C/G/T memo entries held in the shared-memory cuckoo table (0 = none) */
+    uint32_t cuckoo_probes;      /* sub-tables = probes per read (2 or 3) */
+    uint32_t cuckoo_slots;       /* 4-byte slots over all sub-tables */
 } fqtk_b200_matcher_info;
 
 /* ---- lifecycle -------------------------------------------------------------------------------------
@@ -90,6 +93,10 @@ FQTK_B200_API int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t 
 FQTK_B200_API void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m);
 FQTK_B200_API int fqtk_b200_matcher_get_info(const fqtk_b200_matcher* m, fqtk_b200_matcher_info* info);
 FQTK_B200_API void fqtk_b200_set_table_budget(uint64_t max_candidates);
+/* Tuning / test knob for matchers created afterwards: shared-memory cuckoo table of the pure-A/C/G/T memo entries
+ * (k_probe3, L <= 16): -1 = automatic (default), 0 = none (the packed route runs k_probe2), 2 or 3 = force that many
+ * sub-tables.  Results are identical for every setting. */
+FQTK_B200_API void fqtk_b200_set_cuckoo_arity(int arity);
 
 /* ---- reference-facing calls: HOST buffers ----------------------------------------------------------
  * BarcodeMatcher::assign (barcode_matching.rs:165-186) for one read, any length: len < L -> NONE (:167-169);

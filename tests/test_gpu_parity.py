@@ -255,6 +255,40 @@ def test_configs_reduced_n(cfg_id, n, use_cache):
                          expect_mode="table" if use_cache else "brute")
 
 
+@pytest.mark.parametrize("arity", [0, 2, 3])
+def test_packed_route_kernel_variants(arity):
+    """The HBM-resident packed route has two kernels for L <= 16: k_probe3 (shared-memory cuckoo table of the pure
+    A/C/G/T memo entries, 2 or 3 sub-tables) and k_probe2 (hot tier + global memo table; arity 0).  All bit-exact."""
+    torch = torch_cuda()
+    L = _lib.lib()
+    rng = np.random.default_rng(4242 + arity)
+    try:
+        L.fqtk_b200_set_cuckoo_arity(arity)
+        for cfg_id, n in [(2, 150_000), (3, 200_000)]:
+            cfg = synth.CONFIGS[cfg_id]
+            panel = synth.panel(cfg)
+            bcs = [bytes(r) for r in panel]
+            with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, True) as m:
+                assert int(m.info().cuckoo_probes) == arity
+                assert (int(m.info().cuckoo_entries) > 0) == (arity != 0)
+            reads = synth.reads_host(panel, cfg.seed_reads, 31, n)
+            reads[::41, 3] = ord("N")
+            reads[::97, 1] = ord("r")
+            check_against_oracle(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, reads, True, expect_mode="table")
+        for _ in range(16):  # pad nibbles (L % 8 != 0), one-word and two-word keys, dirty reads, odd parameters
+            Lb = int(rng.choice([1, 2, 3, 7, 8, 9, 12, 15, 16]))
+            S = int(rng.choice([1, 2, 5, 40, 300]))
+            pa = ALPHABETS[["acgt", "acgtn", "iupac"][int(rng.integers(0, 3))]]
+            ra = ALPHABETS[["acgt", "acgtn", "dirty"][int(rng.integers(0, 3))]]
+            bcs = random_panel(rng, S, Lb, pa)
+            mm, delta = int(rng.choice([0, 1, 2])), int(rng.choice([0, 1, 2, 3]))
+            reads = random_reads(rng, bcs, Lb, 5000 + int(rng.integers(0, 300)), ra)
+            check_against_oracle(bcs, mm, delta, reads, True)
+    finally:
+        L.fqtk_b200_set_cuckoo_arity(-1)
+    del torch
+
+
 def test_synth_device_equals_host():
     torch = torch_cuda()
     for cfg_id in (2, 3, 5):
