@@ -719,91 +719,128 @@ __global__ void __launch_bounds__(PROBE2_THREADS, 1) k_probe2(const MatchParams 
 //   * the read's one-hot nibbles are compressed to a 32-bit key (2 bits per base, common.cuh acgt_key) and tested
 //     for validity (every nibble exactly one bit) in ~10 integer ops;
 //   * the key is looked up in an NP-ary cuckoo table of 4-byte QUOTIENT entries in shared memory: sub-table i is
-//     indexed by the top sb_i bits of k * ck_mul(i) and the entry holds the low 32 - sb_i bits of that product next
-//     to a sb_i-bit value code, so one LDS.32 + one XOR both verify the key exactly and deliver the value;
-//     the NP candidates are merged with a min (at most one can match; an empty slot decodes to the largest code);
+//     indexed by the top sb_i bits of k * ck_mul(i) and the entry holds the low 32 - sb_i bits of that product above
+//     a value code, so one LDS.32 and one multiply-add (entry - remainder) both verify the key exactly and deliver
+//     the code; the NP candidates are merged with a min (at most one can match; an empty slot yields a code >= limit);
+//   * the code's low bits (best, next) go through a lane-replicated shared-memory LUT, its high bits are the sample;
 //   * a valid read that is not in the table is farther than max_mismatches from every barcode -> None;
-//   * reads with any other symbol (no-calls, IUPAC, junk; ~3 % of real reads) take the slow path: the global memo
-//     table (which also holds the N-containing neighbours) and, outside its alphabet, the warp-cooperative scan.
+//   * reads with any other symbol (no-calls, IUPAC, junk; ~3 % of real reads) are written as None, parked in a
+//     lane-private stash in global memory (L2-resident) and resolved a few tiles later, many at a time, through the
+//     global memo table (which also holds the N-containing neighbours) or the warp-cooperative scan; the same thread
+//     then overwrites the result word and moves the count from the unmatched bin to the sample's.
+// The kernel is bound by the SM's integer pipes, so the arithmetic is spread over both of them on purpose: adds and
+// address computations are written as multiply-adds with an opaque multiplier (IMAD, fma pipe) and only the logic
+// ops, shifts, compares and selects stay on the alu pipe (both pipes issue one warp instruction per 2 clocks).
 // A warp owns tiles of 128 consecutive reads, four per lane (W x LDG.128 in, one STG.128 out), double-buffered.
-// Per-sample counts: lane-replicated shared-memory histogram; the unmatched bin is (reads done) - (sum of bins).
+// Per-sample counts: lane-replicated shared-memory histogram, bin S = unmatched.
 // ------------------------------------------------------------------------------------------------------
 constexpr int PROBE3_THREADS = 1024;
 constexpr int PROBE3_R = 4;
 constexpr int PROBE3_TILE = 32 * PROBE3_R;
+constexpr uint32_t PROBE3_STASH_CAP = 16;                   // stash entries per lane
+constexpr uint32_t PROBE3_STASH_DRAIN = PROBE3_STASH_CAP - 2 * PROBE3_R;  // drain when a lane could overflow next round
 
-// One read: key, validity, NP probes, branch-free decode.  `bin` = sample index for the histogram (S when the read
-// is unmatched or must still go through the slow path).  Value code layout (kernels.h): idx | best | next - next_min.
+struct Probe3Ctx {
+    uint32_t base[3];    // shared-window address of sub-table i
+    uint32_t a_lut;      // ... of this lane's decode-LUT replica
+    uint32_t a_hist;     // ... of this lane's histogram replica
+    uint32_t lut_stride, hstride;  // bytes between consecutive LUT entries / bins of one replica
+    uint32_t one, four;  // 1 and 4 read from the kernel parameters, so that ptxas cannot fold x * one + c back into an
+};                       //   alu-pipe add / LEA: these adds and scalings stay multiply-adds on the fma pipe
+
+FQ_D uint32_t imad(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
+
+// hist[bin * hrep + lane % hrep] += v
+FQ_D void hist_add(const Probe3Ctx& c, uint32_t bin, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(imad(bin, c.hstride, c.a_hist)), "r"(v) : "memory");
+}
+FQ_D void hist_inc(const Probe3Ctx& c, uint32_t bin) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(imad(bin, c.hstride, c.a_hist)) : "memory");
+}
+
+// One read through the shared-memory table.  Returns the result word (NONE for unmatched AND for reads that are not
+// pure A/C/G/T, which `valid` reports); `bin` = histogram bin (S when NONE).
 template <int W, int NP, bool PAD>
-FQ_D uint32_t ck_lookup(const MatchParams& p, const uint32_t (&base)[3], const uint32_t (&w)[W], bool& valid,
-                        uint32_t& bin) {
-    const uint32_t k = acgt_key<W>(w, PAD ? p.last_pad : 0u, valid);
+FQ_D uint32_t ck_lookup(const MatchParams& p, const Probe3Ctx& c, const uint32_t (&w)[W], bool& valid, uint32_t& bin) {
+    // acgt_key (common.cuh), with the subtractions and the left shift on the fma pipe
+    const uint32_t pad = PAD ? p.last_pad : 0u;
+    const uint32_t x0 = (W == 1) ? (w[0] | pad) : w[0];
+    uint32_t t = imad(x0, c.one, 0xEEEEEEEFu) & (x0 | 0x88888888u);
+    uint32_t k = (x0 ^ (x0 >> 1)) & 0x33333333u;
+    if constexpr (W == 2) {
+        const uint32_t x1 = w[W - 1] | pad;
+        t |= imad(x1, c.one, 0xEEEEEEEFu) & (x1 | 0x88888888u);
+        k |= (x1 ^ imad(x1, c.one, x1)) & 0xCCCCCCCCu;
+    }
+    valid = t == 0u;
     uint32_t u = 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < NP; i++) {
         const uint32_t slot = (k * ck_mul(i)) >> p.ck_shift[i];
-        const uint32_t e = lds32_ro(base[i] + slot * 4u);
-        u = min(u, e ^ (k * p.ck_mulb[i]));  // < ck_limit iff this slot holds the key; then u is its value code
+        const uint32_t e = lds32_ro(imad(slot, c.four, c.base[i]));
+        u = min(u, imad(k, p.ck_negmulb[i], e));  // entry - remainder: the value code iff this slot holds the key
     }
     const bool found = valid && u < p.ck_limit;
     const uint32_t idx = u >> p.ck_lb;
-    const uint32_t low = ((u << p.ck_bsh) & p.ck_bmask8) | (u & p.ck_nmask);  // best << 8 | (next - next_min)
+    const uint32_t low = lds32_ro(imad(u & p.ck_lowmask, c.lut_stride, c.a_lut));  // best << 8 | next
     bin = found ? idx : p.S;
-    return found ? idx * 65536u + low + p.ck_next_min : NONE;
+    return found ? idx * 65536u + low : NONE;
 }
 
-// Resolves R reads per lane; every lane of the warp must call it (the slow path is warp-cooperative).
-template <int W, int NP, bool PAD, int R>
-FQ_D void probe3_resolve(const MatchParams& p, const uint32_t (&base)[3], const uint32_t (&w)[R][W],
-                         uint32_t (&res)[R], uint32_t (&bin)[R], uint32_t live, uint32_t lane) {
-    uint32_t bad = 0u;  // bit r: read r is not pure A/C/G/T
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        bool valid;
-        res[r] = ck_lookup<W, NP, PAD>(p, base, w[r], valid, bin[r]);
-        bad |= valid ? 0u : (1u << r);
+// memo-table / warp-cooperative resolution of one read per lane (`act` lanes only); all 32 lanes must call it
+template <int W>
+FQ_D uint32_t slow_resolve(const MatchParams& p, const uint32_t (&kw)[W], bool act, uint32_t lane) {
+    uint32_t out = NONE;
+    bool slow = false;
+    if (act) {
+        const bool hit = table_lookup<W>(p, kw, hash_key<W>(kw), out);
+        slow = !hit && !read_in_table_alphabet<W>(kw, p.last_pad);
     }
-    bad &= live;
-    while (__any_sync(0xFFFFFFFFu, bad != 0u)) {
-        const uint32_t r = (uint32_t)__ffs(bad) - 1u;  // this lane's first unresolved read (if any)
+    uint32_t pending = __ballot_sync(0xFFFFFFFFu, slow);
+    while (pending) {
+        const int src_lane = __ffs(pending) - 1;
+        pending &= pending - 1u;
+        uint32_t bw[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) bw[k] = __shfl_sync(0xFFFFFFFFu, kw[k], src_lane);
+        const uint32_t o = warp_brute_one<W>(p, bw, lane);
+        if ((int)lane == src_lane) out = o;
+    }
+    return out;
+}
+
+// Lane-private stash of reads waiting for the slow path: entry e of this thread lives at base + e * stride bytes,
+// stride = 16 * (threads of the launch), so the 32 lanes of a warp write 512 contiguous bytes per entry index.
+struct Stash {
+    uint8_t* next;  // where this lane's next entry goes
+    uint32_t cnt;   // entries parked
+};
+
+// Resolve every stashed read of the warp; results and counts are patched.
+template <int W>
+FQ_D void probe3_drain(const MatchParams& p, const Probe3Ctx& c, const uint8_t* __restrict__ stash, uint32_t cnt,
+                       uint32_t* __restrict__ results, uint32_t lane) {
+    const uint32_t maxc = __reduce_max_sync(0xFFFFFFFFu, cnt);
+    const size_t stride = (size_t)p.ck_stash_threads * 16u;
+    for (uint32_t e = 0; e < maxc; e++) {
+        const bool act = e < cnt;
         uint32_t kw[W];
+        uint32_t idx = 0;
 #pragma unroll
-        for (int k = 0; k < W; k++) {
-            kw[k] = w[0][k];
-#pragma unroll
-            for (int q = 1; q < R; q++) kw[k] = (r == (uint32_t)q) ? w[q][k] : kw[k];
+        for (int k = 0; k < W; k++) kw[k] = 0u;
+        if (act) {
+            const uint4 q = __ldcg(reinterpret_cast<const uint4*>(stash + e * stride));
+            kw[0] = q.x;
+            if constexpr (W == 2) kw[W - 1] = q.y;
+            idx = q.z;
         }
-        uint32_t out = NONE;
-        bool slow = false;
-        if (bad) {
-            const bool hit = table_lookup<W>(p, kw, hash_key<W>(kw), out);
-            slow = !hit && !read_in_table_alphabet<W>(kw, p.last_pad);
-        }
-        uint32_t pending = __ballot_sync(0xFFFFFFFFu, slow);
-        while (pending) {
-            const int src_lane = __ffs(pending) - 1;
-            pending &= pending - 1u;
-            uint32_t bw[W];
-#pragma unroll
-            for (int k = 0; k < W; k++) bw[k] = __shfl_sync(0xFFFFFFFFu, kw[k], src_lane);
-            const uint32_t o = warp_brute_one<W>(p, bw, lane);
-            if ((int)lane == src_lane) out = o;
-        }
-        if (bad) {
-            const uint32_t ob = (out == NONE) ? p.S : (out >> 16);
-#pragma unroll
-            for (int q = 0; q < R; q++) {
-                res[q] = (r == (uint32_t)q) ? out : res[q];
-                bin[q] = (r == (uint32_t)q) ? ob : bin[q];
-            }
-            bad &= bad - 1u;
+        const uint32_t out = slow_resolve<W>(p, kw, act, lane);
+        if (act && out != NONE) {  // it was written and counted as unmatched when it was parked
+            results[idx] = out;
+            hist_inc(c, out >> 16);
+            hist_add(c, p.S, 0xFFFFFFFFu);
         }
     }
-}
-
-// hist[bin * hrep + lane % hrep] += 1 (unconditional: unmatched reads have bin S)
-FQ_D void hist_inc(uint32_t hist_lane_addr, uint32_t hstride, uint32_t bin) {
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_lane_addr + bin * hstride) : "memory");
 }
 
 template <int W>
@@ -821,38 +858,64 @@ FQ_D void probe3_load(const uint32_t* __restrict__ packed, uint32_t tile, uint32
 }
 
 template <int W, int NP, bool PAD>
-FQ_D void probe3_tile(const MatchParams& p, const uint32_t (&base)[3], const uint32_t (&w)[PROBE3_R][W],
-                      uint32_t* __restrict__ results, uint32_t tile, uint32_t lane, uint32_t a_hist, uint32_t hstride) {
+FQ_D void probe3_tile(const MatchParams& p, const Probe3Ctx& c, const uint32_t (&w)[PROBE3_R][W],
+                      uint32_t* __restrict__ results, uint32_t tile, uint32_t lane, Stash& st) {
     uint32_t res[PROBE3_R], bin[PROBE3_R];
-    probe3_resolve<W, NP, PAD, PROBE3_R>(p, base, w, res, bin, 0xFu, lane);
-    reinterpret_cast<uint4*>(results)[tile * 32u + lane] = make_uint4(res[0], res[1], res[2], res[3]);
+    bool valid[PROBE3_R];
 #pragma unroll
-    for (int r = 0; r < PROBE3_R; r++) hist_inc(a_hist, hstride, bin[r]);
+    for (int r = 0; r < PROBE3_R; r++) res[r] = ck_lookup<W, NP, PAD>(p, c, w[r], valid[r], bin[r]);
+    const uint32_t g = tile * 32u + lane;  // this lane's group of four consecutive reads
+    reinterpret_cast<uint4*>(results)[g] = make_uint4(res[0], res[1], res[2], res[3]);
+#pragma unroll
+    for (int r = 0; r < PROBE3_R; r++) hist_inc(c, bin[r]);
+    if (__any_sync(0xFFFFFFFFu, !(valid[0] && valid[1] && valid[2] && valid[3]))) {
+        const uint32_t stride = p.ck_stash_threads * 16u;
+#pragma unroll
+        for (int r = 0; r < PROBE3_R; r++) {
+            if (!valid[r]) {
+                *reinterpret_cast<uint2*>(st.next) = make_uint2(w[r][0], w[r][W - 1]);
+                *reinterpret_cast<uint32_t*>(st.next + 8) = imad(g, c.four, (uint32_t)r);
+                st.next += stride;
+                st.cnt++;
+            }
+        }
+    }
 }
 
 template <int W, int NP, bool PAD>
 __global__ void __launch_bounds__(PROBE3_THREADS, 1) k_probe3(const MatchParams p, const ReadSource src,
                                                            uint32_t* __restrict__ results) {
     extern __shared__ uint4 s_dyn[];
+    // layout: cuckoo entries | decode LUT replicas | histogram replicas
     uint32_t* s_ck = reinterpret_cast<uint32_t*>(s_dyn);
-    uint32_t* s_hist = s_ck + p.ck_words;
+    uint32_t* s_lut = s_ck + p.ck_words;
+    const uint32_t lrep = p.ck_lut_rep, n_lut = p.ck_lowmask + 1u;
+    uint32_t* s_hist = s_lut + n_lut * lrep;
     const uint32_t hrep = p.ck_hist_rep;
     {
         const uint4* g4 = reinterpret_cast<const uint4*>(p.ck_entries);  // ck_words is a multiple of 4
         uint4* s4 = reinterpret_cast<uint4*>(s_ck);
         for (uint32_t t = threadIdx.x; t < p.ck_words / 4u; t += blockDim.x) s4[t] = __ldg(g4 + t);
     }
+    for (uint32_t t = threadIdx.x; t < n_lut * lrep; t += blockDim.x) s_lut[t] = __ldg(p.ck_entries + p.ck_words + t / lrep);
     for (uint32_t t = threadIdx.x; t < (p.S + 1u) * hrep; t += blockDim.x) s_hist[t] = 0u;
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n_warps = blockDim.x >> 5, warp_in_cta = threadIdx.x >> 5;
-    uint32_t base[3];
+    Probe3Ctx c;
 #pragma unroll
-    for (int i = 0; i < 3; i++) base[i] = smem_addr(s_ck) + p.ck_off[i < NP ? i : 0] * 4u;
-    uint32_t a_hist = smem_addr(s_hist) + (lane & (hrep - 1u)) * 4u;
-    const uint32_t hstride = hrep * 4u;
-    asm volatile("" : "+r"(base[0]), "+r"(base[1]), "+r"(base[2]), "+r"(a_hist));  // keep them in registers
+    for (int i = 0; i < 3; i++) c.base[i] = smem_addr(s_ck) + p.ck_off[i < NP ? i : 0] * 4u;
+    c.a_lut = smem_addr(s_lut) + (lane & (lrep - 1u)) * 4u;
+    c.a_hist = smem_addr(s_hist) + (lane & (hrep - 1u)) * 4u;
+    c.lut_stride = lrep * 4u;
+    c.hstride = hrep * 4u;
+    c.one = p.ck_one;
+    c.four = p.ck_four;
+    asm volatile("" : "+r"(c.base[0]), "+r"(c.base[1]), "+r"(c.base[2]), "+r"(c.a_lut), "+r"(c.a_hist));
+
+    uint8_t* const stash = reinterpret_cast<uint8_t*>(p.ck_stash + ((size_t)blockIdx.x * blockDim.x + threadIdx.x));
+    Stash st{stash, 0u};
 
     const uint32_t n_tiles = (uint32_t)(src.n / (uint64_t)PROBE3_TILE);
     const uint32_t stride = gridDim.x * n_warps;
@@ -864,36 +927,46 @@ __global__ void __launch_bounds__(PROBE3_THREADS, 1) k_probe3(const MatchParams 
     while (tile < n_tiles) {
         uint32_t nt = tile + stride;
         if (nt < n_tiles) probe3_load<W>(src.packed, nt, lane, wb);
-        probe3_tile<W, NP, PAD>(p, base, wa, results, tile, lane, a_hist, hstride);
+        probe3_tile<W, NP, PAD>(p, c, wa, results, tile, lane, st);
         tile = nt;
-        if (tile >= n_tiles) break;
-        nt = tile + stride;
-        if (nt < n_tiles) probe3_load<W>(src.packed, nt, lane, wa);
-        probe3_tile<W, NP, PAD>(p, base, wb, results, tile, lane, a_hist, hstride);
-        tile = nt;
+        if (tile < n_tiles) {
+            nt = tile + stride;
+            if (nt < n_tiles) probe3_load<W>(src.packed, nt, lane, wa);
+            probe3_tile<W, NP, PAD>(p, c, wb, results, tile, lane, st);
+            tile = nt;
+        }
+        if (__any_sync(0xFFFFFFFFu, st.cnt > PROBE3_STASH_DRAIN)) {
+            probe3_drain<W>(p, c, stash, st.cnt, results, lane);
+            st = Stash{stash, 0u};
+        }
     }
+    probe3_drain<W>(p, c, stash, st.cnt, results, lane);
 
     // ---- tail: fewer than 128 reads, one per lane, first warp of the grid ----
     if (blockIdx.x == 0 && threadIdx.x < 32u) {
         for (uint64_t b0 = (uint64_t)n_tiles * PROBE3_TILE; b0 < src.n; b0 += 32u) {
             const uint64_t i = b0 + lane;
             const bool live = i < src.n;
-            uint32_t w1[1][W], r1[1], bin1[1];
+            uint32_t w1[W];
 #pragma unroll
-            for (int k = 0; k < W; k++) w1[0][k] = live ? __ldg(src.packed + i * W + k) : 0u;
-            probe3_resolve<W, NP, PAD, 1>(p, base, w1, r1, bin1, live ? 1u : 0u, lane);
+            for (int k = 0; k < W; k++) w1[k] = live ? __ldg(src.packed + i * W + k) : 0u;
+            bool valid;
+            uint32_t bin;
+            uint32_t out = ck_lookup<W, NP, PAD>(p, c, w1, valid, bin);
+            const uint32_t slow = slow_resolve<W>(p, w1, live && !valid, lane);
             if (live) {
-                results[i] = r1[0];
-                hist_inc(a_hist, hstride, bin1[0]);
+                if (!valid) out = slow;
+                results[i] = out;
+                hist_inc(c, out == NONE ? p.S : (out >> 16));
             }
         }
     }
     // ---- flush the replicated bins (bin S = unmatched) ----
     __syncthreads();
     for (uint32_t b = threadIdx.x; b <= p.S; b += blockDim.x) {
-        uint32_t c = 0;
-        for (uint32_t r = 0; r < hrep; r++) c += s_hist[b * hrep + r];
-        if (c) atomicAdd(&p.counts[b], (unsigned long long)c);
+        uint32_t v = 0;
+        for (uint32_t r = 0; r < hrep; r++) v += s_hist[b * hrep + r];
+        if (v) atomicAdd(&p.counts[b], (unsigned long long)v);
     }
 }
 
@@ -1056,15 +1129,19 @@ static cudaError_t launch_probe2_w(const MatchParams& p, const ReadSource& src, 
     return cudaGetLastError();
 }
 
-size_t probe3_smem_bytes(uint32_t ck_words, uint32_t S, uint32_t hist_rep) {
-    return (size_t)ck_words * 4 + (size_t)(S + 1u) * hist_rep * 4;
+size_t probe3_smem_bytes(uint32_t ck_words, uint32_t lut_words, uint32_t S, uint32_t hist_rep) {
+    return (size_t)ck_words * 4 + (size_t)lut_words * 4 + (size_t)(S + 1u) * hist_rep * 4;
+}
+uint32_t probe3_stash_threads(const LaunchGeometry& g) { return (uint32_t)g.sm_count * PROBE3_THREADS; }
+size_t probe3_stash_bytes(const LaunchGeometry& g) {
+    return (size_t)probe3_stash_threads(g) * PROBE3_STASH_CAP * sizeof(uint4);
 }
 
 template <int W, int NP, bool PAD>
 static cudaError_t launch_probe3_wnp(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
                                      const LaunchGeometry& g, cudaStream_t stream) {
     auto k = k_probe3<W, NP, PAD>;
-    const size_t smem = probe3_smem_bytes(p.ck_words, p.S, p.ck_hist_rep);
+    const size_t smem = probe3_smem_bytes(p.ck_words, (p.ck_lowmask + 1u) * p.ck_lut_rep, p.S, p.ck_hist_rep);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const uint64_t n_warp_tiles = (src.n + PROBE3_TILE - 1) / PROBE3_TILE;
     const uint64_t want = (n_warp_tiles + PROBE3_THREADS / 32 - 1) / (PROBE3_THREADS / 32);
