@@ -74,7 +74,6 @@ struct fqtk_b200_matcher {
     uint32_t* d_tier = nullptr;
     uint32_t* d_bloom = nullptr;
     uint32_t* d_cuckoo = nullptr;
-    void* d_stash = nullptr;
     uint64_t cuckoo_entries = 0;
     uint64_t tier_entries = 0;
     unsigned long long* d_counts = nullptr;
@@ -286,20 +285,10 @@ int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, cons
         if (code_of(e.second) == (1u << cb) - 1u) { cb++; break; }  // the all-ones code means "empty slot"
     if (cb > 16) return 1;
 
-    // decode LUT: low = code & lowmask -> best << 8 | next, replicated per lane group in shared memory
     const uint32_t lb = bb + nb;
-    if (lb > 10) return 1;
-    std::vector<uint32_t> lut(1u << lb, 0u);
-    for (uint32_t b = 0; b <= max_best; b++)
-        for (uint32_t x = 0; x <= max_next - min_next; x++) lut[(b << nb) | x] = (b << 8) | (x + min_next);
-    uint32_t lrep = 32;
-    while (lrep > 1 && (size_t)lut.size() * lrep * 4 > 4096) lrep >>= 1;
-    const size_t lut_words = lut.size() * lrep;
-
     // geometry: the smallest 2-ary layout at load <= 0.40, else the smallest 3-ary one at load <= 0.80, that leaves
     // room for >= 4 histogram replicas
     const size_t smem_max = (size_t)m->geo.max_smem_optin - 1024;
-    const size_t hist_min = (size_t)(S + 1u) * 4u * 4u + lut_words * 4;
     struct Geo { uint32_t np, sb[3]; };
     std::vector<Geo> options;
     const int force = ck_force_np();
@@ -320,7 +309,8 @@ int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, cons
         const uint64_t slots = slots_of(g);
         const double max_load = g.np == 2 ? 0.40 : 0.80;
         if ((double)ent.size() > max_load * (double)slots) continue;
-        if (slots * 4 + hist_min > smem_max) continue;
+        const uint32_t stash_cap = fq::probe3_stash_cap((uint32_t)slots, S, smem_max);
+        if (stash_cap == 0) continue;
         uint32_t off[3] = {0, 0, 0};
         for (uint32_t i = 1; i < g.np; i++) off[i] = off[i - 1] + (1u << g.sb[i - 1]);
         std::vector<uint32_t> slot_key(slots, 0u), slot_code(slots, 0xFFFFFFFFu);  // code 0xFFFFFFFF = empty
@@ -350,16 +340,16 @@ int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, cons
             if (!placed) { ok = false; break; }
         }
         if (!ok) continue;
-        // serialise (cuckoo entries, then the decode LUT) + verify with the kernel's own arithmetic
-        std::vector<uint32_t> words(slots + lut.size(), 0xFFFFFFFFu);
+        // serialise + verify with the kernel's own arithmetic
+        std::vector<uint32_t> words(slots, 0xFFFFFFFFu);
         for (uint32_t i = 0; i < g.np; i++)
             for (uint32_t q = 0; q < (1u << g.sb[i]); q++) {
                 const uint32_t at = off[i] + q;
                 if (slot_code[at] == 0xFFFFFFFFu) continue;
                 words[at] = ((slot_key[at] * fq::ck_mul((int)i)) << g.sb[i]) | slot_code[at];
             }
-        std::copy(lut.begin(), lut.end(), words.begin() + slots);
-        const uint32_t limit = (1u << cb) - 1u, lowmask = (1u << lb) - 1u;
+        const uint32_t limit = (1u << cb) - 1u;
+        const uint32_t bsh = 8u - nb, bmask8 = ((1u << bb) - 1u) << 8, nmask = (1u << nb) - 1u;
         uint32_t negmulb[3] = {0, 0, 0};
         for (uint32_t i = 0; i < g.np; i++) negmulb[i] = 0u - (fq::ck_mul((int)i) << g.sb[i]);
         for (auto& e : ent) {
@@ -368,13 +358,11 @@ int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, cons
                 const uint32_t sl = (e.first * fq::ck_mul((int)i)) >> (32u - g.sb[i]);
                 u = std::min(u, words[off[i] + sl] + e.first * negmulb[i]);
             }
-            const uint32_t word = ((u >> lb) << 16) | lut[u & lowmask];
+            const uint32_t word = ((u >> lb) << 16) + (((u << bsh) & bmask8) | (u & nmask)) + min_next;
             if (!(u < limit) || word != e.second) return fail(FQTK_B200_ERR_CUDA, "cuckoo table self-check failed");
         }
         CU(cudaMalloc(&m->d_cuckoo, words.size() * 4));
         CU(cudaMemcpy(m->d_cuckoo, words.data(), words.size() * 4, cudaMemcpyHostToDevice));
-        const size_t stash_bytes = fq::probe3_stash_bytes(m->geo);
-        CU(cudaMalloc(&m->d_stash, stash_bytes));
         fq::MatchParams& p = m->params;
         p.ck_entries = m->d_cuckoo;
         p.ck_np = g.np;
@@ -387,13 +375,11 @@ int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, cons
         }
         p.ck_limit = limit;
         p.ck_lb = lb;
-        p.ck_lowmask = lowmask;
-        p.ck_lut_rep = lrep;
-        p.ck_stash = reinterpret_cast<uint4*>(m->d_stash);
-        p.ck_stash_threads = fq::probe3_stash_threads(m->geo);
-        uint32_t rep = 32;
-        while (rep > 1 && fq::probe3_smem_bytes((uint32_t)slots, (uint32_t)lut_words, S, rep) > smem_max) rep >>= 1;
-        p.ck_hist_rep = rep;
+        p.ck_bsh = bsh;
+        p.ck_bmask8 = bmask8;
+        p.ck_nmask = nmask;
+        p.ck_next_min = min_next;
+        p.ck_stash_cap = stash_cap;
         m->cuckoo_entries = ent.size();
         return 0;
     }
@@ -714,13 +700,9 @@ int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t S, uint32_t L,
     m->params.ck_entries = nullptr;
     m->params.ck_np = 0;
     m->params.ck_words = 0;
-    m->params.ck_hist_rep = 1;
     m->params.ck_one = 1;
     m->params.ck_four = 4;
-    m->params.ck_lut_rep = 1;
-    m->params.ck_lowmask = 0;
-    m->params.ck_stash = nullptr;
-    m->params.ck_stash_threads = 0;
+    m->params.ck_stash_cap = 0;
     m->mode = FQTK_B200_MODE_BRUTE;
     if (use_cache && W <= (uint32_t)fq::MAX_FAST_WORDS) {
         rc = build_table(m);
@@ -754,7 +736,6 @@ void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m) {
     if (m->d_tier) cudaFree(m->d_tier);
     if (m->d_bloom) cudaFree(m->d_bloom);
     if (m->d_cuckoo) cudaFree(m->d_cuckoo);
-    if (m->d_stash) cudaFree(m->d_stash);
     if (m->d_counts) cudaFree(m->d_counts);
     delete m;
 }

@@ -38,12 +38,11 @@ struct MatchParams {
     uint32_t ck_shift[3];        // 32 - sb_i  (sub-table i has 2^sb_i slots)
     uint32_t ck_negmulb[3];      // -(ck_mul(i) << sb_i): entry + k * ck_negmulb[i] = entry - (the key's remainder << sb_i)
     uint32_t ck_limit;           // 2^cb - 1: a probe found its key iff entry - remainder < ck_limit (then it is the code)
-    uint32_t ck_lb;              // value code = idx << lb | low; the decode LUT (ck_lowmask + 1 words after the cuckoo
-    uint32_t ck_lowmask;         //   entries in ck_entries) maps low = code & ck_lowmask to best << 8 | next
-    uint32_t ck_lut_rep;         // shared-memory replicas of the decode LUT (power of two <= 32)
-    uint4* ck_stash;             // lane-private stash of reads that are not pure A/C/G/T: entry e of thread t at
-    uint32_t ck_stash_threads;   //   ck_stash[e * ck_stash_threads + t] = {w0, w1, read index, -}
-    uint32_t ck_hist_rep;        // histogram replicas of k_probe3 (power of two <= 32)
+    uint32_t ck_lb;              // value code = idx << lb | best << nb | (next - ck_next_min), lb = bb + nb
+    uint32_t ck_bsh, ck_bmask8;  // (code << ck_bsh) & ck_bmask8 = best << 8   (ck_bsh = 8 - nb)
+    uint32_t ck_nmask;           // code & ck_nmask = next - ck_next_min
+    uint32_t ck_next_min;
+    uint32_t ck_stash_cap;       // stash entries per warp of k_probe3 (shared memory left after the table + histogram)
     uint32_t ck_one, ck_four;    // 1 and 4 (see Probe3Ctx in match_kernels.cu)
 };
 
@@ -105,9 +104,8 @@ cudaError_t launch_route(const uint32_t* d_results, uint64_t n, uint32_t S, uint
                          unsigned long long* d_offsets, void* d_workspace, const LaunchGeometry& g, cudaStream_t stream);
 cudaError_t prepare_kernels(const LaunchGeometry& g);  // opt-in shared memory attributes, once per device
 
-size_t probe3_smem_bytes(uint32_t ck_words, uint32_t lut_words, uint32_t S, uint32_t hist_rep);
-size_t probe3_stash_bytes(const LaunchGeometry& g);
-uint32_t probe3_stash_threads(const LaunchGeometry& g);  // threads of one k_probe3 launch (lane-private stash stride)
+size_t probe3_fixed_smem_bytes(uint32_t ck_words, uint32_t S);
+uint32_t probe3_stash_cap(uint32_t ck_words, uint32_t S, size_t smem_max);  // 0 = k_probe3 does not fit
 size_t probe2_fixed_smem_bytes(uint32_t W, uint32_t S, int threads);  // k_probe2 shared memory besides tier + Bloom
 int probe2_threads();
 uint32_t probe2_hist_rep(uint32_t S);

@@ -722,69 +722,77 @@ __global__ void __launch_bounds__(PROBE2_THREADS, 1) k_probe2(const MatchParams 
 //     indexed by the top sb_i bits of k * ck_mul(i) and the entry holds the low 32 - sb_i bits of that product above
 //     a value code, so one LDS.32 and one multiply-add (entry - remainder) both verify the key exactly and deliver
 //     the code; the NP candidates are merged with a min (at most one can match; an empty slot yields a code >= limit);
-//   * the code's low bits (best, next) go through a lane-replicated shared-memory LUT, its high bits are the sample;
 //   * a valid read that is not in the table is farther than max_mismatches from every barcode -> None;
-//   * reads with any other symbol (no-calls, IUPAC, junk; ~3 % of real reads) are written as None, parked in a
-//     lane-private stash in global memory (L2-resident) and resolved a few tiles later, many at a time, through the
-//     global memo table (which also holds the N-containing neighbours) or the warp-cooperative scan; the same thread
-//     then overwrites the result word and moves the count from the unmatched bin to the sample's.
-// The kernel is bound by the SM's integer pipes, so the arithmetic is spread over both of them on purpose: adds and
-// address computations are written as multiply-adds with an opaque multiplier (IMAD, fma pipe) and only the logic
-// ops, shifts, compares and selects stay on the alu pipe (both pipes issue one warp instruction per 2 clocks).
+//   * reads with any other symbol (no-calls, IUPAC, junk; ~3 % of real reads) are written as None, parked in a small
+//     per-warp stash in shared memory and resolved a warp-full at a time through the global memo table (which also
+//     holds the N-containing neighbours) or the warp-cooperative scan; the result word is then overwritten.
+// Per-sample counts: a lane-private (bank = lane, conflict-free) shared-memory histogram of PACKED 16-bit counters
+// (two bins per word: bin b adds 1 << 16 * (b & 1) to word b >> 1); all warps run the same number of loop rounds and
+// every PROBE3_FLUSH_ROUNDS rounds the CTA flushes the counters to the global u64 table under a barrier, long before
+// any 16-bit field can overflow.  Bin S = unmatched, bin S + 1 = parked (counted when it is resolved).
+// The kernel is bound by the SM's integer and shared-memory pipes, so adds and address computations on the hot path
+// are written as multiply-adds with an operand read from the kernel parameters (IMAD on the fma pipe) and only the
+// logic ops, shifts, compares and selects stay on the alu pipe (both issue one warp instruction per 2 clocks).
 // A warp owns tiles of 128 consecutive reads, four per lane (W x LDG.128 in, one STG.128 out), double-buffered.
-// Per-sample counts: lane-replicated shared-memory histogram, bin S = unmatched.
 // ------------------------------------------------------------------------------------------------------
 constexpr int PROBE3_THREADS = 1024;
 constexpr int PROBE3_R = 4;
 constexpr int PROBE3_TILE = 32 * PROBE3_R;
-constexpr uint32_t PROBE3_STASH_CAP = 16;                   // stash entries per lane
-constexpr uint32_t PROBE3_STASH_DRAIN = PROBE3_STASH_CAP - 2 * PROBE3_R;  // drain when a lane could overflow next round
+constexpr uint32_t PROBE3_STASH_MAX = 48;      // stash entries per warp (8-byte key + 4-byte read index each), at most
+constexpr uint32_t PROBE3_STASH_MIN = 16;      // ... at least (else the geometry is rejected on the host)
+// a packed counter gains at most 32 warps x 4 reads per round (main path) plus as many again from drains
+constexpr uint32_t PROBE3_FLUSH_ROUNDS = 128;  // 128 * 256 = 32768 < 65536
 
 struct Probe3Ctx {
-    uint32_t base[3];    // shared-window address of sub-table i
-    uint32_t a_lut;      // ... of this lane's decode-LUT replica
-    uint32_t a_hist;     // ... of this lane's histogram replica
-    uint32_t lut_stride, hstride;  // bytes between consecutive LUT entries / bins of one replica
-    uint32_t one, four;  // 1 and 4 read from the kernel parameters, so that ptxas cannot fold x * one + c back into an
-};                       //   alu-pipe add / LEA: these adds and scalings stay multiply-adds on the fma pipe
+    uint32_t base[3];  // shared-window address of sub-table i
+    uint32_t a_skey;   // ... of this warp's stash: ck_stash_cap keys (8 bytes each), then the read indices
+    uint32_t a_hist;   // ... of this lane's histogram column (word w of the column at a_hist + 128 * w)
+};
+// p.ck_one (= 1) and p.ck_four (= 4) come from the kernel parameters so that ptxas cannot fold x * one + c back into
+// an alu-pipe add / LEA: those adds and scalings stay multiply-adds on the fma pipe.
 
 FQ_D uint32_t imad(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
 
-// hist[bin * hrep + lane % hrep] += v
-FQ_D void hist_add(const Probe3Ctx& c, uint32_t bin, uint32_t v) {
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(imad(bin, c.hstride, c.a_hist)), "r"(v) : "memory");
-}
-FQ_D void hist_inc(const Probe3Ctx& c, uint32_t bin) {
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(imad(bin, c.hstride, c.a_hist)) : "memory");
+// packed histogram: bin b lives in the (b & 1) half of word b >> 1 of the lane's column
+FQ_D void hist_inc(const MatchParams& p, const Probe3Ctx& c, uint32_t bin) {
+    const uint32_t addr = imad(bin & ~1u, p.ck_four * 16u, c.a_hist);  // (bin >> 1) * 128
+    const uint32_t val = imad(bin & 1u, 65535u, p.ck_one);             // 1 or 65536
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
 }
 
-// One read through the shared-memory table.  Returns the result word (NONE for unmatched AND for reads that are not
-// pure A/C/G/T, which `valid` reports); `bin` = histogram bin (S when NONE).
-template <int W, int NP, bool PAD>
-FQ_D uint32_t ck_lookup(const MatchParams& p, const Probe3Ctx& c, const uint32_t (&w)[W], bool& valid, uint32_t& bin) {
-    // acgt_key (common.cuh), with the subtractions and the left shift on the fma pipe
+// Compressed key + validity of one read: acgt_key (common.cuh), with the subtractions and the left shift on the fma pipe.
+template <int W, bool PAD>
+FQ_D uint32_t ck_key(const MatchParams& p, const uint32_t (&w)[W], bool& valid) {
     const uint32_t pad = PAD ? p.last_pad : 0u;
     const uint32_t x0 = (W == 1) ? (w[0] | pad) : w[0];
-    uint32_t t = imad(x0, c.one, 0xEEEEEEEFu) & (x0 | 0x88888888u);
+    uint32_t t = imad(x0, p.ck_one, 0xEEEEEEEFu) & (x0 | 0x88888888u);
     uint32_t k = (x0 ^ (x0 >> 1)) & 0x33333333u;
     if constexpr (W == 2) {
         const uint32_t x1 = w[W - 1] | pad;
-        t |= imad(x1, c.one, 0xEEEEEEEFu) & (x1 | 0x88888888u);
-        k |= (x1 ^ imad(x1, c.one, x1)) & 0xCCCCCCCCu;
+        t |= imad(x1, p.ck_one, 0xEEEEEEEFu) & (x1 | 0x88888888u);
+        k |= (x1 ^ imad(x1, p.ck_one, x1)) & 0xCCCCCCCCu;
     }
     valid = t == 0u;
+    return k;
+}
+
+// One key through the shared-memory table.  Returns the result word (NONE for unmatched AND for reads that are not
+// pure A/C/G/T); `bin` = histogram bin (S: unmatched, S + 1: parked).
+template <int NP>
+FQ_D uint32_t ck_find(const MatchParams& p, const Probe3Ctx& c, uint32_t k, bool valid, uint32_t& bin) {
     uint32_t u = 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < NP; i++) {
         const uint32_t slot = (k * ck_mul(i)) >> p.ck_shift[i];
-        const uint32_t e = lds32_ro(imad(slot, c.four, c.base[i]));
+        const uint32_t e = lds32_ro(imad(slot, p.ck_four, c.base[i]));
         u = min(u, imad(k, p.ck_negmulb[i], e));  // entry - remainder: the value code iff this slot holds the key
     }
     const bool found = valid && u < p.ck_limit;
+    // value code = idx << lb | best << nb | (next - next_min)
     const uint32_t idx = u >> p.ck_lb;
-    const uint32_t low = lds32_ro(imad(u & p.ck_lowmask, c.lut_stride, c.a_lut));  // best << 8 | next
-    bin = found ? idx : p.S;
-    return found ? idx * 65536u + low : NONE;
+    const uint32_t low = ((u << p.ck_bsh) & p.ck_bmask8) | (u & p.ck_nmask);
+    bin = found ? idx : (valid ? p.S : p.S + 1u);
+    return found ? imad(idx, 65536u, imad(low, p.ck_one, p.ck_next_min)) : NONE;
 }
 
 // memo-table / warp-cooperative resolution of one read per lane (`act` lanes only); all 32 lanes must call it
@@ -809,36 +817,60 @@ FQ_D uint32_t slow_resolve(const MatchParams& p, const uint32_t (&kw)[W], bool a
     return out;
 }
 
-// Lane-private stash of reads waiting for the slow path: entry e of this thread lives at base + e * stride bytes,
-// stride = 16 * (threads of the launch), so the 32 lanes of a warp write 512 contiguous bytes per entry index.
-struct Stash {
-    uint8_t* next;  // where this lane's next entry goes
-    uint32_t cnt;   // entries parked
-};
-
-// Resolve every stashed read of the warp; results and counts are patched.
+// Resolve every stashed read of the warp (`cnt` is warp-uniform): patch the result words, count the reads.
 template <int W>
-FQ_D void probe3_drain(const MatchParams& p, const Probe3Ctx& c, const uint8_t* __restrict__ stash, uint32_t cnt,
-                       uint32_t* __restrict__ results, uint32_t lane) {
-    const uint32_t maxc = __reduce_max_sync(0xFFFFFFFFu, cnt);
-    const size_t stride = (size_t)p.ck_stash_threads * 16u;
-    for (uint32_t e = 0; e < maxc; e++) {
+__device__ __noinline__ void probe3_drain(const MatchParams& p, const Probe3Ctx c, uint32_t cnt,
+                                          uint32_t* __restrict__ results, uint32_t lane) {
+    __syncwarp();  // the parked entries, and the None words written for them, are ordered before this point
+    for (uint32_t b = 0; b < cnt; b += 32u) {
+        const uint32_t e = b + lane;
         const bool act = e < cnt;
         uint32_t kw[W];
         uint32_t idx = 0;
 #pragma unroll
         for (int k = 0; k < W; k++) kw[k] = 0u;
         if (act) {
-            const uint4 q = __ldcg(reinterpret_cast<const uint4*>(stash + e * stride));
-            kw[0] = q.x;
-            if constexpr (W == 2) kw[W - 1] = q.y;
-            idx = q.z;
+            uint32_t k2[2];
+            lds_key<2>(c.a_skey + e * 8u, k2);
+            kw[0] = k2[0];
+            if constexpr (W == 2) kw[W - 1] = k2[1];
+            idx = lds32(c.a_skey + p.ck_stash_cap * 8u + e * 4u);
         }
         const uint32_t out = slow_resolve<W>(p, kw, act, lane);
-        if (act && out != NONE) {  // it was written and counted as unmatched when it was parked
-            results[idx] = out;
-            hist_inc(c, out >> 16);
-            hist_add(c, p.S, 0xFFFFFFFFu);
+        if (act) {
+            if (out != NONE) results[idx] = out;  // it was written as None when it was parked
+            hist_inc(p, c, out == NONE ? p.S : (out >> 16));
+        }
+    }
+    __syncwarp();  // the stash is free again
+}
+
+// Cold path: a tile brought more non-ACGT reads than the stash holds.  Called after the tile's result words are
+// stored: re-reads the lane's four reads, then parks and resolves the tile's four slots one after the other, at most
+// ck_stash_cap lanes at a time.
+template <int W>
+__device__ __noinline__ void probe3_park_bulk(const MatchParams& p, const Probe3Ctx c,
+                                              const uint32_t* __restrict__ packed, uint32_t bad, uint32_t g,
+                                              uint32_t* __restrict__ results, uint32_t lane) {
+#pragma unroll 1
+    for (uint32_t r = 0; r < (uint32_t)PROBE3_R; r++) {
+        uint32_t k2[2];
+        k2[0] = __ldg(packed + ((size_t)g * PROBE3_R + r) * W);
+        k2[1] = __ldg(packed + ((size_t)g * PROBE3_R + r) * W + (W - 1));
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, (bad >> r) & 1u);
+        while (todo) {
+            uint32_t take = 0, left = todo;
+            for (uint32_t n = 0; n < p.ck_stash_cap && left; n++) {
+                take |= left & (0u - left);
+                left &= left - 1u;
+            }
+            if ((take >> lane) & 1u) {
+                const uint32_t pos = (uint32_t)__popc(take & ((1u << lane) - 1u));
+                sts_key<2>(c.a_skey + pos * 8u, k2);
+                sts32(c.a_skey + p.ck_stash_cap * 8u + pos * 4u, g * 4u + r);
+            }
+            probe3_drain<W>(p, c, (uint32_t)__popc(take), results, lane);
+            todo = left;
         }
     }
 }
@@ -857,48 +889,75 @@ FQ_D void probe3_load(const uint32_t* __restrict__ packed, uint32_t tile, uint32
     }
 }
 
-template <int W, int NP, bool PAD>
-FQ_D void probe3_tile(const MatchParams& p, const Probe3Ctx& c, const uint32_t (&w)[PROBE3_R][W],
-                      uint32_t* __restrict__ results, uint32_t tile, uint32_t lane, Stash& st) {
-    uint32_t res[PROBE3_R], bin[PROBE3_R];
-    bool valid[PROBE3_R];
+// Phase 1 of a tile: keys + validity of the lane's four reads; the reads that are not pure A/C/G/T are parked in the
+// warp's stash (ballot + popc compaction).  After this the raw words are dead and their registers take the next tile.
+// Returns true (warp-uniform) when the tile has more such reads than the stash holds: the caller then runs
+// probe3_park_bulk once the tile's result words are stored.
+template <int W, bool PAD>
+FQ_D bool probe3_keys(const MatchParams& p, const Probe3Ctx& c, const uint32_t (&w)[PROBE3_R][W], uint32_t (&k)[PROBE3_R],
+                      bool (&valid)[PROBE3_R], uint32_t* __restrict__ results, uint32_t g, uint32_t lane, uint32_t& cnt) {
 #pragma unroll
-    for (int r = 0; r < PROBE3_R; r++) res[r] = ck_lookup<W, NP, PAD>(p, c, w[r], valid[r], bin[r]);
-    const uint32_t g = tile * 32u + lane;  // this lane's group of four consecutive reads
-    reinterpret_cast<uint4*>(results)[g] = make_uint4(res[0], res[1], res[2], res[3]);
+    for (int r = 0; r < PROBE3_R; r++) k[r] = ck_key<W, PAD>(p, w[r], valid[r]);
+    if (!__any_sync(0xFFFFFFFFu, !(valid[0] && valid[1] && valid[2] && valid[3]))) return false;
+    uint32_t bal[PROBE3_R], n_new = 0;
 #pragma unroll
-    for (int r = 0; r < PROBE3_R; r++) hist_inc(c, bin[r]);
-    if (__any_sync(0xFFFFFFFFu, !(valid[0] && valid[1] && valid[2] && valid[3]))) {
-        const uint32_t stride = p.ck_stash_threads * 16u;
-#pragma unroll
-        for (int r = 0; r < PROBE3_R; r++) {
-            if (!valid[r]) {
-                *reinterpret_cast<uint2*>(st.next) = make_uint2(w[r][0], w[r][W - 1]);
-                *reinterpret_cast<uint32_t*>(st.next + 8) = imad(g, c.four, (uint32_t)r);
-                st.next += stride;
-                st.cnt++;
-            }
-        }
+    for (int r = 0; r < PROBE3_R; r++) {
+        bal[r] = __ballot_sync(0xFFFFFFFFu, !valid[r]);
+        n_new += (uint32_t)__popc(bal[r]);
     }
+    if (n_new > p.ck_stash_cap) return true;  // bad reads in bulk (rare)
+    if (cnt + n_new > p.ck_stash_cap) {       // no room: resolve what is parked (earlier tiles) first
+        probe3_drain<W>(p, c, cnt, results, lane);
+        cnt = 0u;
+    }
+    const uint32_t lane_lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < PROBE3_R; r++) {
+        if (!valid[r]) {
+            const uint32_t pos = cnt + (uint32_t)__popc(bal[r] & lane_lt);
+            uint32_t k2[2] = {w[r][0], w[r][W - 1]};
+            sts_key<2>(c.a_skey + pos * 8u, k2);
+            sts32(c.a_skey + p.ck_stash_cap * 8u + pos * 4u, g * 4u + (uint32_t)r);
+        }
+        cnt += (uint32_t)__popc(bal[r]);
+    }
+    return false;
 }
 
-template <int W, int NP, bool PAD>
-__global__ void __launch_bounds__(PROBE3_THREADS, 1) k_probe3(const MatchParams p, const ReadSource src,
-                                                           uint32_t* __restrict__ results) {
+// all threads of the CTA: add the packed counters to the global table and zero them
+FQ_D void probe3_flush_hist(const MatchParams& p, uint32_t* s_hist) {
+    __syncthreads();
+    const uint32_t n_words = (p.S + 3u) / 2u;  // bins 0 .. S + 1
+    for (uint32_t wd = threadIdx.x; wd < n_words; wd += blockDim.x) {
+        uint32_t lo = 0, hi = 0;
+        for (uint32_t r = 0; r < 32u; r++) {
+            const uint32_t col = (r + wd) & 31u;  // rotate the start column: no bank conflicts across the warp
+            const uint32_t v = s_hist[wd * 32u + col];
+            s_hist[wd * 32u + col] = 0u;
+            lo += v & 0xFFFFu;
+            hi += v >> 16;
+        }
+        if (lo && 2u * wd <= p.S) atomicAdd(&p.counts[2u * wd], (unsigned long long)lo);
+        if (hi && 2u * wd + 1u <= p.S) atomicAdd(&p.counts[2u * wd + 1u], (unsigned long long)hi);
+    }
+    __syncthreads();
+}
+
+template <int W, int NP, bool PAD, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ MatchParams p, const ReadSource src,
+                                                       uint32_t* __restrict__ results) {
     extern __shared__ uint4 s_dyn[];
-    // layout: cuckoo entries | decode LUT replicas | histogram replicas
+    // layout: cuckoo entries | packed histogram (32 lane columns) | per-warp stashes
     uint32_t* s_ck = reinterpret_cast<uint32_t*>(s_dyn);
-    uint32_t* s_lut = s_ck + p.ck_words;
-    const uint32_t lrep = p.ck_lut_rep, n_lut = p.ck_lowmask + 1u;
-    uint32_t* s_hist = s_lut + n_lut * lrep;
-    const uint32_t hrep = p.ck_hist_rep;
+    uint32_t* s_hist = s_ck + p.ck_words;
+    const uint32_t n_hist_words = ((p.S + 3u) / 2u) * 32u;
+    uint32_t* s_stash = s_hist + n_hist_words;
     {
         const uint4* g4 = reinterpret_cast<const uint4*>(p.ck_entries);  // ck_words is a multiple of 4
         uint4* s4 = reinterpret_cast<uint4*>(s_ck);
         for (uint32_t t = threadIdx.x; t < p.ck_words / 4u; t += blockDim.x) s4[t] = __ldg(g4 + t);
     }
-    for (uint32_t t = threadIdx.x; t < n_lut * lrep; t += blockDim.x) s_lut[t] = __ldg(p.ck_entries + p.ck_words + t / lrep);
-    for (uint32_t t = threadIdx.x; t < (p.S + 1u) * hrep; t += blockDim.x) s_hist[t] = 0u;
+    for (uint32_t t = threadIdx.x; t < n_hist_words; t += blockDim.x) s_hist[t] = 0u;
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31u;
@@ -906,41 +965,48 @@ __global__ void __launch_bounds__(PROBE3_THREADS, 1) k_probe3(const MatchParams 
     Probe3Ctx c;
 #pragma unroll
     for (int i = 0; i < 3; i++) c.base[i] = smem_addr(s_ck) + p.ck_off[i < NP ? i : 0] * 4u;
-    c.a_lut = smem_addr(s_lut) + (lane & (lrep - 1u)) * 4u;
-    c.a_hist = smem_addr(s_hist) + (lane & (hrep - 1u)) * 4u;
-    c.lut_stride = lrep * 4u;
-    c.hstride = hrep * 4u;
-    c.one = p.ck_one;
-    c.four = p.ck_four;
-    asm volatile("" : "+r"(c.base[0]), "+r"(c.base[1]), "+r"(c.base[2]), "+r"(c.a_lut), "+r"(c.a_hist));
-
-    uint8_t* const stash = reinterpret_cast<uint8_t*>(p.ck_stash + ((size_t)blockIdx.x * blockDim.x + threadIdx.x));
-    Stash st{stash, 0u};
+    c.a_hist = smem_addr(s_hist) + lane * 4u;
+    c.a_skey = smem_addr(s_stash) + warp_in_cta * (p.ck_stash_cap * 12u);
+    asm volatile("" : "+r"(c.base[0]), "+r"(c.base[1]), "+r"(c.base[2]), "+r"(c.a_hist));
+    uint32_t cnt = 0;  // reads parked in the warp's stash (warp-uniform)
 
     const uint32_t n_tiles = (uint32_t)(src.n / (uint64_t)PROBE3_TILE);
     const uint32_t stride = gridDim.x * n_warps;
     uint32_t tile = blockIdx.x * n_warps + warp_in_cta;
+    // every warp of the CTA runs the same number of rounds (one tile each) so that the flush barrier is legal
+    const uint32_t first = blockIdx.x * n_warps;
+    const uint32_t rounds = first < n_tiles ? (n_tiles - first + stride - 1u) / stride : 0u;  // of the CTA's first warp
 
-    // two register buffers, alternating: the next tile's keys are in flight while this one is resolved
-    uint32_t wa[PROBE3_R][W], wb[PROBE3_R][W];
-    if (tile < n_tiles) probe3_load<W>(src.packed, tile, lane, wa);
-    while (tile < n_tiles) {
-        uint32_t nt = tile + stride;
-        if (nt < n_tiles) probe3_load<W>(src.packed, nt, lane, wb);
-        probe3_tile<W, NP, PAD>(p, c, wa, results, tile, lane, st);
-        tile = nt;
+    // one register buffer: a tile's raw words are dead once its keys exist (and its odd reads are parked), so the next
+    // tile's loads are issued right there and fly while this tile is probed, decoded, stored and counted
+    uint32_t w[PROBE3_R][W];
+    if (tile < n_tiles) probe3_load<W>(src.packed, tile, lane, w);
+    for (uint32_t round = 0; round < rounds; round++) {
         if (tile < n_tiles) {
-            nt = tile + stride;
-            if (nt < n_tiles) probe3_load<W>(src.packed, nt, lane, wa);
-            probe3_tile<W, NP, PAD>(p, c, wb, results, tile, lane, st);
-            tile = nt;
+            const uint32_t g = tile * 32u + lane;  // this lane's group of four consecutive reads
+            uint32_t k[PROBE3_R];
+            bool valid[PROBE3_R];
+            const bool bulk = probe3_keys<W, PAD>(p, c, w, k, valid, results, g, lane, cnt);
+            tile += stride;
+            if (tile < n_tiles) probe3_load<W>(src.packed, tile, lane, w);
+            uint32_t res[PROBE3_R], bin[PROBE3_R];
+#pragma unroll
+            for (int r = 0; r < PROBE3_R; r++) res[r] = ck_find<NP>(p, c, k[r], valid[r], bin[r]);
+            reinterpret_cast<uint4*>(results)[g] = make_uint4(res[0], res[1], res[2], res[3]);
+#pragma unroll
+            for (int r = 0; r < PROBE3_R; r++) hist_inc(p, c, bin[r]);
+            if (bulk) {
+                const uint32_t bad = (valid[0] ? 0u : 1u) | (valid[1] ? 0u : 2u) | (valid[2] ? 0u : 4u) | (valid[3] ? 0u : 8u);
+                probe3_park_bulk<W>(p, c, src.packed, bad, g, results, lane);
+            }
         }
-        if (__any_sync(0xFFFFFFFFu, st.cnt > PROBE3_STASH_DRAIN)) {
-            probe3_drain<W>(p, c, stash, st.cnt, results, lane);
-            st = Stash{stash, 0u};
+        if ((round + 1u) % PROBE3_FLUSH_ROUNDS == 0u) {
+            probe3_drain<W>(p, c, cnt, results, lane);
+            cnt = 0u;
+            probe3_flush_hist(p, s_hist);
         }
     }
-    probe3_drain<W>(p, c, stash, st.cnt, results, lane);
+    probe3_drain<W>(p, c, cnt, results, lane);
 
     // ---- tail: fewer than 128 reads, one per lane, first warp of the grid ----
     if (blockIdx.x == 0 && threadIdx.x < 32u) {
@@ -952,22 +1018,16 @@ __global__ void __launch_bounds__(PROBE3_THREADS, 1) k_probe3(const MatchParams 
             for (int k = 0; k < W; k++) w1[k] = live ? __ldg(src.packed + i * W + k) : 0u;
             bool valid;
             uint32_t bin;
-            uint32_t out = ck_lookup<W, NP, PAD>(p, c, w1, valid, bin);
+            uint32_t out = ck_find<NP>(p, c, ck_key<W, PAD>(p, w1, valid), valid, bin);
             const uint32_t slow = slow_resolve<W>(p, w1, live && !valid, lane);
             if (live) {
                 if (!valid) out = slow;
                 results[i] = out;
-                hist_inc(c, out == NONE ? p.S : (out >> 16));
+                hist_inc(p, c, out == NONE ? p.S : (out >> 16));
             }
         }
     }
-    // ---- flush the replicated bins (bin S = unmatched) ----
-    __syncthreads();
-    for (uint32_t b = threadIdx.x; b <= p.S; b += blockDim.x) {
-        uint32_t v = 0;
-        for (uint32_t r = 0; r < hrep; r++) v += s_hist[b * hrep + r];
-        if (v) atomicAdd(&p.counts[b], (unsigned long long)v);
-    }
+    probe3_flush_hist(p, s_hist);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1129,26 +1189,49 @@ static cudaError_t launch_probe2_w(const MatchParams& p, const ReadSource& src, 
     return cudaGetLastError();
 }
 
-size_t probe3_smem_bytes(uint32_t ck_words, uint32_t lut_words, uint32_t S, uint32_t hist_rep) {
-    return (size_t)ck_words * 4 + (size_t)lut_words * 4 + (size_t)(S + 1u) * hist_rep * 4;
+// shared memory of k_probe3 without the stashes; the stashes take stash_cap * 12 bytes per warp of the largest CTA
+size_t probe3_fixed_smem_bytes(uint32_t ck_words, uint32_t S) {
+    return (size_t)ck_words * 4 + (size_t)((S + 3u) / 2u) * 32 * 4;
 }
-uint32_t probe3_stash_threads(const LaunchGeometry& g) { return (uint32_t)g.sm_count * PROBE3_THREADS; }
-size_t probe3_stash_bytes(const LaunchGeometry& g) {
-    return (size_t)probe3_stash_threads(g) * PROBE3_STASH_CAP * sizeof(uint4);
+uint32_t probe3_stash_cap(uint32_t ck_words, uint32_t S, size_t smem_max) {  // 0 = does not fit
+    const size_t fixed = probe3_fixed_smem_bytes(ck_words, S);
+    if (fixed > smem_max) return 0;
+    const size_t cap = (smem_max - fixed) / ((size_t)(PROBE3_THREADS / 32) * 12);
+    if (cap < PROBE3_STASH_MIN) return 0;
+    return (uint32_t)std::min<size_t>(cap, PROBE3_STASH_MAX);
+}
+static size_t probe3_smem_bytes(const MatchParams& p) {
+    return probe3_fixed_smem_bytes(p.ck_words, p.S) + (size_t)(PROBE3_THREADS / 32) * p.ck_stash_cap * 12;
+}
+
+static int probe3_threads() {  // FQTK_B200_P3_THREADS=768 trades resident warps for registers (A/B timing)
+    static const int v = [] {
+        const char* e = getenv("FQTK_B200_P3_THREADS");
+        const int t = e ? atoi(e) : 0;
+        return t == 768 ? 768 : PROBE3_THREADS;
+    }();
+    return v;
+}
+
+template <int W, int NP, bool PAD, int THREADS>
+static cudaError_t launch_probe3_wnpt(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
+                                      const LaunchGeometry& g, cudaStream_t stream) {
+    auto k = k_probe3<W, NP, PAD, THREADS>;
+    const size_t smem = probe3_smem_bytes(p);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const uint64_t n_warp_tiles = (src.n + PROBE3_TILE - 1) / PROBE3_TILE;
+    const uint64_t want = (n_warp_tiles + THREADS / 32 - 1) / (THREADS / 32);
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)g.sm_count));
+    k<<<grid, THREADS, smem, stream>>>(p, src, d_results);
+    count_launch();
+    return cudaGetLastError();
 }
 
 template <int W, int NP, bool PAD>
 static cudaError_t launch_probe3_wnp(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
                                      const LaunchGeometry& g, cudaStream_t stream) {
-    auto k = k_probe3<W, NP, PAD>;
-    const size_t smem = probe3_smem_bytes(p.ck_words, (p.ck_lowmask + 1u) * p.ck_lut_rep, p.S, p.ck_hist_rep);
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const uint64_t n_warp_tiles = (src.n + PROBE3_TILE - 1) / PROBE3_TILE;
-    const uint64_t want = (n_warp_tiles + PROBE3_THREADS / 32 - 1) / (PROBE3_THREADS / 32);
-    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)g.sm_count));
-    k<<<grid, PROBE3_THREADS, smem, stream>>>(p, src, d_results);
-    count_launch();
-    return cudaGetLastError();
+    return probe3_threads() == 768 ? launch_probe3_wnpt<W, NP, PAD, 768>(p, src, d_results, g, stream)
+                                   : launch_probe3_wnpt<W, NP, PAD, PROBE3_THREADS>(p, src, d_results, g, stream);
 }
 
 template <int W, int NP>
