@@ -740,8 +740,8 @@ constexpr int PROBE3_R = 4;
 constexpr int PROBE3_TILE = 32 * PROBE3_R;
 constexpr uint32_t PROBE3_STASH_MAX = 48;      // stash entries per warp (8-byte key + 4-byte read index each), at most
 constexpr uint32_t PROBE3_STASH_MIN = 16;      // ... at least (else the geometry is rejected on the host)
-// a packed counter gains at most 32 warps x 4 reads per round (main path) plus as many again from drains
-constexpr uint32_t PROBE3_FLUSH_ROUNDS = 128;  // 128 * 256 = 32768 < 65536
+// a packed counter gains at most 32 warps x 2 tiles x 4 reads per round (main path) plus as many again from drains
+constexpr uint32_t PROBE3_FLUSH_ROUNDS = 64;   // 64 * 512 = 32768 < 65536
 
 struct Probe3Ctx {
     uint32_t base[3];  // shared-window address of sub-table i
@@ -753,10 +753,13 @@ struct Probe3Ctx {
 
 FQ_D uint32_t imad(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
 
-// packed histogram: bin b lives in the (b & 1) half of word b >> 1 of the lane's column
-FQ_D void hist_inc(const MatchParams& p, const Probe3Ctx& c, uint32_t bin) {
-    const uint32_t addr = imad(bin & ~1u, p.ck_four * 16u, c.a_hist);  // (bin >> 1) * 128
-    const uint32_t val = imad(bin & 1u, 65535u, p.ck_one);             // 1 or 65536
+// packed histogram: sample b lives in the (b & 1) half of word b >> 1 of the lane's column.  Only matched reads are
+// counted (the unmatched bin is reads processed - sum of the sample bins); an unmatched read adds 0 to word 0, so the
+// atomic itself is unconditional (a predicated shared-memory atomic costs a branch and a reconvergence barrier).
+FQ_D void hist_inc_if(const MatchParams& p, const Probe3Ctx& c, uint32_t bin, bool on) {
+    const uint32_t b = on ? bin : 0u;
+    const uint32_t addr = imad(b & ~1u, p.ck_four * 16u, c.a_hist);             // (bin >> 1) * 128
+    const uint32_t val = on ? imad(bin & 1u, 65535u, p.ck_one) : 0u;            // 1 or 65536, or nothing
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
 }
 
@@ -776,10 +779,10 @@ FQ_D uint32_t ck_key(const MatchParams& p, const uint32_t (&w)[W], bool& valid) 
     return k;
 }
 
-// One key through the shared-memory table.  Returns the result word (NONE for unmatched AND for reads that are not
-// pure A/C/G/T); `bin` = histogram bin (S: unmatched, S + 1: parked).
+// One key through the shared-memory table: the result word (NONE for unmatched AND for reads that are not pure
+// A/C/G/T) and the matched read's count.
 template <int NP>
-FQ_D uint32_t ck_find(const MatchParams& p, const Probe3Ctx& c, uint32_t k, bool valid, uint32_t& bin) {
+FQ_D uint32_t ck_find(const MatchParams& p, const Probe3Ctx& c, uint32_t k, bool valid) {
     uint32_t u = 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < NP; i++) {
@@ -791,8 +794,9 @@ FQ_D uint32_t ck_find(const MatchParams& p, const Probe3Ctx& c, uint32_t k, bool
     // value code = idx << lb | best << nb | (next - next_min)
     const uint32_t idx = u >> p.ck_lb;
     const uint32_t low = ((u << p.ck_bsh) & p.ck_bmask8) | (u & p.ck_nmask);
-    bin = found ? idx : (valid ? p.S : p.S + 1u);
-    return found ? imad(idx, 65536u, imad(low, p.ck_one, p.ck_next_min)) : NONE;
+    const uint32_t word = imad(idx, 65536u, imad(low, p.ck_one, p.ck_next_min));
+    hist_inc_if(p, c, idx, found);
+    return found ? word : NONE;
 }
 
 // memo-table / warp-cooperative resolution of one read per lane (`act` lanes only); all 32 lanes must call it
@@ -837,9 +841,9 @@ __device__ __noinline__ void probe3_drain(const MatchParams& p, const Probe3Ctx 
             idx = lds32(c.a_skey + p.ck_stash_cap * 8u + e * 4u);
         }
         const uint32_t out = slow_resolve<W>(p, kw, act, lane);
-        if (act) {
-            if (out != NONE) results[idx] = out;  // it was written as None when it was parked
-            hist_inc(p, c, out == NONE ? p.S : (out >> 16));
+        if (act && out != NONE) {
+            results[idx] = out;  // it was written as None when it was parked
+            hist_inc_if(p, c, out >> 16, true);
         }
     }
     __syncwarp();  // the stash is free again
@@ -889,26 +893,33 @@ FQ_D void probe3_load(const uint32_t* __restrict__ packed, uint32_t tile, uint32
     }
 }
 
-// Phase 1 of a tile: keys + validity of the lane's four reads; the reads that are not pure A/C/G/T are parked in the
-// warp's stash (ballot + popc compaction).  After this the raw words are dead and their registers take the next tile.
-// Returns true (warp-uniform) when the tile has more such reads than the stash holds: the caller then runs
-// probe3_park_bulk once the tile's result words are stored.
-template <int W, bool PAD>
-FQ_D bool probe3_keys(const MatchParams& p, const Probe3Ctx& c, const uint32_t (&w)[PROBE3_R][W], uint32_t (&k)[PROBE3_R],
-                      bool (&valid)[PROBE3_R], uint32_t* __restrict__ results, uint32_t g, uint32_t lane, uint32_t& cnt) {
+// One tile: keys + validity, probes, result words, counts; the reads that are not pure A/C/G/T are parked in the
+// warp's stash (ballot + popc compaction) or, when a tile brings more of them than the stash holds, resolved at once.
+template <int W, int NP, bool PAD>
+FQ_D void probe3_tile(const MatchParams& p, const Probe3Ctx& c, const uint32_t (&w)[PROBE3_R][W],
+                      const uint32_t* __restrict__ packed, uint32_t* __restrict__ results, uint32_t tile, uint32_t lane,
+                      uint32_t& cnt) {
+    uint32_t res[PROBE3_R];
+    bool valid[PROBE3_R];
 #pragma unroll
-    for (int r = 0; r < PROBE3_R; r++) k[r] = ck_key<W, PAD>(p, w[r], valid[r]);
-    if (!__any_sync(0xFFFFFFFFu, !(valid[0] && valid[1] && valid[2] && valid[3]))) return false;
+    for (int r = 0; r < PROBE3_R; r++) res[r] = ck_find<NP>(p, c, ck_key<W, PAD>(p, w[r], valid[r]), valid[r]);
+    const uint32_t g = tile * 32u + lane;  // this lane's group of four consecutive reads
+    reinterpret_cast<uint4*>(results)[g] = make_uint4(res[0], res[1], res[2], res[3]);
+    if (!__any_sync(0xFFFFFFFFu, !(valid[0] && valid[1] && valid[2] && valid[3]))) return;
     uint32_t bal[PROBE3_R], n_new = 0;
 #pragma unroll
     for (int r = 0; r < PROBE3_R; r++) {
         bal[r] = __ballot_sync(0xFFFFFFFFu, !valid[r]);
         n_new += (uint32_t)__popc(bal[r]);
     }
-    if (n_new > p.ck_stash_cap) return true;  // bad reads in bulk (rare)
-    if (cnt + n_new > p.ck_stash_cap) {       // no room: resolve what is parked (earlier tiles) first
+    if (cnt + n_new > p.ck_stash_cap) {  // no room: resolve what is parked first
         probe3_drain<W>(p, c, cnt, results, lane);
         cnt = 0u;
+    }
+    if (n_new > p.ck_stash_cap) {  // bad reads in bulk (rare)
+        const uint32_t bad = (valid[0] ? 0u : 1u) | (valid[1] ? 0u : 2u) | (valid[2] ? 0u : 4u) | (valid[3] ? 0u : 8u);
+        probe3_park_bulk<W>(p, c, packed, bad, g, results, lane);
+        return;
     }
     const uint32_t lane_lt = (1u << lane) - 1u;
 #pragma unroll
@@ -921,13 +932,14 @@ FQ_D bool probe3_keys(const MatchParams& p, const Probe3Ctx& c, const uint32_t (
         }
         cnt += (uint32_t)__popc(bal[r]);
     }
-    return false;
 }
 
-// all threads of the CTA: add the packed counters to the global table and zero them
-FQ_D void probe3_flush_hist(const MatchParams& p, uint32_t* s_hist) {
+// all threads of the CTA: add the packed sample counters to the global table, zero them, and add their sum to
+// *s_matched (the unmatched count falls out at the end as reads processed - matched)
+FQ_D void probe3_flush_hist(const MatchParams& p, uint32_t* s_hist, unsigned long long* s_matched) {
     __syncthreads();
-    const uint32_t n_words = (p.S + 3u) / 2u;  // bins 0 .. S + 1
+    const uint32_t n_words = (p.S + 1u) / 2u;
+    unsigned long long mine = 0ull;
     for (uint32_t wd = threadIdx.x; wd < n_words; wd += blockDim.x) {
         uint32_t lo = 0, hi = 0;
         for (uint32_t r = 0; r < 32u; r++) {
@@ -937,9 +949,11 @@ FQ_D void probe3_flush_hist(const MatchParams& p, uint32_t* s_hist) {
             lo += v & 0xFFFFu;
             hi += v >> 16;
         }
-        if (lo && 2u * wd <= p.S) atomicAdd(&p.counts[2u * wd], (unsigned long long)lo);
-        if (hi && 2u * wd + 1u <= p.S) atomicAdd(&p.counts[2u * wd + 1u], (unsigned long long)hi);
+        if (lo) atomicAdd(&p.counts[2u * wd], (unsigned long long)lo);
+        if (hi) atomicAdd(&p.counts[2u * wd + 1u], (unsigned long long)hi);  // 2 wd + 1 < S whenever hi != 0
+        mine += lo + hi;
     }
+    if (mine) atomicAdd(s_matched, mine);
     __syncthreads();
 }
 
@@ -947,10 +961,11 @@ template <int W, int NP, bool PAD, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ MatchParams p, const ReadSource src,
                                                        uint32_t* __restrict__ results) {
     extern __shared__ uint4 s_dyn[];
+    __shared__ unsigned long long s_matched;  // reads of this CTA that landed in a sample bin
     // layout: cuckoo entries | packed histogram (32 lane columns) | per-warp stashes
     uint32_t* s_ck = reinterpret_cast<uint32_t*>(s_dyn);
     uint32_t* s_hist = s_ck + p.ck_words;
-    const uint32_t n_hist_words = ((p.S + 3u) / 2u) * 32u;
+    const uint32_t n_hist_words = ((p.S + 1u) / 2u) * 32u;
     uint32_t* s_stash = s_hist + n_hist_words;
     {
         const uint4* g4 = reinterpret_cast<const uint4*>(p.ck_entries);  // ck_words is a multiple of 4
@@ -958,6 +973,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ M
         for (uint32_t t = threadIdx.x; t < p.ck_words / 4u; t += blockDim.x) s4[t] = __ldg(g4 + t);
     }
     for (uint32_t t = threadIdx.x; t < n_hist_words; t += blockDim.x) s_hist[t] = 0u;
+    if (threadIdx.x == 0) s_matched = 0ull;
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31u;
@@ -968,45 +984,43 @@ __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ M
     c.a_hist = smem_addr(s_hist) + lane * 4u;
     c.a_skey = smem_addr(s_stash) + warp_in_cta * (p.ck_stash_cap * 12u);
     asm volatile("" : "+r"(c.base[0]), "+r"(c.base[1]), "+r"(c.base[2]), "+r"(c.a_hist));
-    uint32_t cnt = 0;  // reads parked in the warp's stash (warp-uniform)
+    uint32_t cnt = 0;   // reads parked in the warp's stash (warp-uniform)
+    uint32_t done = 0;  // tiles this warp has processed
 
     const uint32_t n_tiles = (uint32_t)(src.n / (uint64_t)PROBE3_TILE);
     const uint32_t stride = gridDim.x * n_warps;
     uint32_t tile = blockIdx.x * n_warps + warp_in_cta;
-    // every warp of the CTA runs the same number of rounds (one tile each) so that the flush barrier is legal
+    // every warp of the CTA runs the same number of rounds (two tiles each) so that the flush barrier is legal
     const uint32_t first = blockIdx.x * n_warps;
-    const uint32_t rounds = first < n_tiles ? (n_tiles - first + stride - 1u) / stride : 0u;  // of the CTA's first warp
+    const uint32_t cta_tiles = first < n_tiles ? (n_tiles - first + stride - 1u) / stride : 0u;  // of the CTA's first warp
+    const uint32_t rounds = (cta_tiles + 1u) / 2u;
 
-    // one register buffer: a tile's raw words are dead once its keys exist (and its odd reads are parked), so the next
-    // tile's loads are issued right there and fly while this tile is probed, decoded, stored and counted
-    uint32_t w[PROBE3_R][W];
-    if (tile < n_tiles) probe3_load<W>(src.packed, tile, lane, w);
+    // two register buffers, alternating: the next tile's keys are in flight while this one is resolved
+    uint32_t wa[PROBE3_R][W], wb[PROBE3_R][W];
+    if (tile < n_tiles) probe3_load<W>(src.packed, tile, lane, wa);
     for (uint32_t round = 0; round < rounds; round++) {
         if (tile < n_tiles) {
-            const uint32_t g = tile * 32u + lane;  // this lane's group of four consecutive reads
-            uint32_t k[PROBE3_R];
-            bool valid[PROBE3_R];
-            const bool bulk = probe3_keys<W, PAD>(p, c, w, k, valid, results, g, lane, cnt);
-            tile += stride;
-            if (tile < n_tiles) probe3_load<W>(src.packed, tile, lane, w);
-            uint32_t res[PROBE3_R], bin[PROBE3_R];
-#pragma unroll
-            for (int r = 0; r < PROBE3_R; r++) res[r] = ck_find<NP>(p, c, k[r], valid[r], bin[r]);
-            reinterpret_cast<uint4*>(results)[g] = make_uint4(res[0], res[1], res[2], res[3]);
-#pragma unroll
-            for (int r = 0; r < PROBE3_R; r++) hist_inc(p, c, bin[r]);
-            if (bulk) {
-                const uint32_t bad = (valid[0] ? 0u : 1u) | (valid[1] ? 0u : 2u) | (valid[2] ? 0u : 4u) | (valid[3] ? 0u : 8u);
-                probe3_park_bulk<W>(p, c, src.packed, bad, g, results, lane);
+            uint32_t nt = tile + stride;
+            if (nt < n_tiles) probe3_load<W>(src.packed, nt, lane, wb);
+            probe3_tile<W, NP, PAD>(p, c, wa, src.packed, results, tile, lane, cnt);
+            done++;
+            tile = nt;
+            if (tile < n_tiles) {
+                nt = tile + stride;
+                if (nt < n_tiles) probe3_load<W>(src.packed, nt, lane, wa);
+                probe3_tile<W, NP, PAD>(p, c, wb, src.packed, results, tile, lane, cnt);
+                done++;
+                tile = nt;
             }
         }
         if ((round + 1u) % PROBE3_FLUSH_ROUNDS == 0u) {
             probe3_drain<W>(p, c, cnt, results, lane);
             cnt = 0u;
-            probe3_flush_hist(p, s_hist);
+            probe3_flush_hist(p, s_hist, &s_matched);
         }
     }
     probe3_drain<W>(p, c, cnt, results, lane);
+    unsigned long long processed = (lane == 0u) ? (unsigned long long)done * PROBE3_TILE : 0ull;
 
     // ---- tail: fewer than 128 reads, one per lane, first warp of the grid ----
     if (blockIdx.x == 0 && threadIdx.x < 32u) {
@@ -1017,17 +1031,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ M
 #pragma unroll
             for (int k = 0; k < W; k++) w1[k] = live ? __ldg(src.packed + i * W + k) : 0u;
             bool valid;
-            uint32_t bin;
-            uint32_t out = ck_find<NP>(p, c, ck_key<W, PAD>(p, w1, valid), valid, bin);
+            const uint32_t key = ck_key<W, PAD>(p, w1, valid);
+            uint32_t out = ck_find<NP>(p, c, key, valid && live);
             const uint32_t slow = slow_resolve<W>(p, w1, live && !valid, lane);
             if (live) {
-                if (!valid) out = slow;
+                if (!valid) {
+                    out = slow;
+                    hist_inc_if(p, c, out >> 16, out != NONE);
+                }
                 results[i] = out;
-                hist_inc(p, c, out == NONE ? p.S : (out >> 16));
+                processed += 1ull;
             }
         }
     }
-    probe3_flush_hist(p, s_hist);
+    probe3_flush_hist(p, s_hist, &s_matched);
+    // unmatched = processed - matched (s_matched is complete after the flush's closing barrier)
+    if (processed) atomicAdd(&p.counts[p.S], processed);
+    if (threadIdx.x == 0 && s_matched) atomicAdd(&p.counts[p.S], 0ull - s_matched);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1191,7 +1211,7 @@ static cudaError_t launch_probe2_w(const MatchParams& p, const ReadSource& src, 
 
 // shared memory of k_probe3 without the stashes; the stashes take stash_cap * 12 bytes per warp of the largest CTA
 size_t probe3_fixed_smem_bytes(uint32_t ck_words, uint32_t S) {
-    return (size_t)ck_words * 4 + (size_t)((S + 3u) / 2u) * 32 * 4;
+    return (size_t)ck_words * 4 + (size_t)((S + 1u) / 2u) * 32 * 4;
 }
 uint32_t probe3_stash_cap(uint32_t ck_words, uint32_t S, size_t smem_max) {  // 0 = does not fit
     const size_t fixed = probe3_fixed_smem_bytes(ck_words, S);
