@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -723,45 +724,26 @@ __global__ void __launch_bounds__(PROBE2_THREADS, 1) k_probe2(const MatchParams 
 //     a value code, so one LDS.32 and one multiply-add (entry - remainder) both verify the key exactly and deliver
 //     the code; the NP candidates are merged with a min (at most one can match; an empty slot yields a code >= limit);
 //   * a valid read that is not in the table is farther than max_mismatches from every barcode -> None;
-//   * reads with any other symbol (no-calls, IUPAC, junk; ~3 % of real reads) are written as None, parked in a small
-//     per-warp stash in shared memory and resolved a warp-full at a time through the global memo table (which also
-//     holds the N-containing neighbours) or the warp-cooperative scan; the result word is then overwritten.
-// Per-sample counts: a lane-private (bank = lane, conflict-free) shared-memory histogram of PACKED 16-bit counters
-// (two bins per word: bin b adds 1 << 16 * (b & 1) to word b >> 1); all warps run the same number of loop rounds and
-// every PROBE3_FLUSH_ROUNDS rounds the CTA flushes the counters to the global u64 table under a barrier, long before
-// any 16-bit field can overflow.  Bin S = unmatched, bin S + 1 = parked (counted when it is resolved).
-// The kernel is bound by the SM's integer and shared-memory pipes, so adds and address computations on the hot path
-// are written as multiply-adds with an operand read from the kernel parameters (IMAD on the fma pipe) and only the
+//   * reads with any other symbol (no-calls, IUPAC, junk; ~3 % of real reads) are written as None and counted as
+//     unmatched, parked in a small per-warp stash in shared memory (one ballot per pass: each lane parks its first
+//     such read) and resolved a warp-full at a time through the global memo table (which also holds the N-containing
+//     neighbours) or, outside its alphabet, the warp-cooperative scan; the result word and the counts are patched.
+// Per-sample counts: lane-replicated shared-memory histogram (bin S = unmatched), one unconditional atomic per read.
+// The kernel is bound by instruction issue and the SM's integer pipes, so adds and address computations on the hot
+// path are written as multiply-adds with an operand read from the kernel parameters (IMAD, fma pipe) and only the
 // logic ops, shifts, compares and selects stay on the alu pipe (both issue one warp instruction per 2 clocks).
-// A warp owns tiles of 128 consecutive reads, four per lane (W x LDG.128 in, one STG.128 out), double-buffered.
+// A warp owns tiles of 32 * R consecutive reads, R per lane (R * W / 4 x LDG.128 in, R / 4 x STG.128 out), with the
+// next tile's words in flight in a second register buffer while this one is resolved.
 // ------------------------------------------------------------------------------------------------------
-constexpr int PROBE3_THREADS = 1024;
-constexpr int PROBE3_R = 4;
-constexpr int PROBE3_TILE = 32 * PROBE3_R;
-constexpr uint32_t PROBE3_STASH_MAX = 48;      // stash entries per warp (8-byte key + 4-byte read index each), at most
-constexpr uint32_t PROBE3_STASH_MIN = 16;      // ... at least (else the geometry is rejected on the host)
-// a packed counter gains at most 32 warps x 2 tiles x 4 reads per round (main path) plus as many again from drains
-constexpr uint32_t PROBE3_FLUSH_ROUNDS = 64;   // 64 * 512 = 32768 < 65536
-
 struct Probe3Ctx {
     uint32_t base[3];  // shared-window address of sub-table i
-    uint32_t a_skey;   // ... of this warp's stash: ck_stash_cap keys (8 bytes each), then the read indices
-    uint32_t a_hist;   // ... of this lane's histogram column (word w of the column at a_hist + 128 * w)
+    uint32_t a_hist;   // ... of this lane's histogram replica
+    uint32_t a_stash;  // ... of this warp's stash: ck_stash_cap keys (8 bytes each), then as many read indices
 };
 // p.ck_one (= 1) and p.ck_four (= 4) come from the kernel parameters so that ptxas cannot fold x * one + c back into
 // an alu-pipe add / LEA: those adds and scalings stay multiply-adds on the fma pipe.
 
 FQ_D uint32_t imad(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
-
-// packed histogram: sample b lives in the (b & 1) half of word b >> 1 of the lane's column.  Only matched reads are
-// counted (the unmatched bin is reads processed - sum of the sample bins); an unmatched read adds 0 to word 0, so the
-// atomic itself is unconditional (a predicated shared-memory atomic costs a branch and a reconvergence barrier).
-FQ_D void hist_inc_if(const MatchParams& p, const Probe3Ctx& c, uint32_t bin, bool on) {
-    const uint32_t b = on ? bin : 0u;
-    const uint32_t addr = imad(b & ~1u, p.ck_four * 16u, c.a_hist);             // (bin >> 1) * 128
-    const uint32_t val = on ? imad(bin & 1u, 65535u, p.ck_one) : 0u;            // 1 or 65536, or nothing
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
-}
 
 // Compressed key + validity of one read: acgt_key (common.cuh), with the subtractions and the left shift on the fma pipe.
 template <int W, bool PAD>
@@ -780,9 +762,9 @@ FQ_D uint32_t ck_key(const MatchParams& p, const uint32_t (&w)[W], bool& valid) 
 }
 
 // One key through the shared-memory table: the result word (NONE for unmatched AND for reads that are not pure
-// A/C/G/T) and the matched read's count.
+// A/C/G/T) and the histogram bin (S when NONE).
 template <int NP>
-FQ_D uint32_t ck_find(const MatchParams& p, const Probe3Ctx& c, uint32_t k, bool valid) {
+FQ_D uint32_t ck_find(const MatchParams& p, const Probe3Ctx& c, uint32_t k, bool valid, uint32_t& bin) {
     uint32_t u = 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < NP; i++) {
@@ -795,7 +777,7 @@ FQ_D uint32_t ck_find(const MatchParams& p, const Probe3Ctx& c, uint32_t k, bool
     const uint32_t idx = u >> p.ck_lb;
     const uint32_t low = ((u << p.ck_bsh) & p.ck_bmask8) | (u & p.ck_nmask);
     const uint32_t word = imad(idx, 65536u, imad(low, p.ck_one, p.ck_next_min));
-    hist_inc_if(p, c, idx, found);
+    bin = found ? idx : p.S;
     return found ? word : NONE;
 }
 
@@ -821,7 +803,30 @@ FQ_D uint32_t slow_resolve(const MatchParams& p, const uint32_t (&kw)[W], bool a
     return out;
 }
 
-// Resolve every stashed read of the warp (`cnt` is warp-uniform): patch the result words, count the reads.
+// hist[bin * hrep + lane % hrep] += v
+FQ_D void hist_add(const MatchParams& p, const Probe3Ctx& c, uint32_t bin, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(imad(bin, p.ck_hist_rep * 4u, c.a_hist)), "r"(v) : "memory");
+}
+
+constexpr uint32_t PROBE3_INLINE_LANES = 16;  // this many lanes with an odd read in one pass: not worth parking
+constexpr uint32_t PROBE3_STASH_MIN = 16, PROBE3_STASH_MAX = 64;  // stash entries per warp (>= PROBE3_INLINE_LANES)
+
+// Resolve one read per `act` lane now: patch its result word and the counts (it was written as None / unmatched).
+template <int W>
+__device__ __noinline__ void probe3_resolve_now(const MatchParams& p, const Probe3Ctx c, const uint32_t (&k2)[2], bool act,
+                                                uint32_t idx, uint32_t* __restrict__ results, uint32_t lane) {
+    uint32_t kw[W];
+    kw[0] = k2[0];
+    if constexpr (W == 2) kw[W - 1] = k2[1];
+    const uint32_t out = slow_resolve<W>(p, kw, act, lane);
+    if (act && out != NONE) {
+        results[idx] = out;
+        hist_add(p, c, out >> 16, 1u);
+        hist_add(p, c, p.S, 0xFFFFFFFFu);
+    }
+}
+
+// Resolve the first `cnt` stashed reads of the warp (`cnt` is warp-uniform): patch result words and counts.
 template <int W>
 __device__ __noinline__ void probe3_drain(const MatchParams& p, const Probe3Ctx c, uint32_t cnt,
                                           uint32_t* __restrict__ results, uint32_t lane) {
@@ -835,145 +840,105 @@ __device__ __noinline__ void probe3_drain(const MatchParams& p, const Probe3Ctx 
         for (int k = 0; k < W; k++) kw[k] = 0u;
         if (act) {
             uint32_t k2[2];
-            lds_key<2>(c.a_skey + e * 8u, k2);
+            lds_key<2>(c.a_stash + e * 8u, k2);
             kw[0] = k2[0];
             if constexpr (W == 2) kw[W - 1] = k2[1];
-            idx = lds32(c.a_skey + p.ck_stash_cap * 8u + e * 4u);
+            idx = lds32(c.a_stash + p.ck_stash_cap * 8u + e * 4u);
         }
         const uint32_t out = slow_resolve<W>(p, kw, act, lane);
-        if (act && out != NONE) {
-            results[idx] = out;  // it was written as None when it was parked
-            hist_inc_if(p, c, out >> 16, true);
+        if (act && out != NONE) {  // it was written as None and counted as unmatched when it was parked
+            results[idx] = out;
+            hist_add(p, c, out >> 16, 1u);
+            hist_add(p, c, p.S, 0xFFFFFFFFu);
         }
     }
     __syncwarp();  // the stash is free again
 }
 
-// Cold path: a tile brought more non-ACGT reads than the stash holds.  Called after the tile's result words are
-// stored: re-reads the lane's four reads, then parks and resolves the tile's four slots one after the other, at most
-// ck_stash_cap lanes at a time.
-template <int W>
-__device__ __noinline__ void probe3_park_bulk(const MatchParams& p, const Probe3Ctx c,
-                                              const uint32_t* __restrict__ packed, uint32_t bad, uint32_t g,
-                                              uint32_t* __restrict__ results, uint32_t lane) {
-#pragma unroll 1
-    for (uint32_t r = 0; r < (uint32_t)PROBE3_R; r++) {
-        uint32_t k2[2];
-        k2[0] = __ldg(packed + ((size_t)g * PROBE3_R + r) * W);
-        k2[1] = __ldg(packed + ((size_t)g * PROBE3_R + r) * W + (W - 1));
-        uint32_t todo = __ballot_sync(0xFFFFFFFFu, (bad >> r) & 1u);
-        while (todo) {
-            uint32_t take = 0, left = todo;
-            for (uint32_t n = 0; n < p.ck_stash_cap && left; n++) {
-                take |= left & (0u - left);
-                left &= left - 1u;
-            }
-            if ((take >> lane) & 1u) {
-                const uint32_t pos = (uint32_t)__popc(take & ((1u << lane) - 1u));
-                sts_key<2>(c.a_skey + pos * 8u, k2);
-                sts32(c.a_skey + p.ck_stash_cap * 8u + pos * 4u, g * 4u + r);
-            }
-            probe3_drain<W>(p, c, (uint32_t)__popc(take), results, lane);
-            todo = left;
-        }
+template <int W, int R>
+FQ_D void probe3_load(const uint32_t* __restrict__ packed, uint32_t tile, uint32_t lane, uint32_t (&w)[R][W]) {
+    static_assert((W == 1 || W == 2) && (R == 4 || R == 8), "k_probe3 covers L <= 16, 4 or 8 reads per lane");
+    constexpr int NV = R * W / 4;  // 16-byte vectors per lane
+    const uint4* in = reinterpret_cast<const uint4*>(packed) + (size_t)(tile * 32u + lane) * NV;
+    uint32_t flat[R * W];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        const uint4 q = __ldg(in + v);
+        flat[4 * v + 0] = q.x; flat[4 * v + 1] = q.y; flat[4 * v + 2] = q.z; flat[4 * v + 3] = q.w;
     }
+#pragma unroll
+    for (int r = 0; r < R; r++)
+#pragma unroll
+        for (int k = 0; k < W; k++) w[r][k] = flat[r * W + k];
 }
 
-template <int W>
-FQ_D void probe3_load(const uint32_t* __restrict__ packed, uint32_t tile, uint32_t lane, uint32_t (&w)[PROBE3_R][W]) {
-    static_assert(W == 1 || W == 2, "k_probe3 covers L <= 16");
-    const uint4* in = reinterpret_cast<const uint4*>(packed) + (size_t)(tile * 32u + lane) * W;
-    if constexpr (W == 1) {
-        const uint4 q = __ldg(in);
-        w[0][0] = q.x; w[1][0] = q.y; w[2][0] = q.z; w[3][0] = q.w;
-    } else {
-        const uint4 q0 = __ldg(in), q1 = __ldg(in + 1);
-        w[0][0] = q0.x; w[0][W - 1] = q0.y; w[1][0] = q0.z; w[1][W - 1] = q0.w;
-        w[2][0] = q1.x; w[2][W - 1] = q1.y; w[3][0] = q1.z; w[3][W - 1] = q1.w;
-    }
-}
-
-// One tile: keys + validity, probes, result words, counts; the reads that are not pure A/C/G/T are parked in the
-// warp's stash (ballot + popc compaction) or, when a tile brings more of them than the stash holds, resolved at once.
-template <int W, int NP, bool PAD>
-FQ_D void probe3_tile(const MatchParams& p, const Probe3Ctx& c, const uint32_t (&w)[PROBE3_R][W],
-                      const uint32_t* __restrict__ packed, uint32_t* __restrict__ results, uint32_t tile, uint32_t lane,
-                      uint32_t& cnt) {
-    uint32_t res[PROBE3_R];
-    bool valid[PROBE3_R];
+template <int W, int NP, bool PAD, int R>
+FQ_D void probe3_tile(const MatchParams& p, const Probe3Ctx& c, const uint32_t (&w)[R][W],
+                      uint32_t* __restrict__ results, uint32_t tile, uint32_t lane, uint32_t& cnt) {
+    uint32_t res[R], bin[R];
+    bool valid[R];
 #pragma unroll
-    for (int r = 0; r < PROBE3_R; r++) res[r] = ck_find<NP>(p, c, ck_key<W, PAD>(p, w[r], valid[r]), valid[r]);
-    const uint32_t g = tile * 32u + lane;  // this lane's group of four consecutive reads
-    reinterpret_cast<uint4*>(results)[g] = make_uint4(res[0], res[1], res[2], res[3]);
-    if (!__any_sync(0xFFFFFFFFu, !(valid[0] && valid[1] && valid[2] && valid[3]))) return;
-    uint32_t bal[PROBE3_R], n_new = 0;
+    for (int r = 0; r < R; r++) res[r] = ck_find<NP>(p, c, ck_key<W, PAD>(p, w[r], valid[r]), valid[r], bin[r]);
+    const uint32_t g = tile * 32u + lane;  // this lane's group of R consecutive reads
+    uint4* out4 = reinterpret_cast<uint4*>(results) + (size_t)g * (R / 4);
 #pragma unroll
-    for (int r = 0; r < PROBE3_R; r++) {
-        bal[r] = __ballot_sync(0xFFFFFFFFu, !valid[r]);
-        n_new += (uint32_t)__popc(bal[r]);
-    }
-    if (cnt + n_new > p.ck_stash_cap) {  // no room: resolve what is parked first
-        probe3_drain<W>(p, c, cnt, results, lane);
-        cnt = 0u;
-    }
-    if (n_new > p.ck_stash_cap) {  // bad reads in bulk (rare)
-        const uint32_t bad = (valid[0] ? 0u : 1u) | (valid[1] ? 0u : 2u) | (valid[2] ? 0u : 4u) | (valid[3] ? 0u : 8u);
-        probe3_park_bulk<W>(p, c, packed, bad, g, results, lane);
-        return;
-    }
+    for (int v = 0; v < R / 4; v++) out4[v] = make_uint4(res[4 * v], res[4 * v + 1], res[4 * v + 2], res[4 * v + 3]);
+    // hist[bin * hrep + lane % hrep] += 1 (unmatched reads, and for now the parked ones, have bin S)
+#pragma unroll
+    for (int r = 0; r < R; r++)
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(imad(bin[r], p.ck_hist_rep * 4u, c.a_hist)) : "memory");
+    bool all_valid = true;
+#pragma unroll
+    for (int r = 0; r < R; r++) all_valid = all_valid && valid[r];
+    if (!__any_sync(0xFFFFFFFFu, !all_valid)) return;
+    // every pass takes each lane's first read that is not pure A/C/G/T (lanes rarely have two): a handful of them
+    // are parked in the warp's stash, half a warp or more is resolved on the spot
+    uint32_t bad = 0u;
+#pragma unroll
+    for (int r = 0; r < R; r++) bad |= valid[r] ? 0u : (1u << r);
     const uint32_t lane_lt = (1u << lane) - 1u;
+    do {
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, bad != 0u);
+        const uint32_t n_new = (uint32_t)__popc(bal);
+        const uint32_t r = (uint32_t)__ffs(bad) - 1u;
+        uint32_t k2[2] = {w[0][0], w[0][W - 1]};
 #pragma unroll
-    for (int r = 0; r < PROBE3_R; r++) {
-        if (!valid[r]) {
-            const uint32_t pos = cnt + (uint32_t)__popc(bal[r] & lane_lt);
-            uint32_t k2[2] = {w[r][0], w[r][W - 1]};
-            sts_key<2>(c.a_skey + pos * 8u, k2);
-            sts32(c.a_skey + p.ck_stash_cap * 8u + pos * 4u, g * 4u + (uint32_t)r);
+        for (int q = 1; q < R; q++) {
+            k2[0] = (r == (uint32_t)q) ? w[q][0] : k2[0];
+            k2[1] = (r == (uint32_t)q) ? w[q][W - 1] : k2[1];
         }
-        cnt += (uint32_t)__popc(bal[r]);
-    }
+        if (n_new >= PROBE3_INLINE_LANES) {
+            probe3_resolve_now<W>(p, c, k2, bad != 0u, g * R + r, results, lane);
+        } else {
+            if (cnt + n_new > p.ck_stash_cap) {  // no room: resolve what is parked first
+                probe3_drain<W>(p, c, cnt, results, lane);
+                cnt = 0u;
+            }
+            if (bad) {
+                const uint32_t pos = cnt + (uint32_t)__popc(bal & lane_lt);
+                sts_key<2>(c.a_stash + pos * 8u, k2);
+                sts32(c.a_stash + p.ck_stash_cap * 8u + pos * 4u, g * R + r);
+            }
+            cnt += n_new;
+        }
+        bad &= bad - 1u;
+    } while (__any_sync(0xFFFFFFFFu, bad != 0u));
 }
 
-// all threads of the CTA: add the packed sample counters to the global table, zero them, and add their sum to
-// *s_matched (the unmatched count falls out at the end as reads processed - matched)
-FQ_D void probe3_flush_hist(const MatchParams& p, uint32_t* s_hist, unsigned long long* s_matched) {
-    __syncthreads();
-    const uint32_t n_words = (p.S + 1u) / 2u;
-    unsigned long long mine = 0ull;
-    for (uint32_t wd = threadIdx.x; wd < n_words; wd += blockDim.x) {
-        uint32_t lo = 0, hi = 0;
-        for (uint32_t r = 0; r < 32u; r++) {
-            const uint32_t col = (r + wd) & 31u;  // rotate the start column: no bank conflicts across the warp
-            const uint32_t v = s_hist[wd * 32u + col];
-            s_hist[wd * 32u + col] = 0u;
-            lo += v & 0xFFFFu;
-            hi += v >> 16;
-        }
-        if (lo) atomicAdd(&p.counts[2u * wd], (unsigned long long)lo);
-        if (hi) atomicAdd(&p.counts[2u * wd + 1u], (unsigned long long)hi);  // 2 wd + 1 < S whenever hi != 0
-        mine += lo + hi;
-    }
-    if (mine) atomicAdd(s_matched, mine);
-    __syncthreads();
-}
-
-template <int W, int NP, bool PAD, int THREADS>
+template <int W, int NP, bool PAD, int R, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ MatchParams p, const ReadSource src,
                                                        uint32_t* __restrict__ results) {
     extern __shared__ uint4 s_dyn[];
-    __shared__ unsigned long long s_matched;  // reads of this CTA that landed in a sample bin
-    // layout: cuckoo entries | packed histogram (32 lane columns) | per-warp stashes
+    // layout: cuckoo entries | histogram replicas | per-warp stashes
     uint32_t* s_ck = reinterpret_cast<uint32_t*>(s_dyn);
     uint32_t* s_hist = s_ck + p.ck_words;
-    const uint32_t n_hist_words = ((p.S + 1u) / 2u) * 32u;
-    uint32_t* s_stash = s_hist + n_hist_words;
+    const uint32_t hrep = p.ck_hist_rep;
     {
         const uint4* g4 = reinterpret_cast<const uint4*>(p.ck_entries);  // ck_words is a multiple of 4
         uint4* s4 = reinterpret_cast<uint4*>(s_ck);
         for (uint32_t t = threadIdx.x; t < p.ck_words / 4u; t += blockDim.x) s4[t] = __ldg(g4 + t);
     }
-    for (uint32_t t = threadIdx.x; t < n_hist_words; t += blockDim.x) s_hist[t] = 0u;
-    if (threadIdx.x == 0) s_matched = 0ull;
+    for (uint32_t t = threadIdx.x; t < (p.S + 1u) * hrep; t += blockDim.x) s_hist[t] = 0u;
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31u;
@@ -981,73 +946,63 @@ __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ M
     Probe3Ctx c;
 #pragma unroll
     for (int i = 0; i < 3; i++) c.base[i] = smem_addr(s_ck) + p.ck_off[i < NP ? i : 0] * 4u;
-    c.a_hist = smem_addr(s_hist) + lane * 4u;
-    c.a_skey = smem_addr(s_stash) + warp_in_cta * (p.ck_stash_cap * 12u);
+    c.a_hist = smem_addr(s_hist) + (lane & (hrep - 1u)) * 4u;
+    c.a_stash = smem_addr(s_hist + (p.S + 1u) * hrep) + warp_in_cta * (p.ck_stash_cap * 12u);
     asm volatile("" : "+r"(c.base[0]), "+r"(c.base[1]), "+r"(c.base[2]), "+r"(c.a_hist));
-    uint32_t cnt = 0;   // reads parked in the warp's stash (warp-uniform)
-    uint32_t done = 0;  // tiles this warp has processed
+    uint32_t cnt = 0;  // reads parked in the warp's stash (warp-uniform)
 
-    const uint32_t n_tiles = (uint32_t)(src.n / (uint64_t)PROBE3_TILE);
+    constexpr uint32_t TILE = 32u * R;
+    const uint32_t n_tiles = (uint32_t)(src.n / (uint64_t)TILE);
     const uint32_t stride = gridDim.x * n_warps;
     uint32_t tile = blockIdx.x * n_warps + warp_in_cta;
-    // every warp of the CTA runs the same number of rounds (two tiles each) so that the flush barrier is legal
-    const uint32_t first = blockIdx.x * n_warps;
-    const uint32_t cta_tiles = first < n_tiles ? (n_tiles - first + stride - 1u) / stride : 0u;  // of the CTA's first warp
-    const uint32_t rounds = (cta_tiles + 1u) / 2u;
 
-    // two register buffers, alternating: the next tile's keys are in flight while this one is resolved
-    uint32_t wa[PROBE3_R][W], wb[PROBE3_R][W];
-    if (tile < n_tiles) probe3_load<W>(src.packed, tile, lane, wa);
-    for (uint32_t round = 0; round < rounds; round++) {
-        if (tile < n_tiles) {
-            uint32_t nt = tile + stride;
-            if (nt < n_tiles) probe3_load<W>(src.packed, nt, lane, wb);
-            probe3_tile<W, NP, PAD>(p, c, wa, src.packed, results, tile, lane, cnt);
-            done++;
-            tile = nt;
-            if (tile < n_tiles) {
-                nt = tile + stride;
-                if (nt < n_tiles) probe3_load<W>(src.packed, nt, lane, wa);
-                probe3_tile<W, NP, PAD>(p, c, wb, src.packed, results, tile, lane, cnt);
-                done++;
-                tile = nt;
-            }
-        }
-        if ((round + 1u) % PROBE3_FLUSH_ROUNDS == 0u) {
-            probe3_drain<W>(p, c, cnt, results, lane);
-            cnt = 0u;
-            probe3_flush_hist(p, s_hist, &s_matched);
-        }
+    // two register buffers, alternating: the next tile's words are in flight while this one is resolved
+    uint32_t wa[R][W], wb[R][W];
+    if (tile < n_tiles) probe3_load<W, R>(src.packed, tile, lane, wa);
+    while (tile < n_tiles) {
+        uint32_t nt = tile + stride;
+        if (nt < n_tiles) probe3_load<W, R>(src.packed, nt, lane, wb);
+        probe3_tile<W, NP, PAD, R>(p, c, wa, results, tile, lane, cnt);
+        tile = nt;
+        if (tile >= n_tiles) break;
+        nt = tile + stride;
+        if (nt < n_tiles) probe3_load<W, R>(src.packed, nt, lane, wa);
+        probe3_tile<W, NP, PAD, R>(p, c, wb, results, tile, lane, cnt);
+        tile = nt;
     }
-    probe3_drain<W>(p, c, cnt, results, lane);
-    unsigned long long processed = (lane == 0u) ? (unsigned long long)done * PROBE3_TILE : 0ull;
 
-    // ---- tail: fewer than 128 reads, one per lane, first warp of the grid ----
+    probe3_drain<W>(p, c, cnt, results, lane);
+
+    // ---- tail: fewer than a tile of reads, one per lane, first warp of the grid ----
     if (blockIdx.x == 0 && threadIdx.x < 32u) {
-        for (uint64_t b0 = (uint64_t)n_tiles * PROBE3_TILE; b0 < src.n; b0 += 32u) {
+        for (uint64_t b0 = (uint64_t)n_tiles * TILE; b0 < src.n; b0 += 32u) {
             const uint64_t i = b0 + lane;
             const bool live = i < src.n;
             uint32_t w1[W];
 #pragma unroll
             for (int k = 0; k < W; k++) w1[k] = live ? __ldg(src.packed + i * W + k) : 0u;
             bool valid;
+            uint32_t bin;
             const uint32_t key = ck_key<W, PAD>(p, w1, valid);
-            uint32_t out = ck_find<NP>(p, c, key, valid && live);
+            uint32_t out = ck_find<NP>(p, c, key, valid, bin);
             const uint32_t slow = slow_resolve<W>(p, w1, live && !valid, lane);
             if (live) {
                 if (!valid) {
                     out = slow;
-                    hist_inc_if(p, c, out >> 16, out != NONE);
+                    bin = (out == NONE) ? p.S : (out >> 16);
                 }
                 results[i] = out;
-                processed += 1ull;
+                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(imad(bin, p.ck_hist_rep * 4u, c.a_hist)) : "memory");
             }
         }
     }
-    probe3_flush_hist(p, s_hist, &s_matched);
-    // unmatched = processed - matched (s_matched is complete after the flush's closing barrier)
-    if (processed) atomicAdd(&p.counts[p.S], processed);
-    if (threadIdx.x == 0 && s_matched) atomicAdd(&p.counts[p.S], 0ull - s_matched);
+    // ---- flush the replicated bins (bin S = unmatched) ----
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b <= p.S; b += blockDim.x) {
+        uint32_t v = 0;
+        for (uint32_t r = 0; r < hrep; r++) v += s_hist[b * hrep + r];
+        if (v) atomicAdd(&p.counts[b], (unsigned long long)v);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1209,37 +1164,32 @@ static cudaError_t launch_probe2_w(const MatchParams& p, const ReadSource& src, 
     return cudaGetLastError();
 }
 
-// shared memory of k_probe3 without the stashes; the stashes take stash_cap * 12 bytes per warp of the largest CTA
-size_t probe3_fixed_smem_bytes(uint32_t ck_words, uint32_t S) {
-    return (size_t)ck_words * 4 + (size_t)((S + 1u) / 2u) * 32 * 4;
-}
-uint32_t probe3_stash_cap(uint32_t ck_words, uint32_t S, size_t smem_max) {  // 0 = does not fit
-    const size_t fixed = probe3_fixed_smem_bytes(ck_words, S);
-    if (fixed > smem_max) return 0;
-    const size_t cap = (smem_max - fixed) / ((size_t)(PROBE3_THREADS / 32) * 12);
-    if (cap < PROBE3_STASH_MIN) return 0;
-    return (uint32_t)std::min<size_t>(cap, PROBE3_STASH_MAX);
-}
-static size_t probe3_smem_bytes(const MatchParams& p) {
-    return probe3_fixed_smem_bytes(p.ck_words, p.S) + (size_t)(PROBE3_THREADS / 32) * p.ck_stash_cap * 12;
+constexpr uint32_t PROBE3_MAX_WARPS = 32;
+size_t probe3_smem_bytes(uint32_t ck_words, uint32_t S, uint32_t hist_rep, uint32_t stash_cap) {
+    return (size_t)ck_words * 4 + (size_t)(S + 1u) * hist_rep * 4 + (size_t)PROBE3_MAX_WARPS * stash_cap * 12;
 }
 
-static int probe3_threads() {  // FQTK_B200_P3_THREADS=768 trades resident warps for registers (A/B timing)
+// launch shape of k_probe3: FQTK_B200_P3_SHAPE = "<reads per lane>x<threads>" (4x1024 | 4x768 | 8x768 | 8x512), for A/B timing
+static int probe3_shape() {
     static const int v = [] {
-        const char* e = getenv("FQTK_B200_P3_THREADS");
-        const int t = e ? atoi(e) : 0;
-        return t == 768 ? 768 : PROBE3_THREADS;
+        const char* e = getenv("FQTK_B200_P3_SHAPE");
+        if (!e) return 0;
+        if (!strcmp(e, "4x1024")) return 0;
+        if (!strcmp(e, "4x768")) return 1;
+        if (!strcmp(e, "8x768")) return 2;
+        if (!strcmp(e, "8x512")) return 3;
+        return 0;
     }();
     return v;
 }
 
-template <int W, int NP, bool PAD, int THREADS>
-static cudaError_t launch_probe3_wnpt(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
-                                      const LaunchGeometry& g, cudaStream_t stream) {
-    auto k = k_probe3<W, NP, PAD, THREADS>;
-    const size_t smem = probe3_smem_bytes(p);
+template <int W, int NP, bool PAD, int R, int THREADS>
+static cudaError_t launch_probe3_shape(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
+                                       const LaunchGeometry& g, cudaStream_t stream) {
+    auto k = k_probe3<W, NP, PAD, R, THREADS>;
+    const size_t smem = probe3_smem_bytes(p.ck_words, p.S, p.ck_hist_rep, p.ck_stash_cap);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const uint64_t n_warp_tiles = (src.n + PROBE3_TILE - 1) / PROBE3_TILE;
+    const uint64_t n_warp_tiles = (src.n + 32 * R - 1) / (32 * R);
     const uint64_t want = (n_warp_tiles + THREADS / 32 - 1) / (THREADS / 32);
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)g.sm_count));
     k<<<grid, THREADS, smem, stream>>>(p, src, d_results);
@@ -1250,8 +1200,12 @@ static cudaError_t launch_probe3_wnpt(const MatchParams& p, const ReadSource& sr
 template <int W, int NP, bool PAD>
 static cudaError_t launch_probe3_wnp(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
                                      const LaunchGeometry& g, cudaStream_t stream) {
-    return probe3_threads() == 768 ? launch_probe3_wnpt<W, NP, PAD, 768>(p, src, d_results, g, stream)
-                                   : launch_probe3_wnpt<W, NP, PAD, PROBE3_THREADS>(p, src, d_results, g, stream);
+    switch (probe3_shape()) {
+        case 1: return launch_probe3_shape<W, NP, PAD, 4, 768>(p, src, d_results, g, stream);
+        case 2: return launch_probe3_shape<W, NP, PAD, 8, 768>(p, src, d_results, g, stream);
+        case 3: return launch_probe3_shape<W, NP, PAD, 8, 512>(p, src, d_results, g, stream);
+        default: return launch_probe3_shape<W, NP, PAD, 4, 1024>(p, src, d_results, g, stream);
+    }
 }
 
 template <int W, int NP>
