@@ -309,7 +309,7 @@ int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, cons
         const uint64_t slots = slots_of(g);
         const double max_load = g.np == 2 ? 0.40 : 0.80;
         if ((double)ent.size() > max_load * (double)slots) continue;
-        if (fq::probe3_smem_bytes((uint32_t)slots, S, 4, 16) > smem_max) continue;  // >= 4 histogram replicas + stashes
+        if (fq::probe3_smem_bytes((uint32_t)slots, S, 16) > smem_max) continue;  // table + histogram + minimal stashes
         uint32_t off[3] = {0, 0, 0};
         for (uint32_t i = 1; i < g.np; i++) off[i] = off[i - 1] + (1u << g.sb[i - 1]);
         std::vector<uint32_t> slot_key(slots, 0u), slot_code(slots, 0xFFFFFFFFu);  // code 0xFFFFFFFF = empty
@@ -378,11 +378,8 @@ int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, cons
         p.ck_bmask8 = bmask8;
         p.ck_nmask = nmask;
         p.ck_next_min = min_next;
-        uint32_t rep = 32;
-        while (rep > 1 && fq::probe3_smem_bytes((uint32_t)slots, S, rep, 16) > smem_max) rep >>= 1;
-        p.ck_hist_rep = rep;
         uint32_t cap = 16;
-        while (cap < 64 && fq::probe3_smem_bytes((uint32_t)slots, S, rep, cap + 1) <= smem_max) cap++;
+        while (cap < 64 && fq::probe3_smem_bytes((uint32_t)slots, S, cap + 1) <= smem_max) cap++;
         p.ck_stash_cap = cap;
         m->cuckoo_entries = ent.size();
         return 0;
@@ -704,9 +701,9 @@ int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t S, uint32_t L,
     m->params.ck_entries = nullptr;
     m->params.ck_np = 0;
     m->params.ck_words = 0;
+    m->params.ck_pf_dist = 1;
     m->params.ck_one = 1;
     m->params.ck_four = 4;
-    m->params.ck_hist_rep = 1;
     m->params.ck_stash_cap = 32;
     m->mode = FQTK_B200_MODE_BRUTE;
     if (use_cache && W <= (uint32_t)fq::MAX_FAST_WORDS) {

@@ -42,8 +42,8 @@ struct MatchParams {
     uint32_t ck_bsh, ck_bmask8;  // (code << ck_bsh) & ck_bmask8 = best << 8   (ck_bsh = 8 - nb)
     uint32_t ck_nmask;           // code & ck_nmask = next - ck_next_min
     uint32_t ck_next_min;
-    uint32_t ck_hist_rep;        // histogram replicas of k_probe3 (power of two <= 32)
     uint32_t ck_stash_cap;       // stash entries per warp of k_probe3 (16 .. 64)
+    uint32_t ck_pf_dist;         // L2 prefetch distance of k_probe3, in tiles beyond the register double buffer
     uint32_t ck_one, ck_four;    // 1 and 4 (see Probe3Ctx in match_kernels.cu)
 };
 
@@ -105,7 +105,7 @@ cudaError_t launch_route(const uint32_t* d_results, uint64_t n, uint32_t S, uint
                          unsigned long long* d_offsets, void* d_workspace, const LaunchGeometry& g, cudaStream_t stream);
 cudaError_t prepare_kernels(const LaunchGeometry& g);  // opt-in shared memory attributes, once per device
 
-size_t probe3_smem_bytes(uint32_t ck_words, uint32_t S, uint32_t hist_rep, uint32_t stash_cap);
+size_t probe3_smem_bytes(uint32_t ck_words, uint32_t S, uint32_t stash_cap);
 size_t probe2_fixed_smem_bytes(uint32_t W, uint32_t S, int threads);  // k_probe2 shared memory besides tier + Bloom
 int probe2_threads();
 uint32_t probe2_hist_rep(uint32_t S);

@@ -728,7 +728,8 @@ __global__ void __launch_bounds__(PROBE2_THREADS, 1) k_probe2(const MatchParams 
 //     unmatched, parked in a small per-warp stash in shared memory (one ballot per pass: each lane parks its first
 //     such read) and resolved a warp-full at a time through the global memo table (which also holds the N-containing
 //     neighbours) or, outside its alphabet, the warp-cooperative scan; the result word and the counts are patched.
-// Per-sample counts: lane-replicated shared-memory histogram (bin S = unmatched), one unconditional atomic per read.
+// Per-sample counts: lane-private (conflict-free) shared-memory histogram of packed 16-bit counters, one unconditional
+// atomic per read, flushed to the global u64 table under a barrier every PROBE3_FLUSH_ROUNDS rounds.
 // The kernel is bound by instruction issue and the SM's integer pipes, so adds and address computations on the hot
 // path are written as multiply-adds with an operand read from the kernel parameters (IMAD, fma pipe) and only the
 // logic ops, shifts, compares and selects stay on the alu pipe (both issue one warp instruction per 2 clocks).
@@ -744,6 +745,7 @@ struct Probe3Ctx {
 // an alu-pipe add / LEA: those adds and scalings stay multiply-adds on the fma pipe.
 
 FQ_D uint32_t imad(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
+FQ_HD uint32_t probe3_unmatched_bin(uint32_t S) { return S | 1u; }  // smallest odd index >= S (see hist_inc)
 
 // Compressed key + validity of one read: acgt_key (common.cuh), with the subtractions and the left shift on the fma pipe.
 template <int W, bool PAD>
@@ -762,7 +764,7 @@ FQ_D uint32_t ck_key(const MatchParams& p, const uint32_t (&w)[W], bool& valid) 
 }
 
 // One key through the shared-memory table: the result word (NONE for unmatched AND for reads that are not pure
-// A/C/G/T) and the histogram bin (S when NONE).
+// A/C/G/T) and the histogram bin (the unmatched bin when NONE).
 template <int NP>
 FQ_D uint32_t ck_find(const MatchParams& p, const Probe3Ctx& c, uint32_t k, bool valid, uint32_t& bin) {
     uint32_t u = 0xFFFFFFFFu;
@@ -777,7 +779,7 @@ FQ_D uint32_t ck_find(const MatchParams& p, const Probe3Ctx& c, uint32_t k, bool
     const uint32_t idx = u >> p.ck_lb;
     const uint32_t low = ((u << p.ck_bsh) & p.ck_bmask8) | (u & p.ck_nmask);
     const uint32_t word = imad(idx, 65536u, imad(low, p.ck_one, p.ck_next_min));
-    bin = found ? idx : p.S;
+    bin = found ? idx : probe3_unmatched_bin(p.S);
     return found ? word : NONE;
 }
 
@@ -803,9 +805,43 @@ FQ_D uint32_t slow_resolve(const MatchParams& p, const uint32_t (&kw)[W], bool a
     return out;
 }
 
-// hist[bin * hrep + lane % hrep] += v
-FQ_D void hist_add(const MatchParams& p, const Probe3Ctx& c, uint32_t bin, uint32_t v) {
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(imad(bin, p.ck_hist_rep * 4u, c.a_hist)), "r"(v) : "memory");
+// Packed histogram: 32 lane-private columns (bank = lane: no conflicts), two 16-bit counters per word; bin b is the
+// (b & 1) half of word b >> 1.  The unmatched bin U is the smallest ODD index >= S, i.e. always a high half, so that
+// taking one away (adding 0xFFFF0000) cannot carry into a neighbour.  The CTA flushes the counters to the global
+// u64 table every PROBE3_FLUSH_ROUNDS rounds, under a barrier, long before a 16-bit field can wrap.
+FQ_D void hist_inc(const MatchParams& p, const Probe3Ctx& c, uint32_t bin) {
+    const uint32_t addr = imad(bin & ~1u, p.ck_four * 16u, c.a_hist);  // (bin >> 1) * 128
+    const uint32_t val = imad(bin & 1u, 65535u, p.ck_one);             // 1 or 65536
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
+}
+FQ_D void hist_unmatched_dec(const MatchParams& p, const Probe3Ctx& c) {
+    const uint32_t addr = c.a_hist + (probe3_unmatched_bin(p.S) >> 1) * 128u;
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(0xFFFF0000u) : "memory");
+}
+// a 16-bit field gains at most (32 warps) x (2 tiles x 4 reads, counted once and re-counted at most once) per round
+constexpr uint32_t PROBE3_FLUSH_ROUNDS = 64;  // 64 * 32 * 16 = 32768 < 65536
+
+// all threads of the CTA: add the packed counters to the global table and zero them
+FQ_D void probe3_flush_hist(const MatchParams& p, uint32_t* s_hist) {
+    __syncthreads();
+    const uint32_t U = probe3_unmatched_bin(p.S);
+    const uint32_t n_words = (U + 1u) / 2u;
+    for (uint32_t wd = threadIdx.x; wd < n_words; wd += blockDim.x) {
+        uint32_t lo = 0, hi = 0;
+        for (uint32_t r = 0; r < 32u; r++) {
+            const uint32_t col = (r + wd) & 31u;  // rotate the start column: no bank conflicts across the warp
+            const uint32_t v = s_hist[wd * 32u + col];
+            s_hist[wd * 32u + col] = 0u;
+            lo += v & 0xFFFFu;
+            hi += v >> 16;
+        }
+        lo &= 0xFFFFu;  // fields are sums modulo 2^16 (the unmatched one may have borrowed in single columns)
+        hi &= 0xFFFFu;
+        const uint32_t b0 = 2u * wd, b1 = 2u * wd + 1u;
+        if (lo && b0 < p.S) atomicAdd(&p.counts[b0], (unsigned long long)lo);
+        if (hi) atomicAdd(&p.counts[b1 < p.S ? b1 : p.S], (unsigned long long)hi);  // b1 >= S only for the unmatched bin
+    }
+    __syncthreads();
 }
 
 constexpr uint32_t PROBE3_INLINE_LANES = 16;  // this many lanes with an odd read in one pass: not worth parking
@@ -821,8 +857,8 @@ __device__ __noinline__ void probe3_resolve_now(const MatchParams& p, const Prob
     const uint32_t out = slow_resolve<W>(p, kw, act, lane);
     if (act && out != NONE) {
         results[idx] = out;
-        hist_add(p, c, out >> 16, 1u);
-        hist_add(p, c, p.S, 0xFFFFFFFFu);
+        hist_inc(p, c, out >> 16);
+        hist_unmatched_dec(p, c);
     }
 }
 
@@ -848,11 +884,20 @@ __device__ __noinline__ void probe3_drain(const MatchParams& p, const Probe3Ctx 
         const uint32_t out = slow_resolve<W>(p, kw, act, lane);
         if (act && out != NONE) {  // it was written as None and counted as unmatched when it was parked
             results[idx] = out;
-            hist_add(p, c, out >> 16, 1u);
-            hist_add(p, c, p.S, 0xFFFFFFFFu);
+            hist_inc(p, c, out >> 16);
+            hist_unmatched_dec(p, c);
         }
     }
     __syncwarp();  // the stash is free again
+}
+
+// Ask L2 for a whole tile (32 * R reads) two rounds ahead of its use: one TMA bulk-prefetch by one lane, no registers.
+template <int W, int R>
+FQ_D void probe3_prefetch_l2(const uint32_t* __restrict__ packed, uint32_t tile, uint32_t lane) {
+    if (lane == 0u) {
+        const uint32_t* ptr = packed + (size_t)tile * (32u * R * W);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(32u * R * W * 4u) : "memory");
+    }
 }
 
 template <int W, int R>
@@ -883,10 +928,9 @@ FQ_D void probe3_tile(const MatchParams& p, const Probe3Ctx& c, const uint32_t (
     uint4* out4 = reinterpret_cast<uint4*>(results) + (size_t)g * (R / 4);
 #pragma unroll
     for (int v = 0; v < R / 4; v++) out4[v] = make_uint4(res[4 * v], res[4 * v + 1], res[4 * v + 2], res[4 * v + 3]);
-    // hist[bin * hrep + lane % hrep] += 1 (unmatched reads, and for now the parked ones, have bin S)
+    // counts (unmatched reads, and for now the parked ones, go to the unmatched bin)
 #pragma unroll
-    for (int r = 0; r < R; r++)
-        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(imad(bin[r], p.ck_hist_rep * 4u, c.a_hist)) : "memory");
+    for (int r = 0; r < R; r++) hist_inc(p, c, bin[r]);
     bool all_valid = true;
 #pragma unroll
     for (int r = 0; r < R; r++) all_valid = all_valid && valid[r];
@@ -929,16 +973,16 @@ template <int W, int NP, bool PAD, int R, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ MatchParams p, const ReadSource src,
                                                        uint32_t* __restrict__ results) {
     extern __shared__ uint4 s_dyn[];
-    // layout: cuckoo entries | histogram replicas | per-warp stashes
+    // layout: cuckoo entries | packed histogram (32 lane columns) | per-warp stashes
     uint32_t* s_ck = reinterpret_cast<uint32_t*>(s_dyn);
     uint32_t* s_hist = s_ck + p.ck_words;
-    const uint32_t hrep = p.ck_hist_rep;
+    const uint32_t n_hist_words = ((probe3_unmatched_bin(p.S) + 1u) / 2u) * 32u;
     {
         const uint4* g4 = reinterpret_cast<const uint4*>(p.ck_entries);  // ck_words is a multiple of 4
         uint4* s4 = reinterpret_cast<uint4*>(s_ck);
         for (uint32_t t = threadIdx.x; t < p.ck_words / 4u; t += blockDim.x) s4[t] = __ldg(g4 + t);
     }
-    for (uint32_t t = threadIdx.x; t < (p.S + 1u) * hrep; t += blockDim.x) s_hist[t] = 0u;
+    for (uint32_t t = threadIdx.x; t < n_hist_words; t += blockDim.x) s_hist[t] = 0u;
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31u;
@@ -946,8 +990,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ M
     Probe3Ctx c;
 #pragma unroll
     for (int i = 0; i < 3; i++) c.base[i] = smem_addr(s_ck) + p.ck_off[i < NP ? i : 0] * 4u;
-    c.a_hist = smem_addr(s_hist) + (lane & (hrep - 1u)) * 4u;
-    c.a_stash = smem_addr(s_hist + (p.S + 1u) * hrep) + warp_in_cta * (p.ck_stash_cap * 12u);
+    c.a_hist = smem_addr(s_hist) + lane * 4u;
+    c.a_stash = smem_addr(s_hist + n_hist_words) + warp_in_cta * (p.ck_stash_cap * 12u);
     asm volatile("" : "+r"(c.base[0]), "+r"(c.base[1]), "+r"(c.base[2]), "+r"(c.a_hist));
     uint32_t cnt = 0;  // reads parked in the warp's stash (warp-uniform)
 
@@ -955,22 +999,36 @@ __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ M
     const uint32_t n_tiles = (uint32_t)(src.n / (uint64_t)TILE);
     const uint32_t stride = gridDim.x * n_warps;
     uint32_t tile = blockIdx.x * n_warps + warp_in_cta;
+    const uint32_t pf = stride * p.ck_pf_dist;  // L2 prefetch distance beyond the register buffer
+    // every warp of the CTA runs the same number of rounds (two tiles each) so that the flush barrier is legal
+    const uint32_t first = blockIdx.x * n_warps;
+    const uint32_t cta_tiles = first < n_tiles ? (n_tiles - first + stride - 1u) / stride : 0u;  // of the CTA's first warp
+    const uint32_t rounds = (cta_tiles + 1u) / 2u;
 
     // two register buffers, alternating: the next tile's words are in flight while this one is resolved
     uint32_t wa[R][W], wb[R][W];
     if (tile < n_tiles) probe3_load<W, R>(src.packed, tile, lane, wa);
-    while (tile < n_tiles) {
-        uint32_t nt = tile + stride;
-        if (nt < n_tiles) probe3_load<W, R>(src.packed, nt, lane, wb);
-        probe3_tile<W, NP, PAD, R>(p, c, wa, results, tile, lane, cnt);
-        tile = nt;
-        if (tile >= n_tiles) break;
-        nt = tile + stride;
-        if (nt < n_tiles) probe3_load<W, R>(src.packed, nt, lane, wa);
-        probe3_tile<W, NP, PAD, R>(p, c, wb, results, tile, lane, cnt);
-        tile = nt;
+    for (uint32_t round = 0; round < rounds; round++) {
+        if (tile < n_tiles) {
+            uint32_t nt = tile + stride;
+            if (nt < n_tiles) probe3_load<W, R>(src.packed, nt, lane, wb);
+            if (nt + pf < n_tiles) probe3_prefetch_l2<W, R>(src.packed, nt + pf, lane);
+            probe3_tile<W, NP, PAD, R>(p, c, wa, results, tile, lane, cnt);
+            tile = nt;
+            if (tile < n_tiles) {
+                nt = tile + stride;
+                if (nt < n_tiles) probe3_load<W, R>(src.packed, nt, lane, wa);
+                if (nt + pf < n_tiles) probe3_prefetch_l2<W, R>(src.packed, nt + pf, lane);
+                probe3_tile<W, NP, PAD, R>(p, c, wb, results, tile, lane, cnt);
+                tile = nt;
+            }
+        }
+        if ((round + 1u) % PROBE3_FLUSH_ROUNDS == 0u) {
+            probe3_drain<W>(p, c, cnt, results, lane);
+            cnt = 0u;
+            probe3_flush_hist(p, s_hist);
+        }
     }
-
     probe3_drain<W>(p, c, cnt, results, lane);
 
     // ---- tail: fewer than a tile of reads, one per lane, first warp of the grid ----
@@ -989,20 +1047,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ M
             if (live) {
                 if (!valid) {
                     out = slow;
-                    bin = (out == NONE) ? p.S : (out >> 16);
+                    bin = (out == NONE) ? probe3_unmatched_bin(p.S) : (out >> 16);
                 }
                 results[i] = out;
-                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(imad(bin, p.ck_hist_rep * 4u, c.a_hist)) : "memory");
+                hist_inc(p, c, bin);
             }
         }
     }
-    // ---- flush the replicated bins (bin S = unmatched) ----
-    __syncthreads();
-    for (uint32_t b = threadIdx.x; b <= p.S; b += blockDim.x) {
-        uint32_t v = 0;
-        for (uint32_t r = 0; r < hrep; r++) v += s_hist[b * hrep + r];
-        if (v) atomicAdd(&p.counts[b], (unsigned long long)v);
-    }
+    probe3_flush_hist(p, s_hist);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1165,8 +1217,9 @@ static cudaError_t launch_probe2_w(const MatchParams& p, const ReadSource& src, 
 }
 
 constexpr uint32_t PROBE3_MAX_WARPS = 32;
-size_t probe3_smem_bytes(uint32_t ck_words, uint32_t S, uint32_t hist_rep, uint32_t stash_cap) {
-    return (size_t)ck_words * 4 + (size_t)(S + 1u) * hist_rep * 4 + (size_t)PROBE3_MAX_WARPS * stash_cap * 12;
+size_t probe3_smem_bytes(uint32_t ck_words, uint32_t S, uint32_t stash_cap) {
+    return (size_t)ck_words * 4 + (size_t)((probe3_unmatched_bin(S) + 1u) / 2u) * 32 * 4 +
+           (size_t)PROBE3_MAX_WARPS * stash_cap * 12;
 }
 
 // launch shape of k_probe3: FQTK_B200_P3_SHAPE = "<reads per lane>x<threads>" (4x1024 | 4x768 | 8x768 | 8x512), for A/B timing
@@ -1183,11 +1236,22 @@ static int probe3_shape() {
     return v;
 }
 
+static uint32_t probe3_pf_dist() {  // FQTK_B200_P3_PF = tiles of L2 prefetch distance (A/B timing), default 1
+    static const uint32_t v = [] {
+        const char* e = getenv("FQTK_B200_P3_PF");
+        const int t = e ? atoi(e) : 1;
+        return (uint32_t)(t >= 0 && t <= 64 ? t : 1);
+    }();
+    return v;
+}
+
 template <int W, int NP, bool PAD, int R, int THREADS>
-static cudaError_t launch_probe3_shape(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
+static cudaError_t launch_probe3_shape(const MatchParams& p_in, const ReadSource& src, uint32_t* d_results,
                                        const LaunchGeometry& g, cudaStream_t stream) {
+    MatchParams p = p_in;
+    p.ck_pf_dist = probe3_pf_dist();
     auto k = k_probe3<W, NP, PAD, R, THREADS>;
-    const size_t smem = probe3_smem_bytes(p.ck_words, p.S, p.ck_hist_rep, p.ck_stash_cap);
+    const size_t smem = probe3_smem_bytes(p.ck_words, p.S, p.ck_stash_cap);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const uint64_t n_warp_tiles = (src.n + 32 * R - 1) / (32 * R);
     const uint64_t want = (n_warp_tiles + THREADS / 32 - 1) / (THREADS / 32);
