@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfqtk_b200.so")
+LIB_PATH = os.environ.get("FQTK_B200_LIB") or os.path.join(_HERE, "libfqtk_b200.so")  # env: A/B builds only
 
 NONE = 0xFFFFFFFF
 OK = 0

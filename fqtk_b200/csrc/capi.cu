@@ -701,7 +701,6 @@ int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t S, uint32_t L,
     m->params.ck_entries = nullptr;
     m->params.ck_np = 0;
     m->params.ck_words = 0;
-    m->params.ck_pf_dist = 1;
     m->params.ck_one = 1;
     m->params.ck_four = 4;
     m->params.ck_stash_cap = 32;

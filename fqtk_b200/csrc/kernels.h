@@ -43,7 +43,6 @@ struct MatchParams {
     uint32_t ck_nmask;           // code & ck_nmask = next - ck_next_min
     uint32_t ck_next_min;
     uint32_t ck_stash_cap;       // stash entries per warp of k_probe3 (16 .. 64)
-    uint32_t ck_pf_dist;         // L2 prefetch distance of k_probe3, in tiles beyond the register double buffer
     uint32_t ck_one, ck_four;    // 1 and 4 (see Probe3Ctx in match_kernels.cu)
 };
 

@@ -746,6 +746,7 @@ struct Probe3Ctx {
 
 FQ_D uint32_t imad(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
 FQ_HD uint32_t probe3_unmatched_bin(uint32_t S) { return S | 1u; }  // smallest odd index >= S (see hist_inc)
+FQ_HD uint32_t probe3_hist_words(uint32_t S) { return ((probe3_unmatched_bin(S) + 1u) / 2u) * 32u; }
 
 // Compressed key + validity of one read: acgt_key (common.cuh), with the subtractions and the left shift on the fma pipe.
 template <int W, bool PAD>
@@ -891,7 +892,8 @@ __device__ __noinline__ void probe3_drain(const MatchParams& p, const Probe3Ctx 
     __syncwarp();  // the stash is free again
 }
 
-// Ask L2 for a whole tile (32 * R reads) two rounds ahead of its use: one TMA bulk-prefetch by one lane, no registers.
+// Ask L2 for a whole tile (32 * R reads) two tiles ahead of its use: one TMA bulk prefetch by one lane, no registers
+// (measured on B200, cfg 3: 1.33 -> 1.23 ms; distances of 2 and 4 tiles beyond the register buffer: no further gain).
 template <int W, int R>
 FQ_D void probe3_prefetch_l2(const uint32_t* __restrict__ packed, uint32_t tile, uint32_t lane) {
     if (lane == 0u) {
@@ -976,7 +978,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ M
     // layout: cuckoo entries | packed histogram (32 lane columns) | per-warp stashes
     uint32_t* s_ck = reinterpret_cast<uint32_t*>(s_dyn);
     uint32_t* s_hist = s_ck + p.ck_words;
-    const uint32_t n_hist_words = ((probe3_unmatched_bin(p.S) + 1u) / 2u) * 32u;
+    const uint32_t n_hist_words = probe3_hist_words(p.S);
     {
         const uint4* g4 = reinterpret_cast<const uint4*>(p.ck_entries);  // ck_words is a multiple of 4
         uint4* s4 = reinterpret_cast<uint4*>(s_ck);
@@ -999,7 +1001,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ M
     const uint32_t n_tiles = (uint32_t)(src.n / (uint64_t)TILE);
     const uint32_t stride = gridDim.x * n_warps;
     uint32_t tile = blockIdx.x * n_warps + warp_in_cta;
-    const uint32_t pf = stride * p.ck_pf_dist;  // L2 prefetch distance beyond the register buffer
     // every warp of the CTA runs the same number of rounds (two tiles each) so that the flush barrier is legal
     const uint32_t first = blockIdx.x * n_warps;
     const uint32_t cta_tiles = first < n_tiles ? (n_tiles - first + stride - 1u) / stride : 0u;  // of the CTA's first warp
@@ -1012,13 +1013,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ M
         if (tile < n_tiles) {
             uint32_t nt = tile + stride;
             if (nt < n_tiles) probe3_load<W, R>(src.packed, nt, lane, wb);
-            if (nt + pf < n_tiles) probe3_prefetch_l2<W, R>(src.packed, nt + pf, lane);
+            if (nt + stride < n_tiles) probe3_prefetch_l2<W, R>(src.packed, nt + stride, lane);
             probe3_tile<W, NP, PAD, R>(p, c, wa, results, tile, lane, cnt);
             tile = nt;
             if (tile < n_tiles) {
                 nt = tile + stride;
                 if (nt < n_tiles) probe3_load<W, R>(src.packed, nt, lane, wa);
-                if (nt + pf < n_tiles) probe3_prefetch_l2<W, R>(src.packed, nt + pf, lane);
+                if (nt + stride < n_tiles) probe3_prefetch_l2<W, R>(src.packed, nt + stride, lane);
                 probe3_tile<W, NP, PAD, R>(p, c, wb, results, tile, lane, cnt);
                 tile = nt;
             }
@@ -1218,7 +1219,7 @@ static cudaError_t launch_probe2_w(const MatchParams& p, const ReadSource& src, 
 
 constexpr uint32_t PROBE3_MAX_WARPS = 32;
 size_t probe3_smem_bytes(uint32_t ck_words, uint32_t S, uint32_t stash_cap) {
-    return (size_t)ck_words * 4 + (size_t)((probe3_unmatched_bin(S) + 1u) / 2u) * 32 * 4 +
+    return (size_t)ck_words * 4 + (size_t)probe3_hist_words(S) * 4 +
            (size_t)PROBE3_MAX_WARPS * stash_cap * 12;
 }
 
@@ -1236,20 +1237,9 @@ static int probe3_shape() {
     return v;
 }
 
-static uint32_t probe3_pf_dist() {  // FQTK_B200_P3_PF = tiles of L2 prefetch distance (A/B timing), default 1
-    static const uint32_t v = [] {
-        const char* e = getenv("FQTK_B200_P3_PF");
-        const int t = e ? atoi(e) : 1;
-        return (uint32_t)(t >= 0 && t <= 64 ? t : 1);
-    }();
-    return v;
-}
-
 template <int W, int NP, bool PAD, int R, int THREADS>
-static cudaError_t launch_probe3_shape(const MatchParams& p_in, const ReadSource& src, uint32_t* d_results,
+static cudaError_t launch_probe3_shape(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
                                        const LaunchGeometry& g, cudaStream_t stream) {
-    MatchParams p = p_in;
-    p.ck_pf_dist = probe3_pf_dist();
     auto k = k_probe3<W, NP, PAD, R, THREADS>;
     const size_t smem = probe3_smem_bytes(p.ck_words, p.S, p.ck_stash_cap);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
