@@ -45,8 +45,9 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=0, help="override reads per GPU per step (default: the config's N)")
     ap.add_argument("--e2e-reads", type=int, default=128 << 20, help="reads per GPU per e2e step (pinned host memory)")
     ap.add_argument("--mode", choices=["auto", "table", "brute"], default="auto")
-    ap.add_argument("--cuckoo", type=int, default=-1, choices=[-1, 0, 2, 3],
-                    help="shared-memory cuckoo table arity for k_probe3 (-1 auto, 0 = off -> k_probe2); A/B timing")
+    ap.add_argument("--cuckoo", type=int, default=-1, choices=[-1, 0, 1, 2, 3],
+                    help="packed-route kernel knob (fqtk_b200_set_cuckoo_arity): -1 auto, 0 k_probe2, 1 k_probe4, "
+                         "2/3 k_probe3 with that many sub-tables; A/B timing")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-brute", action="store_true")
@@ -297,7 +298,9 @@ def run_b200(args):
     mode = matcher.mode
     info = matcher.info()
     kernel = "k_brute" if mode != "table" else (
-        f"k_probe3<W={W},NP={int(info.cuckoo_probes)}>" if int(info.cuckoo_probes) and W <= 2 else "k_probe2")
+        f"k_probe3<W={W},NP={int(info.cuckoo_probes)}>" if int(info.cuckoo_probes) and W <= 2 else
+        f"k_probe4<W={W}>" if int(info.l2_table_entries) and (W == 3 or args.cuckoo == 1) else
+        "k_probe2+l2table" if int(info.l2_table_entries) else "k_probe2")
     counts_t = torch.zeros(cfg.n_samples + 1, dtype=torch.int64, device=dev)
 
     def barrier():
@@ -468,7 +471,8 @@ def run_b200(args):
             "memo_table": {"entries": int(info.table_entries), "slots": int(info.table_slots),
                            "bytes": int(info.table_bytes), "candidates": int(info.table_candidates),
                            "cuckoo_entries": int(info.cuckoo_entries), "cuckoo_probes": int(info.cuckoo_probes),
-                           "cuckoo_slots": int(info.cuckoo_slots)},
+                           "cuckoo_slots": int(info.cuckoo_slots), "l2_table_entries": int(info.l2_table_entries),
+                           "l2_table_bytes": int(info.l2_table_bytes)},
             "brute_force": brute, "routing": routing,
             "matched_fraction": round(1.0 - float(counts[-1]) / float(counts.sum()), 5),
         }

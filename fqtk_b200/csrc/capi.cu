@@ -74,6 +74,8 @@ struct fqtk_b200_matcher {
     uint32_t* d_tier = nullptr;
     uint32_t* d_bloom = nullptr;
     uint32_t* d_cuckoo = nullptr;
+    uint2* d_g4 = nullptr;
+    uint64_t g4_entries = 0;
     uint64_t cuckoo_entries = 0;
     uint64_t tier_entries = 0;
     unsigned long long* d_counts = nullptr;
@@ -292,7 +294,7 @@ int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, cons
     struct Geo { uint32_t np, sb[3]; };
     std::vector<Geo> options;
     const int force = ck_force_np();
-    if (force == 0) return 1;
+    if (force == 0 || force == 1) return 1;  // 0: k_probe2 only, 1: k_probe4's table only
     for (uint32_t s = std::max(cb, 4u); s <= 16; s++) {
         if (force != 3) {
             options.push_back({2, {s, s, 0}});
@@ -385,6 +387,96 @@ int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, cons
         return 0;
     }
     return 1;
+}
+
+// k_probe4's global table (kernels.h): every Some(..) memo entry whose key is pure A/C/G/T under its compressed key, in
+// 8-byte slots, four to a 32-byte bucket, bucketised linear probing at load <= 0.6 so that it stays L2-resident
+// (cfg 4: 1.7 M entries, 23 MB instead of the memo table's 122 MB).  Returns 0 when built, 1 when the panel does not qualify, < 0 on error.
+template <int W>
+int build_g4_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, const std::vector<uint32_t>& res, uint64_t n) {
+    const uint32_t S = m->S, L = m->L, pad = m->params.last_pad;
+    if (S + 1u > 8192u || L > 24u) return 1;
+    const uint32_t hi_bits = L > 16u ? 2u * (L - 16u) : 0u;
+    const uint32_t hi_mask = hi_bits ? ((1u << hi_bits) - 1u) : 0u;
+    struct Ent { uint32_t lo, hi, word; };
+    std::vector<Ent> ent;
+    for (uint64_t t = 0; t < n; t++) {
+        if (res[t] == fq::NONE) continue;
+        uint32_t kw[W];
+        for (int k = 0; k < W; k++) kw[k] = keys[t * W + k];
+        bool valid;
+        uint32_t hi;
+        const uint32_t lo = fq::acgt_key64<W>(kw, pad, hi_mask, hi, valid);
+        if (valid) ent.push_back({lo, hi, res[t]});
+    }
+    std::sort(ent.begin(), ent.end(), [](const Ent& a, const Ent& b) {
+        return a.hi != b.hi ? a.hi < b.hi : (a.lo != b.lo ? a.lo < b.lo : a.word < b.word);
+    });
+    ent.erase(std::unique(ent.begin(), ent.end(), [](const Ent& a, const Ent& b) {
+        return a.lo == b.lo && a.hi == b.hi && a.word == b.word; }), ent.end());
+    for (size_t t = 1; t < ent.size(); t++)
+        if (ent[t].lo == ent[t - 1].lo && ent[t].hi == ent[t - 1].hi) return 1;  // cannot happen: one string, one result
+    if (ent.empty()) return 1;
+    // value code (L > 16 only) = idx << (bb + nb) | best << nb | (next - next_min), as in k_probe3
+    uint32_t max_idx = 0, max_best = 0, min_next = 255, max_next = 0;
+    for (auto& e : ent) {
+        max_idx = std::max(max_idx, e.word >> 16);
+        max_best = std::max(max_best, (e.word >> 8) & 0xFFu);
+        min_next = std::min(min_next, e.word & 0xFFu);
+        max_next = std::max(max_next, e.word & 0xFFu);
+    }
+    auto bits_for = [](uint32_t v) { uint32_t b = 0; while (b < 32 && (v >> b)) b++; return b; };
+    const uint32_t ib = bits_for(max_idx), bb = bits_for(max_best), nb = bits_for(max_next - min_next);
+    uint32_t vb = std::max(1u, ib + bb + nb);
+    auto code_of = [&](uint32_t r) {
+        return ((r >> 16) << (bb + nb)) | (((r >> 8) & 0xFFu) << nb) | ((r & 0xFFu) - min_next);
+    };
+    if (hi_bits) {
+        for (auto& e : ent)
+            if (code_of(e.word) == (1u << vb) - 1u) { vb++; break; }  // the all-ones code marks an empty slot
+        if (hi_bits + vb > 32u) return 1;
+    }
+    const uint64_t buckets64 = std::max<uint64_t>(16, (uint64_t)((double)ent.size() / (4 * 0.6)) + 1);
+    if (buckets64 >= (1ull << 29)) return 1;
+    const uint32_t n_buckets = (uint32_t)buckets64;
+    auto hi_word = [&](const Ent& e) { return hi_bits ? ((e.hi << vb) | code_of(e.word)) : e.word; };
+    std::vector<uint2> table((size_t)n_buckets * 4, make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu));
+    for (auto& e : ent) {
+        uint32_t b = fq::g4_bucket(e.lo, e.hi, n_buckets);
+        while (table[(size_t)b * 4 + 3].y != 0xFFFFFFFFu) b = (b + 1u == n_buckets) ? 0u : b + 1u;  // full: next bucket
+        uint32_t j = 0;
+        while (table[(size_t)b * 4 + j].y != 0xFFFFFFFFu) j++;
+        table[(size_t)b * 4 + j] = make_uint2(e.lo, hi_word(e));
+    }
+    // histogram replicas + stash capacity within the shared-memory budget
+    const size_t smem_max = (size_t)m->geo.max_smem_optin - 1024;
+    uint32_t rep = 16;
+    while (rep > 1 && fq::probe4_smem_bytes(W, S, rep, 32) > smem_max) rep >>= 1;
+    if (fq::probe4_smem_bytes(W, S, rep, 32) > smem_max) return 1;
+    uint32_t cap = 32;
+    while (cap < 64 && fq::probe4_smem_bytes(W, S, rep, cap + 1) <= smem_max) cap++;
+    CU(cudaMalloc(&m->d_g4, table.size() * sizeof(uint2)));
+    CU(cudaMemcpy(m->d_g4, table.data(), table.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    fq::MatchParams& p = m->params;
+    p.g4_table = m->d_g4;
+    p.g4_buckets = n_buckets;
+    p.g4_himask = hi_mask;
+    p.g4_vb = vb;
+    p.g4_limit = (1u << vb) - 1u;
+    p.g4_hist_rep = rep;
+    p.g4_stash_cap = cap;
+    // measured on B200: k_probe4 wins where k_probe2 has no useful hot tier (cfg 5, W = 3: 27 -> 21 ms); with a hot
+    // tier that ends 80 % of the reads in shared memory (cfg 4) k_probe2 + this table is the faster combination
+    p.g4_kernel = (W == 3 || ck_force_np() == 1) ? 1u : 0u;
+    if (hi_bits) {  // decode fields shared with k_probe3 (which never runs for L > 16)
+        p.ck_lb = bb + nb;
+        p.ck_bsh = 8u - nb;
+        p.ck_bmask8 = ((1u << bb) - 1u) << 8;
+        p.ck_nmask = (1u << nb) - 1u;
+        p.ck_next_min = min_next;
+    }
+    m->g4_entries = ent.size();
+    return 0;
 }
 
 int build_table(fqtk_b200_matcher* m) {
@@ -511,6 +603,12 @@ int build_table(fqtk_b200_matcher* m) {
         const int rc = (W == 1) ? build_cuckoo_w<1>(m, keys, res, n) : build_cuckoo_w<2>(m, keys, res, n);
         if (rc < 0) return rc;
     }
+    // else k_probe4's L2-resident table of the same entries under compressed keys (L <= 24)
+    if (m->params.ck_np == 0 && W <= 3 && ck_force_np() != 0) {
+        const int rc = (W == 1) ? build_g4_w<1>(m, keys, res, n) : (W == 2) ? build_g4_w<2>(m, keys, res, n)
+                                                                          : build_g4_w<3>(m, keys, res, n);
+        if (rc < 0) return rc;
+    }
     return 0;
 }
 
@@ -577,7 +675,7 @@ int fqtk_b200_device_count(void) {
 
 void fqtk_b200_set_table_budget(uint64_t max_candidates) { g_table_budget = max_candidates; }
 
-void fqtk_b200_set_cuckoo_arity(int arity) { g_cuckoo_arity = (arity == 0 || arity == 2 || arity == 3) ? arity : -1; }
+void fqtk_b200_set_cuckoo_arity(int arity) { g_cuckoo_arity = (arity >= 0 && arity <= 3) ? arity : -1; }
 
 uint64_t fqtk_b200_kernel_launches(void) { return fq::kernel_launches(); }
 
@@ -704,6 +802,12 @@ int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t S, uint32_t L,
     m->params.ck_one = 1;
     m->params.ck_four = 4;
     m->params.ck_stash_cap = 32;
+    m->params.g4_table = nullptr;
+    m->params.g4_buckets = 0;
+    m->params.g4_kernel = 0;
+    m->params.g4_himask = 0;
+    m->params.g4_hist_rep = 1;
+    m->params.g4_stash_cap = 32;
     m->mode = FQTK_B200_MODE_BRUTE;
     if (use_cache && W <= (uint32_t)fq::MAX_FAST_WORDS) {
         rc = build_table(m);
@@ -737,6 +841,7 @@ void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m) {
     if (m->d_tier) cudaFree(m->d_tier);
     if (m->d_bloom) cudaFree(m->d_bloom);
     if (m->d_cuckoo) cudaFree(m->d_cuckoo);
+    if (m->d_g4) cudaFree(m->d_g4);
     if (m->d_counts) cudaFree(m->d_counts);
     delete m;
 }
@@ -758,6 +863,8 @@ int fqtk_b200_matcher_get_info(const fqtk_b200_matcher* m, fqtk_b200_matcher_inf
     info->cuckoo_entries = m->cuckoo_entries;
     info->cuckoo_probes = m->params.ck_np;
     info->cuckoo_slots = m->params.ck_words;
+    info->l2_table_entries = m->g4_entries;
+    info->l2_table_bytes = (uint64_t)m->params.g4_buckets * 32u;
     return FQTK_B200_OK;
 }
 

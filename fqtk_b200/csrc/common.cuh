@@ -118,6 +118,37 @@ FQ_HD uint32_t acgt_key(const uint32_t (&w)[W], uint32_t pad, bool& valid) {
     return k;
 }
 
+// The same for L <= 24 (W <= 3), as a (lo, hi) pair for k_probe4's 8-byte table slots: lo = the 32-bit key of words 0
+// and 1 (word 1 absent or padded for L <= 16), hi = the 2 * (L - 16) key bits of word 2, compacted to the low bits
+// (`hi_mask` keeps exactly those; 0 for W <= 2).
+template <int W>
+FQ_HD uint32_t acgt_key64(const uint32_t (&w)[W], uint32_t pad, uint32_t hi_mask, uint32_t& hi, bool& valid) {
+    static_assert(W >= 1 && W <= 3, "compressed 8-byte slots cover L <= 24");
+    if constexpr (W <= 2) {
+        hi = 0u;
+        return acgt_key<W>(w, pad, valid);
+    } else {
+        const uint32_t x0 = w[0], x1 = w[1], x2 = w[W - 1] | pad;
+        const uint32_t bad = ((x0 - 0x11111111u) & (x0 | 0x88888888u)) | ((x1 - 0x11111111u) & (x1 | 0x88888888u)) |
+                             ((x2 - 0x11111111u) & (x2 | 0x88888888u));
+        valid = bad == 0u;
+        uint32_t k2 = (x2 ^ (x2 >> 1)) & 0x33333333u;  // 2 key bits in the low half of every nibble
+        k2 = (k2 | (k2 >> 2)) & 0x0F0F0F0Fu;           // -> 4 per byte
+        k2 = (k2 | (k2 >> 4)) & 0x00FF00FFu;           // -> 8 per half-word
+        k2 = (k2 | (k2 >> 8)) & 0x0000FFFFu;           // -> 16
+        hi = k2 & hi_mask;
+        return ((x0 ^ (x0 >> 1)) & 0x33333333u) | ((x1 ^ (x1 << 1)) & 0xCCCCCCCCu);
+    }
+}
+
+// hash of a compressed key -> home bucket of k_probe4's global table (fast range over n_buckets)
+FQ_HD uint32_t g4_bucket(uint32_t lo, uint32_t hi, uint32_t n_slots) {
+    uint32_t h = lo * 0x9E3779B1u + hi * 0x85EBCA77u;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    return (uint32_t)(((uint64_t)h * (uint64_t)n_slots) >> 32);
+}
+
 // Fixed odd multipliers of the (up to three) cuckoo sub-tables: slot_i = (k * CK_MUL[i]) >> (32 - sb_i), and the low
 // 32 - sb_i bits of the same product are the remainder stored in the entry (multiplication by an odd constant is a
 // bijection of 32-bit keys, so slot + remainder identify the key exactly).

@@ -43,6 +43,19 @@ struct MatchParams {
     uint32_t ck_nmask;           // code & ck_nmask = next - ck_next_min
     uint32_t ck_next_min;
     uint32_t ck_stash_cap;       // stash entries per warp of k_probe3 (16 .. 64)
+    // k_probe4 (L <= 24): every pure-A/C/G/T memo entry under its compressed key in 8-byte slots {key lo, hi word},
+    // grouped in 32-byte BUCKETS of four (one L2 sector per probe), bucketised linear probing in GLOBAL memory at load
+    // <= 0.6, small enough to stay L2-resident.  hi word = the result word itself for L <= 16, (key hi << g4_vb) |
+    // value code (k_probe3's layout, ck_lb .. ck_next_min) for L > 16; an empty slot is all ones; the slots of a
+    // bucket fill in order, so a bucket is full iff its last slot is taken.
+    const uint2* g4_table;       // nullptr = none
+    uint32_t g4_buckets;
+    uint32_t g4_himask;          // low 2 * (L - 16) bits (0 for L <= 16)
+    uint32_t g4_vb;              // value-code bits (L > 16)
+    uint32_t g4_limit;           // 2^g4_vb - 1: the reserved (largest) code
+    uint32_t g4_hist_rep;        // histogram replicas of k_probe4 (power of two <= 16)
+    uint32_t g4_stash_cap;       // stash entries per warp of k_probe4
+    uint32_t g4_kernel;          // 1: the packed route runs k_probe4; 0: k_probe2, whose queue phase probes this table
     uint32_t ck_one, ck_four;    // 1 and 4 (see Probe3Ctx in match_kernels.cu)
 };
 
@@ -105,6 +118,7 @@ cudaError_t launch_route(const uint32_t* d_results, uint64_t n, uint32_t S, uint
 cudaError_t prepare_kernels(const LaunchGeometry& g);  // opt-in shared memory attributes, once per device
 
 size_t probe3_smem_bytes(uint32_t ck_words, uint32_t S, uint32_t stash_cap);
+size_t probe4_smem_bytes(uint32_t W, uint32_t S, uint32_t hist_rep, uint32_t stash_cap);
 size_t probe2_fixed_smem_bytes(uint32_t W, uint32_t S, int threads);  // k_probe2 shared memory besides tier + Bloom
 int probe2_threads();
 uint32_t probe2_hist_rep(uint32_t S);

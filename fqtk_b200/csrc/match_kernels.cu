@@ -416,6 +416,85 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe(const MatchParams p, co
     cnt.flush();
 }
 
+// ---- k_probe4's L2-resident table of compressed keys (kernels.h); also probed by k_probe2's queue phase ----
+// hi word of a slot -> result word
+template <int W>
+FQ_D uint32_t g4_decode(const MatchParams& p, uint32_t hi_word) {
+    if constexpr (W <= 2) {
+        return hi_word;
+    } else {
+        const uint32_t u = hi_word & p.g4_limit;
+        const uint32_t idx = u >> p.ck_lb;
+        const uint32_t low = ((u << p.ck_bsh) & p.ck_bmask8) | (u & p.ck_nmask);
+        return idx * 65536u + low + p.ck_next_min;
+    }
+}
+// L2 eviction-priority policies: the table must survive the read / result stream that flows through L2 next to it
+FQ_D uint64_t l2_policy_keep() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+FQ_D uint64_t l2_policy_stream() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+FQ_D uint4 ldg_hint(const uint4* ptr, uint64_t pol) {
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(ptr), "l"(pol));
+    return v;
+}
+FQ_D void stg_hint(uint4* ptr, const uint4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w), "l"(pol)
+                 : "memory");
+}
+
+// One 32-byte bucket = four slots {key lo, hi word}
+struct G4Bucket {
+    uint4 a, b;  // slots 0,1 | slots 2,3
+};
+FQ_D G4Bucket g4_load(const MatchParams& p, uint32_t bucket, uint64_t pol) {
+    const uint4* q = reinterpret_cast<const uint4*>(p.g4_table) + (size_t)bucket * 2;
+    G4Bucket e;
+    e.a = ldg_hint(q, pol);
+    e.b = ldg_hint(q + 1, pol);
+    return e;
+}
+template <int W>
+FQ_D bool g4_slot_hit(const MatchParams& p, uint32_t slot_lo, uint32_t slot_hi, uint32_t lo, uint32_t hi) {
+    if constexpr (W <= 2) {
+        return slot_lo == lo && slot_hi != 0xFFFFFFFFu;
+    } else {
+        return slot_lo == lo && (slot_hi >> p.g4_vb) == hi && slot_hi != 0xFFFFFFFFu;
+    }
+}
+// hi word of the matching slot, or 0xFFFFFFFF
+template <int W>
+FQ_D uint32_t g4_search(const MatchParams& p, const G4Bucket& e, uint32_t lo, uint32_t hi) {
+    uint32_t v = 0xFFFFFFFFu;
+    v = g4_slot_hit<W>(p, e.a.x, e.a.y, lo, hi) ? e.a.y : v;
+    v = g4_slot_hit<W>(p, e.a.z, e.a.w, lo, hi) ? e.a.w : v;
+    v = g4_slot_hit<W>(p, e.b.x, e.b.y, lo, hi) ? e.b.y : v;
+    v = g4_slot_hit<W>(p, e.b.z, e.b.w, lo, hi) ? e.b.w : v;
+    return v;
+}
+// Full lookup of one key from its (already loaded) home bucket: walks on only when the bucket is full and has no match.
+template <int W>
+FQ_D uint32_t g4_lookup(const MatchParams& p, G4Bucket e, uint32_t bucket, uint32_t lo, uint32_t hi, bool valid,
+                        uint64_t pol) {
+    uint32_t v = g4_search<W>(p, e, lo, hi);
+    while (valid && v == 0xFFFFFFFFu && e.b.w != 0xFFFFFFFFu) {  // full bucket without the key: it may have overflowed
+        bucket = (bucket + 1u == p.g4_buckets) ? 0u : bucket + 1u;
+        e = g4_load(p, bucket, pol);
+        v = g4_search<W>(p, e, lo, hi);
+    }
+    return valid ? v : 0xFFFFFFFFu;
+}
+
 // k_probe2: the HBM-resident packed route.  A warp owns tiles of 128 consecutive reads, four per lane
 // (W x LDG.128 in, one STG.128 out), and resolves them through three tiers:
 //   1. hot tier in SHARED memory: the table entries whose best distance is 0 (the barcodes themselves and their
@@ -542,6 +621,7 @@ __global__ void __launch_bounds__(PROBE2_THREADS, 1) k_probe2(const MatchParams 
     const uint32_t hshift = 2u + (uint32_t)__popc(hrep - 1u);
     const uint32_t a_tvals = smem_addr(s_tvals), a_bloom = smem_addr(s_bloom);
     asm volatile("" : "+r"(a_tier), "+r"(a_qk), "+r"(a_hist));  // keep them in registers
+    const uint64_t pol_keep = l2_policy_keep();
     const uint32_t tshift = p.tier_shift;  // 32 - log2(tier_slots)
     const bool has_tier = tshift < 32u;
     uint32_t none_count = 0;
@@ -641,8 +721,22 @@ __global__ void __launch_bounds__(PROBE2_THREADS, 1) k_probe2(const MatchParams 
                     const uint32_t bm = bloom_mask(h);
                     maybe = (lds32_ro(a_bloom + (h >> p.bloom_shift) * 4u) & bm) == bm;
                 }
-                if (maybe) table_lookup<W>(p, kw, h, out);
-                slow = out == NONE && !read_in_table_alphabet<W>(kw, p.last_pad);
+                bool in_g4 = false;  // pure A/C/G/T read and a compact table of those entries exists: one L2 sector decides
+                if constexpr (W <= 3) {
+                    if (p.g4_table != nullptr) {
+                        uint32_t khi;
+                        const uint32_t klo = acgt_key64<W>(kw, p.last_pad, p.g4_himask, khi, in_g4);
+                        if (in_g4 && maybe) {
+                            const uint32_t b0 = g4_bucket(klo, khi, p.g4_buckets);
+                            const uint32_t v = g4_lookup<W>(p, g4_load(p, b0, pol_keep), b0, klo, khi, true, pol_keep);
+                            if (v != 0xFFFFFFFFu) out = g4_decode<W>(p, v);
+                        }
+                    }
+                }
+                if (!in_g4) {
+                    if (maybe) table_lookup<W>(p, kw, h, out);
+                    slow = out == NONE && !read_in_table_alphabet<W>(kw, p.last_pad);
+                }
             }
             uint32_t pending = __ballot_sync(0xFFFFFFFFu, slow);
             while (pending) {
@@ -1059,6 +1153,188 @@ __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ M
 }
 
 // ------------------------------------------------------------------------------------------------------
+// k_probe4: the HBM-resident packed route for panels whose pure-A/C/G/T memo entries do not fit in shared memory
+// (cfg 4: 1 536 samples at 2 mismatches; cfg 5: 6 144 IUPAC samples of 20 bases).  Same structure as k_probe3 —
+// compressed key + validity, unconditional histogram atomic, odd reads parked in a per-warp stash and resolved a
+// warp-full at a time through the full memo table — but the lookup goes to a GLOBAL table of 8-byte slots
+// {key lo, hi word} that is 4 - 5 x smaller than the memo table (compressed keys, no N-containing entries) and so
+// stays L2-resident while the reads stream through (table loads carry an L2 evict_last policy, the read / result
+// stream evict_first).  Slots come four to a 32-byte bucket — one L2 sector per probe — and a lane has two home
+// buckets in flight at a time; only a full bucket without the key is followed by the next one (load <= 0.6: rare).
+// A valid read that is not in the table is None.
+// ------------------------------------------------------------------------------------------------------
+constexpr int PROBE4_THREADS = 1024;
+constexpr int PROBE4_R = 4;
+
+struct Probe4Ctx {
+    uint32_t a_hist;   // shared-window address of this lane's histogram replica
+    uint32_t a_stash;  // ... of this warp's stash: g4_stash_cap keys (W words each), then as many read indices
+};
+
+FQ_D void hist4_add(const MatchParams& p, const Probe4Ctx& c, uint32_t bin, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(imad(bin, p.g4_hist_rep * 4u, c.a_hist)), "r"(v) : "memory");
+}
+
+template <int W>
+__device__ __noinline__ void probe4_drain(const MatchParams& p, const Probe4Ctx c, uint32_t cnt,
+                                          uint32_t* __restrict__ results, uint32_t lane) {
+    __syncwarp();
+    const uint32_t a_idx = c.a_stash + p.g4_stash_cap * (W * 4u);
+    for (uint32_t b = 0; b < cnt; b += 32u) {
+        const uint32_t e = b + lane;
+        const bool act = e < cnt;
+        uint32_t kw[W];
+        uint32_t idx = 0;
+#pragma unroll
+        for (int k = 0; k < W; k++) kw[k] = act ? lds32(c.a_stash + (e * W + k) * 4u) : 0u;
+        if (act) idx = lds32(a_idx + e * 4u);
+        const uint32_t out = slow_resolve<W>(p, kw, act, lane);
+        if (act && out != NONE) {  // it was written as None and counted as unmatched when it was parked
+            results[idx] = out;
+            hist4_add(p, c, out >> 16, 1u);
+            hist4_add(p, c, p.S, 0xFFFFFFFFu);
+        }
+    }
+    __syncwarp();
+}
+
+template <int W, bool PAD>
+__global__ void __launch_bounds__(PROBE4_THREADS, 1) k_probe4(const __grid_constant__ MatchParams p, const ReadSource src,
+                                                             uint32_t* __restrict__ results) {
+    constexpr int R = PROBE4_R;
+    extern __shared__ uint4 s_dyn[];
+    // layout: histogram replicas | per-warp stashes
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_dyn);
+    const uint32_t hrep = p.g4_hist_rep;
+    for (uint32_t t = threadIdx.x; t < (p.S + 1u) * hrep; t += blockDim.x) s_hist[t] = 0u;
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_warps = blockDim.x >> 5, warp_in_cta = threadIdx.x >> 5;
+    Probe4Ctx c;
+    c.a_hist = smem_addr(s_hist) + (lane & (hrep - 1u)) * 4u;
+    c.a_stash = smem_addr(s_hist + (p.S + 1u) * hrep) + warp_in_cta * (p.g4_stash_cap * (W * 4u + 4u));
+    const uint32_t pad = PAD ? p.last_pad : 0u;
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    uint32_t cnt = 0;  // reads parked in the warp's stash (warp-uniform)
+    const uint64_t pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
+
+    constexpr uint32_t TILE = 32u * R;
+    constexpr int NV = R * W / 4;  // 16-byte vectors per lane per tile
+    const uint32_t n_tiles = (uint32_t)(src.n / (uint64_t)TILE);
+    const uint32_t stride = gridDim.x * n_warps;
+    for (uint32_t tile = blockIdx.x * n_warps + warp_in_cta; tile < n_tiles; tile += stride) {
+        // the tile after next is requested from L2 now (one TMA bulk prefetch by one lane); this tile's words were
+        // requested two iterations ago, so the loads below are L2 hits
+        if (lane == 0u && tile + 2u * stride < n_tiles) {
+            const uint32_t* ptr = src.packed + (size_t)(tile + 2u * stride) * (TILE * W);
+            asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(ptr), "r"(TILE * W * 4u),
+                         "l"(pol_stream)
+                         : "memory");
+        }
+        const uint32_t g = tile * 32u + lane;  // this lane's group of R consecutive reads
+        uint32_t flat[R * W];
+        {
+            const uint4* in = reinterpret_cast<const uint4*>(src.packed) + (size_t)g * NV;
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                const uint4 q = ldg_hint(in + v, pol_stream);
+                flat[4 * v + 0] = q.x; flat[4 * v + 1] = q.y; flat[4 * v + 2] = q.z; flat[4 * v + 3] = q.w;
+            }
+        }
+        uint32_t lo[R], hi[R], bucket[R];
+        bool valid[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            uint32_t kw[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) kw[k] = flat[r * W + k];
+            lo[r] = acgt_key64<W>(kw, pad, p.g4_himask, hi[r], valid[r]);
+            bucket[r] = g4_bucket(lo[r], hi[r], p.g4_buckets);
+        }
+        uint32_t res[R];
+        bool all_valid = true;
+#pragma unroll
+        for (int h = 0; h < R; h += 2) {  // two home buckets (2 x 32 bytes) in flight per lane at a time
+            const G4Bucket e0 = g4_load(p, bucket[h], pol_keep), e1 = g4_load(p, bucket[h + 1], pol_keep);
+            const uint32_t v0 = g4_lookup<W>(p, e0, bucket[h], lo[h], hi[h], valid[h], pol_keep);
+            const uint32_t v1 = g4_lookup<W>(p, e1, bucket[h + 1], lo[h + 1], hi[h + 1], valid[h + 1], pol_keep);
+            res[h] = v0 != 0xFFFFFFFFu ? g4_decode<W>(p, v0) : NONE;
+            res[h + 1] = v1 != 0xFFFFFFFFu ? g4_decode<W>(p, v1) : NONE;
+            hist4_add(p, c, v0 != 0xFFFFFFFFu ? (res[h] >> 16) : p.S, 1u);
+            hist4_add(p, c, v1 != 0xFFFFFFFFu ? (res[h + 1] >> 16) : p.S, 1u);
+            all_valid = all_valid && valid[h] && valid[h + 1];
+        }
+        uint4* out4 = reinterpret_cast<uint4*>(results) + (size_t)g * (R / 4);
+#pragma unroll
+        for (int v = 0; v < R / 4; v++)
+            stg_hint(out4 + v, make_uint4(res[4 * v], res[4 * v + 1], res[4 * v + 2], res[4 * v + 3]), pol_stream);
+        if (__any_sync(0xFFFFFFFFu, !all_valid)) {
+            // every pass parks each lane's first read that is not pure A/C/G/T (lanes rarely have two)
+            uint32_t bad = 0u;
+#pragma unroll
+            for (int r = 0; r < R; r++) bad |= valid[r] ? 0u : (1u << r);
+            do {
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, bad != 0u);
+                const uint32_t n_new = (uint32_t)__popc(bal);
+                if (cnt + n_new > p.g4_stash_cap) {  // no room (g4_stash_cap >= 32): resolve what is parked first
+                    probe4_drain<W>(p, c, cnt, results, lane);
+                    cnt = 0u;
+                }
+                if (bad) {
+                    const uint32_t r = (uint32_t)__ffs(bad) - 1u;
+                    const uint32_t pos = cnt + (uint32_t)__popc(bal & lane_lt);
+#pragma unroll
+                    for (int k = 0; k < W; k++) {
+                        uint32_t wk = flat[k];
+#pragma unroll
+                        for (int q = 1; q < R; q++) wk = (r == (uint32_t)q) ? flat[q * W + k] : wk;
+                        sts32(c.a_stash + (pos * W + k) * 4u, wk);
+                    }
+                    sts32(c.a_stash + p.g4_stash_cap * (W * 4u) + pos * 4u, g * R + r);
+                    bad &= bad - 1u;
+                }
+                cnt += n_new;
+            } while (__any_sync(0xFFFFFFFFu, bad != 0u));
+        }
+    }
+    probe4_drain<W>(p, c, cnt, results, lane);
+
+    // ---- tail: fewer than a tile of reads, one per lane, first warp of the grid ----
+    if (blockIdx.x == 0 && threadIdx.x < 32u) {
+        for (uint64_t b0 = (uint64_t)n_tiles * TILE; b0 < src.n; b0 += 32u) {
+            const uint64_t i = b0 + lane;
+            const bool live = i < src.n;
+            uint32_t w1[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) w1[k] = live ? __ldg(src.packed + i * W + k) : 0u;
+            bool valid;
+            uint32_t hi1;
+            const uint32_t lo1 = acgt_key64<W>(w1, pad, p.g4_himask, hi1, valid);
+            uint32_t out = NONE;
+            {
+                const uint32_t b1 = g4_bucket(lo1, hi1, p.g4_buckets);
+                const uint32_t v1 = g4_lookup<W>(p, g4_load(p, b1, pol_keep), b1, lo1, hi1, live && valid, pol_keep);
+                if (v1 != 0xFFFFFFFFu) out = g4_decode<W>(p, v1);
+            }
+            const uint32_t slow = slow_resolve<W>(p, w1, live && !valid, lane);
+            if (live) {
+                if (!valid) out = slow;
+                results[i] = out;
+                hist4_add(p, c, out == NONE ? p.S : (out >> 16), 1u);
+            }
+        }
+    }
+    // ---- flush the replicated bins (bin S = unmatched) ----
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b <= p.S; b += blockDim.x) {
+        uint32_t v = 0;
+        for (uint32_t r = 0; r < hrep; r++) v += s_hist[b * hrep + r];
+        if (v) atomicAdd(&p.counts[b], (unsigned long long)v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // k_pack: encode() for a batch (mod.rs:49-61), any L
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_pack(const uint8_t* __restrict__ ascii, uint64_t n, uint32_t L,
@@ -1262,6 +1538,30 @@ static cudaError_t launch_probe3_wnp(const MatchParams& p, const ReadSource& src
     }
 }
 
+size_t probe4_smem_bytes(uint32_t W, uint32_t S, uint32_t hist_rep, uint32_t stash_cap) {
+    return (size_t)(S + 1u) * hist_rep * 4 + (size_t)(PROBE4_THREADS / 32) * stash_cap * (W * 4 + 4);
+}
+
+template <int W>
+static cudaError_t launch_probe4_w(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
+                                   const LaunchGeometry& g, cudaStream_t stream) {
+    const size_t smem = probe4_smem_bytes(W, p.S, p.g4_hist_rep, p.g4_stash_cap);
+    const uint64_t n_warp_tiles = (src.n + 32 * PROBE4_R - 1) / (32 * PROBE4_R);
+    const uint64_t want = (n_warp_tiles + PROBE4_THREADS / 32 - 1) / (PROBE4_THREADS / 32);
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)g.sm_count));
+    if (p.last_pad) {
+        auto k = k_probe4<W, true>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, PROBE4_THREADS, smem, stream>>>(p, src, d_results);
+    } else {
+        auto k = k_probe4<W, false>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, PROBE4_THREADS, smem, stream>>>(p, src, d_results);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
 template <int W, int NP>
 static cudaError_t launch_probe3_wn(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
                                     const LaunchGeometry& g, cudaStream_t stream) {
@@ -1280,6 +1580,14 @@ cudaError_t launch_probe(const MatchParams& p, const ReadSource& src, uint32_t* 
                                           : launch_probe3_wn<1, 3>(p, src, d_results, g, stream);
         return p.ck_np == 2 ? launch_probe3_wn<2, 2>(p, src, d_results, g, stream)
                             : launch_probe3_wn<2, 3>(p, src, d_results, g, stream);
+    }
+    if (!ascii && p.g4_table && p.g4_kernel && p.W <= 3u &&
+        ((reinterpret_cast<uintptr_t>(src.packed) | reinterpret_cast<uintptr_t>(d_results)) & 15u) == 0u) {
+        switch (p.W) {
+            case 1: return launch_probe4_w<1>(p, src, d_results, g, stream);
+            case 2: return launch_probe4_w<2>(p, src, d_results, g, stream);
+            default: return launch_probe4_w<3>(p, src, d_results, g, stream);
+        }
     }
     if (ascii) {
         switch (p.W) {

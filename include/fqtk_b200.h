@@ -78,6 +78,8 @@ typedef struct {
     uint64_t cuckoo_entries;     /* pure-A/C/G/T memo entries held in the shared-memory cuckoo table (0 = none) */
     uint32_t cuckoo_probes;      /* sub-tables = probes per read (2 or 3) */
     uint32_t cuckoo_slots;       /* 4-byte slots over all sub-tables */
+    uint64_t l2_table_entries;   /* pure-A/C/G/T memo entries in the compressed 8-byte-slot table of k_probe4 (0 = none) */
+    uint64_t l2_table_bytes;
 } fqtk_b200_matcher_info;
 
 /* ---- lifecycle -------------------------------------------------------------------------------------
@@ -93,9 +95,11 @@ FQTK_B200_API int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t 
 FQTK_B200_API void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m);
 FQTK_B200_API int fqtk_b200_matcher_get_info(const fqtk_b200_matcher* m, fqtk_b200_matcher_info* info);
 FQTK_B200_API void fqtk_b200_set_table_budget(uint64_t max_candidates);
-/* Tuning / test knob for matchers created afterwards: shared-memory cuckoo table of the pure-A/C/G/T memo entries
- * (k_probe3, L <= 16): -1 = automatic (default), 0 = none (the packed route runs k_probe2), 2 or 3 = force that many
- * sub-tables.  Results are identical for every setting. */
+/* Tuning / test knob for matchers created afterwards — which kernel the HBM-resident packed route runs:
+ * -1 = automatic (default): k_probe3 (shared-memory cuckoo table of the pure-A/C/G/T memo entries) when it fits
+ *      (L <= 16), else k_probe4 (the same entries in an L2-resident table of 8-byte slots, L <= 24), else k_probe2;
+ *  0 = k_probe2 only;  1 = k_probe4's table only;  2 or 3 = k_probe3 with that many sub-tables.
+ * Results are identical for every setting. */
 FQTK_B200_API void fqtk_b200_set_cuckoo_arity(int arity);
 
 /* ---- reference-facing calls: HOST buffers ----------------------------------------------------------

@@ -255,10 +255,11 @@ def test_configs_reduced_n(cfg_id, n, use_cache):
                          expect_mode="table" if use_cache else "brute")
 
 
-@pytest.mark.parametrize("arity", [0, 2, 3])
+@pytest.mark.parametrize("arity", [0, 1, 2, 3])
 def test_packed_route_kernel_variants(arity):
-    """The HBM-resident packed route has two kernels for L <= 16: k_probe3 (shared-memory cuckoo table of the pure
-    A/C/G/T memo entries, 2 or 3 sub-tables) and k_probe2 (hot tier + global memo table; arity 0).  All bit-exact."""
+    """The HBM-resident packed route has three kernels: k_probe3 (shared-memory cuckoo table of the pure A/C/G/T memo
+    entries, 2 or 3 sub-tables, L <= 16), k_probe4 (the same entries in an L2-resident table of 8-byte slots, L <= 24;
+    knob 1) and k_probe2 (hot tier + global memo table; knob 0).  All bit-exact."""
     torch = torch_cuda()
     L = _lib.lib()
     rng = np.random.default_rng(4242 + arity)
@@ -269,14 +270,26 @@ def test_packed_route_kernel_variants(arity):
             panel = synth.panel(cfg)
             bcs = [bytes(r) for r in panel]
             with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, True) as m:
-                assert int(m.info().cuckoo_probes) == arity
-                assert (int(m.info().cuckoo_entries) > 0) == (arity != 0)
+                assert int(m.info().cuckoo_probes) == (arity if arity >= 2 else 0)
+                assert (int(m.info().cuckoo_entries) > 0) == (arity >= 2)
+                assert (int(m.info().l2_table_entries) > 0) == (arity == 1)
             reads = synth.reads_host(panel, cfg.seed_reads, 31, n)
             reads[::41, 3] = ord("N")
             reads[::97, 1] = ord("r")
             check_against_oracle(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, reads, True, expect_mode="table")
-        for _ in range(16):  # pad nibbles (L % 8 != 0), one-word and two-word keys, dirty reads, odd parameters
-            Lb = int(rng.choice([1, 2, 3, 7, 8, 9, 12, 15, 16]))
+        if arity in (0, 1):  # the big-table configs on their own kernels (k_probe4 by default), and on k_probe2
+            for cfg_id, n in [(4, 120_000), (5, 80_000)]:
+                cfg = synth.CONFIGS[cfg_id]
+                panel = synth.panel(cfg)
+                bcs = [bytes(r) for r in panel]
+                reads = synth.reads_host(panel, cfg.seed_reads, 77, n)
+                reads[::37, 2] = ord("N")
+                reads[::101, 5] = ord("y")
+                with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, True) as m:
+                    assert (int(m.info().l2_table_entries) > 0) == (arity == 1)
+                check_against_oracle(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, reads, True, expect_mode="table")
+        for _ in range(16):  # pad nibbles (L % 8 != 0), one- to three-word keys, dirty reads, odd parameters
+            Lb = int(rng.choice([1, 2, 3, 7, 8, 9, 12, 15, 16, 17, 20, 23, 24]))
             S = int(rng.choice([1, 2, 5, 40, 300]))
             pa = ALPHABETS[["acgt", "acgtn", "iupac"][int(rng.integers(0, 3))]]
             ra = ALPHABETS[["acgt", "acgtn", "dirty"][int(rng.integers(0, 3))]]
