@@ -180,3 +180,25 @@ def test_demux_metrics_follow_the_reference_update_rule(tmp_path):
     # an empty run divides by zero the way f64 does in the reference (NaN), it does not raise
     rows = demux_metrics(["a"], ["AAAA"], [0, 0])
     assert rows[0].frac_templates != rows[0].frac_templates
+
+
+def test_write_header_reference_kats(kats):
+    """ReadSet::write_header_internal (demux.rs:171-267) against the reference's own six tests (:2084-2196)."""
+    from fqtk_b200.headers import HeaderError, write_header
+
+    for case in kats["write_header"]:
+        args = (case["read_num"], case["header"].encode(), [b.encode() for b in case["sample_barcodes"]],
+                [u.encode() for u in case["umis"]])
+        if "expect_error" in case:
+            with pytest.raises(HeaderError, match=case["expect_error"]):
+                write_header(*args)
+        else:
+            assert write_header(*args).decode() == case["expect"], case["source"]
+    # branches the reference tests do not reach, derived from the code: two UMI segments, a five-part comment,
+    # a three-part comment that already ends in ':', a barcode kept when the comment does not end in a digit
+    assert write_header(1, b"q1", [b"AC"], [b"GG", b"TT"]) == b"@q1:GG+TT 1:N:0:AC"
+    with pytest.raises(HeaderError, match="4 segments"):
+        write_header(1, b"q1 1:N:0:1:2", [b"AC"])
+    assert write_header(1, b"q1 a:b:", [b"AC"]) == b"@q1 a:b:AC"
+    assert write_header(2, b"q1 1:N:0:GATC", [b"AC"]) == b"@q1 2:N:0:GATC+AC"
+    assert write_header(2, b"q1 1:N:0:", [b"AC"]) == b"@q1 2:N:0:AC"
