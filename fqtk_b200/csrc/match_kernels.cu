@@ -823,7 +823,7 @@ __global__ void __launch_bounds__(PROBE2_THREADS, 1) k_probe2(const MatchParams 
 //     such read) and resolved a warp-full at a time through the global memo table (which also holds the N-containing
 //     neighbours) or, outside its alphabet, the warp-cooperative scan; the result word and the counts are patched.
 // Per-sample counts: lane-private (conflict-free) shared-memory histogram of packed 16-bit counters, one unconditional
-// atomic per read, flushed to the global u64 table under a barrier every PROBE3_FLUSH_ROUNDS rounds.
+// atomic per read, flushed to the global u64 table under a barrier every PROBE3_FLUSH_READS reads per lane.
 // The kernel is bound by instruction issue and the SM's integer pipes, so adds and address computations on the hot
 // path are written as multiply-adds with an operand read from the kernel parameters (IMAD, fma pipe) and only the
 // logic ops, shifts, compares and selects stay on the alu pipe (both issue one warp instruction per 2 clocks).
@@ -840,7 +840,7 @@ struct Probe3Ctx {
 
 FQ_D uint32_t imad(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
 FQ_HD uint32_t probe3_unmatched_bin(uint32_t S) { return S | 1u; }  // smallest odd index >= S (see hist_inc)
-FQ_HD uint32_t probe3_hist_words(uint32_t S) { return ((probe3_unmatched_bin(S) + 1u) / 2u) * 32u; }
+FQ_HD uint32_t probe3_hist_words(uint32_t S) { return ((probe3_unmatched_bin(S) + 1u) / 2u) * 32u; }  // the columns
 
 // Compressed key + validity of one read: acgt_key (common.cuh), with the subtractions and the left shift on the fma pipe.
 template <int W, bool PAD>
@@ -901,26 +901,29 @@ FQ_D uint32_t slow_resolve(const MatchParams& p, const uint32_t (&kw)[W], bool a
 }
 
 // Packed histogram: 32 lane-private columns (bank = lane: no conflicts), two 16-bit counters per word; bin b is the
-// (b & 1) half of word b >> 1.  The unmatched bin U is the smallest ODD index >= S, i.e. always a high half, so that
-// taking one away (adding 0xFFFF0000) cannot carry into a neighbour.  The CTA flushes the counters to the global
-// u64 table every PROBE3_FLUSH_ROUNDS rounds, under a barrier, long before a 16-bit field can wrap.
+// (b & 1) half of word b >> 1.  Fields only ever grow: a parked read that turns out to match is counted in its
+// sample's bin when it is resolved and tallied in one extra word (`fix`, right after the columns), which the flush
+// takes off the unmatched total.  The CTA flushes the counters to the global u64 table every PROBE3_FLUSH_READS
+// reads per lane, under a barrier, long before a 16-bit field can wrap: a field gains at most (32 warps) x (reads per
+// lane, counted once and re-counted at most once) = 64 per read per lane.
+constexpr uint32_t PROBE3_FLUSH_READS = 512;  // 512 * 64 = 32768 < 65536
 FQ_D void hist_inc(const MatchParams& p, const Probe3Ctx& c, uint32_t bin) {
     const uint32_t addr = imad(bin & ~1u, p.ck_four * 16u, c.a_hist);  // (bin >> 1) * 128
     const uint32_t val = imad(bin & 1u, 65535u, p.ck_one);             // 1 or 65536
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
 }
-FQ_D void hist_unmatched_dec(const MatchParams& p, const Probe3Ctx& c) {
-    const uint32_t addr = c.a_hist + (probe3_unmatched_bin(p.S) >> 1) * 128u;
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(0xFFFF0000u) : "memory");
+FQ_D void hist_unmatched_dec(const MatchParams& p, const Probe3Ctx& c) {  // cold path
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t addr = c.a_hist - lane * 4u + probe3_hist_words(p.S) * 4u;  // the `fix` word
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
 }
-// a 16-bit field gains at most (32 warps) x (2 tiles x 4 reads, counted once and re-counted at most once) per round
-constexpr uint32_t PROBE3_FLUSH_ROUNDS = 64;  // 64 * 32 * 16 = 32768 < 65536
 
 // all threads of the CTA: add the packed counters to the global table and zero them
 FQ_D void probe3_flush_hist(const MatchParams& p, uint32_t* s_hist) {
     __syncthreads();
     const uint32_t U = probe3_unmatched_bin(p.S);
     const uint32_t n_words = (U + 1u) / 2u;
+    uint32_t* s_fix = s_hist + n_words * 32u;
     for (uint32_t wd = threadIdx.x; wd < n_words; wd += blockDim.x) {
         uint32_t lo = 0, hi = 0;
         for (uint32_t r = 0; r < 32u; r++) {
@@ -930,11 +933,13 @@ FQ_D void probe3_flush_hist(const MatchParams& p, uint32_t* s_hist) {
             lo += v & 0xFFFFu;
             hi += v >> 16;
         }
-        lo &= 0xFFFFu;  // fields are sums modulo 2^16 (the unmatched one may have borrowed in single columns)
-        hi &= 0xFFFFu;
         const uint32_t b0 = 2u * wd, b1 = 2u * wd + 1u;
+        if (b1 >= p.S) {  // the word of the unmatched bin: take off the parked reads that were matched after all
+            hi -= *s_fix;
+            *s_fix = 0u;
+        }
         if (lo && b0 < p.S) atomicAdd(&p.counts[b0], (unsigned long long)lo);
-        if (hi) atomicAdd(&p.counts[b1 < p.S ? b1 : p.S], (unsigned long long)hi);  // b1 >= S only for the unmatched bin
+        if (hi) atomicAdd(&p.counts[b1 < p.S ? b1 : p.S], (unsigned long long)hi);
     }
     __syncthreads();
 }
@@ -1078,7 +1083,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ M
         uint4* s4 = reinterpret_cast<uint4*>(s_ck);
         for (uint32_t t = threadIdx.x; t < p.ck_words / 4u; t += blockDim.x) s4[t] = __ldg(g4 + t);
     }
-    for (uint32_t t = threadIdx.x; t < n_hist_words; t += blockDim.x) s_hist[t] = 0u;
+    for (uint32_t t = threadIdx.x; t < n_hist_words + 4u; t += blockDim.x) s_hist[t] = 0u;  // columns + the fix word
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31u;
@@ -1087,7 +1092,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ M
 #pragma unroll
     for (int i = 0; i < 3; i++) c.base[i] = smem_addr(s_ck) + p.ck_off[i < NP ? i : 0] * 4u;
     c.a_hist = smem_addr(s_hist) + lane * 4u;
-    c.a_stash = smem_addr(s_hist + n_hist_words) + warp_in_cta * (p.ck_stash_cap * 12u);
+    c.a_stash = smem_addr(s_hist + n_hist_words + 4u) + warp_in_cta * (p.ck_stash_cap * 12u);
     asm volatile("" : "+r"(c.base[0]), "+r"(c.base[1]), "+r"(c.base[2]), "+r"(c.a_hist));
     uint32_t cnt = 0;  // reads parked in the warp's stash (warp-uniform)
 
@@ -1118,7 +1123,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ M
                 tile = nt;
             }
         }
-        if ((round + 1u) % PROBE3_FLUSH_ROUNDS == 0u) {
+        if ((round + 1u) % (PROBE3_FLUSH_READS / (2u * R)) == 0u) {
             probe3_drain<W>(p, c, cnt, results, lane);
             cnt = 0u;
             probe3_flush_hist(p, s_hist);
@@ -1495,20 +1500,17 @@ static cudaError_t launch_probe2_w(const MatchParams& p, const ReadSource& src, 
 
 constexpr uint32_t PROBE3_MAX_WARPS = 32;
 size_t probe3_smem_bytes(uint32_t ck_words, uint32_t S, uint32_t stash_cap) {
-    return (size_t)ck_words * 4 + (size_t)probe3_hist_words(S) * 4 +
+    return (size_t)ck_words * 4 + (size_t)probe3_hist_words(S) * 4 + 16 +
            (size_t)PROBE3_MAX_WARPS * stash_cap * 12;
 }
 
-// launch shape of k_probe3: FQTK_B200_P3_SHAPE = "<reads per lane>x<threads>" (4x1024 | 4x768 | 8x768 | 8x512), for A/B timing
+// launch shape of k_probe3: 1024 threads (the kernel needs all 32 resident warps: 768 / 512 threads measured 10 - 30 %
+// slower); 4 reads per lane for two-word keys, 8 for one-word keys (same register footprint; cfg 2: 0.204 -> 0.193 ms).
+// FQTK_B200_P3_SHAPE=4x1024 (A/B timing) forces 4 reads per lane.
 static int probe3_shape() {
     static const int v = [] {
         const char* e = getenv("FQTK_B200_P3_SHAPE");
-        if (!e) return 0;
-        if (!strcmp(e, "4x1024")) return 0;
-        if (!strcmp(e, "4x768")) return 1;
-        if (!strcmp(e, "8x768")) return 2;
-        if (!strcmp(e, "8x512")) return 3;
-        return 0;
+        return (e && !strcmp(e, "4x1024")) ? 1 : 0;
     }();
     return v;
 }
@@ -1530,12 +1532,10 @@ static cudaError_t launch_probe3_shape(const MatchParams& p, const ReadSource& s
 template <int W, int NP, bool PAD>
 static cudaError_t launch_probe3_wnp(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
                                      const LaunchGeometry& g, cudaStream_t stream) {
-    switch (probe3_shape()) {
-        case 1: return launch_probe3_shape<W, NP, PAD, 4, 768>(p, src, d_results, g, stream);
-        case 2: return launch_probe3_shape<W, NP, PAD, 8, 768>(p, src, d_results, g, stream);
-        case 3: return launch_probe3_shape<W, NP, PAD, 8, 512>(p, src, d_results, g, stream);
-        default: return launch_probe3_shape<W, NP, PAD, 4, 1024>(p, src, d_results, g, stream);
+    if constexpr (W == 1) {  // same register footprint as two-word keys at 4 reads per lane
+        if (probe3_shape() == 0) return launch_probe3_shape<W, NP, PAD, 8, 1024>(p, src, d_results, g, stream);
     }
+    return launch_probe3_shape<W, NP, PAD, 4, 1024>(p, src, d_results, g, stream);
 }
 
 size_t probe4_smem_bytes(uint32_t W, uint32_t S, uint32_t hist_rep, uint32_t stash_cap) {

@@ -373,6 +373,41 @@ def test_configs_full_size_properties(cfg_id):
         assert torch.equal(res_t, res_b)
 
 
+def test_mostly_unmatched_stream_at_size():
+    """Counter plumbing under a skewed stream: 300 M reads of which more than half match nothing (reads drawn from a
+    DIFFERENT panel), so the unmatched bin of every CTA runs far past 2^16 between two histogram flushes of k_probe3,
+    and the no-call reads among them are parked and come back unmatched.  Table kernels == brute kernels read for
+    read, counts == histogram of the result words."""
+    torch = torch_cuda()
+    cfg = synth.CONFIGS[3]
+    panel = synth.panel(cfg)
+    other = synth.make_panel(0xBEEF, cfg.n_samples, cfg.barcode_len, 3)
+    bcs = [bytes(r) for r in panel]
+    n = 300_000_000
+    W = cfg.words_per_read
+    stream = torch.cuda.current_stream().cuda_stream
+    d_packed = torch.empty((n, W), dtype=torch.int32, device="cuda")
+    k = n * 2 // 5
+    synth.reads_device(panel, cfg.seed_reads, 0, k, 0, d_packed.data_ptr(), stream)
+    synth.reads_device(other, cfg.seed_reads + 1, 0, n - k, 0, d_packed[k:].data_ptr(), stream)
+    res_t = torch.empty(n, dtype=torch.int32, device="cuda")
+    res_b = torch.empty(n, dtype=torch.int32, device="cuda")
+    with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, True) as mt, \
+            BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, False) as mb:
+        assert int(mt.info().cuckoo_probes) >= 2
+        mt.assign_packed_device(d_packed.data_ptr(), n, res_t.data_ptr(), stream)
+        mb.assign_packed_device(d_packed.data_ptr(), n, res_b.data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert torch.equal(res_t, res_b)
+        ct, cb = mt.counts(), mb.counts()
+        assert np.array_equal(ct, cb)
+        assert int(ct.sum()) == n
+        assert int(ct[-1]) > n // 2
+        idx = torch.where(res_t == -1, torch.full_like(res_t, cfg.n_samples), (res_t >> 16) & 0xFFFF)
+        hist = torch.bincount(idx.to(torch.int64), minlength=cfg.n_samples + 1).cpu().numpy().astype(np.uint64)
+        assert np.array_equal(hist, ct)
+
+
 def test_kernel_launch_counter_moves():
     from fqtk_b200.barcode_matching import kernel_launches
 
