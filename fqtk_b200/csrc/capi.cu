@@ -390,8 +390,8 @@ int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, cons
 }
 
 // k_probe4's global table (kernels.h): every Some(..) memo entry whose key is pure A/C/G/T under its compressed key, in
-// 8-byte slots, four to a 32-byte bucket, bucketised linear probing at load <= 0.6 so that it stays L2-resident
-// (cfg 4: 1.7 M entries, 23 MB instead of the memo table's 122 MB).  Returns 0 when built, 1 when the panel does not qualify, < 0 on error.
+// 8-byte slots, four to a 32-byte bucket, bucketised linear probing at load 0.4 - 0.65 so that it stays L2-resident
+// (cfg 4: 1.7 M entries, 35 MB instead of the memo table's 122 MB).  Returns 0 when built, 1 when the panel does not qualify, < 0 on error.
 template <int W>
 int build_g4_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, const std::vector<uint32_t>& res, uint64_t n) {
     const uint32_t S = m->S, L = m->L, pad = m->params.last_pad;
@@ -436,7 +436,18 @@ int build_g4_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, const st
             if (code_of(e.word) == (1u << vb) - 1u) { vb++; break; }  // the all-ones code marks an empty slot
         if (hi_bits + vb > 32u) return 1;
     }
-    const uint64_t buckets64 = std::max<uint64_t>(16, (uint64_t)((double)ent.size() / (4 * 0.6)) + 1);
+    // load factor: shorter overflow chains (0.4) while the table stays well inside L2, else denser (0.65) so that it
+    // still fits next to the stream — measured on B200: cfg 4 5.10 ms at 0.6 / 4.67 at 0.4 / 4.68 at 0.15 (92 MB);
+    // cfg 5 20.5 ms at 0.7 / 20.8 at 0.6 / 24.1 at 0.4 (50 MB) / 28.5 at 0.15 / 58 at 0.88.  FQTK_B200_G4_LOAD = percent
+    // overrides (A/B timing).
+    static const double g4_load_env = [] {
+        const char* e = getenv("FQTK_B200_G4_LOAD");
+        const int v = e ? atoi(e) : 0;
+        return (v >= 5 && v <= 90) ? v / 100.0 : 0.0;
+    }();
+    const double g4_load = g4_load_env > 0.0 ? g4_load_env
+                                             : ((double)ent.size() * 8.0 / 0.4 <= 40.0 * (1 << 20) ? 0.4 : 0.65);
+    const uint64_t buckets64 = std::max<uint64_t>(16, (uint64_t)((double)ent.size() / (4 * g4_load)) + 1);
     if (buckets64 >= (1ull << 29)) return 1;
     const uint32_t n_buckets = (uint32_t)buckets64;
     auto hi_word = [&](const Ent& e) { return hi_bits ? ((e.hi << vb) | code_of(e.word)) : e.word; };
