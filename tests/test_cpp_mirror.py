@@ -28,3 +28,15 @@ def test_cpp_mirror_reference_cases(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all reference assign cases pass" in r.stdout
+
+
+def test_compressed_key_primitives_on_cpu(tmp_path):
+    """acgt_key / acgt_key64 (csrc/common.cuh, shared by host and device): valid <=> every nibble one-hot, and injective
+    on valid reads — checked on the CPU (tests/cpp/test_keys.cpp), no GPU needed."""
+    exe = str(tmp_path / "test_keys")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-I", "/usr/local/cuda/include",
+           os.path.join(ROOT, "tests", "cpp", "test_keys.cpp"), "-o", exe]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "injective on valid reads" in r.stdout
