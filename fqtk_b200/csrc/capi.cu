@@ -509,17 +509,18 @@ int build_table(fqtk_b200_matcher* m) {
     m->table_candidates = n;
 
     // evaluate every candidate with the brute-force kernel
-    uint32_t *d_keys = nullptr, *d_res = nullptr;
-    CU(cudaMalloc(&d_keys, std::max<size_t>(16, keys.size() * 4)));
-    CU(cudaMalloc(&d_res, std::max<size_t>(16, n * 4)));
-    CU(cudaMemcpy(d_keys, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice));
-    fq::ReadSource src{d_keys, nullptr, nullptr, 0, n};
-    CU(fq::launch_brute(m->params, src, d_res, m->geo, m->streams[0]));
+    struct DeviceBuffer {  // freed on every exit path of this function
+        uint32_t* p = nullptr;
+        ~DeviceBuffer() { if (p) cudaFree(p); }
+    } d_keys, d_res;
+    CU(cudaMalloc(&d_keys.p, std::max<size_t>(16, keys.size() * 4)));
+    CU(cudaMalloc(&d_res.p, std::max<size_t>(16, n * 4)));
+    CU(cudaMemcpy(d_keys.p, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice));
+    fq::ReadSource src{d_keys.p, nullptr, nullptr, 0, n};
+    CU(fq::launch_brute(m->params, src, d_res.p, m->geo, m->streams[0]));
     std::vector<uint32_t> res(n);
-    CU(cudaMemcpyAsync(res.data(), d_res, n * 4, cudaMemcpyDeviceToHost, m->streams[0]));
+    CU(cudaMemcpyAsync(res.data(), d_res.p, n * 4, cudaMemcpyDeviceToHost, m->streams[0]));
     CU(cudaStreamSynchronize(m->streams[0]));
-    cudaFree(d_keys);
-    cudaFree(d_res);
     CU(cudaMemsetAsync(m->d_counts, 0, (size_t)(S + 1) * 8, m->streams[0]));  // the build pass is not a batch
 
     uint64_t n_some = 0;
