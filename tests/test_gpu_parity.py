@@ -408,6 +408,60 @@ def test_mostly_unmatched_stream_at_size():
         assert np.array_equal(hist, ct)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# SURVEY 8f "next" #2: the batched host pipeline (fqtk_b200/demux.py) against the reference's end-to-end vectors
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("use_cache", MODES)
+def test_batched_pipeline_reference_end_to_end_vectors(kats, use_cache):
+    from fqtk_b200.demux import demux_batch
+
+    for case in kats["demux_e2e"]:
+        S = len(case["barcodes"])
+        ids = [f"Sample{j:04d}" for j in range(S)]  # metadata_lines_from_barcodes (demux.rs:1046-1053)
+        inputs = [[(f"ex_{i}".encode(), b.encode(), b";" * len(b)) for i, b in enumerate(col)] for col in case["inputs"]]
+        with BarcodeMatcher(case["barcodes"], case["max_mismatches"], case["min_mismatch_delta"], use_cache) as m:
+            out = demux_batch(m, ids, case["barcodes"], case["read_structures"], inputs, case["output_types"])
+        got = {name: [[h.decode(), s.decode()] for h, s, _ in recs] for name, recs in out.files.items()}
+        assert got == case["expect"], case["source"]
+        for recs in out.files.values():
+            assert all(q == b";" * len(s) for _, s, q in recs)
+        if "expect_counts" in case:
+            assert out.counts.tolist() == case["expect_counts"]
+        assert int(out.counts.sum()) == len(case["inputs"][0])
+
+
+def test_batched_pipeline_at_cfg1_scale():
+    """cfg 1 (10 k single-end reads, 8B+T, 4 samples): every record lands in the file of the sample the oracle assigns,
+    in input order, with the rewritten header; too-short reads are skipped and counted nowhere (demux.rs:2023-2073)."""
+    from fqtk_b200.demux import TooFewBases, demux_batch
+
+    cfg = synth.CONFIGS[1]
+    panel = synth.panel(cfg)
+    bcs = [bytes(r) for r in panel]
+    n = cfg.n_reads
+    reads = synth.reads_host(panel, cfg.seed_reads, 0, n)
+    recs = [(f"r{i} 1:N:0:0".encode(), bytes(reads[i]) + b"A" * 50, b";" * 58) for i in range(n)]
+    recs[17] = (b"short", b"ACGT", b";;;;")  # 4 bases < 8 + 1
+    ids = [f"Sample{j:04d}" for j in range(cfg.n_samples)]
+    om = oracle.OracleMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta)
+    with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta) as m:
+        with pytest.raises(TooFewBases):
+            demux_batch(m, ids, [b.decode() for b in bcs], ["8B+T"], [recs])
+        m.reset_counts()
+        out = demux_batch(m, ids, [b.decode() for b in bcs], ["8B+T"], [recs], skip_too_few_bases=True)
+    assert out.skipped == 1 and int(out.counts.sum()) == n - 1
+    want_files = {}
+    for i in range(n):
+        if i == 17:
+            continue
+        r = om.assign_closed(bytes(reads[i]))
+        prefix = "unmatched" if r is None else ids[r.best_match]
+        want_files.setdefault(f"{prefix}.R1.fq.gz", []).append(
+            (f"r{i} 1:N:0:".encode() + bytes(reads[i]), b"A" * 50, b";" * 50))
+    assert out.files == want_files
+    assert [mm.templates for mm in out.metrics] == out.counts.tolist()
+
+
 def test_kernel_launch_counter_moves():
     from fqtk_b200.barcode_matching import kernel_launches
 

@@ -202,3 +202,21 @@ def test_write_header_reference_kats(kats):
     assert write_header(1, b"q1 a:b:", [b"AC"]) == b"@q1 a:b:AC"
     assert write_header(2, b"q1 1:N:0:GATC", [b"AC"]) == b"@q1 2:N:0:GATC+AC"
     assert write_header(2, b"q1 1:N:0:", [b"AC"]) == b"@q1 2:N:0:AC"
+
+
+def test_read_structures_and_segment_extraction():
+    """Host-only parts of the batched pipeline (fqtk_b200/demux.py): read-structure parsing, minimum length
+    (demux.rs:298), segment extraction with a trailing `+` segment."""
+    from fqtk_b200.demux import ReadStructureError, extract_segments, min_length, parse_read_structure
+
+    assert parse_read_structure("8B+T") == [("B", 8), ("T", None)]
+    assert parse_read_structure("10m8b7c100t") == [("M", 10), ("B", 8), ("C", 7), ("T", 100)]
+    assert min_length(parse_read_structure("8B+T")) == 9
+    assert min_length(parse_read_structure("6B1S1M1T")) == 9
+    for bad in ("", "8", "B8", "+B8T", "0B+T", "8X+T"):
+        with pytest.raises(ReadStructureError):
+            parse_read_structure(bad)
+    segs = extract_segments(parse_read_structure("4B4M8S"), b"AAAACCCCGGGGTTTT", b"0123456789abcdef")
+    assert segs == [("B", b"AAAA", b"0123"), ("M", b"CCCC", b"4567"), ("S", b"GGGGTTTT", b"89abcdef")]
+    segs = extract_segments(parse_read_structure("2B+T"), b"ACGTA", b"!!###")
+    assert segs == [("B", b"AC", b"!!"), ("T", b"GTA", b"###")]
