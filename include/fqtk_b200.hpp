@@ -7,6 +7,7 @@
 // so tests/cpp/test_barcode_matching.cpp reads like the reference's own #[cfg(test)] module.
 // A Rust panic becomes a thrown fqtk_b200::Panic carrying the reference's panic text.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <optional>
 #include <stdexcept>
@@ -94,6 +95,14 @@ class BarcodeMatcher {
         return c;
     }
     void reset_counts() { check(fqtk_b200_matcher_reset_counts(h_)); }
+    // stable partition of read indices by assignment (the batch form of demux.rs:970-975): order[offsets[s] ..
+    // offsets[s + 1]) = the reads of sample s in input order, s = n_samples = unmatched; offsets has n_samples + 2 entries
+    void route(const std::uint32_t* results, std::uint64_t n, std::vector<std::uint32_t>& order,
+               std::vector<std::uint64_t>& offsets) {
+        order.resize(n);
+        offsets.assign(n_samples_ + 2, 0);
+        check(fqtk_b200_matcher_route(h_, results, n, order.data(), offsets.data()));
+    }
     fqtk_b200_matcher* handle() { return h_; }
 
   private:
@@ -107,5 +116,83 @@ class BarcodeMatcher {
     fqtk_b200_matcher* h_ = nullptr;
     std::size_t n_samples_ = 0;
 };
+
+// ReadSet::write_header_internal, src/bin/commands/demux.rs:171-267 — the rewritten FASTQ header line (with the leading
+// '@', without a newline).  The reference's `ensure!` failures and `unwrap` panics become a thrown Panic.
+inline std::string write_header(std::size_t read_num, const std::string& header,
+                                const std::vector<std::string>& sample_barcode_segments,
+                                const std::vector<std::string>& molecular_barcode_segments = {}) {
+    auto count = [](const std::string& t, char c) {
+        std::size_t n = 0;
+        for (char x : t) n += x == c;
+        return n;
+    };
+    auto join = [](const std::vector<std::string>& v) {
+        std::string o;
+        for (std::size_t i = 0; i < v.size(); i++) o += (i ? "+" : "") + v[i];
+        return o;
+    };
+    const std::size_t sp = header.find(' ');
+    const bool has_comment = sp != std::string::npos;
+    const std::string name = has_comment ? header.substr(0, sp) : header;
+    const std::string comment = has_comment ? header.substr(sp + 1) : std::string();
+    std::string out = "@";
+    if (!molecular_barcode_segments.empty()) {  // :189-213
+        const std::size_t sep = count(name, ':');
+        if (sep > 7) throw Panic("Can't handle read name with more than 8 segments: " + header);
+        out += name;
+        out += sep == 7 ? "+" : ":";
+        out += join(molecular_barcode_segments);
+    } else {
+        out += name;
+    }
+    out += ' ';
+    if (!has_comment) {  // :219-223
+        out += std::to_string(read_num) + ":N:0:";
+    } else {
+        if (comment.empty()) throw Panic("empty comment after the read name: " + header);  // chars.last().unwrap(), :230
+        const std::size_t sep = count(comment, ':');
+        if (sep < 3) {  // :228-233
+            out += comment;
+            if (comment.back() != ':') out += ':';
+        } else {
+            if (sep != 3) throw Panic("Comment in did not have 4 segments: " + header);
+            const std::size_t first = comment.find(':');
+            const bool digit = comment.back() >= '0' && comment.back() <= '9';  // Illumina's "0" index, :241-246
+            const std::string remainder = comment.substr(first + 1, comment.size() - first - 1 - (digit ? 1 : 0));
+            out += std::to_string(read_num) + ":" + remainder;
+            if (remainder.empty() || remainder.back() != ':') out += '+';
+        }
+    }
+    out += join(sample_barcode_segments);  // :257-263
+    return out;
+}
+
+// DemuxMetric + DemuxMetric::update, demux.rs:452-497: rows for the S samples and, last, the unmatched pseudo-sample
+// (barcode "."); the ratios exclude the unmatched row from mean and best.  counts = S + 1 integers, last = unmatched.
+struct DemuxMetric {
+    std::string sample_id, barcode;
+    std::uint64_t templates = 0;
+    double frac_templates = 0, ratio_to_mean = 0, ratio_to_best = 0;
+};
+inline std::vector<DemuxMetric> demux_metrics(const std::vector<Sample>& samples, const std::vector<std::uint64_t>& counts,
+                                              const std::string& unmatched_prefix = "unmatched") {
+    if (counts.size() != samples.size() + 1) throw Error(FQTK_B200_ERR_ARG, "need S + 1 counts");
+    std::vector<DemuxMetric> rows;
+    double sample_total = 0, best = 0;
+    for (std::size_t j = 0; j < samples.size(); j++) {
+        rows.push_back({samples[j].sample_id, samples[j].barcode, counts[j]});
+        sample_total += (double)counts[j];
+        best = std::max(best, (double)counts[j]);
+    }
+    rows.push_back({unmatched_prefix, ".", counts.back()});
+    const double total = sample_total + (double)counts.back(), mean = sample_total / (double)samples.size();
+    for (auto& r : rows) {  // IEEE division, as Rust's f64: x / 0 = inf, 0 / 0 = NaN
+        r.frac_templates = (double)r.templates / total;
+        r.ratio_to_mean = (double)r.templates / mean;
+        r.ratio_to_best = (double)r.templates / best;
+    }
+    return rows;
+}
 
 }  // namespace fqtk_b200

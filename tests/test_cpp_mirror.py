@@ -40,3 +40,16 @@ def test_compressed_key_primitives_on_cpu(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "injective on valid reads" in r.stdout
+
+
+def test_cpp_host_mirror_formatting_on_cpu(tmp_path):
+    """write_header / demux_metrics of include/fqtk_b200.hpp against the reference's own tests — no GPU needed (the
+    library is linked only because the header also declares the matcher)."""
+    exe = str(tmp_path / "test_host_mirror")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", "test_host_mirror.cpp"), "-o", exe,
+           "-L", LIBDIR, "-lfqtk_b200", f"-Wl,-rpath,{LIBDIR}"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "match the reference's tests" in r.stdout
