@@ -16,8 +16,6 @@ for s in $STEPS; do
     tests) timeout 1500 python -m pytest tests -m gpu -q --maxfail=8 -x --durations=12 > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?"; tail -40 "$OUT/pytest_gpu.log";;
     bench) timeout 900 python bench.py --steps 10 --warmup 3 > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench rc=$?"; cat "$OUT/bench.json"; tail -5 "$OUT/bench.err";;
     ab) for c in 2 3 0; do timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-brute --cuckoo $c > "$OUT/bench_ab_cuckoo$c.json" 2> "$OUT/bench_ab_cuckoo$c.err"; echo "ab cuckoo=$c rc=$?"; python -c "import json,sys; d=json.load(open('$OUT/bench_ab_cuckoo$c.json')); print(d['roofline']['kernel'], d['roofline']['kernel_ms'], d['roofline']['frac'], d['value'])"; done;;
-    ab768) FQTK_B200_P3_THREADS=768 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-brute > "$OUT/bench_ab_768.json" 2> "$OUT/bench_ab_768.err"; echo "ab768 rc=$?"; python -c "import json,sys; d=json.load(open('$OUT/bench_ab_768.json')); print(d['roofline']['kernel'], d['roofline']['kernel_ms'], d['roofline']['frac'], d['value'])";;
-    shapes) for sh in 4x1024 8x1024; do FQTK_B200_P3_SHAPE=$sh timeout 600 python bench.py --config 2 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-brute > "$OUT/bench_shape_$sh.json" 2> "$OUT/bench_shape_$sh.err"; echo "shape $sh rc=$?"; python -c "import json,sys; d=json.load(open('$OUT/bench_shape_$sh.json')); print(d['roofline']['kernel'], d['roofline']['kernel_ms'], d['roofline']['frac'], d['value'])"; done;;
     benchref) timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"; echo "benchref rc=$?"; cat "$OUT/bench_ref.json";;
     bench2) for c in 2 4 5; do timeout 900 python bench.py --config $c --steps 5 --warmup 3 --no-cpu-baseline > "$OUT/bench_cfg$c.json" 2> "$OUT/bench_cfg$c.err"; echo "bench cfg$c rc=$?"; cat "$OUT/bench_cfg$c.json"; done;;
     ncu)
