@@ -220,3 +220,49 @@ def test_read_structures_and_segment_extraction():
     assert segs == [("B", b"AAAA", b"0123"), ("M", b"CCCC", b"4567"), ("S", b"GGGGTTTT", b"89abcdef")]
     segs = extract_segments(parse_read_structure("2B+T"), b"ACGTA", b"!!###")
     assert segs == [("B", b"AC", b"!!"), ("T", b"GTA", b"###")]
+
+
+class _OracleBackedMatcher:
+    """Stand-in for the GPU matcher so that the HOST logic of fqtk_b200/demux.py runs in the CPU suite: assignments from
+    the oracle, routing = numpy's stable argsort (what fqtk_b200_matcher_route computes on the device)."""
+
+    def __init__(self, barcodes, max_mismatches, min_mismatch_delta):
+        self.om = oracle.OracleMatcher([b.encode() for b in barcodes], max_mismatches, min_mismatch_delta)
+        self.S = len(barcodes)
+        self._counts = np.zeros(self.S + 1, dtype=np.uint64)
+
+    def assign_batch(self, reads, lengths=None):
+        out = np.empty(len(reads), dtype=np.uint32)
+        for i in range(len(reads)):
+            row = bytes(reads[i, :int(lengths[i])] if lengths is not None else reads[i])
+            out[i] = self.om.assign_word(row)
+            self._counts[self.S if out[i] == _lib.NONE else int(out[i]) >> 16] += 1
+        return out
+
+    def route(self, words):
+        bucket = np.where(words == _lib.NONE, self.S, words >> 16).astype(np.int64)
+        order = np.argsort(bucket, kind="stable").astype(np.uint32)
+        offsets = np.zeros(self.S + 2, dtype=np.uint64)
+        offsets[1:] = np.cumsum(np.bincount(bucket, minlength=self.S + 1))
+        return order, offsets
+
+    def counts(self):
+        return self._counts.copy()
+
+
+def test_batched_pipeline_host_logic_with_the_oracle_as_matcher(kats):
+    """The reference's end-to-end demux vectors through fqtk_b200/demux.py with the oracle standing in for the GPU
+    matcher (the GPU suite runs the same vectors through the C ABI)."""
+    from fqtk_b200.demux import demux_batch
+
+    for case in kats["demux_e2e"]:
+        S = len(case["barcodes"])
+        ids = [f"Sample{j:04d}" for j in range(S)]
+        inputs = [[(f"ex_{i}".encode(), b.encode(), b";" * len(b)) for i, b in enumerate(col)] for col in case["inputs"]]
+        m = _OracleBackedMatcher(case["barcodes"], case["max_mismatches"], case["min_mismatch_delta"])
+        out = demux_batch(m, ids, case["barcodes"], case["read_structures"], inputs, case["output_types"])
+        got = {name: [[h.decode(), s.decode()] for h, s, _ in recs] for name, recs in out.files.items()}
+        assert got == case["expect"], case["source"]
+        if "expect_counts" in case:
+            assert out.counts.tolist() == case["expect_counts"]
+            assert [r.templates for r in out.metrics] == case["expect_counts"]
