@@ -21,7 +21,7 @@ MODE_TABLE = 2
 
 # every symbol include/fqtk_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
-    "fqtk_b200_matcher_create", "fqtk_b200_matcher_destroy", "fqtk_b200_matcher_get_info",
+    "fqtk_b200_matcher_create", "fqtk_b200_matcher_create_ex", "fqtk_b200_options_init", "fqtk_b200_matcher_destroy", "fqtk_b200_matcher_get_info",
     "fqtk_b200_set_table_budget", "fqtk_b200_set_cuckoo_arity", "fqtk_b200_matcher_assign", "fqtk_b200_matcher_assign_batch",
     "fqtk_b200_matcher_assign_segments", "fqtk_b200_matcher_assign_segments_device",
     "fqtk_b200_matcher_route_device", "fqtk_b200_matcher_route",
@@ -42,6 +42,12 @@ class MatcherInfo(C.Structure):
         ("cuckoo_entries", C.c_uint64), ("cuckoo_probes", C.c_uint32), ("cuckoo_slots", C.c_uint32),
         ("l2_table_entries", C.c_uint64), ("l2_table_bytes", C.c_uint64),
     ]
+
+
+class Options(C.Structure):
+    """fqtk_b200_options"""
+    _fields_ = [("struct_size", C.c_uint32), ("kernel", C.c_int32), ("table_budget", C.c_uint64),
+                ("chunk_bytes", C.c_uint64), ("l2_table_load_pct", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class Segment(C.Structure):
@@ -71,6 +77,8 @@ def lib() -> C.CDLL:
     vp, u32p, u64p = C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
     sig = {
         "fqtk_b200_matcher_create": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint8, C.c_uint8, C.c_int, C.c_int, C.POINTER(vp)]),
+        "fqtk_b200_matcher_create_ex": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint8, C.c_uint8, C.c_int, C.c_int, C.POINTER(Options), C.POINTER(vp)]),
+        "fqtk_b200_options_init": (None, [C.POINTER(Options)]),
         "fqtk_b200_matcher_destroy": (None, [vp]),
         "fqtk_b200_matcher_get_info": (C.c_int, [vp, C.POINTER(MatcherInfo)]),
         "fqtk_b200_set_table_budget": (None, [C.c_uint64]),

@@ -41,8 +41,11 @@ def unpack(word: int) -> Optional[BarcodeMatch]:
     return BarcodeMatch(word >> 16, (word >> 8) & 0xFF, word & 0xFF)
 
 
-def _raise(rc: int) -> None:
+def _raise(rc: int, sample0_id: Optional[str] = None) -> None:
     msg = _lib.last_error()
+    if rc == _lib.ERR_LENGTH and sample0_id is not None and msg.endswith(" for sample 0"):
+        # the C ABI does not know sample ids; the reference's text names the first sample (barcode_matching.rs:99-105)
+        msg = msg[: -len("0")] + sample0_id
     if rc in (_lib.ERR_EMPTY_PANEL, _lib.ERR_EMPTY_BARCODE, _lib.ERR_LENGTH):
         raise MatcherPanic(msg)
     raise _lib.Fqtk_b200Error(rc, msg)
@@ -52,7 +55,9 @@ class BarcodeMatcher:
     """BarcodeMatcher (barcode_matching.rs:29-186).  `samples`: Sample objects, str or bytes barcodes, in sheet order."""
 
     def __init__(self, samples: Sequence, max_mismatches: int, min_mismatch_delta: int, use_cache: bool = True,
-                 device: int = 0):
+                 device: int = 0, **options):
+        """`options`: fields of fqtk_b200_options (kernel, table_budget, chunk_bytes, l2_table_load_pct) for this handle
+        only; without any the thread's defaults apply (fqtk_b200_matcher_create)."""
         if not (0 <= max_mismatches <= 255 and 0 <= min_mismatch_delta <= 255):
             raise OverflowError("max_mismatches / min_mismatch_delta must fit in u8 (demux.rs:923-924)")
         bcs = barcodes_of(samples)
@@ -65,14 +70,26 @@ class BarcodeMatcher:
             # the reference only notices at match time (count_mismatches panics, :95-106); a dense panel cannot hold it
             raise MatcherPanic("All barcodes must have the same length")
         self.n_samples = len(bcs)
+        self._sample0_id = getattr(samples[0], "sample_id", None)
         self.barcode_len = L
         self.max_mismatches = max_mismatches
         self.min_mismatch_delta = min_mismatch_delta
         self.use_cache = bool(use_cache)
         panel = np.frombuffer(b"".join(bcs), dtype=np.uint8)
         self._h = C.c_void_p()
-        rc = _lib.lib().fqtk_b200_matcher_create(panel.ctypes.data, self.n_samples, L, max_mismatches,
-                                                 min_mismatch_delta, int(self.use_cache), device, C.byref(self._h))
+        if options:
+            opts = _lib.Options()
+            _lib.lib().fqtk_b200_options_init(C.byref(opts))
+            for name, value in options.items():
+                if name not in ("kernel", "table_budget", "chunk_bytes", "l2_table_load_pct"):
+                    raise TypeError(f"unknown matcher option {name!r}")
+                setattr(opts, name, int(value))
+            rc = _lib.lib().fqtk_b200_matcher_create_ex(panel.ctypes.data, self.n_samples, L, max_mismatches,
+                                                        min_mismatch_delta, int(self.use_cache), device,
+                                                        C.byref(opts), C.byref(self._h))
+        else:
+            rc = _lib.lib().fqtk_b200_matcher_create(panel.ctypes.data, self.n_samples, L, max_mismatches,
+                                                     min_mismatch_delta, int(self.use_cache), device, C.byref(self._h))
         if rc != _lib.OK:
             self._h = None
             _raise(rc)
@@ -119,7 +136,7 @@ class BarcodeMatcher:
         rb = bytes(read_bases)
         rc = _lib.lib().fqtk_b200_matcher_assign(self._h, rb, len(rb), C.byref(out))
         if rc != _lib.OK:
-            _raise(rc)
+            _raise(rc, self._sample0_id)
         return int(out.value)
 
     def assign(self, read_bases: bytes) -> Optional[BarcodeMatch]:
@@ -144,7 +161,7 @@ class BarcodeMatcher:
             lp = lengths.ctypes.data
         rc = _lib.lib().fqtk_b200_matcher_assign_batch(self._h, reads.ctypes.data, n, stride, lp, out.ctypes.data)
         if rc != _lib.OK:
-            _raise(rc)
+            _raise(rc, self._sample0_id)
         return out
 
     def assign_batch_ptr(self, rows_ptr: int, n: int, stride: int, results_ptr: int, lengths_ptr: int = 0) -> None:

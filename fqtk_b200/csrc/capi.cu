@@ -31,8 +31,30 @@ int synth_panel_host(uint64_t seed, uint32_t S, uint32_t L, uint32_t min_distanc
 namespace {
 
 thread_local std::string g_err;
-uint64_t g_table_budget = 32ull << 20;
-size_t g_tier_budget_bytes = 132u << 10;  // shared memory the hot tier may take per CTA
+constexpr size_t TIER_BUDGET_BYTES = 132u << 10;  // shared memory the hot tier may take per CTA
+
+// Defaults of fqtk_b200_matcher_create (the form without an options struct).  Thread-local: two host threads that each
+// create a matcher for their own device cannot race on them.  The environment variables are read once
+// (thread-safe static initialisation) and only seed these defaults; they exist for A/B timing.
+int env_int(const char* name, int fallback) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : fallback;
+}
+fqtk_b200_options env_defaults() {
+    static const fqtk_b200_options v = [] {
+        fqtk_b200_options o{};
+        o.struct_size = (uint32_t)sizeof(fqtk_b200_options);
+        o.kernel = env_int("FQTK_B200_CK_NP", FQTK_B200_KERNEL_AUTO);
+        o.table_budget = 32ull << 20;
+        const int mb = env_int("FQTK_B200_CHUNK_MB", 0);
+        o.chunk_bytes = (uint64_t)(mb > 0 ? mb : 32) << 20;
+        const int load = env_int("FQTK_B200_G4_LOAD", 0);
+        o.l2_table_load_pct = (load >= 5 && load <= 90) ? (uint32_t)load : 0u;
+        return o;
+    }();
+    return v;
+}
+thread_local fqtk_b200_options t_defaults = env_defaults();
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -47,21 +69,19 @@ int cuda_fail(cudaError_t e, const char* what) {
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
 
-constexpr int N_PIPE = 3;                       // chunks in flight for the host-buffer call
-uint64_t chunk_bytes() {                        // ASCII bytes per chunk (FQTK_B200_CHUNK_MB overrides, for tuning)
-    static const uint64_t v = [] {
-        const char* e = getenv("FQTK_B200_CHUNK_MB");
-        const long mb = e ? atol(e) : 0;
-        return (uint64_t)(mb > 0 ? mb : 32) << 20;
-    }();
-    return v;
+// decode() of one 4-bit mask (mod.rs:66-83): first IUPAC letter with that mask; the reference panics on mask 0
+char decode_mask(uint32_t mask) {
+    static const char T[17] = "?ACMGRSVTWYHKDBN";
+    return T[mask & 15u];
 }
-#define CHUNK_BYTES chunk_bytes()
+
+constexpr int N_PIPE = 3;                       // chunks in flight for the host-buffer call
 
 }  // namespace
 
 struct fqtk_b200_matcher {
     int device = 0;
+    fqtk_b200_options opt{};  // this handle's options (create_ex), fixed at creation
     fq::LaunchGeometry geo{};
     uint32_t S = 0, L = 0, W = 0, P = 0;
     uint8_t max_mm = 0, min_delta = 0;
@@ -242,12 +262,7 @@ void build_tier(const std::vector<uint32_t>& keys, const std::vector<uint32_t>& 
 // k_probe3's shared-memory table (kernels.h): every Some(..) memo entry whose key is pure A/C/G/T, keyed by the
 // compressed 32-bit key, as an NP-ary cuckoo table of 4-byte quotient entries.  Returns 0 when built, 1 when the
 // panel does not qualify (the matcher then stays on k_probe2), < 0 on a CUDA error.
-int g_cuckoo_arity = -2;  // -2: not set (FQTK_B200_CK_NP decides, default auto)
-int ck_force_np() {  // -1 auto, 0 no cuckoo table (k_probe2 runs instead), 2 | 3 force the arity
-    if (g_cuckoo_arity != -2) return g_cuckoo_arity;
-    const char* e = getenv("FQTK_B200_CK_NP");
-    return e ? atoi(e) : -1;
-}
+// m->opt.kernel: -1 auto, 0 no cuckoo table (k_probe2 runs instead), 1 the L2-resident table only, 2 | 3 force the arity
 
 template <int W>
 int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, const std::vector<uint32_t>& res,
@@ -293,7 +308,7 @@ int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, cons
     const size_t smem_max = (size_t)m->geo.max_smem_optin - 1024;
     struct Geo { uint32_t np, sb[3]; };
     std::vector<Geo> options;
-    const int force = ck_force_np();
+    const int force = m->opt.kernel;
     if (force == 0 || force == 1) return 1;  // 0: k_probe2 only, 1: k_probe4's table only
     for (uint32_t s = std::max(cb, 4u); s <= 16; s++) {
         if (force != 3) {
@@ -440,11 +455,7 @@ int build_g4_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, const st
     // still fits next to the stream — measured on B200: cfg 4 5.10 ms at 0.6 / 4.67 at 0.4 / 4.68 at 0.15 (92 MB);
     // cfg 5 20.5 ms at 0.7 / 20.8 at 0.6 / 24.1 at 0.4 (50 MB) / 28.5 at 0.15 / 58 at 0.88.  FQTK_B200_G4_LOAD = percent
     // overrides (A/B timing).
-    static const double g4_load_env = [] {
-        const char* e = getenv("FQTK_B200_G4_LOAD");
-        const int v = e ? atoi(e) : 0;
-        return (v >= 5 && v <= 90) ? v / 100.0 : 0.0;
-    }();
+    const double g4_load_env = m->opt.l2_table_load_pct ? m->opt.l2_table_load_pct / 100.0 : 0.0;
     const double g4_load = g4_load_env > 0.0 ? g4_load_env
                                              : ((double)ent.size() * 8.0 / 0.4 <= 40.0 * (1 << 20) ? 0.4 : 0.65);
     const uint64_t buckets64 = std::max<uint64_t>(16, (uint64_t)((double)ent.size() / (4 * g4_load)) + 1);
@@ -478,7 +489,7 @@ int build_g4_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, const st
     p.g4_stash_cap = cap;
     // measured on B200: k_probe4 wins where k_probe2 has no useful hot tier (cfg 5, W = 3: 27 -> 21 ms); with a hot
     // tier that ends 80 % of the reads in shared memory (cfg 4) k_probe2 + this table is the faster combination
-    p.g4_kernel = (W == 3 || ck_force_np() == 1) ? 1u : 0u;
+    p.g4_kernel = (W == 3 || m->opt.kernel == 1) ? 1u : 0u;
     if (hi_bits) {  // decode fields shared with k_probe3 (which never runs for L > 16)
         p.ck_lb = bb + nb;
         p.ck_bsh = 8u - nb;
@@ -494,8 +505,8 @@ int build_table(fqtk_b200_matcher* m) {
     const uint32_t S = m->S, L = m->L, W = m->W;
     std::vector<uint8_t> masks((size_t)S * L);
     for (size_t t = 0; t < masks.size(); t++) masks[t] = (uint8_t)fq::encode_byte(m->panel[t]);
-    const uint64_t cand = neighbourhood_size(masks, S, L, m->max_mm, g_table_budget);
-    if (cand > g_table_budget || cand >= (1ull << 31)) return 1;  // over budget: stay in brute mode
+    const uint64_t cand = neighbourhood_size(masks, S, L, m->max_mm, m->opt.table_budget);
+    if (cand > m->opt.table_budget || cand >= (1ull << 31)) return 1;  // over budget: stay in brute mode
 
     std::vector<uint32_t> keys;
     keys.reserve((size_t)cand * W);
@@ -558,7 +569,7 @@ int build_table(fqtk_b200_matcher* m) {
     std::vector<uint32_t> tier;
     uint32_t tslots = 0;
     uint64_t placed = 0;
-    const size_t budget = std::min(g_tier_budget_bytes, smem_max > fixed ? smem_max - fixed : 0);
+    const size_t budget = std::min(TIER_BUDGET_BYTES, smem_max > fixed ? smem_max - fixed : 0);
     switch (W) {
         case 1: build_tier<1>(keys, res, n, budget, tier, tslots, placed); break;
         case 2: build_tier<2>(keys, res, n, budget, tier, tslots, placed); break;
@@ -616,7 +627,7 @@ int build_table(fqtk_b200_matcher* m) {
         if (rc < 0) return rc;
     }
     // else k_probe4's L2-resident table of the same entries under compressed keys (L <= 24)
-    if (m->params.ck_np == 0 && W <= 3 && ck_force_np() != 0) {
+    if (m->params.ck_np == 0 && W <= 3 && m->opt.kernel != 0) {
         const int rc = (W == 1) ? build_g4_w<1>(m, keys, res, n) : (W == 2) ? build_g4_w<2>(m, keys, res, n)
                                                                           : build_g4_w<3>(m, keys, res, n);
         if (rc < 0) return rc;
@@ -649,21 +660,30 @@ int ensure_pipeline(fqtk_b200_matcher* m, size_t in_bytes, size_t out_reads, boo
     return FQTK_B200_OK;
 }
 
-int run_device(fqtk_b200_matcher* m, const fq::ReadSource& src, uint32_t* d_results, cudaStream_t st) {
+int ensure_scratch(uint32_t** slot, size_t* cap, size_t words) {
+    if (words > *cap) {
+        if (*slot) cudaFree(*slot);
+        *slot = nullptr;
+        *cap = 0;
+        CU(cudaMalloc(slot, words * 4));
+        *cap = words;
+    }
+    return FQTK_B200_OK;
+}
+
+// `pipe_slot` >= 0: called from the host-buffer pipeline, whose chunks run on N_PIPE independent streams — scratch must
+// then be the slot's own (a shared buffer would be overwritten by the next chunk's pack while this chunk's kernel reads it).
+int run_device(fqtk_b200_matcher* m, const fq::ReadSource& src, uint32_t* d_results, cudaStream_t st, int pipe_slot = -1) {
     if (src.n >= (1ull << 32)) return fail(FQTK_B200_ERR_ARG, "n_reads must be < 2^32 per device call");
     fq::ReadSource s = src;
     if (m->W > (uint32_t)fq::MAX_FAST_WORDS && s.ascii) {  // L > 32: pack first, then the long-barcode kernel
-        const size_t need = (size_t)s.n * m->W;
-        if (need > m->scratch_words) {
-            if (m->d_scratch) cudaFree(m->d_scratch);
-            m->d_scratch = nullptr;
-            CU(cudaMalloc(&m->d_scratch, need * 4));
-            m->scratch_words = need;
-        }
-        if (s.lengths) return fail(FQTK_B200_ERR_UNSUPPORTED, "per-row lengths with barcodes longer than 32 bases");
-        CU(fq::launch_pack(s.ascii, s.n, m->L, s.stride, m->d_scratch, m->geo, st));
-        s.ascii = nullptr;
-        s.packed = m->d_scratch;
+        uint32_t** buf = pipe_slot >= 0 ? &m->d_seg_packed[pipe_slot] : &m->d_scratch;
+        size_t* cap = pipe_slot >= 0 ? &m->seg_packed_words[pipe_slot] : &m->scratch_words;
+        const int rc = ensure_scratch(buf, cap, (size_t)s.n * m->W + 4);
+        if (rc != FQTK_B200_OK) return rc;
+        CU(fq::launch_pack(s.ascii, s.n, m->L, s.stride, *buf, m->geo, st));
+        s.ascii = nullptr;   // s.lengths stays: rows whose length differs from L are None (barcode_matching.rs:167-169;
+        s.packed = *buf;     // longer rows were vetted by the host), the kernel skips them
     }
     if (m->mode == FQTK_B200_MODE_TABLE)
         CU(fq::launch_probe(m->params, s, d_results, m->geo, st));
@@ -671,6 +691,16 @@ int run_device(fqtk_b200_matcher* m, const fq::ReadSource& src, uint32_t* d_resu
         CU(fq::launch_brute(m->params, s, d_results, m->geo, st));
     return FQTK_B200_OK;
 }
+
+// The host-buffer calls are synchronous: on EVERY exit path (errors included) the pipeline streams are drained, so no
+// DMA is still reading the caller's rows or writing the caller's results when the call returns.
+struct PipelineDrain {
+    fqtk_b200_matcher* m;
+    ~PipelineDrain() {
+        for (int s = 0; s < N_PIPE; s++)
+            if (m->streams[s]) cudaStreamSynchronize(m->streams[s]);
+    }
+};
 
 }  // namespace
 
@@ -685,15 +715,37 @@ int fqtk_b200_device_count(void) {
     return n;
 }
 
-void fqtk_b200_set_table_budget(uint64_t max_candidates) { g_table_budget = max_candidates; }
+void fqtk_b200_set_table_budget(uint64_t max_candidates) { t_defaults.table_budget = max_candidates; }
 
-void fqtk_b200_set_cuckoo_arity(int arity) { g_cuckoo_arity = (arity >= 0 && arity <= 3) ? arity : -1; }
+void fqtk_b200_set_cuckoo_arity(int arity) { t_defaults.kernel = (arity >= 0 && arity <= 3) ? arity : FQTK_B200_KERNEL_AUTO; }
+
+void fqtk_b200_options_init(fqtk_b200_options* opts) {
+    if (opts) *opts = env_defaults();
+}
 
 uint64_t fqtk_b200_kernel_launches(void) { return fq::kernel_launches(); }
 
 int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t S, uint32_t L, uint8_t max_mm, uint8_t min_delta,
                              int use_cache, int device, fqtk_b200_matcher** out) {
+    const fqtk_b200_options o = t_defaults;  // this thread's defaults (fqtk_b200_set_*), seeded from the environment
+    return fqtk_b200_matcher_create_ex(panel_ascii, S, L, max_mm, min_delta, use_cache, device, &o, out);
+}
+
+int fqtk_b200_matcher_create_ex(const uint8_t* panel_ascii, uint32_t S, uint32_t L, uint8_t max_mm, uint8_t min_delta,
+                                int use_cache, int device, const fqtk_b200_options* opts, fqtk_b200_matcher** out) {
     if (!out) return fail(FQTK_B200_ERR_ARG, "out is NULL");
+    fqtk_b200_options opt = env_defaults();
+    if (opts) {
+        if (opts->struct_size < 8u || opts->struct_size > sizeof(fqtk_b200_options))
+            return fail(FQTK_B200_ERR_ARG, "options.struct_size: call fqtk_b200_options_init first");
+        std::memcpy(&opt, opts, opts->struct_size);  // fields an older caller does not know keep their defaults
+        opt.struct_size = (uint32_t)sizeof(fqtk_b200_options);
+        if (opt.kernel < -1 || opt.kernel > 3) return fail(FQTK_B200_ERR_ARG, "options.kernel out of range");
+        if (opt.table_budget == 0) opt.table_budget = 32ull << 20;
+        if (opt.chunk_bytes == 0) opt.chunk_bytes = 32ull << 20;
+        if (opt.l2_table_load_pct && (opt.l2_table_load_pct < 5 || opt.l2_table_load_pct > 90))
+            return fail(FQTK_B200_ERR_ARG, "options.l2_table_load_pct must be 0 (auto) or 5..90");
+    }
     *out = nullptr;
     if (S == 0) return fail(FQTK_B200_ERR_EMPTY_PANEL, "Must provide at least one sample");
     if (L == 0) return fail(FQTK_B200_ERR_EMPTY_BARCODE, "Sample barcode cannot be empty string");
@@ -709,6 +761,7 @@ int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t S, uint32_t L,
     fqtk_b200_matcher* m = new (std::nothrow) fqtk_b200_matcher();
     if (!m) return fail(FQTK_B200_ERR_ARG, "out of host memory");
     m->device = device;
+    m->opt = opt;
     m->S = S;
     m->L = L;
     m->W = fq::words_for_len(L);
@@ -950,18 +1003,20 @@ int fqtk_b200_matcher_assign_batch(fqtk_b200_matcher* m, const uint8_t* rows, ui
             size_t nocalls = 0;
             for (uint32_t k = 0; k < len; k++) nocalls += fq::byte_is_nocall(r[k]);
             if (nocalls > (size_t)m->max_mm + m->max_ns) continue;  // pre-filter makes it None before the panic
-            char buf[160];
-            std::snprintf(buf, sizeof buf, "Read barcode (row %llu) length (%u) differs from expected barcode (",
-                          (unsigned long long)i, len);
-            std::string msg(buf);
+            // the reference's panic text (barcode_matching.rs:99-105): decoded read, lengths, sample 0's barcode; the
+            // sample id is not known on this side of the boundary, so the sample INDEX (always 0: the scan panics at
+            // the first barcode) stands in for it — the host mirrors put the id back
+            std::string msg = "Read barcode (";
+            for (uint32_t k = 0; k < len; k++) msg.push_back(decode_mask(fq::encode_byte(r[k])));
+            msg += ") length (" + std::to_string(len) + ") differs from expected barcode (";
             msg.append(reinterpret_cast<const char*>(m->panel.data()), L);
-            std::snprintf(buf, sizeof buf, ") length (%u) for sample 0", L);
-            msg += buf;
+            msg += ") length (" + std::to_string(L) + ") for sample 0";
             return fail(FQTK_B200_ERR_LENGTH, msg);
         }
     }
     CU(cudaSetDevice(m->device));
-    uint64_t chunk = CHUNK_BYTES / std::max<uint64_t>(stride, 1);
+    PipelineDrain drain{m};
+    uint64_t chunk = m->opt.chunk_bytes / std::max<uint64_t>(stride, 1);
     chunk = std::max<uint64_t>(chunk, 1024);
     chunk = std::min<uint64_t>(chunk, n);
     chunk &= ~3ull;
@@ -978,7 +1033,7 @@ int fqtk_b200_matcher_assign_batch(fqtk_b200_matcher* m, const uint8_t* rows, ui
         if (copy_bytes) CU(cudaMemcpyAsync(m->d_in[slot], rows + done * stride, copy_bytes, cudaMemcpyHostToDevice, st));
         if (lengths) CU(cudaMemcpyAsync(m->d_len[slot], lengths + done, c * 4, cudaMemcpyHostToDevice, st));
         fq::ReadSource src{nullptr, m->d_in[slot], lengths ? m->d_len[slot] : nullptr, stride, c};
-        rc = run_device(m, src, m->d_out[slot], st);
+        rc = run_device(m, src, m->d_out[slot], st, slot);
         if (rc != FQTK_B200_OK) return rc;
         CU(cudaMemcpyAsync(results + done, m->d_out[slot], c * 4, cudaMemcpyDeviceToHost, st));
         done += c;
@@ -1012,17 +1067,6 @@ static int check_segments(const fqtk_b200_matcher* m, const fqtk_b200_segment* s
     return FQTK_B200_OK;
 }
 
-static int ensure_scratch(fqtk_b200_matcher* m, uint32_t** slot, size_t* cap, size_t words) {
-    if (words > *cap) {
-        if (*slot) cudaFree(*slot);
-        *slot = nullptr;
-        CU(cudaMalloc(slot, words * 4));
-        *cap = words;
-    }
-    (void)m;
-    return FQTK_B200_OK;
-}
-
 int fqtk_b200_matcher_assign_segments_device(fqtk_b200_matcher* m, const fqtk_b200_segment* segs, uint32_t n_segs,
                                              uint64_t n, uint32_t* d_results, void* stream) {
     fq::SegmentSource ss{};
@@ -1031,7 +1075,7 @@ int fqtk_b200_matcher_assign_segments_device(fqtk_b200_matcher* m, const fqtk_b2
     if (n && !d_results) return fail(FQTK_B200_ERR_ARG, "NULL results");
     if (n >= (1ull << 32)) return fail(FQTK_B200_ERR_ARG, "n_reads must be < 2^32 per device call");
     CU(cudaSetDevice(m->device));
-    rc = ensure_scratch(m, &m->d_scratch, &m->scratch_words, (size_t)n * m->W + 4);
+    rc = ensure_scratch(&m->d_scratch, &m->scratch_words, (size_t)n * m->W + 4);
     if (rc != FQTK_B200_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     CU(fq::launch_pack_segments(ss, n, m->L, m->d_scratch, m->geo, st));
@@ -1047,6 +1091,7 @@ int fqtk_b200_matcher_assign_segments(fqtk_b200_matcher* m, const fqtk_b200_segm
     if (n == 0) return FQTK_B200_OK;
     if (!results) return fail(FQTK_B200_ERR_ARG, "NULL results");
     CU(cudaSetDevice(m->device));
+    PipelineDrain drain{m};
     // sources may overlap or alias (two segments of the same FASTQ row): ship each distinct (base, stride) once
     uint32_t n_src = 0, src_of[FQTK_B200_MAX_SEGMENTS];
     const uint8_t* sbase[FQTK_B200_MAX_SEGMENTS];
@@ -1065,13 +1110,13 @@ int fqtk_b200_matcher_assign_segments(fqtk_b200_matcher* m, const fqtk_b200_segm
     }
     uint64_t bytes_per_read = 0;
     for (uint32_t k = 0; k < n_src; k++) bytes_per_read += sstride[k];
-    uint64_t chunk = std::max<uint64_t>(CHUNK_BYTES / std::max<uint64_t>(bytes_per_read, 1), 1024);
+    uint64_t chunk = std::max<uint64_t>(m->opt.chunk_bytes / std::max<uint64_t>(bytes_per_read, 1), 1024);
     chunk = std::min<uint64_t>(chunk, n) & ~3ull;
     if (chunk == 0) chunk = n;
     rc = ensure_pipeline(m, (size_t)(chunk * bytes_per_read + 64 * n_src), (size_t)chunk, false);
     if (rc != FQTK_B200_OK) return rc;
     for (int s = 0; s < N_PIPE; s++) {
-        rc = ensure_scratch(m, &m->d_seg_packed[s], &m->seg_packed_words[s], (size_t)chunk * m->W + 4);
+        rc = ensure_scratch(&m->d_seg_packed[s], &m->seg_packed_words[s], (size_t)chunk * m->W + 4);
         if (rc != FQTK_B200_OK) return rc;
     }
     uint64_t done = 0;

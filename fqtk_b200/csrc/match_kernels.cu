@@ -279,30 +279,68 @@ __global__ void __launch_bounds__(BRUTE_THREADS) k_brute(const MatchParams p, co
     cnt.flush();
 }
 
-// L > 32: nibble-word form straight from the packed layout (rare; barcodes this long are unusual).
+// L > 32 (W = 5 .. 32 packed words; rare — barcodes this long are unusual): nibble-word form straight from the packed
+// layout.  The read's words stay in registers (WMAX is a compile-time bound, every loop over them is fully unrolled and
+// predicated on the real W), the panel's ~expected words are staged in shared memory, padded to a multiple of four words
+// per barcode so that a (warp-uniform, broadcast) LDS.128 fetches four at a time; when the panel does not fit it is read
+// through the read-only cache instead.  Per word: x = r & ~exp; a nibble of x is non-zero iff the symbol mismatches
+// (bitenc.rs:441-452); the per-nibble flags of four words share one POPC.  Rows whose length differs from L (only when
+// the caller passed lengths) are None (barcode_matching.rs:167-169; longer rows were vetted by the host).
+template <int WMAX, bool PANEL_SMEM>
 __global__ void __launch_bounds__(256) k_brute_long(const MatchParams p, const ReadSource src,
                                                     uint32_t* __restrict__ results) {
+    static_assert(WMAX % 4 == 0, "four words per LDS.128");
     extern __shared__ uint4 s_dyn[];
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_dyn);
+    const uint32_t W = p.W, Wq = (W + 3u) / 4u;  // Wq = uint4 entries per barcode
+    uint4* s_ne = s_dyn;
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_dyn + (PANEL_SMEM ? (size_t)p.S * Wq : 0));
+    if constexpr (PANEL_SMEM) {
+        uint32_t* flat = reinterpret_cast<uint32_t*>(s_ne);
+        for (uint32_t t = threadIdx.x; t < p.S * Wq * 4u; t += blockDim.x) {
+            const uint32_t j = t / (Wq * 4u), k = t % (Wq * 4u);
+            flat[t] = k < W ? __ldg(p.not_exp + (size_t)j * W + k) : 0u;
+        }
+    }
     Counter cnt;
     cnt.init(s_hist, p);
     __syncthreads();
     const uint64_t total = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < src.n; i += total) {
-        uint32_t r[32];
-        for (uint32_t k = 0; k < p.W; k++) r[k] = __ldg(src.packed + i * p.W + k);
-        uint32_t k1 = EMPTY_KEY, k2 = EMPTY_KEY;
-        for (uint32_t j = 0; j < p.S; j++) {
-            uint32_t d = 0;
-            for (uint32_t k = 0; k < p.W; k++) {
-                uint32_t x = r[k] & __ldg(p.not_exp + (size_t)j * p.W + k);
-                x |= x >> 1;
-                x |= x >> 2;
-                d += __popc(x & 0x11111111u);
+        uint32_t res = NONE;
+        if (src.lengths == nullptr || __ldg(src.lengths + i) == p.L) {
+            uint32_t r[WMAX];
+#pragma unroll
+            for (int k = 0; k < WMAX; k++) r[k] = (uint32_t)k < W ? __ldg(src.packed + i * W + k) : 0u;
+            uint32_t k1 = EMPTY_KEY, k2 = EMPTY_KEY;
+            for (uint32_t j = 0; j < p.S; j++) {
+                uint32_t d = 0;
+#pragma unroll
+                for (int q = 0; q < WMAX / 4; q++) {
+                    if ((uint32_t)q < Wq) {
+                        uint4 ne;
+                        if constexpr (PANEL_SMEM) {
+                            ne = s_ne[j * Wq + q];
+                        } else {
+                            const uint32_t* g = p.not_exp + (size_t)j * W + 4 * q;
+                            ne.x = __ldg(g);
+                            ne.y = 4u * q + 1u < W ? __ldg(g + 1) : 0u;
+                            ne.z = 4u * q + 2u < W ? __ldg(g + 2) : 0u;
+                            ne.w = 4u * q + 3u < W ? __ldg(g + 3) : 0u;
+                        }
+                        // bit 3 of every nibble of f* = "this nibble of (r & ~exp) is non-zero"
+                        const uint32_t x0 = r[4 * q] & ne.x, x1 = r[4 * q + 1] & ne.y, x2 = r[4 * q + 2] & ne.z,
+                                       x3 = r[4 * q + 3] & ne.w;
+                        const uint32_t f0 = (((x0 & 0x77777777u) + 0x77777777u) | x0) & 0x88888888u;
+                        const uint32_t f1 = (((x1 & 0x77777777u) + 0x77777777u) | x1) & 0x88888888u;
+                        const uint32_t f2 = (((x2 & 0x77777777u) + 0x77777777u) | x2) & 0x88888888u;
+                        const uint32_t f3 = (((x3 & 0x77777777u) + 0x77777777u) | x3) & 0x88888888u;
+                        d += (uint32_t)__popc(f0 | (f1 >> 1) | (f2 >> 2) | (f3 >> 3));
+                    }
+                }
+                track2(k1, k2, (d << 16) | j);
             }
-            track2(k1, k2, (d << 16) | j);
+            res = decide(k1, k2, p.max_mm, p.min_delta);
         }
-        const uint32_t res = decide(k1, k2, p.max_mm, p.min_delta);
         results[i] = res;
         cnt.add(res);
     }
@@ -1436,17 +1474,35 @@ static cudaError_t launch_brute_w(const MatchParams& p, const ReadSource& src, u
     }
 }
 
+template <int WMAX>
+static cudaError_t launch_brute_long_w(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
+                                       const LaunchGeometry& g, cudaStream_t stream) {
+    const size_t hb = hist_bytes(p);
+    const size_t panel_bytes = (size_t)p.S * ((p.W + 3u) / 4u) * sizeof(uint4);
+    if (panel_bytes + hb + 1024 <= (size_t)g.max_smem_optin) {
+        auto k = k_brute_long<WMAX, true>;
+        const size_t smem = panel_bytes + hb;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int grid = grid_for(k, 256, smem, g, src.n);
+        k<<<grid, 256, smem, stream>>>(p, src, d_results);
+    } else {
+        auto k = k_brute_long<WMAX, false>;
+        const int grid = grid_for(k, 256, hb, g, src.n);
+        k<<<grid, 256, hb, stream>>>(p, src, d_results);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_brute(const MatchParams& p, const ReadSource& src, uint32_t* d_results, const LaunchGeometry& g,
                          cudaStream_t stream) {
     if (src.n == 0) return cudaSuccess;
     const bool ascii = src.ascii != nullptr;
     if (p.W > (uint32_t)MAX_FAST_WORDS) {
         if (ascii) return cudaErrorInvalidValue;  // caller packs first
-        const size_t hb = hist_bytes(p);
-        const int grid = grid_for(k_brute_long, 256, hb, g, src.n);
-        k_brute_long<<<grid, 256, hb, stream>>>(p, src, d_results);
-        count_launch();
-        return cudaGetLastError();
+        return p.W <= 8u ? launch_brute_long_w<8>(p, src, d_results, g, stream)
+                         : (p.W <= 16u ? launch_brute_long_w<16>(p, src, d_results, g, stream)
+                                       : launch_brute_long_w<32>(p, src, d_results, g, stream));
     }
     switch (p.W) {
         case 1: return ascii ? launch_brute_w<1, true>(p, src, d_results, g, stream) : launch_brute_w<1, false>(p, src, d_results, g, stream);

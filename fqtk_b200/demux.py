@@ -71,7 +71,7 @@ def extract_segments(structure, seq: bytes, qual: bytes) -> list[tuple[str, byte
 @dataclass
 class DemuxResult:
     files: dict = field(default_factory=dict)     # "<prefix>.<code><n>.fq.gz" -> [Record, ...] in input order
-    counts: np.ndarray | None = None              # S + 1, last = unmatched (skipped read-sets are counted nowhere)
+    counts: np.ndarray | None = None              # THIS batch: S + 1, last = unmatched (skipped read-sets are counted nowhere)
     metrics: list[DemuxMetric] = field(default_factory=list)
     skipped: int = 0
 
@@ -127,6 +127,8 @@ def demux_batch(matcher, sample_ids: Sequence[str], barcodes: Sequence[str], rea
                 for idx, (_, s, q) in enumerate([x for x in segs if x[0] == kind]):
                     head = write_header(idx + 1, header, sample_bcs, umis)[1:]
                     result.files.setdefault(f"{prefix}.{FILE_TYPE_CODE[kind]}{idx + 1}.fq.gz", []).append((head, s, q))
-    result.counts = matcher.counts()
+    # this batch's table, from the routing offsets (the matcher's own counters are running totals over every call
+    # since the last reset_counts, single assign() calls included)
+    result.counts = np.diff(np.asarray(offsets, dtype=np.uint64)).astype(np.uint64)
     result.metrics = demux_metrics(list(sample_ids), list(barcodes), [int(c) for c in result.counts], unmatched_prefix)
     return result

@@ -47,10 +47,44 @@ def demux_metrics(sample_ids: Sequence[str], barcodes: Sequence[str], counts: Se
     return rows + [unmatched]
 
 
+def format_f64(x: float) -> str:
+    """An f64 as the reference's csv writer prints it (serde -> csv -> ryu: shortest round-trip digits; exponent form
+    `1e-5` / `1.5e16` below 1e-5 and from 1e16 up, without '+' or leading zeros; `NaN`, `inf`, `-inf`)."""
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "inf" if x > 0 else "-inf"
+    if x == 0.0:
+        return "-0.0" if str(x).startswith("-") else "0.0"
+    r = repr(float(x))  # shortest round-trip digits, like ryu
+    sign = "-" if r.startswith("-") else ""
+    r = r.lstrip("-")
+    if "e" in r:
+        mant, exp = r.split("e")
+        e10 = int(exp)
+    else:
+        mant, e10 = r, 0
+    ip, _, fp = mant.partition(".")
+    digits = (ip + fp).lstrip("0")
+    # decimal exponent of the first significant digit
+    if ip.strip("0"):
+        e10 += len(ip.lstrip("0")) - 1
+    else:
+        e10 -= len(fp) - len(fp.lstrip("0")) + 1
+    digits = digits.rstrip("0") or "0"
+    if -5 <= e10 < 16:  # ryu's plain-decimal range
+        if e10 >= 0:
+            whole, frac = digits[: e10 + 1].ljust(e10 + 1, "0"), digits[e10 + 1:]
+            return f"{sign}{whole}.{frac or '0'}"
+        return f"{sign}0.{'0' * (-e10 - 1)}{digits}"
+    mant = digits[0] + ("." + digits[1:] if len(digits) > 1 else "")
+    return f"{sign}{mant}e{e10}"
+
+
 def write_tsv(path: str, metrics: Sequence[DemuxMetric]) -> None:
     """Tab-separated with the reference's column order (serde field order of DemuxMetric)."""
     with open(path, "w", encoding="utf-8") as fh:
         fh.write("\t".join(HEADER) + "\n")
         for m in metrics:
-            fh.write(f"{m.sample_id}\t{m.barcode}\t{m.templates}\t{m.frac_templates!r}\t{m.ratio_to_mean!r}\t"
-                     f"{m.ratio_to_best!r}\n")
+            fh.write(f"{m.sample_id}\t{m.barcode}\t{m.templates}\t{format_f64(m.frac_templates)}\t"
+                     f"{format_f64(m.ratio_to_mean)}\t{format_f64(m.ratio_to_best)}\n")

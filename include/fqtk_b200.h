@@ -92,10 +92,28 @@ typedef struct {
 FQTK_B200_API int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t n_samples, uint32_t barcode_len,
                                            uint8_t max_mismatches, uint8_t min_mismatch_delta, int use_cache,
                                            int device, fqtk_b200_matcher** out);
+/* The same with per-handle options instead of the defaults (two host threads may create matchers concurrently:
+ * nothing about a handle depends on process-global state).  Initialise with fqtk_b200_options_init, then change fields. */
+#define FQTK_B200_KERNEL_AUTO (-1) /* k_probe3 when the pure-A/C/G/T memo entries fit in shared memory, else k_probe5 / k_probe4 */
+typedef struct {
+    uint32_t struct_size;       /* sizeof(fqtk_b200_options) as the caller compiled it (lets the struct grow) */
+    int32_t kernel;             /* packed-route kernel: FQTK_B200_KERNEL_AUTO, 0 = k_probe2 only, 1 = the L2-resident table
+                                   only, 2 / 3 = k_probe3 with that many sub-tables.  Results are identical for every value */
+    uint64_t table_budget;      /* largest neighbourhood (candidate strings) a memo table is built for; 0 = 32 Mi */
+    uint64_t chunk_bytes;       /* input bytes per chunk of the host-buffer pipeline; 0 = 32 MiB */
+    uint32_t l2_table_load_pct; /* load factor of the L2-resident table in percent, 0 = automatic */
+    uint32_t reserved;
+} fqtk_b200_options;
+FQTK_B200_API void fqtk_b200_options_init(fqtk_b200_options* opts);
+FQTK_B200_API int fqtk_b200_matcher_create_ex(const uint8_t* panel_ascii, uint32_t n_samples, uint32_t barcode_len,
+                                              uint8_t max_mismatches, uint8_t min_mismatch_delta, int use_cache,
+                                              int device, const fqtk_b200_options* opts, fqtk_b200_matcher** out);
 FQTK_B200_API void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m);
 FQTK_B200_API int fqtk_b200_matcher_get_info(const fqtk_b200_matcher* m, fqtk_b200_matcher_info* info);
+/* Deprecated convenience (kept for the tests and A/B timing): defaults of fqtk_b200_matcher_create for matchers created
+ * afterwards BY THE CALLING THREAD (thread-local, so concurrent creates on other threads are unaffected). */
 FQTK_B200_API void fqtk_b200_set_table_budget(uint64_t max_candidates);
-/* Tuning / test knob for matchers created afterwards — which kernel the HBM-resident packed route runs:
+/* Which kernel the HBM-resident packed route runs (= options.kernel):
  * -1 = automatic (default): k_probe3 (shared-memory cuckoo table of the pure-A/C/G/T memo entries) when it fits
  *      (L <= 16), else k_probe4 (the same entries in an L2-resident table of 8-byte slots, L <= 24), else k_probe2;
  *  0 = k_probe2 only;  1 = k_probe4's table only;  2 or 3 = k_probe3 with that many sub-tables.

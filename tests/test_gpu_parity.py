@@ -197,6 +197,93 @@ def test_long_barcodes_take_the_generic_kernel():
         check_against_oracle(bcs, 2, 1, reads, use_cache=True, expect_mode="brute")
 
 
+def test_long_barcodes_through_a_multi_chunk_pipeline_and_with_row_lengths():
+    """the L > 32 host-buffer route packs into scratch before the long-barcode kernel; consecutive chunks run
+    on different streams, so the scratch must be per pipeline slot (a shared one is overwritten while it is read).
+    chunk_bytes = 64 KiB makes 30 000 reads of 40 bases span ~19 chunks.  Also: per-row lengths at L > 32 (the
+    reference-facing assign() always passes one) — shorter rows are None, longer rows panic unless pre-filtered."""
+    rng = np.random.default_rng(55)
+    for L, S in ((40, 23), (70, 9)):
+        bcs = random_panel(rng, S, L, ALPHABETS["iupac"])
+        n = 30_000
+        reads = random_reads(rng, bcs, L, n, ALPHABETS["dirty"])
+        om = oracle.OracleMatcher(bcs, 3, 1, use_cache=True)
+        want, want_counts = om.assign_batch(reads, mode=0)
+        assert (want != _lib.NONE).sum() > n // 10
+        with BarcodeMatcher(bcs, 3, 1, use_cache=True, chunk_bytes=64 << 10) as m:
+            assert m.mode == "brute"
+            for _ in range(3):  # races are timing dependent: several passes
+                m.reset_counts()
+                got = m.assign_batch(reads)
+                assert np.array_equal(got, want)
+                assert np.array_equal(m.counts(), want_counts)
+            # ragged rows: every third row loses its tail (-> None), lengths passed explicitly
+            lens = np.full(n, L, dtype=np.uint32)
+            lens[::3] = rng.integers(0, L, size=len(lens[::3]))
+            want2 = want.copy()
+            want2[::3] = _lib.NONE
+            m.reset_counts()
+            got2 = m.assign_batch(reads, lengths=lens)
+            assert np.array_equal(got2, want2)
+            assert int(m.counts()[-1]) == int((want2 == _lib.NONE).sum())
+            # the single-read call of the reference interface
+            for i in (0, 1, 2, 5, 11):
+                assert m.assign(bytes(reads[i])) == oracle_match(om, bytes(reads[i]))
+            assert m.assign(bytes(reads[0][: L - 1])) is None
+            with pytest.raises(MatcherPanic, match=r"length \(%d\) differs from expected barcode" % (L + 1)):
+                m.assign(bcs[0] + b"A")  # its no-calls are within max_mismatches + max_ns_in_barcodes: no pre-filter
+            assert m.assign(b"N" * (L + 1)) is None  # the no-call pre-filter fires before the length panic
+
+
+def oracle_match(om, read):
+    w = int(om.assign_batch(np.frombuffer(read, dtype=np.uint8).reshape(1, -1), mode=0)[0][0])
+    return None if w == _lib.NONE else BarcodeMatch(w >> 16, (w >> 8) & 0xFF, w & 0xFF)
+
+
+def test_length_panic_text_is_the_reference_text():
+    """barcode_matching.rs:99-105 and its test (:326-341): decoded read, both lengths, the first sample's barcode and id."""
+    from fqtk_b200.samples import Sample
+
+    samples = [Sample("sample_0", "CTATGT", 0), Sample("sample_1", "GGGGGG", 1)]
+    with BarcodeMatcher(samples, 1, 1) as m:
+        with pytest.raises(MatcherPanic) as ei:
+            m.assign(b"GATTACAn")
+        assert ei.value.args[0] == ("Read barcode (GATTACAN) length (8) differs from expected barcode (CTATGT) length (6) "
+                                    "for sample sample_0")
+    with BarcodeMatcher(["CTATGT"], 1, 1) as m:  # bare barcodes: the sample index stands in for the id
+        with pytest.raises(MatcherPanic, match=r"length \(7\) differs from expected barcode \(CTATGT\) length \(6\) for sample 0"):
+            m.assign(b"GATTACA")
+
+
+def test_matchers_created_concurrently_with_different_options():
+    """Per-handle options (create_ex): two host threads creating matchers at the same time cannot influence each other."""
+    import threading
+
+    cfg = synth.CONFIGS[2]
+    panel = synth.panel(cfg)
+    bcs = [bytes(r) for r in panel]
+    reads = synth.reads_host(panel, cfg.seed_reads, 0, 50_000)
+    want, _ = oracle.OracleMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta).assign_batch(reads)
+    out = {}
+
+    def work(kernel):
+        for _ in range(3):
+            with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, True, kernel=kernel) as m:
+                info = m.info()
+                out.setdefault(kernel, []).append((int(info.cuckoo_probes), int(info.l2_table_entries),
+                                                   np.array_equal(m.assign_batch(reads), want)))
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in (0, 1, 2, 3)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for k in (0, 1, 2, 3):
+        assert len(out[k]) == 3
+        for probes, l2e, ok in out[k]:
+            assert ok
+            assert probes == (k if k >= 2 else 0), (k, probes)
+            assert (l2e > 0) == (k == 1), (k, l2e)
+
+
 def test_many_samples_use_global_histogram_and_big_panel():
     rng = np.random.default_rng(6)
     S, L = 9000, 12  # S + 1 > 8192 shared-memory bins

@@ -182,6 +182,30 @@ def test_demux_metrics_follow_the_reference_update_rule(tmp_path):
     assert rows[0].frac_templates != rows[0].frac_templates
 
 
+def test_metrics_floats_print_like_the_reference_csv_writer(tmp_path):
+    """serde -> csv -> ryu: shortest round-trip digits, exponent form without '+' / leading zeros below 1e-5 and from
+    1e16 up, NaN / inf spelled the Rust way (Python's repr gives 1e-05 / 1e+16 / nan)."""
+    from fqtk_b200.metrics import demux_metrics, format_f64, write_tsv
+
+    want = {0.5: "0.5", 1.0: "1.0", 0.0: "0.0", 2 / 3: "0.6666666666666666", 1e-5: "0.00001", 1.5e-5: "0.000015",
+            9.999e-6: "9.999e-6", 1e-7: "1e-7", 1.234e-10: "1.234e-10", 1e15: "1000000000000000.0", 1e16: "1e16",
+            1.5e16: "1.5e16", 123456.789: "123456.789", float("inf"): "inf", float("-inf"): "-inf", -2.5e-9: "-2.5e-9"}
+    for x, text in want.items():
+        assert format_f64(x) == text, (x, format_f64(x), text)
+        if x == x and abs(x) != float("inf"):
+            assert float(format_f64(x)) == x  # round-trips
+    assert format_f64(float("nan")) == "NaN"
+    # a rare sample in a large run lands in the exponent range
+    rows = demux_metrics(["rare", "big"], ["AAAA", "CCCC"], [3, 2_000_000_000, 0])
+    f = tmp_path / "m.txt"
+    write_tsv(str(f), rows)
+    rare = f.read_text().splitlines()[1].split("\t")
+    assert rare[3] == "1.49999999775e-9" and "e-0" not in rare[3] and "e+" not in "".join(rare)
+    empty = demux_metrics(["a"], ["AAAA"], [0, 0])
+    write_tsv(str(f), empty)
+    assert f.read_text().splitlines()[1].split("\t")[3:] == ["NaN", "NaN", "NaN"]
+
+
 def test_write_header_reference_kats(kats):
     """ReadSet::write_header_internal (demux.rs:171-267) against the reference's own six tests (:2084-2196)."""
     from fqtk_b200.headers import HeaderError, write_header
