@@ -299,8 +299,7 @@ def run_b200(args):
     info = matcher.info()
     kernel = "k_brute" if mode != "table" else (
         f"k_probe3<W={W},NP={int(info.cuckoo_probes)}>" if int(info.cuckoo_probes) and W <= 2 else
-        f"k_probe4<W={W}>" if int(info.l2_table_entries) and (W == 3 or args.cuckoo == 1) else
-        "k_probe2+l2table" if int(info.l2_table_entries) else "k_probe2")
+        f"k_probe4<W={W}>" if int(info.l2_table_entries) else "k_probe2")
     counts_t = torch.zeros(cfg.n_samples + 1, dtype=torch.int64, device=dev)
 
     def barrier():

@@ -41,6 +41,7 @@ class MatcherInfo(C.Structure):
         ("table_candidates", C.c_uint64), ("tier_entries", C.c_uint64), ("tier_slots", C.c_uint64),
         ("cuckoo_entries", C.c_uint64), ("cuckoo_probes", C.c_uint32), ("cuckoo_slots", C.c_uint32),
         ("l2_table_entries", C.c_uint64), ("l2_table_bytes", C.c_uint64),
+        ("l2_table_slow_keys", C.c_uint64),
     ]
 
 

@@ -94,8 +94,9 @@ struct fqtk_b200_matcher {
     uint32_t* d_tier = nullptr;
     uint32_t* d_bloom = nullptr;
     uint32_t* d_cuckoo = nullptr;
-    uint2* d_g4 = nullptr;
-    uint64_t g4_entries = 0;
+    uint32_t* d_g4 = nullptr;
+    uint64_t g4_entries = 0, g4_slow_keys = 0;
+    std::vector<uint32_t> h_not_exp;  // host copy of the panel's ~expected nibble words (fingerprint-table build)
     uint64_t cuckoo_entries = 0;
     uint64_t tier_entries = 0;
     unsigned long long* d_counts = nullptr;
@@ -151,9 +152,12 @@ struct Enumerator {
     uint32_t L, W, K;
     std::vector<uint32_t>* out;
     uint32_t cur[fq::MAX_FAST_WORDS];
+    std::vector<uint32_t>* owner = nullptr;  // optional: the barcode each string was enumerated from
+    uint32_t barcode = 0;
     void rec(uint32_t i, uint32_t used) {
         if (i == L) {
             out->insert(out->end(), cur, cur + W);
+            if (owner) owner->push_back(barcode);
             return;
         }
         const uint32_t word = i >> 3, sh = 4u * (i & 7u);
@@ -404,100 +408,148 @@ int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, cons
     return 1;
 }
 
-// k_probe4's global table (kernels.h): every Some(..) memo entry whose key is pure A/C/G/T under its compressed key, in
-// 8-byte slots, four to a 32-byte bucket, bucketised linear probing at load 0.4 - 0.65 so that it stays L2-resident
-// (cfg 4: 1.7 M entries, 35 MB instead of the memo table's 122 MB).  Returns 0 when built, 1 when the panel does not qualify, < 0 on error.
+// k_probe4's global fingerprint table (kernels.h): every candidate string — every A/C/G/T/N string within max_mm of
+// some barcode, whether its result is Some or None — as a 4-byte entry fingerprint | sample index | value code, eight to a
+// 32-byte bucket, bucketised linear probing.  The kernel's lookup is replayed here for every key: a key must come back
+// with its own value or be sent to the (exact) slow path; if any key comes back with a WRONG value — a fingerprint
+// collision with an entry of another barcode that the read is also within max_mm of — the hash is re-seeded.
+// Returns 0 when built, 1 when the panel does not qualify, < 0 on error.
 template <int W>
-int build_g4_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, const std::vector<uint32_t>& res, uint64_t n) {
-    const uint32_t S = m->S, L = m->L, pad = m->params.last_pad;
-    if (S + 1u > 8192u || L > 24u) return 1;
-    const uint32_t hi_bits = L > 16u ? 2u * (L - 16u) : 0u;
-    const uint32_t hi_mask = hi_bits ? ((1u << hi_bits) - 1u) : 0u;
-    struct Ent { uint32_t lo, hi, word; };
-    std::vector<Ent> ent;
+int build_g4_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, const std::vector<uint32_t>& res,
+               const std::vector<uint32_t>& owners, uint64_t n) {
+    const uint32_t S = m->S;
+    if (S + 1u > 8192u || owners.size() != n) return 1;
+    struct Ent { uint32_t w[W]; uint32_t word, owner; };
+    std::vector<Ent> ent(n);
     for (uint64_t t = 0; t < n; t++) {
-        if (res[t] == fq::NONE) continue;
-        uint32_t kw[W];
-        for (int k = 0; k < W; k++) kw[k] = keys[t * W + k];
-        bool valid;
-        uint32_t hi;
-        const uint32_t lo = fq::acgt_key64<W>(kw, pad, hi_mask, hi, valid);
-        if (valid) ent.push_back({lo, hi, res[t]});
+        for (int k = 0; k < W; k++) ent[t].w[k] = keys[t * W + k];
+        ent[t].word = res[t];
+        // a Some entry is verified against its best match, a None candidate against the barcode that enumerated it
+        ent[t].owner = res[t] != fq::NONE ? (res[t] >> 16) : owners[t];
     }
-    std::sort(ent.begin(), ent.end(), [](const Ent& a, const Ent& b) {
-        return a.hi != b.hi ? a.hi < b.hi : (a.lo != b.lo ? a.lo < b.lo : a.word < b.word);
-    });
-    ent.erase(std::unique(ent.begin(), ent.end(), [](const Ent& a, const Ent& b) {
-        return a.lo == b.lo && a.hi == b.hi && a.word == b.word; }), ent.end());
+    auto key_less = [](const Ent& a, const Ent& b) {
+        for (int k = W - 1; k >= 0; k--)
+            if (a.w[k] != b.w[k]) return a.w[k] < b.w[k];
+        return false;
+    };
+    auto key_eq = [](const Ent& a, const Ent& b) {
+        for (int k = 0; k < W; k++)
+            if (a.w[k] != b.w[k]) return false;
+        return true;
+    };
+    std::sort(ent.begin(), ent.end(), key_less);
     for (size_t t = 1; t < ent.size(); t++)
-        if (ent[t].lo == ent[t - 1].lo && ent[t].hi == ent[t - 1].hi) return 1;  // cannot happen: one string, one result
+        if (key_eq(ent[t], ent[t - 1]) && ent[t].word != ent[t - 1].word) return 1;  // cannot happen: one string, one result
+    ent.erase(std::unique(ent.begin(), ent.end(), key_eq), ent.end());
     if (ent.empty()) return 1;
-    // value code (L > 16 only) = idx << (bb + nb) | best << nb | (next - next_min), as in k_probe3
-    uint32_t max_idx = 0, max_best = 0, min_next = 255, max_next = 0;
+    auto distance_to = [&](const Ent& e, uint32_t j) {
+        uint32_t ne[W];
+        for (int k = 0; k < W; k++) ne[k] = m->h_not_exp[(size_t)j * W + k];
+        return fq::nibble_distance<W>(e.w, ne);
+    };
+    std::vector<uint32_t> owner(ent.size());
+    for (size_t t = 0; t < ent.size(); t++) {
+        owner[t] = ent[t].owner;
+        if (distance_to(ent[t], owner[t]) > m->max_mm)
+            return fail(FQTK_B200_ERR_CUDA, "fingerprint table: a candidate is farther than max_mm from its barcode");
+    }
+    // value code = best << nb | (next - next_min)
+    uint32_t max_best = 0, min_next = 255, max_next = 0;
     for (auto& e : ent) {
-        max_idx = std::max(max_idx, e.word >> 16);
+        if (e.word == fq::NONE) continue;
         max_best = std::max(max_best, (e.word >> 8) & 0xFFu);
         min_next = std::min(min_next, e.word & 0xFFu);
         max_next = std::max(max_next, e.word & 0xFFu);
     }
+    if (min_next > max_next) min_next = max_next = 0;  // no Some entry at all
     auto bits_for = [](uint32_t v) { uint32_t b = 0; while (b < 32 && (v >> b)) b++; return b; };
-    const uint32_t ib = bits_for(max_idx), bb = bits_for(max_best), nb = bits_for(max_next - min_next);
-    uint32_t vb = std::max(1u, ib + bb + nb);
-    auto code_of = [&](uint32_t r) {
-        return ((r >> 16) << (bb + nb)) | (((r >> 8) & 0xFFu) << nb) | ((r & 0xFFu) - min_next);
+    const uint32_t ib = std::max(1u, bits_for(S - 1u)), bb = bits_for(max_best), nb = bits_for(max_next - min_next);
+    uint32_t cb = std::max(1u, bb + nb);
+    const uint32_t max_code = (max_best << nb) | (max_next - min_next);
+    while (max_code >= (1u << cb) - 2u) cb++;  // 2^cb - 2 = None candidate, 2^cb - 1 = empty slot
+    if (ib + cb > 24u) return 1;               // fewer than 8 fingerprint bits
+    const uint32_t fp_bits = 32u - ib - cb, fp_shift = ib + cb;
+    auto entry_of = [&](size_t t, uint32_t fp_in_place) {
+        const uint32_t w = ent[t].word;
+        const uint32_t code = w == fq::NONE ? (1u << cb) - 2u : ((((w >> 8) & 0xFFu) << nb) | ((w & 0xFFu) - min_next));
+        return fp_in_place | (owner[t] << cb) | code;
     };
-    if (hi_bits) {
-        for (auto& e : ent)
-            if (code_of(e.word) == (1u << vb) - 1u) { vb++; break; }  // the all-ones code marks an empty slot
-        if (hi_bits + vb > 32u) return 1;
-    }
-    // load factor: shorter overflow chains (0.4) while the table stays well inside L2, else denser (0.65) so that it
-    // still fits next to the stream — measured on B200: cfg 4 5.10 ms at 0.6 / 4.67 at 0.4 / 4.68 at 0.15 (92 MB);
-    // cfg 5 20.5 ms at 0.7 / 20.8 at 0.6 / 24.1 at 0.4 (50 MB) / 28.5 at 0.15 / 58 at 0.88.  FQTK_B200_G4_LOAD = percent
-    // overrides (A/B timing).
-    const double g4_load_env = m->opt.l2_table_load_pct ? m->opt.l2_table_load_pct / 100.0 : 0.0;
-    const double g4_load = g4_load_env > 0.0 ? g4_load_env
-                                             : ((double)ent.size() * 8.0 / 0.4 <= 40.0 * (1 << 20) ? 0.4 : 0.65);
-    const uint64_t buckets64 = std::max<uint64_t>(16, (uint64_t)((double)ent.size() / (4 * g4_load)) + 1);
-    if (buckets64 >= (1ull << 29)) return 1;
-    const uint32_t n_buckets = (uint32_t)buckets64;
-    auto hi_word = [&](const Ent& e) { return hi_bits ? ((e.hi << vb) | code_of(e.word)) : e.word; };
-    std::vector<uint2> table((size_t)n_buckets * 4, make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu));
-    for (auto& e : ent) {
-        uint32_t b = fq::g4_bucket(e.lo, e.hi, n_buckets);
-        while (table[(size_t)b * 4 + 3].y != 0xFFFFFFFFu) b = (b + 1u == n_buckets) ? 0u : b + 1u;  // full: next bucket
-        uint32_t j = 0;
-        while (table[(size_t)b * 4 + j].y != 0xFFFFFFFFu) j++;
-        table[(size_t)b * 4 + j] = make_uint2(e.lo, hi_word(e));
-    }
-    // histogram replicas + stash capacity within the shared-memory budget
+    // shared memory of the kernel: ~expected words + histogram replicas + stashes
     const size_t smem_max = (size_t)m->geo.max_smem_optin - 1024;
     uint32_t rep = 16;
     while (rep > 1 && fq::probe4_smem_bytes(W, S, rep, 32) > smem_max) rep >>= 1;
     if (fq::probe4_smem_bytes(W, S, rep, 32) > smem_max) return 1;
     uint32_t cap = 32;
     while (cap < 64 && fq::probe4_smem_bytes(W, S, rep, cap + 1) <= smem_max) cap++;
-    CU(cudaMalloc(&m->d_g4, table.size() * sizeof(uint2)));
-    CU(cudaMemcpy(m->d_g4, table.data(), table.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    // load factor: measured on B200 (profiles/README.md); options.l2_table_load_pct overrides (A/B timing)
+    // cfg 5 (29.6 MB at 0.5): 12.2 ms at 0.4, 10.75 at 0.5, 10.66 at 0.6 — fewer overflow walks vs a smaller table
+    const double load = m->opt.l2_table_load_pct ? m->opt.l2_table_load_pct / 100.0 : 0.55;
+    const uint64_t buckets64 = std::max<uint64_t>(16, (uint64_t)((double)ent.size() / (8 * load)) + 1);
+    if (buckets64 >= (1ull << 28)) return 1;
+    const uint32_t n_buckets = (uint32_t)buckets64;
+    std::vector<uint32_t> table;
+    uint32_t seed = 0;
+    uint64_t slow_keys = 0;
+    bool built = false;
+    for (uint32_t attempt = 0; attempt < 8 && !built; attempt++) {
+        seed = attempt * 0x632BE5ABu;
+        table.assign((size_t)n_buckets * 8, 0xFFFFFFFFu);
+        for (size_t t = 0; t < ent.size(); t++) {
+            uint32_t b, fpp;
+            fq::g4_hashes<W>(ent[t].w, seed, n_buckets, b, fpp);
+            fpp &= 0u - (1u << fp_shift);  // the fingerprint: top fp_bits of the second hash, in place
+            while (table[(size_t)b * 8 + 7] != 0xFFFFFFFFu) b = (b + 1u == n_buckets) ? 0u : b + 1u;  // full: next bucket
+            uint32_t j = 0;
+            while (table[(size_t)b * 8 + j] != 0xFFFFFFFFu) j++;
+            table[(size_t)b * 8 + j] = entry_of(t, fpp);
+        }
+        // replay the kernel's lookup (g4_lookup in match_kernels.cu) for every key
+        built = true;
+        slow_keys = 0;
+        for (size_t t = 0; t < ent.size() && built; t++) {
+            uint32_t b, fpp;
+            fq::g4_hashes<W>(ent[t].w, seed, n_buckets, b, fpp);
+            fpp &= 0u - (1u << fp_shift);  // the fingerprint: top fp_bits of the second hash, in place
+            uint32_t tmin;
+            for (;;) {
+                tmin = 0xFFFFFFFFu;
+                for (int j = 0; j < 8; j++) tmin = std::min(tmin, table[(size_t)b * 8 + j] ^ fpp);
+                if (tmin < (1u << fp_shift) || table[(size_t)b * 8 + 7] == 0xFFFFFFFFu) break;
+                b = (b + 1u == n_buckets) ? 0u : b + 1u;
+            }
+            if (tmin >= (1u << fp_shift)) return fail(FQTK_B200_ERR_CUDA, "fingerprint table self-check failed (key not found)");
+            const uint32_t idx = std::min(tmin >> cb, S - 1u), code = tmin & ((1u << cb) - 1u);
+            if (distance_to(ent[t], idx) > m->max_mm) {  // another key's entry: the kernel parks the read (exact slow path)
+                slow_keys++;
+                continue;
+            }
+            uint32_t word = fq::NONE;
+            if (code < (1u << cb) - 2u) word = (idx << 16) | ((code >> nb) << 8) | ((code & ((1u << nb) - 1u)) + min_next);
+            if (word != ent[t].word) built = false;  // collision that passes verification with another value: re-seed
+        }
+    }
+    if (!built) return 1;
+    CU(cudaMalloc(&m->d_g4, table.size() * 4));
+    CU(cudaMemcpy(m->d_g4, table.data(), table.size() * 4, cudaMemcpyHostToDevice));
     fq::MatchParams& p = m->params;
     p.g4_table = m->d_g4;
     p.g4_buckets = n_buckets;
-    p.g4_himask = hi_mask;
-    p.g4_vb = vb;
-    p.g4_limit = (1u << vb) - 1u;
+    p.g4_seed = seed;
+    p.g4_fp_bits = fp_bits;
+    p.g4_fp_shift = fp_shift;
+    p.g4_cb = cb;
+    p.g4_nb = nb;
+    p.g4_fp_mask = 0u - (1u << fp_shift);
+    p.g4_lim = 1u << fp_shift;
+    p.g4_cmask = (1u << cb) - 1u;
+    p.g4_nmask = (1u << nb) - 1u;
+    p.g4_code_none = (1u << cb) - 2u;
+    p.g4_next_min = min_next;
     p.g4_hist_rep = rep;
     p.g4_stash_cap = cap;
-    // measured on B200: k_probe4 wins where k_probe2 has no useful hot tier (cfg 5, W = 3: 27 -> 21 ms); with a hot
-    // tier that ends 80 % of the reads in shared memory (cfg 4) k_probe2 + this table is the faster combination
-    p.g4_kernel = (W == 3 || m->opt.kernel == 1) ? 1u : 0u;
-    if (hi_bits) {  // decode fields shared with k_probe3 (which never runs for L > 16)
-        p.ck_lb = bb + nb;
-        p.ck_bsh = 8u - nb;
-        p.ck_bmask8 = ((1u << bb) - 1u) << 8;
-        p.ck_nmask = (1u << nb) - 1u;
-        p.ck_next_min = min_next;
-    }
+    p.g4_flags = (uint32_t)env_int("FQTK_B200_G4_FLAGS", 3);
     m->g4_entries = ent.size();
+    m->g4_slow_keys = slow_keys;
     return 0;
 }
 
@@ -510,8 +562,12 @@ int build_table(fqtk_b200_matcher* m) {
 
     std::vector<uint32_t> keys;
     keys.reserve((size_t)cand * W);
+    std::vector<uint32_t> owners;  // the barcode every candidate was enumerated from (it is within max_mm of it)
+    owners.reserve((size_t)cand);
     Enumerator en{nullptr, L, W, std::min<uint32_t>(m->max_mm, L), &keys, {0, 0, 0, 0}};
+    en.owner = &owners;
     for (uint32_t j = 0; j < S; j++) {
+        en.barcode = j;
         en.e = masks.data() + (size_t)j * L;
         std::memset(en.cur, 0, sizeof en.cur);
         en.rec(0, 0);
@@ -626,10 +682,12 @@ int build_table(fqtk_b200_matcher* m) {
         const int rc = (W == 1) ? build_cuckoo_w<1>(m, keys, res, n) : build_cuckoo_w<2>(m, keys, res, n);
         if (rc < 0) return rc;
     }
-    // else k_probe4's L2-resident table of the same entries under compressed keys (L <= 24)
-    if (m->params.ck_np == 0 && W <= 3 && m->opt.kernel != 0) {
-        const int rc = (W == 1) ? build_g4_w<1>(m, keys, res, n) : (W == 2) ? build_g4_w<2>(m, keys, res, n)
-                                                                          : build_g4_w<3>(m, keys, res, n);
+    // else k_probe4's L2-resident fingerprint table of every candidate.  Measured on B200: it wins where k_probe2 has no
+    // useful hot tier (cfg 5, W = 3: 27 -> 10.7 ms per 1 B reads); with a hot tier that ends 80 % of the reads in shared
+    // memory (cfg 4, W = 2) k_probe2 is still ahead (5.2 vs 5.7 ms), so one- and two-word panels only take it on request
+    if (m->params.ck_np == 0 && m->opt.kernel != 0 && (W >= 3 || m->opt.kernel == 1)) {
+        const int rc = (W == 1) ? build_g4_w<1>(m, keys, res, owners, n) : (W == 2) ? build_g4_w<2>(m, keys, res, owners, n)
+                     : (W == 3) ? build_g4_w<3>(m, keys, res, owners, n) : build_g4_w<4>(m, keys, res, owners, n);
         if (rc < 0) return rc;
     }
     return 0;
@@ -757,6 +815,8 @@ int fqtk_b200_matcher_create_ex(const uint8_t* panel_ascii, uint32_t S, uint32_t
         return fail(FQTK_B200_ERR_CUDA, "no CUDA device: fqtk_b200 has no CPU fallback");
     if (device < 0 || device >= ndev) return fail(FQTK_B200_ERR_ARG, "bad device ordinal");
     CU(cudaSetDevice(device));
+    if (const int mb = env_int("FQTK_B200_L2_PERSIST_MB", -1); mb >= 0)  // A/B: persisting-L2 carve-out of the device
+        CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)mb << 20));
 
     fqtk_b200_matcher* m = new (std::nothrow) fqtk_b200_matcher();
     if (!m) return fail(FQTK_B200_ERR_ARG, "out of host memory");
@@ -869,10 +929,9 @@ int fqtk_b200_matcher_create_ex(const uint8_t* panel_ascii, uint32_t S, uint32_t
     m->params.ck_stash_cap = 32;
     m->params.g4_table = nullptr;
     m->params.g4_buckets = 0;
-    m->params.g4_kernel = 0;
-    m->params.g4_himask = 0;
     m->params.g4_hist_rep = 1;
     m->params.g4_stash_cap = 32;
+    m->h_not_exp = not_exp;
     m->mode = FQTK_B200_MODE_BRUTE;
     if (use_cache && W <= (uint32_t)fq::MAX_FAST_WORDS) {
         rc = build_table(m);
@@ -930,6 +989,7 @@ int fqtk_b200_matcher_get_info(const fqtk_b200_matcher* m, fqtk_b200_matcher_inf
     info->cuckoo_slots = m->params.ck_words;
     info->l2_table_entries = m->g4_entries;
     info->l2_table_bytes = (uint64_t)m->params.g4_buckets * 32u;
+    info->l2_table_slow_keys = m->g4_slow_keys;
     return FQTK_B200_OK;
 }
 

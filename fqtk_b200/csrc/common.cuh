@@ -118,35 +118,76 @@ FQ_HD uint32_t acgt_key(const uint32_t (&w)[W], uint32_t pad, bool& valid) {
     return k;
 }
 
-// The same for L <= 24 (W <= 3), as a (lo, hi) pair for k_probe4's 8-byte table slots: lo = the 32-bit key of words 0
-// and 1 (word 1 absent or padded for L <= 16), hi = the 2 * (L - 16) key bits of word 2, compacted to the low bits
-// (`hi_mask` keeps exactly those; 0 for W <= 2).
+// ---- k_probe4's fingerprint table (kernels.h) ----------------------------------------------------------------
+// One-hot test of a whole read: every nibble of every word exactly one bit (pure A/C/G/T).  `pad` = last_word_pad_for_len.
 template <int W>
-FQ_HD uint32_t acgt_key64(const uint32_t (&w)[W], uint32_t pad, uint32_t hi_mask, uint32_t& hi, bool& valid) {
-    static_assert(W >= 1 && W <= 3, "compressed 8-byte slots cover L <= 24");
-    if constexpr (W <= 2) {
-        hi = 0u;
-        return acgt_key<W>(w, pad, valid);
-    } else {
-        const uint32_t x0 = w[0], x1 = w[1], x2 = w[W - 1] | pad;
-        const uint32_t bad = ((x0 - 0x11111111u) & (x0 | 0x88888888u)) | ((x1 - 0x11111111u) & (x1 | 0x88888888u)) |
-                             ((x2 - 0x11111111u) & (x2 | 0x88888888u));
-        valid = bad == 0u;
-        uint32_t k2 = (x2 ^ (x2 >> 1)) & 0x33333333u;  // 2 key bits in the low half of every nibble
-        k2 = (k2 | (k2 >> 2)) & 0x0F0F0F0Fu;           // -> 4 per byte
-        k2 = (k2 | (k2 >> 4)) & 0x00FF00FFu;           // -> 8 per half-word
-        k2 = (k2 | (k2 >> 8)) & 0x0000FFFFu;           // -> 16
-        hi = k2 & hi_mask;
-        return ((x0 ^ (x0 >> 1)) & 0x33333333u) | ((x1 ^ (x1 << 1)) & 0xCCCCCCCCu);
+FQ_HD bool acgt_only(const uint32_t (&w)[W], uint32_t pad) {
+    uint32_t bad = 0u;
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        const uint32_t x = (i == W - 1) ? (w[i] | pad) : w[i];
+        bad |= (x - 0x11111111u) & (x | 0x88888888u);
     }
+    return bad == 0u;
+}
+// True when every symbol of the read is one of A,C,G,T,N (masks 1,2,4,8,15) — the same predicate as
+// read_in_table_alphabet, in the form that costs the fewest instructions on the device: the all-ones nibbles are found
+// (x & x>>1 & x>>2 & x>>3), rewritten to a one-hot nibble, and the word then takes the one-hot test of acgt_only.
+// `pad` (last_word_pad_for_len) makes the unused nibbles of the last word pass.
+template <int W>
+FQ_HD bool acgtn_only(const uint32_t (&w)[W], uint32_t pad) {
+    uint32_t bad = 0u;
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        const uint32_t x = (i == W - 1) ? (w[i] | pad) : w[i];
+        const uint32_t t = x & (x >> 1);
+        const uint32_t f = t & (t >> 2) & 0x11111111u;  // 1 in every nibble that is 0xF
+        const uint32_t y = x ^ (f * 14u);                // 0xF -> 0x1
+        bad |= (y - 0x11111111u) & (y | 0x88888888u);
+    }
+    return bad == 0u;
 }
 
-// hash of a compressed key -> home bucket of k_probe4's global table (fast range over n_buckets)
-FQ_HD uint32_t g4_bucket(uint32_t lo, uint32_t hi, uint32_t n_slots) {
-    uint32_t h = lo * 0x9E3779B1u + hi * 0x85EBCA77u;
-    h ^= h >> 15;
-    h *= 0x2C1B3C6Du;
-    return (uint32_t)(((uint64_t)h * (uint64_t)n_slots) >> 32);
+// Home bucket and fingerprint hash of a read's packed words: two independent 32-bit mixes, so that the fingerprint bits
+// are not a function of the bucket.  Every word is first folded onto itself (w ^ w >> 15): a plain multiply-add over the
+// words is LINEAR in their top nibbles (w << 28 times an odd constant keeps 4 bits), which made reads that differ only
+// in symbols 7 / 15 / 23 / 31 collide in bucket AND fingerprint systematically; after the fold such a difference reaches
+// 19 bits of the product.  (Exactness never rests on the hash: see kernels.h; a weak hash only costs re-seeds.)
+// Identical on host (table build) and device (probe).  The fingerprint of an entry is the TOP fp_bits of `fp_hash`.
+template <int W>
+FQ_HD void g4_hashes(const uint32_t (&w)[W], uint32_t seed, uint32_t n_buckets, uint32_t& bucket, uint32_t& fp_hash) {
+    uint32_t f[W];
+#pragma unroll
+    for (int i = 0; i < W; i++) f[i] = w[i] ^ (w[i] >> 15);
+    uint32_t h1 = f[0] * 0x9E3779B1u + seed, h2 = f[0] * 0x165667B1u + seed;
+    if constexpr (W > 1) { h1 += f[W > 1 ? 1 : 0] * 0x85EBCA77u; h2 += f[W > 1 ? 1 : 0] * 0xD3A2646Du; }
+    if constexpr (W > 2) { h1 += f[W > 2 ? 2 : 0] * 0xC2B2AE3Du; h2 += f[W > 2 ? 2 : 0] * 0xFD7046C5u; }
+    if constexpr (W > 3) { h1 += f[W > 3 ? 3 : 0] * 0x27D4EB2Fu; h2 += f[W > 3 ? 3 : 0] * 0xB55A4F09u; }
+    h1 ^= h1 >> 15;
+    h1 *= 0x2C1B3C6Du;
+    h1 ^= h1 >> 12;
+    h2 ^= h2 >> 16;
+    h2 *= 0x45D9F3B5u;
+    bucket = (uint32_t)(((uint64_t)h1 * (uint64_t)n_buckets) >> 32);
+    fp_hash = h2;
+}
+// Mismatches between a read and one barcode from the barcode's ~expected nibble words (bitenc.rs:441-452): a nibble of
+// r & ~exp is non-zero iff the symbol mismatches; the flags of up to four words share one popcount.
+template <int W>
+FQ_HD uint32_t nibble_distance(const uint32_t (&w)[W], const uint32_t (&ne)[W]) {
+    static_assert(W <= 4, "one popcount covers four words");
+    uint32_t acc = 0u;
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        const uint32_t x = w[i] & ne[i];
+        const uint32_t f = (((x & 0x77777777u) + 0x77777777u) | x) & 0x88888888u;  // bit 3 of every non-zero nibble
+        acc |= f >> (3 - i);
+    }
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__popc(acc);
+#else
+    return (uint32_t)__builtin_popcount(acc);
+#endif
 }
 
 // Fixed odd multipliers of the (up to three) cuckoo sub-tables: slot_i = (k * CK_MUL[i]) >> (32 - sb_i), and the low

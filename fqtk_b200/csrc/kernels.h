@@ -43,19 +43,33 @@ struct MatchParams {
     uint32_t ck_nmask;           // code & ck_nmask = next - ck_next_min
     uint32_t ck_next_min;
     uint32_t ck_stash_cap;       // stash entries per warp of k_probe3 (16 .. 64)
-    // k_probe4 (L <= 24): every pure-A/C/G/T memo entry under its compressed key in 8-byte slots {key lo, hi word},
-    // grouped in 32-byte BUCKETS of four (one L2 sector per probe), bucketised linear probing in GLOBAL memory at load
-    // <= 0.6, small enough to stay L2-resident.  hi word = the result word itself for L <= 16, (key hi << g4_vb) |
-    // value code (k_probe3's layout, ck_lb .. ck_next_min) for L > 16; an empty slot is all ones; the slots of a
-    // bucket fill in order, so a bucket is full iff its last slot is taken.
-    const uint2* g4_table;       // nullptr = none
+    // k_probe4 (L <= 32): FINGERPRINT table in global memory of every candidate string (every A/C/G/T/N string within
+    // max_mm of some barcode, whether its result is Some or None), keyed by the read's packed words: 4-byte entries
+    //     fingerprint << (ib + cb) | sample index << cb | value code,
+    // eight to a 32-byte bucket (ONE 256-bit load per probe: a random lookup costs the SM's L1 one clock per lane whatever
+    // its width, tools/microbench_gather.cu), bucketised linear probing, slots of a bucket filled in order, empty = all
+    // ones.  Half the bytes per entry of an exact-key table, so the whole table stays L2-resident next to the stream.
+    // Exactness does not rest on the hash: (i) only reads over A/C/G/T/N use the table at all, every other read takes the
+    // exact slow path; (ii) a fingerprint match is VERIFIED: the read must be within max_mm of the entry's barcode (its
+    // ~expected nibble words are staged in shared memory) — an A/C/G/T/N read that is NOT a table key is farther than
+    // max_mm from every barcode, so it passes for no entry; (iii) a table key that meets another key's entry either fails
+    // the verification (slow path) or is caught by the builder, which replays the kernel's lookup for EVERY key and
+    // re-seeds the hash until each one yields its own value or the slow path.
+    // value code = best << nb | (next - next_min); 2^cb - 2 = "candidate whose result is None"; 2^cb - 1 only in empty slots.
+    const uint32_t* g4_table;    // g4_buckets * 8 entries; nullptr = none
     uint32_t g4_buckets;
-    uint32_t g4_himask;          // low 2 * (L - 16) bits (0 for L <= 16)
-    uint32_t g4_vb;              // value-code bits (L > 16)
-    uint32_t g4_limit;           // 2^g4_vb - 1: the reserved (largest) code
+    uint32_t g4_seed;
+    uint32_t g4_fp_bits;         // fingerprint bits (>= 8)
+    uint32_t g4_fp_shift;        // ib + cb
+    uint32_t g4_cb;              // value-code bits
+    uint32_t g4_nb;              // bits of (next - next_min)
+    uint32_t g4_fp_mask, g4_lim; // derived: ~(2^fp_shift - 1), 2^fp_shift
+    uint32_t g4_cmask, g4_nmask; // derived: 2^cb - 1, 2^nb - 1
+    uint32_t g4_code_none;       // derived: 2^cb - 2
+    uint32_t g4_next_min;
     uint32_t g4_hist_rep;        // histogram replicas of k_probe4 (power of two <= 16)
     uint32_t g4_stash_cap;       // stash entries per warp of k_probe4
-    uint32_t g4_kernel;          // 1: the packed route runs k_probe4; 0: k_probe2, whose queue phase probes this table
+    uint32_t g4_flags;           // A/B switches: 1 = table loads evict_last, 2 = stream evict_first, 4 = L2 prefetch of the next tile, bits 4-5 = launch shape
     uint32_t ck_one, ck_four;    // 1 and 4 (see Probe3Ctx in match_kernels.cu)
 };
 
@@ -119,6 +133,7 @@ cudaError_t prepare_kernels(const LaunchGeometry& g);  // opt-in shared memory a
 
 size_t probe3_smem_bytes(uint32_t ck_words, uint32_t S, uint32_t stash_cap);
 size_t probe4_smem_bytes(uint32_t W, uint32_t S, uint32_t hist_rep, uint32_t stash_cap);
+inline __host__ __device__ uint32_t probe4_ne_stride(uint32_t W) { return W == 3u ? 4u : W; }  // words per barcode in shared memory
 size_t probe2_fixed_smem_bytes(uint32_t W, uint32_t S, int threads);  // k_probe2 shared memory besides tier + Bloom
 int probe2_threads();
 uint32_t probe2_hist_rep(uint32_t S);

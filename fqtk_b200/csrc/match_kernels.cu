@@ -454,20 +454,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe(const MatchParams p, co
     cnt.flush();
 }
 
-// ---- k_probe4's L2-resident table of compressed keys (kernels.h); also probed by k_probe2's queue phase ----
-// hi word of a slot -> result word
-template <int W>
-FQ_D uint32_t g4_decode(const MatchParams& p, uint32_t hi_word) {
-    if constexpr (W <= 2) {
-        return hi_word;
-    } else {
-        const uint32_t u = hi_word & p.g4_limit;
-        const uint32_t idx = u >> p.ck_lb;
-        const uint32_t low = ((u << p.ck_bsh) & p.ck_bmask8) | (u & p.ck_nmask);
-        return idx * 65536u + low + p.ck_next_min;
-    }
-}
-// L2 eviction-priority policies: the table must survive the read / result stream that flows through L2 next to it
+// L2 eviction-priority policies: k_probe4's table must survive the read / result stream that flows through L2 next to it
 FQ_D uint64_t l2_policy_keep() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -476,6 +463,11 @@ FQ_D uint64_t l2_policy_keep() {
 FQ_D uint64_t l2_policy_stream() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+FQ_D uint64_t l2_policy_normal() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
 FQ_D uint4 ldg_hint(const uint4* ptr, uint64_t pol) {
@@ -489,48 +481,6 @@ FQ_D void stg_hint(uint4* ptr, const uint4 v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z),
                  "r"(v.w), "l"(pol)
                  : "memory");
-}
-
-// One 32-byte bucket = four slots {key lo, hi word}
-struct G4Bucket {
-    uint4 a, b;  // slots 0,1 | slots 2,3
-};
-FQ_D G4Bucket g4_load(const MatchParams& p, uint32_t bucket, uint64_t pol) {
-    const uint4* q = reinterpret_cast<const uint4*>(p.g4_table) + (size_t)bucket * 2;
-    G4Bucket e;
-    e.a = ldg_hint(q, pol);
-    e.b = ldg_hint(q + 1, pol);
-    return e;
-}
-template <int W>
-FQ_D bool g4_slot_hit(const MatchParams& p, uint32_t slot_lo, uint32_t slot_hi, uint32_t lo, uint32_t hi) {
-    if constexpr (W <= 2) {
-        return slot_lo == lo && slot_hi != 0xFFFFFFFFu;
-    } else {
-        return slot_lo == lo && (slot_hi >> p.g4_vb) == hi && slot_hi != 0xFFFFFFFFu;
-    }
-}
-// hi word of the matching slot, or 0xFFFFFFFF
-template <int W>
-FQ_D uint32_t g4_search(const MatchParams& p, const G4Bucket& e, uint32_t lo, uint32_t hi) {
-    uint32_t v = 0xFFFFFFFFu;
-    v = g4_slot_hit<W>(p, e.a.x, e.a.y, lo, hi) ? e.a.y : v;
-    v = g4_slot_hit<W>(p, e.a.z, e.a.w, lo, hi) ? e.a.w : v;
-    v = g4_slot_hit<W>(p, e.b.x, e.b.y, lo, hi) ? e.b.y : v;
-    v = g4_slot_hit<W>(p, e.b.z, e.b.w, lo, hi) ? e.b.w : v;
-    return v;
-}
-// Full lookup of one key from its (already loaded) home bucket: walks on only when the bucket is full and has no match.
-template <int W>
-FQ_D uint32_t g4_lookup(const MatchParams& p, G4Bucket e, uint32_t bucket, uint32_t lo, uint32_t hi, bool valid,
-                        uint64_t pol) {
-    uint32_t v = g4_search<W>(p, e, lo, hi);
-    while (valid && v == 0xFFFFFFFFu && e.b.w != 0xFFFFFFFFu) {  // full bucket without the key: it may have overflowed
-        bucket = (bucket + 1u == p.g4_buckets) ? 0u : bucket + 1u;
-        e = g4_load(p, bucket, pol);
-        v = g4_search<W>(p, e, lo, hi);
-    }
-    return valid ? v : 0xFFFFFFFFu;
 }
 
 // k_probe2: the HBM-resident packed route.  A warp owns tiles of 128 consecutive reads, four per lane
@@ -659,7 +609,6 @@ __global__ void __launch_bounds__(PROBE2_THREADS, 1) k_probe2(const MatchParams 
     const uint32_t hshift = 2u + (uint32_t)__popc(hrep - 1u);
     const uint32_t a_tvals = smem_addr(s_tvals), a_bloom = smem_addr(s_bloom);
     asm volatile("" : "+r"(a_tier), "+r"(a_qk), "+r"(a_hist));  // keep them in registers
-    const uint64_t pol_keep = l2_policy_keep();
     const uint32_t tshift = p.tier_shift;  // 32 - log2(tier_slots)
     const bool has_tier = tshift < 32u;
     uint32_t none_count = 0;
@@ -759,22 +708,8 @@ __global__ void __launch_bounds__(PROBE2_THREADS, 1) k_probe2(const MatchParams 
                     const uint32_t bm = bloom_mask(h);
                     maybe = (lds32_ro(a_bloom + (h >> p.bloom_shift) * 4u) & bm) == bm;
                 }
-                bool in_g4 = false;  // pure A/C/G/T read and a compact table of those entries exists: one L2 sector decides
-                if constexpr (W <= 3) {
-                    if (p.g4_table != nullptr) {
-                        uint32_t khi;
-                        const uint32_t klo = acgt_key64<W>(kw, p.last_pad, p.g4_himask, khi, in_g4);
-                        if (in_g4 && maybe) {
-                            const uint32_t b0 = g4_bucket(klo, khi, p.g4_buckets);
-                            const uint32_t v = g4_lookup<W>(p, g4_load(p, b0, pol_keep), b0, klo, khi, true, pol_keep);
-                            if (v != 0xFFFFFFFFu) out = g4_decode<W>(p, v);
-                        }
-                    }
-                }
-                if (!in_g4) {
-                    if (maybe) table_lookup<W>(p, kw, h, out);
-                    slow = out == NONE && !read_in_table_alphabet<W>(kw, p.last_pad);
-                }
+                if (maybe) table_lookup<W>(p, kw, h, out);
+                slow = out == NONE && !read_in_table_alphabet<W>(kw, p.last_pad);
             }
             uint32_t pending = __ballot_sync(0xFFFFFFFFu, slow);
             while (pending) {
@@ -1197,28 +1132,115 @@ __global__ void __launch_bounds__(THREADS, 1) k_probe3(const __grid_constant__ M
 
 // ------------------------------------------------------------------------------------------------------
 // k_probe4: the HBM-resident packed route for panels whose pure-A/C/G/T memo entries do not fit in shared memory
-// (cfg 4: 1 536 samples at 2 mismatches; cfg 5: 6 144 IUPAC samples of 20 bases).  Same structure as k_probe3 —
-// compressed key + validity, unconditional histogram atomic, odd reads parked in a per-warp stash and resolved a
-// warp-full at a time through the full memo table — but the lookup goes to a GLOBAL table of 8-byte slots
-// {key lo, hi word} that is 4 - 5 x smaller than the memo table (compressed keys, no N-containing entries) and so
-// stays L2-resident while the reads stream through (table loads carry an L2 evict_last policy, the read / result
-// stream evict_first).  Slots come four to a 32-byte bucket — one L2 sector per probe — and a lane has two home
-// buckets in flight at a time; only a full bucket without the key is followed by the next one (load <= 0.6: rare).
-// A valid read that is not in the table is None.
+// (cfg 5: 6 144 IUPAC samples of 20 bases, 2.5 M entries).  Every pure-A/C/G/T read makes ONE random 32-byte load from
+// a global FINGERPRINT table (layout and exactness argument: kernels.h) that is small enough (4 bytes per candidate
+// string) to stay L2-resident while the reads stream through — table loads carry an L2 evict_last policy, the read /
+// result stream evict_first — and a fingerprint match is verified against the barcode's ~expected nibble words in
+// shared memory.  What bounds the kernel is the SM's L1 request path: a warp-wide load of 32 random lines costs 32 clocks
+// whatever its width (tools/microbench_gather.cu: 284 G lookups/s chip-wide), so the design is one load instruction per
+// read; the second bucket of the rare overflow chain is loaded only by the lanes that need it.
+// Reads that are not pure A/C/G/T (no-calls, IUPAC codes, junk) and reads whose fingerprint match fails verification are
+// written as None / counted as unmatched, parked in a per-warp stash and resolved a warp-full at a time through the
+// exact memo table (or, outside its alphabet, the warp-cooperative scan), as in k_probe3.
 // ------------------------------------------------------------------------------------------------------
-constexpr int PROBE4_THREADS = 1024;
+constexpr int PROBE4_THREADS = 1024;  // the largest launch shape (shared-memory sizing)
 constexpr int PROBE4_R = 4;
 
 struct Probe4Ctx {
     uint32_t a_hist;   // shared-window address of this lane's histogram replica
     uint32_t a_stash;  // ... of this warp's stash: g4_stash_cap keys (W words each), then as many read indices
+    uint32_t a_ne;     // ... of the panel's ~expected nibble words (probe4_ne_stride(W) words per barcode)
 };
 
 FQ_D void hist4_add(const MatchParams& p, const Probe4Ctx& c, uint32_t bin, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(imad(bin, p.g4_hist_rep * 4u, c.a_hist)), "r"(v) : "memory");
 }
 
+struct G4Bucket {
+    uint32_t e[8];
+};
+FQ_D G4Bucket g4_load(const MatchParams& p, uint32_t bucket, uint64_t pol) {
+    G4Bucket b;
+    const uint32_t* q = p.g4_table + (size_t)bucket * 8;
+    asm volatile("ld.global.nc.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(b.e[0]), "=r"(b.e[1]), "=r"(b.e[2]), "=r"(b.e[3]), "=r"(b.e[4]), "=r"(b.e[5]), "=r"(b.e[6]),
+                   "=r"(b.e[7])
+                 : "l"(q), "l"(pol));
+    return b;
+}
+// the entry of the bucket whose fingerprint equals the read's, with the fingerprint field cleared (idx << cb | code),
+// or a value >= 2^fp_shift when there is none (two matches: the smaller entry; the builder replays the same rule).
+// `fp_hash` is the whole second hash: its top fp_bits are the fingerprint, `fp_mask` selects them (one LOP3 per entry).
+FQ_D uint32_t g4_match(const G4Bucket& b, uint32_t fp_hash, uint32_t fp_mask) {
+    uint32_t t[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) t[j] = b.e[j] ^ (fp_hash & fp_mask);
+    return min(min(min(t[0], t[1]), min(t[2], t[3])), min(min(t[4], t[5]), min(t[6], t[7])));
+}
 template <int W>
+FQ_D void lds_ne(uint32_t a, uint32_t (&ne)[W]) {  // one barcode's ~expected words
+    if constexpr (W == 1) {
+        ne[0] = lds32_ro(a);
+    } else if constexpr (W == 2) {
+        const uint2 v = lds64_ro(a);
+        ne[0] = v.x;
+        ne[W - 1] = v.y;
+    } else {
+        const uint4 v = lds128_ro(a);
+        ne[0] = v.x;
+        ne[1] = v.y;
+        ne[2] = v.z;
+        if constexpr (W == 4) ne[W - 1] = v.w;
+    }
+}
+
+// Lookup rules (all derived constants of the entry layout come precomputed in MatchParams):
+//   read with a symbol outside A/C/G/T/N   -> slow path, whatever the table says: such a read is no table key, and it can
+//                                             pass the verification of another key's entry (junk / IUPAC symbols match
+//                                             more than a base does), so exactness must not rest on the fingerprint
+//   fingerprint match + verified          -> the entry's value (Some or None): the read IS that table key, or the builder's
+//                                            replay would have re-seeded the hash
+//   fingerprint match, not verified       -> slow path (another key's entry)
+//   no match                              -> None: the table holds every A/C/G/T/N string within max_mm of a barcode
+// `t` = g4_match of the bucket that ended the walk.  Returns the result word; `park` = the read takes the slow path.
+template <int W>
+FQ_D uint32_t g4_decide(const MatchParams& p, uint32_t t, const uint32_t (&w)[W], const uint32_t (&ne)[W], uint32_t idx,
+                        uint32_t pad, bool& park) {
+    const bool in_alphabet = acgtn_only<W>(w, pad);
+    const bool hit = t < p.g4_lim;
+    const bool ok = nibble_distance<W>(w, ne) <= p.max_mm;
+    park = !in_alphabet || (hit && !ok);
+    const uint32_t code = t & p.g4_cmask;
+    const uint32_t best = code >> p.g4_nb, next = (code & p.g4_nmask) + p.g4_next_min;
+    const bool some = in_alphabet && hit && ok && code < p.g4_code_none;
+    return some ? ((idx << 16) | (best << 8) | next) : NONE;
+}
+
+// One read, start to end (the tail of a batch): all 32 lanes call it together.
+template <int W>
+FQ_D uint32_t g4_lookup_one(const MatchParams& p, const Probe4Ctx& c, const uint32_t (&w)[W], uint32_t pad, uint64_t pol,
+                            bool& park) {
+    uint32_t bucket, fph;
+    g4_hashes<W>(w, p.g4_seed, p.g4_buckets, bucket, fph);
+    G4Bucket b = g4_load(p, bucket, pol);
+    uint32_t t = g4_match(b, fph, p.g4_fp_mask);
+    bool more = t >= p.g4_lim && b.e[7] != 0xFFFFFFFFu;
+    while (__any_sync(0xFFFFFFFFu, more)) {
+        if (more) {
+            bucket = (bucket + 1u == p.g4_buckets) ? 0u : bucket + 1u;
+            b = g4_load(p, bucket, pol);
+            t = g4_match(b, fph, p.g4_fp_mask);
+            more = t >= p.g4_lim && b.e[7] != 0xFFFFFFFFu;
+        }
+    }
+    const uint32_t idx = min(t >> p.g4_cb, p.S - 1u);  // (the clamp only matters for the lanes without a hit)
+    uint32_t ne[W];
+    lds_ne<W>(imad(idx, probe4_ne_stride(W) * 4u, c.a_ne), ne);
+    return g4_decide<W>(p, t, w, ne, idx, pad, park);
+}
+
+// (the extra template parameters only make the copy private to one kernel: ptxas 12.9 crashes on a shared one)
+template <int W, bool PAD, int THREADS, int IF>
 __device__ __noinline__ void probe4_drain(const MatchParams& p, const Probe4Ctx c, uint32_t cnt,
                                           uint32_t* __restrict__ results, uint32_t lane) {
     __syncwarp();
@@ -1241,107 +1263,196 @@ __device__ __noinline__ void probe4_drain(const MatchParams& p, const Probe4Ctx 
     __syncwarp();
 }
 
-template <int W, bool PAD>
-__global__ void __launch_bounds__(PROBE4_THREADS, 1) k_probe4(const __grid_constant__ MatchParams p, const ReadSource src,
-                                                             uint32_t* __restrict__ results) {
+template <int W, bool PAD, int THREADS, int IF>  // IF = home buckets in flight per lane (2 or 4)
+__global__ void __launch_bounds__(THREADS, 1) k_probe4(const __grid_constant__ MatchParams p, const ReadSource src,
+                                                      uint32_t* __restrict__ results) {
     constexpr int R = PROBE4_R;
+    static_assert(IF == 2 || IF == 4, "two or four lookups in flight");
+    constexpr uint32_t NES = W == 3 ? 4 : W;  // probe4_ne_stride
     extern __shared__ uint4 s_dyn[];
-    // layout: histogram replicas | per-warp stashes
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_dyn);
+    // layout: ~expected words of the panel | histogram replicas | per-warp stashes
+    uint32_t* s_ne = reinterpret_cast<uint32_t*>(s_dyn);
+    uint32_t* s_hist = s_ne + (size_t)p.S * NES;
     const uint32_t hrep = p.g4_hist_rep;
+    for (uint32_t t = threadIdx.x; t < p.S * NES; t += blockDim.x) {
+        const uint32_t j = t / NES, k = t % NES;
+        s_ne[t] = k < (uint32_t)W ? __ldg(p.not_exp + (size_t)j * W + k) : 0u;
+    }
     for (uint32_t t = threadIdx.x; t < (p.S + 1u) * hrep; t += blockDim.x) s_hist[t] = 0u;
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n_warps = blockDim.x >> 5, warp_in_cta = threadIdx.x >> 5;
     Probe4Ctx c;
+    c.a_ne = smem_addr(s_ne);
     c.a_hist = smem_addr(s_hist) + (lane & (hrep - 1u)) * 4u;
     c.a_stash = smem_addr(s_hist + (p.S + 1u) * hrep) + warp_in_cta * (p.g4_stash_cap * (W * 4u + 4u));
     const uint32_t pad = PAD ? p.last_pad : 0u;
     const uint32_t lane_lt = (1u << lane) - 1u;
     uint32_t cnt = 0;  // reads parked in the warp's stash (warp-uniform)
-    const uint64_t pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
+    const uint64_t pol_keep = (p.g4_flags & 1u) ? l2_policy_keep() : l2_policy_normal();
+    const uint64_t pol_stream = (p.g4_flags & 2u) ? l2_policy_stream() : l2_policy_normal();
 
     constexpr uint32_t TILE = 32u * R;
     constexpr int NV = R * W / 4;  // 16-byte vectors per lane per tile
     const uint32_t n_tiles = (uint32_t)(src.n / (uint64_t)TILE);
     const uint32_t stride = gridDim.x * n_warps;
-    for (uint32_t tile = blockIdx.x * n_warps + warp_in_cta; tile < n_tiles; tile += stride) {
-        // the tile after next is requested from L2 now (one TMA bulk prefetch by one lane); this tile's words were
-        // requested two iterations ago, so the loads below are L2 hits
-        if (lane == 0u && tile + 2u * stride < n_tiles) {
-            const uint32_t* ptr = src.packed + (size_t)(tile + 2u * stride) * (TILE * W);
-            asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(ptr), "r"(TILE * W * 4u),
-                         "l"(pol_stream)
-                         : "memory");
-        }
-        const uint32_t g = tile * 32u + lane;  // this lane's group of R consecutive reads
-        uint32_t flat[R * W];
-        {
-            const uint4* in = reinterpret_cast<const uint4*>(src.packed) + (size_t)g * NV;
+    // ---- the three stages of a tile ----
+    auto load_words = [&](uint32_t tile, uint32_t (&flat)[R * W]) {
+        const uint4* in = reinterpret_cast<const uint4*>(src.packed) + (size_t)(tile * 32u + lane) * NV;
 #pragma unroll
-            for (int v = 0; v < NV; v++) {
-                const uint4 q = ldg_hint(in + v, pol_stream);
-                flat[4 * v + 0] = q.x; flat[4 * v + 1] = q.y; flat[4 * v + 2] = q.z; flat[4 * v + 3] = q.w;
+        for (int v = 0; v < NV; v++) {
+            const uint4 q = ldg_hint(in + v, pol_stream);
+            flat[4 * v + 0] = q.x; flat[4 * v + 1] = q.y; flat[4 * v + 2] = q.z; flat[4 * v + 3] = q.w;
+        }
+    };
+    // hashes + home-bucket loads of reads [h0, h0 + N) of the lane
+    auto issue = [&](const uint32_t (&flat)[R * W], uint32_t (&bucket)[R], uint32_t (&fph)[R], G4Bucket* e, int h0, int n) {
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            if (q >= h0 && q < h0 + n) {
+                uint32_t kw[W];
+#pragma unroll
+                for (int k = 0; k < W; k++) kw[k] = flat[q * W + k];
+                g4_hashes<W>(kw, p.g4_seed, p.g4_buckets, bucket[q], fph[q]);
+                e[q - h0] = g4_load(p, bucket[q], pol_keep);
             }
         }
-        uint32_t lo[R], hi[R], bucket[R];
-        bool valid[R];
+    };
+    auto match = [&](const G4Bucket* e, const uint32_t (&fph)[R], uint32_t (&t)[R], uint32_t& more, int h0, int n) {
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            if (q >= h0 && q < h0 + n) {
+                t[q] = g4_match(e[q - h0], fph[q], p.g4_fp_mask);
+                more |= (t[q] >= p.g4_lim && e[q - h0].e[7] != 0xFFFFFFFFu) ? (1u << q) : 0u;
+            }
+        }
+    };
+    // overflow walk, verification, decision, result store, counts, parking
+    auto finish = [&](uint32_t tile, const uint32_t (&flat)[R * W], uint32_t (&bucket)[R], const uint32_t (&fph)[R],
+                      uint32_t (&t)[R], uint32_t more) {
+        // the overflow walk (rare at the table's load factor): one more bucket per round for each lane's first read
+        // that needs it, until no lane needs any
+        while (__any_sync(0xFFFFFFFFu, more != 0u)) {
+            if (more) {
+                const uint32_t r = (uint32_t)__ffs(more) - 1u;
+                uint32_t bk = bucket[0], fh = fph[0];
+#pragma unroll
+                for (int q = 1; q < R; q++) {
+                    bk = (r == (uint32_t)q) ? bucket[q] : bk;
+                    fh = (r == (uint32_t)q) ? fph[q] : fh;
+                }
+                bk = (bk + 1u == p.g4_buckets) ? 0u : bk + 1u;
+                const G4Bucket e = g4_load(p, bk, pol_keep);
+                const uint32_t tt = g4_match(e, fh, p.g4_fp_mask);
+#pragma unroll
+                for (int q = 0; q < R; q++) {
+                    bucket[q] = (r == (uint32_t)q) ? bk : bucket[q];
+                    t[q] = (r == (uint32_t)q) ? tt : t[q];
+                }
+                if (!(tt >= p.g4_lim && e.e[7] != 0xFFFFFFFFu)) more &= more - 1u;
+            }
+        }
+        // the matched entries' barcodes from shared memory (all R loads in flight), then verification and decision
+        uint32_t idx[R], ne[R][W];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            idx[r] = min(t[r] >> p.g4_cb, p.S - 1u);  // (the clamp only matters for the lanes without a hit)
+            lds_ne<W>(imad(idx[r], NES * 4u, c.a_ne), ne[r]);
+        }
+        uint32_t res[R];
+        uint32_t bad = 0u;  // bit r: read r takes the slow path
 #pragma unroll
         for (int r = 0; r < R; r++) {
             uint32_t kw[W];
 #pragma unroll
             for (int k = 0; k < W; k++) kw[k] = flat[r * W + k];
-            lo[r] = acgt_key64<W>(kw, pad, p.g4_himask, hi[r], valid[r]);
-            bucket[r] = g4_bucket(lo[r], hi[r], p.g4_buckets);
+            bool park;
+            res[r] = g4_decide<W>(p, t[r], kw, ne[r], idx[r], pad, park);
+            hist4_add(p, c, res[r] != NONE ? idx[r] : p.S, 1u);
+            bad |= park ? (1u << r) : 0u;
         }
-        uint32_t res[R];
-        bool all_valid = true;
-#pragma unroll
-        for (int h = 0; h < R; h += 2) {  // two home buckets (2 x 32 bytes) in flight per lane at a time
-            const G4Bucket e0 = g4_load(p, bucket[h], pol_keep), e1 = g4_load(p, bucket[h + 1], pol_keep);
-            const uint32_t v0 = g4_lookup<W>(p, e0, bucket[h], lo[h], hi[h], valid[h], pol_keep);
-            const uint32_t v1 = g4_lookup<W>(p, e1, bucket[h + 1], lo[h + 1], hi[h + 1], valid[h + 1], pol_keep);
-            res[h] = v0 != 0xFFFFFFFFu ? g4_decode<W>(p, v0) : NONE;
-            res[h + 1] = v1 != 0xFFFFFFFFu ? g4_decode<W>(p, v1) : NONE;
-            hist4_add(p, c, v0 != 0xFFFFFFFFu ? (res[h] >> 16) : p.S, 1u);
-            hist4_add(p, c, v1 != 0xFFFFFFFFu ? (res[h + 1] >> 16) : p.S, 1u);
-            all_valid = all_valid && valid[h] && valid[h + 1];
-        }
+        const uint32_t g = tile * 32u + lane;  // this lane's group of R consecutive reads
         uint4* out4 = reinterpret_cast<uint4*>(results) + (size_t)g * (R / 4);
 #pragma unroll
         for (int v = 0; v < R / 4; v++)
             stg_hint(out4 + v, make_uint4(res[4 * v], res[4 * v + 1], res[4 * v + 2], res[4 * v + 3]), pol_stream);
-        if (__any_sync(0xFFFFFFFFu, !all_valid)) {
-            // every pass parks each lane's first read that is not pure A/C/G/T (lanes rarely have two)
-            uint32_t bad = 0u;
+        // park each lane's slow-path reads (symbols outside A/C/G/T/N, fingerprint collisions: rare): one pass per read
+        // slot that has any
+        uint32_t bal;
+        while ((bal = __ballot_sync(0xFFFFFFFFu, bad != 0u)) != 0u) {
+            const uint32_t n_new = (uint32_t)__popc(bal);
+            if (cnt + n_new > p.g4_stash_cap) {  // no room (g4_stash_cap >= 32): resolve what is parked first
+                probe4_drain<W, PAD, THREADS, IF>(p, c, cnt, results, lane);
+                cnt = 0u;
+            }
+            if (bad) {
+                const uint32_t r = (uint32_t)__ffs(bad) - 1u;
+                const uint32_t pos = cnt + (uint32_t)__popc(bal & lane_lt);
 #pragma unroll
-            for (int r = 0; r < R; r++) bad |= valid[r] ? 0u : (1u << r);
-            do {
-                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, bad != 0u);
-                const uint32_t n_new = (uint32_t)__popc(bal);
-                if (cnt + n_new > p.g4_stash_cap) {  // no room (g4_stash_cap >= 32): resolve what is parked first
-                    probe4_drain<W>(p, c, cnt, results, lane);
-                    cnt = 0u;
+                for (int k = 0; k < W; k++) {
+                    uint32_t wk = flat[k];
+#pragma unroll
+                    for (int q = 1; q < R; q++) wk = (r == (uint32_t)q) ? flat[q * W + k] : wk;
+                    sts32(c.a_stash + (pos * W + k) * 4u, wk);
                 }
-                if (bad) {
-                    const uint32_t r = (uint32_t)__ffs(bad) - 1u;
-                    const uint32_t pos = cnt + (uint32_t)__popc(bal & lane_lt);
+                sts32(c.a_stash + p.g4_stash_cap * (W * 4u) + pos * 4u, g * R + r);
+                bad &= bad - 1u;
+            }
+            cnt += n_new;
+        }
+    };
+
+    const uint32_t tile0 = blockIdx.x * n_warps + warp_in_cta;
+    if constexpr (THREADS <= 512) {
+        // Software pipeline across tiles (128 registers per thread): the NEXT tile's home buckets are requested before this
+        // tile is verified and stored, the words of the tile after that before the next match — a warp has R lookups in
+        // flight nearly all the time, which is what the L1 request path needs to stay busy with only 16 warps per SM.
+        static_assert(IF == R, "the pipelined form keeps all R lookups of a tile in flight");
+        uint32_t wa[R * W], wb[R * W], bucket_a[R], fph_a[R], bucket_b[R], fph_b[R];
+        G4Bucket e[R];
+        if (tile0 < n_tiles) {
+            load_words(tile0, wa);
+            issue(wa, bucket_a, fph_a, e, 0, R);
+            if (tile0 + stride < n_tiles) load_words(tile0 + stride, wb);
+        }
+        for (uint32_t tile = tile0; tile < n_tiles; tile += stride) {
+            uint32_t t[R], more = 0u;
+            match(e, fph_a, t, more, 0, R);
+            const uint32_t next = tile + stride;
+            if (next < n_tiles) issue(wb, bucket_b, fph_b, e, 0, R);
+            finish(tile, wa, bucket_a, fph_a, t, more);
 #pragma unroll
-                    for (int k = 0; k < W; k++) {
-                        uint32_t wk = flat[k];
+            for (int k = 0; k < R * W; k++) wa[k] = wb[k];
 #pragma unroll
-                        for (int q = 1; q < R; q++) wk = (r == (uint32_t)q) ? flat[q * W + k] : wk;
-                        sts32(c.a_stash + (pos * W + k) * 4u, wk);
-                    }
-                    sts32(c.a_stash + p.g4_stash_cap * (W * 4u) + pos * 4u, g * R + r);
-                    bad &= bad - 1u;
-                }
-                cnt += n_new;
-            } while (__any_sync(0xFFFFFFFFu, bad != 0u));
+            for (int q = 0; q < R; q++) {
+                bucket_a[q] = bucket_b[q];
+                fph_a[q] = fph_b[q];
+            }
+            if (next + stride < n_tiles) load_words(next + stride, wb);
+        }
+    } else {
+        // Plain grid-stride loop: phases over the R reads of the lane, so that a warp waits once per kind of memory
+        // round trip (words -> home buckets -> barcode words), not once per read.
+        for (uint32_t tile = tile0; tile < n_tiles; tile += stride) {
+            uint32_t flat[R * W];
+            load_words(tile, flat);
+            if ((p.g4_flags & 4u) && lane < (uint32_t)(NV * 4) && tile + stride < n_tiles) {  // ask L2 for the next tile
+                const uint32_t* nxt = src.packed + (size_t)(tile + stride) * (TILE * W) + lane * 32u;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+            }
+            uint32_t bucket[R], fph[R], t[R];
+            uint32_t more = 0u;  // bit r: read r's bucket is full and has no match: walk on
+#pragma unroll
+            for (int h = 0; h < R; h += IF) {
+                G4Bucket e[IF];
+                issue(flat, bucket, fph, e, h, IF);
+                match(e, fph, t, more, h, IF);
+            }
+            finish(tile, flat, bucket, fph, t, more);
         }
     }
-    probe4_drain<W>(p, c, cnt, results, lane);
+    probe4_drain<W, PAD, THREADS, IF>(p, c, cnt, results, lane);
 
     // ---- tail: fewer than a tile of reads, one per lane, first warp of the grid ----
     if (blockIdx.x == 0 && threadIdx.x < 32u) {
@@ -1351,18 +1462,11 @@ __global__ void __launch_bounds__(PROBE4_THREADS, 1) k_probe4(const __grid_const
             uint32_t w1[W];
 #pragma unroll
             for (int k = 0; k < W; k++) w1[k] = live ? __ldg(src.packed + i * W + k) : 0u;
-            bool valid;
-            uint32_t hi1;
-            const uint32_t lo1 = acgt_key64<W>(w1, pad, p.g4_himask, hi1, valid);
-            uint32_t out = NONE;
-            {
-                const uint32_t b1 = g4_bucket(lo1, hi1, p.g4_buckets);
-                const uint32_t v1 = g4_lookup<W>(p, g4_load(p, b1, pol_keep), b1, lo1, hi1, live && valid, pol_keep);
-                if (v1 != 0xFFFFFFFFu) out = g4_decode<W>(p, v1);
-            }
-            const uint32_t slow = slow_resolve<W>(p, w1, live && !valid, lane);
+            bool park;
+            uint32_t out = g4_lookup_one<W>(p, c, w1, pad, pol_keep, park);
+            const uint32_t slow = slow_resolve<W>(p, w1, live && park, lane);
             if (live) {
-                if (!valid) out = slow;
+                if (park) out = slow;
                 results[i] = out;
                 hist4_add(p, c, out == NONE ? p.S : (out >> 16), 1u);
             }
@@ -1595,27 +1699,40 @@ static cudaError_t launch_probe3_wnp(const MatchParams& p, const ReadSource& src
 }
 
 size_t probe4_smem_bytes(uint32_t W, uint32_t S, uint32_t hist_rep, uint32_t stash_cap) {
-    return (size_t)(S + 1u) * hist_rep * 4 + (size_t)(PROBE4_THREADS / 32) * stash_cap * (W * 4 + 4);
+    return (size_t)S * probe4_ne_stride(W) * 4 + (size_t)(S + 1u) * hist_rep * 4 +
+           (size_t)(PROBE4_THREADS / 32) * stash_cap * (W * 4 + 4) + 16;
 }
 
+// launch shape of k_probe4: threads per CTA (one CTA per SM) x home buckets in flight per lane; g4_flags bits 4-5 (A/B
+// timing): 0 = 1024 x 2, 1 = 1024 x 4, 2 = 768 x 4, 3 = 512 x 4
+template <int W, bool PAD, int THREADS, int IF>
+static cudaError_t launch_probe4_shape(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
+                                       const LaunchGeometry& g, cudaStream_t stream) {
+    const size_t smem = probe4_smem_bytes(W, p.S, p.g4_hist_rep, p.g4_stash_cap);
+    const uint64_t n_warp_tiles = (src.n + 32 * PROBE4_R - 1) / (32 * PROBE4_R);
+    const uint64_t want = (n_warp_tiles + THREADS / 32 - 1) / (THREADS / 32);
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)g.sm_count));
+    auto k = k_probe4<W, PAD, THREADS, IF>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<grid, THREADS, smem, stream>>>(p, src, d_results);
+    count_launch();
+    return cudaGetLastError();
+}
+template <int W, bool PAD>
+static cudaError_t launch_probe4_wp(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
+                                    const LaunchGeometry& g, cudaStream_t stream) {
+    switch ((p.g4_flags >> 4) & 3u) {
+        case 0: return launch_probe4_shape<W, PAD, 1024, 2>(p, src, d_results, g, stream);
+        case 1: return launch_probe4_shape<W, PAD, 1024, 4>(p, src, d_results, g, stream);
+        case 2: return launch_probe4_shape<W, PAD, 768, 4>(p, src, d_results, g, stream);
+        default: return launch_probe4_shape<W, PAD, 512, 4>(p, src, d_results, g, stream);
+    }
+}
 template <int W>
 static cudaError_t launch_probe4_w(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
                                    const LaunchGeometry& g, cudaStream_t stream) {
-    const size_t smem = probe4_smem_bytes(W, p.S, p.g4_hist_rep, p.g4_stash_cap);
-    const uint64_t n_warp_tiles = (src.n + 32 * PROBE4_R - 1) / (32 * PROBE4_R);
-    const uint64_t want = (n_warp_tiles + PROBE4_THREADS / 32 - 1) / (PROBE4_THREADS / 32);
-    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)g.sm_count));
-    if (p.last_pad) {
-        auto k = k_probe4<W, true>;
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<grid, PROBE4_THREADS, smem, stream>>>(p, src, d_results);
-    } else {
-        auto k = k_probe4<W, false>;
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<grid, PROBE4_THREADS, smem, stream>>>(p, src, d_results);
-    }
-    count_launch();
-    return cudaGetLastError();
+    return p.last_pad ? launch_probe4_wp<W, true>(p, src, d_results, g, stream)
+                      : launch_probe4_wp<W, false>(p, src, d_results, g, stream);
 }
 
 template <int W, int NP>
@@ -1637,12 +1754,12 @@ cudaError_t launch_probe(const MatchParams& p, const ReadSource& src, uint32_t* 
         return p.ck_np == 2 ? launch_probe3_wn<2, 2>(p, src, d_results, g, stream)
                             : launch_probe3_wn<2, 3>(p, src, d_results, g, stream);
     }
-    if (!ascii && p.g4_table && p.g4_kernel && p.W <= 3u &&
-        ((reinterpret_cast<uintptr_t>(src.packed) | reinterpret_cast<uintptr_t>(d_results)) & 15u) == 0u) {
+    if (!ascii && p.g4_table && ((reinterpret_cast<uintptr_t>(src.packed) | reinterpret_cast<uintptr_t>(d_results)) & 15u) == 0u) {
         switch (p.W) {
             case 1: return launch_probe4_w<1>(p, src, d_results, g, stream);
             case 2: return launch_probe4_w<2>(p, src, d_results, g, stream);
-            default: return launch_probe4_w<3>(p, src, d_results, g, stream);
+            case 3: return launch_probe4_w<3>(p, src, d_results, g, stream);
+            default: return launch_probe4_w<4>(p, src, d_results, g, stream);
         }
     }
     if (ascii) {

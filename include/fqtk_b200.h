@@ -78,8 +78,9 @@ typedef struct {
     uint64_t cuckoo_entries;     /* pure-A/C/G/T memo entries held in the shared-memory cuckoo table (0 = none) */
     uint32_t cuckoo_probes;      /* sub-tables = probes per read (2 or 3) */
     uint32_t cuckoo_slots;       /* 4-byte slots over all sub-tables */
-    uint64_t l2_table_entries;   /* pure-A/C/G/T memo entries in the compressed 8-byte-slot table of k_probe4 (0 = none) */
+    uint64_t l2_table_entries;   /* pure-A/C/G/T candidate strings in the L2-resident fingerprint table of k_probe4 (0 = none) */
     uint64_t l2_table_bytes;
+    uint64_t l2_table_slow_keys; /* of those, keys the kernel sends to the exact slow path (fingerprint collisions) */
 } fqtk_b200_matcher_info;
 
 /* ---- lifecycle -------------------------------------------------------------------------------------

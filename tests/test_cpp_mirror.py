@@ -31,7 +31,7 @@ def test_cpp_mirror_reference_cases(tmp_path):
 
 
 def test_compressed_key_primitives_on_cpu(tmp_path):
-    """acgt_key / acgt_key64 (csrc/common.cuh, shared by host and device): valid <=> every nibble one-hot, and injective
+    """acgt_key, acgt_only, nibble_distance, g4_hashes (csrc/common.cuh, shared by host and device): valid <=> every nibble one-hot, and injective
     on valid reads — checked on the CPU (tests/cpp/test_keys.cpp), no GPU needed."""
     exe = str(tmp_path / "test_keys")
     cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-I", "/usr/local/cuda/include",

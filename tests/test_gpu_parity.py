@@ -345,8 +345,8 @@ def test_configs_reduced_n(cfg_id, n, use_cache):
 @pytest.mark.parametrize("arity", [0, 1, 2, 3])
 def test_packed_route_kernel_variants(arity):
     """The HBM-resident packed route has three kernels: k_probe3 (shared-memory cuckoo table of the pure A/C/G/T memo
-    entries, 2 or 3 sub-tables, L <= 16), k_probe4 (the same entries in an L2-resident table of 8-byte slots, L <= 24;
-    knob 1) and k_probe2 (hot tier + global memo table; knob 0).  All bit-exact."""
+    entries, 2 or 3 sub-tables, L <= 16), k_probe4 (L2-resident fingerprint table of every pure A/C/G/T candidate,
+    verified against the panel, L <= 32; knob 1) and k_probe2 (hot tier + global memo table; knob 0).  All bit-exact."""
     torch = torch_cuda()
     L = _lib.lib()
     rng = np.random.default_rng(4242 + arity)
@@ -376,7 +376,7 @@ def test_packed_route_kernel_variants(arity):
                     assert (int(m.info().l2_table_entries) > 0) == (arity == 1)
                 check_against_oracle(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, reads, True, expect_mode="table")
         for _ in range(16):  # pad nibbles (L % 8 != 0), one- to three-word keys, dirty reads, odd parameters
-            Lb = int(rng.choice([1, 2, 3, 7, 8, 9, 12, 15, 16, 17, 20, 23, 24]))
+            Lb = int(rng.choice([1, 2, 3, 7, 8, 9, 12, 15, 16, 17, 20, 23, 24, 25, 29, 32]))
             S = int(rng.choice([1, 2, 5, 40, 300]))
             pa = ALPHABETS[["acgt", "acgtn", "iupac"][int(rng.integers(0, 3))]]
             ra = ALPHABETS[["acgt", "acgtn", "dirty"][int(rng.integers(0, 3))]]
