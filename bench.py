@@ -11,8 +11,14 @@ of synthetic reads of the named config, per GPU.  Prints ONE JSON line on rank 0
   roofline   dominant kernel vs the measured HBM copy peak, on ALGORITHMIC bytes B(L) = 4*ceil(L/8) + 4 per read
   cpu_baseline   the oracle (C restatement of the reference's matcher, memo cache on) timed on this box's host cores
 
+  configs    the other single-GPU-sized configs of BASELINE.json next to the headline: cfg 2 (weak, 100 M reads per GPU),
+             cfg 4 and cfg 5 (STRONG: 1 B reads sharded over the N ranks), each with its own kernel roofline
+  parity_check   outside the timed region: per-rank histogram of the result words, all-reduced, == the all-reduced device
+             counts; rank 0 replays a window of ANOTHER rank's shard through the oracle
+
 `--impl reference` times the reference's CPU implementation of the path (the oracle port; the reference is Rust and
-cannot be built in this image) on the same workload: each step is a bounded sample of the same read stream.
+cannot be built in this image) on the same workload: each step is a bounded sample of the same read stream.  That arm
+loads nothing of the product: panel and reads come from the oracle's own copy of the workload generator.
 """
 from __future__ import annotations
 
@@ -51,14 +57,24 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-brute", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg 2 / 4 / 5 entries of the line")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target CPU seconds for the cpu_baseline sample")
     return ap.parse_args()
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def host_panel(cfg):
+    """The config's panel from the ORACLE's copy of the workload generator (byte-identical to fqtk_b200.synth.panel;
+    tests/test_oracle_kats.py checks it) — the CPU legs load nothing of the product."""
+    import oracle
+
+    return oracle.synth_panel(cfg.seed_panel, cfg.n_samples, cfg.barcode_len, cfg.min_distance, cfg.n_degenerate)
+
+
 def host_reads(panel, seed, first, n, threads=16):
     """Host replay of the synthetic stream, sliced over a few threads (ctypes releases the GIL)."""
-    from fqtk_b200 import synth
+    import oracle
 
     L = panel.shape[1]
     out = np.empty((n, L), dtype=np.uint8)
@@ -68,7 +84,7 @@ def host_reads(panel, seed, first, n, threads=16):
     def work(t):
         lo, hi = bounds[t], bounds[t + 1]
         if hi > lo:
-            out[lo:hi] = synth.reads_host(panel, seed, first + lo, hi - lo)
+            out[lo:hi] = oracle.synth_reads(panel, seed, first + lo, hi - lo)
 
     with ThreadPoolExecutor(threads) as ex:
         list(ex.map(work, range(threads)))
@@ -201,10 +217,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from fqtk_b200 import synth
+    from fqtk_b200.synth import CONFIGS  # plain dataclasses: importing them does not load the CUDA library
 
-    cfg = synth.CONFIGS[args.config]
-    panel = synth.panel(cfg)
+    cfg = CONFIGS[args.config]
+    panel = host_panel(cfg)
     total_steps = args.steps + args.warmup
     calib = host_reads(panel, cfg.seed_reads, 0, 1_000_000)
     rate, _, _ = time_oracle(cfg, panel, calib, 1)
@@ -231,7 +247,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": config_dict(cfg, n, "reference-cpu"),
+        "config": dict(config_dict(cfg, n, "reference-cpu"), input="ASCII barcode rows in host memory",
+                       sample_of_config_reads=cfg.n_reads,
+                       note=f"a CPU rate: every step is a {n}-read sample of the config's {cfg.n_reads}-read stream"),
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                          "all_cores_upper_bound": {"value": round(vN, 3), "cores": used,
                                                    "note": "OpenMP-sharded, one matcher + cache per thread; NOT what "
@@ -251,13 +269,213 @@ def config_dict(cfg, n_reads, mode):
     }
 
 
+def pin_to_gpu_numa_node(local):
+    """Bind this rank to the CPUs next to its GPU BEFORE any pinned buffer is allocated, so that first-touch puts the
+    e2e buffers on the GPU's NUMA node.  Reports what happened instead of swallowing it."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        if not cpus:
+            return {"pinned": False, "why": "NVML reports no CPU affinity for this GPU"}
+        os.sched_setaffinity(0, cpus)
+        return {"pinned": True, "cpus": len(cpus), "first_cpu": cpus[0], "last_cpu": cpus[-1]}
+    except Exception as e:  # noqa: BLE001 — report, do not hide
+        sys.stderr.write(f"[bench] NUMA pinning of rank {local} failed: {e!r}\n")
+        return {"pinned": False, "why": repr(e)}
+
+
+def kernel_name(info, mode, W):
+    if mode != "table":
+        return "k_brute"
+    if int(info.cuckoo_probes) and W <= 2:
+        return f"k_probe3<W={W},NP={int(info.cuckoo_probes)}>"
+    if int(info.l2_table_entries):
+        return f"k_probe4<W={W}>"
+    return f"k_probe2<W={W}>"
+
+
+class Ctx:
+    """What every measurement needs: torch, the process group, this rank's device and stream, the roofline peak."""
+
+    def __init__(self, torch, dist, world, rank, local, dev, stream):
+        self.torch, self.dist, self.world, self.rank, self.local, self.dev, self.stream = torch, dist, world, rank, local, dev, stream
+        self.peak, self.peak_src = measured_peak()
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(self, ok):
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
+
+def parity_check(ctx, cfg, matcher, panel, d_packed, d_res, n_local, first_local, shard_of):
+    """Outside the timed region.  (i) every rank histograms ITS result words on the device; the all-reduced histogram must
+    equal the all-reduced device count table of one pass (a wrong shard offset or a double reduce that kept the sum would
+    show).  (ii) rank 0 replays a strided 20 k-read window of ANOTHER rank's shard — regenerated on the host from the
+    stream's definition — through the oracle and compares it with the result words that rank computed."""
+    import oracle
+    from fqtk_b200.distributed import all_reduce_counts, tensor_from_device_ptr
+
+    torch, dist = ctx.torch, ctx.dist
+    S = cfg.n_samples
+    matcher.reset_counts()
+    matcher.assign_packed_device(d_packed.data_ptr(), n_local, d_res.data_ptr(), ctx.stream)
+    torch.cuda.synchronize()
+    counts = tensor_from_device_ptr(matcher.counts_device_ptr(), S + 1, ctx.dev).clone()
+    idx = torch.where(d_res == -1, torch.full_like(d_res, S), (d_res >> 16) & 0xFFFF)
+    hist = torch.bincount(idx.to(torch.int64), minlength=S + 1)
+    del idx
+    local_ok = bool(torch.equal(hist, counts))
+    all_reduce_counts(counts)
+    all_reduce_counts(hist)
+    ok = bool(torch.equal(hist, counts)) and local_ok
+    # window replay: the source rank is the next one (rank 0 itself when alone)
+    span = 20_000
+    src_rank = 1 % ctx.world
+    src_first, src_n = shard_of(src_rank)
+    off = min(max(src_n // 3 + 17, 0), max(src_n - span, 0))
+    span = min(span, src_n)
+    window = torch.empty(span, dtype=torch.int32, device=ctx.dev)
+    if ctx.rank == src_rank:
+        window.copy_(d_res[off:off + span])
+    if ctx.world > 1:
+        dist.broadcast(window, src=src_rank)
+    replay = None
+    if ctx.rank == 0:
+        reads = host_reads(panel, cfg.seed_reads, src_first + off, span)
+        om = oracle.OracleMatcher([bytes(r) for r in panel], cfg.max_mismatches, cfg.min_mismatch_delta, use_cache=True)
+        want, _ = om.assign_batch(reads)
+        replay = bool(np.array_equal(window.cpu().numpy().view(np.uint32), want))
+        ok = ok and replay
+    ok = ctx.all_ok(ok)
+    matcher.reset_counts()
+    return {"ranks": ctx.world, "ok": ok, "reads_counted": int(counts.sum().item()),
+            "window": {"of_rank": src_rank, "first_read": int(src_first + off), "reads": int(span)},
+            "what": "all-reduced histogram of every rank's result words == all-reduced device counts; rank 0 replays a "
+                    "window of another rank's shard through the CPU oracle"}
+
+
+def measure_config(ctx, args, cfg_id, steps, warmup, strong, cuckoo=-1, mode="auto", keep=False, check=True):
+    """One config on this rank's shard: device-timed passes over an HBM-resident packed batch + the count all-reduce.
+    `strong`: the config's N reads are split over the ranks (contiguous shards); else every rank takes N (weak)."""
+    from fqtk_b200 import BarcodeMatcher, synth
+    from fqtk_b200.barcode_matching import kernel_launches
+    from fqtk_b200.distributed import all_reduce_counts, shard_bounds, tensor_from_device_ptr, weak_shard_first_read
+
+    torch, dist, dev, world, rank = ctx.torch, ctx.dist, ctx.dev, ctx.world, ctx.rank
+    cfg = synth.CONFIGS[cfg_id]
+    n_cfg = args.reads if (args.reads and cfg_id == args.config) else cfg.n_reads
+    if strong:
+        def shard_of(r):
+            lo, hi = shard_bounds(n_cfg, r, world)
+            return lo, hi - lo
+    else:
+        def shard_of(r):
+            return weak_shard_first_read(n_cfg, r), n_cfg
+    first, n = shard_of(rank)
+    n_total = n_cfg if strong else n_cfg * world
+    W = cfg.words_per_read
+    panel = synth.panel(cfg)
+    bcs = [bytes(r) for r in panel]
+    d_packed = torch.empty((n, W), dtype=torch.int32, device=dev)
+    d_res = torch.empty(n, dtype=torch.int32, device=dev)
+    synth.reads_device(panel, cfg.seed_reads, first, n, 0, d_packed.data_ptr(), ctx.stream)
+    opts = {} if cuckoo == -1 else {"kernel": cuckoo}
+    matcher = BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, use_cache=(mode != "brute"),
+                             device=ctx.local, **opts)
+    if mode == "table" and matcher.mode != "table":
+        raise SystemExit("memo table could not be built for this config")
+    info = matcher.info()
+    kernel = kernel_name(info, matcher.mode, W)
+    counts_t = torch.zeros(cfg.n_samples + 1, dtype=torch.int64, device=dev)
+
+    def one_pass():
+        matcher.assign_packed_device(d_packed.data_ptr(), n, d_res.data_ptr(), ctx.stream)
+
+    for _ in range(max(warmup, 0)):
+        one_pass()
+    ctx.barrier()
+    matcher.reset_counts()
+    launches0 = kernel_launches()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 2)]
+    ctx.barrier()
+    evs[0].record()
+    for k in range(steps):
+        one_pass()
+        evs[k + 1].record()
+    # the single collective of the path: the final per-sample count table (S+1 u64) summed over NVLink
+    # (int64 view of the matcher's own device counters; same stream ordering, no host round trip)
+    counts_t.copy_(tensor_from_device_ptr(matcher.counts_device_ptr(), cfg.n_samples + 1, dev))
+    if world > 1:
+        all_reduce_counts(counts_t)
+    evs[steps + 1].record()
+    ctx.barrier()
+    launches = kernel_launches() - launches0
+    total_ms = ctx.max_over_ranks(evs[0].elapsed_time(evs[steps + 1]))
+    k_ms_local = statistics.mean(evs[k].elapsed_time(evs[k + 1]) for k in range(steps))
+    k_ms = ctx.max_over_ranks(k_ms_local)
+    counts = counts_t.cpu().numpy()
+    assert int(counts.sum()) == n_total * steps, "per-sample counts must add up to every read processed"
+    value = n_total * steps / (total_ms * 1e-3) / 1e6
+    # roofline of the dominant kernel: this rank's launches, algorithmic bytes only, slowest rank's mean launch time
+    bytes_per_launch = n * cfg.algorithmic_bytes_per_read
+    achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": round(achieved, 2), "peak": ctx.peak, "unit": "GB/s",
+        "frac": round(achieved / ctx.peak, 4), "traffic": ncu_traffic(cfg_id, kernel), "kernel": kernel,
+        "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_read": cfg.algorithmic_bytes_per_read,
+        "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": ctx.peak_src,
+    }
+    out = {
+        "cfg": cfg, "n": n, "n_total": n_total, "first": first, "value": value, "total_ms": total_ms, "roofline": roofline,
+        "launches": int(launches), "counts": counts, "info": info, "mode": matcher.mode, "kernel": kernel,
+        "panel": panel, "shard_of": shard_of,
+    }
+    if check and not args.no_parity_check:
+        out["parity_check"] = parity_check(ctx, cfg, matcher, panel, d_packed, d_res, n, first, shard_of)
+    if keep:
+        out.update(matcher=matcher, d_packed=d_packed, d_res=d_res)
+    else:
+        matcher.close()
+        del d_packed, d_res
+        torch.cuda.empty_cache()
+    return out
+
+
+def config_entry(m, steps, scaling):
+    """One entry of the line's `configs` object."""
+    cfg = m["cfg"]
+    return {
+        "workload": cfg.name, "n_reads": m["n_total"], "reads_per_gpu_per_step": m["n"], "scaling": scaling,
+        "steps": steps, "value": round(m["value"], 2), "unit": UNIT, "ms": round(m["total_ms"] / steps, 4),
+        "roofline": m["roofline"], "gpu_launches": m["launches"],
+        "matched_fraction": round(1.0 - float(m["counts"][-1]) / float(m["counts"].sum()), 5),
+        "parity_check": m.get("parity_check"),
+    }
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from fqtk_b200 import BarcodeMatcher, _lib, synth
-    from fqtk_b200.barcode_matching import kernel_launches
-    from fqtk_b200.distributed import all_reduce_counts, tensor_from_device_ptr, weak_shard_first_read
+    from fqtk_b200 import _lib, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -266,102 +484,33 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: fqtk_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa_node(local) if world > 1 else {"pinned": False, "why": "single rank"}
     if world > 1:
         # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) out of it
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
-        try:  # pin this rank to the CPUs next to its GPU so the pinned e2e buffers land on the right NUMA node
-            import pynvml
-
-            pynvml.nvmlInit()
-            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
-        except Exception:
-            pass
         dist.init_process_group("nccl", device_id=dev)
+    ctx = Ctx(torch, dist, world, rank, local, dev, torch.cuda.current_stream().cuda_stream)
+    stream = ctx.stream
+    peak = ctx.peak
 
-    cfg = synth.CONFIGS[args.config]
-    n = args.reads or cfg.n_reads
-    W = cfg.words_per_read
-    panel = synth.panel(cfg)
-    bcs = [bytes(r) for r in panel]
-    stream = torch.cuda.current_stream().cuda_stream
-
-    # each rank synthesises its own shard [rank*n, (rank+1)*n) of the stream straight into HBM (weak scaling)
-    d_packed = torch.empty((n, W), dtype=torch.int32, device=dev)
-    d_res = torch.empty(n, dtype=torch.int32, device=dev)
-    synth.reads_device(panel, cfg.seed_reads, weak_shard_first_read(n, rank), n, 0, d_packed.data_ptr(), stream)
-    _lib.lib().fqtk_b200_set_cuckoo_arity(args.cuckoo)
-    matcher = BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, use_cache=(args.mode != "brute"),
-                             device=local)
-    if args.mode == "table" and matcher.mode != "table":
-        raise SystemExit("memo table could not be built for this config")
-    mode = matcher.mode
-    info = matcher.info()
-    kernel = "k_brute" if mode != "table" else (
-        f"k_probe3<W={W},NP={int(info.cuckoo_probes)}>" if int(info.cuckoo_probes) and W <= 2 else
-        f"k_probe4<W={W}>" if int(info.l2_table_entries) else "k_probe2")
-    counts_t = torch.zeros(cfg.n_samples + 1, dtype=torch.int64, device=dev)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def one_pass():
-        matcher.assign_packed_device(d_packed.data_ptr(), n, d_res.data_ptr(), stream)
-
-    for _ in range(max(args.warmup, 0)):
-        one_pass()
-    barrier()
-    matcher.reset_counts()
-
+    # ---- the headline: args.config (cfg 3), weak scaling: each rank synthesises its own shard straight into HBM ----
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.15)
-    launches0 = kernel_launches()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 2)]
-    barrier()
-    evs[0].record()
-    for k in range(args.steps):
-        one_pass()
-        evs[k + 1].record()
-    if world > 1:
-        # the single collective of the path: the final per-sample count table (S+1 u64) summed over NVLink
-        # (int64 view of the matcher's own device counters; cudaMemcpyAsync-free: same stream ordering)
-        counts_t.copy_(tensor_from_device_ptr(matcher.counts_device_ptr(), cfg.n_samples + 1, dev))
-        all_reduce_counts(counts_t)
-    evs[args.steps + 1].record()
-    barrier()
-    launches = kernel_launches() - launches0
+    head = measure_config(ctx, args, args.config, args.steps, args.warmup, strong=False, cuckoo=args.cuckoo,
+                          mode=args.mode, keep=True)
+    clocks = None
     if sampler:
         time.sleep(0.15)
         clocks = sampler.stop()
-    total_ms = evs[0].elapsed_time(evs[args.steps + 1])
-    kernel_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    if world == 1:
-        counts_t.copy_(tensor_from_device_ptr(matcher.counts_device_ptr(), cfg.n_samples + 1, dev))
-    counts = counts_t.cpu().numpy()
-    assert int(counts.sum()) == n * args.steps * world, "per-sample counts must add up to every read processed"
-    value = n * args.steps * world / (total_ms * 1e-3) / 1e6
-
-    # ---- roofline of the dominant kernel (this rank's launches; algorithmic bytes only) ----
-    peak, peak_src = measured_peak()
-    k_ms = statistics.mean(kernel_ms)
-    bytes_per_launch = n * cfg.algorithmic_bytes_per_read
-    achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9
-    roofline = {
-        "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-        "traffic": ncu_traffic(args.config, kernel), "kernel": kernel,
-        "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_read": cfg.algorithmic_bytes_per_read,
-        "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
-        "pair_compares_per_s": round(n * cfg.n_samples / (k_ms * 1e-3), 1) if mode == "brute" else None,
-    }
+    cfg, n, W = head["cfg"], head["n"], head["cfg"].words_per_read
+    matcher, d_packed, d_res = head["matcher"], head["d_packed"], head["d_res"]
+    panel, info, mode, kernel, counts = head["panel"], head["info"], head["mode"], head["kernel"], head["counts"]
+    value, total_ms, roofline, launches = head["value"], head["total_ms"], head["roofline"], head["launches"]
+    roofline["pair_compares_per_s"] = (round(n * cfg.n_samples / (roofline["kernel_ms"] * 1e-3), 1)
+                                       if mode == "brute" else None)
 
     # ---- brute-force kernel family on the same batch, for the record ----
     brute = None
@@ -383,6 +532,8 @@ def run_b200(args):
                  "roofline_frac": round(nb * cfg.algorithmic_bytes_per_read / (bms * 1e-3) / 1e9 / peak, 5)}
         matcher.set_mode("table")
         matcher.reset_counts()
+        # the north star's kernel (every read x every barcode) in the headline block too, next to the kernel that ran
+        roofline["pair_compares_per_s_brute_kernel"] = brute["pair_compares_per_s"]
 
     # ---- per-sample routing of the batch, for the record ----
     routing = None
@@ -419,7 +570,7 @@ def run_b200(args):
         while ne * (L + 4) * max(1, min(world, 8)) > 0.25 * avail and ne > (1 << 20):
             ne //= 2
         d_ascii = torch.empty((ne, L), dtype=torch.uint8, device=dev)
-        synth.reads_device(panel, cfg.seed_reads, weak_shard_first_read(n, rank), ne, d_ascii.data_ptr(), 0, stream)
+        synth.reads_device(panel, cfg.seed_reads, head["first"], ne, d_ascii.data_ptr(), 0, stream)
         h_in, h_out = C.c_void_p(), C.c_void_p()
         _lib.check(_lib.lib().fqtk_b200_host_alloc(C.byref(h_in), ne * L))
         _lib.check(_lib.lib().fqtk_b200_host_alloc(C.byref(h_out), ne * 4))
@@ -431,7 +582,7 @@ def run_b200(args):
         for _ in range(2):
             matcher.assign_batch_ptr(h_in.value, ne, L, h_out.value)
         matcher.reset_counts()
-        barrier()
+        ctx.barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             matcher.assign_batch_ptr(h_in.value, ne, L, h_out.value)  # synchronous: returns with results on the host
@@ -455,9 +606,37 @@ def run_b200(args):
         _lib.lib().fqtk_b200_host_free(h_in)
         _lib.lib().fqtk_b200_host_free(h_out)
 
+    matcher.close()
+    del d_packed, d_res
+    torch.cuda.empty_cache()
+
+    # ---- the other configs of BASELINE.json: cfg 2 weak; cfg 4 and cfg 5 STRONG over the N ranks ----
+    configs = None
+    if not args.no_configs:
+        configs = {}
+        csteps, cwarm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 3))
+        for cid, strong in ((2, False), (4, True), (5, True)):
+            if cid == args.config:
+                continue
+            m = measure_config(ctx, args, cid, csteps, cwarm, strong=strong)
+            entry = config_entry(m, csteps, "strong" if strong else "weak")
+            if strong and world > 1:
+                # the same N reads on ONE GPU of this box (rank 0, the others idle), for the strong-scaling efficiency
+                t1 = None
+                if rank == 0:
+                    solo = Ctx(torch, dist, 1, 0, local, dev, stream)
+                    m1 = measure_config(solo, args, cid, csteps, cwarm, strong=True, check=False)
+                    t1 = m1["total_ms"] / csteps
+                ctx.barrier()
+                if rank == 0:
+                    entry["strong_scaling"] = {"ms_1gpu_same_box": round(t1, 4), "ms_n_gpus": entry["ms"], "n_gpus": world,
+                                               "speedup": round(t1 / entry["ms"], 3),
+                                               "efficiency": round(t1 / entry["ms"] / world, 4)}
+            configs[f"cfg{cid}"] = entry
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(cfg, panel, args.cpu_seconds)
+        cpu = cpu_baseline(cfg, host_panel(cfg), args.cpu_seconds)
 
     if rank == 0:
         line = {
@@ -474,9 +653,9 @@ def run_b200(args):
                            "l2_table_bytes": int(info.l2_table_bytes)},
             "brute_force": brute, "routing": routing,
             "matched_fraction": round(1.0 - float(counts[-1]) / float(counts.sum()), 5),
+            "parity_check": head.get("parity_check"), "configs": configs, "numa": numa,
         }
         emit(line)
-    matcher.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -30,6 +30,11 @@ SYMBOLS = [
     "fqtk_b200_matcher_reset_counts", "fqtk_b200_matcher_set_mode", "fqtk_b200_kernel_launches",
     "fqtk_b200_last_error", "fqtk_b200_device_count", "fqtk_b200_host_alloc", "fqtk_b200_host_free",
     "fqtk_b200_synth_panel", "fqtk_b200_synth_reads_host", "fqtk_b200_synth_reads_device",
+    "fqtk_b200_matcher_assign_batch_packed", "fqtk_b200_pack_host", "fqtk_b200_copy_ceiling",
+    "fqtk_b200_group_create", "fqtk_b200_group_destroy", "fqtk_b200_group_size", "fqtk_b200_group_device",
+    "fqtk_b200_group_matcher", "fqtk_b200_group_shard", "fqtk_b200_group_assign_batch",
+    "fqtk_b200_group_assign_batch_packed", "fqtk_b200_group_assign_packed_device", "fqtk_b200_group_counts",
+    "fqtk_b200_group_reset_counts",
 ]
 
 
@@ -103,6 +108,21 @@ def lib() -> C.CDLL:
         "fqtk_b200_device_count": (C.c_int, []),
         "fqtk_b200_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
         "fqtk_b200_host_free": (C.c_int, [vp]),
+        "fqtk_b200_matcher_assign_batch_packed": (C.c_int, [vp, vp, C.c_uint64, vp, vp]),
+        "fqtk_b200_pack_host": (C.c_int, [vp, C.c_uint64, C.c_uint32, C.c_uint64, vp, C.c_int]),
+        "fqtk_b200_copy_ceiling": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
+        "fqtk_b200_group_create": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint8, C.c_uint8, C.c_int, C.POINTER(C.c_int),
+                                             C.c_uint32, C.POINTER(Options), C.POINTER(vp)]),
+        "fqtk_b200_group_destroy": (None, [vp]),
+        "fqtk_b200_group_size": (C.c_uint32, [vp]),
+        "fqtk_b200_group_device": (C.c_int, [vp, C.c_uint32]),
+        "fqtk_b200_group_matcher": (vp, [vp, C.c_uint32]),
+        "fqtk_b200_group_shard": (None, [vp, C.c_uint64, C.c_uint32, u64p, u64p]),
+        "fqtk_b200_group_assign_batch": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp]),
+        "fqtk_b200_group_assign_batch_packed": (C.c_int, [vp, vp, C.c_uint64, vp, vp]),
+        "fqtk_b200_group_assign_packed_device": (C.c_int, [vp, C.POINTER(vp), u64p, C.POINTER(vp), C.POINTER(vp)]),
+        "fqtk_b200_group_counts": (C.c_int, [vp, vp]),
+        "fqtk_b200_group_reset_counts": (C.c_int, [vp]),
         "fqtk_b200_synth_panel": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
         "fqtk_b200_synth_reads_host": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, vp]),
         "fqtk_b200_synth_reads_device": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, vp]),

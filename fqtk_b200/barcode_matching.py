@@ -170,6 +170,21 @@ class BarcodeMatcher:
         if rc != _lib.OK:
             _raise(rc)
 
+    def assign_batch_packed(self, packed: np.ndarray, want_words: bool = True, want_index: bool = False):
+        """The same batch call for reads the host already holds in BitEnc form (`pack_host`): (N, W) uint32 in, result
+        words (uint32[N]) and / or bare sample indices (uint16[N], 0xFFFF = None) out."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint32)
+        assert packed.ndim == 2 and packed.shape[1] == self.words_per_read
+        n = packed.shape[0]
+        words = np.empty(n, dtype=np.uint32) if want_words else None
+        index = np.empty(n, dtype=np.uint16) if want_index else None
+        rc = _lib.lib().fqtk_b200_matcher_assign_batch_packed(
+            self._h, packed.ctypes.data, n, words.ctypes.data if want_words else None,
+            index.ctypes.data if want_index else None)
+        if rc != _lib.OK:
+            _raise(rc)
+        return words, index
+
     def assign_segments(self, segments, n: int, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Barcodes that arrive in pieces (demux.rs:121-123): `segments` = [(rows, offset, length), ...] where `rows` is
         a C-contiguous (n, stride) uint8 host array; the pieces are gathered + encoded on the device, in order."""
@@ -242,6 +257,132 @@ class BarcodeMatcher:
 
     def reset_counts(self) -> None:
         _lib.check(_lib.lib().fqtk_b200_matcher_reset_counts(self._h))
+
+
+class MatcherGroup:
+    """One matcher per GPU of the box behind one handle (fqtk_b200_group_*): contiguous shards of every batch, ONE count
+    table (demux.rs:921-926, 970-975).  `devices` None = every visible device."""
+
+    def __init__(self, samples: Sequence, max_mismatches: int, min_mismatch_delta: int, use_cache: bool = True,
+                 devices: Optional[Sequence[int]] = None, **options):
+        bcs = barcodes_of(samples)
+        if len(bcs) == 0:
+            raise MatcherPanic("Must provide at least one sample")
+        L = len(bcs[0])
+        if any(len(b) != L for b in bcs):
+            raise MatcherPanic("All barcodes must have the same length")
+        self.n_samples, self.barcode_len = len(bcs), L
+        self._sample0_id = getattr(samples[0], "sample_id", None)
+        panel = np.frombuffer(b"".join(bcs), dtype=np.uint8)
+        opts = _lib.Options()
+        _lib.lib().fqtk_b200_options_init(C.byref(opts))
+        for name, value in options.items():
+            if name not in ("kernel", "table_budget", "chunk_bytes", "l2_table_load_pct"):
+                raise TypeError(f"unknown matcher option {name!r}")
+            setattr(opts, name, int(value))
+        devs = (C.c_int * len(devices))(*devices) if devices else None
+        self._h = C.c_void_p()
+        rc = _lib.lib().fqtk_b200_group_create(panel.ctypes.data, self.n_samples, L, max_mismatches, min_mismatch_delta,
+                                               int(bool(use_cache)), devs, len(devices) if devices else 0,
+                                               C.byref(opts), C.byref(self._h))
+        if rc != _lib.OK:
+            self._h = None
+            _raise(rc)
+
+    def close(self) -> None:
+        h = getattr(self, "_h", None)
+        if h:
+            _lib.lib().fqtk_b200_group_destroy(h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def size(self) -> int:
+        return int(_lib.lib().fqtk_b200_group_size(self._h))
+
+    @property
+    def devices(self) -> list:
+        return [int(_lib.lib().fqtk_b200_group_device(self._h, k)) for k in range(self.size)]
+
+    def shard(self, n_reads: int, k: int):
+        first, count = C.c_uint64(), C.c_uint64()
+        _lib.lib().fqtk_b200_group_shard(self._h, n_reads, k, C.byref(first), C.byref(count))
+        return int(first.value), int(count.value)
+
+    def assign_batch(self, reads: np.ndarray, lengths: Optional[np.ndarray] = None) -> np.ndarray:
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        n, stride = reads.shape
+        out = np.empty(n, dtype=np.uint32)
+        lp = None
+        if lengths is not None:
+            lengths = np.ascontiguousarray(lengths, dtype=np.uint32)
+            lp = lengths.ctypes.data
+        rc = _lib.lib().fqtk_b200_group_assign_batch(self._h, reads.ctypes.data, n, stride, lp, out.ctypes.data)
+        if rc != _lib.OK:
+            _raise(rc, self._sample0_id)
+        return out
+
+    def assign_batch_ptr(self, rows_ptr: int, n: int, stride: int, results_ptr: int) -> None:
+        rc = _lib.lib().fqtk_b200_group_assign_batch(self._h, rows_ptr, n, stride, None, results_ptr)
+        if rc != _lib.OK:
+            _raise(rc, self._sample0_id)
+
+    def assign_batch_packed(self, packed: np.ndarray, want_words: bool = True, want_index: bool = False):
+        packed = np.ascontiguousarray(packed, dtype=np.uint32)
+        n = packed.shape[0]
+        words = np.empty(n, dtype=np.uint32) if want_words else None
+        index = np.empty(n, dtype=np.uint16) if want_index else None
+        rc = _lib.lib().fqtk_b200_group_assign_batch_packed(
+            self._h, packed.ctypes.data, n, words.ctypes.data if want_words else None,
+            index.ctypes.data if want_index else None)
+        if rc != _lib.OK:
+            _raise(rc)
+        return words, index
+
+    def assign_batch_packed_ptr(self, packed_ptr: int, n: int, results_ptr: int = 0, index_ptr: int = 0) -> None:
+        rc = _lib.lib().fqtk_b200_group_assign_batch_packed(self._h, packed_ptr, n, results_ptr or None, index_ptr or None)
+        if rc != _lib.OK:
+            _raise(rc)
+
+    def assign_packed_device(self, d_packed: Sequence[int], n_reads: Sequence[int], d_results: Sequence[int],
+                             streams: Optional[Sequence[int]] = None) -> None:
+        G = self.size
+        assert len(d_packed) == len(n_reads) == len(d_results) == G
+        pk = (C.c_void_p * G)(*d_packed)
+        rs = (C.c_void_p * G)(*d_results)
+        ns = (C.c_uint64 * G)(*n_reads)
+        st = (C.c_void_p * G)(*streams) if streams else None
+        rc = _lib.lib().fqtk_b200_group_assign_packed_device(self._h, pk, ns, rs, st)
+        if rc != _lib.OK:
+            _raise(rc)
+
+    def counts(self) -> np.ndarray:
+        out = np.zeros(self.n_samples + 1, dtype=np.uint64)
+        _lib.check(_lib.lib().fqtk_b200_group_counts(self._h, out.ctypes.data))
+        return out
+
+    def reset_counts(self) -> None:
+        _lib.check(_lib.lib().fqtk_b200_group_reset_counts(self._h))
+
+
+def pack_host(reads: np.ndarray, threads: int = 0) -> np.ndarray:
+    """encode() of every row on the host (fqtk_b200_pack_host): (N, stride >= L) uint8 -> (N, W) uint32 BitEnc words."""
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    n, L = reads.shape
+    out = np.empty((n, (L + 7) // 8), dtype=np.uint32)
+    _lib.check(_lib.lib().fqtk_b200_pack_host(reads.ctypes.data, n, L, L, out.ctypes.data, threads))
+    return out
 
 
 def encode(bases: bytes) -> list[int]:

@@ -29,8 +29,13 @@ int synth_panel_host(uint64_t seed, uint32_t S, uint32_t L, uint32_t min_distanc
 }  // namespace fq
 
 namespace {
-
 thread_local std::string g_err;
+}
+namespace fq {
+void set_last_error(const std::string& msg) { g_err = msg; }  // for the other translation units of the library
+}
+namespace {
+
 constexpr size_t TIER_BUDGET_BYTES = 132u << 10;  // shared memory the hot tier may take per CTA
 
 // Defaults of fqtk_b200_matcher_create (the form without an options struct).  Thread-local: two host threads that each
@@ -1096,6 +1101,41 @@ int fqtk_b200_matcher_assign_batch(fqtk_b200_matcher* m, const uint8_t* rows, ui
         rc = run_device(m, src, m->d_out[slot], st, slot);
         if (rc != FQTK_B200_OK) return rc;
         CU(cudaMemcpyAsync(results + done, m->d_out[slot], c * 4, cudaMemcpyDeviceToHost, st));
+        done += c;
+        slot = (slot + 1) % N_PIPE;
+    }
+    for (int s = 0; s < N_PIPE; s++) CU(cudaStreamSynchronize(m->streams[s]));
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_matcher_assign_batch_packed(fqtk_b200_matcher* m, const uint32_t* packed, uint64_t n, uint32_t* results,
+                                          uint16_t* sample_index) {
+    if (!m || (n && !packed) || (n && !results && !sample_index)) return fail(FQTK_B200_ERR_ARG, "NULL argument");
+    if (n == 0) return FQTK_B200_OK;
+    CU(cudaSetDevice(m->device));
+    PipelineDrain drain{m};
+    const uint64_t row_bytes = (uint64_t)m->W * 4u;
+    uint64_t chunk = std::max<uint64_t>(m->opt.chunk_bytes / row_bytes, 1024);
+    chunk = std::min<uint64_t>(chunk, n) & ~3ull;  // chunk starts stay 16-byte aligned on the device (vector loads)
+    if (chunk == 0) chunk = n;
+    int rc = ensure_pipeline(m, (size_t)(chunk * row_bytes + 16), (size_t)chunk, sample_index != nullptr);
+    if (rc != FQTK_B200_OK) return rc;
+    uint64_t done = 0;
+    int slot = 0;
+    while (done < n) {
+        const uint64_t c = std::min(chunk, n - done);
+        cudaStream_t st = m->streams[slot];
+        uint32_t* d_words = reinterpret_cast<uint32_t*>(m->d_in[slot]);
+        CU(cudaMemcpyAsync(d_words, packed + done * m->W, (size_t)(c * row_bytes), cudaMemcpyHostToDevice, st));
+        fq::ReadSource src{d_words, nullptr, nullptr, 0, c};
+        rc = run_device(m, src, m->d_out[slot], st, slot);
+        if (rc != FQTK_B200_OK) return rc;
+        if (results) CU(cudaMemcpyAsync(results + done, m->d_out[slot], c * 4, cudaMemcpyDeviceToHost, st));
+        if (sample_index) {
+            uint16_t* d16 = reinterpret_cast<uint16_t*>(m->d_len[slot]);
+            CU(fq::launch_narrow_u16(m->d_out[slot], c, d16, m->geo, st));
+            CU(cudaMemcpyAsync(sample_index + done, d16, c * 2, cudaMemcpyDeviceToHost, st));
+        }
         done += c;
         slot = (slot + 1) % N_PIPE;
     }

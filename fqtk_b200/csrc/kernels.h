@@ -129,6 +129,8 @@ size_t route_workspace_bytes(uint64_t n, uint32_t S, const LaunchGeometry& g);
 bool route_supported(uint32_t S, const LaunchGeometry& g);
 cudaError_t launch_route(const uint32_t* d_results, uint64_t n, uint32_t S, uint32_t* d_order,
                          unsigned long long* d_offsets, void* d_workspace, const LaunchGeometry& g, cudaStream_t stream);
+cudaError_t launch_narrow_u16(const uint32_t* d_results, uint64_t n, uint16_t* d_out, const LaunchGeometry& g,
+                              cudaStream_t stream);
 cudaError_t prepare_kernels(const LaunchGeometry& g);  // opt-in shared memory attributes, once per device
 
 size_t probe3_smem_bytes(uint32_t ck_words, uint32_t S, uint32_t stash_cap);

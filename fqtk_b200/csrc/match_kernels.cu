@@ -1807,6 +1807,25 @@ cudaError_t launch_pack_segments(const SegmentSource& seg, uint64_t n, uint32_t 
     return cudaGetLastError();
 }
 
+// result words -> u16 sample indices (0xFFFF = None): the 2-byte-per-read return format of the packed host call
+__global__ void __launch_bounds__(256) k_narrow_u16(const uint32_t* __restrict__ results, uint64_t n,
+                                                    uint16_t* __restrict__ out) {
+    const uint64_t total = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += total) {
+        const uint32_t r = __ldg(results + i);
+        out[i] = r == NONE ? (uint16_t)0xFFFFu : (uint16_t)(r >> 16);
+    }
+}
+
+cudaError_t launch_narrow_u16(const uint32_t* d_results, uint64_t n, uint16_t* d_out, const LaunchGeometry& g,
+                              cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const int grid = grid_for(k_narrow_u16, 256, 0, g, n);
+    k_narrow_u16<<<grid, 256, 0, stream>>>(d_results, n, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t prepare_kernels(const LaunchGeometry&) { return cudaSuccess; }
 
 }  // namespace fq

@@ -138,6 +138,18 @@ FQTK_B200_API int fqtk_b200_matcher_assign_batch(fqtk_b200_matcher* m, const uin
                                                  uint64_t n_reads, uint64_t row_stride, const uint32_t* lengths,
                                                  uint32_t* results);
 
+/* The same batch call for a host that already holds the reads in the reference's own BitEnc form (what encode(),
+ * mod.rs:49-61, returns — fqtk_b200_pack_host produces it): `packed` = n_reads * W u32 words in HOST memory, layout as for
+ * the device calls below.  Half the bytes of ASCII rows over PCIe (8 instead of 16 at dual 8+8 bp).  Results come back as
+ * result words (`results`, 4 bytes per read) and / or as bare sample indices (`sample_index`, 2 bytes per read, 0xFFFF =
+ * None: all the caller's routing needs, demux.rs:970-975); either pointer may be NULL, not both.  Synchronous, chunked. */
+FQTK_B200_API int fqtk_b200_matcher_assign_batch_packed(fqtk_b200_matcher* m, const uint32_t* packed, uint64_t n_reads,
+                                                        uint32_t* results, uint16_t* sample_index);
+/* encode() of n_reads host rows (mod.rs:49-61): row i at rows + i*row_stride, barcode_len symbols each -> W words each.
+ * Pure encoding on the host (two symbols per table lookup, `threads` host threads, 0 = all), no GPU involved. */
+FQTK_B200_API int fqtk_b200_pack_host(const uint8_t* rows, uint64_t n_reads, uint32_t barcode_len, uint64_t row_stride,
+                                      uint32_t* out_packed, int threads);
+
 /* The same call for barcodes that arrive in pieces (SURVEY 8f "next" #1: B-segment extraction fused on the GPU).
  * ReadSet::sample_barcode_sequence (demux.rs:121-123) concatenates the sample-barcode segments of ALL inputs, in input
  * order then in-read order; here each fixed-length B segment is described once and gathered + encoded on the device:
@@ -192,6 +204,45 @@ FQTK_B200_API int fqtk_b200_matcher_route(fqtk_b200_matcher* m, const uint32_t* 
 FQTK_B200_API int fqtk_b200_matcher_counts(fqtk_b200_matcher* m, uint64_t* out_counts); /* syncs the device */
 FQTK_B200_API int fqtk_b200_matcher_counts_device(fqtk_b200_matcher* m, uint64_t** d_counts); /* for ncclAllReduce */
 FQTK_B200_API int fqtk_b200_matcher_reset_counts(fqtk_b200_matcher* m);
+
+/* ---- several GPUs of one box in ONE process ----------------------------------------------------
+ * The reference owns one matcher and one count table (demux.rs:921-926, 970-975).  A group is the same thing over G
+ * devices: the panel's tables are built on every device (concurrently, one host thread each), a batch is split into G
+ * contiguous shards (fqtk_b200_group_shard: shard k = reads [first, first + count), in input order, so results[] is
+ * filled exactly as by a single matcher), each shard runs on its device from its own host thread, and the G count tables
+ * are summed on the first device — peers are read over NVLink through peer-mapped pointers by one small kernel (staged
+ * copies where peer access is not available).  `devices` NULL / n_devices 0 = every visible device.  A host that
+ * already runs NCCL can instead all-reduce the per-device tables itself: fqtk_b200_group_matcher + ..._counts_device. */
+typedef struct fqtk_b200_group fqtk_b200_group;
+FQTK_B200_API int fqtk_b200_group_create(const uint8_t* panel_ascii, uint32_t n_samples, uint32_t barcode_len,
+                                         uint8_t max_mismatches, uint8_t min_mismatch_delta, int use_cache,
+                                         const int* devices, uint32_t n_devices, const fqtk_b200_options* opts,
+                                         fqtk_b200_group** out);
+FQTK_B200_API void fqtk_b200_group_destroy(fqtk_b200_group* g);
+FQTK_B200_API uint32_t fqtk_b200_group_size(const fqtk_b200_group* g);
+FQTK_B200_API int fqtk_b200_group_device(const fqtk_b200_group* g, uint32_t k);                /* device ordinal of shard k */
+FQTK_B200_API fqtk_b200_matcher* fqtk_b200_group_matcher(fqtk_b200_group* g, uint32_t k);     /* borrowed, not owned */
+FQTK_B200_API void fqtk_b200_group_shard(const fqtk_b200_group* g, uint64_t n_reads, uint32_t k, uint64_t* first,
+                                         uint64_t* count);
+/* fqtk_b200_matcher_assign_batch / _assign_batch_packed over the group: host buffers, synchronous. */
+FQTK_B200_API int fqtk_b200_group_assign_batch(fqtk_b200_group* g, const uint8_t* barcodes_ascii, uint64_t n_reads,
+                                               uint64_t row_stride, const uint32_t* lengths, uint32_t* results);
+FQTK_B200_API int fqtk_b200_group_assign_batch_packed(fqtk_b200_group* g, const uint32_t* packed, uint64_t n_reads,
+                                                      uint32_t* results, uint16_t* sample_index);
+/* HBM-resident shards: d_packed[k] / d_results[k] live on device k (n_reads[k] reads); asynchronous on streams[k]
+ * (streams NULL = default streams). */
+FQTK_B200_API int fqtk_b200_group_assign_packed_device(fqtk_b200_group* g, const uint32_t* const* d_packed,
+                                                       const uint64_t* n_reads, uint32_t* const* d_results,
+                                                       void* const* streams);
+/* The ONE count table: S + 1 u64 summed over the devices (synchronises them).  */
+FQTK_B200_API int fqtk_b200_group_counts(fqtk_b200_group* g, uint64_t* out_counts);
+FQTK_B200_API int fqtk_b200_group_reset_counts(fqtk_b200_group* g);
+
+/* ---- measurement aid: what the platform's pinned-memory copies alone can do (no kernels) ----
+ * Moves in_bytes host->device and out_bytes device->host in chunks over three streams, like the host-buffer calls do,
+ * `reps` times after one warm-up; *seconds_per_rep = mean wall time.  The ceiling any host-buffer call is held against. */
+FQTK_B200_API int fqtk_b200_copy_ceiling(int device, uint64_t in_bytes, uint64_t out_bytes, uint64_t chunk_in_bytes,
+                                         int reps, double* seconds_per_rep);
 
 /* ---- control / introspection ---- */
 FQTK_B200_API int fqtk_b200_matcher_set_mode(fqtk_b200_matcher* m, int mode); /* TABLE needs a built table */

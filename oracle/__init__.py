@@ -29,10 +29,8 @@ ERR_ARG = -4
 
 def build(force: bool = False) -> str:
     """Compile liboracle.so with the committed Makefile (gcc).  Returns the path."""
-    src = os.path.join(_HERE, "fqtk_oracle.c")
-    stale = (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(
-        os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "fqtk_oracle.h"))
-    )
+    srcs = [os.path.join(_HERE, f) for f in ("fqtk_oracle.c", "fqtk_synth.c", "fqtk_oracle.h", "Makefile")]
+    stale = (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "clean", "all"], check=True, capture_output=True)
     return _SO
@@ -74,6 +72,10 @@ def lib() -> C.CDLL:
         f = getattr(L, name)
         f.restype = C.c_int
         f.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, u32p]
+    L.fqo_synth_reads.restype = None
+    L.fqo_synth_reads.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+    L.fqo_synth_panel.restype = C.c_int
+    L.fqo_synth_panel.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     L.fqo_assign_batch.restype = C.c_int
     L.fqo_assign_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
     L.fqo_assign_batch_mt.restype = C.c_int
@@ -239,6 +241,23 @@ def assign_batch_mt(barcodes_panel: np.ndarray, max_mismatches: int, min_mismatc
     if used < 0:
         raise OraclePanic(f"assign_batch_mt rc={used}")
     return res, counts, used
+
+
+def synth_panel(seed: int, n_samples: int, barcode_len: int, min_distance: int = 3, n_degenerate: int = 0) -> np.ndarray:
+    """(S, L) uint8 ASCII panel of the synthetic workload (fqtk_synth.c) — the same bytes fqtk_b200.synth.make_panel gives."""
+    out = np.empty((n_samples, barcode_len), dtype=np.uint8)
+    if lib().fqo_synth_panel(seed, n_samples, barcode_len, min_distance, n_degenerate, out.ctypes.data) != 0:
+        raise ValueError("no panel with that many samples at that distance")
+    return out
+
+
+def synth_reads(panel: np.ndarray, seed: int, first: int, n: int) -> np.ndarray:
+    """(n, L) uint8 ASCII reads [first, first + n) of the synthetic stream — the same bytes fqtk_b200.synth.reads_host gives."""
+    panel = np.ascontiguousarray(panel, dtype=np.uint8)
+    S, L = panel.shape
+    out = np.empty((n, L), dtype=np.uint8)
+    lib().fqo_synth_reads(panel.ctypes.data, S, L, seed, first, n, out.ctypes.data)
+    return out
 
 
 def max_threads() -> int:

@@ -99,6 +99,14 @@ int fqo_assign_batch_mt(const uint8_t* panel, uint32_t S, uint32_t L, uint8_t ma
 
 int fqo_max_threads(void);
 
+/* ---- synthetic workload (fqtk_synth.c): the benchmark's deterministic read stream and panels, byte for byte what
+ * fqtk_b200/csrc/synth.cu generates — here so that the CPU reference arm of bench.py loads nothing of the product.
+ * Workload generation only: nothing below matches reads. ---- */
+void fqo_synth_reads(const uint8_t* panel, uint32_t S, uint32_t L, uint64_t seed, uint64_t first, uint64_t n,
+                     uint8_t* out /* n * L */);
+int fqo_synth_panel(uint64_t seed, uint32_t S, uint32_t L, uint32_t min_distance, uint32_t n_degenerate,
+                    uint8_t* out /* S * L */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -284,6 +284,86 @@ def test_matchers_created_concurrently_with_different_options():
             assert (l2e > 0) == (k == 1), (k, l2e)
 
 
+def test_packed_host_wire_format():
+    """fqtk_b200_matcher_assign_batch_packed: BitEnc words in HOST memory in (what encode() returns; half the PCIe bytes of
+    ASCII rows), result words and / or 2-byte sample indices out — the same answers as the ASCII call, chunked pipeline
+    included (chunk_bytes = 256 KiB -> ~30 chunks)."""
+    from fqtk_b200.barcode_matching import pack_host
+
+    for cfg_id, n in ((3, 250_003), (5, 60_001), (2, 100_000)):
+        cfg = synth.CONFIGS[cfg_id]
+        panel = synth.panel(cfg)
+        bcs = [bytes(r) for r in panel]
+        reads = synth.reads_host(panel, cfg.seed_reads, 5, n)
+        reads[::53, 1] = ord("r")
+        want, want_counts = oracle.OracleMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta).assign_batch(reads)
+        packed = pack_host(reads)
+        for use_cache in MODES:
+            with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, use_cache, chunk_bytes=256 << 10) as m:
+                words, index = m.assign_batch_packed(packed, want_words=True, want_index=True)
+                assert np.array_equal(words, want)
+                assert np.array_equal(index, np.where(want == _lib.NONE, 0xFFFF, want >> 16).astype(np.uint16))
+                assert np.array_equal(m.counts(), want_counts)
+                m.reset_counts()
+                words, index = m.assign_batch_packed(packed, want_words=False, want_index=True)
+                assert words is None and np.array_equal(index.astype(np.uint32) == 0xFFFF, want == _lib.NONE)
+                assert np.array_equal(m.counts(), want_counts)
+    # barcodes longer than 32 bases go through the same call
+    rng = np.random.default_rng(3)
+    bcs = random_panel(rng, 11, 45, ALPHABETS["acgtn"])
+    reads = random_reads(rng, bcs, 45, 20_000, ALPHABETS["dirty"])
+    want, _ = oracle.OracleMatcher(bcs, 2, 1).assign_batch(reads, mode=0)
+    with BarcodeMatcher(bcs, 2, 1, True, chunk_bytes=64 << 10) as m:
+        words, _ = m.assign_batch_packed(pack_host(reads))
+        assert np.array_equal(words, want)
+
+
+@pytest.mark.parametrize("devices", [None, [0, 0, 0]])
+def test_group_of_matchers_is_one_matcher(devices):
+    """fqtk_b200_group_*: a batch split into contiguous shards over the devices of the box (every visible device; and
+    three handles on device 0, which exercises the shard / reduce logic on a one-GPU box) gives exactly the result words of
+    a single matcher, in input order, and ONE count table — host ASCII rows, host packed words and HBM-resident shards."""
+    torch = torch_cuda()
+    from fqtk_b200 import MatcherGroup
+    from fqtk_b200.barcode_matching import pack_host
+
+    cfg = synth.CONFIGS[3]
+    panel = synth.panel(cfg)
+    bcs = [bytes(r) for r in panel]
+    n = 1_000_003
+    reads = synth.reads_host(panel, cfg.seed_reads, 99, n)
+    reads[::97, 3] = ord("R")
+    want, want_counts = oracle.OracleMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta).assign_batch(reads)
+    with MatcherGroup(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, True, devices=devices, chunk_bytes=1 << 20) as g:
+        G = g.size
+        assert G == (len(devices) if devices else torch.cuda.device_count())
+        bounds = [g.shard(n, k) for k in range(G)]
+        assert bounds[0][0] == 0 and sum(c for _, c in bounds) == n
+        assert all(bounds[k][0] + bounds[k][1] == bounds[k + 1][0] for k in range(G - 1))
+        assert np.array_equal(g.assign_batch(reads), want)
+        assert np.array_equal(g.counts(), want_counts)
+        g.reset_counts()
+        packed = pack_host(reads)
+        words, index = g.assign_batch_packed(packed, want_words=True, want_index=True)
+        assert np.array_equal(words, want)
+        assert np.array_equal(index.astype(np.uint32) == 0xFFFF, want == _lib.NONE)
+        assert np.array_equal(g.counts(), want_counts)
+        g.reset_counts()
+        # HBM-resident shards, one per device, asynchronous launches
+        d_packed, d_res = [], []
+        for k, (first, count) in enumerate(bounds):
+            dev = torch.device("cuda", g.devices[k])
+            d_packed.append(torch.from_numpy(packed[first:first + count].view(np.int32)).to(dev))
+            d_res.append(torch.empty(count, dtype=torch.int32, device=dev))
+        for _ in range(2):
+            g.assign_packed_device([t.data_ptr() for t in d_packed], [c for _, c in bounds], [t.data_ptr() for t in d_res])
+        got = np.concatenate([t.cpu().numpy().view(np.uint32) for t in d_res])
+        assert np.array_equal(got, want)
+        assert np.array_equal(g.counts(), 2 * want_counts)  # ONE table over all devices, accumulated over both passes
+    with pytest.raises(_lib.Fqtk_b200Error):
+        MatcherGroup(bcs, 1, 2, True, devices=[99])
+
+
 def test_many_samples_use_global_histogram_and_big_panel():
     rng = np.random.default_rng(6)
     S, L = 9000, 12  # S + 1 > 8192 shared-memory bins

@@ -290,3 +290,30 @@ def test_batched_pipeline_host_logic_with_the_oracle_as_matcher(kats):
         if "expect_counts" in case:
             assert out.counts.tolist() == case["expect_counts"]
             assert [r.templates for r in out.metrics] == case["expect_counts"]
+
+
+def test_pack_host_is_encode_for_every_row():
+    """fqtk_b200_pack_host (two symbols per table lookup, several host threads) == encode() (mod.rs:49-61) of every row:
+    checked against the numpy restatement and, per row, against the oracle's encode; all 256 byte values, odd and even L,
+    row strides wider than L."""
+    import oracle
+    from fqtk_b200 import _lib, synth
+    from fqtk_b200.barcode_matching import pack_host
+
+    rng = np.random.default_rng(2024)
+    for L in (1, 2, 7, 8, 9, 16, 17, 20, 31, 32, 33, 40, 254):
+        n = 200_000 if L == 16 else 3000
+        reads = rng.integers(0, 256, size=(n, L), dtype=np.uint8)
+        reads[::3] = np.frombuffer(b"ACGTNacgtn.RYKMSWBDHVUu-*", dtype=np.uint8)[rng.integers(0, 25, size=reads[::3].shape)]
+        got = pack_host(reads, threads=0 if L == 16 else 1)
+        assert np.array_equal(got, synth.pack_host(reads)), L
+        W = (L + 7) // 8
+        for i in (0, 1, n - 1):
+            blocks, n_symbols = oracle.encode(bytes(reads[i]))
+            assert n_symbols == L and blocks == got[i].tolist(), (L, i)
+        # a wider row stride: only the first L bytes of a row count
+        wide = np.full((n, L + 5), ord("T"), dtype=np.uint8)
+        wide[:, :L] = reads
+        out = np.empty((n, W), dtype=np.uint32)
+        _lib.check(_lib.lib().fqtk_b200_pack_host(wide.ctypes.data, n, L, L + 5, out.ctypes.data, 2))
+        assert np.array_equal(out, got), L

@@ -208,3 +208,19 @@ def test_batch_mt_equals_single_thread():
     assert used >= 1
     assert np.array_equal(res1, res2) and np.array_equal(c1, c2)
     assert int(c1.sum()) == reads.shape[0]
+
+
+def test_oracle_workload_generator_is_the_products_generator():
+    """bench.py's CPU legs (cpu_baseline, --impl reference) take panel and reads from the oracle's own copy of the
+    synthetic workload generator (oracle/fqtk_synth.c), so that the reference arm loads nothing of the product; it must
+    produce, byte for byte, the stream of fqtk_b200/csrc/synth.cu that the GPU arm measures."""
+    from fqtk_b200 import synth
+
+    for cid in (1, 2, 3, 5):
+        cfg = synth.CONFIGS[cid]
+        want_panel = synth.panel(cfg)
+        got_panel = oracle.synth_panel(cfg.seed_panel, cfg.n_samples, cfg.barcode_len, cfg.min_distance, cfg.n_degenerate)
+        assert np.array_equal(got_panel, want_panel), cid
+        for first, n in ((0, 5000), (cfg.n_reads - 777, 777), (123_456_789 % cfg.n_reads, 3000)):
+            assert np.array_equal(oracle.synth_reads(got_panel, cfg.seed_reads, first, n),
+                                  synth.reads_host(want_panel, cfg.seed_reads, first, n)), (cid, first)
