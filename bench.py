@@ -58,6 +58,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-brute", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg 2 / 4 / 5 entries of the line")
+    ap.add_argument("--single-process", action="store_true",
+                    help="ONE process driving --gpus N devices through the C ABI's group handle (fqtk_b200_group_*) "
+                         "instead of one torchrun rank per GPU")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target CPU seconds for the cpu_baseline sample")
     return ap.parse_args()
@@ -471,6 +474,208 @@ def config_entry(m, steps, scaling):
     }
 
 
+def measure_e2e(ctx, args, cfg, panel, matcher, d_packed, d_res, first, n):
+    """The same metric through the reference-facing C-ABI calls on pinned HOST buffers, copies inside the timed region
+    (wall clock around the synchronous calls, max over ranks), for both wire formats:
+      ascii   fqtk_b200_matcher_assign_batch: L ASCII bytes per read in, 4-byte result words out (the drop-in form)
+      packed  fqtk_b200_matcher_assign_batch_packed: the reference's own BitEnc words in (4*W bytes), u16 sample index out
+    each next to the platform's ceiling for exactly those bytes (fqtk_b200_copy_ceiling: the same chunked pinned copies
+    with no kernel in between, all ranks at once)."""
+    import ctypes as C
+
+    import psutil
+
+    from fqtk_b200 import _lib, synth
+
+    torch, world = ctx.torch, ctx.world
+    lib = _lib.lib()
+    L, W = cfg.barcode_len, cfg.words_per_read
+    ne = min(args.e2e_reads, n)
+    avail = psutil.virtual_memory().available
+    while ne * (L + 4 * W + 8) * max(1, min(world, 8)) > 0.25 * avail and ne > (1 << 20):
+        ne //= 2
+    ne &= ~3
+
+    def pinned(nbytes):
+        p = C.c_void_p()
+        _lib.check(lib.fqtk_b200_host_alloc(C.byref(p), nbytes))
+        return p
+
+    h_in, h_out, h_pk, h_idx = pinned(ne * L), pinned(ne * 4), pinned(ne * W * 4), pinned(ne * 2)
+    h_in_np = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_uint8)), shape=(ne, L))
+    h_out_np = np.ctypeslib.as_array(C.cast(h_out, C.POINTER(C.c_uint32)), shape=(ne,))
+    h_pk_np = np.ctypeslib.as_array(C.cast(h_pk, C.POINTER(C.c_uint32)), shape=(ne, W))
+    h_idx_np = np.ctypeslib.as_array(C.cast(h_idx, C.POINTER(C.c_uint16)), shape=(ne,))
+    d_ascii = torch.empty((ne, L), dtype=torch.uint8, device=ctx.dev)
+    synth.reads_device(panel, cfg.seed_reads, first, ne, d_ascii.data_ptr(), 0, ctx.stream)
+    h_in_np[:] = d_ascii.cpu().numpy()
+    del d_ascii
+    t0 = time.perf_counter()
+    _lib.check(lib.fqtk_b200_pack_host(h_in.value, ne, L, L, h_pk.value, 0))  # the host's own encode() of the rows
+    pack_s = time.perf_counter() - t0
+
+    def timed(call):
+        matcher.reset_counts()
+        for _ in range(2):
+            call()
+        matcher.reset_counts()
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            call()  # synchronous: returns with the results on the host
+        torch.cuda.synchronize()
+        return ctx.max_over_ranks(time.perf_counter() - t0) / args.steps
+
+    def ceiling(in_bytes, out_bytes):
+        sec = C.c_double()
+        ctx.barrier()
+        _lib.check(lib.fqtk_b200_copy_ceiling(ctx.local, in_bytes, out_bytes, 32 << 20, 3, C.byref(sec)))
+        return ctx.max_over_ranks(sec.value)
+
+    dt_ascii = timed(lambda: matcher.assign_batch_ptr(h_in.value, ne, L, h_out.value))
+    # the host results must be the device path's results for the same reads
+    chk = min(ne, 1 << 20)
+    matcher.reset_counts()
+    matcher.assign_packed_device(d_packed.data_ptr(), chk, d_res.data_ptr(), ctx.stream)
+    torch.cuda.synchronize()
+    want = d_res[:chk].cpu().numpy().view(np.uint32)
+    assert np.array_equal(want, h_out_np[:chk]), "e2e results differ"
+    dt_packed = timed(lambda: _lib.check(lib.fqtk_b200_matcher_assign_batch_packed(
+        matcher._h, h_pk.value, ne, None, h_idx.value)))
+    assert np.array_equal(np.where(want == 0xFFFFFFFF, 0xFFFF, want >> 16).astype(np.uint16), h_idx_np[:chk]), \
+        "packed e2e results differ"
+    assert np.array_equal(h_pk_np[:chk], synth.pack_host(h_in_np[:chk])), "host pack differs from encode()"
+    ceil_ascii = ceiling(ne * L, ne * 4)
+    ceil_packed = ceiling(ne * W * 4, ne * 2)
+
+    def mreads(sec):
+        return round(ne * world / sec / 1e6, 2)
+
+    out = {
+        "value": mreads(dt_ascii), "unit": UNIT, "h2d_bytes_per_step": ne * L * world, "d2h_bytes_per_step": ne * 4 * world,
+        "reads_per_gpu_per_step": ne, "ms_per_step": round(dt_ascii * 1e3, 3),
+        "api": "fqtk_b200_matcher_assign_batch (ASCII rows in pinned host memory -> result words in pinned host memory; "
+               "chunked H2D / kernel / D2H overlap inside the call)",
+        "ceiling": mreads(ceil_ascii), "frac_of_ceiling": round(ceil_ascii / dt_ascii, 4),
+        "ceiling_what": "fqtk_b200_copy_ceiling: the same bytes through the same chunked pinned copies, no kernel, all "
+                        "ranks at once (tools/h2d_ceiling.cu is the stand-alone form)",
+        "h2d_gb_per_s_per_gpu": round(ne * L / dt_ascii / 1e9, 2),
+        "packed": {
+            "value": mreads(dt_packed), "unit": UNIT, "h2d_bytes_per_step": ne * W * 4 * world,
+            "d2h_bytes_per_step": ne * 2 * world, "ms_per_step": round(dt_packed * 1e3, 3),
+            "api": "fqtk_b200_matcher_assign_batch_packed (the reference's BitEnc words in pinned host memory -> u16 "
+                   "sample indices); the host's encode() of the rows (fqtk_b200_pack_host) is NOT in the timed region",
+            "ceiling": mreads(ceil_packed), "frac_of_ceiling": round(ceil_packed / dt_packed, 4),
+            "host_pack_mreads_per_s": round(ne / pack_s / 1e6, 1), "host_pack_threads": os.cpu_count(),
+        },
+    }
+    for p in (h_in, h_out, h_pk, h_idx):
+        lib.fqtk_b200_host_free(p)
+    matcher.reset_counts()
+    return out
+
+
+def run_single_process(args):
+    """The headline config through fqtk_b200_group_*: one process, one matcher per GPU, contiguous shards, ONE count table
+    summed on the first device over peer-mapped pointers — the process model of the Rust host."""
+    import ctypes as C
+
+    import torch
+
+    from fqtk_b200 import MatcherGroup, _lib, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: fqtk_b200 has no CPU fallback")
+    G = min(args.gpus, torch.cuda.device_count())
+    cfg = synth.CONFIGS[args.config]
+    n = args.reads or cfg.n_reads
+    W, L = cfg.words_per_read, cfg.barcode_len
+    panel = synth.panel(cfg)
+    bcs = [bytes(r) for r in panel]
+    peak, peak_src = measured_peak()
+    group = MatcherGroup(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, True, devices=list(range(G)))
+    d_packed, d_res, streams = [], [], []
+    for k in range(G):  # weak scaling: device k holds reads [k*n, (k+1)*n) of the stream
+        with torch.cuda.device(k):
+            dev = torch.device("cuda", k)
+            d_packed.append(torch.empty((n, W), dtype=torch.int32, device=dev))
+            d_res.append(torch.empty(n, dtype=torch.int32, device=dev))
+            streams.append(torch.cuda.current_stream(dev).cuda_stream)
+            synth.reads_device(panel, cfg.seed_reads, k * n, n, 0, d_packed[k].data_ptr(), streams[k])
+    pk, rs, ns = [t.data_ptr() for t in d_packed], [t.data_ptr() for t in d_res], [n] * G
+
+    def sync_all():
+        for k in range(G):
+            torch.cuda.synchronize(k)
+
+    for _ in range(max(args.warmup, 1)):
+        group.assign_packed_device(pk, ns, rs, streams)
+    sync_all()
+    group.reset_counts()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(G)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(G)]
+    for k in range(G):
+        with torch.cuda.device(k):
+            ev0[k].record()
+    for _ in range(args.steps):
+        group.assign_packed_device(pk, ns, rs, streams)
+    for k in range(G):
+        with torch.cuda.device(k):
+            ev1[k].record()
+    sync_all()
+    t0 = time.perf_counter()
+    counts = group.counts()  # the reduce over the devices (peer-mapped loads on device 0) + D2H
+    reduce_ms = (time.perf_counter() - t0) * 1e3
+    total_ms = max(ev0[k].elapsed_time(ev1[k]) for k in range(G)) + reduce_ms
+    assert int(counts.sum()) == n * G * args.steps
+    # parity: every device's histogram of result words, summed, == the group's one table; a window against the oracle
+    hist = np.zeros(cfg.n_samples + 1, dtype=np.int64)
+    for k in range(G):
+        idx = torch.where(d_res[k] == -1, torch.full_like(d_res[k], cfg.n_samples), (d_res[k] >> 16) & 0xFFFF)
+        hist += torch.bincount(idx.to(torch.int64), minlength=cfg.n_samples + 1).cpu().numpy()
+    ok = bool(np.array_equal(hist * args.steps, counts.astype(np.int64)))
+    import oracle
+
+    src = G - 1
+    off, span = n // 3 + 17, 20_000
+    want, _ = oracle.OracleMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta).assign_batch(
+        host_reads(panel, cfg.seed_reads, src * n + off, span))
+    ok = ok and bool(np.array_equal(d_res[src][off:off + span].cpu().numpy().view(np.uint32), want))
+    value = n * G * args.steps / (total_ms * 1e-3) / 1e6
+    k_ms = max(ev0[k].elapsed_time(ev1[k]) for k in range(G)) / args.steps
+    roofline = {"bound": "hbm", "achieved": round(n * cfg.algorithmic_bytes_per_read / (k_ms * 1e-3) / 1e9, 2), "peak": peak,
+                "unit": "GB/s", "frac": round(n * cfg.algorithmic_bytes_per_read / (k_ms * 1e-3) / 1e9 / peak, 4),
+                "traffic": None, "kernel": "group of per-device matchers", "kernel_ms": round(k_ms, 4), "peak_source": peak_src}
+    # e2e: ONE pinned host batch of G * ne reads through fqtk_b200_group_assign_batch
+    e2e = None
+    if not args.no_e2e:
+        ne = min(args.e2e_reads, n) & ~3
+        lib = _lib.lib()
+        h_in, h_out = C.c_void_p(), C.c_void_p()
+        _lib.check(lib.fqtk_b200_host_alloc(C.byref(h_in), G * ne * L))
+        _lib.check(lib.fqtk_b200_host_alloc(C.byref(h_out), G * ne * 4))
+        h_in_np = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_uint8)), shape=(G * ne, L))
+        h_in_np[:] = host_reads(panel, cfg.seed_reads, 0, G * ne)
+        for _ in range(2):
+            group.assign_batch_ptr(h_in.value, G * ne, L, h_out.value)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            group.assign_batch_ptr(h_in.value, G * ne, L, h_out.value)
+        dt = (time.perf_counter() - t0) / args.steps
+        e2e = {"value": round(G * ne / dt / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": G * ne * L,
+               "d2h_bytes_per_step": G * ne * 4, "ms_per_step": round(dt * 1e3, 3),
+               "api": "fqtk_b200_group_assign_batch (one pinned host batch, contiguous shards, one host thread per device)"}
+        lib.fqtk_b200_host_free(h_in)
+        lib.fqtk_b200_host_free(h_out)
+    emit({"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
+          "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "u32", "data": "synthetic", "config": dict(config_dict(cfg, n, "table"), process_model="single process, "
+                                                              "fqtk_b200_group_* (one matcher per GPU, one count table)"),
+          "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(_lib.lib().fqtk_b200_kernel_launches()),
+          "count_reduce_ms": round(reduce_ms, 3), "parity_check": {"ranks": G, "ok": ok}})
+    group.close()
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -561,50 +766,7 @@ def run_b200(args):
     # ---- e2e: the reference-facing C-ABI call on HOST buffers (pinned), H2D + kernel + D2H every step ----
     e2e = None
     if not args.no_e2e:
-        import ctypes as C
-        import psutil
-
-        L = cfg.barcode_len
-        ne = min(args.e2e_reads, n)
-        avail = psutil.virtual_memory().available
-        while ne * (L + 4) * max(1, min(world, 8)) > 0.25 * avail and ne > (1 << 20):
-            ne //= 2
-        d_ascii = torch.empty((ne, L), dtype=torch.uint8, device=dev)
-        synth.reads_device(panel, cfg.seed_reads, head["first"], ne, d_ascii.data_ptr(), 0, stream)
-        h_in, h_out = C.c_void_p(), C.c_void_p()
-        _lib.check(_lib.lib().fqtk_b200_host_alloc(C.byref(h_in), ne * L))
-        _lib.check(_lib.lib().fqtk_b200_host_alloc(C.byref(h_out), ne * 4))
-        h_in_np = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_uint8)), shape=(ne, L))
-        h_out_np = np.ctypeslib.as_array(C.cast(h_out, C.POINTER(C.c_uint32)), shape=(ne,))
-        h_in_np[:] = d_ascii.cpu().numpy()
-        del d_ascii
-        matcher.reset_counts()
-        for _ in range(2):
-            matcher.assign_batch_ptr(h_in.value, ne, L, h_out.value)
-        matcher.reset_counts()
-        ctx.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            matcher.assign_batch_ptr(h_in.value, ne, L, h_out.value)  # synchronous: returns with results on the host
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        # the host results must be the device path's results for the same reads
-        matcher.reset_counts()
-        matcher.assign_packed_device(d_packed.data_ptr(), min(ne, 1 << 20), d_res.data_ptr(), stream)
-        torch.cuda.synchronize()
-        chk = min(ne, 1 << 20)
-        assert np.array_equal(d_res[:chk].cpu().numpy().view(np.uint32), h_out_np[:chk]), "e2e results differ"
-        e2e = {"value": round(ne * args.steps * world / dt / 1e6, 2), "unit": UNIT,
-               "h2d_bytes_per_step": ne * L * world, "d2h_bytes_per_step": ne * 4 * world,
-               "reads_per_gpu_per_step": ne, "ms_per_step": round(dt / args.steps * 1e3, 3),
-               "api": "fqtk_b200_matcher_assign_batch (ASCII rows in pinned host memory -> result words in pinned "
-                      "host memory; chunked H2D / kernel / D2H overlap inside the call)"}
-        _lib.lib().fqtk_b200_host_free(h_in)
-        _lib.lib().fqtk_b200_host_free(h_out)
+        e2e = measure_e2e(ctx, args, cfg, panel, matcher, d_packed, d_res, head["first"], n)
 
     matcher.close()
     del d_packed, d_res
@@ -683,6 +845,8 @@ def main():
     quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
+    elif args.single_process:
+        run_single_process(args)
     else:
         run_b200(args)
 

@@ -1,14 +1,8 @@
 set -u
-O=gpurun_out/r02k; mkdir -p $O
-timeout 900 python bench.py --steps 5 --warmup 3 > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"; tail -5 $O/bench.err
-python - <<PY
+O=gpurun_out/r02l; mkdir -p $O
+timeout 900 python bench.py --steps 5 --warmup 3 --no-configs --no-cpu-baseline --no-brute > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"; tail -5 $O/bench.err
+python -c "
 import json
-d=json.load(open("$O/bench.json"))
-print("value", d["value"], "roofline", d["roofline"]["frac"], d["roofline"]["kernel"], "e2e", d["e2e"]["value"] if d["e2e"] else None)
-print("parity", d["parity_check"])
-for k,v in (d["configs"] or {}).items():
-    print(k, v["value"], v["ms"], v["roofline"]["frac"], v["roofline"]["kernel"], v["parity_check"]["ok"] if v["parity_check"] else None, v.get("strong_scaling"))
-print("cpu", d["cpu_baseline"]["value"] if d["cpu_baseline"] else None, "numa", d["numa"])
-PY
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; echo "ref rc=$?"; cut -c1-400 $O/bench_ref.json
-grep -c fqtk_b200 /proc/self/maps > /dev/null
+d=json.load(open('$O/bench.json')); print(json.dumps(d['e2e'], indent=1))"
+timeout 600 python bench.py --single-process --gpus 1 --steps 5 --warmup 2 > $O/bench_sp.json 2> $O/bench_sp.err; echo "sp rc=$?"; tail -3 $O/bench_sp.err; cut -c1-1500 $O/bench_sp.json
+tools/h2d_ceiling 1 134217728 16 4; tools/h2d_ceiling 1 134217728 8 2
