@@ -95,6 +95,7 @@ struct fqtk_b200_matcher {
     uint4* d_planes = nullptr;
     uint4* d_planes2 = nullptr;
     uint32_t* d_not_exp = nullptr;
+    uint32_t* d_sliced = nullptr;
     uint32_t* d_table = nullptr;
     uint32_t* d_tier = nullptr;
     uint32_t* d_bloom = nullptr;
@@ -901,6 +902,19 @@ int fqtk_b200_matcher_create_ex(const uint8_t* panel_ascii, uint32_t S, uint32_t
     }
     CUB(cudaMalloc(&m->d_not_exp, not_exp.size() * 4));
     CUB(cudaMemcpy(m->d_not_exp, not_exp.data(), not_exp.size() * 4, cudaMemcpyHostToDevice));
+    if (W <= (uint32_t)fq::MAX_FAST_WORDS && S + 1u <= 8192u) {
+        // k_brute_sliced's transposed panel: word (g, i, v), bit j: barcode 32g + j mismatches a read symbol with mask v at i
+        const uint32_t G = (S + 31u) / 32u, LP = 8u * W;
+        std::vector<uint32_t> sliced((size_t)G * LP * 16u, 0u);
+        for (uint32_t j = 0; j < S; j++)
+            for (uint32_t i = 0; i < L; i++) {
+                const uint32_t forbid = ~fq::encode_byte(m->panel[(size_t)j * L + i]) & 0xFu;
+                for (uint32_t v = 0; v < 16u; v++)
+                    if (v & forbid) sliced[((size_t)(j >> 5) * LP + i) * 16u + v] |= 1u << (j & 31u);
+            }
+        CUB(cudaMalloc(&m->d_sliced, sliced.size() * 4));
+        CUB(cudaMemcpy(m->d_sliced, sliced.data(), sliced.size() * 4, cudaMemcpyHostToDevice));
+    }
     CUB(cudaMalloc(&m->d_counts, (size_t)(S + 1) * 8));
     CUB(cudaMemset(m->d_counts, 0, (size_t)(S + 1) * 8));
     for (int s = 0; s < N_PIPE; s++) CUB(cudaStreamCreateWithFlags(&m->streams[s], cudaStreamNonBlocking));
@@ -908,6 +922,7 @@ int fqtk_b200_matcher_create_ex(const uint8_t* panel_ascii, uint32_t S, uint32_t
     m->params.planes = m->d_planes;
     m->params.planes2 = m->d_planes2;
     m->params.not_exp = m->d_not_exp;
+    m->params.sliced = m->d_sliced;
     m->params.table = nullptr;
     m->params.counts = m->d_counts;
     m->params.S = S;
@@ -966,6 +981,7 @@ void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m) {
     if (m->d_planes) cudaFree(m->d_planes);
     if (m->d_planes2) cudaFree(m->d_planes2);
     if (m->d_not_exp) cudaFree(m->d_not_exp);
+    if (m->d_sliced) cudaFree(m->d_sliced);
     if (m->d_table) cudaFree(m->d_table);
     if (m->d_tier) cudaFree(m->d_tier);
     if (m->d_bloom) cudaFree(m->d_bloom);

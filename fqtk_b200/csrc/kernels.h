@@ -11,7 +11,10 @@ struct MatchParams {
                                //  32*p + i of the barcode does NOT admit A/C/G/T
     const uint4* planes2;      // L <= 16 only: [ceil(S/2)] the planes of barcodes 2q (low 16 bits) and 2q+1 (high 16 bits)
                                //  packed into one word each; planes[] itself is padded to an even number of entries
-    const uint32_t* not_exp;   // [S * W] ~expected nibble words (only read by the L > 32 kernel)
+    const uint32_t* not_exp;   // [S * W] ~expected nibble words (the L > 32 kernel; k_probe4's verification)
+    const uint32_t* sliced;    // k_brute_sliced (L <= 32): [G][8W][16] words, G = ceil(S/32) groups of 32 barcodes: bit j of
+                               //   word (g, i, v) is set iff barcode 32g + j mismatches a read symbol with 4-bit mask v at
+                               //   position i (positions >= L: 0); nullptr = not built
     const uint32_t* table;     // memo table slots in global memory (nullptr in brute mode)
     const uint32_t* tier_entries;  // hot tier (table entries whose best distance is 0), staged into shared memory by
                                    //   k_probe2: 2-choice cuckoo, tier_slots entries of tier_entry_words(W) words

@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "sliced_adders.cuh"
 
 namespace fq {
 
@@ -94,6 +95,63 @@ FQ_D void init_lut(uint8_t* lut) {
     for (uint32_t t = threadIdx.x; t < 256u; t += blockDim.x) lut[t] = (uint8_t)encode_byte(t);
 }
 
+// shared-memory access by 32-bit window address (keeps address arithmetic to one IMAD / IADD per access)
+FQ_D uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+FQ_D uint4 lds128_ro(uint32_t a) {  // read-only data (tier): may be scheduled freely
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+FQ_D uint2 lds64_ro(uint32_t a) {
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+FQ_D uint32_t lds32_ro(uint32_t a) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+FQ_D uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+FQ_D void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+template <int W>
+FQ_D void sts_key(uint32_t a, const uint32_t (&w)[W]) {
+    if constexpr (W == 1) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(w[0]) : "memory");
+    } else if constexpr (W == 2) {
+        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(w[0]), "r"(w[1]) : "memory");
+    } else if constexpr (W == 3) {
+        asm volatile("st.shared.u32 [%0], %1;\n\tst.shared.u32 [%0+4], %2;\n\tst.shared.u32 [%0+8], %3;" ::"r"(a), "r"(w[0]),
+                     "r"(w[W > 1 ? 1 : 0]), "r"(w[W > 2 ? 2 : 0])
+                     : "memory");
+    } else {
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(w[0]), "r"(w[W > 1 ? 1 : 0]),
+                     "r"(w[W > 2 ? 2 : 0]), "r"(w[W > 3 ? 3 : 0])
+                     : "memory");
+    }
+}
+template <int W>
+FQ_D void lds_key(uint32_t a, uint32_t (&w)[W]) {
+    if constexpr (W == 1) {
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[0]) : "r"(a) : "memory");
+    } else if constexpr (W == 2) {
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(a) : "memory");
+    } else if constexpr (W == 3) {
+        asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];"
+                     : "=r"(w[0]), "=r"(w[W > 1 ? 1 : 0]), "=r"(w[W > 2 ? 2 : 0])
+                     : "r"(a)
+                     : "memory");
+    } else {
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(w[0]), "=r"(w[W > 1 ? 1 : 0]), "=r"(w[W > 2 ? 2 : 0]), "=r"(w[W > 3 ? 3 : 0])
+                     : "r"(a)
+                     : "memory");
+    }
+}
 // ------------------------------------------------------------------------------------------------------
 // counting
 // ------------------------------------------------------------------------------------------------------
@@ -275,6 +333,159 @@ __global__ void __launch_bounds__(BRUTE_THREADS) k_brute(const MatchParams p, co
         }
         results[i] = res;
         cnt.add(res);
+    }
+    cnt.flush();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_brute_sliced: every read x every barcode, BIT-SLICED ACROSS BARCODES (SURVEY 7 option iii).  Thread per read; the panel
+// is transposed into groups of 32 barcodes: word (g, i, v) has bit j set iff barcode 32g + j mismatches a read symbol with
+// 4-bit mask v at position i (bitenc.rs:441-452, for ALL 16 masks: IUPAC codes, no-calls and junk bytes in reads are exact
+// by construction).  For one group a thread fetches the 8W words its own symbols select (conflict-free: the lanes of a
+// warp differ only in v, 16 consecutive words), adds them with a carry-save adder tree into vertical counters (bit p of
+// 32 distances at once: ~2 logic ops per position instead of ~8 instructions per barcode), and compares the counters
+// bit-sliced with its running second-best distance; only barcodes that beat it (rare after the first group) are extracted
+// one by one into the running (distance << 16 | index) min / second-min pair — the same keys as k_brute, so ties go to the
+// first index (barcode_matching.rs:132) and the second smallest counts multiplicity (:140).
+// Shared memory holds a chunk of groups; a panel larger than a chunk is walked chunk by chunk for every batch of reads.
+// ------------------------------------------------------------------------------------------------------
+constexpr int SLICED_THREADS = 512;
+constexpr uint32_t SLICED_CHUNK_BYTES = 96u << 10;  // table bytes staged at a time
+
+template <int W>
+struct Sliced {
+    static constexpr int LP = 8 * W;                         // positions, padded to whole packed words
+    static constexpr int NB = SlicedAdder<LP>::PLANES;       // counter planes: distances 0 .. LP
+    static constexpr uint32_t GROUP_BYTES = LP * 16 * 4;     // one group of 32 barcodes
+};
+
+// counters of one group for this thread's read: `a` = shared-window address of the group + the read's symbol offsets
+template <int W>
+FQ_D void sliced_counters(const uint32_t (&off)[8 * W], uint32_t group_addr, uint32_t (&c)[Sliced<W>::NB]) {
+    constexpr int LP = Sliced<W>::LP;
+    uint32_t x[LP];
+#pragma unroll
+    for (int i = 0; i < LP; i++) x[i] = lds32_ro(group_addr + off[i] + (uint32_t)i * 64u);
+    SlicedAdder<LP>::add(x, c);
+}
+
+// distance of barcode `j` of the group from the vertical counters
+template <int NB>
+FQ_D uint32_t sliced_extract(const uint32_t (&c)[NB], uint32_t j) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int pl = 0; pl < NB; pl++) d |= ((c[pl] >> j) & 1u) << pl;
+    return d;
+}
+
+template <int W, bool ASCII>
+__global__ void __launch_bounds__(SLICED_THREADS) k_brute_sliced(const MatchParams p, const ReadSource src,
+                                                                 uint32_t* __restrict__ results, uint32_t chunk_groups) {
+    constexpr int LP = Sliced<W>::LP, NB = Sliced<W>::NB;
+    constexpr uint32_t GB = Sliced<W>::GROUP_BYTES;
+    extern __shared__ uint4 s_dyn[];
+    __shared__ uint8_t s_lut[256];
+    uint32_t* s_tab = reinterpret_cast<uint32_t*>(s_dyn);
+    uint32_t* s_hist = s_tab + (size_t)chunk_groups * (GB / 4);
+    const uint32_t G = (p.S + 31u) / 32u;
+    const uint32_t n_chunks = (G + chunk_groups - 1u) / chunk_groups;
+    if constexpr (ASCII) init_lut(s_lut);
+    Counter cnt;
+    cnt.init(s_hist, p);
+    auto stage = [&](uint32_t chunk) {  // groups [chunk * chunk_groups, ...) -> shared memory (all threads)
+        const uint32_t g0 = chunk * chunk_groups, ng = min(chunk_groups, G - g0);
+        const uint4* src4 = reinterpret_cast<const uint4*>(p.sliced + (size_t)g0 * (GB / 4));
+        uint4* dst4 = reinterpret_cast<uint4*>(s_tab);
+        for (uint32_t t = threadIdx.x; t < ng * (GB / 16); t += blockDim.x) dst4[t] = __ldg(src4 + t);
+    };
+    if (n_chunks == 1u) stage(0);
+    __syncthreads();
+    const uint32_t a_tab = smem_addr(s_tab);
+    const uint64_t batch = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_batches = (src.n + batch - 1) / batch;  // every thread of the CTA runs every batch (barriers inside)
+    for (uint64_t bi = 0; bi < n_batches; bi++) {
+        const uint64_t i = bi * batch + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const bool live = i < src.n;
+        uint32_t w[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) w[k] = 0u;
+        bool row_ok = true;
+        if (live) {
+            if constexpr (ASCII)
+                row_ok = load_ascii<W>(src, i, p.L, s_lut, w);
+            else
+                load_packed<W>(src.packed, i, w);
+        }
+        uint32_t off[LP];  // byte offset of the read's symbol inside a position's 16 words
+#pragma unroll
+        for (int k = 0; k < LP; k++) {
+            const int sh = 4 * (k & 7) - 2;
+            off[k] = (sh >= 0 ? (w[k >> 3] >> sh) : (w[k >> 3] << 2)) & 0x3Cu;
+        }
+        uint32_t k1 = EMPTY_KEY, k2 = EMPTY_KEY;  // running best / second best (distance << 16 | index)
+        uint32_t thr[NB];                          // bit planes of the threshold T = second-best distance (all ones: none yet)
+#pragma unroll
+        for (int pl = 0; pl < NB; pl++) thr[pl] = 0xFFFFFFFFu;
+        bool have2 = false;  // two barcodes seen: T is meaningful
+        for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
+            if (n_chunks > 1u) {
+                __syncthreads();
+                stage(chunk);
+                __syncthreads();
+            }
+            const uint32_t g0 = chunk * chunk_groups, ng = min(chunk_groups, G - g0);
+            for (uint32_t gl = 0; gl < ng; gl++) {
+                const uint32_t g = g0 + gl;
+                uint32_t c[NB];
+                sliced_counters<W>(off, a_tab + gl * GB, c);
+                const uint32_t vm = (g + 1u == G && (p.S & 31u)) ? ((1u << (p.S & 31u)) - 1u) : 0xFFFFFFFFu;  // real barcodes
+                if (!have2) {
+                    // fewer than two barcodes seen so far (the first group): smallest and second smallest of the group
+                    // found bit-sliced — from the top plane down, keep the candidates that have a 0 where any has one
+                    uint32_t pool = vm;
+#pragma unroll
+                    for (int which = 0; which < 2; which++) {
+                        if (pool) {
+                            uint32_t cand = pool, d = 0u;
+#pragma unroll
+                            for (int pl = NB - 1; pl >= 0; pl--) {
+                                const uint32_t t = cand & ~c[pl];
+                                d |= t ? 0u : (1u << pl);
+                                cand = t ? t : cand;
+                            }
+                            const uint32_t j = (uint32_t)__ffs(cand) - 1u;  // first index among equals (barcode_matching.rs:132)
+                            track2(k1, k2, (d << 16) | (g * 32u + j));
+                            pool &= ~(1u << j);
+                        }
+                    }
+                } else {
+                    // bit-sliced d < T over the 32 barcodes; a barcode closer than the second best so far is rare
+                    uint32_t lt = 0u, eq = vm;
+#pragma unroll
+                    for (int pl = NB - 1; pl >= 0; pl--) {
+                        lt |= eq & ~c[pl] & thr[pl];
+                        eq &= ~(c[pl] ^ thr[pl]);
+                    }
+                    if (lt == 0u) continue;
+                    do {
+                        const uint32_t j = (uint32_t)__ffs(lt) - 1u;
+                        lt &= lt - 1u;
+                        track2(k1, k2, (sliced_extract<NB>(c, j) << 16) | (g * 32u + j));
+                    } while (lt);
+                }
+                if (k2 != EMPTY_KEY) {  // (re)build the threshold planes from the second-best distance
+                    have2 = true;
+                    const uint32_t T = k2 >> 16;
+#pragma unroll
+                    for (int pl = 0; pl < NB; pl++) thr[pl] = 0u - ((T >> pl) & 1u);
+                }
+            }
+        }
+        if (live) {
+            const uint32_t res = row_ok ? decide(k1, k2, p.max_mm, p.min_delta) : NONE;
+            results[i] = res;
+            cnt.add(res);
+        }
     }
     cnt.flush();
 }
@@ -497,63 +708,6 @@ constexpr int PROBE2_TILE = 32 * PROBE2_R;   // reads per warp tile
 constexpr int PROBE2_QUEUE = PROBE2_TILE;    // queue entries per warp: every read of a tile may be unresolved
 constexpr uint32_t PROBE2_HIST_BYTES = 25u << 10;  // shared memory the replicated histogram may take
 
-// shared-memory access by 32-bit window address (keeps address arithmetic to one IMAD / IADD per access)
-FQ_D uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-FQ_D uint4 lds128_ro(uint32_t a) {  // read-only data (tier): may be scheduled freely
-    uint4 v;
-    asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-}
-FQ_D uint2 lds64_ro(uint32_t a) {
-    uint2 v;
-    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
-    return v;
-}
-FQ_D uint32_t lds32_ro(uint32_t a) {
-    uint32_t v;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-FQ_D uint32_t lds32(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-FQ_D void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-template <int W>
-FQ_D void sts_key(uint32_t a, const uint32_t (&w)[W]) {
-    if constexpr (W == 1) {
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(w[0]) : "memory");
-    } else if constexpr (W == 2) {
-        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(w[0]), "r"(w[1]) : "memory");
-    } else if constexpr (W == 3) {
-        asm volatile("st.shared.u32 [%0], %1;\n\tst.shared.u32 [%0+4], %2;\n\tst.shared.u32 [%0+8], %3;" ::"r"(a), "r"(w[0]),
-                     "r"(w[W > 1 ? 1 : 0]), "r"(w[W > 2 ? 2 : 0])
-                     : "memory");
-    } else {
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(w[0]), "r"(w[W > 1 ? 1 : 0]),
-                     "r"(w[W > 2 ? 2 : 0]), "r"(w[W > 3 ? 3 : 0])
-                     : "memory");
-    }
-}
-template <int W>
-FQ_D void lds_key(uint32_t a, uint32_t (&w)[W]) {
-    if constexpr (W == 1) {
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[0]) : "r"(a) : "memory");
-    } else if constexpr (W == 2) {
-        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(a) : "memory");
-    } else if constexpr (W == 3) {
-        asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];"
-                     : "=r"(w[0]), "=r"(w[W > 1 ? 1 : 0]), "=r"(w[W > 2 ? 2 : 0])
-                     : "r"(a)
-                     : "memory");
-    } else {
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(w[0]), "=r"(w[W > 1 ? 1 : 0]), "=r"(w[W > 2 ? 2 : 0]), "=r"(w[W > 3 ? 3 : 0])
-                     : "r"(a)
-                     : "memory");
-    }
-}
 // histogram: hist[(result >> 16) * hrep + lane % hrep] += 1 unless the result is NONE (predicated, no branch).
 // `hist_lane_addr` already includes the lane's replica offset; `hshift` = log2(hrep * 4 bytes).
 FQ_D void red_hist(uint32_t hist_lane_addr, uint32_t hshift, uint32_t result) {
@@ -1598,10 +1752,41 @@ static cudaError_t launch_brute_long_w(const MatchParams& p, const ReadSource& s
     return cudaGetLastError();
 }
 
+template <int W, bool ASCII>
+static cudaError_t launch_brute_sliced(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
+                                       const LaunchGeometry& g, cudaStream_t stream) {
+    const uint32_t G = (p.S + 31u) / 32u;
+    const size_t hb = hist_bytes(p);
+    const uint32_t chunk_groups = std::max<uint32_t>(1u, std::min<uint32_t>(G, SLICED_CHUNK_BYTES / Sliced<W>::GROUP_BYTES));
+    const size_t smem = (size_t)chunk_groups * Sliced<W>::GROUP_BYTES + hb;
+    auto k = k_brute_sliced<W, ASCII>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = grid_for(k, SLICED_THREADS, smem, g, src.n);
+    k<<<grid, SLICED_THREADS, smem, stream>>>(p, src, d_results, chunk_groups);
+    count_launch();
+    return cudaGetLastError();
+}
+
+static bool brute_v1() {  // FQTK_B200_BRUTE_V1=1 (A/B timing): the barcode-pair kernel of round 1 instead of the bit-sliced one
+    static const bool v = [] {
+        const char* e = getenv("FQTK_B200_BRUTE_V1");
+        return e && atoi(e) != 0;
+    }();
+    return v;
+}
+
 cudaError_t launch_brute(const MatchParams& p, const ReadSource& src, uint32_t* d_results, const LaunchGeometry& g,
                          cudaStream_t stream) {
     if (src.n == 0) return cudaSuccess;
     const bool ascii = src.ascii != nullptr;
+    if (p.sliced != nullptr && p.W <= (uint32_t)MAX_FAST_WORDS && !brute_v1()) {
+        switch (p.W) {
+            case 1: return ascii ? launch_brute_sliced<1, true>(p, src, d_results, g, stream) : launch_brute_sliced<1, false>(p, src, d_results, g, stream);
+            case 2: return ascii ? launch_brute_sliced<2, true>(p, src, d_results, g, stream) : launch_brute_sliced<2, false>(p, src, d_results, g, stream);
+            case 3: return ascii ? launch_brute_sliced<3, true>(p, src, d_results, g, stream) : launch_brute_sliced<3, false>(p, src, d_results, g, stream);
+            default: return ascii ? launch_brute_sliced<4, true>(p, src, d_results, g, stream) : launch_brute_sliced<4, false>(p, src, d_results, g, stream);
+        }
+    }
     if (p.W > (uint32_t)MAX_FAST_WORDS) {
         if (ascii) return cudaErrorInvalidValue;  // caller packs first
         return p.W <= 8u ? launch_brute_long_w<8>(p, src, d_results, g, stream)

@@ -1,8 +1,6 @@
 set -u
-O=gpurun_out/r02l; mkdir -p $O
-timeout 900 python bench.py --steps 5 --warmup 3 --no-configs --no-cpu-baseline --no-brute > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"; tail -5 $O/bench.err
-python -c "
-import json
-d=json.load(open('$O/bench.json')); print(json.dumps(d['e2e'], indent=1))"
-timeout 600 python bench.py --single-process --gpus 1 --steps 5 --warmup 2 > $O/bench_sp.json 2> $O/bench_sp.err; echo "sp rc=$?"; tail -3 $O/bench_sp.err; cut -c1-1500 $O/bench_sp.json
-tools/h2d_ceiling 1 134217728 16 4; tools/h2d_ceiling 1 134217728 8 2
+python -m pytest tests -m gpu -x -q -k "kats or fuzz or configs_reduced_n or long_barcodes or many_samples or length_rules or single_sample or extreme" 2>&1 | tail -5
+for c in 3 4 5 2; do
+python bench.py --config $c --mode brute --reads 67108864 --steps 3 --warmup 1 --no-cpu-baseline --no-e2e --no-brute --no-configs --no-parity-check 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('cfg$c sliced', d['roofline']['kernel'], d['roofline']['kernel_ms'], d['roofline']['pair_compares_per_s'])"
+FQTK_B200_BRUTE_V1=1 python bench.py --config $c --mode brute --reads 67108864 --steps 3 --warmup 1 --no-cpu-baseline --no-e2e --no-brute --no-configs --no-parity-check 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('cfg$c v1    ', d['roofline']['kernel'], d['roofline']['kernel_ms'], d['roofline']['pair_compares_per_s'])"
+done
