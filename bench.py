@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=0, help="override reads per GPU per step (default: the config's N)")
     ap.add_argument("--e2e-reads", type=int, default=128 << 20, help="reads per GPU per e2e step (pinned host memory)")
     ap.add_argument("--mode", choices=["auto", "table", "brute"], default="auto")
-    ap.add_argument("--cuckoo", type=int, default=-1, choices=[-1, 0, 1, 2, 3],
+    ap.add_argument("--cuckoo", type=int, default=-1, choices=[-1, 0, 1, 2, 3, 5],
                     help="packed-route kernel knob (fqtk_b200_set_cuckoo_arity): -1 auto, 0 k_probe2, 1 k_probe4, "
                          "2/3 k_probe3 with that many sub-tables; A/B timing")
     ap.add_argument("--no-e2e", action="store_true")
@@ -295,6 +295,8 @@ def pin_to_gpu_numa_node(local):
 def kernel_name(info, mode, W):
     if mode != "table":
         return "k_brute"
+    if int(info.cuckoo_probes) and W <= 2 and int(info.l2_table_entries):
+        return f"k_probe5<W={W},NP={int(info.cuckoo_probes)}>"
     if int(info.cuckoo_probes) and W <= 2:
         return f"k_probe3<W={W},NP={int(info.cuckoo_probes)}>"
     if int(info.l2_table_entries):

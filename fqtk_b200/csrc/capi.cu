@@ -276,13 +276,15 @@ void build_tier(const std::vector<uint32_t>& keys, const std::vector<uint32_t>& 
 
 template <int W>
 int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, const std::vector<uint32_t>& res,
-                   uint64_t n) {
+                   uint64_t n, bool exact_only) {
+    // exact_only (k_probe5): only the entries with best distance 0; the rest of the neighbourhood is in the fingerprint table
     const uint32_t S = m->S, pad = m->params.last_pad;
     if (S + 1u > 8192u) return 1;
     // pure-A/C/G/T entries, de-duplicated (the same string is enumerated once per barcode it is close to)
     std::vector<std::pair<uint32_t, uint32_t>> ent;  // (compressed key, result word)
     for (uint64_t t = 0; t < n; t++) {
         if (res[t] == fq::NONE) continue;
+        if (exact_only && ((res[t] >> 8) & 0xFFu) != 0u) continue;
         uint32_t kw[W];
         for (int k = 0; k < W; k++) kw[k] = keys[t * W + k];
         bool valid;
@@ -320,6 +322,7 @@ int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, cons
     std::vector<Geo> options;
     const int force = m->opt.kernel;
     if (force == 0 || force == 1) return 1;  // 0: k_probe2 only, 1: k_probe4's table only
+    if (exact_only != (force == 5) && force != -1) return 1;  // 5: k_probe5 (exact-only table); 2 / 3: k_probe3 (full table)
     for (uint32_t s = std::max(cb, 4u); s <= 16; s++) {
         if (force != 3) {
             options.push_back({2, {s, s, 0}});
@@ -336,7 +339,8 @@ int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, cons
         const uint64_t slots = slots_of(g);
         const double max_load = g.np == 2 ? 0.40 : 0.80;
         if ((double)ent.size() > max_load * (double)slots) continue;
-        if (fq::probe3_smem_bytes((uint32_t)slots, S, 16) > smem_max) continue;  // table + histogram + minimal stashes
+        if ((exact_only ? fq::probe5_smem_bytes((uint32_t)slots, S, W, 1) : fq::probe3_smem_bytes((uint32_t)slots, S, 16)) > smem_max)
+            continue;  // table + histogram + minimal stashes (k_probe5: + ~expected words + warp queues)
         uint32_t off[3] = {0, 0, 0};
         for (uint32_t i = 1; i < g.np; i++) off[i] = off[i - 1] + (1u << g.sb[i - 1]);
         std::vector<uint32_t> slot_key(slots, 0u), slot_code(slots, 0xFFFFFFFFu);  // code 0xFFFFFFFF = empty
@@ -408,6 +412,7 @@ int build_cuckoo_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, cons
         uint32_t cap = 16;
         while (cap < 64 && fq::probe3_smem_bytes((uint32_t)slots, S, cap + 1) <= smem_max) cap++;
         p.ck_stash_cap = cap;
+        p.ck_exact_only = exact_only ? 1u : 0u;
         m->cuckoo_entries = ent.size();
         return 0;
     }
@@ -485,11 +490,16 @@ int build_g4_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, const st
     uint32_t rep = 16;
     while (rep > 1 && fq::probe4_smem_bytes(W, S, rep, 32) > smem_max) rep >>= 1;
     if (fq::probe4_smem_bytes(W, S, rep, 32) > smem_max) return 1;
+    if (m->params.ck_exact_only)  // k_probe5 shares the replica count: it must also fit next to its cuckoo table
+        while (rep > 1 && fq::probe5_smem_bytes(m->params.ck_words, S, W, rep) > smem_max) rep >>= 1;
     uint32_t cap = 32;
     while (cap < 64 && fq::probe4_smem_bytes(W, S, rep, cap + 1) <= smem_max) cap++;
     // load factor: measured on B200 (profiles/README.md); options.l2_table_load_pct overrides (A/B timing)
-    // cfg 5 (29.6 MB at 0.5): 12.2 ms at 0.4, 10.75 at 0.5, 10.66 at 0.6 — fewer overflow walks vs a smaller table
-    const double load = m->opt.l2_table_load_pct ? m->opt.l2_table_load_pct / 100.0 : 0.55;
+    // Measured on B200 (1 B reads): cfg 5 (k_probe4) 12.2 ms at 0.4, 10.75 at 0.5, 10.66 at 0.6, 11.4 at 0.75, 16.3 at 0.85;
+    // cfg 4 (k_probe5) 6.19 ms at 0.3, 5.55 at 0.4, 4.73 at 0.55, 4.66 at 0.65, 5.18 at 0.75, 8.46 at 0.85 — a smaller table
+    // stays L2-resident against the stream (the ~half of the probes that find nothing land on uniformly random buckets),
+    // a fuller one walks overflow chains
+    const double load = m->opt.l2_table_load_pct ? m->opt.l2_table_load_pct / 100.0 : 0.6;
     const uint64_t buckets64 = std::max<uint64_t>(16, (uint64_t)((double)ent.size() / (8 * load)) + 1);
     if (buckets64 >= (1ull << 28)) return 1;
     const uint32_t n_buckets = (uint32_t)buckets64;
@@ -535,6 +545,24 @@ int build_g4_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, const st
         }
     }
     if (!built) return 1;
+    if (getenv("FQTK_B200_DEBUG")) {
+        uint64_t full = 0, used = 0;
+        for (uint32_t b = 0; b < n_buckets; b++) {
+            full += table[(size_t)b * 8 + 7] != 0xFFFFFFFFu;
+            for (int j = 0; j < 8; j++) used += table[(size_t)b * 8 + j] != 0xFFFFFFFFu;
+        }
+        // walk length of an unsuccessful search from every bucket
+        uint64_t walks = 0, longest = 0;
+        for (uint32_t b = 0; b < n_buckets; b++) {
+            uint32_t c = b, len = 0;
+            while (table[(size_t)c * 8 + 7] != 0xFFFFFFFFu && len < 1000) { c = (c + 1u == n_buckets) ? 0u : c + 1u; len++; }
+            walks += len;
+            longest = std::max<uint64_t>(longest, len);
+        }
+        std::fprintf(stderr, "[fqtk_b200] fingerprint table: %zu keys, %u buckets, load %.3f, full buckets %.2f %%, mean miss walk %.3f, longest %llu, slow keys %llu, seed %u\n",
+                     ent.size(), n_buckets, (double)used / (8.0 * n_buckets), 100.0 * full / n_buckets, (double)walks / n_buckets,
+                     (unsigned long long)longest, (unsigned long long)slow_keys, seed);
+    }
     CU(cudaMalloc(&m->d_g4, table.size() * 4));
     CU(cudaMemcpy(m->d_g4, table.data(), table.size() * 4, cudaMemcpyHostToDevice));
     fq::MatchParams& p = m->params;
@@ -684,17 +712,32 @@ int build_table(fqtk_b200_matcher* m) {
         }
     }
     // k_probe3's shared-memory cuckoo table of the pure-A/C/G/T entries (L <= 16)
-    if (W <= 2) {
-        const int rc = (W == 1) ? build_cuckoo_w<1>(m, keys, res, n) : build_cuckoo_w<2>(m, keys, res, n);
+    if (W <= 2 && m->opt.kernel != 5) {
+        const int rc = (W == 1) ? build_cuckoo_w<1>(m, keys, res, n, false) : build_cuckoo_w<2>(m, keys, res, n, false);
         if (rc < 0) return rc;
+    }
+    // else, for one- and two-word panels, k_probe5: only the EXACT entries in shared memory + the fingerprint table below
+    bool probe5 = false;
+    if (m->params.ck_np == 0 && W <= 2 && (m->opt.kernel == -1 || m->opt.kernel == 5)) {
+        const int rc = (W == 1) ? build_cuckoo_w<1>(m, keys, res, n, true) : build_cuckoo_w<2>(m, keys, res, n, true);
+        if (rc < 0) return rc;
+        probe5 = m->params.ck_np != 0;
     }
     // else k_probe4's L2-resident fingerprint table of every candidate.  Measured on B200: it wins where k_probe2 has no
     // useful hot tier (cfg 5, W = 3: 27 -> 10.7 ms per 1 B reads); with a hot tier that ends 80 % of the reads in shared
     // memory (cfg 4, W = 2) k_probe2 is still ahead (5.2 vs 5.7 ms), so one- and two-word panels only take it on request
-    if (m->params.ck_np == 0 && m->opt.kernel != 0 && (W >= 3 || m->opt.kernel == 1)) {
+    if ((m->params.ck_np == 0 || probe5) && m->opt.kernel != 0 && (W >= 3 || m->opt.kernel == 1 || probe5)) {
         const int rc = (W == 1) ? build_g4_w<1>(m, keys, res, owners, n) : (W == 2) ? build_g4_w<2>(m, keys, res, owners, n)
                      : (W == 3) ? build_g4_w<3>(m, keys, res, owners, n) : build_g4_w<4>(m, keys, res, owners, n);
         if (rc < 0) return rc;
+        if (probe5 && m->params.g4_table == nullptr) {  // no fingerprint table after all: k_probe5 cannot run
+            cudaFree(m->d_cuckoo);
+            m->d_cuckoo = nullptr;
+            m->params.ck_entries = nullptr;
+            m->params.ck_np = 0;
+            m->params.ck_exact_only = 0;
+            m->cuckoo_entries = 0;
+        }
     }
     return 0;
 }
@@ -781,7 +824,9 @@ int fqtk_b200_device_count(void) {
 
 void fqtk_b200_set_table_budget(uint64_t max_candidates) { t_defaults.table_budget = max_candidates; }
 
-void fqtk_b200_set_cuckoo_arity(int arity) { t_defaults.kernel = (arity >= 0 && arity <= 3) ? arity : FQTK_B200_KERNEL_AUTO; }
+void fqtk_b200_set_cuckoo_arity(int arity) {
+    t_defaults.kernel = ((arity >= 0 && arity <= 3) || arity == 5) ? arity : FQTK_B200_KERNEL_AUTO;
+}
 
 void fqtk_b200_options_init(fqtk_b200_options* opts) {
     if (opts) *opts = env_defaults();
@@ -804,7 +849,7 @@ int fqtk_b200_matcher_create_ex(const uint8_t* panel_ascii, uint32_t S, uint32_t
             return fail(FQTK_B200_ERR_ARG, "options.struct_size: call fqtk_b200_options_init first");
         std::memcpy(&opt, opts, opts->struct_size);  // fields an older caller does not know keep their defaults
         opt.struct_size = (uint32_t)sizeof(fqtk_b200_options);
-        if (opt.kernel < -1 || opt.kernel > 3) return fail(FQTK_B200_ERR_ARG, "options.kernel out of range");
+        if (opt.kernel < -1 || opt.kernel > 5 || opt.kernel == 4) return fail(FQTK_B200_ERR_ARG, "options.kernel out of range");
         if (opt.table_budget == 0) opt.table_budget = 32ull << 20;
         if (opt.chunk_bytes == 0) opt.chunk_bytes = 32ull << 20;
         if (opt.l2_table_load_pct && (opt.l2_table_load_pct < 5 || opt.l2_table_load_pct > 90))
@@ -947,6 +992,7 @@ int fqtk_b200_matcher_create_ex(const uint8_t* panel_ascii, uint32_t S, uint32_t
     m->params.ck_one = 1;
     m->params.ck_four = 4;
     m->params.ck_stash_cap = 32;
+    m->params.ck_exact_only = 0;
     m->params.g4_table = nullptr;
     m->params.g4_buckets = 0;
     m->params.g4_hist_rep = 1;

@@ -46,6 +46,8 @@ struct MatchParams {
     uint32_t ck_nmask;           // code & ck_nmask = next - ck_next_min
     uint32_t ck_next_min;
     uint32_t ck_stash_cap;       // stash entries per warp of k_probe3 (16 .. 64)
+    uint32_t ck_exact_only;      // 1: the cuckoo table holds only the best-distance-0 entries (k_probe5: the rest of the
+                                 //    neighbourhood is in the fingerprint table below)
     // k_probe4 (L <= 32): FINGERPRINT table in global memory of every candidate string (every A/C/G/T/N string within
     // max_mm of some barcode, whether its result is Some or None), keyed by the read's packed words: 4-byte entries
     //     fingerprint << (ib + cb) | sample index << cb | value code,
@@ -138,6 +140,7 @@ cudaError_t prepare_kernels(const LaunchGeometry& g);  // opt-in shared memory a
 
 size_t probe3_smem_bytes(uint32_t ck_words, uint32_t S, uint32_t stash_cap);
 size_t probe4_smem_bytes(uint32_t W, uint32_t S, uint32_t hist_rep, uint32_t stash_cap);
+size_t probe5_smem_bytes(uint32_t ck_words, uint32_t S, uint32_t W, uint32_t hist_rep);
 inline __host__ __device__ uint32_t probe4_ne_stride(uint32_t W) { return W == 3u ? 4u : W; }  // words per barcode in shared memory
 size_t probe2_fixed_smem_bytes(uint32_t W, uint32_t S, int threads);  // k_probe2 shared memory besides tier + Bloom
 int probe2_threads();

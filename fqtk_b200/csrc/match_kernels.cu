@@ -1636,6 +1636,187 @@ __global__ void __launch_bounds__(THREADS, 1) k_probe4(const __grid_constant__ M
 }
 
 // ------------------------------------------------------------------------------------------------------
+// k_probe5: the HBM-resident packed route for L <= 16 panels whose full neighbourhood does not fit in shared memory but
+// whose EXACT entries do (cfg 4: 1 536 samples at 2 mismatches — 1.7 M pure-A/C/G/T entries, 1 536 of them exact).
+// k_probe3's front end on a shared-memory cuckoo table that holds only the best-distance-0 entries (two LDS.32 per read, the
+// ~80 % of a real stream that is an exact barcode ends there), and for the rest of the tile — pure reads that are not
+// exact, no-call reads, anything else — k_probe2's trick: compact them into a per-warp queue and send them, ~26 busy
+// lanes at a time, through k_probe4's L2-resident fingerprint table (ONE 256-bit load per read, verified against the
+// barcode's ~expected words in shared memory; exactness argument in kernels.h).  What the fingerprint table cannot
+// answer exactly (symbols outside A/C/G/T/N, fingerprint collisions) goes through the memo table / warp-cooperative scan
+// right there.  Counts: k_probe3's lane-private packed histogram, one atomic per read once its result is known.
+// ------------------------------------------------------------------------------------------------------
+constexpr int PROBE5_THREADS = 1024;
+constexpr int PROBE5_R = 4;
+
+// the exact slow path as a real call (keeps its code out of the queue loop); the extra template parameters only make the
+// copy private to one kernel (ptxas 12.9 crashes on shared noinline copies)
+template <int W, int NP, bool PAD>
+__device__ __noinline__ uint32_t probe5_slow(const MatchParams& p, uint32_t k0, uint32_t k1, bool act, uint32_t lane) {
+    uint32_t kw[W];
+    kw[0] = k0;
+    if constexpr (W == 2) kw[W - 1] = k1;
+    return slow_resolve<W>(p, kw, act, lane);
+}
+
+template <int W, int NP, bool PAD>
+__global__ void __launch_bounds__(PROBE5_THREADS, 1) k_probe5(const __grid_constant__ MatchParams p, const ReadSource src,
+                                                             uint32_t* __restrict__ results) {
+    constexpr int R = PROBE5_R;
+    constexpr uint32_t TILE = 32u * R;
+    extern __shared__ uint4 s_dyn[];
+    // layout: cuckoo entries (exact keys) | histogram replicas (32-bit counters: a CTA sees < 2^32 reads) | ~expected words
+    //         | warp queues
+    uint32_t* s_ck = reinterpret_cast<uint32_t*>(s_dyn);
+    uint32_t* s_hist = s_ck + p.ck_words;
+    const uint32_t hrep = p.g4_hist_rep;
+    const uint32_t n_hist_words = (p.S + 1u) * hrep;
+    uint32_t* s_ne = s_hist + n_hist_words;
+    uint32_t* s_queue = s_ne + (size_t)p.S * W;
+    {
+        const uint4* g4 = reinterpret_cast<const uint4*>(p.ck_entries);  // ck_words is a multiple of 4
+        uint4* s4 = reinterpret_cast<uint4*>(s_ck);
+        for (uint32_t t = threadIdx.x; t < p.ck_words / 4u; t += blockDim.x) s4[t] = __ldg(g4 + t);
+    }
+    for (uint32_t t = threadIdx.x; t < n_hist_words; t += blockDim.x) s_hist[t] = 0u;
+    for (uint32_t t = threadIdx.x; t < p.S * W; t += blockDim.x) s_ne[t] = __ldg(p.not_exp + t);
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31u, lane_lt = (1u << lane) - 1u;
+    const uint32_t n_warps = blockDim.x >> 5, warp_in_cta = threadIdx.x >> 5;
+    Probe3Ctx c;
+#pragma unroll
+    for (int i = 0; i < 3; i++) c.base[i] = smem_addr(s_ck) + p.ck_off[i < NP ? i : 0] * 4u;
+    c.a_hist = smem_addr(s_hist) + (lane & (hrep - 1u)) * 4u;
+    c.a_stash = 0u;
+    auto count = [&](uint32_t bin) {  // bin S = unmatched
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(imad(bin, hrep * 4u, c.a_hist)) : "memory");
+    };
+    const uint32_t a_ne = smem_addr(s_ne);
+    const uint32_t a_q = smem_addr(s_queue) + warp_in_cta * (TILE * W * 4u);  // entry q: key in, result out (word 0)
+    const uint32_t pad = PAD ? p.last_pad : 0u;
+    const uint64_t pol_keep = l2_policy_keep();
+
+    const uint32_t n_tiles = (uint32_t)(src.n / (uint64_t)TILE);
+    const uint32_t stride = gridDim.x * n_warps;
+    uint32_t tile = blockIdx.x * n_warps + warp_in_cta;
+
+    // the fingerprint-table lookup of one read per `act` lane (all 32 lanes call it together)
+    auto lookup = [&](const uint32_t (&kw)[W], bool act) -> uint32_t {
+        uint32_t bucket, fph;
+        g4_hashes<W>(kw, p.g4_seed, p.g4_buckets, bucket, fph);
+        G4Bucket b;
+#pragma unroll
+        for (int j = 0; j < 8; j++) b.e[j] = 0xFFFFFFFFu;
+        if (act) b = g4_load(p, bucket, pol_keep);
+        uint32_t t = g4_match(b, fph, p.g4_fp_mask);
+        bool more = act && t >= p.g4_lim && b.e[7] != 0xFFFFFFFFu;
+        while (__any_sync(0xFFFFFFFFu, more)) {
+            if (more) {
+                bucket = (bucket + 1u == p.g4_buckets) ? 0u : bucket + 1u;
+                b = g4_load(p, bucket, pol_keep);
+                t = g4_match(b, fph, p.g4_fp_mask);
+                more = t >= p.g4_lim && b.e[7] != 0xFFFFFFFFu;
+            }
+        }
+        const uint32_t idx = min(t >> p.g4_cb, p.S - 1u);
+        uint32_t ne[W];
+        lds_ne<W>(imad(idx, W * 4u, a_ne), ne);
+        bool park;
+        uint32_t out = g4_decide<W>(p, t, kw, ne, idx, pad, park);
+        park = park && act;
+        if (__any_sync(0xFFFFFFFFu, park)) {  // rare: symbols outside A/C/G/T/N, fingerprint collisions
+            const uint32_t slow = probe5_slow<W, NP, PAD>(p, kw[0], kw[W - 1], park, lane);  // memo table, else the scan
+            if (park) out = slow;
+        }
+        return act ? out : NONE;
+    };
+
+    auto do_tile = [&](const uint32_t (&w)[R][W], uint32_t t_idx) {
+        uint32_t res[R], bin[R];
+        bool valid[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) res[r] = ck_find<NP>(p, c, ck_key<W, PAD>(p, w[r], valid[r]), valid[r], bin[r]);
+        // everything the exact table did not answer goes to the warp's queue
+        uint32_t qcount = 0;  // warp-uniform
+        uint32_t qi[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const bool pend = res[r] == NONE;
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pend);
+            qi[r] = qcount + (uint32_t)__popc(bal & lane_lt);
+            if (pend) sts_key<W>(a_q + qi[r] * (W * 4u), w[r]);
+            qcount += (uint32_t)__popc(bal);
+        }
+        __syncwarp();
+        for (uint32_t qb = 0; qb < qcount; qb += 32u) {
+            const uint32_t q = qb + lane;
+            const bool act = q < qcount;
+            uint32_t kw[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) kw[k] = 0u;
+            if (act) lds_key<W>(a_q + q * (W * 4u), kw);
+            const uint32_t out = lookup(kw, act);
+            if (act) sts32(a_q + q * (W * 4u), out);  // the entry's key has been consumed: reuse it for the result
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (res[r] == NONE) {
+                res[r] = lds32(a_q + qi[r] * (W * 4u));
+                bin[r] = res[r] == NONE ? p.S : (res[r] >> 16);
+            }
+        }
+        __syncwarp();  // the queue is reused by the next tile
+        const uint32_t g = t_idx * 32u + lane;
+        reinterpret_cast<uint4*>(results)[g] = make_uint4(res[0], res[1], res[2], res[3]);
+#pragma unroll
+        for (int r = 0; r < R; r++) count(min(bin[r], p.S));  // (ck_find's own unmatched bin is S | 1)
+    };
+
+    uint32_t wa[R][W], wb[R][W];
+    if (tile < n_tiles) probe3_load<W, R>(src.packed, tile, lane, wa);
+    while (tile < n_tiles) {
+        {
+            uint32_t nt = tile + stride;
+            if (nt < n_tiles) probe3_load<W, R>(src.packed, nt, lane, wb);
+            if (nt + stride < n_tiles) probe3_prefetch_l2<W, R>(src.packed, nt + stride, lane);
+            do_tile(wa, tile);
+            tile = nt;
+            if (tile < n_tiles) {
+                nt = tile + stride;
+                if (nt < n_tiles) probe3_load<W, R>(src.packed, nt, lane, wa);
+                if (nt + stride < n_tiles) probe3_prefetch_l2<W, R>(src.packed, nt + stride, lane);
+                do_tile(wb, tile);
+                tile = nt;
+            }
+        }
+    }
+    // ---- tail: fewer than a tile of reads, one per lane, first warp of the grid ----
+    if (blockIdx.x == 0 && threadIdx.x < 32u) {
+        for (uint64_t b0 = (uint64_t)n_tiles * TILE; b0 < src.n; b0 += 32u) {
+            const uint64_t i = b0 + lane;
+            const bool live = i < src.n;
+            uint32_t w1[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) w1[k] = live ? __ldg(src.packed + i * W + k) : 0u;
+            const uint32_t out = lookup(w1, live);
+            if (live) {
+                results[i] = out;
+                count(out == NONE ? p.S : (out >> 16));
+            }
+        }
+    }
+    // ---- flush the replicated bins (bin S = unmatched) ----
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b <= p.S; b += blockDim.x) {
+        uint32_t v = 0;
+        for (uint32_t r = 0; r < hrep; r++) v += s_hist[b * hrep + r];
+        if (v) atomicAdd(&p.counts[b], (unsigned long long)v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // k_pack: encode() for a batch (mod.rs:49-61), any L
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_pack(const uint8_t* __restrict__ ascii, uint64_t n, uint32_t L,
@@ -1920,6 +2101,31 @@ static cudaError_t launch_probe4_w(const MatchParams& p, const ReadSource& src, 
                       : launch_probe4_wp<W, false>(p, src, d_results, g, stream);
 }
 
+size_t probe5_smem_bytes(uint32_t ck_words, uint32_t S, uint32_t W, uint32_t hist_rep) {
+    return (size_t)ck_words * 4 + (size_t)(S + 1u) * hist_rep * 4 + (size_t)S * W * 4 +
+           (size_t)(PROBE5_THREADS / 32) * (32 * PROBE5_R) * W * 4 + 16;
+}
+
+template <int W, int NP>
+static cudaError_t launch_probe5_wn(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
+                                    const LaunchGeometry& g, cudaStream_t stream) {
+    const size_t smem = probe5_smem_bytes(p.ck_words, p.S, W, p.g4_hist_rep);
+    const uint64_t n_warp_tiles = (src.n + 32 * PROBE5_R - 1) / (32 * PROBE5_R);
+    const uint64_t want = (n_warp_tiles + PROBE5_THREADS / 32 - 1) / (PROBE5_THREADS / 32);
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)g.sm_count));
+    if (p.last_pad) {
+        auto k = k_probe5<W, NP, true>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, PROBE5_THREADS, smem, stream>>>(p, src, d_results);
+    } else {
+        auto k = k_probe5<W, NP, false>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, PROBE5_THREADS, smem, stream>>>(p, src, d_results);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
 template <int W, int NP>
 static cudaError_t launch_probe3_wn(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
                                     const LaunchGeometry& g, cudaStream_t stream) {
@@ -1932,7 +2138,14 @@ cudaError_t launch_probe(const MatchParams& p, const ReadSource& src, uint32_t* 
     if (src.n == 0) return cudaSuccess;
     if (p.table == nullptr || p.W > (uint32_t)MAX_FAST_WORDS) return cudaErrorInvalidValue;
     const bool ascii = src.ascii != nullptr;
-    if (!ascii && p.ck_np && p.W <= 2u &&
+    if (!ascii && p.ck_np && p.ck_exact_only && p.g4_table && p.W <= 2u &&
+        ((reinterpret_cast<uintptr_t>(src.packed) | reinterpret_cast<uintptr_t>(d_results)) & 15u) == 0u) {
+        if (p.W == 1) return p.ck_np == 2 ? launch_probe5_wn<1, 2>(p, src, d_results, g, stream)
+                                          : launch_probe5_wn<1, 3>(p, src, d_results, g, stream);
+        return p.ck_np == 2 ? launch_probe5_wn<2, 2>(p, src, d_results, g, stream)
+                            : launch_probe5_wn<2, 3>(p, src, d_results, g, stream);
+    }
+    if (!ascii && p.ck_np && !p.ck_exact_only && p.W <= 2u &&
         ((reinterpret_cast<uintptr_t>(src.packed) | reinterpret_cast<uintptr_t>(d_results)) & 15u) == 0u) {
         if (p.W == 1) return p.ck_np == 2 ? launch_probe3_wn<1, 2>(p, src, d_results, g, stream)
                                           : launch_probe3_wn<1, 3>(p, src, d_results, g, stream);

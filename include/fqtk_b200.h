@@ -95,11 +95,13 @@ FQTK_B200_API int fqtk_b200_matcher_create(const uint8_t* panel_ascii, uint32_t 
                                            int device, fqtk_b200_matcher** out);
 /* The same with per-handle options instead of the defaults (two host threads may create matchers concurrently:
  * nothing about a handle depends on process-global state).  Initialise with fqtk_b200_options_init, then change fields. */
-#define FQTK_B200_KERNEL_AUTO (-1) /* k_probe3 when the pure-A/C/G/T memo entries fit in shared memory, else k_probe5 / k_probe4 */
+#define FQTK_B200_KERNEL_AUTO (-1) /* k_probe3 when the pure-A/C/G/T memo entries fit in shared memory, else k_probe5 (L <= 16)
+                                      or k_probe4 (L <= 32), else k_probe2 */
 typedef struct {
     uint32_t struct_size;       /* sizeof(fqtk_b200_options) as the caller compiled it (lets the struct grow) */
-    int32_t kernel;             /* packed-route kernel: FQTK_B200_KERNEL_AUTO, 0 = k_probe2 only, 1 = the L2-resident table
-                                   only, 2 / 3 = k_probe3 with that many sub-tables.  Results are identical for every value */
+    int32_t kernel;             /* packed-route kernel: FQTK_B200_KERNEL_AUTO, 0 = k_probe2 only, 1 = k_probe4 (the L2-resident
+                                   fingerprint table only), 2 / 3 = k_probe3 with that many sub-tables, 5 = k_probe5 (exact
+                                   entries in shared memory + the fingerprint table).  Results are identical for every value */
     uint64_t table_budget;      /* largest neighbourhood (candidate strings) a memo table is built for; 0 = 32 Mi */
     uint64_t chunk_bytes;       /* input bytes per chunk of the host-buffer pipeline; 0 = 32 MiB */
     uint32_t l2_table_load_pct; /* load factor of the L2-resident table in percent, 0 = automatic */

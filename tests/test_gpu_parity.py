@@ -422,11 +422,12 @@ def test_configs_reduced_n(cfg_id, n, use_cache):
                          expect_mode="table" if use_cache else "brute")
 
 
-@pytest.mark.parametrize("arity", [0, 1, 2, 3])
+@pytest.mark.parametrize("arity", [0, 1, 2, 3, 5])
 def test_packed_route_kernel_variants(arity):
-    """The HBM-resident packed route has three kernels: k_probe3 (shared-memory cuckoo table of the pure A/C/G/T memo
-    entries, 2 or 3 sub-tables, L <= 16), k_probe4 (L2-resident fingerprint table of every pure A/C/G/T candidate,
-    verified against the panel, L <= 32; knob 1) and k_probe2 (hot tier + global memo table; knob 0).  All bit-exact."""
+    """The HBM-resident packed route has four kernels: k_probe3 (shared-memory cuckoo table of the pure A/C/G/T memo
+    entries, 2 or 3 sub-tables, L <= 16), k_probe4 (L2-resident fingerprint table of every A/C/G/T/N candidate, verified
+    against the panel, L <= 32; knob 1), k_probe5 (the exact entries in shared memory + the fingerprint table, L <= 16;
+    knob 5) and k_probe2 (hot tier + global memo table; knob 0).  All bit-exact."""
     torch = torch_cuda()
     L = _lib.lib()
     rng = np.random.default_rng(4242 + arity)
@@ -437,14 +438,17 @@ def test_packed_route_kernel_variants(arity):
             panel = synth.panel(cfg)
             bcs = [bytes(r) for r in panel]
             with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, True) as m:
-                assert int(m.info().cuckoo_probes) == (arity if arity >= 2 else 0)
-                assert (int(m.info().cuckoo_entries) > 0) == (arity >= 2)
-                assert (int(m.info().l2_table_entries) > 0) == (arity == 1)
+                if arity == 5:
+                    assert int(m.info().cuckoo_probes) in (2, 3) and int(m.info().cuckoo_entries) > 0
+                else:
+                    assert int(m.info().cuckoo_probes) == (arity if arity >= 2 else 0)
+                    assert (int(m.info().cuckoo_entries) > 0) == (arity >= 2)
+                assert (int(m.info().l2_table_entries) > 0) == (arity in (1, 5))
             reads = synth.reads_host(panel, cfg.seed_reads, 31, n)
             reads[::41, 3] = ord("N")
             reads[::97, 1] = ord("r")
             check_against_oracle(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, reads, True, expect_mode="table")
-        if arity in (0, 1):  # the big-table configs on their own kernels (k_probe4 by default), and on k_probe2
+        if arity in (0, 1, 5):  # the big-table configs on their own kernels, and on k_probe2
             for cfg_id, n in [(4, 120_000), (5, 80_000)]:
                 cfg = synth.CONFIGS[cfg_id]
                 panel = synth.panel(cfg)
@@ -453,7 +457,7 @@ def test_packed_route_kernel_variants(arity):
                 reads[::37, 2] = ord("N")
                 reads[::101, 5] = ord("y")
                 with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, True) as m:
-                    assert (int(m.info().l2_table_entries) > 0) == (arity == 1)
+                    assert (int(m.info().l2_table_entries) > 0) == (arity in (1, 5))
                 check_against_oracle(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, reads, True, expect_mode="table")
         for _ in range(16):  # pad nibbles (L % 8 != 0), one- to three-word keys, dirty reads, odd parameters
             Lb = int(rng.choice([1, 2, 3, 7, 8, 9, 12, 15, 16, 17, 20, 23, 24, 25, 29, 32]))
