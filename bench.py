@@ -577,6 +577,83 @@ def measure_e2e(ctx, args, cfg, panel, matcher, d_packed, d_res, first, n):
     return out
 
 
+def measure_fastq(ctx, args, cfg, panel, matcher):
+    """The ingest side: the headline config's barcodes taken straight out of in-memory, uncompressed
+    index FASTQ chunks (I1 and I2, 8 bases each at cfg 3): fqtk_b200_fastq_scan (host, one thread per chunk) -> per-read
+    offsets -> fqtk_b200_matcher_assign_fastq (the chunks cross PCIe whole; gather + encode + match on the GPU)."""
+    import ctypes as C
+
+    from fqtk_b200 import _lib
+
+    lib = _lib.lib()
+    L = cfg.barcode_len
+    n = 4 << 20
+    reads = host_reads(panel, cfg.seed_reads, 0, n)
+    halves = [(0, L // 2), (L // 2, L)] if L >= 2 else [(0, L)]
+    rec_head = np.frombuffer(b"@A00000:000:HXXXXXXXX:1:1101:00000:00000 1:N:0:0\n", dtype=np.uint8)
+    pinned = []
+
+    def pinned_array(count, dtype):  # the reader's chunk buffers and the scanner's tables live in pinned memory
+        p = C.c_void_p()
+        _lib.check(lib.fqtk_b200_host_alloc(C.byref(p), count * np.dtype(dtype).itemsize))
+        pinned.append(p)
+        ct = {np.uint8: C.c_uint8, np.uint32: C.c_uint32, np.uint64: C.c_uint64}[dtype]
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), shape=(count,))
+
+    texts = []
+    for lo, hi in halves:  # one FASTQ chunk per index read: fixed-width records built with numpy
+        w = hi - lo
+        rec = pinned_array(n * (rec_head.size + w + 3 + w + 1), np.uint8).reshape(n, -1)
+        rec[:, :rec_head.size] = rec_head
+        rec[:, rec_head.size:rec_head.size + w] = reads[:, lo:hi]
+        rec[:, rec_head.size + w:rec_head.size + w + 3] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+        rec[:, rec_head.size + w + 3:rec_head.size + 2 * w + 3] = ord("F")
+        rec[:, -1] = ord("\n")
+        texts.append(rec.reshape(-1))
+    t0 = time.perf_counter()
+    tables = []
+
+    def scan_one(text):
+        seq = pinned_array(n, np.uint64)
+        ln = pinned_array(n, np.uint32)
+        k, used = C.c_uint64(), C.c_uint64()
+        _lib.check(lib.fqtk_b200_fastq_scan(text.ctypes.data, text.size, n, None, seq.ctypes.data, ln.ctypes.data,
+                                            C.byref(k), C.byref(used)))
+        assert k.value == n and used.value == text.size
+        return seq, ln
+
+    with ThreadPoolExecutor(len(texts)) as ex:
+        tables = list(ex.map(scan_one, texts))
+    scan_s = time.perf_counter() - t0
+    srcs = (_lib.FastqSource * len(texts))()
+    for k, (text, (seq, ln)) in enumerate(zip(texts, tables)):
+        srcs[k] = _lib.FastqSource(text.ctypes.data, text.size, seq.ctypes.data, ln.ctypes.data)
+    segs = (_lib.FastqSegment * len(texts))(*[_lib.FastqSegment(k, 0, hi - lo) for k, (lo, hi) in enumerate(halves)])
+    out = np.empty(n, dtype=np.uint32)
+    matcher.reset_counts()
+    _lib.check(lib.fqtk_b200_matcher_assign_fastq(matcher._h, srcs, len(texts), segs, len(texts), n, out.ctypes.data))
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        _lib.check(lib.fqtk_b200_matcher_assign_fastq(matcher._h, srcs, len(texts), segs, len(texts), n, out.ctypes.data))
+    gpu_s = (time.perf_counter() - t0) / reps
+    want = matcher.assign_batch(reads[: 1 << 18])
+    assert np.array_equal(out[: 1 << 18], want), "FASTQ ingest results differ from dense barcode rows"
+    matcher.reset_counts()
+    fastq_bytes = sum(int(t.size) for t in texts)
+    del texts, tables, srcs
+    for p in pinned:
+        lib.fqtk_b200_host_free(p)
+    return {"reads": n, "fastq_bytes": fastq_bytes, "inputs": 2 if L >= 2 else 1,
+            "scan_mreads_per_s": round(n / scan_s / 1e6, 2), "scan_threads": 2 if L >= 2 else 1,
+            "assign_fastq_mreads_per_s": round(n / gpu_s / 1e6, 2),
+            "end_to_end_mreads_per_s": round(n / (scan_s + gpu_s) / 1e6, 2),
+            "h2d_bytes_per_read": round((fastq_bytes + (2 if L >= 2 else 1) * 12 * n) / n, 1),
+            "what": "uncompressed index FASTQ text in pinned host memory -> fqtk_b200_fastq_scan -> "
+                    "fqtk_b200_matcher_assign_fastq (raw chunks + offset tables over PCIe, B segments gathered and encoded on "
+                    "the GPU); scan and GPU call timed back to back, not overlapped"}
+
+
 def run_single_process(args):
     """The headline config through fqtk_b200_group_*: one process, one matcher per GPU, contiguous shards, ONE count table
     summed on the first device over peer-mapped pointers — the process model of the Rust host."""
@@ -770,6 +847,9 @@ def run_b200(args):
     if not args.no_e2e:
         e2e = measure_e2e(ctx, args, cfg, panel, matcher, d_packed, d_res, head["first"], n)
 
+    ingest = None
+    if rank == 0 and not args.no_e2e:
+        ingest = measure_fastq(ctx, args, cfg, panel, matcher)
     matcher.close()
     del d_packed, d_res
     torch.cuda.empty_cache()
@@ -817,7 +897,7 @@ def run_b200(args):
                            "l2_table_bytes": int(info.l2_table_bytes)},
             "brute_force": brute, "routing": routing,
             "matched_fraction": round(1.0 - float(counts[-1]) / float(counts.sum()), 5),
-            "parity_check": head.get("parity_check"), "configs": configs, "numa": numa,
+            "parity_check": head.get("parity_check"), "configs": configs, "numa": numa, "fastq_ingest": ingest,
         }
         emit(line)
     if world > 1:

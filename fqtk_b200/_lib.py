@@ -34,7 +34,8 @@ SYMBOLS = [
     "fqtk_b200_group_create", "fqtk_b200_group_destroy", "fqtk_b200_group_size", "fqtk_b200_group_device",
     "fqtk_b200_group_matcher", "fqtk_b200_group_shard", "fqtk_b200_group_assign_batch",
     "fqtk_b200_group_assign_batch_packed", "fqtk_b200_group_assign_packed_device", "fqtk_b200_group_counts",
-    "fqtk_b200_group_reset_counts",
+    "fqtk_b200_group_reset_counts", "fqtk_b200_fastq_scan", "fqtk_b200_matcher_assign_fastq",
+    "fqtk_b200_matcher_assign_fastq_device",
 ]
 
 
@@ -59,6 +60,19 @@ class Options(C.Structure):
 class Segment(C.Structure):
     """fqtk_b200_segment"""
     _fields_ = [("base", C.c_void_p), ("row_stride", C.c_uint64), ("offset", C.c_uint32), ("length", C.c_uint32)]
+
+
+class FastqSource(C.Structure):
+    """fqtk_b200_fastq_source"""
+    _fields_ = [("chunk", C.c_void_p), ("chunk_bytes", C.c_uint64), ("seq_offsets", C.c_void_p), ("seq_lengths", C.c_void_p)]
+
+
+class FastqSegment(C.Structure):
+    """fqtk_b200_fastq_segment"""
+    _fields_ = [("source", C.c_uint32), ("offset", C.c_uint32), ("length", C.c_uint32)]
+
+
+SEGMENT_REST = 0xFFFFFFFF
 
 
 class Fqtk_b200Error(RuntimeError):
@@ -123,6 +137,11 @@ def lib() -> C.CDLL:
         "fqtk_b200_group_assign_packed_device": (C.c_int, [vp, C.POINTER(vp), u64p, C.POINTER(vp), C.POINTER(vp)]),
         "fqtk_b200_group_counts": (C.c_int, [vp, vp]),
         "fqtk_b200_group_reset_counts": (C.c_int, [vp]),
+        "fqtk_b200_fastq_scan": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp, vp, vp, u64p, u64p]),
+        "fqtk_b200_matcher_assign_fastq": (C.c_int, [vp, C.POINTER(FastqSource), C.c_uint32, C.POINTER(FastqSegment), C.c_uint32,
+                                                     C.c_uint64, vp]),
+        "fqtk_b200_matcher_assign_fastq_device": (C.c_int, [vp, C.POINTER(FastqSource), C.c_uint32, C.POINTER(FastqSegment),
+                                                            C.c_uint32, C.c_uint64, vp, vp]),
         "fqtk_b200_synth_panel": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
         "fqtk_b200_synth_reads_host": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, vp]),
         "fqtk_b200_synth_reads_device": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, vp]),

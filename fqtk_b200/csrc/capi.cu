@@ -120,6 +120,10 @@ struct fqtk_b200_matcher {
     uint32_t* d_scratch = nullptr;   // packed scratch for the L > 32 ASCII route and the device segment gather
     size_t scratch_words = 0;
     uint32_t* d_seg_packed[N_PIPE] = {};  // packed scratch per pipeline slot for the host segment gather
+    void* d_fq[3 * FQTK_B200_MAX_SEGMENTS] = {};  // raw FASTQ chunks + their offset / length tables (assign_fastq)
+    size_t fq_cap[3 * FQTK_B200_MAX_SEGMENTS] = {};
+    uint32_t* d_fq_len = nullptr;  // gathered barcode lengths (REST segments)
+    size_t fq_len_cap = 0;
     size_t seg_packed_words[N_PIPE] = {};
 };
 
@@ -1021,6 +1025,9 @@ void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m) {
         if (m->streams[s]) cudaStreamDestroy(m->streams[s]);
     }
     if (m->d_scratch) cudaFree(m->d_scratch);
+    for (void* q : m->d_fq)
+        if (q) cudaFree(q);
+    if (m->d_fq_len) cudaFree(m->d_fq_len);
     if (m->d_route_ws) cudaFree(m->d_route_ws);
     for (int s = 0; s < N_PIPE; s++)
         if (m->d_seg_packed[s]) cudaFree(m->d_seg_packed[s]);
@@ -1305,6 +1312,155 @@ int fqtk_b200_matcher_assign_segments(fqtk_b200_matcher* m, const fqtk_b200_segm
         slot = (slot + 1) % N_PIPE;
     }
     for (int s = 0; s < N_PIPE; s++) CU(cudaStreamSynchronize(m->streams[s]));
+    return FQTK_B200_OK;
+}
+
+static int check_fastq_args(const fqtk_b200_matcher* m, const fqtk_b200_fastq_source* sources, uint32_t n_sources,
+                            const fqtk_b200_fastq_segment* segs, uint32_t n_segs, bool& any_rest, uint64_t& fixed_total) {
+    if (!m || !sources || !segs || n_sources == 0 || n_sources > FQTK_B200_MAX_SEGMENTS || n_segs == 0 ||
+        n_segs > FQTK_B200_MAX_SEGMENTS)
+        return fail(FQTK_B200_ERR_ARG, "need 1..8 sources and 1..8 segments");
+    any_rest = false;
+    fixed_total = 0;
+    for (uint32_t k = 0; k < n_segs; k++) {
+        if (segs[k].source >= n_sources) return fail(FQTK_B200_ERR_ARG, "segment names a source that was not given");
+        if (segs[k].length == 0) return fail(FQTK_B200_ERR_ARG, "zero-length segment");
+        if (segs[k].length == FQTK_B200_SEGMENT_REST)
+            any_rest = true;
+        else
+            fixed_total += segs[k].length;
+    }
+    for (uint32_t s = 0; s < n_sources; s++)
+        if (!sources[s].chunk || !sources[s].seq_offsets) return fail(FQTK_B200_ERR_ARG, "NULL chunk / seq_offsets");
+    if (!any_rest && fixed_total != m->L) {  // as for fixed-stride segments: every read would be None or panic
+        char buf[160];
+        std::snprintf(buf, sizeof buf, "Read barcode length (%llu) differs from expected barcode length (%u)",
+                      (unsigned long long)fixed_total, m->L);
+        return fail(FQTK_B200_ERR_LENGTH, buf);
+    }
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_matcher_assign_fastq_device(fqtk_b200_matcher* m, const fqtk_b200_fastq_source* sources, uint32_t n_sources,
+                                          const fqtk_b200_fastq_segment* segs, uint32_t n_segs, uint64_t n,
+                                          uint32_t* d_results, void* stream) {
+    bool any_rest;
+    uint64_t fixed_total;
+    int rc = check_fastq_args(m, sources, n_sources, segs, n_segs, any_rest, fixed_total);
+    if (rc != FQTK_B200_OK) return rc;
+    if (n && !d_results) return fail(FQTK_B200_ERR_ARG, "NULL results");
+    if (n >= (1ull << 32)) return fail(FQTK_B200_ERR_ARG, "n_reads must be < 2^32 per device call");
+    if (n == 0) return FQTK_B200_OK;
+    CU(cudaSetDevice(m->device));
+    fq::OffsetSource os{};
+    os.n_segments = n_segs;
+    for (uint32_t s = 0; s < n_sources; s++) {
+        os.base[s] = sources[s].chunk;
+        os.seq_offsets[s] = sources[s].seq_offsets;
+        os.seq_lengths[s] = sources[s].seq_lengths;
+    }
+    for (uint32_t k = 0; k < n_segs; k++) {
+        os.source_of[k] = segs[k].source;
+        os.offset[k] = segs[k].offset;
+        os.length[k] = segs[k].length;
+        if (segs[k].length == FQTK_B200_SEGMENT_REST && !sources[segs[k].source].seq_lengths)
+            return fail(FQTK_B200_ERR_ARG, "a REST segment needs the source's seq_lengths");
+    }
+    rc = ensure_scratch(&m->d_scratch, &m->scratch_words, (size_t)n * m->W + 4);
+    if (rc != FQTK_B200_OK) return rc;
+    if (any_rest && n > m->fq_len_cap) {
+        if (m->d_fq_len) cudaFree(m->d_fq_len);
+        m->d_fq_len = nullptr;
+        m->fq_len_cap = 0;
+        CU(cudaMalloc(&m->d_fq_len, (size_t)n * 4));
+        m->fq_len_cap = (size_t)n;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(fq::launch_pack_offsets(os, n, m->L, m->d_scratch, any_rest ? m->d_fq_len : nullptr, m->geo, st));
+    fq::ReadSource src{m->d_scratch, nullptr, nullptr, 0, n};
+    rc = run_device(m, src, d_results, st);
+    if (rc != FQTK_B200_OK) return rc;
+    if (any_rest) CU(fq::launch_fix_lengths(d_results, m->d_fq_len, n, m->L, m->S, m->d_counts, m->geo, st));
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_matcher_assign_fastq(fqtk_b200_matcher* m, const fqtk_b200_fastq_source* sources, uint32_t n_sources,
+                                   const fqtk_b200_fastq_segment* segs, uint32_t n_segs, uint64_t n, uint32_t* results) {
+    bool any_rest;
+    uint64_t fixed_total;
+    int rc = check_fastq_args(m, sources, n_sources, segs, n_segs, any_rest, fixed_total);
+    if (rc != FQTK_B200_OK) return rc;
+    if (n == 0) return FQTK_B200_OK;
+    if (!results) return fail(FQTK_B200_ERR_ARG, "NULL results");
+    for (uint32_t s = 0; s < n_sources; s++)
+        if (!sources[s].seq_lengths) return fail(FQTK_B200_ERR_ARG, "the host call needs seq_lengths for every source");
+    // ReadSetIterator::next (demux.rs:298-315): every read must hold its segments; then BarcodeMatcher::assign's length rules
+    // for barcodes that come out longer than L (only possible with a REST segment)
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t total = 0;
+        for (uint32_t k = 0; k < n_segs; k++) {
+            const fqtk_b200_fastq_source& so = sources[segs[k].source];
+            const uint64_t len = so.seq_lengths[i], need = (uint64_t)segs[k].offset +
+                                                           (segs[k].length == FQTK_B200_SEGMENT_REST ? 1u : segs[k].length);
+            if (so.seq_offsets[i] + len > so.chunk_bytes) return fail(FQTK_B200_ERR_ARG, "a sequence line runs past its chunk");
+            if (len < need) {
+                char buf[200];
+                std::snprintf(buf, sizeof buf, "Read %llu had too few bases to demux %llu vs. %llu needed in read structure.",
+                              (unsigned long long)i, (unsigned long long)len, (unsigned long long)need);
+                return fail(FQTK_B200_ERR_ARG, buf);
+            }
+            total += segs[k].length == FQTK_B200_SEGMENT_REST ? len - segs[k].offset : segs[k].length;
+        }
+        if (total > m->L) {
+            std::string bc;
+            for (uint32_t k = 0; k < n_segs; k++) {
+                const fqtk_b200_fastq_source& so = sources[segs[k].source];
+                const uint64_t len = segs[k].length == FQTK_B200_SEGMENT_REST ? so.seq_lengths[i] - segs[k].offset : segs[k].length;
+                bc.append(reinterpret_cast<const char*>(so.chunk + so.seq_offsets[i] + segs[k].offset), (size_t)len);
+            }
+            size_t nocalls = 0;
+            for (char ch : bc) nocalls += fq::byte_is_nocall((uint8_t)ch);
+            if (nocalls > (size_t)m->max_mm + m->max_ns) continue;  // the pre-filter makes it None before the panic
+            std::string msg = "Read barcode (";
+            for (char ch : bc) msg.push_back(decode_mask(fq::encode_byte((uint8_t)ch)));
+            msg += ") length (" + std::to_string(bc.size()) + ") differs from expected barcode (";
+            msg.append(reinterpret_cast<const char*>(m->panel.data()), m->L);
+            msg += ") length (" + std::to_string(m->L) + ") for sample 0";
+            return fail(FQTK_B200_ERR_LENGTH, msg);
+        }
+    }
+    CU(cudaSetDevice(m->device));
+    PipelineDrain drain{m};
+    cudaStream_t st = m->streams[0];
+    auto ensure = [&](int slot, size_t bytes) -> int {
+        if (bytes > m->fq_cap[slot]) {
+            if (m->d_fq[slot]) cudaFree(m->d_fq[slot]);
+            m->d_fq[slot] = nullptr;
+            m->fq_cap[slot] = 0;
+            CU(cudaMalloc(&m->d_fq[slot], bytes + 64));
+            m->fq_cap[slot] = bytes;
+        }
+        return FQTK_B200_OK;
+    };
+    fqtk_b200_fastq_source dev[FQTK_B200_MAX_SEGMENTS];
+    for (uint32_t s = 0; s < n_sources; s++) {
+        if ((rc = ensure(3 * s, sources[s].chunk_bytes)) != FQTK_B200_OK) return rc;
+        if ((rc = ensure(3 * s + 1, n * 8)) != FQTK_B200_OK) return rc;
+        if ((rc = ensure(3 * s + 2, n * 4)) != FQTK_B200_OK) return rc;
+        CU(cudaMemcpyAsync(m->d_fq[3 * s], sources[s].chunk, sources[s].chunk_bytes, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(m->d_fq[3 * s + 1], sources[s].seq_offsets, n * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(m->d_fq[3 * s + 2], sources[s].seq_lengths, n * 4, cudaMemcpyHostToDevice, st));
+        dev[s].chunk = static_cast<const uint8_t*>(m->d_fq[3 * s]);
+        dev[s].chunk_bytes = sources[s].chunk_bytes;
+        dev[s].seq_offsets = static_cast<const uint64_t*>(m->d_fq[3 * s + 1]);
+        dev[s].seq_lengths = static_cast<const uint32_t*>(m->d_fq[3 * s + 2]);
+    }
+    rc = ensure_pipeline(m, 16, (size_t)n, false);
+    if (rc != FQTK_B200_OK) return rc;
+    rc = fqtk_b200_matcher_assign_fastq_device(m, dev, n_sources, segs, n_segs, n, m->d_out[0], st);
+    if (rc != FQTK_B200_OK) return rc;
+    CU(cudaMemcpyAsync(results, m->d_out[0], n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return FQTK_B200_OK;
 }
 

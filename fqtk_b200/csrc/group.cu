@@ -298,6 +298,49 @@ int fqtk_b200_pack_host(const uint8_t* rows, uint64_t n, uint32_t L, uint64_t st
     return FQTK_B200_OK;
 }
 
+// ---- 4-line FASTQ record scanner (the part of seq_io's reader the GPU path needs: where the sequence lines are) ----
+int fqtk_b200_fastq_scan(const uint8_t* chunk, uint64_t chunk_bytes, uint64_t max_records, uint64_t* head_offsets,
+                         uint64_t* seq_offsets, uint32_t* seq_lengths, uint64_t* n_records, uint64_t* consumed) {
+    if ((chunk_bytes && !chunk) || !seq_offsets || !seq_lengths || !n_records || !consumed)
+        return g_fail(FQTK_B200_ERR_ARG, "NULL argument");
+    uint64_t pos = 0, n = 0;
+    *n_records = 0;
+    *consumed = 0;
+    while (n < max_records && pos < chunk_bytes) {
+        uint64_t start[4], len[4];
+        uint64_t p = pos;
+        bool whole = true;
+        for (int line = 0; line < 4; line++) {
+            const void* nl = p < chunk_bytes ? std::memchr(chunk + p, '\n', (size_t)(chunk_bytes - p)) : nullptr;
+            if (!nl) {
+                whole = false;  // the record runs past the chunk: the caller carries it over
+                break;
+            }
+            const uint64_t end = (uint64_t)(static_cast<const uint8_t*>(nl) - chunk);
+            start[line] = p;
+            len[line] = end - p;
+            if (len[line] && chunk[end - 1] == '\r') len[line]--;
+            p = end + 1;
+        }
+        if (!whole) break;
+        if (len[0] == 0 || chunk[start[0]] != '@')
+            return g_fail(FQTK_B200_ERR_ARG, "FASTQ record " + std::to_string(n) + ": header line does not start with '@'");
+        if (len[2] == 0 || chunk[start[2]] != '+')
+            return g_fail(FQTK_B200_ERR_ARG, "FASTQ record " + std::to_string(n) + ": separator line does not start with '+'");
+        if (len[1] != len[3])
+            return g_fail(FQTK_B200_ERR_ARG, "FASTQ record " + std::to_string(n) + ": sequence and quality lengths differ");
+        if (len[1] > 0xFFFFFFFFull) return g_fail(FQTK_B200_ERR_ARG, "FASTQ record too long");
+        if (head_offsets) head_offsets[n] = start[0];
+        seq_offsets[n] = start[1];
+        seq_lengths[n] = (uint32_t)len[1];
+        n++;
+        pos = p;
+    }
+    *n_records = n;
+    *consumed = pos;
+    return FQTK_B200_OK;
+}
+
 // ---- the platform's pinned-memory copy ceiling ----------------------------------------------------------------------
 int fqtk_b200_copy_ceiling(int device, uint64_t in_bytes, uint64_t out_bytes, uint64_t chunk_in_bytes, int reps,
                            double* seconds_per_rep) {

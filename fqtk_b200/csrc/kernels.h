@@ -101,6 +101,20 @@ struct SegmentSource {
     uint32_t n_segments;
 };
 
+// Barcode segments taken straight out of raw FASTQ chunks (demux.rs:288-342 + :121-123): read i's sequence line starts at
+// base[s] + seq_offsets[s][i] in source s; segment k of that source = bytes [offset, offset + length) of the line, or
+// [offset, end of line) when length == REST (a trailing `+B`), which needs seq_lengths[s].
+struct OffsetSource {
+    static constexpr uint32_t REST = 0xFFFFFFFFu;
+    const uint8_t* base[8];
+    const uint64_t* seq_offsets[8];
+    const uint32_t* seq_lengths[8];  // may be nullptr when no segment of the source is REST
+    uint32_t source_of[8];           // segment -> source
+    uint32_t offset[8];
+    uint32_t length[8];
+    uint32_t n_segments;
+};
+
 struct LaunchGeometry {
     int sm_count;
     int max_smem_optin;
@@ -134,6 +148,10 @@ size_t route_workspace_bytes(uint64_t n, uint32_t S, const LaunchGeometry& g);
 bool route_supported(uint32_t S, const LaunchGeometry& g);
 cudaError_t launch_route(const uint32_t* d_results, uint64_t n, uint32_t S, uint32_t* d_order,
                          unsigned long long* d_offsets, void* d_workspace, const LaunchGeometry& g, cudaStream_t stream);
+cudaError_t launch_pack_offsets(const OffsetSource& seg, uint64_t n, uint32_t L, uint32_t* d_packed, uint32_t* d_lengths,
+                                const LaunchGeometry& g, cudaStream_t stream);
+cudaError_t launch_fix_lengths(uint32_t* d_results, const uint32_t* d_lengths, uint64_t n, uint32_t L, uint32_t S,
+                               unsigned long long* d_counts, const LaunchGeometry& g, cudaStream_t stream);
 cudaError_t launch_narrow_u16(const uint32_t* d_results, uint64_t n, uint16_t* d_out, const LaunchGeometry& g,
                               cudaStream_t stream);
 cudaError_t prepare_kernels(const LaunchGeometry& g);  // opt-in shared memory attributes, once per device

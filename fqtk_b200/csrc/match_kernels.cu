@@ -2205,6 +2205,84 @@ cudaError_t launch_pack_segments(const SegmentSource& seg, uint64_t n, uint32_t 
     return cudaGetLastError();
 }
 
+// k_pack_offsets: ReadSetIterator::next's segment extraction (demux.rs:288-342) + sample_barcode_sequence (:121-123) +
+// encode() (mod.rs:49-61) for reads that still sit in raw FASTQ text: the B segments are gathered by per-read offsets of
+// the sequence lines (fqtk_b200_fastq_scan) and packed straight into BitEnc words.  lengths[i] = bases gathered for read i
+// (it differs from L only with a trailing `+B` segment); symbols beyond L are dropped, missing ones stay 0.
+__global__ void __launch_bounds__(256) k_pack_offsets(const OffsetSource seg, uint64_t n, uint32_t L,
+                                                      uint32_t* __restrict__ packed, uint32_t* __restrict__ lengths) {
+    __shared__ uint8_t s_lut[256];
+    init_lut(s_lut);
+    __syncthreads();
+    const uint32_t W = words_for_len(L);
+    const uint64_t total = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += total) {
+        uint32_t acc = 0u, pos = 0u;  // pos = symbols gathered so far
+        for (uint32_t s = 0; s < seg.n_segments; s++) {
+            const uint32_t so = seg.source_of[s];
+            const uint8_t* src = seg.base[so] + __ldg(seg.seq_offsets[so] + i) + seg.offset[s];
+            uint32_t len = seg.length[s];
+            if (len == OffsetSource::REST) {
+                const uint32_t sl = __ldg(seg.seq_lengths[so] + i);
+                len = sl > seg.offset[s] ? sl - seg.offset[s] : 0u;
+            }
+            for (uint32_t k = 0; k < len; k++, pos++) {
+                if (pos < L) {
+                    acc |= (uint32_t)s_lut[__ldg(src + k)] << (4u * (pos & 7u));
+                    if ((pos & 7u) == 7u) {
+                        packed[i * W + (pos >> 3)] = acc;
+                        acc = 0u;
+                    }
+                }
+            }
+        }
+        if (pos < L) {  // a short read: zero the rest of its row (its result is None whatever the row holds)
+            for (uint32_t wd = pos >> 3; wd < W; wd++) {
+                packed[i * W + wd] = acc;
+                acc = 0u;
+            }
+        } else if (L & 7u) {
+            packed[i * W + (W - 1u)] = acc;
+        }
+        if (lengths) lengths[i] = pos;
+    }
+}
+
+// reads whose gathered barcode length differs from L are None (barcode_matching.rs:167-169; longer ones were vetted by
+// the host): undo whatever the matching kernel made of their row, counts included
+__global__ void __launch_bounds__(256) k_fix_lengths(uint32_t* __restrict__ results, const uint32_t* __restrict__ lengths,
+                                                     uint64_t n, uint32_t L, uint32_t S, unsigned long long* __restrict__ counts) {
+    const uint64_t total = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += total) {
+        if (__ldg(lengths + i) != L) {
+            const uint32_t r = results[i];
+            if (r != NONE) {
+                results[i] = NONE;
+                atomicAdd(&counts[r >> 16], ~0ull);  // - 1
+                atomicAdd(&counts[S], 1ull);
+            }
+        }
+    }
+}
+
+cudaError_t launch_pack_offsets(const OffsetSource& seg, uint64_t n, uint32_t L, uint32_t* d_packed, uint32_t* d_lengths,
+                                const LaunchGeometry& g, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const int grid = grid_for(k_pack_offsets, 256, 0, g, n);
+    k_pack_offsets<<<grid, 256, 0, stream>>>(seg, n, L, d_packed, d_lengths);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fix_lengths(uint32_t* d_results, const uint32_t* d_lengths, uint64_t n, uint32_t L, uint32_t S,
+                               unsigned long long* d_counts, const LaunchGeometry& g, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const int grid = grid_for(k_fix_lengths, 256, 0, g, n);
+    k_fix_lengths<<<grid, 256, 0, stream>>>(d_results, d_lengths, n, L, S, d_counts);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // result words -> u16 sample indices (0xFFFF = None): the 2-byte-per-read return format of the packed host call
 __global__ void __launch_bounds__(256) k_narrow_u16(const uint32_t* __restrict__ results, uint64_t n,
                                                     uint16_t* __restrict__ out) {

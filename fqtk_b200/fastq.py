@@ -1,0 +1,159 @@
+"""Raw FASTQ text in, assignments out — the ingest side of SURVEY 8f "next" #1 / #2 without a per-record host loop:
+
+    fqtk_b200_fastq_scan          where the records of an in-memory FASTQ chunk are (ReadSetIterator::next, demux.rs:288-342)
+    fqtk_b200_matcher_assign_fastq    the B segments gathered by offset and encoded ON THE DEVICE, then matched
+    fqtk_b200_matcher_route       stable per-sample partition of the read indices (demux.rs:970-975)
+
+`demux_fastq_batch` strings them together for one batch of lock-stepped FASTQ chunks and hands back the same DemuxResult as
+`demux.demux_batch`; only the final formatting of output records (header rewriting) touches records one by one.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from .demux import (FILE_TYPE_CODE, OUTPUT_ORDER, DemuxResult, TooFewBases, min_length, parse_read_structure)
+from .headers import write_header
+from .metrics import demux_metrics
+
+
+@dataclass
+class FastqIndex:
+    """Where the records of one FASTQ chunk are (fqtk_b200_fastq_scan)."""
+    chunk: np.ndarray          # uint8 view of the text
+    head_offsets: np.ndarray   # uint64[n]: '@' of every record
+    seq_offsets: np.ndarray    # uint64[n]: first base of every sequence line
+    seq_lengths: np.ndarray    # uint32[n]
+    consumed: int              # the byte after the last complete record
+
+    def __len__(self) -> int:
+        return int(self.seq_offsets.shape[0])
+
+    def header(self, i: int) -> bytes:
+        """Header line of record i without the '@' (and without a trailing carriage return)."""
+        lo, hi = int(self.head_offsets[i]) + 1, int(self.seq_offsets[i]) - 1
+        raw = self.chunk[lo:hi].tobytes()
+        return raw[:-1] if raw.endswith(b"\r") else raw
+
+    def bases(self, i: int, lo: int = 0, hi: int | None = None) -> bytes:
+        a = int(self.seq_offsets[i])
+        n = int(self.seq_lengths[i])
+        return self.chunk[a + lo:a + (n if hi is None else min(hi, n))].tobytes()
+
+    def quals(self, i: int, lo: int = 0, hi: int | None = None) -> bytes:
+        n = int(self.seq_lengths[i])
+        # sequence line, newline (and maybe '\r'), the '+' line, then the quality line of the same length
+        a = int(self.seq_offsets[i]) + n
+        text = self.chunk
+        while text[a] != 0x0A:
+            a += 1
+        a += 1
+        while text[a] != 0x0A:
+            a += 1
+        a += 1
+        return text[a + lo:a + (n if hi is None else min(hi, n))].tobytes()
+
+
+def scan(text, max_records: int | None = None) -> FastqIndex:
+    """fqtk_b200_fastq_scan on an in-memory, uncompressed FASTQ chunk (bytes / bytearray / uint8 array)."""
+    chunk = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else np.ascontiguousarray(text, np.uint8)
+    cap = max_records if max_records is not None else max(1, int(chunk.size) // 6 + 1)  # a record is >= 7 bytes: "@\nA\n+\n!\n"
+    head = np.empty(cap, dtype=np.uint64)
+    seq = np.empty(cap, dtype=np.uint64)
+    length = np.empty(cap, dtype=np.uint32)
+    n, consumed = C.c_uint64(), C.c_uint64()
+    _lib.check(_lib.lib().fqtk_b200_fastq_scan(chunk.ctypes.data, chunk.size, cap, head.ctypes.data, seq.ctypes.data,
+                                               length.ctypes.data, C.byref(n), C.byref(consumed)))
+    k = int(n.value)
+    return FastqIndex(chunk, head[:k].copy(), seq[:k].copy(), length[:k].copy(), int(consumed.value))
+
+
+def barcode_segments(structures: Sequence[Sequence[tuple]]) -> list[tuple[int, int, int]]:
+    """(source, offset, length | SEGMENT_REST) of every sample-barcode segment of the read structures, in
+    ReadSet::sample_barcode_sequence order (demux.rs:121-123)."""
+    out = []
+    for s, st in enumerate(structures):
+        pos = 0
+        for kind, n in st:
+            if kind == "B":
+                out.append((s, pos, _lib.SEGMENT_REST if n is None else n))
+            pos += 0 if n is None else n
+    return out
+
+
+def assign_fastq(matcher, indexes: Sequence[FastqIndex], segments: Sequence[tuple[int, int, int]]) -> np.ndarray:
+    """fqtk_b200_matcher_assign_fastq: result words for the reads of lock-stepped FASTQ chunks."""
+    n = len(indexes[0])
+    srcs = (_lib.FastqSource * len(indexes))()
+    for k, ix in enumerate(indexes):
+        assert len(ix) == n, "FASTQ sources out of sync"
+        srcs[k] = _lib.FastqSource(ix.chunk.ctypes.data, ix.chunk.size, ix.seq_offsets.ctypes.data, ix.seq_lengths.ctypes.data)
+    segs = (_lib.FastqSegment * len(segments))(*[_lib.FastqSegment(*s) for s in segments])
+    out = np.empty(n, dtype=np.uint32)
+    rc = _lib.lib().fqtk_b200_matcher_assign_fastq(matcher._h, srcs, len(indexes), segs, len(segments), n, out.ctypes.data)
+    if rc != _lib.OK:
+        from .barcode_matching import _raise
+
+        _raise(rc, getattr(matcher, "_sample0_id", None))
+    return out
+
+
+def demux_fastq_batch(matcher, sample_ids: Sequence[str], barcodes: Sequence[str], read_structures: Sequence[str],
+                      fastq_texts: Sequence[bytes], output_types: Sequence[str] = ("T",),
+                      unmatched_prefix: str = "unmatched", skip_too_few_bases: bool = False) -> DemuxResult:
+    """One batch of lock-stepped, uncompressed FASTQ chunks through scanner -> offset gather + match (GPU) -> routing (GPU)
+    -> per-sample appends.  Same result type and file naming as demux.demux_batch."""
+    structures = [parse_read_structure(s) for s in read_structures]
+    if len(structures) != len(fastq_texts):
+        raise ValueError("The same number of read structures should be given as FASTQs")  # demux.rs:709-717
+    idx = [scan(t) for t in fastq_texts]
+    n = len(idx[0])
+    if any(len(ix) != n for ix in idx):
+        raise ValueError("FASTQ sources out of sync")  # demux.rs:960-964
+    # the too-few-bases rule (demux.rs:298-315), vectorised over the batch
+    keep = np.ones(n, dtype=bool)
+    for st, ix in zip(structures, idx):
+        keep &= ix.seq_lengths >= min_length(st)
+    if not keep.all():
+        if not skip_too_few_bases:
+            i = int(np.nonzero(~keep)[0][0])
+            st, ix = next((st, ix) for st, ix in zip(structures, idx) if ix.seq_lengths[i] < min_length(st))
+            raise TooFewBases(f"Read {idx[0].header(i).decode(errors='replace')} had too few bases to demux "
+                              f"{int(ix.seq_lengths[i])} vs. {min_length(st)} needed in read structure.")
+        rows = np.nonzero(keep)[0]
+        idx = [FastqIndex(ix.chunk, ix.head_offsets[rows].copy(), ix.seq_offsets[rows].copy(), ix.seq_lengths[rows].copy(),
+                          ix.consumed) for ix in idx]
+    result = DemuxResult(skipped=int(n - keep.sum()))
+    S = len(sample_ids)
+    m = len(idx[0])
+    if m:
+        words = assign_fastq(matcher, idx, barcode_segments(structures))  # GPU: gather + encode + match, one call
+        order, offsets = matcher.route(words)                              # GPU: stable partition by sample
+    else:
+        order, offsets = np.zeros(0, np.uint32), np.zeros(S + 2, np.uint64)
+    kinds = [t for t in OUTPUT_ORDER if t in {x.upper() for x in output_types}]
+    for b in range(S + 1):
+        prefix = sample_ids[b] if b < S else unmatched_prefix
+        for j in order[int(offsets[b]):int(offsets[b + 1])]:
+            j = int(j)
+            segs = []  # (kind, bases, quals) of every segment of every input, in order
+            for st, ix in zip(structures, idx):
+                pos = 0
+                for kind, ln in st:
+                    hi = None if ln is None else pos + ln
+                    segs.append((kind, ix.bases(j, pos, hi), ix.quals(j, pos, hi)))
+                    pos = 0 if ln is None else pos + ln
+            header = idx[0].header(j)
+            sample_bcs = [s for k, s, _ in segs if k == "B"]
+            umis = [s for k, s, _ in segs if k == "M"]
+            for kind in kinds:
+                for t, (_, s, q) in enumerate([x for x in segs if x[0] == kind]):
+                    head = write_header(t + 1, header, sample_bcs, umis)[1:]
+                    result.files.setdefault(f"{prefix}.{FILE_TYPE_CODE[kind]}{t + 1}.fq.gz", []).append((head, s, q))
+    result.counts = np.diff(np.asarray(offsets, dtype=np.uint64)).astype(np.uint64)
+    result.metrics = demux_metrics(list(sample_ids), list(barcodes), [int(c) for c in result.counts], unmatched_prefix)
+    return result

@@ -172,6 +172,48 @@ FQTK_B200_API int fqtk_b200_matcher_assign_segments_device(fqtk_b200_matcher* m,
                                                            uint32_t n_segments, uint64_t n_reads,
                                                            uint32_t* d_results, void* stream);
 
+/* ---- barcodes straight out of raw FASTQ text (SURVEY 8f "next" #1 / #2: ReadSetIterator::next, demux.rs:288-342) ----
+ * fqtk_b200_fastq_scan finds the records of an in-memory, uncompressed 4-line FASTQ chunk: for record r the offset of
+ * its header line ('@' included; head_offsets may be NULL), the offset and length of its sequence line.  Only records
+ * that lie completely inside the chunk are reported; *consumed = the byte after the last of them (the caller carries the
+ * rest over to the next chunk).  '\r' before '\n' is not part of a line.  A record whose first line does not start with
+ * '@', whose third does not start with '+', or whose quality line differs in length from its sequence is an error
+ * (FQTK_B200_ERR_ARG, with the record number in the message).  Host only, no GPU involved. */
+FQTK_B200_API int fqtk_b200_fastq_scan(const uint8_t* chunk, uint64_t chunk_bytes, uint64_t max_records,
+                                       uint64_t* head_offsets, uint64_t* seq_offsets, uint32_t* seq_lengths,
+                                       uint64_t* n_records, uint64_t* consumed);
+/* One input FASTQ of the read set (demux.rs:945-966 walks the inputs in lock step): the chunk and the per-read tables
+ * fqtk_b200_fastq_scan filled for it.  All pointers are HOST pointers for fqtk_b200_matcher_assign_fastq and DEVICE
+ * pointers for ..._assign_fastq_device. */
+typedef struct {
+    const uint8_t* chunk;
+    uint64_t chunk_bytes;
+    const uint64_t* seq_offsets; /* n_reads */
+    const uint32_t* seq_lengths; /* n_reads; may be NULL for the device call when no segment of this source is REST */
+} fqtk_b200_fastq_source;
+/* One sample-barcode segment of a read structure: bytes [offset, offset + length) of the sequence line of `source`, or
+ * everything from `offset` on when length == FQTK_B200_SEGMENT_REST (a trailing `+B`).  Segments are concatenated in the
+ * order given — inputs in order, then segments in read order (ReadSet::sample_barcode_sequence, demux.rs:121-123). */
+#define FQTK_B200_SEGMENT_REST 0xFFFFFFFFu
+typedef struct {
+    uint32_t source;
+    uint32_t offset;
+    uint32_t length;
+} fqtk_b200_fastq_segment;
+/* The batch call on raw FASTQ text: the B segments are gathered by offset and encoded ON THE DEVICE (no dense barcode
+ * rows are built on the host), then matched like any batch.  Host form: ships every chunk and its tables, synchronous;
+ * a read that is too short for a segment fails the call like the reference's "too few bases" panic (demux.rs:309-315;
+ * filter such records out first to get --skip-reasons too-few-bases); barcodes whose gathered length differs from L
+ * follow BarcodeMatcher::assign (shorter: None; longer: FQTK_B200_ERR_LENGTH unless the no-call pre-filter fires).
+ * Device form: asynchronous on `stream`, no vetting (too-short / too-long barcodes come back None). */
+FQTK_B200_API int fqtk_b200_matcher_assign_fastq(fqtk_b200_matcher* m, const fqtk_b200_fastq_source* sources,
+                                                 uint32_t n_sources, const fqtk_b200_fastq_segment* segments,
+                                                 uint32_t n_segments, uint64_t n_reads, uint32_t* results);
+FQTK_B200_API int fqtk_b200_matcher_assign_fastq_device(fqtk_b200_matcher* m, const fqtk_b200_fastq_source* sources,
+                                                        uint32_t n_sources, const fqtk_b200_fastq_segment* segments,
+                                                        uint32_t n_segments, uint64_t n_reads, uint32_t* d_results,
+                                                        void* stream);
+
 /* ---- HBM-resident calls: DEVICE buffers, asynchronous on `stream` (a cudaStream_t, NULL = default) ----
  * `d_packed`: n_reads * W u32 words, read i at words [i*W, (i+1)*W), symbol k of a read in bits 4*(k%8) of its
  * word k/8 — the reference's own BitEnc layout (mod.rs:49-61, bitenc.rs:311-322).  `d_results`: n_reads u32.

@@ -601,6 +601,80 @@ def test_batched_pipeline_reference_end_to_end_vectors(kats, use_cache):
         assert int(out.counts.sum()) == len(case["inputs"][0])
 
 
+def fastq_text(records):
+    return "".join(f"@{h}\n{s}\n+\n{';' * len(s)}\n" for h, s in records).encode()
+
+
+@pytest.mark.parametrize("use_cache", MODES)
+def test_fastq_ingest_reference_end_to_end_vectors(kats, use_cache):
+    """The reference's five end-to-end demux vectors again, this time from raw FASTQ TEXT: scanner -> per-read offsets ->
+    B segments gathered and encoded on the GPU (fqtk_b200_matcher_assign_fastq) -> routing; no dense barcode rows and no
+    per-record loop on the way in."""
+    from fqtk_b200.fastq import demux_fastq_batch
+
+    for case in kats["demux_e2e"]:
+        S = len(case["barcodes"])
+        ids = [f"Sample{j:04d}" for j in range(S)]
+        texts = [fastq_text([(f"ex_{i}", b) for i, b in enumerate(col)]) for col in case["inputs"]]
+        with BarcodeMatcher(case["barcodes"], case["max_mismatches"], case["min_mismatch_delta"], use_cache) as m:
+            out = demux_fastq_batch(m, ids, case["barcodes"], case["read_structures"], texts, case["output_types"])
+        got = {name: [[h.decode(), s.decode()] for h, s, _ in recs] for name, recs in out.files.items()}
+        assert got == case["expect"], case["source"]
+        for recs in out.files.values():
+            assert all(q == b";" * len(s) for _, s, q in recs)
+        if "expect_counts" in case:
+            assert out.counts.tolist() == case["expect_counts"]
+        assert int(out.counts.sum()) == len(case["inputs"][0])
+
+
+def test_fastq_ingest_at_size_and_with_trailing_barcode_segments():
+    """Dual-index layout of cfg 3 from two raw index FASTQ chunks (I1, I2: 8B each) + a read FASTQ, 300 k read sets with
+    ragged headers: the device gather must give exactly the result words of dense barcode rows.  Then `+B` (the whole index
+    read is the barcode, variable length): shorter barcodes are None, longer ones follow BarcodeMatcher::assign's panic /
+    pre-filter rule, too-short reads fail like ReadSetIterator::next."""
+    from fqtk_b200 import fastq
+    from fqtk_b200.demux import parse_read_structure
+
+    cfg = synth.CONFIGS[3]
+    panel = synth.panel(cfg)
+    bcs = [bytes(r) for r in panel]
+    n = 300_007
+    reads = synth.reads_host(panel, cfg.seed_reads, 1234, n)
+    reads[::61, 2] = ord("n")
+    want, want_counts = oracle.OracleMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta).assign_batch(reads)
+    i1 = fastq_text([(f"r{i}:{'x' * (i % 13)} 1:N:0:0", bytes(reads[i, :8]).decode()) for i in range(n)])
+    i2 = fastq_text([(f"r{i} 2:N:0:0", bytes(reads[i, 8:]).decode() + "AC"[: i % 3]) for i in range(n)])
+    ix = [fastq.scan(i1), fastq.scan(i2)]
+    segs = fastq.barcode_segments([parse_read_structure("8B"), parse_read_structure("8B+S")])
+    with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, True) as m:
+        got = fastq.assign_fastq(m, ix, segs)
+        assert np.array_equal(got, want)
+        assert np.array_equal(m.counts(), want_counts)
+        # a read shorter than its segment: the reference panics in ReadSetIterator::next (demux.rs:309-315)
+        short = fastq.scan(fastq_text([("a", "ACGTACG")]))
+        with pytest.raises(_lib.Fqtk_b200Error, match="too few bases"):
+            fastq.assign_fastq(m, [short, short], segs)
+    # `+B`: variable-length barcodes
+    L = 8
+    bcs8 = [b"ACGTACGT", b"TTTTGGGG", b"CCCCAAAA"]
+    seqs = ["ACGTACGT", "ACGTACG", "TTTTGGGG", "ACGTACGTA"[:8], "NNNNNNNNNN", "CCCCAAAA", "CC"]
+    ix8 = [fastq.scan(fastq_text([(f"q{i}", s) for i, s in enumerate(seqs)]))]
+    rest = fastq.barcode_segments([parse_read_structure("+B")])
+    om = oracle.OracleMatcher(bcs8, 1, 1)
+    with BarcodeMatcher(bcs8, 1, 1, True) as m:
+        got = fastq.assign_fastq(m, ix8, rest)
+        for i, sq in enumerate(seqs):
+            w = int(got[i])
+            exp = om.assign(sq.encode())  # the literal assign(): short -> None, all-N longer read -> None by the pre-filter
+            assert (None if w == _lib.NONE else (w >> 16, (w >> 8) & 0xFF, w & 0xFF)) == \
+                (None if exp is None else (exp.best_match, exp.best_mismatches, exp.next_best_mismatches)), (i, sq)
+        assert int(m.counts().sum()) == len(seqs)
+        long_ix = [fastq.scan(fastq_text([("z", "ACGTACGTAC")]))]
+        with pytest.raises(MatcherPanic, match=r"length \(10\) differs from expected barcode \(ACGTACGT\) length \(8\)"):
+            fastq.assign_fastq(m, long_ix, rest)
+    assert L == 8
+
+
 def test_batched_pipeline_at_cfg1_scale():
     """cfg 1 (10 k single-end reads, 8B+T, 4 samples): every record lands in the file of the sample the oracle assigns,
     in input order, with the rewritten header; too-short reads are skipped and counted nowhere (demux.rs:2023-2073)."""

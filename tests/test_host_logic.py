@@ -317,3 +317,44 @@ def test_pack_host_is_encode_for_every_row():
         out = np.empty((n, W), dtype=np.uint32)
         _lib.check(_lib.lib().fqtk_b200_pack_host(wide.ctypes.data, n, L, L + 5, out.ctypes.data, 2))
         assert np.array_equal(out, got), L
+
+
+def test_fastq_scanner():
+    """fqtk_b200_fastq_scan: offsets / lengths of every complete 4-line record, carry-over of a record cut by the chunk
+    boundary, CRLF line ends, and the three malformed-record errors.  Host only."""
+    from fqtk_b200 import _lib, fastq
+
+    recs = [(f"r{i} 1:N:0:{i}", "ACGTN"[: 1 + i % 5] * (1 + i % 7), i) for i in range(1000)]
+    text = "".join(f"@{h}\n{s}\n+\n{'I' * len(s)}\n" for h, s, _ in recs).encode()
+    ix = fastq.scan(text)
+    assert len(ix) == 1000 and ix.consumed == len(text)
+    for i in (0, 1, 499, 999):
+        assert ix.header(i).decode() == recs[i][0]
+        assert ix.bases(i).decode() == recs[i][1] and ix.quals(i) == b"I" * len(recs[i][1])
+        assert int(ix.seq_lengths[i]) == len(recs[i][1])
+        assert text[int(ix.head_offsets[i])] == ord("@")
+    # a chunk boundary in the middle of a record: only whole records are reported, `consumed` says where to resume
+    for cut in (len(text) - 1, len(text) - 3, len(text) // 2, 5):
+        part = fastq.scan(text[:cut])
+        assert text[:part.consumed].count(b"\n") == 4 * len(part)
+        rest = fastq.scan(text[part.consumed:])
+        assert len(part) + len(rest) == 1000 and rest.consumed == len(text) - part.consumed
+    # max_records stops early
+    few = fastq.scan(text, max_records=10)
+    assert len(few) == 10 and few.consumed == int(ix.head_offsets[10])
+    # CRLF
+    crlf = fastq.scan(b"@a x\r\nACGT\r\n+\r\n!!!!\r\n")
+    assert len(crlf) == 1 and crlf.header(0) == b"a x" and crlf.bases(0) == b"ACGT" and crlf.quals(0) == b"!!!!"
+    assert len(fastq.scan(b"")) == 0
+    for bad, what in ((b"r\nAC\n+\n!!\n", "'@'"), (b"@r\nAC\n-\n!!\n", "'+'"), (b"@r\nAC\n+\n!\n", "lengths differ")):
+        with pytest.raises(_lib.Fqtk_b200Error, match=re.escape(what)):
+            fastq.scan(bad)
+
+
+def test_barcode_segments_of_read_structures():
+    from fqtk_b200 import _lib
+    from fqtk_b200.demux import parse_read_structure
+    from fqtk_b200.fastq import barcode_segments
+
+    st = [parse_read_structure(x) for x in ("8B92T", "10M8B7C100T", "+T", "3T+B")]
+    assert barcode_segments(st) == [(0, 0, 8), (1, 10, 8), (3, 3, _lib.SEGMENT_REST)]
