@@ -610,12 +610,12 @@ def measure_fastq(ctx, args, cfg, panel, matcher):
         rec[:, rec_head.size + w + 3:rec_head.size + 2 * w + 3] = ord("F")
         rec[:, -1] = ord("\n")
         texts.append(rec.reshape(-1))
+    bufs = [(pinned_array(n, np.uint64), pinned_array(n, np.uint32)) for _ in texts]
     t0 = time.perf_counter()
     tables = []
 
-    def scan_one(text):
-        seq = pinned_array(n, np.uint64)
-        ln = pinned_array(n, np.uint32)
+    def scan_one(job):
+        text, (seq, ln) = job
         k, used = C.c_uint64(), C.c_uint64()
         _lib.check(lib.fqtk_b200_fastq_scan(text.ctypes.data, text.size, n, None, seq.ctypes.data, ln.ctypes.data,
                                             C.byref(k), C.byref(used)))
@@ -623,7 +623,7 @@ def measure_fastq(ctx, args, cfg, panel, matcher):
         return seq, ln
 
     with ThreadPoolExecutor(len(texts)) as ex:
-        tables = list(ex.map(scan_one, texts))
+        tables = list(ex.map(scan_one, zip(texts, bufs)))
     scan_s = time.perf_counter() - t0
     srcs = (_lib.FastqSource * len(texts))()
     for k, (text, (seq, ln)) in enumerate(zip(texts, tables)):
