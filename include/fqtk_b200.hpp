@@ -104,6 +104,11 @@ class BarcodeMatcher {
         check(fqtk_b200_matcher_route(h_, results, n, order.data(), offsets.data()));
     }
     fqtk_b200_matcher* handle() { return h_; }
+    // same batch call for reads the host holds in BitEnc form (fqtk_b200_pack_host); either output may be null
+    void assign_batch_packed(const std::uint32_t* packed, std::uint64_t n, std::uint32_t* results,
+                             std::uint16_t* sample_index = nullptr) {
+        check(fqtk_b200_matcher_assign_batch_packed(h_, packed, n, results, sample_index));
+    }
 
   private:
     static void check(int rc) {
@@ -194,5 +199,50 @@ inline std::vector<DemuxMetric> demux_metrics(const std::vector<Sample>& samples
     }
     return rows;
 }
+
+// One matcher per GPU of the box behind one handle (fqtk_b200_group_*): contiguous shards of every batch, ONE count
+// table — what demux.rs:921-926 / 970-975 own, over several devices.  `devices` empty = every visible device.
+class MatcherGroup {
+  public:
+    MatcherGroup(const std::vector<Sample>& samples, std::uint8_t max_mismatches, std::uint8_t min_mismatch_delta,
+                 bool use_cache, const std::vector<int>& devices = {}) {
+        if (samples.empty()) throw Panic("Must provide at least one sample");
+        const std::size_t L = samples[0].barcode.size();
+        std::string panel;
+        for (const auto& s : samples) {
+            if (s.barcode.empty()) throw Panic("Sample barcode cannot be empty string");
+            if (s.barcode.size() != L) throw Panic("All barcodes must have the same length");
+            panel += s.barcode;
+        }
+        n_samples_ = samples.size();
+        const int rc = fqtk_b200_group_create(reinterpret_cast<const std::uint8_t*>(panel.data()), (std::uint32_t)samples.size(),
+                                              (std::uint32_t)L, max_mismatches, min_mismatch_delta, use_cache ? 1 : 0,
+                                              devices.empty() ? nullptr : devices.data(), (std::uint32_t)devices.size(),
+                                              nullptr, &g_);
+        if (rc != FQTK_B200_OK) throw Error(rc, fqtk_b200_last_error());
+    }
+    ~MatcherGroup() { fqtk_b200_group_destroy(g_); }
+    MatcherGroup(const MatcherGroup&) = delete;
+    MatcherGroup& operator=(const MatcherGroup&) = delete;
+
+    std::uint32_t size() const { return fqtk_b200_group_size(g_); }
+    void assign_batch(const std::uint8_t* rows, std::uint64_t n, std::uint64_t stride, std::uint32_t* results,
+                      const std::uint32_t* lengths = nullptr) {
+        const int rc = fqtk_b200_group_assign_batch(g_, rows, n, stride, lengths, results);
+        if (rc == FQTK_B200_ERR_LENGTH) throw Panic(fqtk_b200_last_error());
+        if (rc != FQTK_B200_OK) throw Error(rc, fqtk_b200_last_error());
+    }
+    std::vector<std::uint64_t> counts() {
+        std::vector<std::uint64_t> c(n_samples_ + 1);
+        const int rc = fqtk_b200_group_counts(g_, c.data());
+        if (rc != FQTK_B200_OK) throw Error(rc, fqtk_b200_last_error());
+        return c;
+    }
+    void reset_counts() { fqtk_b200_group_reset_counts(g_); }
+
+  private:
+    fqtk_b200_group* g_ = nullptr;
+    std::size_t n_samples_ = 0;
+};
 
 }  // namespace fqtk_b200

@@ -97,9 +97,38 @@ static void run(bool use_cache) {
     }
 }
 
+// the demux caller's loop (demux.rs:967-975) over a GROUP of matchers: three handles on device 0 (so that it also runs on a
+// one-GPU box) must fill results[] and ONE count table exactly like a single matcher
+static void run_group() {
+    const std::vector<std::string> bcs = {"AAAAAAAA", "CCCCCCCC", "GGGGGGGG", "GGGGGGTT"};
+    auto samples = barcodes_to_samples(bcs);
+    std::string rows;
+    const std::uint64_t n = 40000;
+    for (std::uint64_t i = 0; i < n; i++) {
+        std::string r = bcs[i % 4];
+        if (i % 7 == 0) r[i % 8] = 'N';
+        if (i % 11 == 0) r = "ACGTACGT";
+        rows += r;
+    }
+    std::vector<std::uint32_t> one(n), many(n);
+    BarcodeMatcher m(samples, 1, 2, true);
+    m.assign_batch(reinterpret_cast<const std::uint8_t*>(rows.data()), n, 8, one.data());
+    fqtk_b200::MatcherGroup g(samples, 1, 2, true, std::vector<int>{0, 0, 0});
+    CHECK(g.size() == 3);
+    g.assign_batch(reinterpret_cast<const std::uint8_t*>(rows.data()), n, 8, many.data());
+    CHECK(one == many);
+    CHECK(m.counts() == g.counts());
+    g.assign_batch(reinterpret_cast<const std::uint8_t*>(rows.data()), n, 8, many.data());
+    auto c1 = m.counts(), c2 = g.counts();
+    bool doubled = true;
+    for (std::size_t j = 0; j < c1.size(); j++) doubled = doubled && c2[j] == 2 * c1[j];
+    CHECK(doubled);
+}
+
 int main() {
     run(true);
     run(false);
+    run_group();
     if (failures) {
         std::fprintf(stderr, "%d check(s) failed\n", failures);
         return 1;
