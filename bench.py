@@ -203,12 +203,17 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(cfg_id, kernel):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists."""
+def ncu_traffic(cfg_id, kernel, n_launch):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists, scaled to the number of
+    reads THIS launch processes (a strong-scaling shard is a fraction of the captured launch)."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(f"cfg{cfg_id}_{kernel.split('<')[0]}")
+            d = json.load(open(p))
+            key = f"cfg{cfg_id}_{kernel.split('<')[0]}"
+            if key not in d:
+                return None
+            return int(d[key] * n_launch / d.get(key + "_reads", n_launch))
         except Exception:
             return None
     return None
@@ -444,7 +449,7 @@ def measure_config(ctx, args, cfg_id, steps, warmup, strong, cuckoo=-1, mode="au
     achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "achieved": round(achieved, 2), "peak": ctx.peak, "unit": "GB/s",
-        "frac": round(achieved / ctx.peak, 4), "traffic": ncu_traffic(cfg_id, kernel), "kernel": kernel,
+        "frac": round(achieved / ctx.peak, 4), "traffic": ncu_traffic(cfg_id, kernel, n), "kernel": kernel,
         "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_read": cfg.algorithmic_bytes_per_read,
         "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": ctx.peak_src,
     }

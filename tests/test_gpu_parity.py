@@ -512,6 +512,23 @@ def test_configs_full_size_properties(cfg_id):
     stream = torch.cuda.current_stream().cuda_stream
     d_packed = torch.empty((n, W), dtype=torch.int32, device="cuda")
     synth.reads_device(panel, cfg.seed_reads, 0, n, 0, d_packed.data_ptr(), stream)
+    # the rare paths of the table kernels at full N: windows of the stream are overwritten with
+    #   (a) 3 000 consecutive reads that ALL carry a no-call: every lane of a tile is odd at once (k_probe3's resolve-on-the
+    #       -spot branch, its stash overflowing; k_probe5's queue holding a whole tile),
+    #   (b) reads with IUPAC codes / junk symbols sprinkled over a long stretch (the stash / slow path with few lanes busy),
+    # and the batch ends 37 reads short of a tile boundary (the one-read-per-lane tail).
+    n -= 37
+    inject = {}
+    for first, span, kind in ((n // 2 + 5, 3_000, "burst"), (n // 5 + 11, 60_000, "sprinkle"), (n - 2_000, 2_000, "sprinkle")):
+        host = synth.reads_host(panel, cfg.seed_reads, first, span)
+        if kind == "burst":
+            host[np.arange(span), np.arange(span) % cfg.barcode_len] = ord("N")
+        else:
+            host[::7, 1] = ord("R")
+            host[3::11, cfg.barcode_len - 1] = ord("-")
+            host[5::13, 0] = ord("n")
+        inject[first] = host
+        d_packed[first:first + span] = torch.from_numpy(synth.pack_host(host).view(np.int32)).cuda()
     res_t = torch.empty(n, dtype=torch.int32, device="cuda")
     res_b = torch.empty(n, dtype=torch.int32, device="cuda")
     with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, True) as mt, \
@@ -532,11 +549,16 @@ def test_configs_full_size_properties(cfg_id):
         # strided sub-ranges against the oracle
         om = oracle.OracleMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, use_cache=True)
         span = 20_000
-        for first in (0, n // 3 + 17, n - span):
+        for first in (0, n // 3 + 17):
             host_reads = synth.reads_host(panel, cfg.seed_reads, first, span)
             want, _ = om.assign_batch(host_reads)
             got = res_t[first:first + span].cpu().numpy().view(np.uint32)
             assert np.array_equal(got, want), (cfg_id, first)
+        for first, host_reads in inject.items():  # the overwritten windows, against the oracle on what was written
+            want, _ = om.assign_batch(host_reads)
+            got = res_t[first:first + len(host_reads)].cpu().numpy().view(np.uint32)
+            assert np.array_equal(got, want), (cfg_id, first)
+            assert (want != _lib.NONE).any()
         # idempotence of the counters
         mt.assign_packed_device(d_packed.data_ptr(), n, res_t.data_ptr(), stream)
         torch.cuda.synchronize()

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (the .ncu-rep files stay on the box under /tmp: gpurun brings back at most 64 MiB; the summaries carry what is read here)
 # One gpurun session: GPU tests, bench, ncu launch list + full captures of the dominant kernels.  Outputs -> gpurun_out/$TAG.
 # usage: tools/gpu_session.sh [tag] [steps...]   steps default: tests bench launches ncu
 set -u
@@ -10,9 +11,9 @@ nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.max.mem,power.limi
 B="python bench.py --no-cpu-baseline --no-e2e --no-brute --no-configs --no-parity-check"
 cap() {  # name, kernel regex, bench args...
   name=$1; regex=$2; shift 2
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$regex -s 2 -c 1 -o "$OUT/prof_$name" -f $B --steps 2 --warmup 1 "$@" > "$OUT/ncu_$name.log" 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$regex -s 2 -c 1 -o "/tmp/prof_$name" -f $B --steps 2 --warmup 1 "$@" > "$OUT/ncu_$name.log" 2>&1
   echo "ncu $name rc=$?"
-  python tools/ncu_summary.py "$OUT/prof_$name.ncu-rep" --sass --min 0.3 > "$OUT/summary_$name.txt" 2>&1
+  python tools/ncu_summary.py "/tmp/prof_$name.ncu-rep" --sass --min 0.3 > "$OUT/summary_$name.txt" 2>&1
 }
 for s in $STEPS; do
   echo "=== $s ($(date +%T)) ==="
