@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-brute", action="store_true")
+    ap.add_argument("--no-routing", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg 2 / 4 / 5 entries of the line")
     ap.add_argument("--single-process", action="store_true",
                     help="ONE process driving --gpus N devices through the C ABI's group handle (fqtk_b200_group_*) "
@@ -826,7 +827,7 @@ def run_b200(args):
 
     # ---- per-sample routing of the batch, for the record ----
     routing = None
-    if not args.no_brute:
+    if not args.no_routing:
         matcher.assign_packed_device(d_packed.data_ptr(), n, d_res.data_ptr(), stream)
         d_order = torch.empty(n, dtype=torch.int32, device=dev)
         d_off = torch.zeros(cfg.n_samples + 2, dtype=torch.int64, device=dev)

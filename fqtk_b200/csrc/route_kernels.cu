@@ -26,6 +26,18 @@ constexpr int ROUTE_THREADS = 256;        // 8 warps per CTA
 constexpr int ROUTE_SCAN_THREADS = 1024;
 constexpr int ROUTE_UNROLL = 4;           // 32-read steps whose loads are issued together
 
+// result words are read once per pass: no L1 allocation
+FQ_D uint32_t ld_stream_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+FQ_D uint4 ld_stream_u4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 FQ_D uint32_t bucket_of_result(uint32_t r, uint32_t S) {
     const uint32_t b = r >> 16;
     return (r == NONE || b >= S) ? S : b;
@@ -315,6 +327,165 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_scatter_tile(const uint32_
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Tile version 2 (S + 2 buckets next to a 32 KB tile in shared memory, two CTAs per SM): the rank of a read among the
+// reads of its bucket in the same 32-read step comes from ONE shared-memory atomic instead of a ballot per bucket bit:
+// every lane ORs its lane bit into the warp-private cell {mask, count} of its bucket, the cell read back is the set
+// of lanes of the step in that bucket (rank = popc of the lower lanes) and the warp's running count of the bucket;
+// the group's first lane then clears the mask and advances the count.  Counting and ranking are one pass (the rank is
+// relative to the warp's 512-read chunk; the warp / bucket prefixes are added when the read is placed), the tile
+// leaves through shared memory as before so that every bucket's run is one contiguous burst.  A dummy bucket behind
+// the unmatched one takes the lanes past the end of the last tile, so the ranking loop has no predicates.
+// ------------------------------------------------------------------------------------------------------
+constexpr int R2_THREADS = 512;
+constexpr int R2_WARPS = R2_THREADS / 32;
+constexpr int R2_STEPS = RT_TILE / R2_THREADS;  // 32-read steps per warp and tile
+constexpr int R2_IDX_BITS = 13;                 // RT_TILE = 1 << 13
+static_assert(RT_TILE == (1 << R2_IDX_BITS), "tile-local index bits");
+
+// results -> per-CTA bucket counts, 128-bit loads (the CTA ranges are tile-aligned, so 16-byte alignment only
+// depends on the base pointer, checked by the host)
+__global__ void __launch_bounds__(R2_THREADS) k_route_hist_cta4(const uint32_t* __restrict__ results, uint64_t n, uint32_t S,
+                                                                uint32_t n_ctas, uint32_t* __restrict__ hist) {
+    extern __shared__ uint32_t s_tab[];  // [S + 1]
+    const uint32_t B = S + 1u;
+    for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) s_tab[b] = 0u;
+    __syncthreads();
+    uint64_t lo, hi;
+    cta_range(n, blockIdx.x, n_ctas, lo, hi);
+    const uint64_t hi4 = lo + ((hi - lo) & ~(uint64_t)3);
+    const uint4* v = reinterpret_cast<const uint4*>(results + lo);
+    const uint64_t n4 = (hi4 - lo) >> 2;
+    for (uint64_t base = 0; base < n4; base += (uint64_t)R2_THREADS * ROUTE_UNROLL) {
+        uint4 r[ROUTE_UNROLL];
+#pragma unroll
+        for (int u = 0; u < ROUTE_UNROLL; u++) {
+            const uint64_t i = base + (uint64_t)R2_THREADS * u + threadIdx.x;
+            r[u] = i < n4 ? ld_stream_u4(v + i) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < ROUTE_UNROLL; u++)
+            if (base + (uint64_t)R2_THREADS * u + threadIdx.x < n4) {
+                atomicAdd(&s_tab[bucket_of_result(r[u].x, S)], 1u);
+                atomicAdd(&s_tab[bucket_of_result(r[u].y, S)], 1u);
+                atomicAdd(&s_tab[bucket_of_result(r[u].z, S)], 1u);
+                atomicAdd(&s_tab[bucket_of_result(r[u].w, S)], 1u);
+            }
+    }
+    for (uint64_t i = hi4 + threadIdx.x; i < hi; i += R2_THREADS) atomicAdd(&s_tab[bucket_of_result(__ldg(results + i), S)], 1u);
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) hist[(size_t)b * n_ctas + blockIdx.x] = s_tab[b];
+}
+
+__global__ void __launch_bounds__(R2_THREADS, 2)
+    k_route_scatter_tile2(const uint32_t* __restrict__ results, uint64_t n, uint32_t S, uint32_t n_ctas,
+                          const uint32_t* __restrict__ hist, const unsigned long long* __restrict__ offsets,
+                          uint32_t* __restrict__ order) {
+    extern __shared__ uint32_t s_mem[];
+    const uint32_t B = S + 1u, B1 = B + 1u;  // bucket B = the dummy for lanes past the end of the batch
+    uint32_t* cursor = s_mem;                                    // [B1] next output slot of every bucket for this CTA
+    uint32_t* delta = cursor + B1;                               // [B1] cursor - first sorted-tile position (this tile)
+    uint32_t* part = delta + B1;                                 // [R2_WARPS] scan partials
+    uint2* cell = reinterpret_cast<uint2*>(part + R2_WARPS);     // [R2_WARPS][B1] {.x lanes of the step, .y count -> base}
+    uint32_t* sorted = reinterpret_cast<uint32_t*>(cell + (size_t)R2_WARPS * B1);  // [RT_TILE] bucket << 13 | index
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5, lane_bit = 1u << lane, lane_lt = lane_bit - 1u;
+    uint2* my = cell + (size_t)w * B1;
+
+    for (uint32_t b = threadIdx.x; b < B1; b += R2_THREADS)
+        cursor[b] = b < B ? (uint32_t)offsets[b] + hist[(size_t)b * n_ctas + blockIdx.x] : 0u;
+    for (uint32_t t = threadIdx.x; t < R2_WARPS * B1; t += R2_THREADS) cell[t] = make_uint2(0u, 0u);
+    uint64_t lo, hi;
+    cta_range(n, blockIdx.x, n_ctas, lo, hi);
+    const uint32_t per = (B1 + R2_THREADS - 1) / R2_THREADS;  // buckets per thread in the prefix phase
+    const uint32_t b_lo = min(threadIdx.x * per, B1), b_hi = min(b_lo + per, B1);
+
+    uint32_t r[R2_STEPS];  // this tile's result words, then bucket << 13 | rank inside the warp's chunk
+    if (lo < hi) {
+        const uint32_t tile_n = (uint32_t)min((uint64_t)RT_TILE, hi - lo);
+#pragma unroll
+        for (int st = 0; st < R2_STEPS; st++) {
+            const uint32_t idx = w * (R2_STEPS * 32u) + st * 32u + lane;
+            r[st] = idx < tile_n ? ld_stream_u32(results + lo + idx) : 0u;
+        }
+    }
+    __syncthreads();
+    for (uint64_t tile_lo = lo; tile_lo < hi; tile_lo += RT_TILE) {
+        const uint32_t tile_n = (uint32_t)min((uint64_t)RT_TILE, hi - tile_lo);
+        // 1: count and rank inside the warp's chunk
+#pragma unroll
+        for (int st = 0; st < R2_STEPS; st++) {
+            const uint32_t idx = w * (R2_STEPS * 32u) + st * 32u + lane;
+            const uint32_t b = idx < tile_n ? bucket_of_result(r[st], S) : B;
+            atomicOr(&my[b].x, lane_bit);
+            __syncwarp();
+            const uint2 c = my[b];
+            __syncwarp();
+            if ((c.x & lane_lt) == 0u) my[b] = make_uint2(0u, c.y + __popc(c.x));
+            __syncwarp();
+            r[st] = b << R2_IDX_BITS | (c.y + __popc(c.x & lane_lt));
+        }
+        __syncthreads();
+        // 2: per bucket the exclusive prefix over the warps, per tile the exclusive prefix over the buckets
+        uint32_t mine = 0;
+        for (uint32_t b = b_lo; b < b_hi; b++)
+#pragma unroll
+            for (int ww = 0; ww < R2_WARPS; ww++) mine += cell[(size_t)ww * B1 + b].y;
+        uint32_t incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+            if (lane >= (uint32_t)off) incl += v;
+        }
+        if (lane == 31u) part[w] = incl;
+        __syncthreads();
+        uint32_t run = incl - mine;
+        for (uint32_t k = 0; k < w; k++) run += part[k];
+        for (uint32_t b = b_lo; b < b_hi; b++) {
+            const uint32_t base = run;
+#pragma unroll
+            for (int ww = 0; ww < R2_WARPS; ww++) {
+                const uint32_t c = cell[(size_t)ww * B1 + b].y;
+                cell[(size_t)ww * B1 + b].y = run;
+                run += c;
+            }
+            const uint32_t cur = cursor[b];
+            delta[b] = cur - base;
+            cursor[b] = cur + (run - base);
+        }
+        __syncthreads();
+        // 3: place (bucket, tile index) at its sorted position
+#pragma unroll
+        for (int st = 0; st < R2_STEPS; st++) {
+            const uint32_t idx = w * (R2_STEPS * 32u) + st * 32u + lane;
+            const uint32_t b = r[st] >> R2_IDX_BITS, rank = r[st] & (RT_TILE - 1u);
+            sorted[my[b].y + rank] = b << R2_IDX_BITS | idx;
+        }
+        __syncthreads();
+        // the next tile's words are on their way while this one leaves
+        {
+            const uint64_t next_lo = tile_lo + RT_TILE;
+            const uint32_t next_n = next_lo < hi ? (uint32_t)min((uint64_t)RT_TILE, hi - next_lo) : 0u;
+#pragma unroll
+            for (int st = 0; st < R2_STEPS; st++) {
+                const uint32_t idx = w * (R2_STEPS * 32u) + st * 32u + lane;
+                r[st] = idx < next_n ? ld_stream_u32(results + next_lo + idx) : 0u;
+            }
+        }
+        // 4: every bucket's run leaves as one contiguous burst at the CTA's cursor; cells back to zero
+        for (uint32_t pos = threadIdx.x; pos < tile_n; pos += R2_THREADS) {
+            const uint32_t v = sorted[pos];
+            order[delta[v >> R2_IDX_BITS] + pos] = (uint32_t)tile_lo + (v & (RT_TILE - 1u));
+        }
+        for (uint32_t t = threadIdx.x; t < R2_WARPS * B1; t += R2_THREADS) cell[t].y = 0u;
+        __syncthreads();
+    }
+}
+
+static size_t route_tile2_smem(uint32_t S) {
+    const size_t B1 = S + 2u;
+    return (2 * B1 + R2_WARPS) * 4 + (size_t)R2_WARPS * B1 * 8 + (size_t)RT_TILE * 4;
+}
+
 static size_t route_tile_smem(uint32_t S) {
     const size_t B = S + 1u;
     return (3 * B + (size_t)RT_WARPS * B + RT_THREADS) * 4 + (size_t)RT_TILE * 2 * 2;
@@ -323,13 +494,25 @@ static size_t route_tile_smem(uint32_t S) {
 struct RoutePlan {
     uint32_t n_warps, warps_per_cta, grid, bucket_bits;  // n_warps = histogram columns (warps, or CTAs in tile mode)
     size_t smem;
-    bool tile;
+    bool tile, tile2;
 };
 
 static RoutePlan plan_route(uint64_t n, uint32_t S, const LaunchGeometry& g) {
     RoutePlan p{};
     p.bucket_bits = 1;
     while ((1u << p.bucket_bits) < S + 1u) p.bucket_bits++;
+    if (!getenv("FQTK_B200_ROUTE_V1") && !getenv("FQTK_B200_ROUTE_V2") && S + 2u <= (1u << (32 - R2_IDX_BITS)) &&
+        route_tile2_smem(S) + 1024 <= (size_t)g.max_smem_optin) {
+        p.tile = p.tile2 = true;
+        p.smem = route_tile2_smem(S);
+        const uint64_t tiles = (n + RT_TILE - 1) / RT_TILE;
+        const uint32_t per_sm = 2 * (p.smem + 1024) <= (size_t)g.max_smem_optin + 1024 ? 2 : 1;
+        uint64_t ctas = (uint64_t)g.sm_count * per_sm;
+        if (ctas > tiles) ctas = tiles ? tiles : 1;
+        p.n_warps = p.grid = (uint32_t)ctas;
+        p.warps_per_cta = R2_WARPS;
+        return p;
+    }
     if (S + 1u <= RT_MAX_BUCKETS && route_tile_smem(S) + 1024 <= (size_t)g.max_smem_optin && !getenv("FQTK_B200_ROUTE_V1")) {
         p.tile = true;
         p.smem = route_tile_smem(S);
@@ -379,6 +562,22 @@ cudaError_t launch_route(const uint32_t* d_results, uint64_t n, uint32_t S, uint
     uint32_t* hist = reinterpret_cast<uint32_t*>(d_workspace);
     unsigned long long* totals =
         reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(d_workspace) + (((size_t)(S + 1u) * p.n_warps * 4u + 7) & ~(size_t)7));
+    if (p.tile2) {
+        const size_t hsmem = (size_t)(S + 1u) * 4u;
+        cudaFuncSetAttribute(k_route_scatter_tile2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+        if ((reinterpret_cast<uintptr_t>(d_results) & 15u) == 0)
+            k_route_hist_cta4<<<p.grid, R2_THREADS, hsmem, stream>>>(d_results, n, S, p.n_warps, hist);
+        else
+            k_route_hist_cta<<<p.grid, RT_THREADS, hsmem, stream>>>(d_results, n, S, p.n_warps, hist);
+        count_launch();
+        k_route_scan_rows<<<S + 1u, ROUTE_SCAN_THREADS, 0, stream>>>(hist, p.n_warps, totals);
+        count_launch();
+        k_route_scan_totals<<<1, ROUTE_SCAN_THREADS, 0, stream>>>(totals, S + 1u, d_offsets);
+        count_launch();
+        k_route_scatter_tile2<<<p.grid, R2_THREADS, p.smem, stream>>>(d_results, n, S, p.n_warps, hist, d_offsets, d_order);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (p.tile) {
         const size_t hsmem = (size_t)(S + 1u) * 4u;
         cudaFuncSetAttribute(k_route_scatter_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);

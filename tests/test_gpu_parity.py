@@ -831,6 +831,40 @@ def test_route_is_the_stable_partition(cfg_id, n):
         assert o0.size == 0 and not f0.any()
 
 
+@pytest.mark.parametrize("S", [1, 5, 384, 1000, 1536, 3000])
+def test_route_kernel_versions_and_edge_sizes(S):
+    """Routing only looks at result words, so any word stream drives it: skewed buckets, None words, sizes around the
+    8 192-read tile and the 32-read step, a result pointer that is not 16-byte aligned (scalar histogram loads).
+    S = 1 ... 1 000 take the mask-rank tile kernel, 1 536 the ballot tile kernel, 3 000 the per-warp version."""
+    torch = torch_cuda()
+    rng = np.random.default_rng(1000 + S)
+    panel = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=(S, 12))
+    panel = np.unique(panel, axis=0)
+    assert panel.shape[0] >= min(S, 3000) - 8
+    S = panel.shape[0]
+    stream = torch.cuda.current_stream().cuda_stream
+    with BarcodeMatcher([bytes(r) for r in panel], 0, 0, use_cache=False) as m:
+        for n in (1, 31, 32, 33, 511, 8191, 8192, 8193, 3 * 8192 + 5, 300 * 8192 + 17, 2_500_003):
+            b = rng.integers(0, S, size=n)
+            b[rng.random(n) < 0.15] = 0          # one heavy sample
+            none = rng.random(n) < 0.1
+            res = ((b.astype(np.uint32) << 16) | rng.integers(0, 3, size=n).astype(np.uint32) << 8 | 2).astype(np.uint32)
+            res[none] = _lib.NONE
+            want_order, want_offsets = expected_route(res, S)
+            order, offsets = m.route(res)
+            assert np.array_equal(offsets, want_offsets), (S, n)
+            assert np.array_equal(order, want_order), (S, n)
+            # device entry with a pointer 4 bytes past a 16-byte boundary
+            d = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+            d[1:] = torch.from_numpy(res.view(np.int32)).cuda()
+            d_order = torch.empty(n, dtype=torch.int32, device="cuda")
+            d_off = torch.zeros(S + 2, dtype=torch.int64, device="cuda")
+            m.route_device(d.data_ptr() + 4, n, d_order.data_ptr(), d_off.data_ptr(), stream)
+            torch.cuda.synchronize()
+            assert np.array_equal(d_order.cpu().numpy().view(np.uint32), want_order), (S, n, "unaligned")
+            assert np.array_equal(d_off.cpu().numpy().astype(np.uint64), want_offsets)
+
+
 def test_route_full_size_properties():
     """cfg 3 at 500 M reads on the device: order is a permutation, every bucket run is ascending and homogeneous."""
     torch = torch_cuda()
