@@ -841,7 +841,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         rms = e0.elapsed_time(e1) / 3
         assert int(d_off[-1].item()) == n
-        routing = {"kernels": "k_route_hist + k_route_scan_* + k_route_scatter", "reads": n, "ms": round(rms, 4),
+        routing = {"kernels": "k_route_hist_cta4 + k_route_scan_* + k_route_scatter_tile2", "reads": n, "ms": round(rms, 4),
                    "value": round(n / (rms * 1e-3) / 1e6, 2), "unit": UNIT + " per GPU",
                    "algorithmic_bytes_per_read": 12,
                    "roofline_frac": round(n * 12 / (rms * 1e-3) / 1e9 / peak, 4)}

@@ -377,28 +377,120 @@ __global__ void __launch_bounds__(R2_THREADS) k_route_hist_cta4(const uint32_t* 
     for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) hist[(size_t)b * n_ctas + blockIdx.x] = s_tab[b];
 }
 
+struct Tile2Smem {
+    uint32_t *cursor, *delta, *part, *mask, *cnt, *sorted;
+};
+
+// one tile of k_route_scatter_tile2; FULL = all RT_TILE reads exist here and in the tile that is prefetched
+template <bool FULL>
+FQ_D void route_tile2(const Tile2Smem& sm, const uint32_t* __restrict__ results, uint32_t* __restrict__ order, uint32_t S,
+                      uint64_t tile_lo, uint32_t tile_n, uint32_t next_n, uint32_t (&r)[R2_STEPS]) {
+    const uint32_t B = S + 1u, B1 = B + 1u;
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5, lane_bit = 1u << lane, lane_lt = lane_bit - 1u;
+    uint32_t* my_mask = sm.mask + w * B1;
+    uint32_t* my_cnt = sm.cnt + w * B1;
+    const uint32_t per = (B1 + R2_THREADS - 1) / R2_THREADS;  // buckets per thread in the prefix phase
+    const uint32_t b_lo = min(threadIdx.x * per, B1), b_hi = min(b_lo + per, B1);
+    // 1: count and rank inside the warp's chunk: the lanes of the step in my bucket come back from the mask cell, the
+    //    group's first lane takes the warp's running count of the bucket with one returning atomic and hands it round
+#pragma unroll
+    for (int st = 0; st < R2_STEPS; st++) {
+        const uint32_t idx = w * (R2_STEPS * 32u) + st * 32u + lane;
+        const uint32_t b = (FULL || idx < tile_n) ? bucket_of_result(r[st], S) : B;
+        atomicOr(&my_mask[b], lane_bit);
+        __syncwarp();
+        const uint32_t m = my_mask[b];
+        __syncwarp();
+        uint32_t c = 0;
+        if ((m & lane_lt) == 0u) {
+            c = atomicAdd(&my_cnt[b], (uint32_t)__popc(m));
+            my_mask[b] = 0u;
+        }
+        __syncwarp();
+        c = __shfl_sync(0xFFFFFFFFu, c, __ffs(m) - 1);
+        r[st] = b << R2_IDX_BITS | (c + __popc(m & lane_lt));
+    }
+    __syncthreads();
+    // 2: per bucket the exclusive prefix over the warps, per tile the exclusive prefix over the buckets
+    uint32_t mine = 0;
+    for (uint32_t b = b_lo; b < b_hi; b++)
+#pragma unroll
+        for (int ww = 0; ww < R2_WARPS; ww++) mine += sm.cnt[ww * B1 + b];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= (uint32_t)off) incl += v;
+    }
+    if (lane == 31u) sm.part[w] = incl;
+    __syncthreads();
+    uint32_t run = incl - mine;
+    for (uint32_t k = 0; k < w; k++) run += sm.part[k];
+    for (uint32_t b = b_lo; b < b_hi; b++) {
+        const uint32_t base = run;
+#pragma unroll
+        for (int ww = 0; ww < R2_WARPS; ww++) {
+            const uint32_t c = sm.cnt[ww * B1 + b];
+            sm.cnt[ww * B1 + b] = run;
+            run += c;
+        }
+        const uint32_t cur = sm.cursor[b];
+        sm.delta[b] = cur - base;
+        sm.cursor[b] = cur + (run - base);
+    }
+    __syncthreads();
+    // 3: place (bucket, tile index) at its sorted position
+#pragma unroll
+    for (int st = 0; st < R2_STEPS; st++) {
+        const uint32_t idx = w * (R2_STEPS * 32u) + st * 32u + lane;
+        const uint32_t b = r[st] >> R2_IDX_BITS, rank = r[st] & (RT_TILE - 1u);
+        sm.sorted[my_cnt[b] + rank] = b << R2_IDX_BITS | idx;
+    }
+    // the next tile's words are on their way while this one leaves
+#pragma unroll
+    for (int st = 0; st < R2_STEPS; st++) {
+        const uint32_t idx = w * (R2_STEPS * 32u) + st * 32u + lane;
+        r[st] = (FULL || idx < next_n) ? ld_stream_u32(results + tile_lo + RT_TILE + idx) : 0u;
+    }
+    __syncthreads();
+    // 4: every bucket's run leaves as one contiguous burst at the CTA's cursor; counts back to zero
+    if (FULL) {
+#pragma unroll
+        for (int k = 0; k < R2_STEPS; k++) {
+            const uint32_t pos = k * R2_THREADS + threadIdx.x;
+            const uint32_t v = sm.sorted[pos];
+            order[sm.delta[v >> R2_IDX_BITS] + pos] = (uint32_t)tile_lo + (v & (RT_TILE - 1u));
+        }
+    } else {
+        for (uint32_t pos = threadIdx.x; pos < tile_n; pos += R2_THREADS) {
+            const uint32_t v = sm.sorted[pos];
+            order[sm.delta[v >> R2_IDX_BITS] + pos] = (uint32_t)tile_lo + (v & (RT_TILE - 1u));
+        }
+    }
+    for (uint32_t t = threadIdx.x; t < R2_WARPS * B1; t += R2_THREADS) sm.cnt[t] = 0u;
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(R2_THREADS, 2)
     k_route_scatter_tile2(const uint32_t* __restrict__ results, uint64_t n, uint32_t S, uint32_t n_ctas,
                           const uint32_t* __restrict__ hist, const unsigned long long* __restrict__ offsets,
                           uint32_t* __restrict__ order) {
     extern __shared__ uint32_t s_mem[];
     const uint32_t B = S + 1u, B1 = B + 1u;  // bucket B = the dummy for lanes past the end of the batch
-    uint32_t* cursor = s_mem;                                    // [B1] next output slot of every bucket for this CTA
-    uint32_t* delta = cursor + B1;                               // [B1] cursor - first sorted-tile position (this tile)
-    uint32_t* part = delta + B1;                                 // [R2_WARPS] scan partials
-    uint2* cell = reinterpret_cast<uint2*>(part + R2_WARPS);     // [R2_WARPS][B1] {.x lanes of the step, .y count -> base}
-    uint32_t* sorted = reinterpret_cast<uint32_t*>(cell + (size_t)R2_WARPS * B1);  // [RT_TILE] bucket << 13 | index
-    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5, lane_bit = 1u << lane, lane_lt = lane_bit - 1u;
-    uint2* my = cell + (size_t)w * B1;
+    Tile2Smem sm;
+    sm.cursor = s_mem;                       // [B1] next output slot of every bucket for this CTA
+    sm.delta = sm.cursor + B1;               // [B1] cursor - first sorted-tile position (this tile)
+    sm.part = sm.delta + B1;                 // [R2_WARPS] scan partials
+    sm.mask = sm.part + R2_WARPS;            // [R2_WARPS][B1] lanes of the current step per bucket
+    sm.cnt = sm.mask + R2_WARPS * B1;        // [R2_WARPS][B1] reads of the warp's chunk per bucket -> first sorted position
+    sm.sorted = sm.cnt + R2_WARPS * B1;      // [RT_TILE] bucket << 13 | tile index
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
 
     for (uint32_t b = threadIdx.x; b < B1; b += R2_THREADS)
-        cursor[b] = b < B ? (uint32_t)offsets[b] + hist[(size_t)b * n_ctas + blockIdx.x] : 0u;
-    for (uint32_t t = threadIdx.x; t < R2_WARPS * B1; t += R2_THREADS) cell[t] = make_uint2(0u, 0u);
+        sm.cursor[b] = b < B ? (uint32_t)offsets[b] + hist[(size_t)b * n_ctas + blockIdx.x] : 0u;
+    for (uint32_t t = threadIdx.x; t < 2u * R2_WARPS * B1; t += R2_THREADS) sm.mask[t] = 0u;  // masks and counts
     uint64_t lo, hi;
     cta_range(n, blockIdx.x, n_ctas, lo, hi);
-    const uint32_t per = (B1 + R2_THREADS - 1) / R2_THREADS;  // buckets per thread in the prefix phase
-    const uint32_t b_lo = min(threadIdx.x * per, B1), b_hi = min(b_lo + per, B1);
-
     uint32_t r[R2_STEPS];  // this tile's result words, then bucket << 13 | rank inside the warp's chunk
     if (lo < hi) {
         const uint32_t tile_n = (uint32_t)min((uint64_t)RT_TILE, hi - lo);
@@ -410,80 +502,19 @@ __global__ void __launch_bounds__(R2_THREADS, 2)
     }
     __syncthreads();
     for (uint64_t tile_lo = lo; tile_lo < hi; tile_lo += RT_TILE) {
-        const uint32_t tile_n = (uint32_t)min((uint64_t)RT_TILE, hi - tile_lo);
-        // 1: count and rank inside the warp's chunk
-#pragma unroll
-        for (int st = 0; st < R2_STEPS; st++) {
-            const uint32_t idx = w * (R2_STEPS * 32u) + st * 32u + lane;
-            const uint32_t b = idx < tile_n ? bucket_of_result(r[st], S) : B;
-            atomicOr(&my[b].x, lane_bit);
-            __syncwarp();
-            const uint2 c = my[b];
-            __syncwarp();
-            if ((c.x & lane_lt) == 0u) my[b] = make_uint2(0u, c.y + __popc(c.x));
-            __syncwarp();
-            r[st] = b << R2_IDX_BITS | (c.y + __popc(c.x & lane_lt));
+        const uint64_t left = hi - tile_lo;
+        if (left >= 2u * RT_TILE) {
+            route_tile2<true>(sm, results, order, S, tile_lo, RT_TILE, RT_TILE, r);
+        } else {
+            const uint32_t tile_n = (uint32_t)min((uint64_t)RT_TILE, left);
+            route_tile2<false>(sm, results, order, S, tile_lo, tile_n, (uint32_t)(left - tile_n), r);
         }
-        __syncthreads();
-        // 2: per bucket the exclusive prefix over the warps, per tile the exclusive prefix over the buckets
-        uint32_t mine = 0;
-        for (uint32_t b = b_lo; b < b_hi; b++)
-#pragma unroll
-            for (int ww = 0; ww < R2_WARPS; ww++) mine += cell[(size_t)ww * B1 + b].y;
-        uint32_t incl = mine;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-            if (lane >= (uint32_t)off) incl += v;
-        }
-        if (lane == 31u) part[w] = incl;
-        __syncthreads();
-        uint32_t run = incl - mine;
-        for (uint32_t k = 0; k < w; k++) run += part[k];
-        for (uint32_t b = b_lo; b < b_hi; b++) {
-            const uint32_t base = run;
-#pragma unroll
-            for (int ww = 0; ww < R2_WARPS; ww++) {
-                const uint32_t c = cell[(size_t)ww * B1 + b].y;
-                cell[(size_t)ww * B1 + b].y = run;
-                run += c;
-            }
-            const uint32_t cur = cursor[b];
-            delta[b] = cur - base;
-            cursor[b] = cur + (run - base);
-        }
-        __syncthreads();
-        // 3: place (bucket, tile index) at its sorted position
-#pragma unroll
-        for (int st = 0; st < R2_STEPS; st++) {
-            const uint32_t idx = w * (R2_STEPS * 32u) + st * 32u + lane;
-            const uint32_t b = r[st] >> R2_IDX_BITS, rank = r[st] & (RT_TILE - 1u);
-            sorted[my[b].y + rank] = b << R2_IDX_BITS | idx;
-        }
-        __syncthreads();
-        // the next tile's words are on their way while this one leaves
-        {
-            const uint64_t next_lo = tile_lo + RT_TILE;
-            const uint32_t next_n = next_lo < hi ? (uint32_t)min((uint64_t)RT_TILE, hi - next_lo) : 0u;
-#pragma unroll
-            for (int st = 0; st < R2_STEPS; st++) {
-                const uint32_t idx = w * (R2_STEPS * 32u) + st * 32u + lane;
-                r[st] = idx < next_n ? ld_stream_u32(results + next_lo + idx) : 0u;
-            }
-        }
-        // 4: every bucket's run leaves as one contiguous burst at the CTA's cursor; cells back to zero
-        for (uint32_t pos = threadIdx.x; pos < tile_n; pos += R2_THREADS) {
-            const uint32_t v = sorted[pos];
-            order[delta[v >> R2_IDX_BITS] + pos] = (uint32_t)tile_lo + (v & (RT_TILE - 1u));
-        }
-        for (uint32_t t = threadIdx.x; t < R2_WARPS * B1; t += R2_THREADS) cell[t].y = 0u;
-        __syncthreads();
     }
 }
 
 static size_t route_tile2_smem(uint32_t S) {
     const size_t B1 = S + 2u;
-    return (2 * B1 + R2_WARPS) * 4 + (size_t)R2_WARPS * B1 * 8 + (size_t)RT_TILE * 4;
+    return (2 * B1 + R2_WARPS) * 4 + (size_t)R2_WARPS * B1 * 8 + (size_t)RT_TILE * 4;  // mask table + counts
 }
 
 static size_t route_tile_smem(uint32_t S) {
