@@ -36,6 +36,8 @@ SYMBOLS = [
     "fqtk_b200_group_assign_batch_packed", "fqtk_b200_group_assign_packed_device", "fqtk_b200_group_counts",
     "fqtk_b200_group_reset_counts", "fqtk_b200_fastq_scan", "fqtk_b200_matcher_assign_fastq",
     "fqtk_b200_matcher_assign_fastq_device",
+    "fqtk_b200_bgzf_create", "fqtk_b200_bgzf_destroy", "fqtk_b200_bgzf_chunk_bytes", "fqtk_b200_bgzf_bound",
+    "fqtk_b200_bgzf_compress", "fqtk_b200_bgzf_compress_device",
 ]
 
 
@@ -142,6 +144,12 @@ def lib() -> C.CDLL:
                                                      C.c_uint64, vp]),
         "fqtk_b200_matcher_assign_fastq_device": (C.c_int, [vp, C.POINTER(FastqSource), C.c_uint32, C.POINTER(FastqSegment),
                                                             C.c_uint32, C.c_uint64, vp, vp]),
+        "fqtk_b200_bgzf_create": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(vp)]),
+        "fqtk_b200_bgzf_destroy": (None, [vp]),
+        "fqtk_b200_bgzf_chunk_bytes": (C.c_uint64, [vp]),
+        "fqtk_b200_bgzf_bound": (C.c_uint64, [C.c_uint64]),
+        "fqtk_b200_bgzf_compress": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, vp, C.c_uint64, u64p]),
+        "fqtk_b200_bgzf_compress_device": (C.c_int, [vp, vp, C.c_uint64, C.c_int, vp, C.c_uint64, vp, vp]),
         "fqtk_b200_synth_panel": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
         "fqtk_b200_synth_reads_host": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, vp]),
         "fqtk_b200_synth_reads_device": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, vp]),

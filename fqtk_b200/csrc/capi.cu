@@ -507,6 +507,15 @@ int build_g4_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, const st
     const uint64_t buckets64 = std::max<uint64_t>(16, (uint64_t)((double)ent.size() / (8 * load)) + 1);
     if (buckets64 >= (1ull << 28)) return 1;
     const uint32_t n_buckets = (uint32_t)buckets64;
+    // insertion order: the closer a key is to its barcode, the more reads carry it (exact barcodes first), so the keys
+    // that end up in an overflow bucket are the rare ones; None candidates last
+    std::vector<uint32_t> insert_order(ent.size());
+    for (size_t t = 0; t < ent.size(); t++) insert_order[t] = (uint32_t)t;
+    std::stable_sort(insert_order.begin(), insert_order.end(), [&](uint32_t a, uint32_t b) {
+        const uint32_t ka = ent[a].word == fq::NONE ? 256u : ((ent[a].word >> 8) & 0xFFu);
+        const uint32_t kb = ent[b].word == fq::NONE ? 256u : ((ent[b].word >> 8) & 0xFFu);
+        return ka < kb;
+    });
     std::vector<uint32_t> table;
     uint32_t seed = 0;
     uint64_t slow_keys = 0;
@@ -514,7 +523,8 @@ int build_g4_w(fqtk_b200_matcher* m, const std::vector<uint32_t>& keys, const st
     for (uint32_t attempt = 0; attempt < 8 && !built; attempt++) {
         seed = attempt * 0x632BE5ABu;
         table.assign((size_t)n_buckets * 8, 0xFFFFFFFFu);
-        for (size_t t = 0; t < ent.size(); t++) {
+        for (size_t ti = 0; ti < ent.size(); ti++) {
+            const size_t t = insert_order[ti];
             uint32_t b, fpp;
             fq::g4_hashes<W>(ent[t].w, seed, n_buckets, b, fpp);
             fpp &= 0u - (1u << fp_shift);  // the fingerprint: top fp_bits of the second hash, in place

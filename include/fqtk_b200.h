@@ -298,6 +298,28 @@ FQTK_B200_API int fqtk_b200_device_count(void);
 FQTK_B200_API int fqtk_b200_host_alloc(void** ptr, size_t bytes);
 FQTK_B200_API int fqtk_b200_host_free(void* ptr);
 
+/* ---- BGZF output compression (SURVEY 8f "next" #4; replaces the reference's pooled BGZF writers) ----
+ * src/bin/commands/demux.rs:755-798 builds `PoolBuilder::<_, BgzfCompressor>` (pooled-writer 0.4.0 -> bgzf crate ->
+ * libdeflate) with `compression_level` (demux.rs:641-643, default 5): every writer buffers 65 280 bytes (the bgzf crate's
+ * BGZF_BLOCK_SIZE), each full buffer becomes ONE gzip member with the `BC` extra field (SAM spec 4.1), the file ends with
+ * the 28-byte EOF block.  This entry does the same for one writer's bytes: input cut every 65 280 bytes, one member per
+ * piece (LZ77 + dynamic Huffman on the device, a stored block when that does not shrink the piece), members back to back
+ * in input order, optionally the EOF block.  level 0 = stored blocks only (as libdeflate), 1..12 = compressed (one
+ * strategy; the level only sets the header's XFL byte).  The deflate bytes are not libdeflate's (no two implementations
+ * agree); every member inflates to its piece and the CRC32 / ISIZE / BSIZE fields are exact.
+ * A handle owns the device buffers for chunks of `chunk_bytes` input bytes (0 = 64 MiB); not thread-safe. */
+typedef struct fqtk_b200_bgzf fqtk_b200_bgzf;
+FQTK_B200_API int fqtk_b200_bgzf_create(int device, uint64_t chunk_bytes, fqtk_b200_bgzf** out);
+FQTK_B200_API void fqtk_b200_bgzf_destroy(fqtk_b200_bgzf* z);
+FQTK_B200_API uint64_t fqtk_b200_bgzf_chunk_bytes(const fqtk_b200_bgzf* z);
+FQTK_B200_API uint64_t fqtk_b200_bgzf_bound(uint64_t n_bytes); /* output bytes that always suffice, EOF block included */
+/* host buffers (pinned memory makes the copies asynchronous): H2D, kernels and D2H of consecutive chunks overlap */
+FQTK_B200_API int fqtk_b200_bgzf_compress(fqtk_b200_bgzf* z, const uint8_t* in, uint64_t n_bytes, int level, int write_eof,
+                                          uint8_t* out, uint64_t out_capacity, uint64_t* out_bytes);
+/* device buffers, one chunk (n_bytes <= chunk_bytes), enqueued on `stream`; *d_out_bytes (device u64) = bytes written */
+FQTK_B200_API int fqtk_b200_bgzf_compress_device(fqtk_b200_bgzf* z, const uint8_t* d_in, uint64_t n_bytes, int level,
+                                                 uint8_t* d_out, uint64_t out_capacity, uint64_t* d_out_bytes, void* stream);
+
 /* ---- deterministic synthetic workload; counter-based, identical on host and device ----
  * Panel: S barcodes of length L over ACGT with pairwise Hamming distance >= min_distance (greedy, rejection);
  * `n_degenerate` positions per barcode are then rewritten to IUPAC degenerate codes (cfg 5).

@@ -1,0 +1,152 @@
+"""SURVEY 8f "next" #4 tail: BGZF output compression (src/bin/commands/demux.rs:755-798, pooled BGZF writers).
+CPU part: the oracle's restatement of the framing against Python's own gzip reader.  GPU part: the device compressor
+through the C ABI — every member must inflate to its 65 280-byte piece (strict parser), same member boundaries as the
+oracle, EOF block, stored fallback, multi-chunk pipeline, determinism."""
+import ctypes as C
+import gzip
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle.bgzf as ob
+from fqtk_b200 import _lib
+
+
+def fastq_text(n_records: int, seed: int = 7, read_len: int = 150) -> bytes:
+    rng = np.random.default_rng(seed)
+    bases = np.frombuffer(b"ACGT", dtype=np.uint8)
+    quals = np.frombuffer(b"F:,#", dtype=np.uint8)
+    seqs = bases[rng.integers(0, 4, size=(n_records, read_len))]
+    seqs[rng.random((n_records, read_len)) < 0.002] = ord("N")
+    q = quals[np.minimum(3, rng.geometric(0.75, size=(n_records, read_len)) - 1)]
+    out = []
+    for i in range(n_records):
+        out.append(b"@A00123:45:HXXXXXX:1:%d:%d:%d 1:N:0:ACGTACGT+TTGCAATC\n" % (1101 + i // 9000, 1000 + (i * 37) % 30000, 1000 + (i * 91) % 35000))
+        out.append(seqs[i].tobytes() + b"\n+\n" + q[i].tobytes() + b"\n")
+    return b"".join(out)
+
+
+# ------------------------------------------------------------------------------------------------ CPU: the oracle
+def test_oracle_members_are_what_gzip_reads():
+    data = fastq_text(700)
+    for level in (0, 1, 5, 9):
+        img = ob.compress(data, level)
+        assert gzip.decompress(img) == data
+        payload, sizes = ob.parse(img)
+        assert payload == data
+        assert sizes[:-1] == [ob.BGZF_BLOCK_SIZE] * (len(data) // ob.BGZF_BLOCK_SIZE) + [len(data) % ob.BGZF_BLOCK_SIZE]
+        assert sizes[-1] == 0 and img.endswith(ob.BGZF_EOF)
+
+
+def test_oracle_eof_block_is_the_spec_constant_and_parse_is_strict():
+    assert len(ob.BGZF_EOF) == 28 and gzip.decompress(ob.BGZF_EOF) == b""
+    assert ob.parse(ob.BGZF_EOF) == (b"", [0])
+    assert ob.compress(b"") == ob.BGZF_EOF  # a writer that saw no record leaves only the EOF block
+    img = bytearray(ob.compress(b"hello world" * 100))
+    img[-40] ^= 1  # inside the first member's trailer / data
+    with pytest.raises((ValueError, zlib.error)):
+        ob.parse(bytes(img))
+    with pytest.raises(ValueError):
+        ob.parse(ob.compress(b"abc")[:-3])
+
+
+def test_bound_and_symbols_without_a_gpu():
+    L = _lib.lib()
+    for n in (0, 1, 65280, 65281, 10 ** 9):
+        blocks = (n + 65279) // 65280
+        assert L.fqtk_b200_bgzf_bound(n) == n + blocks * 31 + 28
+    if L.fqtk_b200_device_count() == 0:
+        h = C.c_void_p()
+        assert L.fqtk_b200_bgzf_create(0, 0, C.byref(h)) == _lib.ERR_CUDA  # no CPU compressor behind the ABI
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _cases():
+    rng = np.random.default_rng(11)
+    fq = fastq_text(1500)
+    yield "one_byte", b"A"
+    yield "tiny", b"@r\nACGT\n+\nFFFF\n"
+    yield "fastq_3_blocks", fq[:3 * 65280 + 17]
+    yield "exactly_one_block", fq[:65280]
+    yield "one_block_plus_one", fq[:65281]
+    yield "zeros", bytes(200_000)
+    yield "random_incompressible", rng.integers(0, 256, size=150_000, dtype=np.uint8).tobytes()
+    yield "all_byte_values", bytes(range(256)) * 600
+    yield "long_runs", b"".join(bytes([65 + i % 5]) * (1 + (i * 7919) % 700) for i in range(600))
+    yield "period_3", b"ACG" * 50_000
+    yield "period_300", (fq[:300]) * 700
+    yield "two_symbols", bytes(rng.integers(0, 2, size=100_000, dtype=np.uint8) + 65)
+    yield "short_tail", fq[:65280 + 3]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,data", list(_cases()), ids=[c[0] for c in _cases()])
+def test_gpu_members_inflate_to_their_pieces(name, data):
+    from fqtk_b200.bgzf import BgzfCompressor
+    with BgzfCompressor(0, chunk_bytes=4 * 65280) as z:
+        assert z.chunk_bytes == 4 * 65280
+        for level in (5, 0):
+            img = z.compress(data, level)
+            payload, sizes = ob.parse(img)  # strict framing, CRC32, ISIZE, stream end
+            assert payload == data
+            _, want_sizes = ob.parse(ob.compress(data, level))
+            assert sizes == want_sizes  # same members as the reference's writer: one per 65 280 bytes, then EOF
+            assert img.endswith(ob.BGZF_EOF) and gzip.decompress(img) == data
+            assert len(img) <= z.bound(len(data))
+            if level == 0:
+                assert len(img) == len(data) + (len(sizes) - 1) * 31 + 28  # stored blocks
+        assert z.compress(data, 5) == z.compress(data, 5)  # deterministic bytes
+        no_eof = z.compress(data, 5, eof=False)
+        assert no_eof + ob.BGZF_EOF == z.compress(data, 5)
+
+
+@pytest.mark.gpu
+def test_gpu_empty_input_and_arguments():
+    from fqtk_b200.bgzf import BgzfCompressor
+    with BgzfCompressor(0) as z:
+        assert z.compress(b"") == ob.BGZF_EOF
+        assert z.compress(b"", eof=False) == b""
+        with pytest.raises(_lib.Fqtk_b200Error):
+            z.compress(b"abc", level=13)
+        src = np.frombuffer(fastq_text(300), dtype=np.uint8)
+        with pytest.raises(_lib.Fqtk_b200Error):
+            z.compress_into(src, np.empty(100, dtype=np.uint8))  # output too small: an error, not a truncation
+
+
+@pytest.mark.gpu
+def test_gpu_fastq_ratio_and_xfl_levels():
+    """Compression quality on FASTQ text: within 25 % of zlib level 5 (the reference's default level, libdeflate there)."""
+    from fqtk_b200.bgzf import BgzfCompressor
+    data = fastq_text(20_000, seed=3)
+    ref5 = len(ob.compress(data, 5))
+    with BgzfCompressor(0) as z:
+        img = z.compress(data, 5)
+        assert ob.parse(img)[0] == data
+        assert len(img) <= 1.25 * ref5, (len(img), ref5, len(data))
+        assert z.compress(data, 1)[8] == 4 and z.compress(data, 9)[8] == 2 and img[8] == 0  # XFL as the bgzf crate sets it
+
+
+@pytest.mark.gpu
+def test_gpu_multi_chunk_pipeline_at_size_and_device_entry():
+    """64 MiB chunks, 300 MB of FASTQ text through the host entry (several chunks, two streams), and one chunk through
+    the device entry; the image is checked member by member."""
+    import torch
+    from fqtk_b200.bgzf import BgzfCompressor
+    unit = fastq_text(30_000, seed=5)
+    data = unit * (300_000_000 // len(unit))
+    with BgzfCompressor(0) as z:
+        img = z.compress(data, 5)
+        payload, sizes = ob.parse(img)
+        assert payload == data and sizes[:-1].count(65280) == len(data) // 65280
+        n = min(len(data), z.chunk_bytes)
+        d_in = torch.frombuffer(bytearray(data[:n]), dtype=torch.uint8).cuda()
+        d_out = torch.empty(z.bound(n), dtype=torch.uint8, device="cuda")
+        d_n = torch.zeros(1, dtype=torch.int64, device="cuda")
+        z.compress_device(d_in.data_ptr(), n, d_out.data_ptr(), d_out.numel(), d_n.data_ptr(), 5,
+                          torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = d_out[:int(d_n.item())].cpu().numpy().tobytes()
+        assert ob.parse(got)[0] == data[:n]
+        assert got == img[:len(got)]  # the same members the host entry produced for the first chunk
