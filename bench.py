@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-brute", action="store_true")
     ap.add_argument("--no-routing", action="store_true")
+    ap.add_argument("--no-bgzf", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg 2 / 4 / 5 entries of the line")
     ap.add_argument("--single-process", action="store_true",
                     help="ONE process driving --gpus N devices through the C ABI's group handle (fqtk_b200_group_*) "
@@ -583,6 +584,89 @@ def measure_e2e(ctx, args, cfg, panel, matcher, d_packed, d_res, first, n):
     return out
 
 
+def measure_bgzf(ctx, args):
+    """The output side (SURVEY 8f next #4 tail): BGZF compression of FASTQ text, the reference's pooled writers
+    (demux.rs:755-798, level 5).  Device-resident figure (one 64 MiB chunk, CUDA events), the host-buffer call on pinned
+    memory (H2D + kernels + D2H overlapped), and zlib level 5 on one host thread beside them (the reference runs libdeflate on
+    a thread pool; this is the oracle's restatement, a bounded sample)."""
+    import ctypes as C
+
+    import oracle.bgzf as ob
+    from fqtk_b200 import _lib
+    from fqtk_b200.bgzf import BgzfCompressor
+
+    torch = ctx.torch
+    lib = _lib.lib()
+    rng = np.random.default_rng(12345)
+    n_rec, rl = 40_000, 150  # ~14 MB of distinct FASTQ text, repeated: BGZF blocks are independent, so repeats do not help
+    seqs = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(n_rec, rl))]
+    seqs[rng.random((n_rec, rl)) < 0.002] = ord("N")
+    quals = np.frombuffer(b"F:,#", dtype=np.uint8)[np.minimum(3, rng.geometric(0.75, size=(n_rec, rl)) - 1)]
+    recs = []
+    for i in range(n_rec):
+        recs.append(b"@A00123:45:HXXXXXX:1:%d:%d:%d 1:N:0:ACGTACGT+TTGCAATC\n" % (1101 + i // 9000, 1000 + (i * 37) % 30000, 1000 + (i * 91) % 35000))
+        recs.append(seqs[i].tobytes() + b"\n+\n" + quals[i].tobytes() + b"\n")
+    unit = b"".join(recs)
+    with BgzfCompressor(ctx.local) as z:
+        chunk = z.chunk_bytes
+        text = (unit * (chunk // len(unit) + 1))[:chunk]
+        d_in = torch.frombuffer(bytearray(text), dtype=torch.uint8).to(ctx.dev)
+        d_out = torch.empty(z.bound(chunk), dtype=torch.uint8, device=ctx.dev)
+        d_n = torch.zeros(1, dtype=torch.int64, device=ctx.dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        for _ in range(2):
+            z.compress_device(d_in.data_ptr(), chunk, d_out.data_ptr(), d_out.numel(), d_n.data_ptr(), 5, stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            z.compress_device(d_in.data_ptr(), chunk, d_out.data_ptr(), d_out.numel(), d_n.data_ptr(), 5, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        dms = e0.elapsed_time(e1) / reps
+        out_n = int(d_n.item())
+        img = d_out[:out_n].cpu().numpy().tobytes()
+        payload, sizes = ob.parse(img)  # every member inflates to its piece (outside the timed region)
+        assert payload == text and len(sizes) == (chunk + 65279) // 65280
+        del d_in, d_out
+        # host-buffer call: 4 chunks of pinned text in, the file image out
+        n_host = 4 * chunk
+        pin = []
+        for nbytes in (n_host, z.bound(n_host)):
+            q = C.c_void_p()
+            _lib.check(lib.fqtk_b200_host_alloc(C.byref(q), nbytes))
+            pin.append(q)
+        src = np.ctypeslib.as_array(C.cast(pin[0], C.POINTER(C.c_uint8)), shape=(n_host,))
+        dst = np.ctypeslib.as_array(C.cast(pin[1], C.POINTER(C.c_uint8)), shape=(z.bound(n_host),))
+        src[:] = np.frombuffer((text * 4)[:n_host], dtype=np.uint8)
+        z.compress_into(src, dst, 5)
+        t0 = time.perf_counter()
+        hreps = 3
+        for _ in range(hreps):
+            n_img = z.compress_into(src, dst, 5)
+        hs = (time.perf_counter() - t0) / hreps
+        for q in pin:
+            lib.fqtk_b200_host_free(q)
+    sample = text[: 24 << 20]
+    t0 = time.perf_counter()
+    ref_img = ob.compress(sample, 5)
+    cs = time.perf_counter() - t0
+    return {"what": "BGZF (65 280-byte members) of synthetic FASTQ text, compression level 5",
+            "kernels": "k_bgzf_deflate + k_bgzf_scan + k_bgzf_gather",
+            "device": {"input_bytes": chunk, "ms": round(dms, 4), "gb_per_s_in": round(chunk / (dms * 1e-3) / 1e9, 2),
+                       "output_bytes": out_n, "ratio": round(chunk / out_n, 3),
+                       "roofline_frac": round((chunk + out_n) / (dms * 1e-3) / 1e9 / ctx.peak, 5)},
+            "host_call": {"api": "fqtk_b200_bgzf_compress (pinned text in, file image out, H2D / kernels / D2H overlapped)",
+                          "input_bytes": n_host, "output_bytes": n_img, "ms": round(hs * 1e3, 3),
+                          "gb_per_s_in": round(n_host / hs / 1e9, 2)},
+            "cpu_zlib_level5_1_thread": {"input_bytes": len(sample), "seconds": round(cs, 3),
+                                         "gb_per_s_in": round(len(sample) / cs / 1e9, 4),
+                                         "ratio": round(len(sample) / len(ref_img), 3),
+                                         "note": "oracle/bgzf.py (zlib; the reference uses libdeflate on its writer thread pool)"},
+            "members_checked": len(sizes)}
+
+
 def measure_fastq(ctx, args, cfg, panel, matcher):
     """The ingest side: the headline config's barcodes taken straight out of in-memory, uncompressed
     index FASTQ chunks (I1 and I2, 8 bases each at cfg 3): fqtk_b200_fastq_scan (host, one thread per chunk) -> per-read
@@ -859,6 +943,10 @@ def run_b200(args):
     matcher.close()
     del d_packed, d_res
     torch.cuda.empty_cache()
+    bgzf = None
+    if rank == 0 and not args.no_bgzf:
+        bgzf = measure_bgzf(ctx, args)
+        torch.cuda.empty_cache()
 
     # ---- the other configs of BASELINE.json: cfg 2 weak; cfg 4 and cfg 5 STRONG over the N ranks ----
     configs = None
@@ -903,7 +991,7 @@ def run_b200(args):
                            "l2_table_bytes": int(info.l2_table_bytes)},
             "brute_force": brute, "routing": routing,
             "matched_fraction": round(1.0 - float(counts[-1]) / float(counts.sum()), 5),
-            "parity_check": head.get("parity_check"), "configs": configs, "numa": numa, "fastq_ingest": ingest,
+            "parity_check": head.get("parity_check"), "configs": configs, "numa": numa, "fastq_ingest": ingest, "bgzf": bgzf,
         }
         emit(line)
     if world > 1:

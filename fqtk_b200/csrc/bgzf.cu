@@ -6,9 +6,9 @@
 // field (SAM spec 4.1), and ends each file with the 28-byte EOF block.  The members are independent of each other, so a
 // batch of output text is an embarrassingly parallel set of 64 KB compression jobs: one CTA per BGZF block here.
 //
-// Per block (8 warps, everything in shared memory):
-//   1  LZ77 parse: warp w owns one eighth of the block.  32 positions per step: a 4-byte hash finds the most recent
-//      earlier position of the warp's part with the same hash (1 024-entry table per warp; the step's own positions are
+// Per block (16 warps, everything in shared memory; two blocks per SM):
+//   1  LZ77 parse: warp w owns one sixteenth of the block.  32 positions per step: a 4-byte hash finds the most recent
+//      earlier position of the warp's part with the same hash (512-entry table per warp; the step's own positions are
 //      inserted with "largest position wins", which makes the table — and the output — deterministic), plus the run
 //      candidate at distance 1; match lengths by 4-byte compares; the greedy parse of the 32 positions (which of them start
 //      a token, given how far the previous step's last match reaches) is the set reachable from the first uncovered
@@ -19,7 +19,7 @@
 //      thread per alphabet; the code-length alphabet (RFC 1951 3.2.7, run-length symbols 16 / 17 / 18) the same way.
 //   3  bit emission: every warp knows its bit offset from its own histogram; 32 tokens per step, warp scan of the bit
 //      lengths, bits OR-ed into a warp-private shared window, whole words stored coalesced.
-//   4  CRC-32 of the block: 256 partial CRCs, each advanced over the bytes behind it by multiplication with
+//   4  CRC-32 of the block: 512 partial CRCs, each advanced over the bytes behind it by multiplication with
 //      x^(8 n) mod P (zlib's crc32_combine arithmetic), XOR-reduced.
 // A block that does not shrink is written as a stored deflate block (BGZF guarantees the 64 KB bound that way).
 // The bytes are not libdeflate's — no two deflate implementations agree — so parity is what the reference's own tests
@@ -44,11 +44,12 @@ namespace {
 constexpr uint32_t BZ_IN = 65280;        // input bytes per BGZF block (bgzf crate BGZF_BLOCK_SIZE)
 constexpr uint32_t BZ_HDR = 18, BZ_TRL = 8;
 constexpr uint32_t BZ_SLOT = 65536 + 64;  // output slot stride per block (multiple of 16; block image at +2)
-constexpr int BZ_THREADS = 256, BZ_WARPS = 8;
-constexpr uint32_t BZ_HASH_BITS = 10, BZ_HASH = 1u << BZ_HASH_BITS;  // 16 KB of heads per CTA: two CTAs fit an SM
-constexpr uint32_t BZ_TOK_PER_WARP = 8192;  // >= ceil(65280 / 8) tokens
+constexpr int BZ_THREADS = 512, BZ_WARPS = 16;
+constexpr uint32_t BZ_HASH_BITS = 9, BZ_HASH = 1u << BZ_HASH_BITS;  // 16 KB of heads per CTA: two CTAs (32 warps) fit an SM
+constexpr uint32_t BZ_TOK_PER_WARP = 4096;  // >= ceil(65280 / 16) tokens
 constexpr uint32_t NLIT = 286, NDIST = 30, DOFF = 288, NSYM = 320;  // histogram layout: lit/len 0..285, dist 288..317
 constexpr uint32_t CRC_POLY = 0xEDB88320u;
+constexpr uint32_t BZ_WIN = 56;  // words of a warp's bit window: 31 + 32 tokens x 48 bits = 50 words at most
 
 __device__ uint32_t d_crc_table[256];
 __device__ uint32_t d_x2n[32];
@@ -109,10 +110,10 @@ __device__ __forceinline__ uint32_t x2nmodp(uint32_t n, uint32_t k) {  // x^(n *
 struct BzShared {
     uint32_t in[(65536 + 64) / 4];           // the block, zero-padded
     uint16_t head[BZ_WARPS][BZ_HASH];        // per-warp hash heads: position inside the warp's part, 0xFFFF = none
-    uint32_t hist[BZ_WARPS][NSYM];           // per-warp symbol counts
+    uint32_t hist[BZ_WARPS][NSYM / 2];       // per-warp symbol counts, two 16-bit counters per word (a part has < 65 536 tokens)
     uint32_t freq[NSYM];                     // block totals
     uint32_t crc_tab[256];
-    uint32_t win[BZ_WARPS][72];              // bit windows of the emitters
+    uint32_t win[BZ_WARPS][BZ_WIN];          // bit windows of the emitters
     uint32_t hdr[160];                       // the dynamic-block header bits
     uint32_t sortA[2][NLIT + 2];             // Huffman scratch (lit/len, dist): frequencies in ascending order -> depths
     uint16_t order[2][NLIT + 2];             //   symbol at every sorted position
@@ -123,8 +124,11 @@ struct BzShared {
     uint32_t ntok[BZ_WARPS];
     uint32_t start_bit[BZ_WARPS + 2];        // bit offset of the header (0), of every warp's tokens, and the end
     uint32_t hdr_bits;
-    uint32_t crc_part[BZ_THREADS];
+    uint32_t crc_part[BZ_WARPS];
 };
+
+__device__ __forceinline__ void hist_inc(uint32_t* h, uint32_t sym) { atomicAdd(&h[sym >> 1], 1u << ((sym & 1u) * 16u)); }
+__device__ __forceinline__ uint32_t hist_get(const uint32_t* h, uint32_t sym) { return (h[sym >> 1] >> ((sym & 1u) * 16u)) & 0xFFFFu; }
 
 __device__ __forceinline__ uint32_t read4(const uint32_t* in, uint32_t pos) {  // unaligned little-endian 4 bytes
     const uint32_t lo = in[pos >> 2], hi = in[(pos >> 2) + 1u];
@@ -179,18 +183,27 @@ __device__ void huff_lengths(uint32_t* A, const uint16_t* order, uint32_t m, uin
         for (uint32_t c = num[l]; c > 0; c--) out_len[order[--j]] = (uint8_t)l;
 }
 
-// One thread: canonical codes (RFC 1951 3.2.2) of symbols [0, n), stored bit-reversed (deflate sends codes MSB first).
-__device__ void huff_codes(const uint8_t* len, uint32_t n, uint16_t* code) {
-    uint32_t cnt[16], nextc[16];
-    for (int i = 0; i < 16; i++) cnt[i] = 0;
-    for (uint32_t s = 0; s < n; s++) cnt[len[s]]++;
-    cnt[0] = 0;
-    uint32_t c = 0;
-    nextc[0] = 0;
-    for (int b = 1; b < 16; b++) { c = (c + cnt[b - 1]) << 1; nextc[b] = c; }
-    for (uint32_t s = 0; s < n; s++) {
+// `nthreads` threads (t = 0 .. nthreads-1, one warp or fewer): canonical codes (RFC 1951 3.2.2) of symbols [0, n), stored
+// bit-reversed (deflate sends codes MSB first).  The k-th symbol of a length, in symbol order, gets first_code + k.
+__device__ void huff_codes(const uint8_t* len, uint32_t n, uint16_t* code, uint32_t t, uint32_t nthreads) {
+    uint32_t first[16];
+    {
+        uint32_t cnt[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) cnt[i] = 0;
+        for (uint32_t s = 0; s < n; s++) cnt[len[s]]++;  // (every thread counts for itself: n <= 286 byte loads)
+        cnt[0] = 0;
+        uint32_t c = 0;
+        first[0] = 0;
+#pragma unroll
+        for (int b = 1; b < 16; b++) { c = (c + cnt[b - 1]) << 1; first[b] = c; }
+    }
+    for (uint32_t s = t; s < n; s += nthreads) {
         const uint32_t l = len[s];
-        code[s] = l ? (uint16_t)(__brev(nextc[l]++) >> (32u - l)) : 0;
+        if (!l) { code[s] = 0; continue; }
+        uint32_t k = 0;
+        for (uint32_t u = 0; u < s; u++) k += len[u] == l;
+        code[s] = (uint16_t)(__brev(first[l] + k) >> (32u - l));
     }
 }
 
@@ -251,10 +264,10 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
             for (uint32_t t = n + tid; t < ((n + 3u) & ~3u) + 64u; t += BZ_THREADS) dstb[t] = 0;
         }
         for (uint32_t t = tid; t < BZ_WARPS * BZ_HASH / 2u; t += BZ_THREADS) reinterpret_cast<uint32_t*>(S.head)[t] = 0xFFFFFFFFu;
-        for (uint32_t t = tid; t < BZ_WARPS * NSYM; t += BZ_THREADS) (&S.hist[0][0])[t] = 0u;
+        for (uint32_t t = tid; t < BZ_WARPS * NSYM / 2u; t += BZ_THREADS) (&S.hist[0][0])[t] = 0u;
         for (uint32_t t = tid; t < NSYM; t += BZ_THREADS) { S.clen[t] = 0; S.code[t] = 0; }
         for (uint32_t t = tid; t < 160u; t += BZ_THREADS) S.hdr[t] = 0u;
-        for (uint32_t t = tid; t < BZ_WARPS * 72u; t += BZ_THREADS) (&S.win[0][0])[t] = 0u;
+        for (uint32_t t = tid; t < BZ_WARPS * BZ_WIN; t += BZ_THREADS) (&S.win[0][0])[t] = 0u;
         if (tid < 2u) S.used[tid] = 0u;
         __syncthreads();
 
@@ -275,10 +288,15 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
                 const uint32_t rel = pos - s0;
                 const uint32_t cand = valid ? head[h] : 0xFFFFu;
                 __syncwarp();
-                if (valid) head[h] = (uint16_t)rel;
+                // the largest position of the step wins its hash slot.  Runs (quality strings, poly-N) make neighbouring
+                // lanes hash alike: a lane whose upper neighbour has the same hash leaves the slot to it, what is left
+                // of the conflicts is settled by re-writing until nobody sees a smaller position than its own
+                const uint32_t h_up = __shfl_down_sync(0xFFFFFFFFu, h, 1);
+                const bool ins = valid && !(lane < 31u && pos + 1u < s1 && h_up == h);
+                if (ins) head[h] = (uint16_t)rel;
                 __syncwarp();
-                for (;;) {  // largest position of the step wins its hash slot
-                    const bool again = valid && head[h] < rel;
+                for (;;) {
+                    const bool again = ins && head[h] < rel;
                     if (!__any_sync(0xFFFFFFFFu, again)) break;
                     if (again) head[h] = (uint16_t)rel;
                     __syncwarp();
@@ -336,12 +354,12 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
                         if (best_len) {
                             uint32_t sym, eb, ev;
                             len_symbol(best_len - 3u, sym, eb, ev);
-                            atomicAdd(&hist[sym], 1u);
+                            hist_inc(hist, sym);
                             dist_symbol(best_dist - 1u, sym, eb, ev);
-                            atomicAdd(&hist[DOFF + sym], 1u);
+                            hist_inc(hist, DOFF + sym);
                             tokens[idx] = 0x80000000u | ((best_len - 3u) << 16) | (best_dist - 1u);
                         } else {
-                            atomicAdd(&hist[v & 0xFFu], 1u);
+                            hist_inc(hist, v & 0xFFu);
                             tokens[idx] = v & 0xFFu;
                         }
                     }
@@ -359,7 +377,7 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
             for (uint32_t s = tid; s < NSYM; s += BZ_THREADS) {
                 uint32_t f = 0;
 #pragma unroll
-                for (int ww = 0; ww < BZ_WARPS; ww++) f += S.hist[ww][s];
+                for (int ww = 0; ww < BZ_WARPS; ww++) f += hist_get(S.hist[ww], s);
                 if (s == 256u) f = 1u;                       // end of block
                 S.freq[s] = f;
             }
@@ -375,14 +393,11 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
             rank_sort(S.freq, NLIT, S.sortA[0], S.order[0], &S.used[0]);
             rank_sort(S.freq + DOFF, NDIST, S.sortA[1], S.order[1], &S.used[1]);
             __syncthreads();
-            if (tid == 0) {
-                huff_lengths(S.sortA[0], S.order[0], S.used[0], 15u, S.clen);
-                huff_codes(S.clen, NLIT, S.code);
-            } else if (tid == 32) {
-                huff_lengths(S.sortA[1], S.order[1], S.used[1], 15u, S.clen + DOFF);
-                huff_codes(S.clen + DOFF, NDIST, S.code + DOFF);
-            }
+            if (tid == 0) huff_lengths(S.sortA[0], S.order[0], S.used[0], 15u, S.clen);
+            else if (tid == 32) huff_lengths(S.sortA[1], S.order[1], S.used[1], 15u, S.clen + DOFF);
             __syncthreads();
+            if (w >= 2) huff_codes(S.clen, NLIT, S.code, tid - 64u, BZ_THREADS - 64u);  // (warp 0 goes on to the header)
+            else if (w == 1) huff_codes(S.clen + DOFF, NDIST, S.code + DOFF, lane, 32u);
             // ---- 3a: header (one thread): BFINAL = 1, BTYPE = 2, HLIT, HDIST, HCLEN, code-length codes, run-length coded lengths
             if (tid == 0) {
                 uint32_t hlit = NLIT, hdist = NDIST;
@@ -425,7 +440,7 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
                     A[b + 1] = fa; ord[b + 1] = oa;
                 }
                 huff_lengths(A, ord, m, 7u, cll);
-                huff_codes(cll, 19u, clc);
+                huff_codes(cll, 19u, clc, 0u, 1u);
                 const uint8_t perm[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
                 uint32_t hclen = 19;
                 while (hclen > 4u && cll[perm[hclen - 1u]] == 0) hclen--;
@@ -447,7 +462,7 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
             {
                 uint32_t bits = 0;
                 for (uint32_t s = lane; s < NSYM; s += 32u) {
-                    const uint32_t c = S.hist[w][s];
+                    const uint32_t c = hist_get(S.hist[w], s);
                     if (!c) continue;
                     uint32_t eb = 0;
                     if (s >= 257u && s < NLIT) eb = len_extra_bits(s);
@@ -536,7 +551,7 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
                         }
                         const uint32_t rem = win[full];
                         __syncwarp();
-                        for (uint32_t k = lane; k <= full + 1u && k < 72u; k += 32u) win[k] = 0u;
+                        for (uint32_t k = lane; k <= full + 1u && k < BZ_WIN; k += 32u) win[k] = 0u;
                         __syncwarp();
                         if (lane == 0) win[0] = rem;
                         __syncwarp();

@@ -1,3 +1,5 @@
 mkdir -p gpurun_out/r02z
-timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_bgzf.py -m gpu -x -q -k "tiny or one_byte or fastq_3_blocks" > gpurun_out/r02z/sanitize.log 2>&1; tail -25 gpurun_out/r02z/sanitize.log
-timeout 900 python -m pytest tests/test_bgzf.py -m gpu -x -q 2>&1 | tail -25
+timeout 900 python -m pytest tests/test_bgzf.py -m gpu -x -q 2>&1 | tail -3
+B="python bench.py --no-cpu-baseline --no-e2e --no-brute --no-routing --no-configs --no-parity-check"
+$B --steps 3 --warmup 3 2> gpurun_out/r02z/bench.err | python -c "
+import json,sys;d=json.loads(sys.stdin.read());b=d['bgzf'];print(b['device'], b['host_call']['gb_per_s_in'])"

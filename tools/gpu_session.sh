@@ -8,7 +8,7 @@ STEPS=${*:-tests bench launches ncu}
 OUT=gpurun_out/$TAG
 mkdir -p "$OUT"
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.max.mem,power.limit --format=csv > "$OUT/gpu.csv" 2>&1
-B="python bench.py --no-cpu-baseline --no-e2e --no-brute --no-routing --no-configs --no-parity-check"
+B="python bench.py --no-cpu-baseline --no-e2e --no-brute --no-routing --no-bgzf --no-configs --no-parity-check"
 cap() {  # name, kernel regex, bench args...
   name=$1; regex=$2; shift 2
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$regex -s 2 -c 1 -o "/tmp/prof_$name" -f $B --steps 2 --warmup 1 "$@" > "$OUT/ncu_$name.log" 2>&1
