@@ -10,6 +10,8 @@ per-sample bulk appends in input order.  Host-side mirror (Python here, Rust in 
       -> SampleWriters::write            :396-415          per output type T, B, M, C: one record per segment,
          ReadSet::write_header           :161-267          header rewritten with read number, UMIs, sample barcode
       -> DemuxMetric                     :452-497          from the matcher's count table
+      -> pooled BGZF writers             :755-798          write_bgzf_files: every output file's records as one text
+                                                           buffer -> fqtk_b200_bgzf_compress (GPU) -> the .fq.gz image
 
 No FASTQ / gzip IO lives here on purpose: records come in and go out as (head, seq, qual) byte triples."""
 from __future__ import annotations
@@ -132,3 +134,15 @@ def demux_batch(matcher, sample_ids: Sequence[str], barcodes: Sequence[str], rea
     result.counts = np.diff(np.asarray(offsets, dtype=np.uint64)).astype(np.uint64)
     result.metrics = demux_metrics(list(sample_ids), list(barcodes), [int(c) for c in result.counts], unmatched_prefix)
     return result
+
+
+def fastq_text(records) -> bytes:
+    """SampleWriters::write (demux.rs:396-415): `@head \\n seq \\n+\\n quals \\n` per record."""
+    return b"".join(b"@" + h + b"\n" + q_s + b"\n+\n" + q + b"\n" for h, q_s, q in records)
+
+
+def write_bgzf_files(result: DemuxResult, compressor, level: int = 5, eof: bool = True) -> dict:
+    """The batch's output files as BGZF images (what the reference's pooled writers leave on disk, demux.rs:755-798,
+    compression level demux.rs:641-643): file name -> bytes.  `compressor` is a fqtk_b200.bgzf.BgzfCompressor; pass
+    eof=False for every batch of a file but the last (a writer appends members and closes with the EOF block)."""
+    return {name: compressor.compress(fastq_text(recs), level, eof) for name, recs in result.files.items()}

@@ -245,4 +245,58 @@ class MatcherGroup {
     std::size_t n_samples_ = 0;
 };
 
+// The reference's output side (src/bin/commands/demux.rs:755-798): `PooledWriter`s over `BgzfCompressor`.  One
+// BgzfPool per device owns the GPU compressor; every BgzfWriter buffers its file's bytes (`write`) and the pool turns
+// what is buffered into BGZF members in one device pass per writer (`flush`: only whole 65 280-byte blocks leave, as the
+// reference's writers do; `finish`: the rest + the EOF block).  `sink` receives the file image bytes in order.
+class BgzfPool {
+  public:
+    explicit BgzfPool(int device = 0, int compression_level = 5, std::uint64_t chunk_bytes = 0) : level_(compression_level) {
+        const int rc = fqtk_b200_bgzf_create(device, chunk_bytes, &z_);
+        if (rc != FQTK_B200_OK) throw Error(rc, fqtk_b200_last_error());
+    }
+    ~BgzfPool() { fqtk_b200_bgzf_destroy(z_); }
+    BgzfPool(const BgzfPool&) = delete;
+    BgzfPool& operator=(const BgzfPool&) = delete;
+
+    // members for `n` bytes (+ EOF block if asked), appended to `out`
+    void compress(const std::uint8_t* data, std::uint64_t n, bool eof, std::string& out) {
+        const std::uint64_t cap = fqtk_b200_bgzf_bound(n);
+        const std::size_t at = out.size();
+        out.resize(at + cap);
+        std::uint64_t written = 0;
+        const int rc = fqtk_b200_bgzf_compress(z_, data, n, level_, eof ? 1 : 0, reinterpret_cast<std::uint8_t*>(&out[at]), cap, &written);
+        if (rc != FQTK_B200_OK) throw Error(rc, fqtk_b200_last_error());
+        out.resize(at + written);
+    }
+
+  private:
+    fqtk_b200_bgzf* z_ = nullptr;
+    int level_;
+};
+
+class BgzfWriter {
+  public:
+    static constexpr std::size_t BLOCK = 65280;  // bgzf crate BGZF_BLOCK_SIZE
+    explicit BgzfWriter(BgzfPool& pool) : pool_(pool) {}
+    void write_all(const void* p, std::size_t n) { buf_.append(static_cast<const char*>(p), n); }
+    void write_all(const std::string& s) { buf_ += s; }
+    // every whole block buffered so far -> members appended to `image`
+    void flush(std::string& image) {
+        const std::size_t whole = buf_.size() / BLOCK * BLOCK;
+        if (!whole) return;
+        pool_.compress(reinterpret_cast<const std::uint8_t*>(buf_.data()), whole, false, image);
+        buf_.erase(0, whole);
+    }
+    // close(): the partial last block, then the EOF block
+    void finish(std::string& image) {
+        pool_.compress(reinterpret_cast<const std::uint8_t*>(buf_.data()), buf_.size(), true, image);
+        buf_.clear();
+    }
+
+  private:
+    BgzfPool& pool_;
+    std::string buf_;
+};
+
 }  // namespace fqtk_b200

@@ -150,3 +150,37 @@ def test_gpu_multi_chunk_pipeline_at_size_and_device_entry():
         got = d_out[:int(d_n.item())].cpu().numpy().tobytes()
         assert ob.parse(got)[0] == data[:n]
         assert got == img[:len(got)]  # the same members the host entry produced for the first chunk
+
+
+@pytest.mark.gpu
+def test_gpu_demux_outputs_as_bgzf_files(tmp_path):
+    """The reference's end-to-end demux vectors with the output side attached: batched pipeline -> per-sample records ->
+    GPU BGZF images; the files read back with Python's gzip reader hold exactly the expected records (the reference's tests
+    read their .fq.gz outputs back the same way, demux.rs:1293-1333 ...)."""
+    import json
+    import os
+
+    from fqtk_b200 import BarcodeMatcher
+    from fqtk_b200.bgzf import BgzfCompressor
+    from fqtk_b200.demux import demux_batch, write_bgzf_files
+
+    kats = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
+    with BgzfCompressor(0, chunk_bytes=65280 * 8) as z:
+        for case in kats["demux_e2e"]:
+            S = len(case["barcodes"])
+            ids = [f"Sample{j:04d}" for j in range(S)]
+            inputs = [[(f"ex_{i}".encode(), b.encode(), b";" * len(b)) for i, b in enumerate(col)] for col in case["inputs"]]
+            with BarcodeMatcher(case["barcodes"], case["max_mismatches"], case["min_mismatch_delta"]) as m:
+                out = demux_batch(m, ids, case["barcodes"], case["read_structures"], inputs, case["output_types"])
+            files = write_bgzf_files(out, z)
+            assert set(files) == set(case["expect"])
+            for name, image in files.items():
+                path = tmp_path / name
+                path.write_bytes(image)
+                with gzip.open(path, "rb") as fh:
+                    lines = fh.read().split(b"\n")
+                assert lines[-1] == b""
+                recs = [[lines[k][1:].decode(), lines[k + 1].decode()] for k in range(0, len(lines) - 1, 4)]
+                assert recs == case["expect"][name], (case["source"], name)
+                assert all(lines[k + 2] == b"+" and lines[k + 3] == b";" * len(lines[k + 1]) for k in range(0, len(lines) - 1, 4))
+                assert image.endswith(ob.BGZF_EOF)
