@@ -333,6 +333,12 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
                     carry -= 32u;
                     continue;
                 }
+                // lazy matching (zlib's rule, free here because every position's match is already known): a match gives
+                // way to a literal when the next position starts a longer one
+                {
+                    const uint32_t len_up = __shfl_down_sync(0xFFFFFFFFu, best_len, 1);
+                    if (lane < 31u && best_len && len_up > best_len) best_len = 0;
+                }
                 // token starts = positions reachable from `carry` along next-token pointers
                 const uint32_t nxt = lane + (best_len ? best_len : 1u);
                 uint32_t jump = min(nxt, 32u);

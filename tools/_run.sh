@@ -1,3 +1,5 @@
-mkdir -p gpurun_out/r02y
-timeout 600 python __graft_entry__.py --smoke 2>&1 | tail -2
-timeout 2400 python -m pytest tests -m gpu -q -x --durations=6 2>&1 | tail -14
+mkdir -p gpurun_out/r02z
+timeout 900 python -m pytest tests/test_bgzf.py -m gpu -x -q 2>&1 | tail -3
+B="python bench.py --no-cpu-baseline --no-e2e --no-brute --no-routing --no-configs --no-parity-check"
+$B --steps 3 --warmup 3 2> gpurun_out/r02z/bench.err | python -c "
+import json,sys;d=json.loads(sys.stdin.read());b=d['bgzf'];print(b['device'], b['host_call']['gb_per_s_in'], b['cpu_zlib_level5_1_thread']['ratio'])"
