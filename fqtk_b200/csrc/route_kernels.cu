@@ -339,9 +339,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_scatter_tile(const uint32_
 // ------------------------------------------------------------------------------------------------------
 constexpr int R2_THREADS = 512;
 constexpr int R2_WARPS = R2_THREADS / 32;
-constexpr int R2_STEPS = RT_TILE / R2_THREADS;  // 32-read steps per warp and tile
-constexpr int R2_IDX_BITS = 13;                 // RT_TILE = 1 << 13
-static_assert(RT_TILE == (1 << R2_IDX_BITS), "tile-local index bits");
+constexpr int R2_STEPS = 16;  // 32-read steps per warp and tile: a tile is 16 reads per thread (4 096 or 8 192 reads)
 
 // results -> per-CTA bucket counts, 128-bit loads (the CTA ranges are tile-aligned, so 16-byte alignment only
 // depends on the base pointer, checked by the host)
@@ -381,15 +379,17 @@ struct Tile2Smem {
     uint32_t *cursor, *delta, *part, *mask, *cnt, *sorted;
 };
 
-// one tile of k_route_scatter_tile2; FULL = all RT_TILE reads exist here and in the tile that is prefetched
-template <bool FULL>
+// one tile of k_route_scatter_tile2; FULL = all TILE reads exist here and in the tile that is prefetched
+template <int THREADS, bool FULL>
 FQ_D void route_tile2(const Tile2Smem& sm, const uint32_t* __restrict__ results, uint32_t* __restrict__ order, uint32_t S,
                       uint64_t tile_lo, uint32_t tile_n, uint32_t next_n, uint32_t (&r)[R2_STEPS]) {
+    constexpr int WARPS = THREADS / 32;
+    constexpr uint32_t TILE = THREADS * R2_STEPS, IDX_BITS = THREADS == 1024 ? 14 : THREADS == 512 ? 13 : 12;
     const uint32_t B = S + 1u, B1 = B + 1u;
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5, lane_bit = 1u << lane, lane_lt = lane_bit - 1u;
     uint32_t* my_mask = sm.mask + w * B1;
     uint32_t* my_cnt = sm.cnt + w * B1;
-    const uint32_t per = (B1 + R2_THREADS - 1) / R2_THREADS;  // buckets per thread in the prefix phase
+    const uint32_t per = (B1 + THREADS - 1) / THREADS;  // buckets per thread in the prefix phase
     const uint32_t b_lo = min(threadIdx.x * per, B1), b_hi = min(b_lo + per, B1);
     // 1: count and rank inside the warp's chunk: the lanes of the step in my bucket come back from the mask cell, the
     //    group's first lane takes the warp's running count of the bucket with one returning atomic and hands it round
@@ -408,14 +408,14 @@ FQ_D void route_tile2(const Tile2Smem& sm, const uint32_t* __restrict__ results,
         }
         __syncwarp();
         c = __shfl_sync(0xFFFFFFFFu, c, __ffs(m) - 1);
-        r[st] = b << R2_IDX_BITS | (c + __popc(m & lane_lt));
+        r[st] = b << IDX_BITS | (c + __popc(m & lane_lt));
     }
     __syncthreads();
     // 2: per bucket the exclusive prefix over the warps, per tile the exclusive prefix over the buckets
     uint32_t mine = 0;
     for (uint32_t b = b_lo; b < b_hi; b++)
 #pragma unroll
-        for (int ww = 0; ww < R2_WARPS; ww++) mine += sm.cnt[ww * B1 + b];
+        for (int ww = 0; ww < WARPS; ww++) mine += sm.cnt[ww * B1 + b];
     uint32_t incl = mine;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -429,7 +429,7 @@ FQ_D void route_tile2(const Tile2Smem& sm, const uint32_t* __restrict__ results,
     for (uint32_t b = b_lo; b < b_hi; b++) {
         const uint32_t base = run;
 #pragma unroll
-        for (int ww = 0; ww < R2_WARPS; ww++) {
+        for (int ww = 0; ww < WARPS; ww++) {
             const uint32_t c = sm.cnt[ww * B1 + b];
             sm.cnt[ww * B1 + b] = run;
             run += c;
@@ -443,57 +443,60 @@ FQ_D void route_tile2(const Tile2Smem& sm, const uint32_t* __restrict__ results,
 #pragma unroll
     for (int st = 0; st < R2_STEPS; st++) {
         const uint32_t idx = w * (R2_STEPS * 32u) + st * 32u + lane;
-        const uint32_t b = r[st] >> R2_IDX_BITS, rank = r[st] & (RT_TILE - 1u);
-        sm.sorted[my_cnt[b] + rank] = b << R2_IDX_BITS | idx;
+        const uint32_t b = r[st] >> IDX_BITS, rank = r[st] & (TILE - 1u);
+        sm.sorted[my_cnt[b] + rank] = b << IDX_BITS | idx;
     }
     // the next tile's words are on their way while this one leaves
 #pragma unroll
     for (int st = 0; st < R2_STEPS; st++) {
         const uint32_t idx = w * (R2_STEPS * 32u) + st * 32u + lane;
-        r[st] = (FULL || idx < next_n) ? ld_stream_u32(results + tile_lo + RT_TILE + idx) : 0u;
+        r[st] = (FULL || idx < next_n) ? ld_stream_u32(results + tile_lo + TILE + idx) : 0u;
     }
     __syncthreads();
     // 4: every bucket's run leaves as one contiguous burst at the CTA's cursor; counts back to zero
     if (FULL) {
 #pragma unroll
         for (int k = 0; k < R2_STEPS; k++) {
-            const uint32_t pos = k * R2_THREADS + threadIdx.x;
+            const uint32_t pos = k * THREADS + threadIdx.x;
             const uint32_t v = sm.sorted[pos];
-            order[sm.delta[v >> R2_IDX_BITS] + pos] = (uint32_t)tile_lo + (v & (RT_TILE - 1u));
+            order[sm.delta[v >> IDX_BITS] + pos] = (uint32_t)tile_lo + (v & (TILE - 1u));
         }
     } else {
-        for (uint32_t pos = threadIdx.x; pos < tile_n; pos += R2_THREADS) {
+        for (uint32_t pos = threadIdx.x; pos < tile_n; pos += THREADS) {
             const uint32_t v = sm.sorted[pos];
-            order[sm.delta[v >> R2_IDX_BITS] + pos] = (uint32_t)tile_lo + (v & (RT_TILE - 1u));
+            order[sm.delta[v >> IDX_BITS] + pos] = (uint32_t)tile_lo + (v & (TILE - 1u));
         }
     }
-    for (uint32_t t = threadIdx.x; t < R2_WARPS * B1; t += R2_THREADS) sm.cnt[t] = 0u;
+    for (uint32_t t = threadIdx.x; t < WARPS * B1; t += THREADS) sm.cnt[t] = 0u;
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(R2_THREADS, 2)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : THREADS == 512 ? 2 : 4)
     k_route_scatter_tile2(const uint32_t* __restrict__ results, uint64_t n, uint32_t S, uint32_t n_ctas,
                           const uint32_t* __restrict__ hist, const unsigned long long* __restrict__ offsets,
                           uint32_t* __restrict__ order) {
     extern __shared__ uint32_t s_mem[];
+    constexpr int WARPS = THREADS / 32;
+    constexpr uint32_t TILE = THREADS * R2_STEPS;
     const uint32_t B = S + 1u, B1 = B + 1u;  // bucket B = the dummy for lanes past the end of the batch
     Tile2Smem sm;
     sm.cursor = s_mem;                       // [B1] next output slot of every bucket for this CTA
     sm.delta = sm.cursor + B1;               // [B1] cursor - first sorted-tile position (this tile)
-    sm.part = sm.delta + B1;                 // [R2_WARPS] scan partials
-    sm.mask = sm.part + R2_WARPS;            // [R2_WARPS][B1] lanes of the current step per bucket
-    sm.cnt = sm.mask + R2_WARPS * B1;        // [R2_WARPS][B1] reads of the warp's chunk per bucket -> first sorted position
-    sm.sorted = sm.cnt + R2_WARPS * B1;      // [RT_TILE] bucket << 13 | tile index
+    sm.part = sm.delta + B1;                 // [WARPS] scan partials
+    sm.mask = sm.part + WARPS;            // [WARPS][B1] lanes of the current step per bucket
+    sm.cnt = sm.mask + WARPS * B1;        // [WARPS][B1] reads of the warp's chunk per bucket -> first sorted position
+    sm.sorted = sm.cnt + WARPS * B1;      // [TILE] bucket << 13 | tile index
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
 
-    for (uint32_t b = threadIdx.x; b < B1; b += R2_THREADS)
+    for (uint32_t b = threadIdx.x; b < B1; b += THREADS)
         sm.cursor[b] = b < B ? (uint32_t)offsets[b] + hist[(size_t)b * n_ctas + blockIdx.x] : 0u;
-    for (uint32_t t = threadIdx.x; t < 2u * R2_WARPS * B1; t += R2_THREADS) sm.mask[t] = 0u;  // masks and counts
+    for (uint32_t t = threadIdx.x; t < 2u * WARPS * B1; t += THREADS) sm.mask[t] = 0u;  // masks and counts
     uint64_t lo, hi;
     cta_range(n, blockIdx.x, n_ctas, lo, hi);
     uint32_t r[R2_STEPS];  // this tile's result words, then bucket << 13 | rank inside the warp's chunk
     if (lo < hi) {
-        const uint32_t tile_n = (uint32_t)min((uint64_t)RT_TILE, hi - lo);
+        const uint32_t tile_n = (uint32_t)min((uint64_t)TILE, hi - lo);
 #pragma unroll
         for (int st = 0; st < R2_STEPS; st++) {
             const uint32_t idx = w * (R2_STEPS * 32u) + st * 32u + lane;
@@ -501,20 +504,28 @@ __global__ void __launch_bounds__(R2_THREADS, 2)
         }
     }
     __syncthreads();
-    for (uint64_t tile_lo = lo; tile_lo < hi; tile_lo += RT_TILE) {
+    for (uint64_t tile_lo = lo; tile_lo < hi; tile_lo += TILE) {
         const uint64_t left = hi - tile_lo;
-        if (left >= 2u * RT_TILE) {
-            route_tile2<true>(sm, results, order, S, tile_lo, RT_TILE, RT_TILE, r);
+        if (left >= 2u * TILE) {
+            route_tile2<THREADS, true>(sm, results, order, S, tile_lo, TILE, TILE, r);
         } else {
-            const uint32_t tile_n = (uint32_t)min((uint64_t)RT_TILE, left);
-            route_tile2<false>(sm, results, order, S, tile_lo, tile_n, (uint32_t)(left - tile_n), r);
+            const uint32_t tile_n = (uint32_t)min((uint64_t)TILE, left);
+            route_tile2<THREADS, false>(sm, results, order, S, tile_lo, tile_n, (uint32_t)(left - tile_n), r);
         }
     }
 }
 
-static size_t route_tile2_smem(uint32_t S) {
-    const size_t B1 = S + 2u;
-    return (2 * B1 + R2_WARPS) * 4 + (size_t)R2_WARPS * B1 * 8 + (size_t)RT_TILE * 4;  // mask table + counts
+static int route_tile2_threads() {  // CTA shape of the mask-rank kernel: 256 / 512 / 1 024 threads x 16 reads per tile (A/B: FQTK_B200_ROUTE_T)
+    static const int t = [] {
+        const char* e = getenv("FQTK_B200_ROUTE_T");
+        const int v = e ? atoi(e) : 512;
+        return (v == 256 || v == 1024) ? v : 512;
+    }();
+    return t;
+}
+static size_t route_tile2_smem(uint32_t S, int threads) {
+    const size_t B1 = S + 2u, warps = threads / 32;
+    return (2 * B1 + warps) * 4 + warps * B1 * 8 + (size_t)threads * R2_STEPS * 4;  // mask table + counts + sorted tile
 }
 
 static size_t route_tile_smem(uint32_t S) {
@@ -526,23 +537,30 @@ struct RoutePlan {
     uint32_t n_warps, warps_per_cta, grid, bucket_bits;  // n_warps = histogram columns (warps, or CTAs in tile mode)
     size_t smem;
     bool tile, tile2;
+    int threads;
 };
 
 static RoutePlan plan_route(uint64_t n, uint32_t S, const LaunchGeometry& g) {
     RoutePlan p{};
     p.bucket_bits = 1;
     while ((1u << p.bucket_bits) < S + 1u) p.bucket_bits++;
-    if (!getenv("FQTK_B200_ROUTE_V1") && !getenv("FQTK_B200_ROUTE_V2") && S + 2u <= (1u << (32 - R2_IDX_BITS)) &&
-        route_tile2_smem(S) + 1024 <= (size_t)g.max_smem_optin) {
-        p.tile = p.tile2 = true;
-        p.smem = route_tile2_smem(S);
-        const uint64_t tiles = (n + RT_TILE - 1) / RT_TILE;
-        const uint32_t per_sm = 2 * (p.smem + 1024) <= (size_t)g.max_smem_optin + 1024 ? 2 : 1;
-        uint64_t ctas = (uint64_t)g.sm_count * per_sm;
-        if (ctas > tiles) ctas = tiles ? tiles : 1;
-        p.n_warps = p.grid = (uint32_t)ctas;
-        p.warps_per_cta = R2_WARPS;
-        return p;
+    {
+        int threads = route_tile2_threads();
+        if (threads != 512 && route_tile2_smem(S, threads) + 1024 > (size_t)g.max_smem_optin) threads = 512;
+        if (!getenv("FQTK_B200_ROUTE_V1") && !getenv("FQTK_B200_ROUTE_V2") && S + 2u <= (1u << 19) &&
+            route_tile2_smem(S, threads) + 1024 <= (size_t)g.max_smem_optin) {
+            p.tile = p.tile2 = true;
+            p.threads = threads;
+            p.smem = route_tile2_smem(S, threads);
+            const uint64_t tiles = (n + RT_TILE - 1) / RT_TILE;  // (CTA ranges are cut at multiples of RT_TILE for every shape)
+            const uint32_t fit = (uint32_t)(((size_t)g.max_smem_optin + 1024) / (p.smem + 1024));
+            const uint32_t per_sm = std::max(1u, std::min(fit, threads == 1024 ? 1u : threads == 512 ? 2u : 4u));
+            uint64_t ctas = (uint64_t)g.sm_count * per_sm;
+            if (ctas > tiles) ctas = tiles ? tiles : 1;
+            p.n_warps = p.grid = (uint32_t)ctas;
+            p.warps_per_cta = (uint32_t)threads / 32u;
+            return p;
+        }
     }
     if (S + 1u <= RT_MAX_BUCKETS && route_tile_smem(S) + 1024 <= (size_t)g.max_smem_optin && !getenv("FQTK_B200_ROUTE_V1")) {
         p.tile = true;
@@ -595,7 +613,6 @@ cudaError_t launch_route(const uint32_t* d_results, uint64_t n, uint32_t S, uint
         reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(d_workspace) + (((size_t)(S + 1u) * p.n_warps * 4u + 7) & ~(size_t)7));
     if (p.tile2) {
         const size_t hsmem = (size_t)(S + 1u) * 4u;
-        cudaFuncSetAttribute(k_route_scatter_tile2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
         if ((reinterpret_cast<uintptr_t>(d_results) & 15u) == 0)
             k_route_hist_cta4<<<p.grid, R2_THREADS, hsmem, stream>>>(d_results, n, S, p.n_warps, hist);
         else
@@ -605,7 +622,16 @@ cudaError_t launch_route(const uint32_t* d_results, uint64_t n, uint32_t S, uint
         count_launch();
         k_route_scan_totals<<<1, ROUTE_SCAN_THREADS, 0, stream>>>(totals, S + 1u, d_offsets);
         count_launch();
-        k_route_scatter_tile2<<<p.grid, R2_THREADS, p.smem, stream>>>(d_results, n, S, p.n_warps, hist, d_offsets, d_order);
+        if (p.threads == 1024) {
+            cudaFuncSetAttribute(k_route_scatter_tile2<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+            k_route_scatter_tile2<1024><<<p.grid, 1024, p.smem, stream>>>(d_results, n, S, p.n_warps, hist, d_offsets, d_order);
+        } else if (p.threads == 512) {
+            cudaFuncSetAttribute(k_route_scatter_tile2<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+            k_route_scatter_tile2<512><<<p.grid, 512, p.smem, stream>>>(d_results, n, S, p.n_warps, hist, d_offsets, d_order);
+        } else {
+            cudaFuncSetAttribute(k_route_scatter_tile2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+            k_route_scatter_tile2<256><<<p.grid, 256, p.smem, stream>>>(d_results, n, S, p.n_warps, hist, d_offsets, d_order);
+        }
         count_launch();
         return cudaGetLastError();
     }

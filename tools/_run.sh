@@ -1,5 +1,6 @@
-mkdir -p gpurun_out/r02z
-timeout 900 python -m pytest tests/test_bgzf.py -m gpu -x -q 2>&1 | tail -3
-B="python bench.py --no-cpu-baseline --no-e2e --no-brute --no-routing --no-configs --no-parity-check"
-$B --steps 3 --warmup 3 2> gpurun_out/r02z/bench.err | python -c "
-import json,sys;d=json.loads(sys.stdin.read());b=d['bgzf'];print(b['device'], b['host_call']['gb_per_s_in'], b['cpu_zlib_level5_1_thread']['ratio'])"
+FQTK_B200_ROUTE_T=1024 python -m pytest tests -m gpu -x -q -k "route_kernel_versions or route_is" 2>&1 | tail -2
+B="python bench.py --no-cpu-baseline --no-e2e --no-brute --no-bgzf --no-configs --no-parity-check"
+for t in 1024 512; do
+FQTK_B200_ROUTE_T=$t $B --steps 3 --warmup 3 2>/dev/null | python -c "
+import json,sys;d=json.loads(sys.stdin.read());print($t, d['routing']['ms'], d['routing']['roofline_frac'])"
+done
