@@ -11,7 +11,7 @@ nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.max.mem,power.limi
 B="python bench.py --no-cpu-baseline --no-e2e --no-brute --no-routing --no-bgzf --no-configs --no-parity-check"
 cap() {  # name, kernel regex, bench args...
   name=$1; regex=$2; shift 2
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$regex -s 2 -c 1 -o "/tmp/prof_$name" -f $B --steps 2 --warmup 1 "$@" > "$OUT/ncu_$name.log" 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$regex -s ${SKIP:-2} -c 1 -o "/tmp/prof_$name" -f $B --steps 2 --warmup 1 "$@" > "$OUT/ncu_$name.log" 2>&1
   echo "ncu $name rc=$?"
   python tools/ncu_summary.py "/tmp/prof_$name.ncu-rep" --sass --min 0.3 > "$OUT/summary_$name.txt" 2>&1
 }
@@ -31,6 +31,12 @@ for s in $STEPS; do
       cap cfg4_k_probe5 k_probe5 --config 4 --reads 268435456
       cap cfg5_k_probe4 k_probe4 --config 5 --reads 268435456
       cap cfg3_k_brute_sliced k_brute_sliced --mode brute --reads 67108864
+      B_SAVE=$B
+      B="python bench.py --no-cpu-baseline --no-e2e --no-brute --no-bgzf --no-configs --no-parity-check"
+      cap cfg3_k_route_scatter k_route_scatter_tile2
+      B="python bench.py --no-cpu-baseline --no-e2e --no-brute --no-routing --no-configs --no-parity-check"
+      cap fastq_k_bgzf_deflate k_bgzf_deflate
+      B=$B_SAVE
       ls -la "$OUT";;
   esac
 done
