@@ -107,25 +107,32 @@ __device__ __forceinline__ uint32_t x2nmodp(uint32_t n, uint32_t k) {  // x^(n *
 }
 
 // ---------------------------------------------------------------------------------------------------- shared memory
-struct BzShared {
-    uint32_t in[(65536 + 64) / 4];           // the block, zero-padded
-    uint16_t head[BZ_WARPS][BZ_HASH];        // per-warp hash heads: position inside the warp's part, 0xFFFF = none
-    uint32_t hist[BZ_WARPS][NSYM / 2];       // per-warp symbol counts, two 16-bit counters per word (a part has < 65 536 tokens)
+struct BzPost {                              // what the phases after the parse need (aliases the hash heads, dead by then)
     uint32_t freq[NSYM];                     // block totals
-    uint32_t crc_tab[256];
     uint32_t win[BZ_WARPS][BZ_WIN];          // bit windows of the emitters
     uint32_t hdr[160];                       // the dynamic-block header bits
     uint32_t sortA[2][NLIT + 2];             // Huffman scratch (lit/len, dist): frequencies in ascending order -> depths
     uint16_t order[2][NLIT + 2];             //   symbol at every sorted position
+    uint8_t rle_sym[NLIT + NDIST + 4], rle_ext[NLIT + NDIST + 4];
+};
+struct BzShared {
+    uint32_t in[(65536 + 64) / 4];           // the block, zero-padded
+    union {
+        uint32_t head[BZ_WARPS][BZ_HASH];    // per-warp hash heads: 1 + position inside the warp's part, 0 = none (32-bit: atomicMax)
+        BzPost post;
+    };
+    uint32_t hist[BZ_WARPS][NSYM / 2];       // per-warp symbol counts, two 16-bit counters per word (a part has < 65 536 tokens)
+    uint32_t crc_tab[256];
     uint16_t code[NSYM];                     // bit-reversed canonical codes
     uint8_t clen[NSYM];                      // code lengths
-    uint8_t rle_sym[NLIT + NDIST + 4], rle_ext[NLIT + NDIST + 4];
     uint32_t used[2];                        // used symbols per alphabet
     uint32_t ntok[BZ_WARPS];
     uint32_t start_bit[BZ_WARPS + 2];        // bit offset of the header (0), of every warp's tokens, and the end
     uint32_t hdr_bits;
     uint32_t crc_part[BZ_WARPS];
 };
+static_assert(sizeof(BzPost) <= sizeof(uint32_t) * BZ_WARPS * BZ_HASH, "the post-parse scratch must fit in the hash heads");
+static_assert(2 * (sizeof(BzShared) + 1024) <= 233472, "two blocks per SM");
 
 __device__ __forceinline__ void hist_inc(uint32_t* h, uint32_t sym) { atomicAdd(&h[sym >> 1], 1u << ((sym & 1u) * 16u)); }
 __device__ __forceinline__ uint32_t hist_get(const uint32_t* h, uint32_t sym) { return (h[sym >> 1] >> ((sym & 1u) * 16u)) & 0xFFFFu; }
@@ -263,11 +270,9 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
             for (uint32_t t = n16 * 16u + tid; t < n; t += BZ_THREADS) dstb[t] = __ldg(src + t);
             for (uint32_t t = n + tid; t < ((n + 3u) & ~3u) + 64u; t += BZ_THREADS) dstb[t] = 0;
         }
-        for (uint32_t t = tid; t < BZ_WARPS * BZ_HASH / 2u; t += BZ_THREADS) reinterpret_cast<uint32_t*>(S.head)[t] = 0xFFFFFFFFu;
+        for (uint32_t t = tid; t < BZ_WARPS * BZ_HASH; t += BZ_THREADS) (&S.head[0][0])[t] = 0u;
         for (uint32_t t = tid; t < BZ_WARPS * NSYM / 2u; t += BZ_THREADS) (&S.hist[0][0])[t] = 0u;
         for (uint32_t t = tid; t < NSYM; t += BZ_THREADS) { S.clen[t] = 0; S.code[t] = 0; }
-        for (uint32_t t = tid; t < 160u; t += BZ_THREADS) S.hdr[t] = 0u;
-        for (uint32_t t = tid; t < BZ_WARPS * BZ_WIN; t += BZ_THREADS) (&S.win[0][0])[t] = 0u;
         if (tid < 2u) S.used[tid] = 0u;
         __syncthreads();
 
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
             // ---- 1: LZ77 parse of this warp's part
             const uint32_t sub = (n + BZ_WARPS - 1u) / BZ_WARPS;
             const uint32_t s0 = min(w * sub, n), s1 = min(s0 + sub, n);
-            uint16_t* head = S.head[w];
+            uint32_t* head = S.head[w];
             uint32_t* hist = S.hist[w];
             uint32_t carry = 0;  // positions of the next step already covered by the last match
             for (uint32_t p = s0; p < s1; p += 32u) {
@@ -286,26 +291,19 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
                 const uint32_t v = read4(S.in, pos);
                 const uint32_t h = (v * 2654435761u) >> (32u - BZ_HASH_BITS);
                 const uint32_t rel = pos - s0;
-                const uint32_t cand = valid ? head[h] : 0xFFFFu;
+                const uint32_t cand = valid ? head[h] : 0u;  // 1 + position, 0 = none
                 __syncwarp();
-                // the largest position of the step wins its hash slot.  Runs (quality strings, poly-N) make neighbouring
-                // lanes hash alike: a lane whose upper neighbour has the same hash leaves the slot to it, what is left
-                // of the conflicts is settled by re-writing until nobody sees a smaller position than its own
+                // the largest position of the step wins its hash slot (every earlier step's positions are smaller): one
+                // atomic max, deterministic whatever order the lanes arrive in.  Runs (quality strings, poly-N) make
+                // neighbouring lanes hash alike: a lane whose upper neighbour has the same hash leaves the slot to it.
                 const uint32_t h_up = __shfl_down_sync(0xFFFFFFFFu, h, 1);
-                const bool ins = valid && !(lane < 31u && pos + 1u < s1 && h_up == h);
-                if (ins) head[h] = (uint16_t)rel;
+                if (valid && !(lane < 31u && pos + 1u < s1 && h_up == h)) atomicMax(&head[h], rel + 1u);
                 __syncwarp();
-                for (;;) {
-                    const bool again = ins && head[h] < rel;
-                    if (!__any_sync(0xFFFFFFFFu, again)) break;
-                    if (again) head[h] = (uint16_t)rel;
-                    __syncwarp();
-                }
                 uint32_t best_len = 0, best_dist = 0;
                 if (carry < 32u) {  // (a step that lies inside the previous match only feeds the hash table)
                     const uint32_t maxlen = valid ? min(258u, s1 - pos) : 0u;
-                    if (cand != 0xFFFFu && maxlen >= 4u) {
-                        const uint32_t cpos = s0 + cand;
+                    if (cand != 0u && maxlen >= 4u) {
+                        const uint32_t cpos = s0 + cand - 1u;
                         uint32_t k = 0;
                         while (k < maxlen) {
                             const uint32_t x = read4(S.in, cpos + k) ^ read4(S.in, pos + k);
@@ -380,27 +378,30 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
         // ---- 2: block totals, Huffman codes
         bool stored = !try_deflate;
         if (try_deflate) {
+            // (the hash heads are dead: their memory is the scratch of the phases below)
+            for (uint32_t t = tid; t < 160u; t += BZ_THREADS) S.post.hdr[t] = 0u;
+            for (uint32_t t = tid; t < BZ_WARPS * BZ_WIN; t += BZ_THREADS) (&S.post.win[0][0])[t] = 0u;
             for (uint32_t s = tid; s < NSYM; s += BZ_THREADS) {
                 uint32_t f = 0;
 #pragma unroll
                 for (int ww = 0; ww < BZ_WARPS; ww++) f += hist_get(S.hist[ww], s);
                 if (s == 256u) f = 1u;                       // end of block
-                S.freq[s] = f;
+                S.post.freq[s] = f;
             }
             __syncthreads();
             if (tid == 0) {  // at least two used distance codes (zlib does the same: some inflaters insist); the literal /
                              // length alphabet always has two (end of block + the first token)
                 uint32_t nd = 0;
-                for (uint32_t s = 0; s < NDIST; s++) nd += S.freq[DOFF + s] != 0u;
+                for (uint32_t s = 0; s < NDIST; s++) nd += S.post.freq[DOFF + s] != 0u;
                 for (uint32_t s = 0; s < 3u && nd < 2u; s++)
-                    if (S.freq[DOFF + s] == 0u) { S.freq[DOFF + s] = 1u; nd++; }
+                    if (S.post.freq[DOFF + s] == 0u) { S.post.freq[DOFF + s] = 1u; nd++; }
             }
             __syncthreads();
-            rank_sort(S.freq, NLIT, S.sortA[0], S.order[0], &S.used[0]);
-            rank_sort(S.freq + DOFF, NDIST, S.sortA[1], S.order[1], &S.used[1]);
+            rank_sort(S.post.freq, NLIT, S.post.sortA[0], S.post.order[0], &S.used[0]);
+            rank_sort(S.post.freq + DOFF, NDIST, S.post.sortA[1], S.post.order[1], &S.used[1]);
             __syncthreads();
-            if (tid == 0) huff_lengths(S.sortA[0], S.order[0], S.used[0], 15u, S.clen);
-            else if (tid == 32) huff_lengths(S.sortA[1], S.order[1], S.used[1], 15u, S.clen + DOFF);
+            if (tid == 0) huff_lengths(S.post.sortA[0], S.post.order[0], S.used[0], 15u, S.clen);
+            else if (tid == 32) huff_lengths(S.post.sortA[1], S.post.order[1], S.used[1], 15u, S.clen + DOFF);
             __syncthreads();
             if (w >= 2) huff_codes(S.clen, NLIT, S.code, tid - 64u, BZ_THREADS - 64u);  // (warp 0 goes on to the header)
             else if (w == 1) huff_codes(S.clen + DOFF, NDIST, S.code + DOFF, lane, 32u);
@@ -420,15 +421,15 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
                     while (i + run < total && L(i + run) == l) run++;
                     if (l == 0u && run >= 3u) {
                         const uint32_t r = min(run, 138u);
-                        if (r <= 10u) { S.rle_sym[nr] = 17; S.rle_ext[nr] = (uint8_t)(r - 3u); }
-                        else { S.rle_sym[nr] = 18; S.rle_ext[nr] = (uint8_t)(r - 11u); }
-                        clf[S.rle_sym[nr]]++; nr++; i += r;
+                        if (r <= 10u) { S.post.rle_sym[nr] = 17; S.post.rle_ext[nr] = (uint8_t)(r - 3u); }
+                        else { S.post.rle_sym[nr] = 18; S.post.rle_ext[nr] = (uint8_t)(r - 11u); }
+                        clf[S.post.rle_sym[nr]]++; nr++; i += r;
                     } else if (l != 0u && run >= 4u) {  // the length itself, then "repeat previous" 3..6 times
-                        S.rle_sym[nr] = (uint8_t)l; S.rle_ext[nr] = 0; clf[l]++; nr++; i++;
+                        S.post.rle_sym[nr] = (uint8_t)l; S.post.rle_ext[nr] = 0; clf[l]++; nr++; i++;
                         const uint32_t r = min(run - 1u, 6u);
-                        S.rle_sym[nr] = 16; S.rle_ext[nr] = (uint8_t)(r - 3u); clf[16]++; nr++; i += r;
+                        S.post.rle_sym[nr] = 16; S.post.rle_ext[nr] = (uint8_t)(r - 3u); clf[16]++; nr++; i += r;
                     } else {
-                        S.rle_sym[nr] = (uint8_t)l; S.rle_ext[nr] = 0; clf[l]++; nr++; i++;
+                        S.post.rle_sym[nr] = (uint8_t)l; S.post.rle_ext[nr] = 0; clf[l]++; nr++; i++;
                     }
                 }
                 // code-length alphabet: at least two used symbols, lengths <= 7
@@ -450,16 +451,16 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
                 const uint8_t perm[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
                 uint32_t hclen = 19;
                 while (hclen > 4u && cll[perm[hclen - 1u]] == 0) hclen--;
-                BitWriter bw{S.hdr, 0u};
+                BitWriter bw{S.post.hdr, 0u};
                 bw.put(1u, 1u); bw.put(2u, 2u);
                 bw.put(hlit - 257u, 5u); bw.put(hdist - 1u, 5u); bw.put(hclen - 4u, 4u);
                 for (uint32_t k = 0; k < hclen; k++) bw.put(cll[perm[k]], 3u);
                 for (uint32_t k = 0; k < nr; k++) {
-                    const uint32_t s = S.rle_sym[k];
+                    const uint32_t s = S.post.rle_sym[k];
                     bw.put(clc[s], cll[s]);
-                    if (s == 16u) bw.put(S.rle_ext[k], 2u);
-                    else if (s == 17u) bw.put(S.rle_ext[k], 3u);
-                    else if (s == 18u) bw.put(S.rle_ext[k], 7u);
+                    if (s == 16u) bw.put(S.post.rle_ext[k], 2u);
+                    else if (s == 17u) bw.put(S.post.rle_ext[k], 3u);
+                    else if (s == 18u) bw.put(S.post.rle_ext[k], 7u);
                 }
                 S.hdr_bits = bw.pos;
             }
@@ -498,12 +499,12 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
                     const uint32_t hb = S.hdr_bits, nw = (hb + 31u) >> 5;
                     for (uint32_t k = lane; k < nw; k += 32u) {
                         const bool edge = k == 0u || k == (hb >> 5);
-                        if (edge) atomicOr(&out_words[k], S.hdr[k]); else out_words[k] = S.hdr[k];
+                        if (edge) atomicOr(&out_words[k], S.post.hdr[k]); else out_words[k] = S.post.hdr[k];
                     }
                 }
                 // ---- 3c: the warp's tokens
                 {
-                    uint32_t* win = S.win[w];
+                    uint32_t* win = S.post.win[w];
                     uint32_t bitpos = S.start_bit[w + 1u];
                     const uint32_t first_word = bitpos >> 5;
                     const uint32_t nt = S.ntok[w] + (w == BZ_WARPS - 1u ? 1u : 0u);  // the last warp appends end-of-block
