@@ -36,6 +36,7 @@ SYMBOLS = [
     "fqtk_b200_group_assign_batch_packed", "fqtk_b200_group_assign_packed_device", "fqtk_b200_group_counts",
     "fqtk_b200_group_reset_counts", "fqtk_b200_fastq_scan", "fqtk_b200_matcher_assign_fastq",
     "fqtk_b200_matcher_assign_fastq_device",
+    "fqtk_b200_fastq_scan_device", "fqtk_b200_matcher_assign_fastq_chunks",
     "fqtk_b200_bgzf_create", "fqtk_b200_bgzf_destroy", "fqtk_b200_bgzf_chunk_bytes", "fqtk_b200_bgzf_bound",
     "fqtk_b200_bgzf_compress", "fqtk_b200_bgzf_compress_device",
 ]
@@ -67,6 +68,11 @@ class Segment(C.Structure):
 class FastqSource(C.Structure):
     """fqtk_b200_fastq_source"""
     _fields_ = [("chunk", C.c_void_p), ("chunk_bytes", C.c_uint64), ("seq_offsets", C.c_void_p), ("seq_lengths", C.c_void_p)]
+
+
+class FastqChunk(C.Structure):
+    """fqtk_b200_fastq_chunk"""
+    _fields_ = [("data", C.c_void_p), ("bytes", C.c_uint64)]
 
 
 class FastqSegment(C.Structure):
@@ -144,6 +150,9 @@ def lib() -> C.CDLL:
                                                      C.c_uint64, vp]),
         "fqtk_b200_matcher_assign_fastq_device": (C.c_int, [vp, C.POINTER(FastqSource), C.c_uint32, C.POINTER(FastqSegment),
                                                             C.c_uint32, C.c_uint64, vp, vp]),
+        "fqtk_b200_fastq_scan_device": (C.c_int, [C.c_int, vp, C.c_uint64, C.c_uint64, vp, vp, vp, u64p, u64p, vp]),
+        "fqtk_b200_matcher_assign_fastq_chunks": (C.c_int, [vp, C.POINTER(FastqChunk), C.c_uint32, C.POINTER(FastqSegment), C.c_uint32,
+                                                            C.c_uint64, vp, u64p, u64p]),
         "fqtk_b200_bgzf_create": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(vp)]),
         "fqtk_b200_bgzf_destroy": (None, [vp]),
         "fqtk_b200_bgzf_chunk_bytes": (C.c_uint64, [vp]),

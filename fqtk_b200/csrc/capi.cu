@@ -1474,6 +1474,191 @@ int fqtk_b200_matcher_assign_fastq(fqtk_b200_matcher* m, const fqtk_b200_fastq_s
     return FQTK_B200_OK;
 }
 
+// ---- the record scanner on the device + the batch call on whole chunks ------------------------------------------------
+namespace {
+struct DevScan {  // temporaries of one chunk's scan
+    uint32_t* tile_counts = nullptr;
+    unsigned long long* prefix = nullptr;  // tiles + 1
+    unsigned long long* nl = nullptr;
+    unsigned long long* err = nullptr;     // 1 scan error word + 2 vetting words
+    ~DevScan() {
+        cudaFree(tile_counts); cudaFree(prefix); cudaFree(nl); cudaFree(err);
+    }
+};
+const char* const SCAN_ERR[3] = {"header line does not start with '@'", "separator line does not start with '+'",
+                                 "sequence and quality lengths differ"};
+}  // namespace
+
+int fqtk_b200_fastq_scan_device(int device, const uint8_t* d_chunk, uint64_t chunk_bytes, uint64_t max_records,
+                                uint64_t* d_head_offsets, uint64_t* d_seq_offsets, uint32_t* d_seq_lengths,
+                                uint64_t* n_records, uint64_t* consumed, void* stream) {
+    if ((chunk_bytes && !d_chunk) || !d_seq_offsets || !d_seq_lengths || !n_records || !consumed)
+        return fail(FQTK_B200_ERR_ARG, "NULL argument");
+    *n_records = 0;
+    *consumed = 0;
+    if (chunk_bytes == 0 || max_records == 0) return FQTK_B200_OK;
+    CU(cudaSetDevice(device));
+    fq::LaunchGeometry geo{};
+    CU(cudaDeviceGetAttribute(&geo.sm_count, cudaDevAttrMultiProcessorCount, device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t tiles = fq::fastq_scan_tiles(chunk_bytes);
+    DevScan t;
+    CU(cudaMalloc(&t.tile_counts, (size_t)tiles * 4));
+    CU(cudaMalloc(&t.prefix, ((size_t)tiles + 1) * 8));
+    CU(cudaMalloc(&t.err, 8));
+    CU(cudaMemsetAsync(t.err, 0xFF, 8, st));
+    CU(fq::launch_nl_count(d_chunk, chunk_bytes, t.tile_counts, t.prefix, st));
+    unsigned long long total_nl = 0;
+    CU(cudaMemcpyAsync(&total_nl, t.prefix + tiles, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint64_t n = std::min<uint64_t>(total_nl / 4, max_records);
+    if (n == 0) return FQTK_B200_OK;
+    CU(cudaMalloc(&t.nl, (size_t)n * 4 * 8));
+    CU(fq::launch_fq_records(d_chunk, chunk_bytes, t.prefix, n * 4, t.nl, n, reinterpret_cast<unsigned long long*>(d_head_offsets),
+                             reinterpret_cast<unsigned long long*>(d_seq_offsets), d_seq_lengths, t.err, geo, st));
+    unsigned long long err = 0, last_nl = 0;
+    CU(cudaMemcpyAsync(&err, t.err, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&last_nl, t.nl + (n * 4 - 1), 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (err != ~0ull)
+        return fail(FQTK_B200_ERR_ARG, "FASTQ record " + std::to_string(err >> 2) + ": " + SCAN_ERR[err & 3u]);
+    *n_records = n;
+    *consumed = last_nl + 1;
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_matcher_assign_fastq_chunks(fqtk_b200_matcher* m, const fqtk_b200_fastq_chunk* chunks, uint32_t n_sources,
+                                          const fqtk_b200_fastq_segment* segs, uint32_t n_segs, uint64_t max_reads,
+                                          uint32_t* results, uint64_t* n_reads, uint64_t* consumed) {
+    if (!m || !chunks || !segs || !n_reads || !consumed || n_sources == 0 || n_sources > FQTK_B200_MAX_SEGMENTS || n_segs == 0 ||
+        n_segs > FQTK_B200_MAX_SEGMENTS)
+        return fail(FQTK_B200_ERR_ARG, "need 1..8 sources and 1..8 segments");
+    *n_reads = 0;
+    for (uint32_t s = 0; s < n_sources; s++) {
+        consumed[s] = 0;
+        if (chunks[s].bytes && !chunks[s].data) return fail(FQTK_B200_ERR_ARG, "NULL chunk");
+    }
+    // the same argument rules as the table form, on stand-in sources (pointers are only tested for NULL there)
+    fqtk_b200_fastq_source dev[FQTK_B200_MAX_SEGMENTS];
+    static const uint64_t dummy = 0;
+    for (uint32_t s = 0; s < n_sources; s++) dev[s] = fqtk_b200_fastq_source{reinterpret_cast<const uint8_t*>(&dummy), chunks[s].bytes, &dummy, nullptr};
+    bool any_rest;
+    uint64_t fixed_total;
+    int rc = check_fastq_args(m, dev, n_sources, segs, n_segs, any_rest, fixed_total);
+    if (rc != FQTK_B200_OK) return rc;
+    if (max_reads >= (1ull << 32)) max_reads = (1ull << 32) - 1;
+    CU(cudaSetDevice(m->device));
+    PipelineDrain drain{m};
+    cudaStream_t st = m->streams[0];
+    auto ensure = [&](int slot, size_t bytes) -> int {
+        if (bytes > m->fq_cap[slot]) {
+            if (m->d_fq[slot]) cudaFree(m->d_fq[slot]);
+            m->d_fq[slot] = nullptr;
+            m->fq_cap[slot] = 0;
+            CU(cudaMalloc(&m->d_fq[slot], bytes + 64));
+            m->fq_cap[slot] = bytes;
+        }
+        return FQTK_B200_OK;
+    };
+    // chunks over PCIe, newline counts per chunk
+    DevScan t[FQTK_B200_MAX_SEGMENTS];
+    unsigned long long total_nl[FQTK_B200_MAX_SEGMENTS] = {};
+    for (uint32_t s = 0; s < n_sources; s++) {
+        if ((rc = ensure(3 * s, chunks[s].bytes)) != FQTK_B200_OK) return rc;
+        const uint32_t tiles = fq::fastq_scan_tiles(chunks[s].bytes);
+        CU(cudaMalloc(&t[s].tile_counts, (size_t)tiles * 4 + 4));
+        CU(cudaMalloc(&t[s].prefix, ((size_t)tiles + 1) * 8));
+        CU(cudaMalloc(&t[s].err, 24));
+        CU(cudaMemsetAsync(t[s].err, 0xFF, 24, st));
+        CU(cudaMemcpyAsync(m->d_fq[3 * s], chunks[s].data, chunks[s].bytes, cudaMemcpyHostToDevice, st));
+        CU(fq::launch_nl_count(static_cast<const uint8_t*>(m->d_fq[3 * s]), chunks[s].bytes, t[s].tile_counts, t[s].prefix, st));
+        CU(cudaMemcpyAsync(&total_nl[s], t[s].prefix + tiles, 8, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    uint64_t n = max_reads;
+    for (uint32_t s = 0; s < n_sources; s++) n = std::min<uint64_t>(n, total_nl[s] / 4);  // the inputs advance in lock step
+    if (n == 0) return FQTK_B200_OK;
+    if (!results) return fail(FQTK_B200_ERR_ARG, "NULL results");
+    // record tables, then the reference's per-read rules, all on the device
+    unsigned long long last_nl[FQTK_B200_MAX_SEGMENTS] = {}, err_scan[FQTK_B200_MAX_SEGMENTS] = {}, err_vet[2] = {};
+    fq::OffsetSource os{};
+    os.n_segments = n_segs;
+    for (uint32_t s = 0; s < n_sources; s++) {
+        if ((rc = ensure(3 * s + 1, n * 8)) != FQTK_B200_OK) return rc;
+        if ((rc = ensure(3 * s + 2, n * 4)) != FQTK_B200_OK) return rc;
+        CU(cudaMalloc(&t[s].nl, (size_t)n * 4 * 8));
+        const uint8_t* d_chunk = static_cast<const uint8_t*>(m->d_fq[3 * s]);
+        CU(fq::launch_fq_records(d_chunk, chunks[s].bytes, t[s].prefix, n * 4, t[s].nl, n, nullptr,
+                                 static_cast<unsigned long long*>(m->d_fq[3 * s + 1]), static_cast<uint32_t*>(m->d_fq[3 * s + 2]),
+                                 t[s].err, m->geo, st));
+        CU(cudaMemcpyAsync(&err_scan[s], t[s].err, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&last_nl[s], t[s].nl + (n * 4 - 1), 8, cudaMemcpyDeviceToHost, st));
+        dev[s].chunk = d_chunk;
+        dev[s].chunk_bytes = chunks[s].bytes;
+        dev[s].seq_offsets = static_cast<const uint64_t*>(m->d_fq[3 * s + 1]);
+        dev[s].seq_lengths = static_cast<const uint32_t*>(m->d_fq[3 * s + 2]);
+        os.base[s] = d_chunk;
+        os.seq_offsets[s] = dev[s].seq_offsets;
+        os.seq_lengths[s] = dev[s].seq_lengths;
+    }
+    for (uint32_t k = 0; k < n_segs; k++) {
+        os.source_of[k] = segs[k].source;
+        os.offset[k] = segs[k].offset;
+        os.length[k] = segs[k].length;
+    }
+    CU(fq::launch_fq_vet(os, n, m->L, (uint32_t)m->max_mm + m->max_ns, t[0].err + 1, m->geo, st));
+    CU(cudaMemcpyAsync(err_vet, t[0].err + 1, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (uint32_t s = 0; s < n_sources; s++)
+        if (err_scan[s] != ~0ull)
+            return fail(FQTK_B200_ERR_ARG, "FASTQ record " + std::to_string(err_scan[s] >> 2) + " of input " + std::to_string(s) + ": " +
+                                               SCAN_ERR[err_scan[s] & 3u]);
+    if (err_vet[0] != ~0ull || err_vet[1] != ~0ull) {
+        // the first offending read, as the reference's read-by-read loop would meet it: its table rows come back and the
+        // message is built from the host's own chunk bytes
+        const bool few = err_vet[0] <= err_vet[1];
+        const uint64_t i = few ? err_vet[0] : err_vet[1];
+        uint64_t off[FQTK_B200_MAX_SEGMENTS] = {};
+        uint32_t len[FQTK_B200_MAX_SEGMENTS] = {};
+        for (uint32_t s = 0; s < n_sources; s++) {
+            CU(cudaMemcpy(&off[s], dev[s].seq_offsets + i, 8, cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(&len[s], dev[s].seq_lengths + i, 4, cudaMemcpyDeviceToHost));
+        }
+        if (few) {
+            for (uint32_t k = 0; k < n_segs; k++) {
+                const uint64_t need = (uint64_t)segs[k].offset + (segs[k].length == FQTK_B200_SEGMENT_REST ? 1u : segs[k].length);
+                if (len[segs[k].source] < need) {
+                    char buf[200];
+                    std::snprintf(buf, sizeof buf, "Read %llu had too few bases to demux %llu vs. %llu needed in read structure.",
+                                  (unsigned long long)i, (unsigned long long)len[segs[k].source], (unsigned long long)need);
+                    return fail(FQTK_B200_ERR_ARG, buf);
+                }
+            }
+        }
+        std::string bc;
+        for (uint32_t k = 0; k < n_segs; k++) {
+            const uint32_t s = segs[k].source;
+            const uint64_t l = segs[k].length == FQTK_B200_SEGMENT_REST ? len[s] - segs[k].offset : segs[k].length;
+            bc.append(reinterpret_cast<const char*>(chunks[s].data + off[s] + segs[k].offset), (size_t)l);
+        }
+        std::string msg = "Read barcode (";
+        for (char ch : bc) msg.push_back(decode_mask(fq::encode_byte((uint8_t)ch)));
+        msg += ") length (" + std::to_string(bc.size()) + ") differs from expected barcode (";
+        msg.append(reinterpret_cast<const char*>(m->panel.data()), m->L);
+        msg += ") length (" + std::to_string(m->L) + ") for sample 0";
+        return fail(FQTK_B200_ERR_LENGTH, msg);
+    }
+    rc = ensure_pipeline(m, 16, (size_t)n, false);
+    if (rc != FQTK_B200_OK) return rc;
+    rc = fqtk_b200_matcher_assign_fastq_device(m, dev, n_sources, segs, n_segs, n, m->d_out[0], st);
+    if (rc != FQTK_B200_OK) return rc;
+    CU(cudaMemcpyAsync(results, m->d_out[0], n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_reads = n;
+    for (uint32_t s = 0; s < n_sources; s++) consumed[s] = last_nl[s] + 1;
+    return FQTK_B200_OK;
+}
+
 int fqtk_b200_matcher_assign(fqtk_b200_matcher* m, const uint8_t* read_bases, size_t len, uint32_t* result) {
     if (!m || !result || (len && !read_bases)) return fail(FQTK_B200_ERR_ARG, "NULL argument");
     if (len > 0xFFFFFFFFull) return fail(FQTK_B200_ERR_ARG, "read too long");

@@ -150,6 +150,16 @@ cudaError_t launch_route(const uint32_t* d_results, uint64_t n, uint32_t S, uint
                          unsigned long long* d_offsets, void* d_workspace, const LaunchGeometry& g, cudaStream_t stream);
 cudaError_t launch_pack_offsets(const OffsetSource& seg, uint64_t n, uint32_t L, uint32_t* d_packed, uint32_t* d_lengths,
                                 const LaunchGeometry& g, cudaStream_t stream);
+// device FASTQ scanner (ingest_kernels.cu)
+uint32_t fastq_scan_tiles(uint64_t bytes);
+cudaError_t launch_nl_count(const uint8_t* d_chunk, uint64_t bytes, uint32_t* d_tile_counts, unsigned long long* d_prefix,
+                            cudaStream_t stream);
+cudaError_t launch_fq_records(const uint8_t* d_chunk, uint64_t bytes, const unsigned long long* d_prefix, uint64_t max_nl,
+                              unsigned long long* d_nl, uint64_t n_records, unsigned long long* d_head_offsets,
+                              unsigned long long* d_seq_offsets, uint32_t* d_seq_lengths, unsigned long long* d_err,
+                              const LaunchGeometry& g, cudaStream_t stream);
+cudaError_t launch_fq_vet(const OffsetSource& os, uint64_t n, uint32_t L, uint32_t max_nocalls, unsigned long long* d_err2,
+                          const LaunchGeometry& g, cudaStream_t stream);
 cudaError_t launch_fix_lengths(uint32_t* d_results, const uint32_t* d_lengths, uint64_t n, uint32_t L, uint32_t S,
                                unsigned long long* d_counts, const LaunchGeometry& g, cudaStream_t stream);
 cudaError_t launch_narrow_u16(const uint32_t* d_results, uint64_t n, uint16_t* d_out, const LaunchGeometry& g,

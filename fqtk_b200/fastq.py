@@ -2,6 +2,8 @@
 
     fqtk_b200_fastq_scan          where the records of an in-memory FASTQ chunk are (ReadSetIterator::next, demux.rs:288-342)
     fqtk_b200_matcher_assign_fastq    the B segments gathered by offset and encoded ON THE DEVICE, then matched
+    fqtk_b200_fastq_scan_device / fqtk_b200_matcher_assign_fastq_chunks   the scanner itself on the device: raw chunks in,
+                                  result words out, no per-record work on the host at all
     fqtk_b200_matcher_route       stable per-sample partition of the read indices (demux.rs:970-975)
 
 `demux_fastq_batch` strings them together for one batch of lock-stepped FASTQ chunks and hands back the same DemuxResult as
@@ -100,6 +102,37 @@ def assign_fastq(matcher, indexes: Sequence[FastqIndex], segments: Sequence[tupl
 
         _raise(rc, getattr(matcher, "_sample0_id", None))
     return out
+
+
+def assign_fastq_chunks(matcher, texts: Sequence, segments: Sequence[tuple[int, int, int]], max_reads: int | None = None):
+    """fqtk_b200_matcher_assign_fastq_chunks: raw lock-stepped FASTQ chunks (host memory) -> (result words of the records that
+    are complete in every chunk, bytes consumed per chunk).  Scan, the reference's per-read rules, gather, encode and match
+    all run on the device; nothing walks the records on the host."""
+    arrs = [np.frombuffer(t, dtype=np.uint8) if not isinstance(t, np.ndarray) else np.ascontiguousarray(t, np.uint8) for t in texts]
+    cap = min(int(a.size) // 7 + 1 for a in arrs)
+    if max_reads is not None:
+        cap = min(cap, int(max_reads))
+    chunks = (_lib.FastqChunk * len(arrs))(*[_lib.FastqChunk(a.ctypes.data if a.size else None, a.size) for a in arrs])
+    segs = (_lib.FastqSegment * len(segments))(*[_lib.FastqSegment(*s) for s in segments])
+    out = np.empty(max(cap, 1), dtype=np.uint32)
+    n = C.c_uint64()
+    consumed = (C.c_uint64 * len(arrs))()
+    rc = _lib.lib().fqtk_b200_matcher_assign_fastq_chunks(matcher._h, chunks, len(arrs), segs, len(segments), cap, out.ctypes.data,
+                                                         C.byref(n), consumed)
+    if rc != _lib.OK:
+        from .barcode_matching import _raise
+
+        _raise(rc, getattr(matcher, "_sample0_id", None))
+    return out[:int(n.value)].copy(), [int(c) for c in consumed]
+
+
+def scan_device(d_chunk: int, chunk_bytes: int, max_records: int, d_head_offsets: int, d_seq_offsets: int, d_seq_lengths: int,
+                device: int = 0, stream: int = 0) -> tuple[int, int]:
+    """fqtk_b200_fastq_scan_device: the scanner for a chunk that is already in device memory -> (records, bytes consumed)."""
+    n, consumed = C.c_uint64(), C.c_uint64()
+    _lib.check(_lib.lib().fqtk_b200_fastq_scan_device(device, d_chunk, chunk_bytes, max_records, d_head_offsets or None, d_seq_offsets,
+                                                      d_seq_lengths, C.byref(n), C.byref(consumed), stream or None))
+    return int(n.value), int(consumed.value)
 
 
 def demux_fastq_batch(matcher, sample_ids: Sequence[str], barcodes: Sequence[str], read_structures: Sequence[str],

@@ -214,6 +214,27 @@ FQTK_B200_API int fqtk_b200_matcher_assign_fastq_device(fqtk_b200_matcher* m, co
                                                         uint32_t n_segments, uint64_t n_reads, uint32_t* d_results,
                                                         void* stream);
 
+/* The scanner on the DEVICE (the chunk crosses PCIe anyway): same tables, same rules and error texts as
+ * fqtk_b200_fastq_scan for a chunk that is already in device memory; every pointer but n_records / consumed is a device
+ * pointer (d_head_offsets may be NULL).  Synchronous on `stream` (the two counts come back to the host). */
+FQTK_B200_API int fqtk_b200_fastq_scan_device(int device, const uint8_t* d_chunk, uint64_t chunk_bytes, uint64_t max_records,
+                                              uint64_t* d_head_offsets, uint64_t* d_seq_offsets, uint32_t* d_seq_lengths,
+                                              uint64_t* n_records, uint64_t* consumed, void* stream);
+/* The whole ingest step in one call: raw FASTQ chunks of the inputs (HOST memory, one per input, in lock step) -> result
+ * words.  The chunks are copied to the device, scanned THERE, the reference's per-read rules (too few bases,
+ * demux.rs:298-315; barcode longer than the panel's, barcode_matching.rs:95-106 after the no-call pre-filter :170-172) are
+ * checked there too, then gather + encode + match as in fqtk_b200_matcher_assign_fastq.  *n_reads = records matched
+ * (complete in every chunk, at most max_reads), consumed[s] = bytes of chunk s they cover (the caller carries the rest
+ * over).  Errors are the table form's, for the first offending read in input order. */
+typedef struct {
+    const uint8_t* data;
+    uint64_t bytes;
+} fqtk_b200_fastq_chunk;
+FQTK_B200_API int fqtk_b200_matcher_assign_fastq_chunks(fqtk_b200_matcher* m, const fqtk_b200_fastq_chunk* chunks,
+                                                        uint32_t n_sources, const fqtk_b200_fastq_segment* segments,
+                                                        uint32_t n_segments, uint64_t max_reads, uint32_t* results,
+                                                        uint64_t* n_reads, uint64_t* consumed);
+
 /* ---- HBM-resident calls: DEVICE buffers, asynchronous on `stream` (a cudaStream_t, NULL = default) ----
  * `d_packed`: n_reads * W u32 words, read i at words [i*W, (i+1)*W), symbol k of a read in bits 4*(k%8) of its
  * word k/8 — the reference's own BitEnc layout (mod.rs:49-61, bitenc.rs:311-322).  `d_results`: n_reads u32.

@@ -697,6 +697,118 @@ def test_fastq_ingest_at_size_and_with_trailing_barcode_segments():
     assert L == 8
 
 
+def test_device_fastq_scanner_equals_the_host_scanner():
+    """fqtk_b200_fastq_scan_device against fqtk_b200_fastq_scan on the same chunks: LF and CRLF records, a record cut off by the
+    chunk end, empty chunk, max_records, and the three malformed-record errors (same text, same first record)."""
+    torch = torch_cuda()
+    from fqtk_b200 import fastq
+    rng = np.random.default_rng(5)
+
+    def records(n, crlf=False, var=True):
+        out = []
+        for i in range(n):
+            ln = int(rng.integers(1, 200)) if var else 8
+            seq = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=ln))
+            eol = b"\r\n" if crlf and i % 3 == 0 else b"\n"
+            out.append(b"@r%d some comment" % i + eol + seq + eol + b"+" + (b"r%d" % i if i % 5 == 0 else b"") + eol + b"I" * ln + eol)
+        return b"".join(out)
+
+    def dev_scan(text, max_records=None):
+        n_cap = max(1, len(text) // 7 + 1) if max_records is None else max_records
+        d = torch.frombuffer(bytearray(text) if text else bytearray(1), dtype=torch.uint8).cuda()
+        d_head = torch.zeros(n_cap, dtype=torch.int64, device="cuda")
+        d_seq = torch.zeros(n_cap, dtype=torch.int64, device="cuda")
+        d_len = torch.zeros(n_cap, dtype=torch.int32, device="cuda")
+        n, used = fastq.scan_device(d.data_ptr(), len(text), n_cap, d_head.data_ptr(), d_seq.data_ptr(), d_len.data_ptr())
+        return n, used, d_head[:n].cpu().numpy().astype(np.uint64), d_seq[:n].cpu().numpy().astype(np.uint64), \
+            d_len[:n].cpu().numpy().astype(np.uint32)
+
+    for text in (records(5000), records(3000, crlf=True), records(40000, var=False), records(7) + b"@cut\nACGT\n+\nII",
+                 records(3)[:-1], b"", b"\n" * 3, records(70000) ):
+        want = fastq.scan(text)
+        n, used, head, seq, ln = dev_scan(text)
+        assert (n, used) == (len(want), want.consumed)
+        assert np.array_equal(head, want.head_offsets) and np.array_equal(seq, want.seq_offsets) and np.array_equal(ln, want.seq_lengths)
+    text = records(1000)
+    want = fastq.scan(text, 10)
+    n, used, head, seq, ln = dev_scan(text, 10)
+    assert (n, used) == (10, want.consumed) and np.array_equal(seq, want.seq_offsets)
+    recs = [b"@r%d\nACGTACGT\n+\nIIIIIIII\n" % i for i in range(300)]
+
+    def with_record(i, rec):
+        return b"".join(recs[:i] + [rec] + recs[i + 1:])
+
+    for bad, what in ((with_record(150, b"Xr150\nACGTACGT\n+\nIIIIIIII\n"), "record 150: header line"),
+                      (with_record(200, b"@r200\nACGTACGT\n-\nIIIIIIII\n"), "record 200: separator line"),
+                      (with_record(9, b"@r9\nACGTACGT\n+\nIIIIIII\n"), "record 9: sequence and quality lengths differ"),
+                      (with_record(9, b"@r9\nACGTACGT\n+\nIIIIIII\n").replace(b"@r5\n", b"r5\n"), "record 5: header line")):
+        with pytest.raises(_lib.Fqtk_b200Error) as host_err:
+            fastq.scan(bad)
+        with pytest.raises(_lib.Fqtk_b200Error) as dev_err:
+            dev_scan(bad)
+        assert what in dev_err.value.message
+        assert dev_err.value.message == host_err.value.message
+
+
+def test_assign_fastq_chunks_equals_scan_then_assign():
+    """The one-call ingest (chunks -> device scan -> device rules -> gather / encode / match) against host scan +
+    assign_fastq, on dual-index chunks with a trailing +B segment, carry-over at the chunk end, and the reference's two
+    per-read errors (too few bases; barcode longer than the panel's, unless the no-call pre-filter gets there first)."""
+    from fqtk_b200 import fastq
+    cfg = synth.CONFIGS[3]
+    panel = synth.panel(cfg)
+    bcs = [bytes(r) for r in panel]
+    n = 150_000
+    reads = synth.reads_host(panel, cfg.seed_reads, 3, n)
+
+    def fq_text(col_lo, col_hi, extra=b""):
+        return b"".join(b"@q%d\n" % i + bytes(reads[i, col_lo:col_hi]) + extra + b"\n+\n" + b"F" * (col_hi - col_lo + len(extra)) + b"\n"
+                        for i in range(n))
+
+    i1, i2 = fq_text(0, 8), fq_text(8, 16, b"TTTT")  # I2 carries 4 template bases behind its 8 barcode bases
+    segs_fixed = [(0, 0, 8), (1, 0, 8)]
+    with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta) as m:
+        want = fastq.assign_fastq(m, [fastq.scan(i1), fastq.scan(i2)], segs_fixed)
+        m.reset_counts()
+        got, used = fastq.assign_fastq_chunks(m, [i1, i2], segs_fixed)
+        assert np.array_equal(got, want) and used == [len(i1), len(i2)]
+        assert int(m.counts().sum()) == n
+        # chunk ends in the middle of a record of one input: the records complete in BOTH inputs are matched
+        cut1, cut2 = i1[: len(i1) // 2 + 5], i2[: len(i2) // 3 + 1]
+        k = min(len(fastq.scan(cut1)), len(fastq.scan(cut2)))
+        got, used = fastq.assign_fastq_chunks(m, [cut1, cut2], segs_fixed)
+        assert got.shape[0] == k and np.array_equal(got, want[:k])
+        assert used == [int(fastq.scan(cut1).head_offsets[k]) if k < len(fastq.scan(cut1)) else fastq.scan(cut1).consumed,
+                        int(fastq.scan(cut2).head_offsets[k]) if k < len(fastq.scan(cut2)) else fastq.scan(cut2).consumed]
+        got, _ = fastq.assign_fastq_chunks(m, [i1, i2], segs_fixed, max_reads=1000)
+        assert np.array_equal(got, want[:1000])
+        # errors: the table form's, for the first offending read
+        short = i1.replace(b"@q777\n" + bytes(reads[777, 0:8]), b"@q777\n" + bytes(reads[777, 0:5]), 1).replace(
+            b"@q777\n" + bytes(reads[777, 0:5]) + b"\n+\nFFFFFFFF", b"@q777\n" + bytes(reads[777, 0:5]) + b"\n+\nFFFFF", 1)
+        with pytest.raises(Exception) as e1:
+            fastq.assign_fastq_chunks(m, [short, i2], segs_fixed)
+        with pytest.raises(Exception) as e2:
+            fastq.assign_fastq(m, [fastq.scan(short), fastq.scan(i2)], segs_fixed)
+        assert "Read 777 had too few bases to demux 5 vs. 8" in str(e1.value) and str(e1.value) == str(e2.value)
+    # trailing +B: I2 = 8B then the rest as barcode too (12 bases) against a 20-base panel would differ; use a 12-base panel
+    panel12 = np.concatenate([panel[:, 8:16], np.full((panel.shape[0], 4), ord("T"), dtype=np.uint8)], axis=1)
+    with BarcodeMatcher([bytes(r) for r in panel12], 1, 2) as m:
+        rest = [(0, 0, _lib.SEGMENT_REST)]
+        want = fastq.assign_fastq(m, [fastq.scan(i2)], rest)
+        got, _ = fastq.assign_fastq_chunks(m, [i2], rest)
+        assert np.array_equal(got, want) and (want != _lib.NONE).mean() > 0.5
+        longer = i2.replace(b"TTTT\n+\nFFFFFFFFFFFF\n", b"TTTTA\n+\nFFFFFFFFFFFFF\n", 1)  # read 0: 13 bases > 12
+        with pytest.raises(Exception) as e1:
+            fastq.assign_fastq_chunks(m, [longer], rest)
+        with pytest.raises(Exception) as e2:
+            fastq.assign_fastq(m, [fastq.scan(longer)], rest)
+        assert "length (13) differs from expected barcode" in str(e1.value) and str(e1.value) == str(e2.value)
+        nn = longer.replace(bytes(reads[0, 8:16]) + b"TTTTA", b"NNNNNNNNTTTTA", 1)  # the no-call pre-filter fires first: None
+        got, _ = fastq.assign_fastq_chunks(m, [nn], rest)
+        want = fastq.assign_fastq(m, [fastq.scan(nn)], rest)
+        assert got[0] == _lib.NONE and np.array_equal(got, want)
+
+
 def test_batched_pipeline_at_cfg1_scale():
     """cfg 1 (10 k single-end reads, 8B+T, 4 samples): every record lands in the file of the sample the oracle assigns,
     in input order, with the rewritten header; too-short reads are skipped and counted nowhere (demux.rs:2023-2073)."""
