@@ -184,3 +184,48 @@ def test_gpu_demux_outputs_as_bgzf_files(tmp_path):
                 assert recs == case["expect"][name], (case["source"], name)
                 assert all(lines[k + 2] == b"+" and lines[k + 3] == b";" * len(lines[k + 1]) for k in range(0, len(lines) - 1, 4))
                 assert image.endswith(ob.BGZF_EOF)
+
+
+@pytest.mark.gpu
+def test_gpu_fuzz_structured_inputs():
+    """400 generated inputs — every size from 1 to 40 bytes, sizes around one and two blocks, alphabets of 1 ... 256 symbols,
+    copies at distances 1 ... 9 000 (inside and across the 4 080-byte parts a warp parses), long runs, matches of exactly
+    3 / 4 / 258 / 259 bytes, Fibonacci-skewed symbol counts (code lengths above the 15-bit limit before the repair) — all
+    through the strict member parser."""
+    from fqtk_b200.bgzf import BgzfCompressor
+    rng = np.random.default_rng(2024)
+    cases = [bytes(rng.integers(65, 69, size=n, dtype=np.uint8)) for n in range(1, 41)]
+    for n in (65279, 65280, 65281, 2 * 65280 - 1, 2 * 65280, 2 * 65280 + 1, 4079, 4080, 4081, 8160, 8161):
+        cases.append(bytes(rng.integers(0, 256, size=n, dtype=np.uint8) & 0x0F))
+    for _ in range(200):
+        n = int(rng.integers(1, 140_000))
+        alpha = int(rng.choice([1, 2, 3, 4, 5, 16, 64, 256]))
+        buf = bytearray(rng.integers(0, alpha, size=n, dtype=np.uint8).tobytes())
+        for _ in range(int(rng.integers(0, 60))):  # plant copies
+            ln = int(rng.choice([3, 4, 5, 17, 100, 257, 258, 259, 300, 1000, 5000]))
+            dist = int(rng.choice([1, 2, 3, 7, 31, 32, 33, 100, 1000, 4079, 4080, 4081, 9000]))
+            if n <= dist + ln:
+                continue
+            dst = int(rng.integers(dist, n - ln))
+            for k in range(ln):  # byte by byte: overlapping copies behave like deflate's
+                buf[dst + k] = buf[dst + k - dist]
+        cases.append(bytes(buf))
+    fib = [1, 1]
+    while sum(fib) < 60_000:
+        fib.append(fib[-1] + fib[-2])
+    cases.append(b"".join(bytes([i]) * c for i, c in enumerate(fib)))  # skewed: forces the length-limit repair
+    skew = np.concatenate([np.full(c, i, dtype=np.uint8) for i, c in enumerate(fib)])
+    rng.shuffle(skew)
+    cases.append(skew.tobytes())
+    for _ in range(140):
+        n = int(rng.integers(1, 70_000))
+        run = rng.geometric(0.05, size=n // 4 + 1)
+        vals = rng.integers(33, 75, size=run.size, dtype=np.uint8)
+        cases.append(np.repeat(vals, run)[:n].tobytes())
+    with BgzfCompressor(0, chunk_bytes=3 * 65280) as z:
+        for i, data in enumerate(cases):
+            img = z.compress(data, 5)
+            payload, sizes = ob.parse(img)
+            assert payload == data, (i, len(data))
+            assert sizes[:-1] == [65280] * (len(data) // 65280) + ([len(data) % 65280] if len(data) % 65280 else [])
+            assert len(img) <= len(data) + 31 * (len(sizes) - 1) + 28  # never larger than stored blocks
