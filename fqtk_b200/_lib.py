@@ -38,7 +38,8 @@ SYMBOLS = [
     "fqtk_b200_matcher_assign_fastq_device",
     "fqtk_b200_fastq_scan_device", "fqtk_b200_matcher_assign_fastq_chunks",
     "fqtk_b200_bgzf_create", "fqtk_b200_bgzf_destroy", "fqtk_b200_bgzf_chunk_bytes", "fqtk_b200_bgzf_bound",
-    "fqtk_b200_bgzf_compress", "fqtk_b200_bgzf_compress_device",
+    "fqtk_b200_bgzf_compress", "fqtk_b200_bgzf_compress_device", "fqtk_b200_bgzf_compress_segments_device",
+    "fqtk_b200_emit_streams", "fqtk_b200_demux_emit_device",
 ]
 
 
@@ -68,6 +69,17 @@ class Segment(C.Structure):
 class FastqSource(C.Structure):
     """fqtk_b200_fastq_source"""
     _fields_ = [("chunk", C.c_void_p), ("chunk_bytes", C.c_uint64), ("seq_offsets", C.c_void_p), ("seq_lengths", C.c_void_p)]
+
+
+class EmitSource(C.Structure):
+    """fqtk_b200_emit_source"""
+    _fields_ = [("d_chunk", C.c_void_p), ("chunk_bytes", C.c_uint64), ("d_head_offsets", C.c_void_p),
+                ("d_seq_offsets", C.c_void_p), ("d_seq_lengths", C.c_void_p)]
+
+
+class ReadSegment(C.Structure):
+    """fqtk_b200_read_segment"""
+    _fields_ = [("source", C.c_uint32), ("kind", C.c_uint32), ("offset", C.c_uint32), ("length", C.c_uint32)]
 
 
 class FastqChunk(C.Structure):
@@ -159,6 +171,10 @@ def lib() -> C.CDLL:
         "fqtk_b200_bgzf_bound": (C.c_uint64, [C.c_uint64]),
         "fqtk_b200_bgzf_compress": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, vp, C.c_uint64, u64p]),
         "fqtk_b200_bgzf_compress_device": (C.c_int, [vp, vp, C.c_uint64, C.c_int, vp, C.c_uint64, vp, vp]),
+        "fqtk_b200_bgzf_compress_segments_device": (C.c_int, [vp, vp, u64p, C.c_uint32, C.c_int, vp, C.c_uint64, u64p, vp]),
+        "fqtk_b200_emit_streams": (C.c_int, [C.POINTER(ReadSegment), C.c_uint32, C.c_char_p, u32p, C.c_char_p, u32p]),
+        "fqtk_b200_demux_emit_device": (C.c_int, [C.c_int, C.POINTER(EmitSource), C.c_uint32, C.POINTER(ReadSegment), C.c_uint32,
+                                                  C.c_char_p, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint64, u64p, u64p, vp]),
         "fqtk_b200_synth_panel": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
         "fqtk_b200_synth_reads_host": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, vp]),
         "fqtk_b200_synth_reads_device": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, vp]),

@@ -242,11 +242,16 @@ struct BitWriter {  // one thread, into shared words
     }
 };
 
+struct BzBlockDesc {  // one BGZF block of a segmented input
+    unsigned long long offset;
+    uint32_t bytes, pad;
+};
+
 // ---------------------------------------------------------------------------------------------------- the kernel
 // grid-stride over BGZF blocks; tokens: BZ_WARPS * BZ_TOK_PER_WARP words per CTA.
 __global__ void __launch_bounds__(BZ_THREADS, 2)
     k_bgzf_deflate(const uint8_t* __restrict__ in, uint64_t n_bytes, uint32_t n_blocks, int level, uint8_t* __restrict__ slots,
-                   uint32_t* __restrict__ sizes, uint32_t* __restrict__ tokens_all) {
+                   uint32_t* __restrict__ sizes, uint32_t* __restrict__ tokens_all, const BzBlockDesc* __restrict__ desc) {
     extern __shared__ uint4 s_raw[];
     BzShared& S = *reinterpret_cast<BzShared*>(s_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5, lane_lt = (1u << lane) - 1u;
@@ -254,8 +259,9 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
     for (uint32_t t = tid; t < 256u; t += BZ_THREADS) S.crc_tab[t] = d_crc_table[t];
 
     for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        const uint64_t in_off = (uint64_t)blk * BZ_IN;
-        const uint32_t n = (uint32_t)min((uint64_t)BZ_IN, n_bytes - in_off);
+        // uniform cut every 65 280 bytes, or (segments: several writers' texts in one buffer) the block list given
+        const uint64_t in_off = desc ? desc[blk].offset : (uint64_t)blk * BZ_IN;
+        const uint32_t n = desc ? desc[blk].bytes : (uint32_t)min((uint64_t)BZ_IN, n_bytes - in_off);
         uint8_t* slot = slots + (size_t)blk * BZ_SLOT + 2;  // block image: 18-byte header, then the deflate data 4-byte aligned
         uint32_t* out_words = reinterpret_cast<uint32_t*>(slot + BZ_HDR);
         __syncthreads();  // the previous block's shared state is dead
@@ -722,7 +728,7 @@ static int bgzf_launch(fqtk_b200_bgzf* z, int k, const uint8_t* d_in, uint64_t n
     const uint32_t n_blocks = (uint32_t)((n + BZ_IN - 1) / BZ_IN);
     if (n_blocks == 0) return FQTK_B200_OK;
     const uint32_t grid = std::min<uint32_t>(z->grid, n_blocks);
-    k_bgzf_deflate<<<grid, BZ_THREADS, sizeof(BzShared), st>>>(d_in, n, n_blocks, level, z->d_slots[k], z->d_sizes[k], z->d_tokens + (size_t)k * z->grid * BZ_WARPS * BZ_TOK_PER_WARP);
+    k_bgzf_deflate<<<grid, BZ_THREADS, sizeof(BzShared), st>>>(d_in, n, n_blocks, level, z->d_slots[k], z->d_sizes[k], z->d_tokens + (size_t)k * z->grid * BZ_WARPS * BZ_TOK_PER_WARP, nullptr);
     fq::count_launch();
     k_bgzf_scan<<<1, 1024, 0, st>>>(z->d_sizes[k], n_blocks, z->d_offsets[k]);
     fq::count_launch();
@@ -856,6 +862,59 @@ int fqtk_b200_bgzf_compress(fqtk_b200_bgzf* z, const uint8_t* in, uint64_t n_byt
         written += sizeof(BGZF_EOF);
     }
     *out_bytes = written;
+    return FQTK_B200_OK;
+}
+
+/* several writers' texts in one device buffer: segment k = d_in[seg_offsets[k], seg_offsets[k+1]) is cut every 65 280 bytes
+ * on its own (a member never spans two writers); the members of all segments leave back to back in d_out and
+ * out_seg_offsets[k] (host) says where segment k's members start (out_seg_offsets[n_segments] = total).  No EOF blocks. */
+int fqtk_b200_bgzf_compress_segments_device(fqtk_b200_bgzf* z, const uint8_t* d_in, const uint64_t* seg_offsets,
+                                            uint32_t n_segments, int level, uint8_t* d_out, uint64_t out_capacity,
+                                            uint64_t* out_seg_offsets, void* stream) {
+    if (!z || !seg_offsets || !out_seg_offsets || (n_segments && !d_out)) return bz_fail(FQTK_B200_ERR_ARG, "bgzf_compress_segments_device: null argument");
+    if (level < 0 || level > 12) return bz_fail(FQTK_B200_ERR_ARG, "bgzf_compress_segments_device: compression level must be 0..12");
+    BZ_CU(cudaSetDevice(z->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    std::vector<BzBlockDesc> desc;
+    std::vector<uint32_t> first_block(n_segments + 1, 0);
+    for (uint32_t k = 0; k < n_segments; k++) {
+        if (seg_offsets[k + 1] < seg_offsets[k]) return bz_fail(FQTK_B200_ERR_ARG, "bgzf_compress_segments_device: offsets must not decrease");
+        first_block[k] = (uint32_t)desc.size();
+        for (uint64_t o = seg_offsets[k]; o < seg_offsets[k + 1]; o += BZ_IN)
+            desc.push_back(BzBlockDesc{o, (uint32_t)std::min<uint64_t>(BZ_IN, seg_offsets[k + 1] - o), 0u});
+    }
+    first_block[n_segments] = (uint32_t)desc.size();
+    for (uint32_t k = 0; k <= n_segments; k++) out_seg_offsets[k] = 0;
+    const uint32_t nb = (uint32_t)desc.size();
+    if (nb == 0) return FQTK_B200_OK;
+    if (!d_in) return bz_fail(FQTK_B200_ERR_ARG, "bgzf_compress_segments_device: null input");
+    // scratch of this call: block list, slots, sizes, offsets (the handle's own buffers are sized for uniform chunks)
+    BzBlockDesc* d_desc = nullptr;
+    uint8_t* d_slots = nullptr;
+    uint32_t* d_sizes = nullptr;
+    unsigned long long* d_offs = nullptr;
+    auto release = [&] { cudaFree(d_desc); cudaFree(d_slots); cudaFree(d_sizes); cudaFree(d_offs); };
+    cudaError_t e = cudaMalloc(&d_desc, (size_t)nb * sizeof(BzBlockDesc));
+    if (e == cudaSuccess) e = cudaMalloc(&d_slots, (size_t)nb * BZ_SLOT);
+    if (e == cudaSuccess) e = cudaMalloc(&d_sizes, (size_t)nb * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_offs, ((size_t)nb + 1) * 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_desc, desc.data(), (size_t)nb * sizeof(BzBlockDesc), cudaMemcpyHostToDevice, st);
+    std::vector<unsigned long long> offs(nb + 1);
+    if (e == cudaSuccess) {
+        k_bgzf_deflate<<<std::min<uint32_t>(z->grid, nb), BZ_THREADS, sizeof(BzShared), st>>>(d_in, 0, nb, level, d_slots, d_sizes, z->d_tokens, d_desc);
+        fq::count_launch();
+        k_bgzf_scan<<<1, 1024, 0, st>>>(d_sizes, nb, d_offs);
+        fq::count_launch();
+        k_bgzf_gather<<<std::min<uint32_t>(nb, (uint32_t)z->sm_count * 8u), 256, 0, st>>>(d_slots, d_sizes, d_offs, nb, d_out, out_capacity);
+        fq::count_launch();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(offs.data(), d_offs, ((size_t)nb + 1) * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    release();
+    if (e != cudaSuccess) return bz_fail(FQTK_B200_ERR_CUDA, std::string("bgzf_compress_segments_device: ") + cudaGetErrorString(e));
+    if (offs[nb] > out_capacity) return bz_fail(FQTK_B200_ERR_ARG, "bgzf_compress_segments_device: output buffer too small");
+    for (uint32_t k = 0; k <= n_segments; k++) out_seg_offsets[k] = offs[first_block[k]];
     return FQTK_B200_OK;
 }
 

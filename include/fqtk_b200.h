@@ -341,6 +341,48 @@ FQTK_B200_API int fqtk_b200_bgzf_compress(fqtk_b200_bgzf* z, const uint8_t* in, 
 FQTK_B200_API int fqtk_b200_bgzf_compress_device(fqtk_b200_bgzf* z, const uint8_t* d_in, uint64_t n_bytes, int level,
                                                  uint8_t* d_out, uint64_t out_capacity, uint64_t* d_out_bytes, void* stream);
 
+/* several writers' texts in ONE device buffer (what fqtk_b200_demux_emit_device leaves): segment k =
+ * d_in[seg_offsets[k], seg_offsets[k+1]) is cut every 65 280 bytes on its own, so no member spans two writers; all members
+ * leave back to back in d_out, out_seg_offsets[k] (HOST, n_segments + 1 entries) = where segment k's members start.  No EOF
+ * blocks (append the 28-byte EOF member when a file is closed).  Synchronous on `stream`. */
+FQTK_B200_API int fqtk_b200_bgzf_compress_segments_device(fqtk_b200_bgzf* z, const uint8_t* d_in, const uint64_t* seg_offsets,
+                                                          uint32_t n_segments, int level, uint8_t* d_out,
+                                                          uint64_t out_capacity, uint64_t* out_seg_offsets, void* stream);
+
+/* ---- the routed records written out on the device (SURVEY 8f "next" #3 / #4) ----
+ * SampleWriters::write (demux.rs:396-415) + ReadSet::write_header_internal (:171-267) for a whole batch whose FASTQ chunks are
+ * in device memory: for every output stream — the T, B, M, C segments selected by `output_kinds`, in the order the
+ * reference walks its writers, e.g. R1 R2 I1 — one text buffer region in which every sample's records
+ * (`@<rewritten header>\n<bases>\n+\n<quals>\n`) form one contiguous run in input order.  The header of a record is
+ * the FIRST input's header rewritten: read number, UMI (M) segments appended to the name, sample-barcode (B) segments
+ * appended to the comment's index field.
+ *   sources[s]     chunk + the tables of fqtk_b200_fastq_scan_device (d_head_offsets is needed for source 0 only)
+ *   segments       EVERY segment of every read structure, inputs in order, segments in read order
+ *   d_order, d_offsets   fqtk_b200_matcher_route_device's output for the batch (n_buckets = S + 1)
+ *   file_offsets   HOST out, [n_streams][n_buckets + 1]: (stream t, bucket b) = d_text[file_offsets[t][b], file_offsets[t][b+1])
+ * Header rule violations (demux.rs:190-194,229-233) fail the call with the reference's text and the read's index. */
+typedef struct {
+    const uint8_t* d_chunk;
+    uint64_t chunk_bytes;
+    const uint64_t* d_head_offsets;
+    const uint64_t* d_seq_offsets;
+    const uint32_t* d_seq_lengths;
+} fqtk_b200_emit_source;
+typedef struct {
+    uint32_t source; /* which input */
+    uint32_t kind;   /* 'T', 'B', 'M', 'S' or 'C' */
+    uint32_t offset; /* first base of the segment in the read */
+    uint32_t length; /* bases, or FQTK_B200_SEGMENT_REST */
+} fqtk_b200_read_segment;
+/* which streams `output_kinds` selects: kind letter and 1-based number of each (file name <prefix>.<R|I|U|C><number>.fq.gz) */
+FQTK_B200_API int fqtk_b200_emit_streams(const fqtk_b200_read_segment* segments, uint32_t n_segments, const char* output_kinds,
+                                         uint32_t* n_streams, char* stream_kinds, uint32_t* stream_numbers);
+FQTK_B200_API int fqtk_b200_demux_emit_device(int device, const fqtk_b200_emit_source* sources, uint32_t n_sources,
+                                              const fqtk_b200_read_segment* segments, uint32_t n_segments,
+                                              const char* output_kinds, const uint32_t* d_order, const uint64_t* d_offsets,
+                                              uint32_t n_buckets, uint64_t n_reads, uint8_t* d_text, uint64_t text_capacity,
+                                              uint64_t* file_offsets, uint64_t* text_bytes, void* stream);
+
 /* ---- deterministic synthetic workload; counter-based, identical on host and device ----
  * Panel: S barcodes of length L over ACGT with pairwise Hamming distance >= min_distance (greedy, rejection);
  * `n_degenerate` positions per barcode are then rewritten to IUPAC degenerate codes (cfg 5).

@@ -229,3 +229,80 @@ def test_gpu_fuzz_structured_inputs():
             assert payload == data, (i, len(data))
             assert sizes[:-1] == [65280] * (len(data) // 65280) + ([len(data) % 65280] if len(data) % 65280 else [])
             assert len(img) <= len(data) + 31 * (len(sizes) - 1) + 28  # never larger than stored blocks
+
+
+@pytest.mark.gpu
+def test_gpu_whole_data_path_equals_the_host_formatted_pipeline():
+    """FASTQ text in -> per-sample BGZF images out with everything on the device (scan, match, route, record writing with
+    header rewrite, BGZF per sample) against the host-formatted pipeline (fqtk_b200.fastq.demux_fastq_batch, itself pinned by
+    the reference's end-to-end tests): same files, same bytes after inflation — the reference's five end-to-end vectors
+    (multiple output types, UMIs, four inputs, several templates per read, +T), then 60 000 dual-index paired-end reads with
+    CRLF lines, comments of every kind the header rules distinguish, a trailing +B, and reads that are too short."""
+    import json
+    import os
+
+    from fqtk_b200 import BarcodeMatcher, synth
+    from fqtk_b200.bgzf import BgzfCompressor
+    from fqtk_b200.demux import TooFewBases, fastq_text as records_text
+    from fqtk_b200.fastq import demux_fastq_batch
+    from fqtk_b200.gpu_demux import demux_fastq_batch_gpu
+
+    def check(m, z, ids, bcs, structures, texts, types, **kw):
+        want = demux_fastq_batch(m, ids, bcs, structures, texts, types, **kw)
+        m.reset_counts()
+        got = demux_fastq_batch_gpu(m, z, ids, bcs, structures, texts, types, **kw)
+        assert set(got.files) == set(want.files)
+        for name, recs in want.files.items():
+            payload, sizes = ob.parse(got.files[name])
+            assert payload == records_text(recs), name
+            assert sizes[-1] == 0 and all(x == 65280 for x in sizes[:-2])
+        assert np.array_equal(got.counts, want.counts) and got.skipped == want.skipped
+        assert [(x.sample_id, x.templates) for x in got.metrics] == [(x.sample_id, x.templates) for x in want.metrics]
+        return got
+
+    kats = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
+    with BgzfCompressor(0) as z:
+        for case in kats["demux_e2e"]:
+            S = len(case["barcodes"])
+            ids = [f"Sample{j:04d}" for j in range(S)]
+            texts = ["".join(f"@ex_{i}\n{b}\n+\n{';' * len(b)}\n" for i, b in enumerate(col)).encode() for col in case["inputs"]]
+            with BarcodeMatcher(case["barcodes"], case["max_mismatches"], case["min_mismatch_delta"]) as m:
+                got = check(m, z, ids, case["barcodes"], case["read_structures"], texts, case["output_types"])
+                assert set(got.files) == set(case["expect"])
+        # at size
+        cfg = synth.CONFIGS[3]
+        panel = synth.panel(cfg)
+        bcs = [bytes(r).decode() for r in panel]
+        ids = [f"S{j}" for j in range(len(bcs))]
+        n = 60_000
+        reads = synth.reads_host(panel, cfg.seed_reads, 7, n)
+        rng = np.random.default_rng(3)
+        comments = [b"", b" 1:N:0:0", b" 2:Y:18:ACGTACGT", b" 1:N:0:", b" 0:0", b" x"]
+        r1, r2, i1, i2 = [], [], [], []
+        for i in range(n):
+            name = b"@A00:1:HX:1:1101:%d:%d" % (1000 + i % 977, 2000 + i // 7)
+            cm = comments[i % len(comments)]
+            eol = b"\r\n" if i % 11 == 0 else b"\n"
+            t1 = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(rng.integers(20, 60))))
+            t2 = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(rng.integers(20, 60))))
+            q = lambda s: bytes(rng.integers(35, 74, size=len(s), dtype=np.uint8))
+            umi = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=6))
+            r1.append(name + cm + eol + umi + t1 + eol + b"+" + eol + q(umi + t1) + eol)
+            r2.append(name + cm.replace(b" 1:", b" 2:") + eol + t2 + eol + b"+" + eol + q(t2) + eol)
+            b1, b2 = bytes(reads[i, 0:8]), bytes(reads[i, 8:16])
+            i1.append(name + cm + eol + b1 + eol + b"+" + eol + b"F" * 8 + eol)
+            i2.append(name + cm + eol + b2 + eol + b"+" + eol + b"F" * 8 + eol)
+        texts = [b"".join(x) for x in (r1, r2, i1, i2)]
+        with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta) as m:
+            got = check(m, z, ids, bcs, ["6M+T", "+T", "8B", "+B"], texts, ["T", "B", "M"])
+            assert len(got.files) > 3 * 300 and got.text_bytes > 10_000_000
+            # too few bases: an error by default, skipped on request
+            texts[2] = texts[2].replace(b"\n" + bytes(reads[5, 0:8]) + b"\n+\nFFFFFFFF\n", b"\n" + bytes(reads[5, 0:3]) + b"\n+\nFFF\n", 1)
+            with pytest.raises(TooFewBases) as e1:
+                demux_fastq_batch_gpu(m, z, ids, bcs, ["6M+T", "+T", "8B", "+B"], texts, ["T"])
+            with pytest.raises(TooFewBases) as e2:
+                demux_fastq_batch(m, ids, bcs, ["6M+T", "+T", "8B", "+B"], texts, ["T"])
+            assert str(e1.value) == str(e2.value)
+            m.reset_counts()
+            got = check(m, z, ids, bcs, ["6M+T", "+T", "8B", "+B"], texts, ["T"], skip_too_few_bases=True)
+            assert got.skipped == 1
