@@ -667,6 +667,77 @@ def measure_bgzf(ctx, args):
             "members_checked": len(sizes)}
 
 
+def measure_gpu_demux(ctx, args):
+    """The whole per-batch data path on the device (fqtk_b200.gpu_demux): paired-end 150 + dual 8 bp index FASTQ text of the
+    headline panel in pinned host memory -> scan, match, route, records with rewritten headers, BGZF per sample -> the
+    compressed images back on the host.  Wall clock around the call, PCIe copies inside."""
+    import oracle.bgzf as ob
+    from fqtk_b200 import BarcodeMatcher, synth
+    from fqtk_b200.bgzf import BgzfCompressor
+    from fqtk_b200.gpu_demux import demux_fastq_batch_gpu
+
+    cfg = synth.CONFIGS[3]
+    panel = synth.panel(cfg)
+    bcs = [bytes(r).decode() for r in panel]
+    ids = [f"S{j:03d}" for j in range(len(bcs))]
+    n, rl = 400_000, 150
+    reads = host_reads(panel, cfg.seed_reads, 0, n)
+    rng = np.random.default_rng(99)
+    head = np.frombuffer(b"@A00123:45:HXXXXXXXX:1:1101:", dtype=np.uint8)
+
+    def fastq(seqs, comment):
+        w = seqs.shape[1]
+        coords = np.frombuffer(b"".join(b"%05d:%05d" % (1000 + i % 30000, 1000 + (i * 7) % 30000) for i in range(n)), dtype=np.uint8).reshape(n, 11)
+        cm = np.frombuffer(comment, dtype=np.uint8)
+        rec = np.empty((n, head.size + 11 + cm.size + 1 + w + 3 + w + 1), dtype=np.uint8)
+        p0 = 0
+        for piece in (head, coords, cm, b"\n", seqs, b"\n+\n", None, b"\n"):
+            if piece is None:
+                piece = np.frombuffer(b"F:,#", dtype=np.uint8)[np.minimum(3, rng.geometric(0.75, size=(n, w)) - 1)]
+            arr = np.frombuffer(piece, dtype=np.uint8) if isinstance(piece, bytes) else piece
+            rec[:, p0:p0 + arr.shape[-1]] = arr
+            p0 += arr.shape[-1]
+        return rec.reshape(-1)
+
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    texts = [fastq(acgt[rng.integers(0, 4, size=(n, rl))], b" 1:N:0:0"), fastq(acgt[rng.integers(0, 4, size=(n, rl))], b" 2:N:0:0"),
+             fastq(reads[:, :8], b" 1:N:0:0"), fastq(reads[:, 8:16], b" 2:N:0:0")]
+    in_bytes = sum(int(t.size) for t in texts)
+    import ctypes as C
+
+    from fqtk_b200 import _lib
+    pinned = []
+    for k, t in enumerate(texts):  # the reader's chunk buffers live in pinned memory
+        q = C.c_void_p()
+        _lib.check(_lib.lib().fqtk_b200_host_alloc(C.byref(q), int(t.size)))
+        pinned.append(q)
+        v = np.ctypeslib.as_array(C.cast(q, C.POINTER(C.c_uint8)), shape=(int(t.size),))
+        v[:] = t
+        texts[k] = v
+    with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta, device=ctx.local) as m, BgzfCompressor(ctx.local) as z:
+        res = demux_fastq_batch_gpu(m, z, ids, bcs, ["+T", "+T", "8B", "8B"], texts, ["T"], device=ctx.local)
+        m.reset_counts()
+        ctx.torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            res = demux_fastq_batch_gpu(m, z, ids, bcs, ["+T", "+T", "8B", "8B"], texts, ["T"], device=ctx.local)
+            m.reset_counts()
+        sec = (time.perf_counter() - t0) / reps
+    del texts
+    for q in pinned:
+        _lib.lib().fqtk_b200_host_free(q)
+    out_bytes = sum(len(v) for v in res.files.values())
+    name = next(iter(sorted(res.files)))
+    payload, _ = ob.parse(res.files[name])  # one file read back by the strict parser (outside the timed region)
+    assert payload.count(b"\n") % 4 == 0 and int(res.counts.sum()) == n
+    return {"what": "FASTQ text (R1 + R2 150 bases, I1 + I2 8 bases; pinned host memory) -> scan, match, route, records with rewritten "
+                    "headers, BGZF level 5 per sample (385 x 2 files) -> compressed images on the host; one call of "
+                    "fqtk_b200.gpu_demux.demux_fastq_batch_gpu, wall clock, copies inside",
+            "reads": n, "input_bytes": in_bytes, "text_bytes": res.text_bytes, "output_bytes": out_bytes, "files": len(res.files),
+            "ms": round(sec * 1e3, 2), "mreads_per_s": round(n / sec / 1e6, 2), "gb_per_s_in": round(in_bytes / sec / 1e9, 2)}
+
+
 def measure_fastq(ctx, args, cfg, panel, matcher):
     """The ingest side: the headline config's barcodes taken straight out of in-memory, uncompressed
     index FASTQ chunks (I1 and I2, 8 bases each at cfg 3): fqtk_b200_fastq_scan (host, one thread per chunk) -> per-read
@@ -962,6 +1033,8 @@ def run_b200(args):
     bgzf = None
     if rank == 0 and not args.no_bgzf:
         bgzf = measure_bgzf(ctx, args)
+        torch.cuda.empty_cache()
+        bgzf["whole_data_path"] = measure_gpu_demux(ctx, args)
         torch.cuda.empty_cache()
 
     # ---- the other configs of BASELINE.json: cfg 2 weak; cfg 4 and cfg 5 STRONG over the N ranks ----

@@ -889,15 +889,15 @@ int fqtk_b200_bgzf_compress_segments_device(fqtk_b200_bgzf* z, const uint8_t* d_
     if (nb == 0) return FQTK_B200_OK;
     if (!d_in) return bz_fail(FQTK_B200_ERR_ARG, "bgzf_compress_segments_device: null input");
     // scratch of this call: block list, slots, sizes, offsets (the handle's own buffers are sized for uniform chunks)
-    BzBlockDesc* d_desc = nullptr;
-    uint8_t* d_slots = nullptr;
-    uint32_t* d_sizes = nullptr;
-    unsigned long long* d_offs = nullptr;
-    auto release = [&] { cudaFree(d_desc); cudaFree(d_slots); cudaFree(d_sizes); cudaFree(d_offs); };
-    cudaError_t e = cudaMalloc(&d_desc, (size_t)nb * sizeof(BzBlockDesc));
-    if (e == cudaSuccess) e = cudaMalloc(&d_slots, (size_t)nb * BZ_SLOT);
-    if (e == cudaSuccess) e = cudaMalloc(&d_sizes, (size_t)nb * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&d_offs, ((size_t)nb + 1) * 8);
+    fq::TempBuf t_desc, t_slots, t_sizes, t_offs;
+    cudaError_t e = t_desc.alloc((size_t)nb * sizeof(BzBlockDesc), st);
+    if (e == cudaSuccess) e = t_slots.alloc((size_t)nb * BZ_SLOT, st);
+    if (e == cudaSuccess) e = t_sizes.alloc((size_t)nb * 4, st);
+    if (e == cudaSuccess) e = t_offs.alloc(((size_t)nb + 1) * 8, st);
+    BzBlockDesc* d_desc = t_desc.as<BzBlockDesc>();
+    uint8_t* d_slots = t_slots.as<uint8_t>();
+    uint32_t* d_sizes = t_sizes.as<uint32_t>();
+    unsigned long long* d_offs = t_offs.as<unsigned long long>();
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_desc, desc.data(), (size_t)nb * sizeof(BzBlockDesc), cudaMemcpyHostToDevice, st);
     std::vector<unsigned long long> offs(nb + 1);
     if (e == cudaSuccess) {
@@ -911,7 +911,6 @@ int fqtk_b200_bgzf_compress_segments_device(fqtk_b200_bgzf* z, const uint8_t* d_
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(offs.data(), d_offs, ((size_t)nb + 1) * 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    release();
     if (e != cudaSuccess) return bz_fail(FQTK_B200_ERR_CUDA, std::string("bgzf_compress_segments_device: ") + cudaGetErrorString(e));
     if (offs[nb] > out_capacity) return bz_fail(FQTK_B200_ERR_ARG, "bgzf_compress_segments_device: output buffer too small");
     for (uint32_t k = 0; k <= n_segments; k++) out_seg_offsets[k] = offs[first_block[k]];

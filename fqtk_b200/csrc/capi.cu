@@ -1476,13 +1476,17 @@ int fqtk_b200_matcher_assign_fastq(fqtk_b200_matcher* m, const fqtk_b200_fastq_s
 
 // ---- the record scanner on the device + the batch call on whole chunks ------------------------------------------------
 namespace {
-struct DevScan {  // temporaries of one chunk's scan
+struct DevScan {  // temporaries of one chunk's scan (stream-ordered: fq::temp_alloc)
     uint32_t* tile_counts = nullptr;
     unsigned long long* prefix = nullptr;  // tiles + 1
     unsigned long long* nl = nullptr;
     unsigned long long* err = nullptr;     // 1 scan error word + 2 vetting words
+    cudaStream_t stream = nullptr;
     ~DevScan() {
-        cudaFree(tile_counts); cudaFree(prefix); cudaFree(nl); cudaFree(err);
+        if (tile_counts) cudaFreeAsync(tile_counts, stream);
+        if (prefix) cudaFreeAsync(prefix, stream);
+        if (nl) cudaFreeAsync(nl, stream);
+        if (err) cudaFreeAsync(err, stream);
     }
 };
 const char* const SCAN_ERR[3] = {"header line does not start with '@'", "separator line does not start with '+'",
@@ -1503,9 +1507,10 @@ int fqtk_b200_fastq_scan_device(int device, const uint8_t* d_chunk, uint64_t chu
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t tiles = fq::fastq_scan_tiles(chunk_bytes);
     DevScan t;
-    CU(cudaMalloc(&t.tile_counts, (size_t)tiles * 4));
-    CU(cudaMalloc(&t.prefix, ((size_t)tiles + 1) * 8));
-    CU(cudaMalloc(&t.err, 8));
+    t.stream = st;
+    CU(fq::temp_alloc(reinterpret_cast<void**>(&t.tile_counts), (size_t)tiles * 4, st));
+    CU(fq::temp_alloc(reinterpret_cast<void**>(&t.prefix), ((size_t)tiles + 1) * 8, st));
+    CU(fq::temp_alloc(reinterpret_cast<void**>(&t.err), 8, st));
     CU(cudaMemsetAsync(t.err, 0xFF, 8, st));
     CU(fq::launch_nl_count(d_chunk, chunk_bytes, t.tile_counts, t.prefix, st));
     unsigned long long total_nl = 0;
@@ -1513,7 +1518,7 @@ int fqtk_b200_fastq_scan_device(int device, const uint8_t* d_chunk, uint64_t chu
     CU(cudaStreamSynchronize(st));
     const uint64_t n = std::min<uint64_t>(total_nl / 4, max_records);
     if (n == 0) return FQTK_B200_OK;
-    CU(cudaMalloc(&t.nl, (size_t)n * 4 * 8));
+    CU(fq::temp_alloc(reinterpret_cast<void**>(&t.nl), (size_t)n * 4 * 8, st));
     CU(fq::launch_fq_records(d_chunk, chunk_bytes, t.prefix, n * 4, t.nl, n, reinterpret_cast<unsigned long long*>(d_head_offsets),
                              reinterpret_cast<unsigned long long*>(d_seq_offsets), d_seq_lengths, t.err, geo, st));
     unsigned long long err = 0, last_nl = 0;
@@ -1566,9 +1571,10 @@ int fqtk_b200_matcher_assign_fastq_chunks(fqtk_b200_matcher* m, const fqtk_b200_
     for (uint32_t s = 0; s < n_sources; s++) {
         if ((rc = ensure(3 * s, chunks[s].bytes)) != FQTK_B200_OK) return rc;
         const uint32_t tiles = fq::fastq_scan_tiles(chunks[s].bytes);
-        CU(cudaMalloc(&t[s].tile_counts, (size_t)tiles * 4 + 4));
-        CU(cudaMalloc(&t[s].prefix, ((size_t)tiles + 1) * 8));
-        CU(cudaMalloc(&t[s].err, 24));
+        t[s].stream = st;
+        CU(fq::temp_alloc(reinterpret_cast<void**>(&t[s].tile_counts), (size_t)tiles * 4 + 4, st));
+        CU(fq::temp_alloc(reinterpret_cast<void**>(&t[s].prefix), ((size_t)tiles + 1) * 8, st));
+        CU(fq::temp_alloc(reinterpret_cast<void**>(&t[s].err), 24, st));
         CU(cudaMemsetAsync(t[s].err, 0xFF, 24, st));
         CU(cudaMemcpyAsync(m->d_fq[3 * s], chunks[s].data, chunks[s].bytes, cudaMemcpyHostToDevice, st));
         CU(fq::launch_nl_count(static_cast<const uint8_t*>(m->d_fq[3 * s]), chunks[s].bytes, t[s].tile_counts, t[s].prefix, st));
@@ -1586,7 +1592,7 @@ int fqtk_b200_matcher_assign_fastq_chunks(fqtk_b200_matcher* m, const fqtk_b200_
     for (uint32_t s = 0; s < n_sources; s++) {
         if ((rc = ensure(3 * s + 1, n * 8)) != FQTK_B200_OK) return rc;
         if ((rc = ensure(3 * s + 2, n * 4)) != FQTK_B200_OK) return rc;
-        CU(cudaMalloc(&t[s].nl, (size_t)n * 4 * 8));
+        CU(fq::temp_alloc(reinterpret_cast<void**>(&t[s].nl), (size_t)n * 4 * 8, st));
         const uint8_t* d_chunk = static_cast<const uint8_t*>(m->d_fq[3 * s]);
         CU(fq::launch_fq_records(d_chunk, chunks[s].bytes, t[s].prefix, n * 4, t[s].nl, n, nullptr,
                                  static_cast<unsigned long long*>(m->d_fq[3 * s + 1]), static_cast<uint32_t*>(m->d_fq[3 * s + 2]),
@@ -1743,6 +1749,19 @@ int fqtk_b200_matcher_reset_counts(fqtk_b200_matcher* m) {
 int fqtk_b200_host_alloc(void** ptr, size_t bytes) {
     if (!ptr) return fail(FQTK_B200_ERR_ARG, "NULL argument");
     CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    return FQTK_B200_OK;
+}
+
+/* asynchronous copies between host memory (pinned for full rate) and device memory on `stream`: for hosts that hold their
+ * device buffers elsewhere (the Python mirrors keep them in torch tensors) */
+int fqtk_b200_copy_to_device(void* d_dst, const void* src, uint64_t bytes, void* stream) {
+    if (bytes && (!d_dst || !src)) return fail(FQTK_B200_ERR_ARG, "NULL argument");
+    CU(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return FQTK_B200_OK;
+}
+int fqtk_b200_copy_to_host(void* dst, const void* d_src, uint64_t bytes, void* stream) {
+    if (bytes && (!dst || !d_src)) return fail(FQTK_B200_ERR_ARG, "NULL argument");
+    CU(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return FQTK_B200_OK;
 }
 

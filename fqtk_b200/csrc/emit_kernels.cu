@@ -327,11 +327,6 @@ int em_fail(int code, const std::string& msg) {
         if (e__ != cudaSuccess) return em_fail(FQTK_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
 
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { cudaFree(p); }
-};
-
 }  // namespace
 
 extern "C" {
@@ -409,13 +404,13 @@ int fqtk_b200_demux_emit_device(int device, const fqtk_b200_emit_source* sources
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t n = n_reads;
     const uint32_t n_tiles = (uint32_t)((n + EM_TILE - 1) / EM_TILE);
-    DevBuf lens, tiles, pre, base, err, foff;
-    EM_CU(cudaMalloc(&lens.p, (size_t)ns * n * 4));
-    EM_CU(cudaMalloc(&tiles.p, (size_t)ns * (n_tiles + 1) * 8));
-    EM_CU(cudaMalloc(&pre.p, (size_t)ns * (n + 1) * 8));
-    EM_CU(cudaMalloc(&base.p, (size_t)EM_MAX_STREAMS * 8));
-    EM_CU(cudaMalloc(&err.p, 8));
-    EM_CU(cudaMalloc(&foff.p, (size_t)ns * (n_buckets + 1) * 8));
+    fq::TempBuf lens, tiles, pre, base, err, foff;
+    EM_CU(lens.alloc((size_t)ns * n * 4, st));
+    EM_CU(tiles.alloc((size_t)ns * (n_tiles + 1) * 8, st));
+    EM_CU(pre.alloc((size_t)ns * (n + 1) * 8, st));
+    EM_CU(base.alloc((size_t)EM_MAX_STREAMS * 8, st));
+    EM_CU(err.alloc(8, st));
+    EM_CU(foff.alloc((size_t)ns * (n_buckets + 1) * 8, st));
     EM_CU(cudaMemsetAsync(err.p, 0xFF, 8, st));
     const uint32_t gx = (uint32_t)std::min<uint64_t>((n + EM_THREADS - 1) / EM_THREADS, (uint64_t)sm * 8);
     k_emit_lengths<<<dim3(gx, ns), EM_THREADS, 0, st>>>(p, d_order, n, static_cast<uint32_t*>(lens.p),

@@ -150,6 +150,38 @@ cudaError_t launch_route(const uint32_t* d_results, uint64_t n, uint32_t S, uint
                          unsigned long long* d_offsets, void* d_workspace, const LaunchGeometry& g, cudaStream_t stream);
 cudaError_t launch_pack_offsets(const OffsetSource& seg, uint64_t n, uint32_t L, uint32_t* d_packed, uint32_t* d_lengths,
                                 const LaunchGeometry& g, cudaStream_t stream);
+// Stream-ordered temporaries (cudaMallocAsync from the device's default pool, which is told once to keep what it is given
+// back instead of returning it to the driver at every synchronisation): the per-call scratch of the scanner, the record
+// writer and the segmented BGZF call costs microseconds, not a cudaMalloc / cudaFree pair per buffer.
+inline cudaError_t temp_alloc(void** p, size_t bytes, cudaStream_t stream) {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        configured[dev] = true;
+    }
+    return cudaMallocAsync(p, bytes ? bytes : 1, stream);
+}
+struct TempBuf {  // freed in stream order when it goes out of scope
+    void* p = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaError_t alloc(size_t bytes, cudaStream_t st) {
+        stream = st;
+        return temp_alloc(&p, bytes, st);
+    }
+    template <typename T>
+    T* as() const { return static_cast<T*>(p); }
+    ~TempBuf() {
+        if (p) cudaFreeAsync(p, stream);
+    }
+};
+
 // device FASTQ scanner (ingest_kernels.cu)
 uint32_t fastq_scan_tiles(uint64_t bytes);
 cudaError_t launch_nl_count(const uint8_t* d_chunk, uint64_t bytes, uint32_t* d_tile_counts, unsigned long long* d_prefix,

@@ -34,6 +34,29 @@ class GpuDemuxResult:
     text_bytes: int = 0                         # uncompressed FASTQ bytes written on the device
 
 
+_PINNED = {"ptr": None, "cap": 0}
+
+
+def _pinned_out(nbytes: int) -> np.ndarray:
+    """A grow-only pinned host buffer for the compressed images (fqtk_b200_host_alloc): the D2H copy runs at full rate."""
+    lib = _lib.lib()
+    if nbytes > _PINNED["cap"]:
+        if _PINNED["ptr"]:
+            lib.fqtk_b200_host_free(_PINNED["ptr"])
+        p = C.c_void_p()
+        cap = max(nbytes * 5 // 4, 1 << 20)
+        _lib.check(lib.fqtk_b200_host_alloc(C.byref(p), cap))
+        _PINNED["ptr"], _PINNED["cap"] = p, cap
+    if nbytes == 0:
+        return np.zeros(0, dtype=np.uint8)
+    return np.ctypeslib.as_array(C.cast(_PINNED["ptr"], C.POINTER(C.c_uint8)), shape=(nbytes,))
+
+
+def _cuda_memcpy(dst: int, src: int, nbytes: int, stream: int, to_device: bool) -> None:
+    lib = _lib.lib()
+    _lib.check((lib.fqtk_b200_copy_to_device if to_device else lib.fqtk_b200_copy_to_host)(dst, src, nbytes, stream or None))
+
+
 def read_segments(structures) -> list[tuple[int, str, int, int]]:
     """(source, kind, offset, length | SEGMENT_REST) of every segment of the read structures, inputs in order."""
     out = []
@@ -62,7 +85,9 @@ def demux_fastq_batch_gpu(matcher, compressor, sample_ids: Sequence[str], barcod
     d_chunks, tables = [], []
     for text in fastq_texts:
         arr = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else text
-        d = torch.from_numpy(arr.copy() if arr.size else np.zeros(1, np.uint8)).to(dev)
+        d = torch.empty(max(int(arr.size), 1), dtype=torch.uint8, device=dev)
+        if arr.size:  # straight from the caller's buffer (pinned memory makes this a full-rate asynchronous copy)
+            _cuda_memcpy(d.data_ptr(), arr.ctypes.data, int(arr.size), stream, to_device=True)
         cap = max(1, int(arr.size) // 7 + 1)
         d_head = torch.empty(cap, dtype=torch.int64, device=dev)
         d_seq = torch.empty(cap, dtype=torch.int64, device=dev)
@@ -141,7 +166,10 @@ def demux_fastq_batch_gpu(matcher, compressor, sample_ids: Sequence[str], barcod
         _lib.check(lib.fqtk_b200_bgzf_compress_segments_device(compressor._h, d_text.data_ptr(), seg_off.ctypes.data_as(C.POINTER(C.c_uint64)),
                                                                n_seg, level, d_out.data_ptr(), out_cap,
                                                                out_off.ctypes.data_as(C.POINTER(C.c_uint64)), stream))
-        image = d_out[:int(out_off[-1])].cpu().numpy()
+        image = _pinned_out(int(out_off[-1]))
+        if image.size:
+            _cuda_memcpy(image.ctypes.data, d_out.data_ptr(), int(image.size), stream, to_device=False)
+            torch.cuda.current_stream(dev).synchronize()
         for t in range(n_streams):
             code = FILE_TYPE_CODE[skinds.raw[t:t + 1].decode()]
             for b in range(S + 1):

@@ -318,6 +318,9 @@ FQTK_B200_API int fqtk_b200_device_count(void);
 /* ---- pinned host memory for the host-buffer calls ---- */
 FQTK_B200_API int fqtk_b200_host_alloc(void** ptr, size_t bytes);
 FQTK_B200_API int fqtk_b200_host_free(void* ptr);
+/* asynchronous copies on `stream` between host memory (pinned: full PCIe rate) and device memory */
+FQTK_B200_API int fqtk_b200_copy_to_device(void* d_dst, const void* src, uint64_t bytes, void* stream);
+FQTK_B200_API int fqtk_b200_copy_to_host(void* dst, const void* d_src, uint64_t bytes, void* stream);
 
 /* ---- BGZF output compression (SURVEY 8f "next" #4; replaces the reference's pooled BGZF writers) ----
  * src/bin/commands/demux.rs:755-798 builds `PoolBuilder::<_, BgzfCompressor>` (pooled-writer 0.4.0 -> bgzf crate ->

@@ -306,3 +306,33 @@ def test_gpu_whole_data_path_equals_the_host_formatted_pipeline():
             m.reset_counts()
             got = check(m, z, ids, bcs, ["6M+T", "+T", "8B", "+B"], texts, ["T"], skip_too_few_bases=True)
             assert got.skipped == 1
+
+
+@pytest.mark.gpu
+def test_gpu_header_rewrite_reference_vectors():
+    """The reference's six write_header tests (demux.rs:2084-2196) through the device kernel: a one-record FASTQ whose read
+    structure yields the test's sample-barcode and UMI segments, two template streams so that read number 2 exists."""
+    import json
+    import os
+
+    from fqtk_b200 import BarcodeMatcher
+    from fqtk_b200.bgzf import BgzfCompressor
+    from fqtk_b200.gpu_demux import demux_fastq_batch_gpu
+
+    kats = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
+    with BgzfCompressor(0) as z:
+        for case in kats["write_header"]:
+            bcs, umis = case["sample_barcodes"], case["umis"]
+            seq = "".join(bcs) + "".join(umis) + "AC"
+            structure = "".join(f"{len(b)}B" for b in bcs) + "".join(f"{len(u)}M" for u in umis) + "1T1T"
+            text = f"@{case['header']}\n{seq}\n+\n{'I' * len(seq)}\n".encode()
+            with BarcodeMatcher(["".join(bcs)], 0, 0) as m:
+                if "expect_error" in case:
+                    with pytest.raises(_lib.Fqtk_b200Error) as e:
+                        demux_fastq_batch_gpu(m, z, ["s"], ["".join(bcs)], [structure], [text], ["T"])
+                    assert case["expect_error"] in e.value.message, case["source"]
+                    continue
+                got = demux_fastq_batch_gpu(m, z, ["s"], ["".join(bcs)], [structure], [text], ["T"])
+            lines = gzip.decompress(got.files[f"s.R{case['read_num']}.fq.gz"]).split(b"\n")
+            assert lines[0].decode() == case["expect"], case["source"]
+            assert lines[1] in (b"A", b"C") and lines[2] == b"+" and lines[3] == b"I"
