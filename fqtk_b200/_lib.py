@@ -40,6 +40,7 @@ SYMBOLS = [
     "fqtk_b200_bgzf_create", "fqtk_b200_bgzf_destroy", "fqtk_b200_bgzf_chunk_bytes", "fqtk_b200_bgzf_bound",
     "fqtk_b200_bgzf_compress", "fqtk_b200_bgzf_compress_device", "fqtk_b200_bgzf_compress_segments_device",
     "fqtk_b200_emit_streams", "fqtk_b200_demux_emit_device", "fqtk_b200_copy_to_device", "fqtk_b200_copy_to_host",
+    "fqtk_b200_demux_chunks",
 ]
 
 
@@ -175,6 +176,8 @@ def lib() -> C.CDLL:
         "fqtk_b200_emit_streams": (C.c_int, [C.POINTER(ReadSegment), C.c_uint32, C.c_char_p, u32p, C.c_char_p, u32p]),
         "fqtk_b200_demux_emit_device": (C.c_int, [C.c_int, C.POINTER(EmitSource), C.c_uint32, C.POINTER(ReadSegment), C.c_uint32,
                                                   C.c_char_p, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint64, u64p, u64p, vp]),
+        "fqtk_b200_demux_chunks": (C.c_int, [vp, vp, C.POINTER(FastqChunk), C.c_uint32, C.POINTER(ReadSegment), C.c_uint32, C.c_char_p,
+                                             C.c_int, C.c_uint64, vp, C.c_uint64, u64p, u32p, u64p, u64p, u64p]),
         "fqtk_b200_copy_to_device": (C.c_int, [vp, vp, C.c_uint64, vp]),
         "fqtk_b200_copy_to_host": (C.c_int, [vp, vp, C.c_uint64, vp]),
         "fqtk_b200_synth_panel": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]),

@@ -122,6 +122,8 @@ struct fqtk_b200_matcher {
     uint32_t* d_seg_packed[N_PIPE] = {};  // packed scratch per pipeline slot for the host segment gather
     void* d_fq[3 * FQTK_B200_MAX_SEGMENTS] = {};  // raw FASTQ chunks + their offset / length tables (assign_fastq)
     size_t fq_cap[3 * FQTK_B200_MAX_SEGMENTS] = {};
+    void* d_fq_head[FQTK_B200_MAX_SEGMENTS] = {};  // header offsets of the records (the whole-batch path)
+    size_t fq_head_cap[FQTK_B200_MAX_SEGMENTS] = {};
     uint32_t* d_fq_len = nullptr;  // gathered barcode lengths (REST segments)
     size_t fq_len_cap = 0;
     size_t seg_packed_words[N_PIPE] = {};
@@ -1037,6 +1039,8 @@ void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m) {
     if (m->d_scratch) cudaFree(m->d_scratch);
     for (void* q : m->d_fq)
         if (q) cudaFree(q);
+    for (void* q : m->d_fq_head)
+        if (q) cudaFree(q);
     if (m->d_fq_len) cudaFree(m->d_fq_len);
     if (m->d_route_ws) cudaFree(m->d_route_ws);
     for (int s = 0; s < N_PIPE; s++)
@@ -1532,9 +1536,14 @@ int fqtk_b200_fastq_scan_device(int device, const uint8_t* d_chunk, uint64_t chu
     return FQTK_B200_OK;
 }
 
-int fqtk_b200_matcher_assign_fastq_chunks(fqtk_b200_matcher* m, const fqtk_b200_fastq_chunk* chunks, uint32_t n_sources,
-                                          const fqtk_b200_fastq_segment* segs, uint32_t n_segs, uint64_t max_reads,
-                                          uint32_t* results, uint64_t* n_reads, uint64_t* consumed) {
+// Shared by fqtk_b200_matcher_assign_fastq_chunks and fqtk_b200_demux_chunks: chunks to the device, records found and vetted
+// there, B segments matched; the result words stay in m->d_out[0] (`results` != NULL: also copied to the host), the record
+// tables in m->d_fq[] (`dev_out`), header offsets in m->d_fq_head[] when `min_len` is given (the whole-batch path: every
+// read must hold ALL segments of its read structure, demux.rs:298-315, not only the B ones).
+static int ingest_chunks_impl(fqtk_b200_matcher* m, const fqtk_b200_fastq_chunk* chunks, uint32_t n_sources,
+                              const fqtk_b200_fastq_segment* segs, uint32_t n_segs, uint64_t max_reads, uint32_t* results,
+                              uint64_t* n_reads, uint64_t* consumed, const uint32_t* min_len, fqtk_b200_fastq_source* dev_out) {
+    const bool want_heads = min_len != nullptr;
     if (!m || !chunks || !segs || !n_reads || !consumed || n_sources == 0 || n_sources > FQTK_B200_MAX_SEGMENTS || n_segs == 0 ||
         n_segs > FQTK_B200_MAX_SEGMENTS)
         return fail(FQTK_B200_ERR_ARG, "need 1..8 sources and 1..8 segments");
@@ -1574,8 +1583,8 @@ int fqtk_b200_matcher_assign_fastq_chunks(fqtk_b200_matcher* m, const fqtk_b200_
         t[s].stream = st;
         CU(fq::temp_alloc(reinterpret_cast<void**>(&t[s].tile_counts), (size_t)tiles * 4 + 4, st));
         CU(fq::temp_alloc(reinterpret_cast<void**>(&t[s].prefix), ((size_t)tiles + 1) * 8, st));
-        CU(fq::temp_alloc(reinterpret_cast<void**>(&t[s].err), 24, st));
-        CU(cudaMemsetAsync(t[s].err, 0xFF, 24, st));
+        CU(fq::temp_alloc(reinterpret_cast<void**>(&t[s].err), 40, st));  // scan | (unused) | min length | vet: few, long
+        CU(cudaMemsetAsync(t[s].err, 0xFF, 40, st));
         CU(cudaMemcpyAsync(m->d_fq[3 * s], chunks[s].data, chunks[s].bytes, cudaMemcpyHostToDevice, st));
         CU(fq::launch_nl_count(static_cast<const uint8_t*>(m->d_fq[3 * s]), chunks[s].bytes, t[s].tile_counts, t[s].prefix, st));
         CU(cudaMemcpyAsync(&total_nl[s], t[s].prefix + tiles, 8, cudaMemcpyDeviceToHost, st));
@@ -1584,7 +1593,7 @@ int fqtk_b200_matcher_assign_fastq_chunks(fqtk_b200_matcher* m, const fqtk_b200_
     uint64_t n = max_reads;
     for (uint32_t s = 0; s < n_sources; s++) n = std::min<uint64_t>(n, total_nl[s] / 4);  // the inputs advance in lock step
     if (n == 0) return FQTK_B200_OK;
-    if (!results) return fail(FQTK_B200_ERR_ARG, "NULL results");
+    if (!results && !want_heads) return fail(FQTK_B200_ERR_ARG, "NULL results");
     // record tables, then the reference's per-read rules, all on the device
     unsigned long long last_nl[FQTK_B200_MAX_SEGMENTS] = {}, err_scan[FQTK_B200_MAX_SEGMENTS] = {}, err_vet[2] = {};
     fq::OffsetSource os{};
@@ -1594,9 +1603,18 @@ int fqtk_b200_matcher_assign_fastq_chunks(fqtk_b200_matcher* m, const fqtk_b200_
         if ((rc = ensure(3 * s + 2, n * 4)) != FQTK_B200_OK) return rc;
         CU(fq::temp_alloc(reinterpret_cast<void**>(&t[s].nl), (size_t)n * 4 * 8, st));
         const uint8_t* d_chunk = static_cast<const uint8_t*>(m->d_fq[3 * s]);
-        CU(fq::launch_fq_records(d_chunk, chunks[s].bytes, t[s].prefix, n * 4, t[s].nl, n, nullptr,
+        if (want_heads && n * 8 > m->fq_head_cap[s]) {
+            if (m->d_fq_head[s]) cudaFree(m->d_fq_head[s]);
+            m->d_fq_head[s] = nullptr;
+            m->fq_head_cap[s] = 0;
+            CU(cudaMalloc(&m->d_fq_head[s], n * 8 + 64));
+            m->fq_head_cap[s] = n * 8;
+        }
+        CU(fq::launch_fq_records(d_chunk, chunks[s].bytes, t[s].prefix, n * 4, t[s].nl, n,
+                                 want_heads ? static_cast<unsigned long long*>(m->d_fq_head[s]) : nullptr,
                                  static_cast<unsigned long long*>(m->d_fq[3 * s + 1]), static_cast<uint32_t*>(m->d_fq[3 * s + 2]),
                                  t[s].err, m->geo, st));
+        if (want_heads) CU(fq::launch_min_len(static_cast<const uint32_t*>(m->d_fq[3 * s + 2]), n, min_len[s], t[s].err + 2, m->geo, st));
         CU(cudaMemcpyAsync(&err_scan[s], t[s].err, 8, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(&last_nl[s], t[s].nl + (n * 4 - 1), 8, cudaMemcpyDeviceToHost, st));
         dev[s].chunk = d_chunk;
@@ -1612,13 +1630,36 @@ int fqtk_b200_matcher_assign_fastq_chunks(fqtk_b200_matcher* m, const fqtk_b200_
         os.offset[k] = segs[k].offset;
         os.length[k] = segs[k].length;
     }
-    CU(fq::launch_fq_vet(os, n, m->L, (uint32_t)m->max_mm + m->max_ns, t[0].err + 1, m->geo, st));
-    CU(cudaMemcpyAsync(err_vet, t[0].err + 1, 16, cudaMemcpyDeviceToHost, st));
+    CU(fq::launch_fq_vet(os, n, m->L, (uint32_t)m->max_mm + m->max_ns, t[0].err + 3, m->geo, st));
+    CU(cudaMemcpyAsync(err_vet, t[0].err + 3, 16, cudaMemcpyDeviceToHost, st));
+    unsigned long long err_min[FQTK_B200_MAX_SEGMENTS];
+    for (uint32_t s = 0; s < n_sources; s++) {
+        err_min[s] = ~0ull;
+        if (want_heads) CU(cudaMemcpyAsync(&err_min[s], t[s].err + 2, 8, cudaMemcpyDeviceToHost, st));
+    }
     CU(cudaStreamSynchronize(st));
     for (uint32_t s = 0; s < n_sources; s++)
         if (err_scan[s] != ~0ull)
             return fail(FQTK_B200_ERR_ARG, "FASTQ record " + std::to_string(err_scan[s] >> 2) + " of input " + std::to_string(s) + ": " +
                                                SCAN_ERR[err_scan[s] & 3u]);
+    if (want_heads) {  // ReadSetIterator::next: "Read {name} had too few bases to demux {len} vs. {min} needed in read structure."
+        unsigned long long first = ~0ull;
+        for (uint32_t s = 0; s < n_sources; s++) first = std::min(first, err_min[s]);
+        if (first != ~0ull && first <= std::min(err_vet[0], err_vet[1])) {
+            for (uint32_t s = 0; s < n_sources; s++) {
+                uint32_t len = 0;
+                CU(cudaMemcpy(&len, static_cast<const uint32_t*>(m->d_fq[3 * s + 2]) + first, 4, cudaMemcpyDeviceToHost));
+                if (len >= min_len[s]) continue;
+                unsigned long long h0 = 0, s0 = 0;
+                CU(cudaMemcpy(&h0, static_cast<const unsigned long long*>(m->d_fq_head[0]) + first, 8, cudaMemcpyDeviceToHost));
+                CU(cudaMemcpy(&s0, static_cast<const unsigned long long*>(m->d_fq[1]) + first, 8, cudaMemcpyDeviceToHost));
+                std::string name(reinterpret_cast<const char*>(chunks[0].data + h0 + 1), (size_t)(s0 - h0 - 2));
+                if (!name.empty() && name.back() == '\r') name.pop_back();
+                return fail(FQTK_B200_ERR_ARG, "Read " + name + " had too few bases to demux " + std::to_string(len) + " vs. " +
+                                                   std::to_string(min_len[s]) + " needed in read structure.");
+            }
+        }
+    }
     if (err_vet[0] != ~0ull || err_vet[1] != ~0ull) {
         // the first offending read, as the reference's read-by-read loop would meet it: its table rows come back and the
         // message is built from the host's own chunk bytes
@@ -1658,10 +1699,115 @@ int fqtk_b200_matcher_assign_fastq_chunks(fqtk_b200_matcher* m, const fqtk_b200_
     if (rc != FQTK_B200_OK) return rc;
     rc = fqtk_b200_matcher_assign_fastq_device(m, dev, n_sources, segs, n_segs, n, m->d_out[0], st);
     if (rc != FQTK_B200_OK) return rc;
-    CU(cudaMemcpyAsync(results, m->d_out[0], n * 4, cudaMemcpyDeviceToHost, st));
+    if (results) CU(cudaMemcpyAsync(results, m->d_out[0], n * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     *n_reads = n;
     for (uint32_t s = 0; s < n_sources; s++) consumed[s] = last_nl[s] + 1;
+    if (dev_out)
+        for (uint32_t s = 0; s < n_sources; s++) dev_out[s] = dev[s];
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_matcher_assign_fastq_chunks(fqtk_b200_matcher* m, const fqtk_b200_fastq_chunk* chunks, uint32_t n_sources,
+                                          const fqtk_b200_fastq_segment* segs, uint32_t n_segs, uint64_t max_reads,
+                                          uint32_t* results, uint64_t* n_reads, uint64_t* consumed) {
+    if (n_reads) *n_reads = 0;
+    if (!results && max_reads) {
+        // (a NULL result buffer is only legal when nothing can come back)
+        bool any = false;
+        for (uint32_t s = 0; chunks && s < n_sources; s++) any = any || chunks[s].bytes;
+        if (any) return fail(FQTK_B200_ERR_ARG, "NULL results");
+    }
+    return ingest_chunks_impl(m, chunks, n_sources, segs, n_segs, max_reads, results, n_reads, consumed, nullptr, nullptr);
+}
+
+// ---- one call per batch: FASTQ chunks in, per-sample BGZF members out -------------------------------------------------
+int fqtk_b200_demux_chunks(fqtk_b200_matcher* m, fqtk_b200_bgzf* z, const fqtk_b200_fastq_chunk* chunks, uint32_t n_sources,
+                           const fqtk_b200_read_segment* segments, uint32_t n_segments, const char* output_kinds, int level,
+                           uint64_t max_reads, uint8_t* out, uint64_t out_capacity, uint64_t* out_offsets, uint32_t* n_streams_out,
+                           uint64_t* batch_counts, uint64_t* n_reads, uint64_t* consumed) {
+    if (!m || !z || !chunks || !segments || !output_kinds || !out_offsets || !n_streams_out || !n_reads || !consumed)
+        return fail(FQTK_B200_ERR_ARG, "NULL argument");
+    if (n_segments == 0 || n_segments > 32) return fail(FQTK_B200_ERR_ARG, "need 1..32 segments");
+    *n_reads = 0;
+    // the B segments for the matcher, the minimum read length of every input (demux.rs:298: fixed lengths, + 1 for a `+`)
+    fqtk_b200_fastq_segment bsegs[FQTK_B200_MAX_SEGMENTS];
+    uint32_t nb = 0, min_len[FQTK_B200_MAX_SEGMENTS] = {};
+    for (uint32_t k = 0; k < n_segments; k++) {
+        if (segments[k].source >= n_sources || segments[k].source >= FQTK_B200_MAX_SEGMENTS)
+            return fail(FQTK_B200_ERR_ARG, "segment names a source that was not given");
+        min_len[segments[k].source] = std::max(min_len[segments[k].source],
+                                               segments[k].offset + (segments[k].length == FQTK_B200_SEGMENT_REST ? 1u : segments[k].length));
+        if (segments[k].kind == 'B') {
+            if (nb == FQTK_B200_MAX_SEGMENTS) return fail(FQTK_B200_ERR_UNSUPPORTED, "more than 8 sample-barcode segments");
+            bsegs[nb++] = fqtk_b200_fastq_segment{segments[k].source, segments[k].offset, segments[k].length};
+        }
+    }
+    if (nb == 0) return fail(FQTK_B200_ERR_ARG, "the read structures hold no sample-barcode segment");
+    uint32_t ns = 0;
+    int rc = fqtk_b200_emit_streams(segments, n_segments, output_kinds, &ns, nullptr, nullptr);
+    if (rc != FQTK_B200_OK) return rc;
+    *n_streams_out = ns;
+    const uint32_t B = m->S + 1u, n_seg = ns * B;
+    for (uint32_t k = 0; k <= n_seg; k++) out_offsets[k] = 0;
+    if (batch_counts)
+        for (uint32_t b = 0; b < B; b++) batch_counts[b] = 0;
+    fqtk_b200_fastq_source dev[FQTK_B200_MAX_SEGMENTS];
+    uint64_t n = 0;
+    rc = ingest_chunks_impl(m, chunks, n_sources, bsegs, nb, max_reads, nullptr, &n, consumed, min_len, dev);
+    if (rc != FQTK_B200_OK || n == 0) return rc;
+    CU(cudaSetDevice(m->device));
+    cudaStream_t st = m->streams[0];
+    // route
+    fq::TempBuf d_order, d_off, d_text, d_out;
+    CU(d_order.alloc((size_t)n * 4, st));
+    CU(d_off.alloc(((size_t)B + 1) * 8, st));
+    rc = fqtk_b200_matcher_route_device(m, m->d_out[0], n, d_order.as<uint32_t>(), d_off.as<uint64_t>(), st);
+    if (rc != FQTK_B200_OK) return rc;
+    if (batch_counts) {
+        std::vector<uint64_t> off(B + 1);
+        CU(cudaMemcpyAsync(off.data(), d_off.p, ((size_t)B + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (uint32_t b = 0; b < B; b++) batch_counts[b] = off[b + 1] - off[b];
+    }
+    if (ns == 0) {
+        *n_reads = n;
+        return FQTK_B200_OK;
+    }
+    // records
+    fqtk_b200_emit_source esrc[FQTK_B200_MAX_SEGMENTS];
+    uint64_t in_bytes = 0, bc_bytes = 16;
+    for (uint32_t s = 0; s < n_sources; s++) {
+        esrc[s] = fqtk_b200_emit_source{dev[s].chunk, dev[s].chunk_bytes, static_cast<const uint64_t*>(m->d_fq_head[s]), dev[s].seq_offsets,
+                                        dev[s].seq_lengths};
+        in_bytes += consumed[s];
+    }
+    for (uint32_t k = 0; k < n_segments; k++)
+        if ((segments[k].kind == 'B' || segments[k].kind == 'M') && segments[k].length != FQTK_B200_SEGMENT_REST) bc_bytes += segments[k].length + 1;
+    // every stream repeats the header (+ read number, UMIs, barcodes) and holds at most the bases + qualities of one input
+    const uint64_t text_cap = (uint64_t)ns * (in_bytes + n * (bc_bytes + 16)) + 64;
+    CU(d_text.alloc(text_cap, st));
+    std::vector<uint64_t> file_off((size_t)ns * (B + 1));
+    uint64_t text_bytes = 0;
+    rc = fqtk_b200_demux_emit_device(m->device, esrc, n_sources, segments, n_segments, output_kinds, d_order.as<uint32_t>(),
+                                     d_off.as<uint64_t>(), B, n, d_text.as<uint8_t>(), text_cap, file_off.data(), &text_bytes, st);
+    if (rc != FQTK_B200_OK) return rc;
+    // every (stream, sample) run -> its own BGZF members
+    std::vector<uint64_t> seg_off(n_seg + 1);
+    for (uint32_t t = 0; t < ns; t++)
+        for (uint32_t b = 0; b < B; b++) seg_off[(size_t)t * B + b] = file_off[(size_t)t * (B + 1) + b];
+    seg_off[n_seg] = text_bytes;
+    const uint64_t comp_cap = fqtk_b200_bgzf_bound(text_bytes) + 31ull * n_seg;
+    CU(d_out.alloc(comp_cap, st));
+    rc = fqtk_b200_bgzf_compress_segments_device(z, d_text.as<uint8_t>(), seg_off.data(), n_seg, level, d_out.as<uint8_t>(), comp_cap,
+                                                 out_offsets, st);
+    if (rc != FQTK_B200_OK) return rc;
+    if (out_offsets[n_seg] > out_capacity)
+        return fail(FQTK_B200_ERR_ARG, "output buffer too small: " + std::to_string(out_offsets[n_seg]) + " bytes needed");
+    if (!out && out_offsets[n_seg]) return fail(FQTK_B200_ERR_ARG, "NULL output buffer");
+    CU(cudaMemcpyAsync(out, d_out.p, out_offsets[n_seg], cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_reads = n;
     return FQTK_B200_OK;
 }
 

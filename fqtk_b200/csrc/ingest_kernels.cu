@@ -181,6 +181,13 @@ __global__ void __launch_bounds__(256) k_fq_vet(const OffsetSource os, uint64_t 
     }
 }
 
+// first read whose sequence line is shorter than its read structure needs (ReadSetIterator::next, demux.rs:298-315)
+__global__ void __launch_bounds__(256) k_fq_min_len(const uint32_t* __restrict__ seq_lengths, uint64_t n, uint32_t min_len,
+                                                    unsigned long long* __restrict__ err) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        if (seq_lengths[i] < min_len) atomicMin(err, (unsigned long long)i);
+}
+
 // ---- launchers -------------------------------------------------------------------------------------------------------
 uint32_t fastq_scan_tiles(uint64_t bytes) { return (uint32_t)((bytes + NL_TILE - 1) / NL_TILE); }
 
@@ -220,6 +227,15 @@ cudaError_t launch_fq_vet(const OffsetSource& os, uint64_t n, uint32_t L, uint32
     if (!n) return cudaSuccess;
     const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 255) / 256, (uint64_t)g.sm_count * 16);
     k_fq_vet<<<grid, 256, 0, stream>>>(os, n, L, max_nocalls, d_err2);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_min_len(const uint32_t* d_seq_lengths, uint64_t n, uint32_t min_len, unsigned long long* d_err,
+                           const LaunchGeometry& g, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 255) / 256, (uint64_t)g.sm_count * 16);
+    k_fq_min_len<<<grid, 256, 0, stream>>>(d_seq_lengths, n, min_len, d_err);
     count_launch();
     return cudaGetLastError();
 }

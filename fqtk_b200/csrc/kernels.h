@@ -190,6 +190,8 @@ cudaError_t launch_fq_records(const uint8_t* d_chunk, uint64_t bytes, const unsi
                               unsigned long long* d_nl, uint64_t n_records, unsigned long long* d_head_offsets,
                               unsigned long long* d_seq_offsets, uint32_t* d_seq_lengths, unsigned long long* d_err,
                               const LaunchGeometry& g, cudaStream_t stream);
+cudaError_t launch_min_len(const uint32_t* d_seq_lengths, uint64_t n, uint32_t min_len, unsigned long long* d_err,
+                           const LaunchGeometry& g, cudaStream_t stream);
 cudaError_t launch_fq_vet(const OffsetSource& os, uint64_t n, uint32_t L, uint32_t max_nocalls, unsigned long long* d_err2,
                           const LaunchGeometry& g, cudaStream_t stream);
 cudaError_t launch_fix_lengths(uint32_t* d_results, const uint32_t* d_lengths, uint64_t n, uint32_t L, uint32_t S,

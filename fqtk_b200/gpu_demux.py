@@ -183,3 +183,56 @@ def demux_fastq_batch_gpu(matcher, compressor, sample_ids: Sequence[str], barcod
     res.counts = np.diff(off).astype(np.uint64)
     res.metrics = demux_metrics(list(sample_ids), list(barcodes), [int(c) for c in res.counts], unmatched_prefix)
     return res
+
+
+def demux_chunks(matcher, compressor, sample_ids: Sequence[str], barcodes: Sequence[str], read_structures: Sequence[str],
+                 fastq_texts: Sequence, output_types: Sequence[str] = ("T",), unmatched_prefix: str = "unmatched",
+                 level: int = 5, eof: bool = True, max_reads: int | None = None):
+    """The same batch through ONE C-ABI call (fqtk_b200_demux_chunks): chunks in host memory in, per-file BGZF bytes out.
+    Returns (GpuDemuxResult, bytes consumed per input).  Reads that are too short for their read structure fail the call
+    with the reference's text (there is no skip option in this form)."""
+    lib = _lib.lib()
+    structures = [parse_read_structure(s) for s in read_structures]
+    if len(structures) != len(fastq_texts):
+        raise ValueError("The same number of read structures should be given as FASTQs")
+    arrs = [np.frombuffer(t, dtype=np.uint8) if not isinstance(t, np.ndarray) else t for t in fastq_texts]
+    S = len(sample_ids)
+    segs_all = read_segments(structures)
+    rsegs = (_lib.ReadSegment * len(segs_all))(*[_lib.ReadSegment(s, ord(kind), off, ln) for s, kind, off, ln in segs_all])
+    kinds = "".join(t.upper() for t in output_types).encode()
+    ns = C.c_uint32()
+    skinds = C.create_string_buffer(16)
+    snums = (C.c_uint32 * 16)()
+    _lib.check(lib.fqtk_b200_emit_streams(rsegs, len(segs_all), kinds, C.byref(ns), skinds, snums))
+    n_streams = int(ns.value)
+    chunks = (_lib.FastqChunk * len(arrs))(*[_lib.FastqChunk(a.ctypes.data if a.size else None, a.size) for a in arrs])
+    in_bytes = sum(int(a.size) for a in arrs)
+    cap = compressor.bound(max(n_streams, 1) * (in_bytes * 2 + 64)) + 31 * max(n_streams, 1) * (S + 1)
+    out = _pinned_out(cap)
+    n_seg = n_streams * (S + 1)
+    out_off = (C.c_uint64 * (n_seg + 1))()
+    counts = (C.c_uint64 * (S + 1))()
+    n_reads = C.c_uint64()
+    consumed = (C.c_uint64 * len(arrs))()
+    cap_reads = (1 << 32) - 1 if max_reads is None else int(max_reads)
+    rc = lib.fqtk_b200_demux_chunks(matcher._h, compressor._h, chunks, len(arrs), rsegs, len(segs_all), kinds, level, cap_reads,
+                                    out.ctypes.data, out.size, out_off, C.byref(ns), counts, C.byref(n_reads), consumed)
+    if rc != _lib.OK:
+        msg = _lib.last_error()
+        if "had too few bases to demux" in msg:
+            raise TooFewBases(msg)
+        from .barcode_matching import _raise
+
+        _raise(rc, getattr(matcher, "_sample0_id", None))
+    res = GpuDemuxResult()
+    for t in range(n_streams):
+        code = FILE_TYPE_CODE[skinds.raw[t:t + 1].decode()]
+        for b in range(S + 1):
+            k = t * (S + 1) + b
+            if out_off[k + 1] == out_off[k]:
+                continue
+            prefix = sample_ids[b] if b < S else unmatched_prefix
+            res.files[f"{prefix}.{code}{int(snums[t])}.fq.gz"] = out[int(out_off[k]):int(out_off[k + 1])].tobytes() + (BGZF_EOF if eof else b"")
+    res.counts = np.array(list(counts), dtype=np.uint64)
+    res.metrics = demux_metrics(list(sample_ids), list(barcodes), [int(c) for c in res.counts], unmatched_prefix)
+    return res, [int(c) for c in consumed]

@@ -386,6 +386,20 @@ FQTK_B200_API int fqtk_b200_demux_emit_device(int device, const fqtk_b200_emit_s
                                               uint32_t n_buckets, uint64_t n_reads, uint8_t* d_text, uint64_t text_capacity,
                                               uint64_t* file_offsets, uint64_t* text_bytes, void* stream);
 
+/* ---- one call per batch: FASTQ chunks in, per-sample BGZF members out ----
+ * The reference's main loop body (demux.rs:945-977) for a batch, entirely on the device: chunks of the inputs (HOST memory,
+ * lock step) -> records found and vetted (too few bases for the read structure: the reference's error text, demux.rs:309-315)
+ * -> B segments matched -> routed -> every selected output segment written with its rewritten header -> every (stream,
+ * sample) run deflated into its own BGZF members -> `out` (HOST).  Run k = stream t * (S + 1) + bucket b (bucket S =
+ * unmatched) occupies out[out_offsets[k], out_offsets[k+1]): append it to that file (and the 28-byte EOF member at close).
+ * batch_counts (S + 1, may be NULL) = this batch's templates per bucket; the matcher's own counters accumulate as usual.
+ * *n_reads / consumed[s] as in fqtk_b200_matcher_assign_fastq_chunks.  Streams: fqtk_b200_emit_streams. */
+FQTK_B200_API int fqtk_b200_demux_chunks(fqtk_b200_matcher* m, fqtk_b200_bgzf* z, const fqtk_b200_fastq_chunk* chunks,
+                                         uint32_t n_sources, const fqtk_b200_read_segment* segments, uint32_t n_segments,
+                                         const char* output_kinds, int level, uint64_t max_reads, uint8_t* out,
+                                         uint64_t out_capacity, uint64_t* out_offsets, uint32_t* n_streams,
+                                         uint64_t* batch_counts, uint64_t* n_reads, uint64_t* consumed);
+
 /* ---- deterministic synthetic workload; counter-based, identical on host and device ----
  * Panel: S barcodes of length L over ACGT with pairwise Hamming distance >= min_distance (greedy, rejection);
  * `n_degenerate` positions per barcode are then rewritten to IUPAC degenerate codes (cfg 5).

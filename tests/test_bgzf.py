@@ -245,7 +245,7 @@ def test_gpu_whole_data_path_equals_the_host_formatted_pipeline():
     from fqtk_b200.bgzf import BgzfCompressor
     from fqtk_b200.demux import TooFewBases, fastq_text as records_text
     from fqtk_b200.fastq import demux_fastq_batch
-    from fqtk_b200.gpu_demux import demux_fastq_batch_gpu
+    from fqtk_b200.gpu_demux import demux_chunks, demux_fastq_batch_gpu
 
     def check(m, z, ids, bcs, structures, texts, types, **kw):
         want = demux_fastq_batch(m, ids, bcs, structures, texts, types, **kw)
@@ -258,6 +258,11 @@ def test_gpu_whole_data_path_equals_the_host_formatted_pipeline():
             assert sizes[-1] == 0 and all(x == 65280 for x in sizes[:-2])
         assert np.array_equal(got.counts, want.counts) and got.skipped == want.skipped
         assert [(x.sample_id, x.templates) for x in got.metrics] == [(x.sample_id, x.templates) for x in want.metrics]
+        if not kw.get("skip_too_few_bases"):  # the one-call C form (fqtk_b200_demux_chunks) must leave the very same files
+            m.reset_counts()
+            one, used = demux_chunks(m, z, ids, bcs, structures, texts, types)
+            assert used == [len(t) for t in texts]
+            assert one.files == got.files and np.array_equal(one.counts, want.counts)
         return got
 
     kats = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
@@ -303,9 +308,26 @@ def test_gpu_whole_data_path_equals_the_host_formatted_pipeline():
             with pytest.raises(TooFewBases) as e2:
                 demux_fastq_batch(m, ids, bcs, ["6M+T", "+T", "8B", "+B"], texts, ["T"])
             assert str(e1.value) == str(e2.value)
+            with pytest.raises(TooFewBases) as e3:
+                demux_chunks(m, z, ids, bcs, ["6M+T", "+T", "8B", "+B"], texts, ["T"])
+            assert str(e3.value).endswith(str(e2.value))
             m.reset_counts()
             got = check(m, z, ids, bcs, ["6M+T", "+T", "8B", "+B"], texts, ["T"], skip_too_few_bases=True)
             assert got.skipped == 1
+            # chunks that end in the middle of a record: the complete read sets are written, the rest is carried over
+            good = [b"".join(x) for x in (r1, r2, i1, i2)]
+            cut = [good[0][: len(good[0]) // 2], good[1][: len(good[1]) // 2 + 777], good[2][: len(good[2]) // 3], good[3]]
+            m.reset_counts()
+            part, used = demux_chunks(m, z, ids, bcs, ["6M+T", "+T", "8B", "+B"], cut, ["T"])
+            k = int(part.counts.sum())
+            assert 0 < k < n and used == [sum(len(x) for x in col[:k]) for col in (r1, r2, i1, i2)]
+            m.reset_counts()
+            rest, used2 = demux_chunks(m, z, ids, bcs, ["6M+T", "+T", "8B", "+B"], [g[u:] for g, u in zip(good, used)], ["T"])
+            assert int(rest.counts.sum()) == n - k
+            whole = demux_fastq_batch(m, ids, bcs, ["6M+T", "+T", "8B", "+B"], good, ["T"])
+            for name, recs in whole.files.items():  # a file = the members of its batches, in order, then the EOF block
+                image = part.files.get(name, ob.BGZF_EOF)[:-28] + rest.files.get(name, ob.BGZF_EOF)
+                assert ob.parse(image)[0] == records_text(recs), name
 
 
 @pytest.mark.gpu
