@@ -724,6 +724,17 @@ def measure_gpu_demux(ctx, args):
             res = demux_fastq_batch_gpu(m, z, ids, bcs, ["+T", "+T", "8B", "8B"], texts, ["T"], device=ctx.local)
             m.reset_counts()
         sec = (time.perf_counter() - t0) / reps
+        # the same batch through the one-call C form (no Python between the device steps)
+        from fqtk_b200.gpu_demux import demux_chunks
+        one, used = demux_chunks(m, z, ids, bcs, ["+T", "+T", "8B", "8B"], texts, ["T"])
+        m.reset_counts()
+        assert one.files == res.files and used == [int(t.size) for t in texts]
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            (buf, offs, cnts), used = demux_chunks(m, z, ids, bcs, ["+T", "+T", "8B", "8B"], texts, ["T"], raw=True)
+            m.reset_counts()
+        sec_one = (time.perf_counter() - t0) / reps
+        assert int(cnts.sum()) == n and int(offs[-1]) == sum(len(v) - 28 for v in one.files.values())
     del texts
     for q in pinned:
         _lib.lib().fqtk_b200_host_free(q)
@@ -735,7 +746,11 @@ def measure_gpu_demux(ctx, args):
                     "headers, BGZF level 5 per sample (385 x 2 files) -> compressed images on the host; one call of "
                     "fqtk_b200.gpu_demux.demux_fastq_batch_gpu, wall clock, copies inside",
             "reads": n, "input_bytes": in_bytes, "text_bytes": res.text_bytes, "output_bytes": out_bytes, "files": len(res.files),
-            "ms": round(sec * 1e3, 2), "mreads_per_s": round(n / sec / 1e6, 2), "gb_per_s_in": round(in_bytes / sec / 1e9, 2)}
+            "ms": round(sec * 1e3, 2), "mreads_per_s": round(n / sec / 1e6, 2), "gb_per_s_in": round(in_bytes / sec / 1e9, 2),
+            "one_call": {"api": "fqtk_b200_demux_chunks (the same batch, one C-ABI call: compressed members of all 770 runs in one pinned "
+                                "buffer + their offsets; no per-file byte strings are built)",
+                         "ms": round(sec_one * 1e3, 2), "mreads_per_s": round(n / sec_one / 1e6, 2),
+                         "gb_per_s_in": round(in_bytes / sec_one / 1e9, 2)}}
 
 
 def measure_fastq(ctx, args, cfg, panel, matcher):

@@ -8,6 +8,7 @@
 //   * demux.rs:968-975           -> counts[S+1]
 // No CPU matching path exists here: distances, decisions and the memo-table contents all come from the kernels.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1752,10 +1753,20 @@ int fqtk_b200_demux_chunks(fqtk_b200_matcher* m, fqtk_b200_bgzf* z, const fqtk_b
     for (uint32_t k = 0; k <= n_seg; k++) out_offsets[k] = 0;
     if (batch_counts)
         for (uint32_t b = 0; b < B; b++) batch_counts[b] = 0;
+    const bool trace = getenv("FQTK_B200_TRACE") != nullptr;  // stage times on stderr (each stage ends in a synchronisation)
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t_prev = now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        const auto t = now();
+        std::fprintf(stderr, "[fqtk_b200] demux_chunks %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+        t_prev = t;
+    };
     fqtk_b200_fastq_source dev[FQTK_B200_MAX_SEGMENTS];
     uint64_t n = 0;
     rc = ingest_chunks_impl(m, chunks, n_sources, bsegs, nb, max_reads, nullptr, &n, consumed, min_len, dev);
     if (rc != FQTK_B200_OK || n == 0) return rc;
+    lap("H2D + scan + vet + match");
     CU(cudaSetDevice(m->device));
     cudaStream_t st = m->streams[0];
     // route
@@ -1770,6 +1781,8 @@ int fqtk_b200_demux_chunks(fqtk_b200_matcher* m, fqtk_b200_bgzf* z, const fqtk_b
         CU(cudaStreamSynchronize(st));
         for (uint32_t b = 0; b < B; b++) batch_counts[b] = off[b + 1] - off[b];
     }
+    if (trace) CU(cudaStreamSynchronize(st));
+    lap("route");
     if (ns == 0) {
         *n_reads = n;
         return FQTK_B200_OK;
@@ -1792,6 +1805,7 @@ int fqtk_b200_demux_chunks(fqtk_b200_matcher* m, fqtk_b200_bgzf* z, const fqtk_b
     rc = fqtk_b200_demux_emit_device(m->device, esrc, n_sources, segments, n_segments, output_kinds, d_order.as<uint32_t>(),
                                      d_off.as<uint64_t>(), B, n, d_text.as<uint8_t>(), text_cap, file_off.data(), &text_bytes, st);
     if (rc != FQTK_B200_OK) return rc;
+    lap("records");
     // every (stream, sample) run -> its own BGZF members
     std::vector<uint64_t> seg_off(n_seg + 1);
     for (uint32_t t = 0; t < ns; t++)
@@ -1802,11 +1816,13 @@ int fqtk_b200_demux_chunks(fqtk_b200_matcher* m, fqtk_b200_bgzf* z, const fqtk_b
     rc = fqtk_b200_bgzf_compress_segments_device(z, d_text.as<uint8_t>(), seg_off.data(), n_seg, level, d_out.as<uint8_t>(), comp_cap,
                                                  out_offsets, st);
     if (rc != FQTK_B200_OK) return rc;
+    lap("BGZF");
     if (out_offsets[n_seg] > out_capacity)
         return fail(FQTK_B200_ERR_ARG, "output buffer too small: " + std::to_string(out_offsets[n_seg]) + " bytes needed");
     if (!out && out_offsets[n_seg]) return fail(FQTK_B200_ERR_ARG, "NULL output buffer");
     CU(cudaMemcpyAsync(out, d_out.p, out_offsets[n_seg], cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    lap("D2H");
     *n_reads = n;
     return FQTK_B200_OK;
 }

@@ -187,10 +187,10 @@ def demux_fastq_batch_gpu(matcher, compressor, sample_ids: Sequence[str], barcod
 
 def demux_chunks(matcher, compressor, sample_ids: Sequence[str], barcodes: Sequence[str], read_structures: Sequence[str],
                  fastq_texts: Sequence, output_types: Sequence[str] = ("T",), unmatched_prefix: str = "unmatched",
-                 level: int = 5, eof: bool = True, max_reads: int | None = None):
+                 level: int = 5, eof: bool = True, max_reads: int | None = None, raw: bool = False):
     """The same batch through ONE C-ABI call (fqtk_b200_demux_chunks): chunks in host memory in, per-file BGZF bytes out.
     Returns (GpuDemuxResult, bytes consumed per input).  Reads that are too short for their read structure fail the call
-    with the reference's text (there is no skip option in this form)."""
+    with the reference's text (there is no skip option in this form).  raw=True skips the per-file byte strings."""
     lib = _lib.lib()
     structures = [parse_read_structure(s) for s in read_structures]
     if len(structures) != len(fastq_texts):
@@ -224,6 +224,8 @@ def demux_chunks(matcher, compressor, sample_ids: Sequence[str], barcodes: Seque
         from .barcode_matching import _raise
 
         _raise(rc, getattr(matcher, "_sample0_id", None))
+    if raw:  # what the C call returns, untouched: (pinned buffer view, run offsets, counts), consumed
+        return (out, np.array(list(out_off), dtype=np.uint64), np.array(list(counts), dtype=np.uint64)), [int(c) for c in consumed]
     res = GpuDemuxResult()
     for t in range(n_streams):
         code = FILE_TYPE_CODE[skinds.raw[t:t + 1].decode()]
