@@ -68,5 +68,54 @@ int main() {
         return 1;
     }
     std::printf("bgzf writer: %zu bytes -> %zu bytes in %zu members, every member inflates (zlib)\n", text.size(), image.size(), members);
+
+    // ---- the one-call batch form (fqtk_b200_demux_chunks): what the Rust main loop would call once per batch ----
+    {
+        const char* bcs[3] = {"AAAAAAAA", "CCCCCCCC", "GGGGGGGG"};
+        const char* obs[4] = {"AAAAAAAA", "CCCCCCCC", "GGGGGGGG", "TTTTTTTT"};  // the 4th matches nothing
+        std::string panel = std::string(bcs[0]) + bcs[1] + bcs[2];
+        fqtk_b200_matcher* m = nullptr;
+        if (fqtk_b200_matcher_create(reinterpret_cast<const std::uint8_t*>(panel.data()), 3, 8, 1, 2, 1, 0, &m) != FQTK_B200_OK) {
+            std::printf("FAIL: matcher_create: %s\n", fqtk_b200_last_error());
+            return 1;
+        }
+        fqtk_b200_bgzf* z = nullptr;
+        if (fqtk_b200_bgzf_create(0, 0, &z) != FQTK_B200_OK) { std::puts("FAIL: bgzf_create"); return 1; }
+        const int n = 30000;
+        std::string chunk, expect[4];
+        unsigned y = 99;
+        for (int i = 0; i < n; i++) {
+            std::string tmpl;
+            for (int k = 0; k < 40 + i % 7; k++) { y = y * 1664525u + 1013904223u; tmpl += "ACGT"[y >> 30]; }
+            const std::string q(tmpl.size(), 'F');
+            const int b = i % 4;
+            chunk += "@r" + std::to_string(i) + "\n" + obs[b] + tmpl + "\n+\n" + std::string(8, 'I') + q + "\n";
+            expect[b] += "@r" + std::to_string(i) + " 1:N:0:" + obs[b] + "\n" + tmpl + "\n+\n" + q + "\n";
+        }
+        chunk += "@cut_off_record\nACGT";  // an incomplete record at the end of the chunk: carried over, not written
+        const fqtk_b200_fastq_chunk ch{reinterpret_cast<const std::uint8_t*>(chunk.data()), chunk.size()};
+        const fqtk_b200_read_segment segs[2] = {{0, 'B', 0, 8}, {0, 'T', 8, FQTK_B200_SEGMENT_REST}};
+        std::string out(fqtk_b200_bgzf_bound(chunk.size() * 2), '\0');
+        std::uint64_t offs[4 + 1], counts[4], n_reads = 0, consumed = 0;
+        std::uint32_t n_streams = 0;
+        const int rc = fqtk_b200_demux_chunks(m, z, &ch, 1, segs, 2, "T", 5, ~0ull, reinterpret_cast<std::uint8_t*>(&out[0]), out.size(), offs,
+                                              &n_streams, counts, &n_reads, &consumed);
+        if (rc != FQTK_B200_OK) { std::printf("FAIL: demux_chunks: %s\n", fqtk_b200_last_error()); return 1; }
+        if (n_streams != 1 || n_reads != (std::uint64_t)n || consumed != chunk.size() - std::strlen("@cut_off_record\nACGT")) {
+            std::printf("FAIL: %u streams, %llu reads, %llu consumed\n", n_streams, (unsigned long long)n_reads, (unsigned long long)consumed);
+            return 1;
+        }
+        for (int b = 0; b < 4; b++) {
+            std::string got;
+            size_t mem = 0;
+            if (!inflate_members(out.substr(offs[b], offs[b + 1] - offs[b]), got, mem) || got != expect[b] || counts[b] != (std::uint64_t)n / 4) {
+                std::printf("FAIL: run of bucket %d differs\n", b);
+                return 1;
+            }
+        }
+        fqtk_b200_bgzf_destroy(z);
+        fqtk_b200_matcher_destroy(m);
+        std::printf("demux_chunks: %d reads -> 4 runs (3 samples + unmatched), every run inflates to its records\n", n);
+    }
     return 0;
 }

@@ -75,3 +75,4 @@ def test_cpp_bgzf_writer_members_inflate_with_zlib(tmp_path):
     r = subprocess.run([_build_bgzf(tmp_path)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "every member inflates" in r.stdout
+    assert "every run inflates to its records" in r.stdout  # fqtk_b200_demux_chunks, the one-call batch form
