@@ -114,6 +114,11 @@ struct BzPost {                              // what the phases after the parse 
     uint32_t sortA[2][NLIT + 2];             // Huffman scratch (lit/len, dist): frequencies in ascending order -> depths
     uint16_t order[2][NLIT + 2];             //   symbol at every sorted position
     uint8_t rle_sym[NLIT + NDIST + 4], rle_ext[NLIT + NDIST + 4];
+    uint32_t num[3][36];                     // huff_lengths scratch (lit/len, dist, code-length alphabet)
+    uint32_t cnt[3][16];                     // codes per length -> first code per length
+    uint32_t clf[20], clA[20];               // code-length alphabet: frequencies, sorted frequencies -> depths
+    uint16_t clord[20], clc[20];             //   sorted symbols, codes
+    uint8_t cll[20];                         //   lengths
 };
 struct BzShared {
     uint32_t in[(65536 + 64) / 4];           // the block, zero-padded
@@ -150,7 +155,7 @@ __device__ __forceinline__ uint32_t read1(const uint32_t* in, uint32_t pos) {
 // "In-place calculation of minimum-redundancy codes"), then lengths above `limit` are repaired the way miniz does
 // (count per length, fold the over-long ones into `limit`, restore the Kraft sum) and handed out again in sorted order:
 // the most frequent symbol (last sorted position) gets the shortest code.
-__device__ void huff_lengths(uint32_t* A, const uint16_t* order, uint32_t m, uint32_t limit, uint8_t* out_len) {
+__device__ void huff_lengths(uint32_t* A, const uint16_t* order, uint32_t m, uint32_t limit, uint8_t* out_len, uint32_t* num /* 33 words of scratch */) {
     if (m == 2u) {
         out_len[order[0]] = 1;
         out_len[order[1]] = 1;
@@ -171,7 +176,6 @@ __device__ void huff_lengths(uint32_t* A, const uint16_t* order, uint32_t m, uin
         avbl = 2 * used; dpth++; used = 0;
     }
     // A[i] = depth, non-increasing in i.  Length limit.
-    uint32_t num[33];
     for (uint32_t i = 0; i <= 32u; i++) num[i] = 0;
     for (uint32_t i = 0; i < m; i++) num[min(A[i], 32u)]++;
     if (A[0] > limit) {
@@ -190,21 +194,22 @@ __device__ void huff_lengths(uint32_t* A, const uint16_t* order, uint32_t m, uin
         for (uint32_t c = num[l]; c > 0; c--) out_len[order[--j]] = (uint8_t)l;
 }
 
-// `nthreads` threads (t = 0 .. nthreads-1, one warp or fewer): canonical codes (RFC 1951 3.2.2) of symbols [0, n), stored
-// bit-reversed (deflate sends codes MSB first).  The k-th symbol of a length, in symbol order, gets first_code + k.
-__device__ void huff_codes(const uint8_t* len, uint32_t n, uint16_t* code, uint32_t t, uint32_t nthreads) {
-    uint32_t first[16];
-    {
-        uint32_t cnt[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) cnt[i] = 0;
-        for (uint32_t s = 0; s < n; s++) cnt[len[s]]++;  // (every thread counts for itself: n <= 286 byte loads)
-        cnt[0] = 0;
-        uint32_t c = 0;
-        first[0] = 0;
-#pragma unroll
-        for (int b = 1; b < 16; b++) { c = (c + cnt[b - 1]) << 1; first[b] = c; }
+// Canonical codes (RFC 1951 3.2.2), stored bit-reversed (deflate sends codes MSB first), in three small steps around two
+// barriers: every thread counts its symbols' lengths into cnt[16] (shared atomics), one thread turns the counts into the
+// first code of every length, then the k-th symbol of a length, in symbol order, gets first_code + k.
+__device__ __forceinline__ void huff_count(const uint8_t* len, uint32_t n, uint32_t* cnt, uint32_t t, uint32_t nthreads) {
+    for (uint32_t s = t; s < n; s += nthreads)
+        if (len[s]) atomicAdd(&cnt[len[s]], 1u);
+}
+__device__ __forceinline__ void huff_first(uint32_t* cnt /* in: counts, out: first code per length */) {
+    uint32_t c = 0, prev = 0;
+    for (int b = 1; b < 16; b++) {
+        c = (c + prev) << 1;
+        prev = cnt[b];
+        cnt[b] = c;
     }
+}
+__device__ void huff_assign(const uint8_t* len, uint32_t n, const uint32_t* first, uint16_t* code, uint32_t t, uint32_t nthreads) {
     for (uint32_t s = t; s < n; s += nthreads) {
         const uint32_t l = len[s];
         if (!l) { code[s] = 0; continue; }
@@ -406,11 +411,16 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
             rank_sort(S.post.freq, NLIT, S.post.sortA[0], S.post.order[0], &S.used[0]);
             rank_sort(S.post.freq + DOFF, NDIST, S.post.sortA[1], S.post.order[1], &S.used[1]);
             __syncthreads();
-            if (tid == 0) huff_lengths(S.post.sortA[0], S.post.order[0], S.used[0], 15u, S.clen);
-            else if (tid == 32) huff_lengths(S.post.sortA[1], S.post.order[1], S.used[1], 15u, S.clen + DOFF);
+            if (tid == 0) huff_lengths(S.post.sortA[0], S.post.order[0], S.used[0], 15u, S.clen, S.post.num[0]);
+            else if (tid == 32) huff_lengths(S.post.sortA[1], S.post.order[1], S.used[1], 15u, S.clen + DOFF, S.post.num[1]);
+            else if (tid >= 64 && tid < 64 + 48) (&S.post.cnt[0][0])[tid - 64] = 0u;
             __syncthreads();
-            if (w >= 2) huff_codes(S.clen, NLIT, S.code, tid - 64u, BZ_THREADS - 64u);  // (warp 0 goes on to the header)
-            else if (w == 1) huff_codes(S.clen + DOFF, NDIST, S.code + DOFF, lane, 32u);
+            huff_count(S.clen, NLIT, S.post.cnt[0], tid, BZ_THREADS);
+            huff_count(S.clen + DOFF, NDIST, S.post.cnt[1], tid, BZ_THREADS);
+            __syncthreads();
+            if (tid == 32) huff_first(S.post.cnt[0]);
+            else if (tid == 64) huff_first(S.post.cnt[1]);
+            // (thread 0 does not need the codes for the header: it goes straight on; the barrier behind the header orders the rest)
             // ---- 3a: header (one thread): BFINAL = 1, BTYPE = 2, HLIT, HDIST, HCLEN, code-length codes, run-length coded lengths
             if (tid == 0) {
                 uint32_t hlit = NLIT, hdist = NDIST;
@@ -419,7 +429,7 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
                 const uint32_t total = hlit + hdist;
                 auto L = [&](uint32_t i) -> uint32_t { return i < hlit ? S.clen[i] : S.clen[DOFF + i - hlit]; };
                 uint32_t nr = 0, i = 0;
-                uint32_t clf[19];
+                uint32_t* clf = S.post.clf;
                 for (int k = 0; k < 19; k++) clf[k] = 0;
                 while (i < total) {
                     const uint32_t l = L(i);
@@ -442,7 +452,10 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
                 uint32_t nused = 0;
                 for (int k = 0; k < 19; k++) nused += clf[k] != 0u;
                 for (int k = 0; k < 19 && nused < 2u; k++) if (!clf[k]) { clf[k] = 1; nused++; }
-                uint32_t A[19]; uint16_t ord[19]; uint8_t cll[19]; uint16_t clc[19];
+                uint32_t* A = S.post.clA;
+                uint16_t* ord = S.post.clord;
+                uint8_t* cll = S.post.cll;
+                uint16_t* clc = S.post.clc;
                 uint32_t m = 0;
                 for (int k = 0; k < 19; k++) cll[k] = 0;
                 for (int k = 0; k < 19; k++) if (clf[k]) { A[m] = clf[k]; ord[m] = (uint16_t)k; m++; }
@@ -452,9 +465,15 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
                     while (b >= 0 && (A[b] > fa || (A[b] == fa && ord[b] > oa))) { A[b + 1] = A[b]; ord[b + 1] = ord[b]; b--; }
                     A[b + 1] = fa; ord[b + 1] = oa;
                 }
-                huff_lengths(A, ord, m, 7u, cll);
-                huff_codes(cll, 19u, clc, 0u, 1u);
-                const uint8_t perm[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+                huff_lengths(A, ord, m, 7u, cll, S.post.num[2]);
+                {
+                    uint32_t* cc = S.post.cnt[2];
+                    for (int k = 0; k < 16; k++) cc[k] = 0;
+                    for (int k = 0; k < 19; k++) if (cll[k]) cc[cll[k]]++;
+                    huff_first(cc);
+                    huff_assign(cll, 19u, cc, clc, 0u, 1u);
+                }
+                static const uint8_t perm[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
                 uint32_t hclen = 19;
                 while (hclen > 4u && cll[perm[hclen - 1u]] == 0) hclen--;
                 BitWriter bw{S.post.hdr, 0u};
@@ -470,6 +489,9 @@ __global__ void __launch_bounds__(BZ_THREADS, 2)
                 }
                 S.hdr_bits = bw.pos;
             }
+            __syncthreads();
+            huff_assign(S.clen, NLIT, S.post.cnt[0], S.code, tid, BZ_THREADS);
+            if (tid < 32u) huff_assign(S.clen + DOFF, NDIST, S.post.cnt[1], S.code + DOFF, tid, 32u);
             __syncthreads();
             // ---- 3b: bit offsets of the warps' token streams from their own histograms
             {
