@@ -342,45 +342,82 @@ __global__ void __launch_bounds__(BRUTE_THREADS) k_brute(const MatchParams p, co
 // is transposed into groups of 32 barcodes: word (g, i, v) has bit j set iff barcode 32g + j mismatches a read symbol with
 // 4-bit mask v at position i (bitenc.rs:441-452, for ALL 16 masks: IUPAC codes, no-calls and junk bytes in reads are exact
 // by construction).  For one group a thread fetches the 8W words its own symbols select (conflict-free: the lanes of a
-// warp differ only in v, 16 consecutive words), adds them with a carry-save adder tree into vertical counters (bit p of
-// 32 distances at once: ~2 logic ops per position instead of ~8 instructions per barcode), and compares the counters
-// bit-sliced with its running second-best distance; only barcodes that beat it (rare after the first group) are extracted
-// one by one into the running (distance << 16 | index) min / second-min pair — the same keys as k_brute, so ties go to the
-// first index (barcode_matching.rs:132) and the second smallest counts multiplicity (:140).
+// warp differ only in v, 16 consecutive words) and adds them with a carry-save adder tree into vertical counters (bit p of
+// 32 distances at once: ~2 logic ops per position instead of ~8 instructions per barcode).
+// The running minima stay bit-sliced too, and the group loop has no branch: bit j of the planes mn / ls holds the smallest
+// and the second smallest distance seen so far among the barcodes 32g + j of all groups g ("slot" j), gi the group that
+// gave the smallest one.  One group costs a compare-exchange of the counters with mn (the borrow chain of c - mn is one
+// LOP3 per plane, the two selects one each), a min of the loser with ls, and one LOP3 per plane of gi.  Only after the
+// last group are the 32 slots reduced: smallest mn, among equals the smallest group, then the smallest slot — the FIRST
+// index with the best distance (barcode_matching.rs:132: strict <) — and the second smallest of the multiset (:140) is
+// the smallest of every other slot's mn and the winning slot's ls.  (Round 2's first version compared every group with
+// the running second best and extracted the barcodes below it one by one: that branch was taken by some lane of nearly
+// every warp, 48 % of the kernel's instructions at S = 384.)
 // Shared memory holds a chunk of groups; a panel larger than a chunk is walked chunk by chunk for every batch of reads.
 // ------------------------------------------------------------------------------------------------------
-constexpr int SLICED_THREADS = 512;
+// two CTAs per SM: 512 threads x <= 64 registers (W <= 2), 384 threads x <= 85 registers (W = 3, 4: off[] alone is 8W)
+constexpr int sliced_threads(int W) { return W <= 2 ? 512 : 384; }
 constexpr uint32_t SLICED_CHUNK_BYTES = 96u << 10;  // table bytes staged at a time
+#ifndef SLICED_UNROLL
+#define SLICED_UNROLL 4
+#endif
 
 template <int W>
 struct Sliced {
     static constexpr int LP = 8 * W;                         // positions, padded to whole packed words
     static constexpr int NB = SlicedAdder<LP>::PLANES;       // counter planes: distances 0 .. LP
     static constexpr uint32_t GROUP_BYTES = LP * 16 * 4;     // one group of 32 barcodes
+    static_assert((1 << NB) - 1 > LP, "the all-ones distance must be larger than any real one (it stands for 'no barcode')");
+    static_assert(SLICED_CHUNK_BYTES / GROUP_BYTES <= 256, "group index inside a chunk: 8 planes");
 };
 
 // counters of one group for this thread's read: `a` = shared-window address of the group + the read's symbol offsets
 template <int W>
-FQ_D void sliced_counters(const uint32_t (&off)[8 * W], uint32_t group_addr, uint32_t (&c)[Sliced<W>::NB]) {
+FQ_D void sliced_counters(const MatchParams& p, const uint32_t (&off)[8 * W], uint32_t group_addr, uint32_t (&c)[Sliced<W>::NB]) {
     constexpr int LP = Sliced<W>::LP;
     uint32_t x[LP];
 #pragma unroll
-    for (int i = 0; i < LP; i++) x[i] = lds32_ro(group_addr + off[i] + (uint32_t)i * 64u);
+    for (int i = 0; i < LP; i++)  // the add is a multiply-add (fma pipe): the alu pipe is what bounds this kernel
+        x[i] = lds32_ro(off[i] * p.ck_one + group_addr + (uint32_t)i * 64u);
     SlicedAdder<LP>::add(x, c);
 }
 
-// distance of barcode `j` of the group from the vertical counters
+// bit-sliced a < b over 32 slots: the borrow out of a - b, one three-input logic op per plane
 template <int NB>
-FQ_D uint32_t sliced_extract(const uint32_t (&c)[NB], uint32_t j) {
-    uint32_t d = 0;
+FQ_D uint32_t sliced_less(const uint32_t (&a)[NB], const uint32_t (&b)[NB], uint32_t one) {
+    uint32_t br = ~a[0] & b[0];
 #pragma unroll
-    for (int pl = 0; pl < NB; pl++) d |= ((c[pl] >> j) & 1u) << pl;
+    for (int pl = 1; pl < NB; pl++)  // (~a & b) | (~(a ^ b) & br) — spelled as the one LOP3 it is (ptxas splits the C form)
+        asm("lop3.b32 %0, %1, %2, %0, 0x8E;" : "+r"(br) : "r"(a[pl]), "r"(b[pl]));
+    return br * one;  // one = p.ck_one: a multiply on the fma pipe keeps ptxas from folding the last step into each of its
+                      // users (7 alu-pipe LOP3 for the top plane instead of 3)
+}
+
+// smallest value among the slots of `pool` (non-empty): returns it, narrows `pool` to the slots that hold it
+template <int NB>
+FQ_D uint32_t sliced_min(const uint32_t (&v)[NB], uint32_t& pool) {
+    uint32_t d = 0u;
+#pragma unroll
+    for (int pl = NB - 1; pl >= 0; pl--) {
+        const uint32_t t = pool & ~v[pl];
+        d |= t ? 0u : (1u << pl);
+        pool = t ? t : pool;
+    }
     return d;
 }
 
-template <int W, bool ASCII>
-__global__ void __launch_bounds__(SLICED_THREADS) k_brute_sliced(const MatchParams p, const ReadSource src,
-                                                                 uint32_t* __restrict__ results, uint32_t chunk_groups) {
+// Interim state of a read between two chunk launches, kept in its result word: idx | best << 16 | second best << 24
+// (distances <= 32, a multi-chunk panel has more than one barcode).
+FQ_D uint32_t sliced_pack_state(uint32_t k1, uint32_t k2) { return (k1 & 0xFFFFu) | ((k1 >> 16) << 16) | ((k2 >> 16) << 24); }
+
+// One launch = one chunk of the panel (groups [chunk * chunk_groups, ...)) against every read; the chunk is staged once per
+// CTA.  chunk 0 runs the slot form and reduces it; later chunks (panels of thousands of barcodes) only compare each group
+// with the second-best distance T so far — a barcode below it is rare by then (about 64 / (barcodes seen) per group and
+// read) — and extract those; the last chunk decides, writes the result words and counts.
+template <int W, bool ASCII, int GBITS, bool FIRST>  // GBITS: planes of the group index inside chunk 0 (2^GBITS >= its groups);
+__global__ void __launch_bounds__(sliced_threads(W), 2) k_brute_sliced(const MatchParams p, const ReadSource src,
+                                                                 uint32_t* __restrict__ results, uint32_t chunk_groups,
+                                                                 uint32_t chunk) {
     constexpr int LP = Sliced<W>::LP, NB = Sliced<W>::NB;
     constexpr uint32_t GB = Sliced<W>::GROUP_BYTES;
     extern __shared__ uint4 s_dyn[];
@@ -388,106 +425,122 @@ __global__ void __launch_bounds__(SLICED_THREADS) k_brute_sliced(const MatchPara
     uint32_t* s_tab = reinterpret_cast<uint32_t*>(s_dyn);
     uint32_t* s_hist = s_tab + (size_t)chunk_groups * (GB / 4);
     const uint32_t G = (p.S + 31u) / 32u;
-    const uint32_t n_chunks = (G + chunk_groups - 1u) / chunk_groups;
+    const uint32_t g0 = chunk * chunk_groups, ng = min(chunk_groups, G - g0);
+    const bool last = g0 + ng == G;
     if constexpr (ASCII) init_lut(s_lut);
     Counter cnt;
     cnt.init(s_hist, p);
-    auto stage = [&](uint32_t chunk) {  // groups [chunk * chunk_groups, ...) -> shared memory (all threads)
-        const uint32_t g0 = chunk * chunk_groups, ng = min(chunk_groups, G - g0);
+    {
         const uint4* src4 = reinterpret_cast<const uint4*>(p.sliced + (size_t)g0 * (GB / 4));
         uint4* dst4 = reinterpret_cast<uint4*>(s_tab);
         for (uint32_t t = threadIdx.x; t < ng * (GB / 16); t += blockDim.x) dst4[t] = __ldg(src4 + t);
-    };
-    if (n_chunks == 1u) stage(0);
+    }
     __syncthreads();
     const uint32_t a_tab = smem_addr(s_tab);
+    const uint32_t tail_mask = (p.S & 31u) ? ~((1u << (p.S & 31u)) - 1u) : 0u;  // slots of the last group past the panel
     const uint64_t batch = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t n_batches = (src.n + batch - 1) / batch;  // every thread of the CTA runs every batch (barriers inside)
-    for (uint64_t bi = 0; bi < n_batches; bi++) {
-        const uint64_t i = bi * batch + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        const bool live = i < src.n;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < src.n; i += batch) {
         uint32_t w[W];
-#pragma unroll
-        for (int k = 0; k < W; k++) w[k] = 0u;
         bool row_ok = true;
-        if (live) {
-            if constexpr (ASCII)
-                row_ok = load_ascii<W>(src, i, p.L, s_lut, w);
-            else
-                load_packed<W>(src.packed, i, w);
-        }
+        if constexpr (ASCII)
+            row_ok = load_ascii<W>(src, i, p.L, s_lut, w);
+        else
+            load_packed<W>(src.packed, i, w);
         uint32_t off[LP];  // byte offset of the read's symbol inside a position's 16 words
 #pragma unroll
         for (int k = 0; k < LP; k++) {
             const int sh = 4 * (k & 7) - 2;
             off[k] = (sh >= 0 ? (w[k >> 3] >> sh) : (w[k >> 3] << 2)) & 0x3Cu;
         }
-        uint32_t k1 = EMPTY_KEY, k2 = EMPTY_KEY;  // running best / second best (distance << 16 | index)
-        uint32_t thr[NB];                          // bit planes of the threshold T = second-best distance (all ones: none yet)
+        uint32_t k1, k2;  // best / second best as (distance << 16 | index)
+        if constexpr (FIRST) {  // chunk 0
+            // per slot: smallest / second smallest distance so far (all ones = none yet), group of the smallest
+            uint32_t mn[NB], ls[NB], gi[GBITS];
 #pragma unroll
-        for (int pl = 0; pl < NB; pl++) thr[pl] = 0xFFFFFFFFu;
-        bool have2 = false;  // two barcodes seen: T is meaningful
-        for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
-            if (n_chunks > 1u) {
-                __syncthreads();
-                stage(chunk);
-                __syncthreads();
+            for (int pl = 0; pl < NB; pl++) mn[pl] = ls[pl] = 0xFFFFFFFFu;
+#pragma unroll
+            for (int b = 0; b < GBITS; b++) gi[b] = 0u;
+            // SLICED_UNROLL groups per trip: the low planes of the group index are compile-time constants and the masks of
+            // the others are built once per trip (uniform datapath, but they take issue slots)
+            constexpr int UB = SLICED_UNROLL == 4 ? 2 : 1;
+            for (uint32_t gl = 0; gl < ng; gl += (uint32_t)SLICED_UNROLL) {
+                const uint32_t gq = gl >> UB;
+#pragma unroll
+                for (int r = 0; r < SLICED_UNROLL; r++) {
+                    if (gl + (uint32_t)r >= ng) break;  // (warp-uniform)
+                    uint32_t c[NB];
+                    sliced_counters<W>(p, off, a_tab + (gl + (uint32_t)r) * GB, c);
+                    if (gl + (uint32_t)r + 1u == G) {  // (warp-uniform) slots past the end of the panel never win
+#pragma unroll
+                        for (int pl = 0; pl < NB; pl++) c[pl] |= tail_mask;
+                    }
+                    const uint32_t lt = sliced_less<NB>(c, mn, p.ck_one);  // slots whose new barcode is STRICTLY closer: ties keep the earlier group
+                    uint32_t lost[NB];
+#pragma unroll
+                    for (int pl = 0; pl < NB; pl++) {
+                        lost[pl] = (mn[pl] & lt) | (c[pl] & ~lt);  // the larger of the two
+                        mn[pl] = (c[pl] & lt) | (mn[pl] & ~lt);
+                    }
+                    const uint32_t lt2 = sliced_less<NB>(lost, ls, p.ck_one);
+#pragma unroll
+                    for (int pl = 0; pl < NB; pl++) ls[pl] = (lost[pl] & lt2) | (ls[pl] & ~lt2);
+#pragma unroll
+                    for (int b = 0; b < UB; b++) gi[b] = ((r >> b) & 1) ? (gi[b] | lt) : (gi[b] & ~lt);
+#pragma unroll
+                    for (int b = UB; b < GBITS; b++) gi[b] = (gi[b] & ~lt) | (lt & (0u - ((gq >> (b - UB)) & 1u)));
+                }
             }
-            const uint32_t g0 = chunk * chunk_groups, ng = min(chunk_groups, G - g0);
+            // reduce the 32 slots: best = smallest mn, among equals the smallest group, then the smallest slot
+            uint32_t pool = 0xFFFFFFFFu;
+            const uint32_t d1 = sliced_min<NB>(mn, pool);
+            const uint32_t g1 = sliced_min<GBITS>(gi, pool);
+            const uint32_t j1 = (uint32_t)__ffs(pool) - 1u;
+            k1 = (d1 << 16) | (g1 * 32u + j1);
+            // second smallest of the multiset: every other slot's smallest, the winning slot's second smallest
+            const uint32_t win = 1u << j1;
+            uint32_t q[NB];
+#pragma unroll
+            for (int pl = 0; pl < NB; pl++) q[pl] = (ls[pl] & win) | (mn[pl] & ~win);
+            pool = 0xFFFFFFFFu;
+            k2 = (p.S < 2u) ? EMPTY_KEY : (sliced_min<NB>(q, pool) << 16);  // one-sample panel: next_best stays 255 (:122)
+        } else {
+            const uint32_t st = results[i];
+            k1 = ((st >> 16) & 0xFFu) << 16 | (st & 0xFFFFu);
+            k2 = (st >> 24) << 16;
+            uint32_t thr[NB];  // planes of T
+#pragma unroll
+            for (int pl = 0; pl < NB; pl++) thr[pl] = 0u - (((k2 >> 16) >> pl) & 1u);
             for (uint32_t gl = 0; gl < ng; gl++) {
                 const uint32_t g = g0 + gl;
                 uint32_t c[NB];
-                sliced_counters<W>(off, a_tab + gl * GB, c);
-                const uint32_t vm = (g + 1u == G && (p.S & 31u)) ? ((1u << (p.S & 31u)) - 1u) : 0xFFFFFFFFu;  // real barcodes
-                if (!have2) {
-                    // fewer than two barcodes seen so far (the first group): smallest and second smallest of the group
-                    // found bit-sliced — from the top plane down, keep the candidates that have a 0 where any has one
-                    uint32_t pool = vm;
+                sliced_counters<W>(p, off, a_tab + gl * GB, c);
+                if (g + 1u == G) {
 #pragma unroll
-                    for (int which = 0; which < 2; which++) {
-                        if (pool) {
-                            uint32_t cand = pool, d = 0u;
-#pragma unroll
-                            for (int pl = NB - 1; pl >= 0; pl--) {
-                                const uint32_t t = cand & ~c[pl];
-                                d |= t ? 0u : (1u << pl);
-                                cand = t ? t : cand;
-                            }
-                            const uint32_t j = (uint32_t)__ffs(cand) - 1u;  // first index among equals (barcode_matching.rs:132)
-                            track2(k1, k2, (d << 16) | (g * 32u + j));
-                            pool &= ~(1u << j);
-                        }
-                    }
-                } else {
-                    // bit-sliced d < T over the 32 barcodes; a barcode closer than the second best so far is rare
-                    uint32_t lt = 0u, eq = vm;
-#pragma unroll
-                    for (int pl = NB - 1; pl >= 0; pl--) {
-                        lt |= eq & ~c[pl] & thr[pl];
-                        eq &= ~(c[pl] ^ thr[pl]);
-                    }
-                    if (lt == 0u) continue;
-                    do {
-                        const uint32_t j = (uint32_t)__ffs(lt) - 1u;
-                        lt &= lt - 1u;
-                        track2(k1, k2, (sliced_extract<NB>(c, j) << 16) | (g * 32u + j));
-                    } while (lt);
+                    for (int pl = 0; pl < NB; pl++) c[pl] |= tail_mask;
                 }
-                if (k2 != EMPTY_KEY) {  // (re)build the threshold planes from the second-best distance
-                    have2 = true;
-                    const uint32_t T = k2 >> 16;
+                uint32_t lt = sliced_less<NB>(c, thr, p.ck_one);
+                if (lt == 0u) continue;
+                do {
+                    const uint32_t j = (uint32_t)__ffs(lt) - 1u;
+                    lt &= lt - 1u;
+                    uint32_t d = 0u;
 #pragma unroll
-                    for (int pl = 0; pl < NB; pl++) thr[pl] = 0u - ((T >> pl) & 1u);
-                }
+                    for (int pl = 0; pl < NB; pl++) d |= ((c[pl] >> j) & 1u) << pl;
+                    track2(k1, k2, (d << 16) | (g * 32u + j));
+                } while (lt);
+#pragma unroll
+                for (int pl = 0; pl < NB; pl++) thr[pl] = 0u - (((k2 >> 16) >> pl) & 1u);
             }
         }
-        if (live) {
+        if (last) {
             const uint32_t res = row_ok ? decide(k1, k2, p.max_mm, p.min_delta) : NONE;
             results[i] = res;
             cnt.add(res);
+        } else {
+            results[i] = sliced_pack_state(k1, k2);
         }
     }
-    cnt.flush();
+    if (last) cnt.flush();
 }
 
 // L > 32 (W = 5 .. 32 packed words; rare — barcodes this long are unusual): nibble-word form straight from the packed
@@ -1933,19 +1986,31 @@ static cudaError_t launch_brute_long_w(const MatchParams& p, const ReadSource& s
     return cudaGetLastError();
 }
 
+template <int W, bool ASCII, int GBITS>
+static cudaError_t launch_brute_sliced_g(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
+                                         const LaunchGeometry& g, cudaStream_t stream, uint32_t chunk_groups) {
+    const uint32_t G = (p.S + 31u) / 32u;
+    const size_t smem = (size_t)chunk_groups * Sliced<W>::GROUP_BYTES + hist_bytes(p);
+    auto k0 = k_brute_sliced<W, ASCII, GBITS, true>;
+    auto k1 = k_brute_sliced<W, ASCII, 1, false>;  // later chunks: no slot state
+    cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (uint32_t chunk = 0; chunk * chunk_groups < G; chunk++) {  // stream order carries the interim state in d_results
+        if (chunk == 0u)
+            k0<<<grid_for(k0, sliced_threads(W), smem, g, src.n), sliced_threads(W), smem, stream>>>(p, src, d_results, chunk_groups, chunk);
+        else
+            k1<<<grid_for(k1, sliced_threads(W), smem, g, src.n), sliced_threads(W), smem, stream>>>(p, src, d_results, chunk_groups, chunk);
+        count_launch();
+    }
+    return cudaGetLastError();
+}
 template <int W, bool ASCII>
 static cudaError_t launch_brute_sliced(const MatchParams& p, const ReadSource& src, uint32_t* d_results,
                                        const LaunchGeometry& g, cudaStream_t stream) {
     const uint32_t G = (p.S + 31u) / 32u;
-    const size_t hb = hist_bytes(p);
     const uint32_t chunk_groups = std::max<uint32_t>(1u, std::min<uint32_t>(G, SLICED_CHUNK_BYTES / Sliced<W>::GROUP_BYTES));
-    const size_t smem = (size_t)chunk_groups * Sliced<W>::GROUP_BYTES + hb;
-    auto k = k_brute_sliced<W, ASCII>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int grid = grid_for(k, SLICED_THREADS, smem, g, src.n);
-    k<<<grid, SLICED_THREADS, smem, stream>>>(p, src, d_results, chunk_groups);
-    count_launch();
-    return cudaGetLastError();
+    if (chunk_groups <= 16u) return launch_brute_sliced_g<W, ASCII, 4>(p, src, d_results, g, stream, chunk_groups);
+    return launch_brute_sliced_g<W, ASCII, 8>(p, src, d_results, g, stream, chunk_groups);  // a chunk is <= 192 groups
 }
 
 static bool brute_v1() {  // FQTK_B200_BRUTE_V1=1 (A/B timing): the barcode-pair kernel of round 1 instead of the bit-sliced one
