@@ -249,61 +249,102 @@ __device__ __forceinline__ uint8_t* put_num(uint8_t* d, uint32_t r) {
     return d;
 }
 
+// Thread per record for the header (a few dozen bytes assembled piece by piece), then the WARP copies the bases and the
+// qualities of its 32 records one record at a time, 32 consecutive bytes per step: those two lines are ~6/7 of the bytes,
+// and written one byte per thread they touch 32 different sectors per store instruction (the first version of this
+// kernel: 3.1 ms for 294 MB of text).
 __global__ void __launch_bounds__(EM_THREADS) k_emit_write(const EmitPlan p, const uint32_t* __restrict__ order, uint64_t n,
                                                           const unsigned long long* __restrict__ pre,
                                                           const unsigned long long* __restrict__ stream_base,
                                                           uint8_t* __restrict__ text) {
     const uint32_t t = blockIdx.y;
-    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t i = order[j];
-        uint8_t* d = text + stream_base[t] + pre[(size_t)t * (n + 1) + j];
-        uint32_t nm = 0;
-        for (uint32_t k = 0; k < p.n_segs; k++) nm += p.seg[k].kind == 'M';
-        const HeaderPlan hp = plan_header(p, i, nm != 0);
-        *d++ = '@';
-        d = put(d, hp.h, hp.name_len);
-        if (nm) {
-            *d++ = hp.umi_sep_plus ? '+' : ':';
-            bool first = true;
-            for (uint32_t k = 0; k < p.n_segs; k++)
-                if (p.seg[k].kind == 'M') {
-                    if (!first) *d++ = '+';
-                    first = false;
-                    const SegView v = seg_view(p, k, i);
-                    d = put(d, v.bases, v.len);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t n_round = (n + 31u) & ~(uint64_t)31u;  // whole warps stay in the loop (shuffles below)
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint8_t *src_b = nullptr, *src_q = nullptr;
+        uint8_t* dst = nullptr;
+        uint32_t len = 0;
+        if (j < n) {
+            const uint64_t i = order[j];
+            uint8_t* d = text + stream_base[t] + pre[(size_t)t * (n + 1) + j];
+            uint32_t nm = 0;
+            for (uint32_t k = 0; k < p.n_segs; k++) nm += p.seg[k].kind == 'M';
+            const HeaderPlan hp = plan_header(p, i, nm != 0);
+            *d++ = '@';
+            d = put(d, hp.h, hp.name_len);
+            if (nm) {
+                *d++ = hp.umi_sep_plus ? '+' : ':';
+                bool first = true;
+                for (uint32_t k = 0; k < p.n_segs; k++)
+                    if (p.seg[k].kind == 'M') {
+                        if (!first) *d++ = '+';
+                        first = false;
+                        const SegView v = seg_view(p, k, i);
+                        d = put(d, v.bases, v.len);
+                    }
+            }
+            *d++ = ' ';
+            const uint32_t r = p.stream_readnum[t];
+            if (hp.mode == 0) {
+                d = put_num(d, r);
+                *d++ = ':'; *d++ = 'N'; *d++ = ':'; *d++ = '0'; *d++ = ':';
+            } else if (hp.mode == 1) {
+                d = put(d, hp.h + hp.c_off, hp.c_len);
+                if (hp.add_colon) *d++ = ':';
+            } else {
+                d = put_num(d, r);
+                *d++ = ':';
+                d = put(d, hp.h + hp.rem_off, hp.rem_len);
+                if (hp.add_plus) *d++ = '+';
+            }
+            {
+                bool first = true;
+                for (uint32_t k = 0; k < p.n_segs; k++)
+                    if (p.seg[k].kind == 'B') {
+                        if (!first) *d++ = '+';
+                        first = false;
+                        const SegView v = seg_view(p, k, i);
+                        d = put(d, v.bases, v.len);
+                    }
+            }
+            *d++ = '\n';
+            const uint32_t sk = p.stream_seg[t];
+            const SegView v = seg_view(p, sk, i);
+            src_b = v.bases;
+            src_q = qual_line(p.chunk[p.seg[sk].source], v.seq_off, v.seq_len) + v.offset;
+            dst = d;
+            len = v.len;
+            d += len;
+            *d++ = '\n'; *d++ = '+'; *d++ = '\n';
+            d[len] = '\n';
+        }
+        // bases at dst[0, len), qualities at dst[len + 3, 2 len + 3): record rr of the warp, all lanes
+        for (int rr = 0; rr < 32; rr++) {
+            const uint32_t ln = __shfl_sync(0xFFFFFFFFu, len, rr);
+            if (ln == 0u) continue;  // (warp-uniform)
+            const uint8_t* sb = reinterpret_cast<const uint8_t*>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(src_b), rr));
+            const uint8_t* sq = reinterpret_cast<const uint8_t*>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(src_q), rr));
+            uint8_t* dd = reinterpret_cast<uint8_t*>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(dst), rr));
+            for (uint32_t k0 = 0; k0 < ln; k0 += 128u) {  // four steps' loads in flight
+                uint8_t b[4], q[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t k = k0 + 32u * u + lane;
+                    if (k < ln) {
+                        b[u] = sb[k];
+                        q[u] = sq[k];
+                    }
                 }
-        }
-        *d++ = ' ';
-        const uint32_t r = p.stream_readnum[t];
-        if (hp.mode == 0) {
-            d = put_num(d, r);
-            *d++ = ':'; *d++ = 'N'; *d++ = ':'; *d++ = '0'; *d++ = ':';
-        } else if (hp.mode == 1) {
-            d = put(d, hp.h + hp.c_off, hp.c_len);
-            if (hp.add_colon) *d++ = ':';
-        } else {
-            d = put_num(d, r);
-            *d++ = ':';
-            d = put(d, hp.h + hp.rem_off, hp.rem_len);
-            if (hp.add_plus) *d++ = '+';
-        }
-        {
-            bool first = true;
-            for (uint32_t k = 0; k < p.n_segs; k++)
-                if (p.seg[k].kind == 'B') {
-                    if (!first) *d++ = '+';
-                    first = false;
-                    const SegView v = seg_view(p, k, i);
-                    d = put(d, v.bases, v.len);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t k = k0 + 32u * u + lane;
+                    if (k < ln) {
+                        dd[k] = b[u];
+                        dd[ln + 3u + k] = q[u];
+                    }
                 }
+            }
         }
-        *d++ = '\n';
-        const uint32_t sk = p.stream_seg[t];
-        const SegView v = seg_view(p, sk, i);
-        d = put(d, v.bases, v.len);
-        *d++ = '\n'; *d++ = '+'; *d++ = '\n';
-        d = put(d, qual_line(p.chunk[p.seg[sk].source], v.seq_off, v.seq_len) + v.offset, v.len);
-        *d++ = '\n';
     }
 }
 

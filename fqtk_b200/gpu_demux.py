@@ -14,8 +14,10 @@ compare this one with)."""
 from __future__ import annotations
 
 import ctypes as C
+import threading
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
-from typing import Sequence
+from typing import Iterable, Iterator, Sequence
 
 import numpy as np
 
@@ -34,12 +36,18 @@ class GpuDemuxResult:
     text_bytes: int = 0                         # uncompressed FASTQ bytes written on the device
 
 
-_PINNED = {"ptr": None, "cap": 0}
+class _PinnedTls(threading.local):  # one grow-only buffer per host thread (DemuxLanes runs one thread per lane)
+    def __init__(self):
+        self.d = {"ptr": None, "cap": 0}
+
+
+_PINNED_TLS = _PinnedTls()
 
 
 def _pinned_out(nbytes: int) -> np.ndarray:
     """A grow-only pinned host buffer for the compressed images (fqtk_b200_host_alloc): the D2H copy runs at full rate."""
     lib = _lib.lib()
+    _PINNED = _PINNED_TLS.d
     if nbytes > _PINNED["cap"]:
         if _PINNED["ptr"]:
             lib.fqtk_b200_host_free(_PINNED["ptr"])
@@ -238,3 +246,51 @@ def demux_chunks(matcher, compressor, sample_ids: Sequence[str], barcodes: Seque
     res.counts = np.array(list(counts), dtype=np.uint64)
     res.metrics = demux_metrics(list(sample_ids), list(barcodes), [int(c) for c in res.counts], unmatched_prefix)
     return res, [int(c) for c in consumed]
+
+
+class DemuxLanes:
+    """K (matcher, compressor) pairs on ONE device, one host thread each; batch i goes to lane i % K.
+
+    The stages of one fqtk_b200_demux_chunks call run back to back (copy in, scan, match, route, records, BGZF, copy out),
+    so one lane leaves the copy engines idle while its kernels run and the SMs idle while it copies.  Two lanes overlap
+    the copy of one batch with the kernels of the other — the device-side form of the reference's reader thread, main loop
+    and writer pool running concurrently (demux.rs:921-934, :755-798).  Results come back in batch order, which is what keeps
+    every output file's records in input order (demux.rs:1505-1523); counts() is the sum over the lanes' matchers.
+    A Rust host does the same with two matcher / compressor handles and two threads."""
+
+    def __init__(self, make_lane, lanes: int = 2):
+        # make_lane() -> (BarcodeMatcher, BgzfCompressor): called once per lane, on the caller's thread
+        self.lanes = [make_lane() for _ in range(lanes)]
+        self._pools = [ThreadPoolExecutor(max_workers=1) for _ in range(lanes)]
+
+    def map(self, batches: Iterable[Sequence], sample_ids, barcodes, read_structures, output_types=("T",), raw: bool = False,
+            depth: int | None = None, **kw) -> Iterator:
+        """Yields demux_chunks(...) of every batch (a sequence of FASTQ texts, one per input), in batch order; at most
+        `depth` (default: the number of lanes) batches are in flight."""
+        depth = depth or len(self.lanes)
+        pending = []
+        for i, texts in enumerate(batches):
+            m, z = self.lanes[i % len(self.lanes)]
+            pending.append(self._pools[i % len(self.lanes)].submit(demux_chunks, m, z, sample_ids, barcodes, read_structures, texts,
+                                                                   output_types, raw=raw, **kw))
+            if len(pending) >= depth:
+                yield pending.pop(0).result()
+        while pending:
+            yield pending.pop(0).result()
+
+    def counts(self) -> np.ndarray:
+        return np.sum([m.counts() for m, _ in self.lanes], axis=0)
+
+    def close(self):
+        for p in self._pools:
+            p.shutdown(wait=True)
+        for m, z in self.lanes:
+            z.close()
+            m.close()
+        self.lanes = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

@@ -331,6 +331,41 @@ def test_gpu_whole_data_path_equals_the_host_formatted_pipeline():
 
 
 @pytest.mark.gpu
+def test_gpu_two_lanes_leave_the_files_of_one_lane():
+    """DemuxLanes: batches alternate between two (matcher, compressor) pairs on two host threads so that one batch's copies
+    overlap the other's kernels.  Same per-batch results, in batch order, as one lane working through the batches; every
+    file = its batches' members in order (records of a sample stay in input order, demux.rs:1505-1523); counts add up."""
+    from fqtk_b200 import BarcodeMatcher, synth
+    from fqtk_b200.bgzf import BgzfCompressor
+    from fqtk_b200.gpu_demux import DemuxLanes, demux_chunks
+
+    cfg = synth.CONFIGS[3]
+    panel = synth.panel(cfg)
+    bcs = [bytes(r).decode() for r in panel]
+    ids = [f"S{j}" for j in range(len(bcs))]
+    rng = np.random.default_rng(5)
+    batches = []
+    for b in range(7):
+        n = int(rng.integers(1500, 6000))
+        reads = synth.reads_host(panel, cfg.seed_reads, 100_000 * b, n)
+        t = [b"".join(b"@r%d_%d 1:N:0:0\n%s\n+\n%s\n" % (b, i, bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=40)), b"F" * 40)
+                      for i in range(n)),
+             b"".join(b"@r%d_%d 1:N:0:0\n%s\n+\n%s\n" % (b, i, bytes(reads[i]), b"F" * 16) for i in range(n))]
+        batches.append(t)
+    structures = ["+T", "8B8B"]
+    with BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta) as m, BgzfCompressor(0) as z:
+        want = [demux_chunks(m, z, ids, bcs, structures, t, ["T", "B"]) for t in batches]
+        total = m.counts()
+    with DemuxLanes(lambda: (BarcodeMatcher(bcs, cfg.max_mismatches, cfg.min_mismatch_delta), BgzfCompressor(0)), lanes=2) as lanes:
+        got = list(lanes.map(batches, ids, bcs, structures, ["T", "B"]))
+        assert np.array_equal(lanes.counts(), total)
+    assert len(got) == len(want)
+    for (g, gu), (w, wu) in zip(got, want):
+        assert gu == wu and g.files == w.files and np.array_equal(g.counts, w.counts)
+    assert int(total.sum()) == sum(int(w.counts.sum()) for w, _ in want)
+
+
+@pytest.mark.gpu
 def test_gpu_header_rewrite_reference_vectors():
     """The reference's six write_header tests (demux.rs:2084-2196) through the device kernel: a one-record FASTQ whose read
     structure yields the test's sample-barcode and UMI segments, two template streams so that read number 2 exists."""

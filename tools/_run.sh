@@ -1,10 +1,6 @@
 set -u
-mkdir -p gpurun_out/s3b
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -4
-B="python bench.py --no-cpu-baseline --no-e2e --no-routing --no-bgzf --no-configs --no-parity-check --no-brute --mode brute --steps 3 --warmup 2"
-for c in 3 4 5 2; do
-  $B --config $c --reads 67108864 2>gpurun_out/s3b/err_$c.txt | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('cfg', $c, 'ms', d['ms_per_step'], 'pairs/s', d['roofline'].get('pair_compares_per_s'), d['roofline'].get('kernel'))"
-  tail -2 gpurun_out/s3b/err_$c.txt
+B="python bench.py --no-cpu-baseline --no-e2e --no-brute --no-routing --no-configs --no-parity-check"
+for L in 2 3 4; do
+FQTK_B200_BENCH_LANES=$L $B --steps 3 --warmup 3 2>/tmp/err.txt | python -c "
+import json,sys;d=json.loads(sys.stdin.read());b=d['bgzf'];w=b['whole_data_path'];print($L, w['one_call']['ms'], w['two_lanes']['ms_per_batch'])"; tail -2 /tmp/err.txt
 done
