@@ -380,6 +380,36 @@ def test_many_samples_use_global_histogram_and_big_panel():
     check_against_oracle(bcs2, 1, 2, reads2, use_cache=False, expect_mode="brute")
 
 
+@pytest.mark.parametrize("L,S", [(8, 1), (8, 2), (8, 31), (8, 33), (16, 64), (16, 545), (16, 3072), (16, 3073), (16, 6200),
+                                 (20, 2047), (20, 2049), (24, 4100), (32, 1536), (32, 1537), (29, 3200)])
+def test_brute_sliced_ties_across_groups_and_chunk_launches(L, S):
+    """k_brute_sliced keeps its running minima bit-sliced per slot (barcodes 32g + j of all groups g), reduces them after the
+    first shared-memory chunk and walks the rest of a large panel one launch per chunk with the interim state in the result
+    word.  Panels made of near-duplicates of a few barcodes put equal best distances in different slots, groups and chunks
+    (FIRST index wins, barcode_matching.rs:132) and equal second-best distances everywhere (:140); S around the group and
+    chunk boundaries (3 072 barcodes per chunk at L <= 16, 2 048 at L <= 24, 1 536 at L <= 32) covers the partial last group
+    of the first and of a later launch."""
+    rng = np.random.default_rng(1000 * L + S)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    roots = acgt[rng.integers(0, 4, size=(7, L))]
+    panel = roots[rng.integers(0, len(roots), size=S)].copy()
+    for j in range(S):  # 0 - 2 substitutions; a few IUPAC codes and no-calls in the sheet
+        for _ in range(int(rng.integers(0, 3))):
+            panel[j, rng.integers(0, L)] = acgt[rng.integers(0, 4)]
+        if rng.random() < 0.05:
+            panel[j, rng.integers(0, L)] = np.frombuffer(b"RYKMSWN", dtype=np.uint8)[rng.integers(0, 7)]
+    bcs = [bytes(r) for r in panel]
+    n = 6000 + int(rng.integers(0, 40))
+    reads = panel[rng.integers(0, S, size=n)].copy()
+    reads[:n // 8] = roots[rng.integers(0, len(roots), size=n // 8)]
+    sub = rng.random(size=reads.shape) < 0.06
+    reads[sub] = acgt[rng.integers(0, 4, size=int(sub.sum()))]
+    reads[rng.random(size=reads.shape) < 0.01] = ord("N")
+    reads[rng.random(size=reads.shape) < 0.003] = ord("S")
+    for mm, delta in [(3, 0), (1, 2), (L, 1)]:
+        check_against_oracle(bcs, mm, delta, reads, use_cache=False, expect_mode="brute")
+
+
 def test_table_budget_falls_back_to_brute():
     L = _lib.lib()
     try:

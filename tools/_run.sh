@@ -1,6 +1,9 @@
 set -u
-B="python bench.py --no-cpu-baseline --no-e2e --no-brute --no-routing --no-configs --no-parity-check"
-for L in 2 3 4; do
-FQTK_B200_BENCH_LANES=$L $B --steps 3 --warmup 3 2>/tmp/err.txt | python -c "
-import json,sys;d=json.loads(sys.stdin.read());b=d['bgzf'];w=b['whole_data_path'];print($L, w['one_call']['ms'], w['two_lanes']['ms_per_batch'])"; tail -2 /tmp/err.txt
+OUT=gpurun_out/s3d; mkdir -p $OUT
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "brute_sliced_ties" 2>&1 | tail -4
+for tool in memcheck racecheck; do
+  timeout 600 compute-sanitizer --tool $tool --kernel-regex kns=k_brute_sliced --log-file $OUT/brute_$tool.log python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "brute_sliced_ties and (8-33 or 16-3073 or 20-2049 or 32-1537)" > $OUT/brute_$tool.out 2>&1
+  echo "brute $tool rc=$?"; tail -2 $OUT/brute_$tool.out; tail -2 $OUT/brute_$tool.log
+  timeout 600 compute-sanitizer --tool $tool --kernel-regex kns=k_emit --log-file $OUT/emit_$tool.log python -m pytest tests/test_bgzf.py -m gpu -x -q -k "header_rewrite or demux_outputs_as_bgzf or two_lanes" > $OUT/emit_$tool.out 2>&1
+  echo "emit $tool rc=$?"; tail -2 $OUT/emit_$tool.out; tail -2 $OUT/emit_$tool.log
 done
