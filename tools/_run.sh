@@ -1,9 +1,8 @@
 set -u
-OUT=gpurun_out/s3d; mkdir -p $OUT
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "brute_sliced_ties" 2>&1 | tail -4
-for tool in memcheck racecheck; do
-  timeout 600 compute-sanitizer --tool $tool --kernel-regex kns=k_brute_sliced --log-file $OUT/brute_$tool.log python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "brute_sliced_ties and (8-33 or 16-3073 or 20-2049 or 32-1537)" > $OUT/brute_$tool.out 2>&1
-  echo "brute $tool rc=$?"; tail -2 $OUT/brute_$tool.out; tail -2 $OUT/brute_$tool.log
-  timeout 600 compute-sanitizer --tool $tool --kernel-regex kns=k_emit --log-file $OUT/emit_$tool.log python -m pytest tests/test_bgzf.py -m gpu -x -q -k "header_rewrite or demux_outputs_as_bgzf or two_lanes" > $OUT/emit_$tool.out 2>&1
-  echo "emit $tool rc=$?"; tail -2 $OUT/emit_$tool.out; tail -2 $OUT/emit_$tool.log
-done
+OUT=gpurun_out/s3e; mkdir -p $OUT
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 5 --warmup 3 > $OUT/bench2.json 2> $OUT/bench2.err
+echo "bench2 rc=$?"; tail -3 $OUT/bench2.err; cut -c1-300 $OUT/bench2.json
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > $OUT/ref2.json 2> $OUT/ref2.err
+echo "ref2 rc=$?"; cut -c1-200 $OUT/ref2.json
+timeout 600 python bench.py --gpus 2 --single-process --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench2sp.json 2> $OUT/bench2sp.err
+echo "bench2sp rc=$?"; tail -2 $OUT/bench2sp.err; cut -c1-200 $OUT/bench2sp.json
