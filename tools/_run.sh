@@ -1,8 +1,8 @@
 set -u
-OUT=gpurun_out/s3e; mkdir -p $OUT
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 5 --warmup 3 > $OUT/bench2.json 2> $OUT/bench2.err
-echo "bench2 rc=$?"; tail -3 $OUT/bench2.err; cut -c1-300 $OUT/bench2.json
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > $OUT/ref2.json 2> $OUT/ref2.err
-echo "ref2 rc=$?"; cut -c1-200 $OUT/ref2.json
-timeout 600 python bench.py --gpus 2 --single-process --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench2sp.json 2> $OUT/bench2sp.err
-echo "bench2sp rc=$?"; tail -2 $OUT/bench2sp.err; cut -c1-200 $OUT/bench2sp.json
+timeout 900 python -m pytest tests/test_bgzf.py tests/test_cpp_mirror.py -m gpu -x -q 2>&1 | tail -3
+B="python bench.py --no-cpu-baseline --no-e2e --no-brute --no-routing --no-configs --no-parity-check"
+for L in 2 3; do
+FQTK_B200_BENCH_LANES=$L $B --steps 3 --warmup 3 2>/tmp/err.txt | python -c "
+import json,sys;d=json.loads(sys.stdin.read());b=d['bgzf'];w=b['whole_data_path'];print($L, 'one', w['one_call']['ms'], 'lanes', w['two_lanes']['ms_per_batch'], 'dev', b['device']['ms'], 'host_call', b['host_call']['ms'])"; tail -2 /tmp/err.txt
+done
+FQTK_B200_TRACE=1 $B --steps 3 --warmup 3 2>&1 >/dev/null | grep demux_chunks | head -12
