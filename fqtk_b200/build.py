@@ -23,7 +23,7 @@ NVCC_FLAGS = [
 
 
 def sources() -> list[str]:
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu"))) + sorted(glob.glob(os.path.join(CSRC, "*.cpp")))
 
 
 def deps() -> list[str]:

@@ -3,7 +3,8 @@
 //                           into contiguous shards with one host thread per device, and the per-sample count table
 //                           summed on the first device over NVLink peer access (the reference keeps ONE table:
 //                           src/bin/commands/demux.rs:921-926, 970-975)
-//   * fqtk_b200_pack_host   encode() (src/lib/mod.rs:49-61) for a batch on the host, two symbols per table lookup
+//   * fqtk_b200_pack_host   encode() (src/lib/mod.rs:49-61) for a batch on the host: two symbols per table lookup, or the
+//                           AVX2 stream form of host_pack.cpp when the rows lie back to back and L is a multiple of 8
 //   * fqtk_b200_copy_ceiling   the pinned-memory copy rate of the platform (no kernels): the ceiling any host-buffer call
 //                           is measured against
 // Everything here goes through the public single-matcher entry points; it holds no matching logic of its own.
@@ -22,6 +23,8 @@
 namespace fq {
 void count_launch();
 void set_last_error(const std::string& msg);
+bool have_avx2();                                                                                 // host_pack.cpp
+void pack_stream(const uint8_t* in, uint64_t n_bytes, uint8_t* out, const uint8_t* lut);  // host_pack.cpp
 }  // namespace fq
 
 namespace {
@@ -263,9 +266,20 @@ int fqtk_b200_pack_host(const uint8_t* rows, uint64_t n, uint32_t L, uint64_t st
             t[v] = (uint8_t)(fq::encode_byte(v & 0xFFu) | (fq::encode_byte(v >> 8) << 4));
         return t;
     }();
+    static const std::vector<uint8_t> lut1 = [] {
+        std::vector<uint8_t> t(256);
+        for (uint32_t v = 0; v < 256u; v++) t[v] = (uint8_t)fq::encode_byte(v);
+        return t;
+    }();
     const uint32_t W = fq::words_for_len(L);
     const uint8_t* lut = lut2.data();
+    // rows back to back and L a multiple of 8 (cfg 2, 3, 4): the batch is one stream of symbols -> host_pack.cpp (AVX2)
+    const bool stream = stride == L && (L % 8u) == 0u && fq::have_avx2();
     auto work = [&](uint64_t lo, uint64_t hi) {
+        if (stream) {
+            fq::pack_stream(rows + lo * L, (hi - lo) * L, reinterpret_cast<uint8_t*>(out_packed + lo * W), lut1.data());
+            return;
+        }
         for (uint64_t i = lo; i < hi; i++) {
             const uint8_t* r = rows + i * stride;
             uint32_t* o = out_packed + i * W;

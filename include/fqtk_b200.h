@@ -148,7 +148,9 @@ FQTK_B200_API int fqtk_b200_matcher_assign_batch(fqtk_b200_matcher* m, const uin
 FQTK_B200_API int fqtk_b200_matcher_assign_batch_packed(fqtk_b200_matcher* m, const uint32_t* packed, uint64_t n_reads,
                                                         uint32_t* results, uint16_t* sample_index);
 /* encode() of n_reads host rows (mod.rs:49-61): row i at rows + i*row_stride, barcode_len symbols each -> W words each.
- * Pure encoding on the host (two symbols per table lookup, `threads` host threads, 0 = all), no GPU involved. */
+ * Pure encoding on the host, no GPU involved, `threads` host threads (0 = all): rows back to back with barcode_len a multiple
+ * of 8 are one stream of symbols and take an AVX2 form (32 symbols per step; csrc/host_pack.cpp), any other layout two symbols
+ * per table lookup; the result is encode()'s for every byte value either way. */
 FQTK_B200_API int fqtk_b200_pack_host(const uint8_t* rows, uint64_t n_reads, uint32_t barcode_len, uint64_t row_stride,
                                       uint32_t* out_packed, int threads);
 

@@ -319,6 +319,29 @@ def test_pack_host_is_encode_for_every_row():
         assert np.array_equal(out, got), L
 
 
+def test_pack_host_stream_path_is_encode_for_every_byte_value():
+    """Rows back to back with L a multiple of 8 take the AVX2 stream form (host_pack.cpp): A/C/G/T/N in either case by byte
+    shuffles, any 32-byte step with another byte in it through the table.  Mostly-clean streams with sparse IUPAC codes,
+    dots, lower case and arbitrary bytes (every value 0 .. 255 appears), sizes that leave scalar tails, 1 / 3 / all threads."""
+    from fqtk_b200 import synth
+    from fqtk_b200.barcode_matching import pack_host
+
+    rng = np.random.default_rng(77)
+    clean = np.frombuffer(b"ACGTNacgtn", dtype=np.uint8)
+    for L in (8, 16, 24, 32, 40):
+        for n in (1, 3, 5, 100_003):
+            reads = clean[rng.integers(0, 5 if n > 5 else 10, size=(n, L))].copy()
+            if n > 5:
+                odd = rng.random(size=reads.shape) < 0.002
+                reads[odd] = rng.integers(0, 256, size=int(odd.sum()), dtype=np.uint8)
+                reads[7::997, L - 1] = np.arange(len(reads[7::997]), dtype=np.uint8)  # every byte value, last column
+                reads[11::31, 0] = clean[5 + rng.integers(0, 5, size=len(reads[11::31]))]  # lower case
+                reads[13::53, 3] = np.frombuffer(b".RYKMSWBDHVUu", dtype=np.uint8)[rng.integers(0, 13, size=len(reads[13::53]))]
+            want = synth.pack_host(reads)
+            for threads in (1, 3, 0):
+                assert np.array_equal(pack_host(reads, threads=threads), want), (L, n, threads)
+
+
 def test_fastq_scanner():
     """fqtk_b200_fastq_scan: offsets / lengths of every complete 4-line record, carry-over of a record cut by the chunk
     boundary, CRLF line ends, and the three malformed-record errors.  Host only."""
