@@ -27,7 +27,8 @@ SYMBOLS = [
     "fqtk_b200_matcher_route_device", "fqtk_b200_matcher_route",
     "fqtk_b200_matcher_assign_packed_device", "fqtk_b200_matcher_assign_ascii_device", "fqtk_b200_pack_device",
     "fqtk_b200_encode_host", "fqtk_b200_matcher_counts", "fqtk_b200_matcher_counts_device",
-    "fqtk_b200_matcher_reset_counts", "fqtk_b200_matcher_set_mode", "fqtk_b200_kernel_launches",
+    "fqtk_b200_matcher_reset_counts", "fqtk_b200_matcher_set_mode", "fqtk_b200_matcher_set_host_pack",
+    "fqtk_b200_kernel_launches",
     "fqtk_b200_last_error", "fqtk_b200_device_count", "fqtk_b200_host_alloc", "fqtk_b200_host_free",
     "fqtk_b200_synth_panel", "fqtk_b200_synth_reads_host", "fqtk_b200_synth_reads_device",
     "fqtk_b200_matcher_assign_batch_packed", "fqtk_b200_pack_host", "fqtk_b200_copy_ceiling",
@@ -138,6 +139,7 @@ def lib() -> C.CDLL:
         "fqtk_b200_matcher_counts_device": (C.c_int, [vp, C.POINTER(vp)]),
         "fqtk_b200_matcher_reset_counts": (C.c_int, [vp]),
         "fqtk_b200_matcher_set_mode": (C.c_int, [vp, C.c_int]),
+        "fqtk_b200_matcher_set_host_pack": (C.c_int, [vp, C.c_int]),
         "fqtk_b200_kernel_launches": (C.c_uint64, []),
         "fqtk_b200_last_error": (C.c_char_p, []),
         "fqtk_b200_device_count": (C.c_int, []),

@@ -126,6 +126,11 @@ class BarcodeMatcher:
     def set_mode(self, mode: str) -> None:
         _lib.check(_lib.lib().fqtk_b200_matcher_set_mode(self._h, {"brute": _lib.MODE_BRUTE, "table": _lib.MODE_TABLE}[mode]))
 
+    def set_host_pack(self, threads: int) -> None:
+        """assign_batch with encode() done by `threads` host threads while the batch is in flight (-1 = auto, 0 = off): the
+        packed words, half the bytes of the ASCII rows, cross PCIe (fqtk_b200_matcher_set_host_pack)."""
+        _lib.check(_lib.lib().fqtk_b200_matcher_set_host_pack(self._h, int(threads)))
+
     @property
     def words_per_read(self) -> int:
         return (self.barcode_len + 7) // 8

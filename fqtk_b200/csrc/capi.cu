@@ -7,8 +7,13 @@
 //                                                                       whose length differs from L
 //   * demux.rs:968-975           -> counts[S+1]
 // No CPU matching path exists here: distances, decisions and the memo-table contents all come from the kernels.
+#include <sched.h>
+
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <memory>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,6 +24,11 @@
 #include "../../include/fqtk_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+
+namespace fq {
+bool have_avx2();                                                                         // host_pack.cpp
+void pack_stream(const uint8_t* in, uint64_t n_bytes, uint8_t* out, const uint8_t* lut);  // host_pack.cpp
+}  // namespace fq
 
 namespace fq {
 cudaError_t synth_reads_device(const uint8_t* d_panel, uint32_t S, uint32_t L, uint64_t seed, uint64_t first,
@@ -82,6 +92,7 @@ char decode_mask(uint32_t mask) {
 }
 
 constexpr int N_PIPE = 3;                       // chunks in flight for the host-buffer call
+constexpr int N_STAGE = 4;                      // pinned staging slots of the host-pack route
 
 }  // namespace
 
@@ -112,6 +123,11 @@ struct fqtk_b200_matcher {
     uint64_t table_entries = 0, table_slots = 0, table_bytes = 0, table_candidates = 0;
     // host-buffer pipeline
     cudaStream_t streams[N_PIPE] = {};
+    // host-pack route of assign_batch (fqtk_b200_matcher_set_host_pack): pinned staging ring + the events of its copies
+    int host_pack_threads = 0;                 // 0 = off
+    uint8_t* h_stage[N_STAGE] = {};
+    size_t stage_cap = 0;
+    cudaEvent_t stage_ev[N_STAGE] = {};
     uint8_t* d_in[N_PIPE] = {};
     uint32_t* d_out[N_PIPE] = {};
     uint32_t* d_len[N_PIPE] = {};
@@ -816,6 +832,97 @@ int run_device(fqtk_b200_matcher* m, const fq::ReadSource& src, uint32_t* d_resu
     return FQTK_B200_OK;
 }
 
+// ---- assign_batch with encode() done by host threads (opt-in: fqtk_b200_matcher_set_host_pack) -------------------------
+// The ASCII rows of a batch cross PCIe at 16 bytes per read (L = 16) and the call runs at the copy rate.  With rows back to
+// back and L a multiple of 8 the host can encode them itself at more than that rate (host_pack.cpp: AVX2, 32 symbols per
+// step) and ship the reference's own BitEnc words — half the bytes — to the packed-route kernel.  T packer threads live for
+// the duration of the call; each packs its slice of every chunk into a ring of N_STAGE pinned staging slots, the calling
+// thread sends a chunk on as soon as all slices are in (H2D -> kernel -> D2H on the pipeline streams) and frees a slot
+// when the event behind its copy has fired.  No locks: per-chunk arrival counters and one `released` counter.
+int assign_batch_host_pack(fqtk_b200_matcher* m, const uint8_t* rows, uint64_t n, uint32_t* results, int T) {
+    static const std::vector<uint8_t> lut = [] {
+        std::vector<uint8_t> t(256);
+        for (uint32_t v = 0; v < 256u; v++) t[v] = (uint8_t)fq::encode_byte(v);
+        return t;
+    }();
+    const uint32_t L = m->L;
+    const uint64_t row_bytes = (uint64_t)m->W * 4u;  // == L / 2
+    uint64_t chunk = std::max<uint64_t>(m->opt.chunk_bytes / (4u * row_bytes), 65536) & ~3ull;  // finer than the plain
+    chunk = std::min<uint64_t>(chunk, n);                                                       // route: pack || copy
+    const uint64_t n_chunks = (n + chunk - 1) / chunk;
+    int rc = ensure_pipeline(m, (size_t)(chunk * row_bytes + 16), (size_t)chunk, false);
+    if (rc != FQTK_B200_OK) return rc;
+    if (chunk * row_bytes > m->stage_cap) {
+        for (int k = 0; k < N_STAGE; k++) {
+            if (m->h_stage[k]) cudaFreeHost(m->h_stage[k]);
+            m->h_stage[k] = nullptr;
+        }
+        m->stage_cap = 0;
+        for (int k = 0; k < N_STAGE; k++) CU(cudaHostAlloc(&m->h_stage[k], chunk * row_bytes, cudaHostAllocPortable));
+        m->stage_cap = chunk * row_bytes;
+    }
+    for (int k = 0; k < N_STAGE; k++)
+        if (!m->stage_ev[k]) CU(cudaEventCreateWithFlags(&m->stage_ev[k], cudaEventDisableTiming));
+
+    std::unique_ptr<std::atomic<int>[]> arrived(new std::atomic<int>[n_chunks]);
+    for (uint64_t c = 0; c < n_chunks; c++) arrived[c].store(0, std::memory_order_relaxed);
+    std::atomic<uint64_t> released{0};  // chunks whose H2D copy is complete: chunk c may be packed iff c < released + N_STAGE
+    std::atomic<bool> stop{false};
+    auto packer = [&](int t) {
+        for (uint64_t c = 0; c < n_chunks; c++) {
+            while (c >= released.load(std::memory_order_acquire) + (uint64_t)N_STAGE) {
+                if (stop.load(std::memory_order_relaxed)) return;
+                std::this_thread::yield();
+            }
+            const uint64_t c0 = c * chunk, cnt = std::min(chunk, n - c0);
+            // slices start at multiples of four rows: 16-byte aligned in the staging slot (non-temporal stores)
+            const uint64_t lo = (cnt * (uint64_t)t / (uint64_t)T) & ~3ull;
+            const uint64_t hi = t + 1 == T ? cnt : ((cnt * (uint64_t)(t + 1) / (uint64_t)T) & ~3ull);
+            if (hi > lo)
+                fq::pack_stream(rows + (c0 + lo) * L, (hi - lo) * L, m->h_stage[c % N_STAGE] + lo * row_bytes, lut.data());
+            arrived[c].fetch_add(1, std::memory_order_release);
+        }
+    };
+    std::vector<std::thread> pool;
+    pool.reserve((size_t)T);
+    for (int t = 0; t < T; t++) pool.emplace_back(packer, t);
+    struct Joiner {  // every exit path: stop the packers, then wait for them
+        std::vector<std::thread>& pool;
+        std::atomic<bool>& stop;
+        ~Joiner() {
+            stop.store(true);
+            for (auto& th : pool) th.join();
+        }
+    } joiner{pool, stop};
+
+    uint64_t submitted = 0;
+    auto poll = [&]() {  // staging slots whose copy has completed
+        uint64_t r = released.load(std::memory_order_relaxed);
+        while (r < submitted && cudaEventQuery(m->stage_ev[r % N_STAGE]) == cudaSuccess) r++;
+        released.store(r, std::memory_order_release);
+    };
+    for (uint64_t c = 0; c < n_chunks; c++) {
+        while (arrived[c].load(std::memory_order_acquire) < T) {
+            poll();
+            std::this_thread::yield();
+        }
+        const uint64_t c0 = c * chunk, cnt = std::min(chunk, n - c0);
+        const int slot = (int)(c % N_PIPE);
+        cudaStream_t st = m->streams[slot];
+        uint32_t* d_words = reinterpret_cast<uint32_t*>(m->d_in[slot]);
+        CU(cudaMemcpyAsync(d_words, m->h_stage[c % N_STAGE], (size_t)(cnt * row_bytes), cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(m->stage_ev[c % N_STAGE], st));
+        submitted = c + 1;
+        fq::ReadSource src{d_words, nullptr, nullptr, 0, cnt};
+        rc = run_device(m, src, m->d_out[slot], st, slot);
+        if (rc != FQTK_B200_OK) return rc;
+        CU(cudaMemcpyAsync(results + c0, m->d_out[slot], cnt * 4, cudaMemcpyDeviceToHost, st));
+        poll();
+    }
+    for (int s = 0; s < N_PIPE; s++) CU(cudaStreamSynchronize(m->streams[s]));
+    return FQTK_B200_OK;
+}
+
 // The host-buffer calls are synchronous: on EVERY exit path (errors included) the pipeline streams are drained, so no
 // DMA is still reading the caller's rows or writing the caller's results when the call returns.
 struct PipelineDrain {
@@ -1044,6 +1151,10 @@ void fqtk_b200_matcher_destroy(fqtk_b200_matcher* m) {
         if (q) cudaFree(q);
     if (m->d_fq_len) cudaFree(m->d_fq_len);
     if (m->d_route_ws) cudaFree(m->d_route_ws);
+    for (int k = 0; k < N_STAGE; k++) {
+        if (m->h_stage[k]) cudaFreeHost(m->h_stage[k]);
+        if (m->stage_ev[k]) cudaEventDestroy(m->stage_ev[k]);
+    }
     for (int s = 0; s < N_PIPE; s++)
         if (m->d_seg_packed[s]) cudaFree(m->d_seg_packed[s]);
     if (m->d_planes) cudaFree(m->d_planes);
@@ -1079,6 +1190,18 @@ int fqtk_b200_matcher_get_info(const fqtk_b200_matcher* m, fqtk_b200_matcher_inf
     info->l2_table_entries = m->g4_entries;
     info->l2_table_bytes = (uint64_t)m->params.g4_buckets * 32u;
     info->l2_table_slow_keys = m->g4_slow_keys;
+    return FQTK_B200_OK;
+}
+
+int fqtk_b200_matcher_set_host_pack(fqtk_b200_matcher* m, int threads) {
+    if (!m) return fail(FQTK_B200_ERR_ARG, "NULL matcher");
+    if (threads < 0) {  // auto: the CPUs this thread may run on, at most 16
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        threads = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+        threads = std::max(1, std::min(threads, 16));
+    }
+    m->host_pack_threads = std::min(threads, 64);
     return FQTK_B200_OK;
 }
 
@@ -1165,6 +1288,9 @@ int fqtk_b200_matcher_assign_batch(fqtk_b200_matcher* m, const uint8_t* rows, ui
     }
     CU(cudaSetDevice(m->device));
     PipelineDrain drain{m};
+    if (m->host_pack_threads > 0 && !lengths && stride == L && (L % 8u) == 0u && m->W <= (uint32_t)fq::MAX_FAST_WORDS &&
+        n >= (1u << 20) && fq::have_avx2())
+        return assign_batch_host_pack(m, rows, n, results, m->host_pack_threads);
     uint64_t chunk = m->opt.chunk_bytes / std::max<uint64_t>(stride, 1);
     chunk = std::max<uint64_t>(chunk, 1024);
     chunk = std::min<uint64_t>(chunk, n);

@@ -307,7 +307,8 @@ int fqtk_b200_pack_host(const uint8_t* rows, uint64_t n, uint32_t L, uint64_t st
         return FQTK_B200_OK;
     }
     std::vector<std::thread> pool;
-    for (int t = 0; t < T; t++) pool.emplace_back(work, n * t / T, n * (t + 1) / T);
+    for (int t = 0; t < T; t++)  // (ranges start at multiples of four rows: 16-byte aligned words for host_pack.cpp)
+        pool.emplace_back(work, (n * t / T) & ~3ull, t + 1 == T ? n : ((n * (t + 1) / T) & ~3ull));
     for (auto& t : pool) t.join();
     return FQTK_B200_OK;
 }

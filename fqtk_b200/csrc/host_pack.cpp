@@ -36,6 +36,9 @@ __attribute__((target("avx2"))) void pack_stream_avx2(const uint8_t* in, uint64_
     const __m256i letter_of = _mm256_broadcastsi128_si256(
         _mm_setr_epi8(-1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, 'N', -1));
     const __m256i weights = _mm256_set1_epi16(0x1001);  // even byte x 1 + odd byte x 16
+    // the words are read next by a DMA engine, not by this core: when the destination is 16-byte aligned they are written
+    // with non-temporal stores (no read-for-ownership of the destination lines: a third less host memory traffic per read)
+    const bool nt = (reinterpret_cast<uintptr_t>(out) & 15u) == 0u;
     uint64_t i = 0;
     for (; i + 32 <= n_bytes; i += 32) {
         const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(in + i));
@@ -50,8 +53,12 @@ __attribute__((target("avx2"))) void pack_stream_avx2(const uint8_t* in, uint64_
         const __m256i pairs = _mm256_maddubs_epi16(mask, weights);           // 16 x (lo | hi << 4) in 16-bit lanes
         const __m256i bytes = _mm256_packus_epi16(pairs, pairs);             // per 128-bit lane: its 8 bytes, twice
         const __m128i both = _mm256_castsi256_si128(_mm256_permute4x64_epi64(bytes, 0x08));  // lane 0's, then lane 1's
-        _mm_storeu_si128(reinterpret_cast<__m128i*>(out + (i >> 1)), both);
+        if (nt)
+            _mm_stream_si128(reinterpret_cast<__m128i*>(out + (i >> 1)), both);
+        else
+            _mm_storeu_si128(reinterpret_cast<__m128i*>(out + (i >> 1)), both);
     }
+    if (nt) _mm_sfence();
     pack_scalar(in + i, n_bytes - i, out + (i >> 1), lut);
 }
 #endif

@@ -313,6 +313,13 @@ FQTK_B200_API int fqtk_b200_copy_ceiling(int device, uint64_t in_bytes, uint64_t
 
 /* ---- control / introspection ---- */
 FQTK_B200_API int fqtk_b200_matcher_set_mode(fqtk_b200_matcher* m, int mode); /* TABLE needs a built table */
+/* Opt-in for fqtk_b200_matcher_assign_batch: let `threads` host threads (-1 = the CPUs the caller may run on, at most 16;
+ * 0 = off, the default) do encode() (mod.rs:49-61) while the batch is in flight, so that the reference's BitEnc words —
+ * half the bytes of the ASCII rows — cross PCIe.  Taken when the rows lie back to back (row_stride == barcode_len), the
+ * barcode length is a multiple of 8, no per-row lengths are given and the batch has >= 2^20 reads; results are the plain
+ * route's.  Worth it when the call is PCIe-bound and host cores are idle (one GPU per 8+ cores); it costs host memory
+ * bandwidth (the rows are read and the words written once more), so not when many GPUs share one host's memory system. */
+FQTK_B200_API int fqtk_b200_matcher_set_host_pack(fqtk_b200_matcher* m, int threads);
 FQTK_B200_API uint64_t fqtk_b200_kernel_launches(void); /* kernels launched by this library in this process */
 FQTK_B200_API const char* fqtk_b200_last_error(void);
 FQTK_B200_API int fqtk_b200_device_count(void);

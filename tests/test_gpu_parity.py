@@ -410,6 +410,42 @@ def test_brute_sliced_ties_across_groups_and_chunk_launches(L, S):
         check_against_oracle(bcs, mm, delta, reads, use_cache=False, expect_mode="brute")
 
 
+@pytest.mark.parametrize("cfg_id,L", [(3, 16), (2, 8), (None, 24)])
+def test_host_pack_route_of_assign_batch_equals_the_plain_route(cfg_id, L):
+    """fqtk_b200_matcher_set_host_pack: encode() done by host threads while the batch is in flight (AVX2 stream form, pinned
+    staging ring, packed words over PCIe).  Same result words and counts as the plain ASCII route and as the oracle, for
+    1 / 3 / 5 packer threads, sizes with chunk tails, reads with no-calls, lower case, IUPAC codes and arbitrary bytes."""
+    rng = np.random.default_rng(40 + L)
+    if cfg_id is None:
+        panel = synth.make_panel(5, 200, L, 3)
+        mm, delta = 1, 2
+    else:
+        cfg = synth.CONFIGS[cfg_id]
+        panel, mm, delta = synth.panel(cfg), cfg.max_mismatches, cfg.min_mismatch_delta
+    bcs = [bytes(r) for r in panel]
+    n = (3 << 20) + 4099
+    reads = panel[rng.integers(0, len(bcs), size=n)].copy()
+    sub = rng.random(size=reads.shape) < 0.01
+    reads[sub] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=int(sub.sum()))]
+    reads[rng.random(size=reads.shape) < 0.003] = ord("N")
+    reads[5::97, 1] = np.frombuffer(b"acgtnRYK.", dtype=np.uint8)[rng.integers(0, 9, size=len(reads[5::97]))]
+    reads[11::4001, L - 1] = rng.integers(0, 256, size=len(reads[11::4001]), dtype=np.uint8)
+    with BarcodeMatcher(bcs, mm, delta, True) as m:
+        want = m.assign_batch(reads)
+        want_counts = m.counts()
+        win = slice(1_000_000, 1_020_000)
+        ow, _ = oracle.OracleMatcher(bcs, mm, delta, use_cache=True).assign_batch(reads[win], mode=0)
+        assert np.array_equal(want[win], ow)
+        for threads, nn in [(1, n), (3, n), (5, (1 << 20) + 3), (-1, n)]:
+            m.reset_counts()
+            m.set_host_pack(threads)
+            got = m.assign_batch(reads[:nn])
+            m.set_host_pack(0)
+            assert np.array_equal(got, want[:nn]), (threads, nn)
+            if nn == n:
+                assert np.array_equal(m.counts(), want_counts)
+
+
 def test_table_budget_falls_back_to_brute():
     L = _lib.lib()
     try:
