@@ -483,6 +483,20 @@ def config_entry(m, steps, scaling):
     }
 
 
+def host_pack_h2d_bytes(ne, L, W):
+    """Bytes one rank's host-pack call moves host -> device: the library's own chunking rule (capi.cu
+    assign_batch_host_pack): `mix` of every 8 chunks go as ASCII rows, the others as packed words."""
+    mix = min(7, max(0, int(os.environ.get("FQTK_B200_HOST_PACK_MIX", "3"))))
+    chunk_bytes = int(os.environ.get("FQTK_B200_CHUNK_MB", "0")) << 20 or (32 << 20)
+    row = W * 4
+    chunk = min(max(chunk_bytes // (4 * row), 65536) & ~3, ne)
+    total = 0
+    for c in range((ne + chunk - 1) // chunk):
+        cnt = min(chunk, ne - c * chunk)
+        total += cnt * (L if (c * mix) % 8 + mix >= 8 else row)
+    return total
+
+
 def measure_e2e(ctx, args, cfg, panel, matcher, d_packed, d_res, first, n):
     """The same metric through the reference-facing C-ABI calls on pinned HOST buffers, copies inside the timed region
     (wall clock around the synchronous calls, max over ranks), for both wire formats:
@@ -566,7 +580,8 @@ def measure_e2e(ctx, args, cfg, panel, matcher, d_packed, d_res, first, n):
     assert np.array_equal(h_pk_np[:chk], synth.pack_host(h_in_np[:chk])), "host pack differs from encode()"
     ceil_ascii = ceiling(ne * L, ne * 4)
     ceil_packed = ceiling(ne * W * 4, ne * 2)
-    ceil_hp = ceiling(ne * W * 4, ne * 4) if dt_hp is not None else None
+    hp_in = host_pack_h2d_bytes(ne, L, W)
+    ceil_hp = ceiling(hp_in, ne * 4) if dt_hp is not None else None
 
     def mreads(sec):
         return round(ne * world / sec / 1e6, 2)
@@ -590,13 +605,14 @@ def measure_e2e(ctx, args, cfg, panel, matcher, d_packed, d_res, first, n):
         },
     }
     if dt_hp is not None:
-        hp = {"value": mreads(dt_hp), "unit": UNIT, "h2d_bytes_per_step": ne * W * 4 * world, "d2h_bytes_per_step": ne * 4 * world,
+        hp = {"value": mreads(dt_hp), "unit": UNIT, "h2d_bytes_per_step": hp_in * world, "d2h_bytes_per_step": ne * 4 * world,
               "ms_per_step": round(dt_hp * 1e3, 3), "host_threads_per_rank": hp_threads,
               "api": "fqtk_b200_matcher_assign_batch after fqtk_b200_matcher_set_host_pack: the same ASCII rows in pinned host "
                      "memory -> result words in pinned host memory; encode() by host threads (AVX2) inside the call, inside the "
-                     "timed region, the reference's BitEnc words cross PCIe",
+                     "timed region: 5 of every 8 chunks cross PCIe as the reference's BitEnc words, 3 as ASCII rows (encode() "
+                     "in the kernel) so that host memory and PCIe are both loaded",
               "ceiling": mreads(ceil_hp), "frac_of_ceiling": round(ceil_hp / dt_hp, 4),
-              "h2d_gb_per_s_per_gpu": round(ne * W * 4 / dt_hp / 1e9, 2)}
+              "h2d_gb_per_s_per_gpu": round(hp_in / dt_hp / 1e9, 2)}
         plain = {k: out[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "ms_per_step", "api", "ceiling",
                                      "frac_of_ceiling", "h2d_gb_per_s_per_gpu")}
         if dt_hp < dt_ascii:  # the faster form of the SAME call (ASCII rows in, result words out) is the headline

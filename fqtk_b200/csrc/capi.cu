@@ -839,6 +839,16 @@ int run_device(fqtk_b200_matcher* m, const fq::ReadSource& src, uint32_t* d_resu
 // the duration of the call; each packs its slice of every chunk into a ring of N_STAGE pinned staging slots, the calling
 // thread sends a chunk on as soon as all slices are in (H2D -> kernel -> D2H on the pipeline streams) and frees a slot
 // when the event behind its copy has fired.  No locks: per-chunk arrival counters and one `released` counter.
+// Packing costs host memory traffic (rows read, words written, words read by the DMA engine: 36 bytes per read at L = 16
+// against 20 for the plain route) and leaves PCIe half idle, so `mix` of every 8 chunks go the plain way — ASCII rows
+// straight over PCIe, encode() in the kernel — to load both at once (FQTK_B200_HOST_PACK_MIX, 0 .. 7).
+int host_pack_mix() {
+    static const int v = [] {
+        const int e = env_int("FQTK_B200_HOST_PACK_MIX", 3);
+        return e < 0 ? 0 : (e > 7 ? 7 : e);
+    }();
+    return v;
+}
 int assign_batch_host_pack(fqtk_b200_matcher* m, const uint8_t* rows, uint64_t n, uint32_t* results, int T) {
     static const std::vector<uint8_t> lut = [] {
         std::vector<uint8_t> t(256);
@@ -850,7 +860,9 @@ int assign_batch_host_pack(fqtk_b200_matcher* m, const uint8_t* rows, uint64_t n
     uint64_t chunk = std::max<uint64_t>(m->opt.chunk_bytes / (4u * row_bytes), 65536) & ~3ull;  // finer than the plain
     chunk = std::min<uint64_t>(chunk, n);                                                       // route: pack || copy
     const uint64_t n_chunks = (n + chunk - 1) / chunk;
-    int rc = ensure_pipeline(m, (size_t)(chunk * row_bytes + 16), (size_t)chunk, false);
+    const int mix = host_pack_mix();
+    auto plain = [mix](uint64_t c) { return (int)((c * (uint64_t)mix) % 8u) + mix >= 8; };  // `mix` of every 8 chunks, spread out
+    int rc = ensure_pipeline(m, (size_t)(chunk * (mix ? (uint64_t)L : row_bytes) + 16), (size_t)chunk, false);
     if (rc != FQTK_B200_OK) return rc;
     if (chunk * row_bytes > m->stage_cap) {
         for (int k = 0; k < N_STAGE; k++) {
@@ -865,11 +877,12 @@ int assign_batch_host_pack(fqtk_b200_matcher* m, const uint8_t* rows, uint64_t n
         if (!m->stage_ev[k]) CU(cudaEventCreateWithFlags(&m->stage_ev[k], cudaEventDisableTiming));
 
     std::unique_ptr<std::atomic<int>[]> arrived(new std::atomic<int>[n_chunks]);
-    for (uint64_t c = 0; c < n_chunks; c++) arrived[c].store(0, std::memory_order_relaxed);
+    for (uint64_t c = 0; c < n_chunks; c++) arrived[c].store(plain(c) ? T : 0, std::memory_order_relaxed);
     std::atomic<uint64_t> released{0};  // chunks whose H2D copy is complete: chunk c may be packed iff c < released + N_STAGE
     std::atomic<bool> stop{false};
     auto packer = [&](int t) {
         for (uint64_t c = 0; c < n_chunks; c++) {
+            if (plain(c)) continue;
             while (c >= released.load(std::memory_order_acquire) + (uint64_t)N_STAGE) {
                 if (stop.load(std::memory_order_relaxed)) return;
                 std::this_thread::yield();
@@ -910,10 +923,15 @@ int assign_batch_host_pack(fqtk_b200_matcher* m, const uint8_t* rows, uint64_t n
         const int slot = (int)(c % N_PIPE);
         cudaStream_t st = m->streams[slot];
         uint32_t* d_words = reinterpret_cast<uint32_t*>(m->d_in[slot]);
-        CU(cudaMemcpyAsync(d_words, m->h_stage[c % N_STAGE], (size_t)(cnt * row_bytes), cudaMemcpyHostToDevice, st));
+        fq::ReadSource src{d_words, nullptr, nullptr, 0, cnt};
+        if (plain(c)) {  // (its staging slot is not used: the event marks it free at once)
+            CU(cudaMemcpyAsync(m->d_in[slot], rows + c0 * L, (size_t)(cnt * L), cudaMemcpyHostToDevice, st));
+            src = fq::ReadSource{nullptr, m->d_in[slot], nullptr, L, cnt};
+        } else {
+            CU(cudaMemcpyAsync(d_words, m->h_stage[c % N_STAGE], (size_t)(cnt * row_bytes), cudaMemcpyHostToDevice, st));
+        }
         CU(cudaEventRecord(m->stage_ev[c % N_STAGE], st));
         submitted = c + 1;
-        fq::ReadSource src{d_words, nullptr, nullptr, 0, cnt};
         rc = run_device(m, src, m->d_out[slot], st, slot);
         if (rc != FQTK_B200_OK) return rc;
         CU(cudaMemcpyAsync(results + c0, m->d_out[slot], cnt * 4, cudaMemcpyDeviceToHost, st));
