@@ -95,6 +95,9 @@ class BarcodeMatcher {
         return c;
     }
     void reset_counts() { check(fqtk_b200_matcher_reset_counts(h_)); }
+    // assign_batch with encode() done by `threads` host threads while the batch is in flight (-1 = auto, 0 = off): most
+    // chunks cross PCIe as BitEnc words instead of ASCII rows; same results (fqtk_b200_matcher_set_host_pack)
+    void set_host_pack(int threads) { check(fqtk_b200_matcher_set_host_pack(h_, threads)); }
     // stable partition of read indices by assignment (the batch form of demux.rs:970-975): order[offsets[s] ..
     // offsets[s + 1]) = the reads of sample s in input order, s = n_samples = unmatched; offsets has n_samples + 2 entries
     void route(const std::uint32_t* results, std::uint64_t n, std::vector<std::uint32_t>& order,
