@@ -898,7 +898,6 @@ int assign_batch_host_pack(fqtk_b200_matcher* m, const uint8_t* rows, uint64_t n
     };
     std::vector<std::thread> pool;
     pool.reserve((size_t)T);
-    for (int t = 0; t < T; t++) pool.emplace_back(packer, t);
     struct Joiner {  // every exit path: stop the packers, then wait for them
         std::vector<std::thread>& pool;
         std::atomic<bool>& stop;
@@ -907,6 +906,11 @@ int assign_batch_host_pack(fqtk_b200_matcher* m, const uint8_t* rows, uint64_t n
             for (auto& th : pool) th.join();
         }
     } joiner{pool, stop};
+    try {
+        for (int t = 0; t < T; t++) pool.emplace_back(packer, t);
+    } catch (const std::exception& e) {  // (nothing may unwind across the C boundary)
+        return fail(FQTK_B200_ERR_ARG, std::string("host-pack route: cannot start ") + std::to_string(T) + " threads: " + e.what());
+    }
 
     uint64_t submitted = 0;
     auto poll = [&]() {  // staging slots whose copy has completed
