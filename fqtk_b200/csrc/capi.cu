@@ -1691,7 +1691,8 @@ int fqtk_b200_fastq_scan_device(int device, const uint8_t* d_chunk, uint64_t chu
 // read must hold ALL segments of its read structure, demux.rs:298-315, not only the B ones).
 static int ingest_chunks_impl(fqtk_b200_matcher* m, const fqtk_b200_fastq_chunk* chunks, uint32_t n_sources,
                               const fqtk_b200_fastq_segment* segs, uint32_t n_segs, uint64_t max_reads, uint32_t* results,
-                              uint64_t* n_reads, uint64_t* consumed, const uint32_t* min_len, fqtk_b200_fastq_source* dev_out) {
+                              uint64_t* n_reads, uint64_t* consumed, const uint32_t* min_len, fqtk_b200_fastq_source* dev_out,
+                              const std::string* rs_text = nullptr) {  // rs_text[s]: read structure of input s as the reference prints it
     const bool want_heads = min_len != nullptr;
     if (!m || !chunks || !segs || !n_reads || !consumed || n_sources == 0 || n_sources > FQTK_B200_MAX_SEGMENTS || n_segs == 0 ||
         n_segs > FQTK_B200_MAX_SEGMENTS)
@@ -1791,7 +1792,7 @@ static int ingest_chunks_impl(fqtk_b200_matcher* m, const fqtk_b200_fastq_chunk*
         if (err_scan[s] != ~0ull)
             return fail(FQTK_B200_ERR_ARG, "FASTQ record " + std::to_string(err_scan[s] >> 2) + " of input " + std::to_string(s) + ": " +
                                                SCAN_ERR[err_scan[s] & 3u]);
-    if (want_heads) {  // ReadSetIterator::next: "Read {name} had too few bases to demux {len} vs. {min} needed in read structure."
+    if (want_heads) {  // ReadSetIterator::next: "Read {name} had too few bases to demux {len} vs. {min} needed in read structure {rs}."
         unsigned long long first = ~0ull;
         for (uint32_t s = 0; s < n_sources; s++) first = std::min(first, err_min[s]);
         if (first != ~0ull && first <= std::min(err_vet[0], err_vet[1])) {
@@ -1805,7 +1806,8 @@ static int ingest_chunks_impl(fqtk_b200_matcher* m, const fqtk_b200_fastq_chunk*
                 std::string name(reinterpret_cast<const char*>(chunks[0].data + h0 + 1), (size_t)(s0 - h0 - 2));
                 if (!name.empty() && name.back() == '\r') name.pop_back();
                 return fail(FQTK_B200_ERR_ARG, "Read " + name + " had too few bases to demux " + std::to_string(len) + " vs. " +
-                                                   std::to_string(min_len[s]) + " needed in read structure.");
+                                                   std::to_string(min_len[s]) + " needed in read structure" +
+                                                   (rs_text ? " " + rs_text[s] : std::string()) + ".");
             }
         }
     }
@@ -1912,7 +1914,12 @@ int fqtk_b200_demux_chunks(fqtk_b200_matcher* m, fqtk_b200_bgzf* z, const fqtk_b
     };
     fqtk_b200_fastq_source dev[FQTK_B200_MAX_SEGMENTS];
     uint64_t n = 0;
-    rc = ingest_chunks_impl(m, chunks, n_sources, bsegs, nb, max_reads, nullptr, &n, consumed, min_len, dev);
+    // the read structures as the reference prints them (`{length}{kind}`, `+{kind}` for the rest), for its panic text
+    std::string rs_text[FQTK_B200_MAX_SEGMENTS];
+    for (uint32_t k = 0; k < n_segments; k++)
+        rs_text[segments[k].source] += (segments[k].length == FQTK_B200_SEGMENT_REST ? std::string("+") : std::to_string(segments[k].length)) +
+                                       std::string(1, (char)segments[k].kind);
+    rc = ingest_chunks_impl(m, chunks, n_sources, bsegs, nb, max_reads, nullptr, &n, consumed, min_len, dev, rs_text);
     if (rc != FQTK_B200_OK || n == 0) return rc;
     lap("H2D + scan + vet + match");
     CU(cudaSetDevice(m->device));

@@ -60,6 +60,17 @@ def min_length(structure: Sequence[tuple[str, int | None]]) -> int:
     return sum(n if n is not None else 1 for _, n in structure)  # demux.rs:298
 
 
+def structure_text(structure: Sequence[tuple[str, int | None]]) -> str:
+    """The read structure as the reference prints it (`{}` of read_structure::ReadStructure): `8B`, `+T`, `10M8B7C100T`."""
+    return "".join(("+" if n is None else str(n)) + kind for kind, n in structure)
+
+
+def too_few_bases_text(name: str, have: int, structure) -> str:
+    """The reference's panic text (demux.rs:307-313)."""
+    return (f"Read {name} had too few bases to demux {have} vs. {min_length(structure)} needed in read structure "
+            f"{structure_text(structure)}.")
+
+
 def extract_segments(structure, seq: bytes, qual: bytes) -> list[tuple[str, bytes, bytes]]:
     """ReadSegment::extract_bases_and_quals for every segment (fixed ones by offset, `+` = the rest)."""
     out, pos = [], 0
@@ -96,8 +107,7 @@ def demux_batch(matcher, sample_ids: Sequence[str], barcodes: Sequence[str], rea
             head, seq, qual = recs[i]
             if len(seq) < min_length(st):
                 if not skip_too_few_bases:
-                    raise TooFewBases(f"Read {head.decode(errors='replace')} had too few bases to demux "
-                                      f"{len(seq)} vs. {min_length(st)} needed in read structure.")
+                    raise TooFewBases(too_few_bases_text(head.decode(errors="replace"), len(seq), st))
                 skip = True
                 break
             segments.extend(extract_segments(st, seq, qual))

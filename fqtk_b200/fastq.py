@@ -18,7 +18,8 @@ from typing import Sequence
 import numpy as np
 
 from . import _lib
-from .demux import (FILE_TYPE_CODE, OUTPUT_ORDER, DemuxResult, TooFewBases, min_length, parse_read_structure)
+from .demux import (FILE_TYPE_CODE, OUTPUT_ORDER, DemuxResult, TooFewBases, min_length, parse_read_structure,
+                    too_few_bases_text)
 from .headers import write_header
 from .metrics import demux_metrics
 
@@ -155,8 +156,7 @@ def demux_fastq_batch(matcher, sample_ids: Sequence[str], barcodes: Sequence[str
         if not skip_too_few_bases:
             i = int(np.nonzero(~keep)[0][0])
             st, ix = next((st, ix) for st, ix in zip(structures, idx) if ix.seq_lengths[i] < min_length(st))
-            raise TooFewBases(f"Read {idx[0].header(i).decode(errors='replace')} had too few bases to demux "
-                              f"{int(ix.seq_lengths[i])} vs. {min_length(st)} needed in read structure.")
+            raise TooFewBases(too_few_bases_text(idx[0].header(i).decode(errors="replace"), int(ix.seq_lengths[i]), st))
         rows = np.nonzero(keep)[0]
         idx = [FastqIndex(ix.chunk, ix.head_offsets[rows].copy(), ix.seq_offsets[rows].copy(), ix.seq_lengths[rows].copy(),
                           ix.consumed) for ix in idx]

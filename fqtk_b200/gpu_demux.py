@@ -23,7 +23,7 @@ import numpy as np
 
 from . import _lib
 from .bgzf import BGZF_EOF
-from .demux import FILE_TYPE_CODE, TooFewBases, min_length, parse_read_structure
+from .demux import FILE_TYPE_CODE, TooFewBases, min_length, parse_read_structure, too_few_bases_text
 from .metrics import DemuxMetric, demux_metrics
 
 
@@ -120,7 +120,7 @@ def demux_fastq_batch_gpu(matcher, compressor, sample_ids: Sequence[str], barcod
             st, t = next((st, t) for st, t in zip(structures, tables) if int(t[2][i].item()) < min_length(st))
             h0, s0 = int(tables[0][0][i].item()), int(tables[0][1][i].item())
             name = bytes(fastq_texts[0][h0 + 1:s0 - 1]).rstrip(b"\r").decode(errors="replace")
-            raise TooFewBases(f"Read {name} had too few bases to demux {int(t[2][i].item())} vs. {min_length(st)} needed in read structure.")
+            raise TooFewBases(too_few_bases_text(name, int(t[2][i].item()), st))
         tables = [[x[keep].contiguous() for x in t] for t in tables]
         n = int(tables[0][0].shape[0])
     res = GpuDemuxResult(skipped=skipped)

@@ -292,6 +292,22 @@ def test_batched_pipeline_host_logic_with_the_oracle_as_matcher(kats):
             assert [r.templates for r in out.metrics] == case["expect_counts"]
 
 
+def test_too_few_bases_panic_text_is_the_reference_text(kats):
+    """demux.rs:1983-2020: a read shorter than its read structure needs panics with the read's name, both lengths AND the
+    read structure as the reference prints it (demux.rs:307-313)."""
+    from fqtk_b200.demux import TooFewBases, demux_batch, parse_read_structure, structure_text
+
+    for text in ("+T", "7B", "10M8B7C100T", "4B4M8S", "17B20T20S20T20S20T", "6M+T"):
+        assert structure_text(parse_read_structure(text)) == text
+    for case in kats["demux_panics"]:
+        ids = [f"Sample{j:04d}" for j in range(len(case["barcodes"]))]
+        inputs = [[(f"ex_{i}".encode(), b.encode(), b";" * len(b)) for i, b in enumerate(col)] for col in case["inputs"]]
+        m = _OracleBackedMatcher(case["barcodes"], case["max_mismatches"], case["min_mismatch_delta"])
+        with pytest.raises(TooFewBases) as e:
+            demux_batch(m, ids, case["barcodes"], case["read_structures"], inputs, case["output_types"])
+        assert str(e.value) == case["expect_panic"], case["source"]
+
+
 def test_pack_host_is_encode_for_every_row():
     """fqtk_b200_pack_host (two symbols per table lookup, several host threads) == encode() (mod.rs:49-61) of every row:
     checked against the numpy restatement and, per row, against the oracle's encode; all 256 byte values, odd and even L,
